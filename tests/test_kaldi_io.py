@@ -1,0 +1,147 @@
+"""Kaldi ark I/O against fixtures produced by the reference's own kaldi_io (tests/golden)."""
+import io
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from xvector_b200 import kaldi_io
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+EXPECTED = np.load(os.path.join(GOLD, "expected.npz"))
+
+
+def _expected(fname):
+    pre = fname + "/"
+    return {k[len(pre):]: EXPECTED[k] for k in EXPECTED.files if k.startswith(pre)}
+
+
+@pytest.mark.parametrize("fname", ["mat_f32.ark", "mat_f64.ark"])
+def test_read_mat_ark_matches_reference_writer(fname):
+    want = _expected(fname)
+    got = list(kaldi_io.read_mat_ark(os.path.join(GOLD, fname)))
+    assert [k for k, _ in got] == list(want.keys())          # order preserved, incl. the 0-row entry
+    for k, m in got:
+        assert m.dtype == want[k].dtype and m.shape == want[k].shape
+        assert np.array_equal(m, want[k])
+
+
+@pytest.mark.parametrize("fname", ["vec_f32.ark", "vec_f64.ark"])
+def test_read_vec_ark_matches_reference_writer(fname):
+    want = _expected(fname)
+    got = dict(kaldi_io.read_vec_flt_ark(os.path.join(GOLD, fname)))
+    assert list(got) == list(want)
+    for k in want:
+        assert got[k].dtype == want[k].dtype and np.array_equal(got[k], want[k])
+
+
+@pytest.mark.parametrize("fname,writer", [("mat_f32.ark", "mat"), ("mat_f64.ark", "mat"),
+                                          ("vec_f32.ark", "vec"), ("vec_f64.ark", "vec")])
+def test_writers_are_byte_identical_to_reference(fname, writer):
+    want = _expected(fname)
+    buf = io.BytesIO()
+    buf.mode = "wb"
+    for k, a in want.items():
+        (kaldi_io.write_mat if writer == "mat" else kaldi_io.write_vec_flt)(buf, a, key=k)
+    with open(os.path.join(GOLD, fname), "rb") as f:
+        assert buf.getvalue() == f.read()
+
+
+def test_vec_entry_bytes_helper_matches_writer():
+    v = np.arange(5, dtype=np.float32)
+    buf = io.BytesIO()
+    buf.mode = "wb"
+    kaldi_io.write_vec_flt(buf, v, key="k1")
+    assert kaldi_io.vec_flt_entry_bytes(v, "k1") == buf.getvalue()
+
+
+def test_compressed_matrix_decodes_like_reference():
+    got = dict(kaldi_io.read_mat_ark(os.path.join(GOLD, "cm.ark")))
+    want = np.load(os.path.join(GOLD, "cm_expected.npy"))
+    assert got["cm_utt"].dtype == np.float32 and got["cm_utt"].shape == want.shape
+    assert np.array_equal(got["cm_utt"], want)
+
+
+def test_text_matrix_parses_like_reference():
+    got = dict(kaldi_io.read_mat_ark(os.path.join(GOLD, "text.ark")))
+    assert np.array_equal(got["t1"], np.load(os.path.join(GOLD, "text_expected.npy")))
+
+
+def test_hand_assembled_entry_layout():
+    # key ' ' \0B FM ' ' \4 rows \4 cols payload
+    m = np.arange(6, dtype=np.float32).reshape(2, 3)
+    blob = b"k-1 \0BFM \4" + struct.pack("<i", 2) + b"\4" + struct.pack("<i", 3) + m.tobytes()
+    (key, got), = list(kaldi_io.read_mat_ark(io.BytesIO(blob)))
+    assert key == "k-1" and np.array_equal(got, m)
+    v = np.array([1.5, -2.0], np.float32)
+    out = io.BytesIO()
+    out.mode = "wb"
+    kaldi_io.write_vec_flt(out, v, key="k-1")
+    assert out.getvalue() == b"k-1 \0BFV \4" + struct.pack("<I", 2) + v.tobytes()
+
+
+def test_key_format_is_enforced_and_eof_is_none():
+    assert kaldi_io.read_key(io.BytesIO(b"")) is None
+    with pytest.raises(AssertionError):
+        kaldi_io.read_key(io.BytesIO(b"bad$key \0B"))
+    # unbuffered stream without peek(): same result as the buffered fast path
+    class Raw(io.RawIOBase):
+        def __init__(self, b): self.b, self.i = b, 0
+        def readable(self): return True
+        def readinto(self, out):
+            n = min(len(out), len(self.b) - self.i)
+            out[:n] = self.b[self.i:self.i + n]; self.i += n
+            return n
+    r = Raw(b"utt1 rest")
+    assert kaldi_io.read_key(r) == "utt1" and r.read(4) == b"rest"
+    b = io.BufferedReader(Raw(b"utt1 rest"))
+    assert kaldi_io.read_key(b) == "utt1" and b.read(4) == b"rest"
+
+
+def test_unknown_headers_and_dtypes_raise():
+    with pytest.raises(kaldi_io.UnknownMatrixHeader):
+        list(kaldi_io.read_mat_ark(io.BytesIO(b"k \0BXM \4")))
+    with pytest.raises(kaldi_io.UnknownVectorHeader):
+        list(kaldi_io.read_vec_flt_ark(io.BytesIO(b"k \0BXV \4")))
+    out = io.BytesIO()
+    out.mode = "wb"
+    with pytest.raises(kaldi_io.UnsupportedDataType):
+        kaldi_io.write_vec_flt(out, np.zeros(3, np.int32), key="k")
+    with pytest.raises(kaldi_io.UnsupportedDataType):
+        kaldi_io.write_mat(out, np.zeros((2, 2), np.int32), key="k")
+
+
+def test_open_or_fd_prefix_offset_gzip_and_pipes(tmp_path):
+    m = np.arange(12, dtype=np.float32).reshape(3, 4)
+    ark = tmp_path / "a.ark"
+    with open(ark, "wb") as f:
+        f.write(b"junk")
+        off = f.tell() + len(b"u1 ")
+        kaldi_io.write_mat(f, m, key="u1")
+    # ark: prefix stripped; ':offset' seeks to the matrix body (what an scp line points at)
+    assert np.array_equal(kaldi_io.read_mat("ark:%s:%d" % (ark, off)), m)
+    scp = tmp_path / "a.scp"
+    scp.write_text("u1 %s:%d\n" % (ark, off))
+    assert np.array_equal(dict(kaldi_io.read_mat_scp(str(scp)))["u1"], m)
+    # gzip
+    import gzip
+    gz = tmp_path / "b.ark.gz"
+    with gzip.open(gz, "wb") as f:
+        kaldi_io.write_mat(f, m, key="u2")
+    assert np.array_equal(dict(kaldi_io.read_mat_ark(str(gz)))["u2"], m)
+    # input pipe / output pipe
+    with open(tmp_path / "c.ark", "wb") as f:
+        kaldi_io.write_mat(f, m, key="u3")
+    got = dict(kaldi_io.read_mat_ark("ark:cat %s |" % (tmp_path / "c.ark")))
+    assert np.array_equal(got["u3"], m)
+    out = tmp_path / "d.ark"
+    fd = kaldi_io.open_or_fd("| cat > %s" % out)
+    kaldi_io.write_vec_flt(fd, np.ones(4, np.float32), key="v")
+    fd.close()
+    import time
+    for _ in range(100):
+        if out.exists() and out.stat().st_size > 0:
+            break
+        time.sleep(0.05)
+    assert np.array_equal(dict(kaldi_io.read_vec_flt_ark(str(out)))["v"], np.ones(4, np.float32))

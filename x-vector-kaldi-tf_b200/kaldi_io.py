@@ -1,0 +1,357 @@
+"""Kaldi ark/scp I/O for the x-vector extractor.
+
+Drop-in for the subset of the reference's ``local/tf/kaldi_io.py`` that the extraction hot
+path touches plus the scp / compressed-matrix readers its
+callers rely on.  Same function names, argument meaning and exception types; the byte
+layouts are pinned by fixtures generated with the reference module itself
+(tests/golden/make_golden_ark.py).
+
+Wire formats (little endian, unaligned, entries concatenated):
+
+    matrix : <key> ' ' '\\0B' 'FM ' '\\4' <i32 rows> '\\4' <i32 cols> rows*cols f32 row-major
+             ('DM ' = f64, 'CM ' = Kaldi compressed matrix, ' [' starts the text form)
+             -- reference kaldi_io.py:395-437 (read), :506-542 (write)
+    vector : <key> ' ' '\\0B' 'FV ' '\\4' <u32 dim> dim f32      ('DV ' = f64)
+             -- reference kaldi_io.py:266-305 (read), :309-343 (write)
+    key    : bytes up to the first space, ``^[./a-zA-Z0-9_-]+$``; an empty key means EOF
+             -- reference kaldi_io.py:120-133
+
+Unlike the reference's ``read_key`` (one ``fd.read(1)`` per character) the readers here pull
+whole headers with a single ``read`` where the stream allows ``peek``; the bytes consumed
+from the stream are identical, so mixing calls with other readers stays safe.
+"""
+from __future__ import annotations
+
+import gzip
+import io
+import re
+import struct
+import subprocess
+import sys
+import threading
+
+import numpy as np
+
+_KEY_RE = re.compile(r"^[./a-zA-Z0-9_-]+$")
+_SPECIFIER_RE = re.compile(r"^(ark|scp)(,scp|,b|,t|,n?f|,n?p|,b?o|,n?s|,n?cs)*:")
+_OFFSET_RE = re.compile(r":[0-9]+$")
+
+
+class UnsupportedDataType(Exception):
+    pass
+
+
+class UnknownVectorHeader(Exception):
+    pass
+
+
+class UnknownMatrixHeader(Exception):
+    pass
+
+
+class BadSampleSize(Exception):
+    pass
+
+
+class BadInputFormat(Exception):
+    pass
+
+
+class SubprocessFailed(Exception):
+    pass
+
+
+# --------------------------------------------------------------------------------------
+# opening streams
+
+def popen(cmd, mode="rb"):
+    """Run ``cmd`` through the shell and return the pipe end matching ``mode``.
+
+    A watcher thread raises SubprocessFailed when the child exits non-zero (reference
+    kaldi_io.py:84-117).
+    """
+    if not isinstance(cmd, str):
+        raise TypeError("invalid cmd type (%s, expected string)" % type(cmd))
+    if mode not in ("r", "w", "rb", "wb"):
+        raise ValueError("invalid mode %s" % mode)
+    reading = mode[0] == "r"
+    proc = subprocess.Popen(cmd, shell=True,
+                            stdout=subprocess.PIPE if reading else None,
+                            stdin=None if reading else subprocess.PIPE)
+
+    def watch():
+        ret = proc.wait()
+        if ret > 0:
+            raise SubprocessFailed("cmd %s returned %d !" % (cmd, ret))
+
+    threading.Thread(target=watch, daemon=True).start()
+    pipe = proc.stdout if reading else proc.stdin
+    return pipe if mode.endswith("b") else io.TextIOWrapper(pipe)
+
+
+def open_or_fd(file, mode="rb"):
+    """Open a Kaldi r/w-filename: plain or gzipped file, ``cmd |`` / ``| cmd`` pipe, optional
+    ``ark:``/``scp:`` prefix and ``:offset`` suffix; anything that is not a string is taken
+    to be an already opened stream and returned as is (reference kaldi_io.py:50-80)."""
+    if not isinstance(file, str):
+        return file
+    offset = None
+    if _SPECIFIER_RE.search(file):
+        file = file.split(":", 1)[1]
+    if _OFFSET_RE.search(file):
+        file, offset = file.rsplit(":", 1)
+    if file[-1] == "|":
+        fd = popen(file[:-1], "rb")
+    elif file[0] == "|":
+        fd = popen(file[1:], "wb")
+    elif file.split(".")[-1] == "gz":
+        fd = gzip.open(file, mode)
+    else:
+        fd = open(file, mode)
+    if offset is not None:
+        fd.seek(int(offset))
+    return fd
+
+
+def _read_exact(fd, n):
+    """``fd.read(n)`` that tolerates short reads from pipes."""
+    buf = fd.read(n)
+    if buf is None:
+        buf = b""
+    if len(buf) == n or not buf:
+        return buf
+    parts = [buf]
+    got = len(buf)
+    while got < n:
+        more = fd.read(n - got)
+        if not more:
+            break
+        parts.append(more)
+        got += len(more)
+    return b"".join(parts)
+
+
+def read_key(fd):
+    """Next utterance key from an ark stream, or None at end of stream."""
+    chars = []
+    peek = getattr(fd, "peek", None)
+    while True:
+        if peek is not None:
+            window = peek(64)[:64]
+            if not window:
+                break
+            cut = window.find(b" ")
+            if cut < 0:
+                chars.append(fd.read(len(window)))
+                continue
+            chars.append(fd.read(cut + 1)[:-1])
+            break
+        c = fd.read(1)
+        if c == b"" or c == b" ":
+            break
+        chars.append(c)
+    key = b"".join(chars).decode().strip()
+    if key == "":
+        return None
+    assert _KEY_RE.match(key) is not None, "bad key %r" % key
+    return key
+
+
+def _check_binary_writable(fd):
+    """The reference asserts ``fd.mode == 'wb'`` (kaldi_io.py:326,524); kept for text-mode
+    mistakes, relaxed for streams whose ``mode`` is not a string (gzip) or absent (BytesIO)."""
+    mode = getattr(fd, "mode", "wb")
+    if isinstance(mode, str):
+        assert mode == "wb", "open the output stream in binary mode ('wb'), got %r" % mode
+
+
+# --------------------------------------------------------------------------------------
+# float vectors
+
+def _read_vec_flt_binary(fd):
+    header = _read_exact(fd, 3).decode()
+    if header == "FV ":
+        dtype = np.dtype("<f4")
+    elif header == "DV ":
+        dtype = np.dtype("<f8")
+    else:
+        raise UnknownVectorHeader("The header contained '%s'" % header)
+    assert _read_exact(fd, 1) == b"\4"
+    dim = struct.unpack("<i", _read_exact(fd, 4))[0]
+    return np.frombuffer(_read_exact(fd, dim * dtype.itemsize), dtype=dtype)
+
+
+def read_vec_flt(file_or_fd):
+    """One Kaldi float vector, binary or text."""
+    fd = open_or_fd(file_or_fd)
+    try:
+        flag = _read_exact(fd, 2).decode()
+        if flag == "\0B":
+            return _read_vec_flt_binary(fd)
+        tokens = (flag + fd.readline().decode()).strip().split()
+        tokens = [t for t in tokens if t not in ("[", "]")]
+        return np.array(tokens, dtype=float)
+    finally:
+        if fd is not file_or_fd:
+            fd.close()
+
+
+def read_vec_flt_ark(file_or_fd):
+    """Generator of (key, vector) over a vector ark."""
+    fd = open_or_fd(file_or_fd)
+    try:
+        key = read_key(fd)
+        while key:
+            yield key, read_vec_flt(fd)
+            key = read_key(fd)
+    finally:
+        if fd is not file_or_fd:
+            fd.close()
+
+
+def read_vec_flt_scp(file_or_fd):
+    """Generator of (key, vector) following an scp of ``key rxfilename[:offset]`` lines."""
+    fd = open_or_fd(file_or_fd)
+    try:
+        for line in fd:
+            key, rxfile = line.decode().split(" ")
+            yield key, read_vec_flt(rxfile.strip())
+    finally:
+        if fd is not file_or_fd:
+            fd.close()
+
+
+def write_vec_flt(file_or_fd, v, key=""):
+    """Append one binary vector (float32 -> 'FV ', float64 -> 'DV ')."""
+    fd = open_or_fd(file_or_fd, mode="wb")
+    _check_binary_writable(fd)
+    try:
+        if v.dtype == "float32":
+            tag = b"FV "
+        elif v.dtype == "float64":
+            tag = b"DV "
+        else:
+            raise UnsupportedDataType("'%s', please use 'float32' or 'float64'" % v.dtype)
+        head = (key + " ").encode() if key != "" else b""
+        fd.write(head + b"\0B" + tag + b"\4" + struct.pack("<I", v.shape[0]))
+        fd.write(v.tobytes())
+    finally:
+        if fd is not file_or_fd:
+            fd.close()
+
+
+def vec_flt_entry_bytes(v, key):
+    """The exact bytes ``write_vec_flt`` emits for one float32 entry (used for batched writes)."""
+    return (key + " ").encode() + b"\0BFV \4" + struct.pack("<I", v.shape[0]) + np.ascontiguousarray(v, "<f4").tobytes()
+
+
+# --------------------------------------------------------------------------------------
+# float matrices
+
+def _read_compressed_mat(fd, fmt):
+    """Kaldi CompressedMatrix, format 'CM ' only (reference kaldi_io.py:455-502):
+    16-byte global header {min f32, range f32, rows i32, cols i32}, per column four u16
+    percentiles, then column-major u8 payload; piecewise-linear decode."""
+    assert fmt == "CM "
+    gmin, grange, rows, cols = struct.unpack("<ffii", _read_exact(fd, 16))
+    gmin, grange = np.float32(gmin), np.float32(grange)
+    pct = np.frombuffer(_read_exact(fd, cols * 8), dtype="<u2").reshape(cols, 4)
+    data = np.frombuffer(_read_exact(fd, cols * rows), dtype=np.uint8).reshape(cols, rows)
+    # percentile u16 -> float (kaldi: min + range * 1/65535 * value), float32 like the reference
+    q = (gmin + grange * np.float32(1.52590218966964e-05) * pct.astype(np.float32)).astype(np.float32)
+    p0, p25, p75, p100 = (q[:, i:i + 1].astype(np.float32) for i in range(4))
+    d = data.astype(np.float32)
+    out = np.where(data <= 64, p0 + (p25 - p0) / np.float32(64.0) * d,
+                   np.where(data <= 192, p25 + (p75 - p25) / np.float32(128.0) * (d - np.float32(64.0)),
+                            p75 + (p100 - p75) / np.float32(63.0) * (d - np.float32(192.0))))
+    return out.astype(np.float32).T
+
+
+def _read_mat_binary(fd):
+    header = _read_exact(fd, 3).decode()
+    if header.startswith("CM"):
+        return _read_compressed_mat(fd, header)
+    if header == "FM ":
+        dtype = np.dtype("<f4")
+    elif header == "DM ":
+        dtype = np.dtype("<f8")
+    else:
+        raise UnknownMatrixHeader("The header contained '%s'" % header)
+    _, rows, _, cols = struct.unpack("<bibi", _read_exact(fd, 10))
+    buf = _read_exact(fd, rows * cols * dtype.itemsize)
+    return np.frombuffer(buf, dtype=dtype).reshape(rows, cols)
+
+
+def _read_mat_ascii(fd):
+    rows = []
+    while True:
+        line = fd.readline().decode()
+        if len(line) == 0:
+            raise BadInputFormat
+        tokens = line.strip().split()
+        if not tokens:
+            continue
+        if tokens[-1] != "]":
+            rows.append(np.array(tokens, dtype="float32"))
+        else:
+            rows.append(np.array(tokens[:-1], dtype="float32"))
+            return np.vstack(rows)
+
+
+def read_mat(file_or_fd):
+    """One Kaldi matrix, binary ('FM ', 'DM ', 'CM ') or text."""
+    fd = open_or_fd(file_or_fd)
+    try:
+        flag = _read_exact(fd, 2).decode()
+        if flag == "\0B":
+            return _read_mat_binary(fd)
+        assert flag == " ["
+        return _read_mat_ascii(fd)
+    finally:
+        if fd is not file_or_fd:
+            fd.close()
+
+
+def read_mat_ark(file_or_fd):
+    """Generator of (key, matrix) over a matrix ark: the extractor's input loop
+    (reference models.py:373 -> kaldi_io.py:372-392)."""
+    fd = open_or_fd(file_or_fd)
+    try:
+        key = read_key(fd)
+        while key:
+            yield key, read_mat(fd)
+            key = read_key(fd)
+    finally:
+        if fd is not file_or_fd:
+            fd.close()
+
+
+def read_mat_scp(file_or_fd):
+    """Generator of (key, matrix) following an scp file."""
+    fd = open_or_fd(file_or_fd)
+    try:
+        for line in fd:
+            key, rxfile = line.decode().split(" ")
+            yield key, read_mat(rxfile.strip())
+    finally:
+        if fd is not file_or_fd:
+            fd.close()
+
+
+def write_mat(file_or_fd, m, key=""):
+    """Append one binary matrix (float32 -> 'FM ', float64 -> 'DM ')."""
+    fd = open_or_fd(file_or_fd, mode="wb")
+    _check_binary_writable(fd)
+    try:
+        if m.dtype == "float32":
+            tag = b"FM "
+        elif m.dtype == "float64":
+            tag = b"DM "
+        else:
+            raise UnsupportedDataType("'%s', please use 'float32' or 'float64'" % m.dtype)
+        head = (key + " ").encode() if key != "" else b""
+        fd.write(head + b"\0B" + tag + b"\4" + struct.pack("<I", m.shape[0]) + b"\4" + struct.pack("<I", m.shape[1]))
+        fd.write(m.tobytes())
+    finally:
+        if fd is not file_or_fd:
+            fd.close()

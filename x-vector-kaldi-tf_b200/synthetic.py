@@ -1,0 +1,93 @@
+"""Deterministic synthetic MFCC features and model weights.
+
+There is no network for corpora or checkpoints, so every test/bench input is generated
+here from fixed seeds.  Two weight sets:
+
+  * ``"A"`` (model_0-like): what ``build_model`` initialises (reference
+    local/tf/models.py:473-474,492-493 and local/tf/tf_block.py:10-15): truncated normal
+    (sigma=0.1, resampled beyond 2 sigma) weights, bias 0.1, identity BatchNorm.
+  * ``"B"`` (trained-like): He-normal weights, random bias and non-trivial BatchNorm
+    statistics, so the fused ``relu(acc+b)*inv + shift`` epilogue is really exercised.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+FEAT_DIM = 23          # conf/mfcc.conf: --num-ceps=23
+
+
+def mfcc(seed, num_frames, feat_dim=FEAT_DIM):
+    """One utterance [T, feat_dim] float32: c0-heavy, zero-mean (post-CMN-like)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    scale = (12.0 / np.sqrt(1.0 + np.arange(feat_dim))).astype(np.float32)
+    return rng.standard_normal((num_frames, feat_dim), dtype=np.float32) * scale
+
+
+def mfcc_batch(seed, lengths, feat_dim=FEAT_DIM):
+    """Concatenated utterances [sum(T), feat_dim] float32 drawn from ONE stream."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    return mfcc(seed, int(lengths.sum()), feat_dim)
+
+
+def lengths_uniform(seed, n, lo=200, hi=1000):
+    """BASELINE config 3/4 length law: integers uniform in [lo, hi]."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return rng.integers(lo, hi + 1, size=n).astype(np.int32)
+
+
+def _trunc_normal(rng, shape, sigma):
+    x = rng.standard_normal(shape)
+    bad = np.abs(x) > 2.0
+    while bad.any():
+        x[bad] = rng.standard_normal(int(bad.sum()))
+        bad = np.abs(x) > 2.0
+    return (x * sigma).astype(np.float32)
+
+
+def make_params(kernel_sizes, layer_sizes, embedding_sizes, feat_dim=FEAT_DIM, num_classes=0,
+                weight_set="A", seed=100):
+    """Parameter dict keyed by the reference's TF variable names (models.py:199-210)."""
+    p = {}
+    prev = feat_dim
+
+    def bn(scope, dim, rng):
+        if weight_set == "A":
+            p[scope + "gamma:0"] = np.ones(dim, np.float32)
+            p[scope + "beta:0"] = np.zeros(dim, np.float32)
+            p[scope + "mean:0"] = np.zeros(dim, np.float32)
+            p[scope + "variance:0"] = np.ones(dim, np.float32)
+        else:
+            p[scope + "gamma:0"] = rng.uniform(0.5, 1.5, dim).astype(np.float32)
+            p[scope + "beta:0"] = (0.1 * rng.standard_normal(dim)).astype(np.float32)
+            p[scope + "mean:0"] = (0.3 + 0.1 * rng.standard_normal(dim)).astype(np.float32)
+            p[scope + "variance:0"] = rng.uniform(0.5, 2.0, dim).astype(np.float32)
+
+    for i, (k, width) in enumerate(zip(kernel_sizes, layer_sizes)):
+        rng = np.random.Generator(np.random.PCG64(seed + i))
+        s = "frame_level_info_layer-%d/" % i
+        if weight_set == "A":
+            p[s + "w:0"] = _trunc_normal(rng, (k, prev, width), 0.1)
+            p[s + "b:0"] = np.full(width, 0.1, np.float32)
+        else:
+            p[s + "w:0"] = (rng.standard_normal((k, prev, width)) * np.sqrt(2.0 / (k * prev))).astype(np.float32)
+            p[s + "b:0"] = rng.uniform(-0.1, 0.1, width).astype(np.float32)
+        bn(s, width, rng)
+        prev = width
+    prev *= 2
+    for i, width in enumerate(embedding_sizes):
+        rng = np.random.Generator(np.random.PCG64(seed + 50 + i))
+        s = "embed_layer-%d/" % i
+        if weight_set == "A":
+            p[s + "w:0"] = _trunc_normal(rng, (prev, width), 0.1)
+            p[s + "b:0"] = np.full(width, 0.1, np.float32)
+        else:
+            p[s + "w:0"] = (rng.standard_normal((prev, width)) * np.sqrt(2.0 / prev)).astype(np.float32)
+            p[s + "b:0"] = rng.uniform(-0.1, 0.1, width).astype(np.float32)
+        bn(s, width, rng)
+        prev = width
+    if num_classes > 0:
+        rng = np.random.Generator(np.random.PCG64(seed + 90))
+        lim = np.sqrt(6.0 / (prev + num_classes))            # xavier uniform (models.py:504-505)
+        p["output/w:0"] = rng.uniform(-lim, lim, (prev, num_classes)).astype(np.float32)
+        p["output/b:0"] = np.full(num_classes, 0.1, np.float32)
+    return p
