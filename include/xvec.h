@@ -1,0 +1,121 @@
+/* xvec.h -- C ABI of libxvec_b200.so: the B200 (sm_100a) x-vector extraction hot path.
+ *
+ * This is the drop-in boundary for the ONE operator call the reference makes into its
+ * runtime on the extraction path:
+ *
+ *     xvector = sess.run(self.embedding[0],
+ *                        feed_dict={input_x: data[1,T,D], dropout_keep_prob: 1.0, phase: False})
+ *                                                       -- reference local/tf/models.py:412-415
+ *
+ * i.e. "features of one chunk in, 512-dim embed_layer-0/scores out", evaluated over the graph
+ * that Model.build_model declares (local/tf/models.py:441-534 / :543-639) with the variables
+ * that Model.load_model restores by NAME (local/tf/models.py:143-162, :199-210).
+ * Each entry point below names the reference interface it replaces.
+ *
+ * Conventions: plain C types only (no torch / C++ types); every function returns XV_OK (0)
+ * or a negative XV_E* code and never throws; xv_last_error() gives a thread-local message;
+ * the caller owns every buffer it passes in, the model owns its weights.  One xv_model is
+ * bound to one CUDA device; calls on the same model must not run concurrently.
+ *
+ * "Segment" = one chunk of one utterance as cut by make_embedding (models.py:388-410): the
+ * rows of ONE sess.run call.  A call here evaluates many segments at once.
+ */
+#ifndef XVEC_B200_H_
+#define XVEC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XV_MAX_FRAME_LAYERS 8
+
+enum {
+  XV_OK = 0,
+  XV_EINVAL = -1,      /* bad argument / unknown variable name / shape mismatch            */
+  XV_ECUDA = -2,       /* CUDA runtime or driver error (message has the CUDA error string) */
+  XV_ENOMEM = -3,      /* workspace too small / allocation failed                          */
+  XV_ESTATE = -4,      /* parameters missing at forward time                               */
+  XV_EOVERFLOW = -5    /* an activation left the fp16 range (reported by xv_check_overflow)*/
+};
+
+enum { XV_ACT_RELU = 0 };
+
+/* Topology = the constants hard-coded in each build_model body
+ * (kernel_sizes / dilation_rates / layer_sizes: models.py:443-445, :545-548). */
+typedef struct xv_topology {
+  int32_t feat_dim;                         /* input_feature_dim (23: conf/mfcc.conf)        */
+  int32_t n_frame_layers;                   /* 5                                             */
+  int32_t taps[XV_MAX_FRAME_LAYERS];        /* kernel_sizes, odd                             */
+  int32_t dilation[XV_MAX_FRAME_LAYERS];    /* dilation_rates (1 for tf.nn.conv1d)           */
+  int32_t width[XV_MAX_FRAME_LAYERS];       /* layer_sizes; multiples of 256                 */
+  int32_t emb_dim;                          /* embedding_sizes[0] = 512                      */
+  int32_t act;                              /* XV_ACT_*                                      */
+  float bn_eps;                             /* 1e-3  (tf_block.py:9)                         */
+  float var_eps;                            /* 1e-5  (models.py:16 VAR2STD_EPSILON)          */
+} xv_topology;
+
+typedef struct xv_model xv_model;           /* opaque: device weights, metadata, tensor maps */
+
+/* Replaces graph construction / import (build_model, tf.train.import_meta_graph: models.py:146). */
+int xv_create(xv_model** out, int device, const xv_topology* topo);
+void xv_destroy(xv_model* m);
+
+/* Replaces saver.restore's per-variable assignment (models.py:147).  `tf_var_name` is the
+ * reference's variable name, e.g. "frame_level_info_layer-2/w:0" [k,Cin,Cout],
+ * ".../b:0", ".../gamma:0", ".../beta:0", ".../mean:0", ".../variance:0",
+ * "embed_layer-0/w:0" [2*C,emb], "embed_layer-0/b:0".  `host` is fp32, C-contiguous, and is
+ * copied.  Names of variables the extraction path never reads (embed_layer-1/..., output/...)
+ * are accepted and ignored. */
+int xv_set_param(xv_model* m, const char* tf_var_name, const float* host,
+                 const int64_t* shape, int32_t rank);
+
+/* Bytes of device scratch a forward over `n_seg` segments with `total_frames` rows needs. */
+size_t xv_workspace_bytes(const xv_model* m, int64_t total_frames, int32_t n_seg);
+
+/* Replaces sess.run(embedding[0], ...) (models.py:414) for a whole batch of segments.
+ *   feats_dev    [total_frames, feat_dim] fp32, device, segments concatenated in order
+ *   seg_len_host [n_seg] int32, HOST: rows of each segment (each >= 1)
+ *   emb_dev      [n_seg, emb_dim] fp32, device: embed_layer-0/scores per segment
+ *   workspace_dev / workspace_bytes: device scratch, >= xv_workspace_bytes(...)
+ *   stream       cudaStream_t (NULL = legacy default stream)
+ * Enqueue only: no host synchronisation, no device allocation. */
+int xv_forward(xv_model* m, const float* feats_dev, const int32_t* seg_len_host, int32_t n_seg,
+               float* emb_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* Debug / parity: as xv_forward, additionally writes each frame layer's output (after
+ * ReLU+BatchNorm, i.e. the tensor models.py:480 produces) as fp32 [total_frames, width[i]]
+ * into layer_out_dev[i] (NULL entries are skipped) and the pooled statistics
+ * [n_seg, 2*width[last]] into stats_out_dev (may be NULL). */
+int xv_forward_layers(xv_model* m, const float* feats_dev, const int32_t* seg_len_host,
+                      int32_t n_seg, float* emb_dev, void* workspace_dev, size_t workspace_bytes,
+                      void* stream, float* const* layer_out_dev, float* stats_out_dev);
+
+/* Host-buffer form of the same call: the shape of the reference's operator boundary (host
+ * numpy in, host numpy out; models.py:410-415).  Copies feats host->device, runs the forward,
+ * copies embeddings device->host and synchronises.  Buffers should be page-locked for full
+ * PCIe speed.  Device scratch is owned (and grown on demand) by the model. */
+int xv_extract_host(xv_model* m, const float* feats_host, const int32_t* seg_len_host,
+                    int32_t n_seg, float* emb_host);
+
+/* Returns XV_OK, or XV_EOVERFLOW if any activation exceeded the fp16 range since the last
+ * call (synchronises `stream`; clears the flag). */
+int xv_check_overflow(xv_model* m, void* stream);
+
+/* Number of kernels the last xv_forward / xv_extract_host launched (for bench.py's
+ * "gpu_launches" claim). */
+int32_t xv_last_launch_count(const xv_model* m);
+
+/* Tuning knob for experiments: 0 = one TMA box per (tap, channel chunk); 1 = load each
+ * activation slab once and address every tap inside it (default chosen by the library). */
+int xv_set_option(xv_model* m, const char* name, int64_t value);
+
+const char* xv_last_error(void);
+const char* xv_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XVEC_B200_H_ */

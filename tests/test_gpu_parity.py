@@ -1,0 +1,189 @@
+"""Parity of the sm_100a path (through the C ABI) against the CPU oracle.  Run on a B200:
+``python -m pytest tests -m gpu``.
+
+Tolerance (north_star / SURVEY 8d): per-utterance max|e-r| / max|r| <= 1e-3 and
+||e-r||2 / ||r||2 <= 1e-3 against the fp64 oracle.  Per-layer checks use 2e-3 of the layer's
+max magnitude (activations are stored in fp16 between layers).
+"""
+import io
+import os
+
+import numpy as np
+import pytest
+
+from oracle import xvector_oracle as orc
+from xvector_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+def _engine(topology, weight_set, **opts):
+    from xvector_b200 import _native
+    t = orc.TOPOLOGIES[topology]
+    params = synthetic.make_params(t["kernel_sizes"], t["layer_sizes"], t["embedding_sizes"], weight_set=weight_set)
+    eng = _native.XvecEngine(t["kernel_sizes"], t["dilations"], t["layer_sizes"], 512, 23, device=0)
+    eng.set_params(params)
+    for k, v in opts.items():
+        eng.set_option(k, v)
+    return eng, params
+
+
+def _oracle_batch(feats, lens, params, topology):
+    out, off = [], 0
+    for n in lens:
+        out.append(orc.forward(feats[off:off + n], params, topology))
+        off += n
+    return np.stack(out)
+
+
+def _run(eng, feats, lens):
+    import torch
+    emb = eng.forward(torch.from_numpy(feats).cuda(), np.asarray(lens, np.int32))
+    torch.cuda.synchronize()
+    eng.check_overflow()
+    return emb.cpu().numpy()
+
+
+def test_library_is_native_and_loaded():
+    from xvector_b200 import _native
+    lib = _native.load_library()
+    assert b"sm_100a" in lib.xv_version()
+    assert os.path.exists(_native.LIB_PATH)
+
+
+@pytest.mark.parametrize("topology", ["ModelWithoutDropout", "ModelWithoutDropoutTdnn"])
+def test_layer_by_layer_against_oracle(topology):
+    import torch
+    eng, params = _engine(topology, "B")
+    lens = np.array([200, 37, 131, 25], np.int32)
+    feats = synthetic.mfcc_batch(11, lens)
+    emb, layers, stats = eng.forward(torch.from_numpy(feats).cuda(), lens, return_layers=True)
+    torch.cuda.synchronize()
+    eng.check_overflow()
+    off = 0
+    for s, n in enumerate(lens):
+        ref_emb, ref_layers, ref_stats = orc.forward(feats[off:off + n], params, topology, return_layers=True)
+        for i, (got, want) in enumerate(zip(layers, ref_layers)):
+            g = got[off:off + n].cpu().numpy().astype(np.float64)
+            err = np.abs(g - want).max() / np.abs(want).max()
+            assert err < 2e-3, "segment %d layer %d: rel err %.3e" % (s, i, err)
+        gs = stats[s].cpu().numpy().astype(np.float64)
+        assert np.abs(gs - ref_stats).max() / np.abs(ref_stats).max() < 2e-3
+        m = orc.parity_metrics(emb[s].cpu().numpy(), ref_emb)
+        assert m["max_rel"] <= TOL, (s, m)
+        off += n
+    eng.close()
+
+
+@pytest.mark.parametrize("topology", ["ModelWithoutDropout", "ModelWithoutDropoutTdnn"])
+@pytest.mark.parametrize("weight_set", ["A", "B"])
+def test_embedding_parity_ragged_batch(topology, weight_set):
+    eng, params = _engine(topology, weight_set)
+    lens = synthetic.lengths_uniform(3, 12, 25, 400)           # ragged, incl. short segments
+    lens[0], lens[1] = 25, 1000
+    feats = synthetic.mfcc_batch(3, lens)
+    got = _run(eng, feats, lens)
+    want = _oracle_batch(feats, lens, params, topology)
+    m = orc.parity_metrics(got, want)
+    print(topology, weight_set, m)
+    assert m["max_rel"] <= TOL and m["l2_rel"] <= TOL and m["min_cos"] >= 0.999999, m
+    eng.close()
+
+
+def test_config1_single_200_frame_utterance():
+    # BASELINE.json configs[0]: one 200 x 23 utterance, seed 1
+    eng, params = _engine("ModelWithoutDropout", "A")
+    x = synthetic.mfcc(1, 200)
+    got = _run(eng, x, [200])
+    m = orc.parity_metrics(got, orc.forward(x, params)[None])
+    assert m["max_rel"] <= TOL and m["l2_rel"] <= TOL, m
+    eng.close()
+
+
+def test_config2_full_batch_sampled_against_oracle():
+    # BASELINE.json configs[1]: 256 utterances x 400 frames x 23; oracle on a sample of utterances
+    eng, params = _engine("ModelWithoutDropout", "B")
+    lens = np.full(256, 400, np.int32)
+    feats = synthetic.mfcc_batch(2, lens)
+    got = _run(eng, feats, lens)
+    assert np.isfinite(got).all()
+    pick = [0, 1, 127, 128, 254, 255]
+    want = np.stack([orc.forward(feats[i * 400:(i + 1) * 400], params) for i in pick])
+    m = orc.parity_metrics(got[pick], want)
+    print("config2", m)
+    assert m["max_rel"] <= TOL and m["l2_rel"] <= TOL, m
+    eng.close()
+
+
+def test_results_do_not_depend_on_batch_composition_or_run():
+    # size-independent property: an utterance's embedding is bit-identical alone, inside any batch,
+    # at any position, and run to run (what makes 1/2/4/8-GPU sharding byte-identical)
+    eng, _ = _engine("ModelWithoutDropoutTdnn", "B")
+    lens = np.array([300, 90, 411, 25, 640, 128, 127, 129], np.int32)
+    feats = synthetic.mfcc_batch(5, lens)
+    full = _run(eng, feats, lens)
+    again = _run(eng, feats, lens)
+    assert np.array_equal(full, again)
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    for i in (0, 3, 4, 7):
+        alone = _run(eng, feats[offs[i]:offs[i + 1]], lens[i:i + 1])
+        assert np.array_equal(alone[0], full[i]), "utterance %d differs when run alone" % i
+    perm = np.array([7, 2, 5, 0, 1, 6, 3, 4])
+    pf = np.concatenate([feats[offs[i]:offs[i + 1]] for i in perm])
+    shuffled = _run(eng, pf, lens[perm])
+    assert np.array_equal(shuffled, full[perm])
+    eng.close()
+
+
+def test_extract_host_equals_device_forward():
+    eng, _ = _engine("ModelWithoutDropout", "B")
+    lens = np.array([200, 333, 50], np.int32)
+    feats = synthetic.mfcc_batch(8, lens)
+    dev = _run(eng, feats, lens)
+    host = eng.extract_host(feats, lens)
+    assert np.array_equal(dev, host)
+    assert eng.last_launch_count == 7          # pack + 5 layers + pool/embed
+    eng.close()
+
+
+def test_error_paths_do_not_crash():
+    from xvector_b200 import _native
+    t = orc.TOPOLOGIES["ModelWithoutDropout"]
+    eng = _native.XvecEngine(t["kernel_sizes"], t["dilations"], t["layer_sizes"], 512, 23, device=0)
+    with pytest.raises(_native.XvecError):                      # parameters missing
+        eng.extract_host(np.zeros((30, 23), np.float32), [30])
+    with pytest.raises(_native.XvecError):                      # wrong shape
+        eng.set_params({"frame_level_info_layer-0/w:0": np.zeros((5, 23, 511), np.float32)})
+    with pytest.raises(_native.XvecError):                      # unknown name
+        eng.set_params({"nonsense/w:0": np.zeros((3,), np.float32)})
+    eng.set_params({"output/w:0": np.zeros((512, 10), np.float32)})   # training-only variable: ignored
+    eng.close()
+
+
+def test_make_embedding_end_to_end_with_chunking_and_skips(tmp_path):
+    import logging
+    from xvector_b200 import kaldi_io
+    from xvector_b200.models import ModelWithoutDropoutTdnn, Model
+
+    os.environ["XVEC_SEED"] = "7"
+    model_dir = str(tmp_path / "model_0")
+    ModelWithoutDropoutTdnn().build_model(10, 23, model_dir, None)
+    params = Model().get_models_weights(model_dir)
+    utts = {"utt_a": synthetic.mfcc(21, 130), "utt_short": synthetic.mfcc(22, 10),
+            "utt_b": synthetic.mfcc(23, 60), "utt_empty": np.zeros((0, 23), np.float32),
+            "utt_c": synthetic.mfcc(24, 101)}
+    buf = io.BytesIO()
+    for k, m in utts.items():
+        kaldi_io.write_mat(buf, m, key=k)
+    out = io.BytesIO()
+    logger = logging.getLogger("test_make_embedding")
+    Model().make_embedding(io.BytesIO(buf.getvalue()), out, model_dir, 25, 50, True, logger)
+    got = dict(kaldi_io.read_vec_flt_ark(io.BytesIO(out.getvalue())))
+    assert list(got) == ["utt_a", "utt_b", "utt_c"]             # skipped: < min_chunk_size, empty
+    for k in got:
+        want = orc.make_embedding_one(utts[k].astype(np.float64), params, "ModelWithoutDropoutTdnn", 25, 50)
+        m = orc.parity_metrics(got[k], want)
+        assert m["max_rel"] <= TOL, (k, m)
+        assert got[k].dtype == np.float32 and got[k].shape == (512,)

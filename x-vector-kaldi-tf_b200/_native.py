@@ -1,0 +1,216 @@
+"""ctypes binding of libxvec_b200.so (C ABI in include/xvec.h).
+
+There is deliberately NO fallback: if the shared library is missing or no B200 is present the
+calls raise -- the product path never routes through a CPU implementation.  PyTorch is used
+only as the device/pinned memory container (``tensor.data_ptr()``) and for stream handles.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_NAME = "libxvec_b200.so"
+LIB_PATH = os.path.join(_HERE, LIB_NAME)
+CSRC = os.path.join(_HERE, "csrc")
+REPO_ROOT = os.path.dirname(_HERE)
+
+XV_MAX_FRAME_LAYERS = 8
+XV_OK, XV_EINVAL, XV_ECUDA, XV_ENOMEM, XV_ESTATE, XV_EOVERFLOW = 0, -1, -2, -3, -4, -5
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+
+class XvTopology(ctypes.Structure):
+    _fields_ = [("feat_dim", ctypes.c_int32), ("n_frame_layers", ctypes.c_int32),
+                ("taps", ctypes.c_int32 * XV_MAX_FRAME_LAYERS),
+                ("dilation", ctypes.c_int32 * XV_MAX_FRAME_LAYERS),
+                ("width", ctypes.c_int32 * XV_MAX_FRAME_LAYERS),
+                ("emb_dim", ctypes.c_int32), ("act", ctypes.c_int32),
+                ("bn_eps", ctypes.c_float), ("var_eps", ctypes.c_float)]
+
+
+class XvecError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("xvec_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+def build_library(verbose=False):
+    """Compile csrc/xvec_api.cu for sm_100a into the in-tree shared library (nvcc cross-compiles
+    without a GPU).  Skips the compile when the library is newer than every source."""
+    sources = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    sources.append(os.path.join(REPO_ROOT, "include", "xvec.h"))
+    if os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in sources):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH, os.path.join(CSRC, "xvec_api.cu")]
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load_library():
+    """Load libxvec_b200.so; raise (never fall back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise XvecError(XV_ESTATE, "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                                    "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    P, I32, I64, SZ = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t
+    lib.xv_create.argtypes = [ctypes.POINTER(P), ctypes.c_int, ctypes.POINTER(XvTopology)]
+    lib.xv_create.restype = ctypes.c_int
+    lib.xv_destroy.argtypes = [P]
+    lib.xv_destroy.restype = None
+    lib.xv_set_param.argtypes = [P, ctypes.c_char_p, P, ctypes.POINTER(I64), I32]
+    lib.xv_set_param.restype = ctypes.c_int
+    lib.xv_workspace_bytes.argtypes = [P, I64, I32]
+    lib.xv_workspace_bytes.restype = SZ
+    lib.xv_forward.argtypes = [P, P, P, I32, P, P, SZ, P]
+    lib.xv_forward.restype = ctypes.c_int
+    lib.xv_forward_layers.argtypes = [P, P, P, I32, P, P, SZ, P, ctypes.POINTER(P), P]
+    lib.xv_forward_layers.restype = ctypes.c_int
+    lib.xv_extract_host.argtypes = [P, P, P, I32, P]
+    lib.xv_extract_host.restype = ctypes.c_int
+    lib.xv_check_overflow.argtypes = [P, P]
+    lib.xv_check_overflow.restype = ctypes.c_int
+    lib.xv_last_launch_count.argtypes = [P]
+    lib.xv_last_launch_count.restype = I32
+    lib.xv_set_option.argtypes = [P, ctypes.c_char_p, I64]
+    lib.xv_set_option.restype = ctypes.c_int
+    lib.xv_last_error.argtypes = []
+    lib.xv_last_error.restype = ctypes.c_char_p
+    lib.xv_version.argtypes = []
+    lib.xv_version.restype = ctypes.c_char_p
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = ["xv_create", "xv_destroy", "xv_set_param", "xv_workspace_bytes", "xv_forward",
+                    "xv_forward_layers", "xv_extract_host", "xv_check_overflow", "xv_last_launch_count",
+                    "xv_set_option", "xv_last_error", "xv_version"]
+
+
+def _check(lib, rc):
+    if rc != XV_OK:
+        raise XvecError(rc, lib.xv_last_error().decode(errors="replace"))
+
+
+class XvecEngine:
+    """One xv_model on one CUDA device: the replacement for the reference's TF session +
+    restored graph (models.py:365-366) on the extraction path."""
+
+    def __init__(self, kernel_sizes, dilations, layer_sizes, emb_dim, feat_dim, device=0,
+                 bn_eps=1e-3, var_eps=1e-5):
+        self.lib = load_library()
+        topo = XvTopology()
+        topo.feat_dim = feat_dim
+        topo.n_frame_layers = len(kernel_sizes)
+        for i, (k, d, w) in enumerate(zip(kernel_sizes, dilations, layer_sizes)):
+            topo.taps[i], topo.dilation[i], topo.width[i] = k, d, w
+        topo.emb_dim = emb_dim
+        topo.act = 0
+        topo.bn_eps = bn_eps
+        topo.var_eps = var_eps
+        self.handle = ctypes.c_void_p()
+        self.device = device
+        self.feat_dim, self.emb_dim = feat_dim, emb_dim
+        self.layer_sizes = list(layer_sizes)
+        _check(self.lib, self.lib.xv_create(ctypes.byref(self.handle), device, ctypes.byref(topo)))
+        self._ws = None
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self.lib.xv_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, name, value):
+        _check(self.lib, self.lib.xv_set_option(self.handle, name.encode(), int(value)))
+
+    def set_params(self, params):
+        """params: dict TF-variable-name -> array (the contract of load_model, models.py:199-210)."""
+        for name, arr in params.items():
+            a = np.ascontiguousarray(np.asarray(arr), dtype=np.float32)
+            shape = (ctypes.c_int64 * a.ndim)(*a.shape)
+            _check(self.lib, self.lib.xv_set_param(self.handle, name.encode(), a.ctypes.data_as(ctypes.c_void_p),
+                                                   shape, a.ndim))
+
+    def workspace_bytes(self, total_frames, n_seg):
+        return int(self.lib.xv_workspace_bytes(self.handle, int(total_frames), int(n_seg)))
+
+    def _workspace(self, nbytes):
+        import torch
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device="cuda:%d" % self.device)
+        return self._ws
+
+    def forward(self, feats_dev, seg_lens, emb_dev=None, stream=None, return_layers=False):
+        """feats_dev: torch float32 CUDA tensor [total_frames, feat_dim]; seg_lens: int32 host array.
+        Enqueues on ``stream`` (default: torch's current stream); returns emb_dev [n_seg, emb_dim]."""
+        import torch
+        lens = np.ascontiguousarray(seg_lens, dtype=np.int32)
+        n_seg, total = int(lens.shape[0]), int(lens.sum())
+        assert feats_dev.is_cuda and feats_dev.dtype == torch.float32 and feats_dev.is_contiguous()
+        assert feats_dev.shape[0] == total and feats_dev.shape[1] == self.feat_dim
+        dev = feats_dev.device
+        if emb_dev is None:
+            emb_dev = torch.empty((n_seg, self.emb_dim), dtype=torch.float32, device=dev)
+        ws = self._workspace(self.workspace_bytes(total, n_seg))
+        s = torch.cuda.current_stream(dev) if stream is None else stream
+        lens_p = lens.ctypes.data_as(ctypes.c_void_p)
+        if not return_layers:
+            _check(self.lib, self.lib.xv_forward(self.handle, feats_dev.data_ptr(), lens_p, n_seg, emb_dev.data_ptr(),
+                                                 ws.data_ptr(), ws.numel(), s.cuda_stream))
+            return emb_dev
+        layers = [torch.empty((total, w), dtype=torch.float32, device=dev) for w in self.layer_sizes]
+        stats = torch.empty((n_seg, 2 * self.layer_sizes[-1]), dtype=torch.float32, device=dev)
+        ptrs = (ctypes.c_void_p * len(layers))(*[t.data_ptr() for t in layers])
+        _check(self.lib, self.lib.xv_forward_layers(self.handle, feats_dev.data_ptr(), lens_p, n_seg,
+                                                    emb_dev.data_ptr(), ws.data_ptr(), ws.numel(), s.cuda_stream,
+                                                    ptrs, stats.data_ptr()))
+        return emb_dev, layers, stats
+
+    def check_overflow(self, stream=None):
+        import torch
+        s = torch.cuda.current_stream(self.device) if stream is None else stream
+        _check(self.lib, self.lib.xv_check_overflow(self.handle, s.cuda_stream))
+
+    def extract_host(self, feats_host, seg_lens, emb_host=None):
+        """Host in / host out (the reference's sess.run boundary).  feats_host: float32
+        [total_frames, feat_dim] numpy array or CPU torch tensor (pinned for full PCIe speed)."""
+        lens = np.ascontiguousarray(seg_lens, dtype=np.int32)
+        n_seg = int(lens.shape[0])
+        if hasattr(feats_host, "data_ptr"):
+            fptr = feats_host.data_ptr()
+            assert feats_host.is_contiguous() and feats_host.shape[0] == int(lens.sum())
+        else:
+            feats_host = np.ascontiguousarray(feats_host, dtype=np.float32)
+            assert feats_host.shape[0] == int(lens.sum())
+            fptr = feats_host.ctypes.data
+        if emb_host is None:
+            emb_host = np.empty((n_seg, self.emb_dim), dtype=np.float32)
+        eptr = emb_host.data_ptr() if hasattr(emb_host, "data_ptr") else emb_host.ctypes.data
+        _check(self.lib, self.lib.xv_extract_host(self.handle, fptr, lens.ctypes.data_as(ctypes.c_void_p), n_seg, eptr))
+        return emb_host
+
+    @property
+    def last_launch_count(self):
+        return int(self.lib.xv_last_launch_count(self.handle))

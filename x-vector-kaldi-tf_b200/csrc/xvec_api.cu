@@ -1,0 +1,586 @@
+// xvec_api.cu -- host side of libxvec_b200.so: the C ABI declared in include/xvec.h.
+// Owns parameter packing (TF variable names -> device layouts), the workspace plan, TMA tensor
+// maps and the kernel launch sequence  pack -> 5 x tdnn_layer -> pool_embed.
+#include "../../include/xvec.h"
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "pack_pool.cuh"
+#include "tdnn_layer.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define XV_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(XV_ECUDA, std::string(#expr) + ": " + cudaGetErrorName(e_) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct FrameLayer {
+  int taps = 0, dilation = 1, c_in = 0, c_in_pad = 0, c_out = 0, k_total = 0;   // k_total = packed K (multiple of 64)
+  int gemm_taps = 0;           // taps seen by the GEMM kernel (1 for the im2col'ed first layer)
+  __half* w_dev = nullptr;     // [c_out, k_total] fp16, K-major
+  float* bias_dev = nullptr;   // [c_out]
+  float* scale_dev = nullptr;  // [c_out]
+  float* shift_dev = nullptr;  // [c_out]
+};
+
+struct Plan {
+  int64_t total_frames = 0;
+  int32_t n_seg = 0;
+  int64_t r_pad = 0;
+  int32_t group = 1, n_groups = 0, n_slabs = 0;
+  size_t off_meta = 0, off_counters = 0, off_valid = 0, off_x0 = 0, off_ha = 0, off_hb = 0, off_hlast = 0,
+         off_partial = 0, bytes = 0;
+};
+
+constexpr int META_SLOTS = 4;
+
+}  // namespace
+
+struct xv_model {
+  xv_topology topo{};
+  int device = 0;
+  int num_sms = 148;
+  int gap = 0;                       // zero rows between segments = max half context of any layer
+  int k0_pad = 0;                    // packed width of the first layer's spliced input
+  int w_mid = 0;                     // widest of layers 0..n-2 (ping-pong buffers)
+  std::map<std::string, std::vector<float>> host_params;
+  std::map<std::string, std::vector<int64_t>> host_shapes;
+  bool dirty = true;
+  std::vector<FrameLayer> layers;
+  float* w0_dev = nullptr;           // [2C, E]
+  float* b0_dev = nullptr;           // [E]
+  uint32_t* overflow_dev = nullptr;
+  uint32_t* overflow_host = nullptr; // pinned
+  EncodeTiledFn encode = nullptr;
+  // pinned staging ring for segment metadata
+  int32_t* meta_host[META_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t meta_event[META_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+  int64_t meta_cap = 0;
+  int meta_next = 0;
+  // xv_extract_host state
+  cudaStream_t stream = nullptr;
+  float* feats_dev = nullptr; size_t feats_cap = 0;
+  float* emb_dev = nullptr; size_t emb_cap = 0;
+  void* ws_dev = nullptr; size_t ws_cap = 0;
+  int32_t last_launches = 0;
+  // options
+  int opt_reuse = 0;
+  int opt_desc_base_offset = 1;
+};
+
+namespace {
+
+Plan make_plan(const xv_model* m, int64_t total_frames, int32_t n_seg) {
+  Plan p;
+  p.total_frames = total_frames;
+  p.n_seg = n_seg;
+  const int64_t rows = m->gap + total_frames + int64_t(n_seg) * m->gap;
+  p.r_pad = round_up(std::max<int64_t>(rows, 1), tdnn::BLOCK_M);
+  const int c_last = m->topo.width[m->topo.n_frame_layers - 1];
+  p.n_slabs = c_last / xvk::POOL_SLAB;
+  p.group = int(std::min<int64_t>(xvk::POOL_MAX_G, std::max<int64_t>(1, n_seg / 64)));
+  p.n_groups = (n_seg + p.group - 1) / p.group;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = size_t(round_up(int64_t(off + bytes), 1024)); return o; };
+  p.off_meta = take(size_t(3) * n_seg * 4);
+  p.off_counters = take(size_t(p.n_groups) * 4);
+  p.off_valid = take(size_t(p.r_pad));
+  p.off_x0 = take(size_t(p.r_pad) * m->k0_pad * 2);
+  p.off_ha = take(size_t(p.r_pad) * m->w_mid * 2);
+  p.off_hb = take(size_t(p.r_pad) * m->w_mid * 2);
+  p.off_hlast = take(size_t(p.r_pad) * c_last * 2);
+  p.off_partial = take(size_t(p.n_slabs) * n_seg * m->topo.emb_dim * 4);
+  p.bytes = off;
+  return p;
+}
+
+int encode_2d(const xv_model* m, CUtensorMap* map, void* base, uint64_t inner, uint64_t outer, uint32_t box_inner,
+              uint32_t box_outer, CUtensorMapSwizzle swz) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {inner * 2};                   // bytes, fp16
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = m->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(XV_ECUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)));
+  return XV_OK;
+}
+
+void free_layers(xv_model* m) {
+  for (auto& L : m->layers) {
+    cudaFree(L.w_dev); cudaFree(L.bias_dev); cudaFree(L.scale_dev); cudaFree(L.shift_dev);
+    L.w_dev = nullptr; L.bias_dev = L.scale_dev = L.shift_dev = nullptr;
+  }
+  cudaFree(m->w0_dev); cudaFree(m->b0_dev);
+  m->w0_dev = m->b0_dev = nullptr;
+}
+
+const std::vector<float>* find_param(const xv_model* m, const std::string& name, std::initializer_list<int64_t> shape) {
+  auto it = m->host_params.find(name);
+  if (it == m->host_params.end()) return nullptr;
+  const auto& s = m->host_shapes.at(name);
+  if (s.size() != shape.size() || !std::equal(s.begin(), s.end(), shape.begin())) return nullptr;
+  return &it->second;
+}
+
+// Pack host parameters into device layouts.  BatchNorm (evaluation branch, tf_block.py:25-26)
+// is folded to scale = gamma * rsqrt(var + eps), shift = beta - mean * scale, in fp32.
+int finalize_params(xv_model* m) {
+  if (!m->dirty) return XV_OK;
+  XV_CUDA(cudaSetDevice(m->device));
+  free_layers(m);
+  const xv_topology& t = m->topo;
+  for (int i = 0; i < t.n_frame_layers; ++i) {
+    FrameLayer& L = m->layers[i];
+    const std::string s = "frame_level_info_layer-" + std::to_string(i) + "/";
+    const auto* w = find_param(m, s + "w:0", {L.taps, L.c_in, L.c_out});
+    const auto* b = find_param(m, s + "b:0", {L.c_out});
+    const auto* gamma = find_param(m, s + "gamma:0", {L.c_out});
+    const auto* beta = find_param(m, s + "beta:0", {L.c_out});
+    const auto* mean = find_param(m, s + "mean:0", {L.c_out});
+    const auto* var = find_param(m, s + "variance:0", {L.c_out});
+    if (!w || !b || !gamma || !beta || !mean || !var)
+      return fail(XV_ESTATE, "missing or mis-shaped parameter(s) under scope '" + s + "' (need w,b,gamma,beta,mean,variance)");
+    // weights: TF [k, Cin, Cout] -> [Cout, K] fp16 (round to nearest), K index = tap * c_in_pad + c
+    // (first layer: c_in_pad == c_in, i.e. densely spliced, zero padded up to k_total)
+    std::vector<__half> wt(size_t(L.c_out) * L.k_total, __float2half_rn(0.f));
+    for (int j = 0; j < L.taps; ++j)
+      for (int c = 0; c < L.c_in; ++c) {
+        const float* src = w->data() + (size_t(j) * L.c_in + c) * L.c_out;
+        const size_t kidx = size_t(j) * L.c_in_pad + c;
+        for (int o = 0; o < L.c_out; ++o) wt[size_t(o) * L.k_total + kidx] = __float2half_rn(src[o]);
+      }
+    std::vector<float> scale(L.c_out), shift(L.c_out);
+    for (int o = 0; o < L.c_out; ++o) {
+      const float inv = (1.0f / sqrtf((*var)[o] + t.bn_eps)) * (*gamma)[o];
+      scale[o] = inv;
+      shift[o] = (*beta)[o] - (*mean)[o] * inv;
+    }
+    XV_CUDA(cudaMalloc(&L.w_dev, wt.size() * sizeof(__half)));
+    XV_CUDA(cudaMalloc(&L.bias_dev, L.c_out * 4));
+    XV_CUDA(cudaMalloc(&L.scale_dev, L.c_out * 4));
+    XV_CUDA(cudaMalloc(&L.shift_dev, L.c_out * 4));
+    XV_CUDA(cudaMemcpy(L.w_dev, wt.data(), wt.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    XV_CUDA(cudaMemcpy(L.bias_dev, b->data(), L.c_out * 4, cudaMemcpyHostToDevice));
+    XV_CUDA(cudaMemcpy(L.scale_dev, scale.data(), L.c_out * 4, cudaMemcpyHostToDevice));
+    XV_CUDA(cudaMemcpy(L.shift_dev, shift.data(), L.c_out * 4, cudaMemcpyHostToDevice));
+  }
+  const int c_last = t.width[t.n_frame_layers - 1];
+  const auto* w0 = find_param(m, "embed_layer-0/w:0", {2 * c_last, t.emb_dim});
+  const auto* b0 = find_param(m, "embed_layer-0/b:0", {t.emb_dim});
+  if (!w0 || !b0) return fail(XV_ESTATE, "missing or mis-shaped embed_layer-0/w:0 or embed_layer-0/b:0");
+  XV_CUDA(cudaMalloc(&m->w0_dev, w0->size() * 4));
+  XV_CUDA(cudaMalloc(&m->b0_dev, b0->size() * 4));
+  XV_CUDA(cudaMemcpy(m->w0_dev, w0->data(), w0->size() * 4, cudaMemcpyHostToDevice));
+  XV_CUDA(cudaMemcpy(m->b0_dev, b0->data(), b0->size() * 4, cudaMemcpyHostToDevice));
+  m->dirty = false;
+  return XV_OK;
+}
+
+int ensure_meta_capacity(xv_model* m, int64_t n_seg) {
+  if (n_seg <= m->meta_cap) return XV_OK;
+  const int64_t cap = std::max<int64_t>(n_seg * 2, 1024);
+  for (int s = 0; s < META_SLOTS; ++s) {
+    if (m->meta_event[s]) XV_CUDA(cudaEventSynchronize(m->meta_event[s]));
+    if (m->meta_host[s]) XV_CUDA(cudaFreeHost(m->meta_host[s]));
+    m->meta_host[s] = nullptr;
+    XV_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&m->meta_host[s]), size_t(3) * cap * 4, cudaHostAllocDefault));
+    if (!m->meta_event[s]) XV_CUDA(cudaEventCreateWithFlags(&m->meta_event[s], cudaEventDisableTiming));
+  }
+  m->meta_cap = cap;
+  return XV_OK;
+}
+
+int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_host, int32_t n_seg, float* emb_dev,
+                 void* workspace_dev, size_t workspace_bytes, cudaStream_t stream, float* const* layer_out_dev,
+                 float* stats_out_dev) {
+  if (!m || !feats_dev || !seg_len_host || !emb_dev || !workspace_dev) return fail(XV_EINVAL, "null argument");
+  if (n_seg <= 0) return fail(XV_EINVAL, "n_seg must be >= 1");
+  XV_CUDA(cudaSetDevice(m->device));
+  int rc = finalize_params(m);
+  if (rc != XV_OK) return rc;
+  int64_t total = 0;
+  for (int i = 0; i < n_seg; ++i) {
+    if (seg_len_host[i] <= 0) return fail(XV_EINVAL, "segment " + std::to_string(i) + " has non-positive length");
+    total += seg_len_host[i];
+  }
+  if (m->gap + total + int64_t(n_seg) * m->gap > (int64_t(1) << 31) - 4096)
+    return fail(XV_EINVAL, "batch too large: packed rows exceed int32 range");
+  const Plan p = make_plan(m, total, n_seg);
+  if (workspace_bytes < p.bytes)
+    return fail(XV_ENOMEM, "workspace too small: need " + std::to_string(p.bytes) + " bytes, got " + std::to_string(workspace_bytes));
+  if (reinterpret_cast<uintptr_t>(workspace_dev) % 1024 != 0) return fail(XV_EINVAL, "workspace must be 1024-byte aligned");
+  uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
+
+  // ---- segment metadata: packed row starts, feature row starts, lengths ------------------
+  rc = ensure_meta_capacity(m, n_seg);
+  if (rc != XV_OK) return rc;
+  const int slot = m->meta_next;
+  m->meta_next = (m->meta_next + 1) % META_SLOTS;
+  XV_CUDA(cudaEventSynchronize(m->meta_event[slot]));      // previous copy out of this slot finished
+  int32_t* mh = m->meta_host[slot];
+  {
+    int64_t row = m->gap, fs = 0;
+    for (int i = 0; i < n_seg; ++i) {
+      mh[i] = int32_t(row);
+      mh[n_seg + i] = int32_t(fs);
+      mh[2 * n_seg + i] = seg_len_host[i];
+      row += seg_len_host[i] + m->gap;
+      fs += seg_len_host[i];
+    }
+  }
+  int32_t* meta_dev = reinterpret_cast<int32_t*>(ws + p.off_meta);
+  XV_CUDA(cudaMemcpyAsync(meta_dev, mh, size_t(3) * n_seg * 4, cudaMemcpyHostToDevice, stream));
+  XV_CUDA(cudaEventRecord(m->meta_event[slot], stream));
+  xvk::SegMeta seg{meta_dev, meta_dev + n_seg, meta_dev + 2 * n_seg, n_seg};
+
+  uint8_t* row_valid = ws + p.off_valid;
+  uint32_t* counters = reinterpret_cast<uint32_t*>(ws + p.off_counters);
+  __half* x0 = reinterpret_cast<__half*>(ws + p.off_x0);
+  __half* ha = reinterpret_cast<__half*>(ws + p.off_ha);
+  __half* hb = reinterpret_cast<__half*>(ws + p.off_hb);
+  __half* hlast = reinterpret_cast<__half*>(ws + p.off_hlast);
+  int launches = 0;
+
+  // ---- pack: fp32 features -> spliced fp16 packed rows + row map ---------------------------
+  {
+    xvk::PackArgs a{};
+    a.feats = feats_dev;
+    a.seg = seg;
+    a.r_pad = int32_t(p.r_pad);
+    a.feat_dim = m->topo.feat_dim;
+    a.taps = m->layers[0].taps;
+    a.dilation = m->layers[0].dilation;
+    a.k0_pad = m->k0_pad;
+    a.x0 = x0;
+    a.row_valid = row_valid;
+    a.counters = counters;
+    a.n_counters = p.n_groups;
+    const int blocks = int(std::max<int64_t>(p.r_pad / xvk::PACK_ROWS_PER_BLOCK,
+                                             (p.n_groups + xvk::PACK_THREADS - 1) / xvk::PACK_THREADS));
+    xvk::pack_im2col_kernel<<<blocks, xvk::PACK_THREADS, 0, stream>>>(a);
+    XV_CUDA(cudaGetLastError());
+    ++launches;
+  }
+
+  // ---- frame-level TDNN stack: one fused tcgen05 kernel per layer --------------------------
+  const int nl = m->topo.n_frame_layers;
+  const __half* in = x0;
+  for (int i = 0; i < nl; ++i) {
+    const FrameLayer& L = m->layers[i];
+    __half* out = (i == nl - 1) ? hlast : ((i & 1) ? hb : ha);
+    const int halo = (L.gemm_taps - 1) / 2 * L.dilation;
+    const bool reuse = m->opt_reuse && L.gemm_taps > 1 && halo <= tdnn::MAX_REUSE_HALO;
+    const int c_in_gemm = (i == 0) ? L.k_total : L.c_in_pad;       // row width of the input matrix
+    CUtensorMap ta, tw, tc;
+    rc = encode_2d(m, &ta, const_cast<__half*>(in), uint64_t(c_in_gemm), uint64_t(p.r_pad), tdnn::BLOCK_K,
+                   reuse ? tdnn::A_BOX_ROWS_REUSE : tdnn::A_BOX_ROWS_PLAIN, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != XV_OK) return rc;
+    rc = encode_2d(m, &tw, L.w_dev, uint64_t(L.k_total), uint64_t(L.c_out), tdnn::BLOCK_K, tdnn::BLOCK_N,
+                   CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != XV_OK) return rc;
+    rc = encode_2d(m, &tc, out, uint64_t(L.c_out), uint64_t(p.r_pad), tdnn::C_CHUNK, tdnn::BLOCK_M,
+                   CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc != XV_OK) return rc;
+    tdnn::LayerArgs a{};
+    a.n_m_tiles = int32_t(p.r_pad / tdnn::BLOCK_M);
+    a.n_n_tiles = L.c_out / tdnn::BLOCK_N;
+    a.c_chunks = c_in_gemm / tdnn::BLOCK_K;
+    a.taps = L.gemm_taps;
+    a.dilation = L.dilation;
+    a.c_in_pad = c_in_gemm;
+    a.reuse = reuse ? 1 : 0;
+    a.desc_base_offset = m->opt_desc_base_offset;
+    a.bias = L.bias_dev;
+    a.scale = L.scale_dev;
+    a.shift = L.shift_dev;
+    a.row_valid = row_valid;
+    a.overflow_flag = m->overflow_dev;
+    const int64_t tiles = int64_t(a.n_m_tiles) * a.n_n_tiles;
+    const int grid = int(std::min<int64_t>(tiles, m->num_sms));
+    tdnn::tdnn_layer_kernel<<<grid, tdnn::NUM_THREADS, tdnn::SMEM_BYTES, stream>>>(ta, tw, tc, a);
+    XV_CUDA(cudaGetLastError());
+    ++launches;
+    if (layer_out_dev && layer_out_dev[i]) {
+      xvk::unpack_rows_kernel<<<n_seg, 256, 0, stream>>>(out, seg, L.c_out, layer_out_dev[i]);
+      XV_CUDA(cudaGetLastError());
+      ++launches;
+    }
+    in = out;
+  }
+
+  // ---- statistics pooling + embed_layer-0 -----------------------------------------------
+  {
+    xvk::PoolArgs a{};
+    a.h = hlast;
+    a.seg = seg;
+    a.channels = m->topo.width[nl - 1];
+    a.emb_dim = m->topo.emb_dim;
+    a.group = p.group;
+    a.w0 = m->w0_dev;
+    a.b0 = m->b0_dev;
+    a.partial = reinterpret_cast<float*>(ws + p.off_partial);
+    a.counters = counters;
+    a.emb = emb_dev;
+    a.stats_out = stats_out_dev;
+    a.var_eps = m->topo.var_eps;
+    dim3 grid(p.n_groups, p.n_slabs);
+    xvk::pool_embed_kernel<<<grid, xvk::POOL_THREADS, 0, stream>>>(a);
+    XV_CUDA(cudaGetLastError());
+    ++launches;
+  }
+  m->last_launches = launches;
+  return XV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* xv_last_error(void) { return g_err.c_str(); }
+const char* xv_version(void) { return "xvec_b200 0.1 (sm_100a; tcgen05 + TMA)"; }
+
+int xv_create(xv_model** out, int device, const xv_topology* topo) {
+  if (!out || !topo) return fail(XV_EINVAL, "null argument");
+  *out = nullptr;
+  const xv_topology& t = *topo;
+  if (t.n_frame_layers < 2 || t.n_frame_layers > XV_MAX_FRAME_LAYERS) return fail(XV_EINVAL, "n_frame_layers out of range");
+  if (t.feat_dim <= 0) return fail(XV_EINVAL, "feat_dim must be positive");
+  if (t.act != XV_ACT_RELU) return fail(XV_EINVAL, "only XV_ACT_RELU is implemented");
+  if (t.emb_dim <= 0 || t.emb_dim % xvk::POOL_THREADS != 0 || t.emb_dim > xvk::POOL_THREADS * xvk::POOL_MAX_EPT)
+    return fail(XV_EINVAL, "emb_dim must be a multiple of 256 and <= 1024");
+  for (int i = 0; i < t.n_frame_layers; ++i) {
+    if (t.taps[i] < 1 || t.taps[i] % 2 == 0) return fail(XV_EINVAL, "taps must be odd and >= 1");
+    if (t.dilation[i] < 1) return fail(XV_EINVAL, "dilation must be >= 1");
+    if (t.width[i] <= 0 || t.width[i] % tdnn::BLOCK_N != 0) return fail(XV_EINVAL, "layer widths must be multiples of 256");
+  }
+  if (t.width[t.n_frame_layers - 1] % xvk::POOL_SLAB != 0) return fail(XV_EINVAL, "last width must be a multiple of 128");
+  int n_dev = 0;
+  XV_CUDA(cudaGetDeviceCount(&n_dev));
+  if (device < 0 || device >= n_dev) return fail(XV_EINVAL, "no such CUDA device");
+  XV_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  XV_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(XV_ECUDA, std::string("this library is built for sm_100a (B200) only; device is sm_") +
+                              std::to_string(prop.major) + std::to_string(prop.minor));
+  xv_model* m = new xv_model();
+  m->topo = t;
+  m->device = device;
+  m->num_sms = prop.multiProcessorCount;
+  m->layers.resize(t.n_frame_layers);
+  int prev = t.feat_dim;
+  for (int i = 0; i < t.n_frame_layers; ++i) {
+    FrameLayer& L = m->layers[i];
+    L.taps = t.taps[i];
+    L.dilation = t.dilation[i];
+    L.c_in = prev;
+    L.c_out = t.width[i];
+    if (i == 0) {                          // spliced (im2col) input: dense K, padded to a multiple of 64
+      L.c_in_pad = prev;
+      L.k_total = int(round_up(int64_t(L.taps) * prev, tdnn::BLOCK_K));
+      L.gemm_taps = 1;
+      m->k0_pad = L.k_total;
+    } else {
+      L.c_in_pad = prev;                   // widths are multiples of 256, hence of 64
+      L.k_total = L.taps * prev;
+      L.gemm_taps = L.taps;
+      m->gap = std::max(m->gap, (L.taps - 1) / 2 * L.dilation);
+    }
+    if (i < t.n_frame_layers - 1) m->w_mid = std::max(m->w_mid, L.c_out);
+    prev = L.c_out;
+  }
+  m->gap = std::max(m->gap, 1);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+    delete m;
+    return fail(XV_ECUDA, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  }
+  m->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  e = cudaFuncSetAttribute(tdnn::tdnn_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn::SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaMalloc(&m->overflow_dev, 4);
+  if (e == cudaSuccess) e = cudaMemset(m->overflow_dev, 0, 4);
+  if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&m->overflow_host), 4, cudaHostAllocDefault);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    std::string msg = std::string("xv_create: ") + cudaGetErrorName(e) + ": " + cudaGetErrorString(e);
+    xv_destroy(m);
+    return fail(XV_ECUDA, msg);
+  }
+  *out = m;
+  return XV_OK;
+}
+
+void xv_destroy(xv_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  cudaDeviceSynchronize();
+  free_layers(m);
+  for (int s = 0; s < META_SLOTS; ++s) {
+    if (m->meta_host[s]) cudaFreeHost(m->meta_host[s]);
+    if (m->meta_event[s]) cudaEventDestroy(m->meta_event[s]);
+  }
+  cudaFree(m->overflow_dev);
+  if (m->overflow_host) cudaFreeHost(m->overflow_host);
+  cudaFree(m->feats_dev); cudaFree(m->emb_dev); cudaFree(m->ws_dev);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+int xv_set_param(xv_model* m, const char* tf_var_name, const float* host, const int64_t* shape, int32_t rank) {
+  if (!m || !tf_var_name || !host || !shape || rank < 1 || rank > 3) return fail(XV_EINVAL, "bad argument");
+  const std::string name(tf_var_name);
+  const xv_topology& t = m->topo;
+  std::vector<int64_t> want;
+  bool used = false, known = false;
+  auto scope_of = [&](const std::string& prefix, int& idx, std::string& leaf) {
+    if (name.compare(0, prefix.size(), prefix) != 0) return false;
+    const size_t slash = name.find('/', prefix.size());
+    if (slash == std::string::npos) return false;
+    try { idx = std::stoi(name.substr(prefix.size(), slash - prefix.size())); } catch (...) { return false; }
+    leaf = name.substr(slash + 1);
+    return true;
+  };
+  int idx = -1;
+  std::string leaf;
+  if (scope_of("frame_level_info_layer-", idx, leaf)) {
+    if (idx < 0 || idx >= t.n_frame_layers) return fail(XV_EINVAL, "no such frame layer: " + name);
+    const FrameLayer& L = m->layers[idx];
+    known = used = true;
+    if (leaf == "w:0") want = {L.taps, L.c_in, L.c_out};
+    else if (leaf == "b:0" || leaf == "gamma:0" || leaf == "beta:0" || leaf == "mean:0" || leaf == "variance:0") want = {L.c_out};
+    else known = used = false;
+  } else if (scope_of("embed_layer-", idx, leaf)) {
+    known = true;
+    if (idx == 0 && leaf == "w:0") { used = true; want = {2 * t.width[t.n_frame_layers - 1], t.emb_dim}; }
+    else if (idx == 0 && leaf == "b:0") { used = true; want = {t.emb_dim}; }
+  } else if (name.compare(0, 7, "output/") == 0 || name.compare(0, 10, "attention/") == 0) {
+    known = true;
+  }
+  if (!known) return fail(XV_EINVAL, "unknown variable name: " + name);
+  if (!used) return XV_OK;                   // training-only variable: not read by the extraction path
+  if (int(want.size()) != rank || !std::equal(want.begin(), want.end(), shape)) {
+    std::string got = "[", exp = "[";
+    for (int i = 0; i < rank; ++i) got += std::to_string(shape[i]) + (i + 1 < rank ? "," : "]");
+    for (size_t i = 0; i < want.size(); ++i) exp += std::to_string(want[i]) + (i + 1 < want.size() ? "," : "]");
+    return fail(XV_EINVAL, "shape mismatch for " + name + ": got " + got + ", expected " + exp);
+  }
+  size_t n = 1;
+  for (int i = 0; i < rank; ++i) n *= size_t(shape[i]);
+  for (size_t i = 0; i < n; ++i)
+    if (!(host[i] == host[i]) || host[i] > 3.0e38f || host[i] < -3.0e38f) return fail(XV_EINVAL, "non-finite value in " + name);
+  m->host_params[name].assign(host, host + n);
+  m->host_shapes[name].assign(shape, shape + rank);
+  m->dirty = true;
+  return XV_OK;
+}
+
+size_t xv_workspace_bytes(const xv_model* m, int64_t total_frames, int32_t n_seg) {
+  if (!m || total_frames <= 0 || n_seg <= 0) return 0;
+  return make_plan(m, total_frames, n_seg).bytes;
+}
+
+int xv_forward(xv_model* m, const float* feats_dev, const int32_t* seg_len_host, int32_t n_seg, float* emb_dev,
+               void* workspace_dev, size_t workspace_bytes, void* stream) {
+  return forward_impl(m, feats_dev, seg_len_host, n_seg, emb_dev, workspace_dev, workspace_bytes,
+                      static_cast<cudaStream_t>(stream), nullptr, nullptr);
+}
+
+int xv_forward_layers(xv_model* m, const float* feats_dev, const int32_t* seg_len_host, int32_t n_seg, float* emb_dev,
+                      void* workspace_dev, size_t workspace_bytes, void* stream, float* const* layer_out_dev,
+                      float* stats_out_dev) {
+  return forward_impl(m, feats_dev, seg_len_host, n_seg, emb_dev, workspace_dev, workspace_bytes,
+                      static_cast<cudaStream_t>(stream), layer_out_dev, stats_out_dev);
+}
+
+int xv_extract_host(xv_model* m, const float* feats_host, const int32_t* seg_len_host, int32_t n_seg, float* emb_host) {
+  if (!m || !feats_host || !seg_len_host || !emb_host) return fail(XV_EINVAL, "null argument");
+  if (n_seg <= 0) return fail(XV_EINVAL, "n_seg must be >= 1");
+  XV_CUDA(cudaSetDevice(m->device));
+  int64_t total = 0;
+  for (int i = 0; i < n_seg; ++i) {
+    if (seg_len_host[i] <= 0) return fail(XV_EINVAL, "segment " + std::to_string(i) + " has non-positive length");
+    total += seg_len_host[i];
+  }
+  const size_t feat_bytes = size_t(total) * m->topo.feat_dim * 4;
+  const size_t emb_bytes = size_t(n_seg) * m->topo.emb_dim * 4;
+  const size_t ws_bytes = xv_workspace_bytes(m, total, n_seg);
+  auto grow = [&](void** p, size_t* cap, size_t need) -> cudaError_t {
+    if (need <= *cap) return cudaSuccess;
+    cudaStreamSynchronize(m->stream);
+    cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    const size_t want = need + need / 4;
+    cudaError_t e = cudaMalloc(p, want);
+    if (e == cudaSuccess) *cap = want;
+    return e;
+  };
+  XV_CUDA(grow(reinterpret_cast<void**>(&m->feats_dev), &m->feats_cap, feat_bytes));
+  XV_CUDA(grow(reinterpret_cast<void**>(&m->emb_dev), &m->emb_cap, emb_bytes));
+  XV_CUDA(grow(&m->ws_dev, &m->ws_cap, ws_bytes));
+  XV_CUDA(cudaMemcpyAsync(m->feats_dev, feats_host, feat_bytes, cudaMemcpyHostToDevice, m->stream));
+  int rc = forward_impl(m, m->feats_dev, seg_len_host, n_seg, m->emb_dev, m->ws_dev, m->ws_cap, m->stream, nullptr, nullptr);
+  if (rc != XV_OK) return rc;
+  XV_CUDA(cudaMemcpyAsync(emb_host, m->emb_dev, emb_bytes, cudaMemcpyDeviceToHost, m->stream));
+  XV_CUDA(cudaMemcpyAsync(m->overflow_host, m->overflow_dev, 4, cudaMemcpyDeviceToHost, m->stream));
+  XV_CUDA(cudaStreamSynchronize(m->stream));
+  if (*m->overflow_host != 0) {
+    XV_CUDA(cudaMemsetAsync(m->overflow_dev, 0, 4, m->stream));
+    return fail(XV_EOVERFLOW, "an activation exceeded the fp16 range (|x| > 65504); results are not trustworthy");
+  }
+  return XV_OK;
+}
+
+int xv_check_overflow(xv_model* m, void* stream) {
+  if (!m) return fail(XV_EINVAL, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  XV_CUDA(cudaSetDevice(m->device));
+  XV_CUDA(cudaMemcpyAsync(m->overflow_host, m->overflow_dev, 4, cudaMemcpyDeviceToHost, s));
+  XV_CUDA(cudaStreamSynchronize(s));
+  if (*m->overflow_host != 0) {
+    XV_CUDA(cudaMemsetAsync(m->overflow_dev, 0, 4, s));
+    return fail(XV_EOVERFLOW, "an activation exceeded the fp16 range (|x| > 65504); results are not trustworthy");
+  }
+  return XV_OK;
+}
+
+int32_t xv_last_launch_count(const xv_model* m) { return m ? m->last_launches : 0; }
+
+int xv_set_option(xv_model* m, const char* name, int64_t value) {
+  if (!m || !name) return fail(XV_EINVAL, "null argument");
+  const std::string n(name);
+  if (n == "reuse_taps") m->opt_reuse = value != 0;
+  else if (n == "desc_base_offset") m->opt_desc_base_offset = value != 0;
+  else return fail(XV_EINVAL, "unknown option: " + n);
+  return XV_OK;
+}
+
+}  // extern "C"

@@ -355,3 +355,52 @@ def write_mat(file_or_fd, m, key=""):
     finally:
         if fd is not file_or_fd:
             fd.close()
+
+
+# --------------------------------------------------------------------------------------
+# native "ark,scp:" writer (what `| copy-vector ark:- ark,scp:A,S` does in the recipe,
+# extract_xvectors.sh:76,86 -- without needing the Kaldi binary)
+
+class ArkScpWriter(object):
+    """Writes a float-vector ark and the scp that indexes it (``key ark_path:offset`` where
+    offset is the byte position of the ``\\0B`` binary marker, as Kaldi's TableWriter emits)."""
+
+    mode = "wb"
+
+    def __init__(self, ark_path, scp_path, scp_ark_name=None):
+        self.ark = open(ark_path, "wb")
+        self.scp = open(scp_path, "wt")
+        self.name = scp_ark_name if scp_ark_name is not None else ark_path
+        self.pos = 0
+
+    def write_vec_entries(self, keys, vectors):
+        blobs, lines = [], []
+        for key, v in zip(keys, vectors):
+            blob = vec_flt_entry_bytes(v, key)
+            lines.append("%s %s:%d\n" % (key, self.name, self.pos + len(key) + 1))
+            self.pos += len(blob)
+            blobs.append(blob)
+        self.ark.write(b"".join(blobs))
+        self.scp.write("".join(lines))
+
+    def close(self):
+        self.ark.close()
+        self.scp.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def open_vector_writer(wspecifier):
+    """``ark,scp:A,S`` / ``scp,ark:S,A`` (no pipe) -> ArkScpWriter; anything else -> open_or_fd."""
+    spec = wspecifier.strip()
+    if spec.startswith("ark,scp:") and "|" not in spec:
+        ark, scp = spec[8:].split(",")
+        return ArkScpWriter(ark, scp)
+    if spec.startswith("scp,ark:") and "|" not in spec:
+        scp, ark = spec[8:].split(",")
+        return ArkScpWriter(ark, scp)
+    return open_or_fd(wspecifier, "wb")
