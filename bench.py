@@ -1,0 +1,446 @@
+#!/usr/bin/env python
+"""bench.py -- x-vector extraction frames/s on B200 (BASELINE.json metric), one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's sm_100a path
+    python bench.py --impl reference [--steps K] [--warmup W]      # the reference's CPU path
+
+A *step* is one pass of the extraction hot path (pack -> 5 fused tcgen05 TDNN layers -> pooling +
+embed_layer-0) over one batch of synthetic MFCC: BASELINE.json configs[1], 256 utterances x 400
+frames x 23 ceps per GPU (weak scaling: every rank gets its own batch; for N > 1 the step ends
+with the NCCL gather of the [256, 512] embeddings to rank 0, the only collective on the path).
+
+  value  frames/s with the features already resident in HBM (CUDA events around each step on the
+         launching stream, L2 flushed between steps, max over ranks).
+  e2e    frames/s through the reference-facing C-ABI call xv_extract_host (the sess.run
+         boundary, reference local/tf/models.py:412-415): pinned HOST features in, HOST
+         embeddings out, H2D + D2H inside the timed region.
+  roofline      the fused TDNN layer kernel (5 launches/step) against the measured tensor peak;
+                per-launch figures for all 7 launches in roofline.launches.
+  cpu_baseline  the reference's CPU path restated in torch fp32 (oracle/xvector_torch_cpu.py --
+                TensorFlow 1.x cannot be installed here), run the way the reference runs it: one
+                utterance per call, 2 threads per process, cores/2 processes
+                (models.py:361-363,410-414; extract_xvectors.sh:63,83).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "xvector_extraction_frames_per_sec"
+UNIT = "frames/s"
+FEAT_DIM = 23
+EMB_DIM = 512
+L2_FLUSH_BYTES = 512 << 20            # > 126 MB L2
+
+TOPOLOGIES = {   # reference local/tf/models.py:443-445 and :545-548
+    "ModelWithoutDropoutTdnn": dict(kernel_sizes=[5, 3, 3, 1, 1], dilations=[1, 2, 3, 1, 1],
+                                    layer_sizes=[512, 512, 512, 512, 1536], embedding_sizes=[512, 512]),
+    "ModelWithoutDropout": dict(kernel_sizes=[5, 5, 7, 1, 1], dilations=[1, 1, 1, 1, 1],
+                                layer_sizes=[512, 512, 512, 512, 1536], embedding_sizes=[512, 512]),
+}
+
+
+def flop_per_frame(topo):
+    """Algorithmic FLOP per frame of each frame layer (2 x taps x C_in x C_out)."""
+    out, prev = [], FEAT_DIM
+    for k, w in zip(topo["kernel_sizes"], topo["layer_sizes"]):
+        out.append(2 * k * prev * w)
+        prev = w
+    return out
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=float(p["hbm_gbs"]), tflops=float(p["bf16_tflops"]),
+                    tflops_sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), source="measured")
+    return dict(hbm_gbs=6650.0, tflops=1590.0, tflops_sustained=1400.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------------ clocks
+BAD_REASONS = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and clock-event reasons of one GPU through NVML while a region runs."""
+    BITS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+            0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, cuda_index, period=0.004):
+        super().__init__(daemon=True)
+        self.period = period
+        self.samples, self.reasons = [], set()
+        self.sm_max = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            import torch
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(cuda_index).uuid)
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(cuda_index)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:      # clocks are evidence, not the product: report why they are missing
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = int(get_reasons(self.h))
+                for bit, name in self.BITS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def finish(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join()
+        if not self.ok or not self.samples:
+            return dict(sm_mhz=None, sm_max_mhz=self.sm_max, reasons=[], note=getattr(self, "err", "no samples"))
+        return dict(sm_mhz=int(statistics.median(self.samples)), sm_max_mhz=self.sm_max,
+                    reasons=sorted(self.reasons), samples=len(self.samples))
+
+
+def clocks_rejected(c):
+    if any(r in BAD_REASONS for r in c.get("reasons", [])):
+        return True
+    if c.get("sm_mhz") and c.get("sm_max_mhz") and not c.get("reasons") and c["sm_mhz"] < 0.6 * c["sm_max_mhz"]:
+        return True        # stuck low with no reason: a leftover clock lock
+    return False
+
+
+# ------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from xvector_b200 import _native, synthetic
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs one process per GPU: launch with python -m torch.distributed.run "
+                             "--nnodes=1 --nproc-per-node %d --master-addr 127.0.0.1 bench.py --gpus %d ..." %
+                             (args.gpus, args.gpus, args.gpus))
+        raise SystemExit("WORLD_SIZE=%d does not match --gpus %d" % (world, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py measures the sm_100a path: no CUDA device is visible (there is no CPU fallback; "
+                         "use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=dev)
+
+    topo = TOPOLOGIES[args.topology]
+    params = synthetic.make_params(topo["kernel_sizes"], topo["layer_sizes"], topo["embedding_sizes"],
+                                   weight_set=args.weight_set)
+    eng = _native.XvecEngine(topo["kernel_sizes"], topo["dilations"], topo["layer_sizes"], EMB_DIM, FEAT_DIM,
+                             device=local_rank)
+    eng.set_params(params)
+    if args.reuse_taps is not None:
+        eng.set_option("reuse_taps", args.reuse_taps)
+        eng.set_option("desc_base_offset", 0 if args.reuse_taps else 1)
+
+    B, T = args.batch, args.frames
+    lens = np.full(B, T, np.int32)
+    frames = int(lens.sum())
+    feats_np = synthetic.mfcc_batch(2 + 1000 * rank, lens)             # configs[1]: seed 2 (rank 0)
+    feats_host = torch.empty((frames, FEAT_DIM), dtype=torch.float32, pin_memory=True)
+    feats_host.numpy()[:] = feats_np
+    emb_host = torch.empty((B, EMB_DIM), dtype=torch.float32, pin_memory=True)
+    feats_dev = feats_host.to(dev)
+    emb_dev = torch.empty((B, EMB_DIM), dtype=torch.float32, device=dev)
+    gathered = [torch.empty_like(emb_dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def step_resident():
+        eng.forward(feats_dev, lens, emb_dev=emb_dev, stream=stream)
+        if world > 1:
+            dist.gather(emb_dev, gathered, dst=0)
+
+    def step_e2e():
+        eng.extract_host(feats_host, lens, emb_host)                   # H2D + kernels + D2H + sync
+        if world > 1:
+            emb_dev.copy_(emb_host, non_blocking=True)
+            dist.gather(emb_dev, gathered, dst=0)
+            if rank == 0:
+                gathered[-1].cpu()
+            torch.cuda.synchronize(dev)
+
+    def timed_resident(steps):
+        barrier(); torch.cuda.synchronize(dev)
+        sampler = ClockSampler(local_rank); sampler.start()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for s, e in evs:
+            flush.zero_()                                              # evict L2 between steps (untimed)
+            s.record(stream)
+            step_resident()
+            e.record(stream)
+        torch.cuda.synchronize(dev); barrier()
+        clocks = sampler.finish()
+        ms = [s.elapsed_time(e) for s, e in evs]
+        return ms, clocks
+
+    def timed_e2e(steps):
+        barrier(); torch.cuda.synchronize(dev)
+        ms = []
+        for _ in range(steps):
+            flush.zero_()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            step_e2e()
+            ms.append((time.perf_counter() - t0) * 1e3)
+        torch.cuda.synchronize(dev); barrier()
+        return ms
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up, then the timed regions ------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    torch.cuda.synchronize(dev)
+    eng.check_overflow()
+    ms, clocks = timed_resident(args.steps)
+    remeasured = False
+    if clocks_rejected(clocks):
+        remeasured = True
+        ms, clocks = timed_resident(args.steps)
+    total_ms = max_over_ranks(sum(ms))
+    ms_per_step = total_ms / args.steps
+    value = world * frames / (ms_per_step * 1e-3)
+
+    for _ in range(max(args.warmup, 3)):
+        step_e2e()
+    e2e_ms = timed_e2e(args.steps)
+    e2e_total = max_over_ranks(sum(e2e_ms))
+    e2e_value = world * frames * args.steps / (e2e_total * 1e-3)
+
+    # ---- per-launch durations (CUDA events on the launching stream, inside the library) -------
+    eng.set_option("profile", 1)
+    per_launch = []
+    for _ in range(3):
+        step_resident()
+    for _ in range(min(args.steps, 50)):
+        flush.zero_()
+        eng.forward(feats_dev, lens, emb_dev=emb_dev, stream=stream)
+        per_launch.append(eng.last_kernel_ms())
+    eng.set_option("profile", 0)
+    launches_per_step = eng.last_launch_count
+    kms = np.asarray(per_launch, dtype=np.float64).mean(axis=0)        # [7]
+    peaks = load_peaks()
+    fl = flop_per_frame(topo)
+    names = ["pack_im2col_kernel"] + ["tdnn_layer_kernel[L%d]" % i for i in range(len(fl))] + ["pool_embed_kernel"]
+    c_last = topo["layer_sizes"][-1]
+    k0_pad = -(-topo["kernel_sizes"][0] * FEAT_DIM // 64) * 64
+    launches = []
+    for i, name in enumerate(names):
+        d = dict(kernel=name, ms=round(float(kms[i]), 5))
+        if name.startswith("tdnn"):
+            li = i - 1
+            tf = frames * fl[li] / (kms[i] * 1e-3) / 1e12
+            d.update(bound="tensor", achieved=round(tf, 1), unit="TFLOP/s", frac=round(tf / peaks["tflops"], 4))
+        else:
+            if name.startswith("pack"):       # fp32 features in, fp16 spliced rows + row map out
+                nbytes = frames * (FEAT_DIM * 4 + k0_pad * 2 + 1)
+            else:                             # fp16 [frames, 1536] in, W0 once, embeddings out
+                nbytes = frames * c_last * 2 + 2 * c_last * EMB_DIM * 4 + B * EMB_DIM * 4
+            gbs = nbytes / (kms[i] * 1e-3) / 1e9
+            d.update(bound="hbm", achieved=round(gbs, 1), unit="GB/s", frac=round(gbs / peaks["hbm_gbs"], 4))
+        launches.append(d)
+    tdnn_ms = float(kms[1:1 + len(fl)].sum())
+    tdnn_tf = frames * sum(fl) / (tdnn_ms * 1e-3) / 1e12
+    roofline = dict(kernel="tdnn_layer_kernel (%d launches/step, figures are per-step sums / averages)" % len(fl),
+                    bound="tensor", achieved=round(tdnn_tf, 1), peak=peaks["tflops"], unit="TFLOP/s",
+                    frac=round(tdnn_tf / peaks["tflops"], 4), traffic=None,
+                    peak_source="%s bf16/fp16 burst (MEASURED_PEAKS.json)" % peaks["source"],
+                    share_of_step=round(tdnn_ms / float(kms.sum()), 4),
+                    step_frac_of_tensor_peak=round(value / world * sum(fl) / 1e12 / peaks["tflops"], 4),
+                    launches=launches)
+
+    out = dict(metric=METRIC, value=round(value, 1), unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+               ms_per_step=round(ms_per_step, 5), higher_is_better=True, scaling="weak", vs_baseline=None,
+               dtype="f16", data="synthetic",
+               config=dict(workload="configs[1]: batch=%d utterances x %d frames x %d-dim MFCC per GPU, %s (%s), "
+                                    "weight set %s" % (B, T, FEAT_DIM, args.topology,
+                                                       "taps %s dil %s" % (topo["kernel_sizes"], topo["dilations"]),
+                                                       args.weight_set),
+                           frames_per_step_per_gpu=frames, l2="flushed between steps (%d MiB write)" % (L2_FLUSH_BYTES >> 20),
+                           parallelism="utterance sharding x%d, NCCL gather to rank 0" % world if world > 1 else "single GPU",
+                           arithmetic="fp16 operands (RN), fp32 accumulate (tcgen05 kind::f16), fp32 epilogue/pooling"),
+               e2e=dict(value=round(e2e_value, 1), unit=UNIT, h2d_bytes_per_step=frames * FEAT_DIM * 4 + B * 3 * 4,
+                        d2h_bytes_per_step=B * EMB_DIM * 4 + 4, ms_per_step=round(e2e_total / args.steps, 5),
+                        api="xv_extract_host (pinned host buffers)"),
+               gpu_launches=int(launches_per_step * args.steps),
+               clocks=clocks, roofline=roofline)
+    if remeasured:
+        out["clocks"]["note"] = "first measurement rejected (throttle reason / low clocks); this is the re-measurement"
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline_subprocess(args)
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+
+
+def cpu_baseline_subprocess(args):
+    """The CPU leg runs in a fresh interpreter (it forks worker processes; this one holds a CUDA context)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1",
+           "--topology", args.topology, "--weight-set", args.weight_set, "--frames", str(args.frames),
+           "--step-seconds", "4"]
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+        line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+        return json.loads(line)["cpu_baseline"]
+    except Exception as e:
+        return dict(value=None, unit=UNIT, cores=None, kind="port", sample="failed: %r" % (e,))
+
+
+# ------------------------------------------------------------------------------------ reference arm
+def _cpu_worker(wid, params, topology, feats, n_utts_max, frames, ready, go, done, counts, threads):
+    import torch
+    from oracle.xvector_torch_cpu import TorchCpuXvector
+    torch.set_num_threads(threads)
+    net = TorchCpuXvector(params, topology)
+    net.forward(feats[:frames])                                        # warm-up (oneDNN primitive creation)
+    while True:
+        ready.wait()
+        n = go.value
+        if n <= 0:
+            return
+        for u in range(n):
+            off = ((wid * 7 + u) % n_utts_max) * frames
+            net.forward(feats[off:off + frames])                       # ONE utterance per call (models.py:410-414)
+        counts[wid] = n
+        done.wait()
+
+
+def run_reference(args):
+    """Times the reference's CPU extraction path.  TensorFlow 1.x is not installable here, so the
+    timed code is the torch fp32 restatement under oracle/ ("port"), run in the reference's own
+    operating mode: B=1 per call, 2 threads per process, cores/2 processes."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from xvector_b200 import synthetic
+    topo = TOPOLOGIES[args.topology]
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 2)
+    threads = 2
+    procs = max(1, min(cores // threads, 64))
+    params = synthetic.make_params(topo["kernel_sizes"], topo["layer_sizes"], topo["embedding_sizes"],
+                                   weight_set=args.weight_set)
+    frames = args.frames
+    n_utts_max = 16
+    feats = synthetic.mfcc_batch(2, np.full(n_utts_max, frames, np.int32))
+    ctx = mp.get_context("fork")
+    ready, done = ctx.Barrier(procs + 1), ctx.Barrier(procs + 1)
+    go = ctx.Value("i", 0)
+    counts = ctx.Array("i", procs)
+    workers = [ctx.Process(target=_cpu_worker, args=(w, params, args.topology, feats, n_utts_max, frames, ready,
+                                                     go, done, counts, threads), daemon=True) for w in range(procs)]
+    for w in workers:
+        w.start()
+
+    def one_step(n):
+        go.value = n
+        ready.wait()
+        t0 = time.perf_counter()
+        done.wait()
+        return time.perf_counter() - t0
+
+    t1 = one_step(1)                                                   # calibrate: seconds per utterance per process
+    n_per = int(max(1, min(512, round(args.step_seconds / max(t1, 1e-4)))))
+    for _ in range(max(args.warmup - 1, 0)):
+        one_step(n_per)
+    times = [one_step(n_per) for _ in range(args.steps)]
+    go.value = 0
+    ready.wait()
+    for w in workers:
+        w.join(timeout=10)
+    step_frames = procs * n_per * frames
+    total = sum(times)
+    value = step_frames * args.steps / total
+    sample = ("%d steps x %d processes x %d utterances of %d frames, one utterance per call, %d threads/process"
+              % (args.steps, procs, n_per, frames, threads))
+    cb = dict(value=round(value, 1), unit=UNIT, cores=procs * threads, kind="port", sample=sample,
+              host_cores_visible=cores,
+              note="torch-CPU fp32 restatement of the reference forward (TensorFlow 1.x absent: oracle/README in DESIGN.md)")
+    out = dict(metric=METRIC, impl="reference", value=round(value, 1), unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+               warmup=args.warmup, ms_per_step=round(total / args.steps * 1e3, 3), higher_is_better=True,
+               scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+               config=dict(workload="configs[1] sample: %d-frame x %d-dim MFCC utterances, %s, weight set %s"
+                                    % (frames, FEAT_DIM, args.topology, args.weight_set),
+                           frames_per_step=step_frames),
+               cpu_baseline=cb,
+               e2e=dict(value=round(value, 1), unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+               gpu_launches=0)
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--topology", choices=sorted(TOPOLOGIES), default="ModelWithoutDropoutTdnn")
+    ap.add_argument("--weight-set", choices=["A", "B"], default="B")
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--frames", type=int, default=400)
+    ap.add_argument("--reuse-taps", type=int, default=None, help="override the library's tap-addressing mode (0/1)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--step-seconds", type=float, default=1.5, help="reference arm: CPU seconds per step (calibrated)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -108,8 +108,16 @@ int xv_check_overflow(xv_model* m, void* stream);
  * "gpu_launches" claim). */
 int32_t xv_last_launch_count(const xv_model* m);
 
+/* With option "profile" = 1 every kernel launch of a forward is bracketed by a CUDA event pair
+ * on the launching stream; this returns the number of launches of the last forward and writes
+ * their device durations (ms, launch order: pack, frame layers 0..n-1, pool+embed) into
+ * ms_out[0..cap).  Synchronises on the last event.  Negative XV_E* on error.  (The reference has
+ * only wall-clock deltas around sess.run, models.py:413-417.) */
+int32_t xv_last_kernel_ms(xv_model* m, float* ms_out, int32_t cap);
+
 /* Tuning knob for experiments: 0 = one TMA box per (tap, channel chunk); 1 = load each
- * activation slab once and address every tap inside it (default chosen by the library). */
+ * activation slab once and address every tap inside it (default chosen by the library).
+ * Options: "reuse_taps", "desc_base_offset", "profile". */
 int xv_set_option(xv_model* m, const char* name, int64_t value);
 
 const char* xv_last_error(void);

@@ -87,6 +87,8 @@ def load_library():
     lib.xv_check_overflow.restype = ctypes.c_int
     lib.xv_last_launch_count.argtypes = [P]
     lib.xv_last_launch_count.restype = I32
+    lib.xv_last_kernel_ms.argtypes = [P, ctypes.POINTER(ctypes.c_float), I32]
+    lib.xv_last_kernel_ms.restype = I32
     lib.xv_set_option.argtypes = [P, ctypes.c_char_p, I64]
     lib.xv_set_option.restype = ctypes.c_int
     lib.xv_last_error.argtypes = []
@@ -99,7 +101,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = ["xv_create", "xv_destroy", "xv_set_param", "xv_workspace_bytes", "xv_forward",
                     "xv_forward_layers", "xv_extract_host", "xv_check_overflow", "xv_last_launch_count",
-                    "xv_set_option", "xv_last_error", "xv_version"]
+                    "xv_last_kernel_ms", "xv_set_option", "xv_last_error", "xv_version"]
 
 
 def _check(lib, rc):
@@ -210,6 +212,15 @@ class XvecEngine:
         eptr = emb_host.data_ptr() if hasattr(emb_host, "data_ptr") else emb_host.ctypes.data
         _check(self.lib, self.lib.xv_extract_host(self.handle, fptr, lens.ctypes.data_as(ctypes.c_void_p), n_seg, eptr))
         return emb_host
+
+    def last_kernel_ms(self):
+        """Device duration (ms) of every launch of the last forward (option ``profile`` must be 1);
+        order: pack, frame layers 0..n-1, pool+embed."""
+        buf = (ctypes.c_float * 32)()
+        n = int(self.lib.xv_last_kernel_ms(self.handle, buf, 32))
+        if n < 0:
+            _check(self.lib, n)
+        return [float(buf[i]) for i in range(min(n, 32))]
 
     @property
     def last_launch_count(self):

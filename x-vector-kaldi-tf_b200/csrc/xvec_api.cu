@@ -91,6 +91,9 @@ struct xv_model {
   // options
   int opt_reuse = 0;
   int opt_desc_base_offset = 1;
+  int opt_profile = 0;               // 1: bracket every kernel launch with CUDA events (bench / diagnostics)
+  std::vector<cudaEvent_t> prof_events;   // 2 per launch, in launch order
+  int prof_used = 0;
 };
 
 namespace {
@@ -217,6 +220,18 @@ int ensure_meta_capacity(xv_model* m, int64_t n_seg) {
   return XV_OK;
 }
 
+// Profiling (opt_profile): an event pair around every launch, on the launching stream.
+int prof_mark(xv_model* m, cudaStream_t stream) {
+  if (!m->opt_profile) return XV_OK;
+  if (m->prof_used == int(m->prof_events.size())) {
+    cudaEvent_t e;
+    XV_CUDA(cudaEventCreate(&e));
+    m->prof_events.push_back(e);
+  }
+  XV_CUDA(cudaEventRecord(m->prof_events[m->prof_used++], stream));
+  return XV_OK;
+}
+
 int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_host, int32_t n_seg, float* emb_dev,
                  void* workspace_dev, size_t workspace_bytes, cudaStream_t stream, float* const* layer_out_dev,
                  float* stats_out_dev) {
@@ -267,6 +282,8 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
   __half* hb = reinterpret_cast<__half*>(ws + p.off_hb);
   __half* hlast = reinterpret_cast<__half*>(ws + p.off_hlast);
   int launches = 0;
+  m->prof_used = 0;
+#define XV_PROF() do { int prc_ = prof_mark(m, stream); if (prc_ != XV_OK) return prc_; } while (0)
 
   // ---- pack: fp32 features -> spliced fp16 packed rows + row map ---------------------------
   {
@@ -284,7 +301,9 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
     a.n_counters = p.n_groups;
     const int blocks = int(std::max<int64_t>(p.r_pad / xvk::PACK_ROWS_PER_BLOCK,
                                              (p.n_groups + xvk::PACK_THREADS - 1) / xvk::PACK_THREADS));
+    XV_PROF();
     xvk::pack_im2col_kernel<<<blocks, xvk::PACK_THREADS, 0, stream>>>(a);
+    XV_PROF();
     XV_CUDA(cudaGetLastError());
     ++launches;
   }
@@ -324,7 +343,9 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
     a.overflow_flag = m->overflow_dev;
     const int64_t tiles = int64_t(a.n_m_tiles) * a.n_n_tiles;
     const int grid = int(std::min<int64_t>(tiles, m->num_sms));
+    XV_PROF();
     tdnn::tdnn_layer_kernel<<<grid, tdnn::NUM_THREADS, tdnn::SMEM_BYTES, stream>>>(ta, tw, tc, a);
+    XV_PROF();
     XV_CUDA(cudaGetLastError());
     ++launches;
     if (layer_out_dev && layer_out_dev[i]) {
@@ -351,11 +372,14 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
     a.stats_out = stats_out_dev;
     a.var_eps = m->topo.var_eps;
     dim3 grid(p.n_groups, p.n_slabs);
+    XV_PROF();
     xvk::pool_embed_kernel<<<grid, xvk::POOL_THREADS, 0, stream>>>(a);
+    XV_PROF();
     XV_CUDA(cudaGetLastError());
     ++launches;
   }
   m->last_launches = launches;
+#undef XV_PROF
   return XV_OK;
 }
 
@@ -448,6 +472,7 @@ void xv_destroy(xv_model* m) {
     if (m->meta_host[s]) cudaFreeHost(m->meta_host[s]);
     if (m->meta_event[s]) cudaEventDestroy(m->meta_event[s]);
   }
+  for (cudaEvent_t e : m->prof_events) cudaEventDestroy(e);
   cudaFree(m->overflow_dev);
   if (m->overflow_host) cudaFreeHost(m->overflow_host);
   cudaFree(m->feats_dev); cudaFree(m->emb_dev); cudaFree(m->ws_dev);
@@ -574,11 +599,23 @@ int xv_check_overflow(xv_model* m, void* stream) {
 
 int32_t xv_last_launch_count(const xv_model* m) { return m ? m->last_launches : 0; }
 
+int32_t xv_last_kernel_ms(xv_model* m, float* ms_out, int32_t cap) {
+  if (!m || !ms_out || cap < 0) return fail(XV_EINVAL, "bad argument");
+  if (!m->opt_profile) return fail(XV_ESTATE, "option 'profile' is off");
+  const int n = m->prof_used / 2;
+  if (n == 0) return 0;
+  XV_CUDA(cudaSetDevice(m->device));
+  XV_CUDA(cudaEventSynchronize(m->prof_events[m->prof_used - 1]));
+  for (int i = 0; i < n && i < cap; ++i) XV_CUDA(cudaEventElapsedTime(ms_out + i, m->prof_events[2 * i], m->prof_events[2 * i + 1]));
+  return n;
+}
+
 int xv_set_option(xv_model* m, const char* name, int64_t value) {
   if (!m || !name) return fail(XV_EINVAL, "null argument");
   const std::string n(name);
   if (n == "reuse_taps") m->opt_reuse = value != 0;
   else if (n == "desc_base_offset") m->opt_desc_base_offset = value != 0;
+  else if (n == "profile") m->opt_profile = value != 0;
   else return fail(XV_EINVAL, "unknown option: " + n);
   return XV_OK;
 }
