@@ -4,8 +4,8 @@
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's sm_100a path
     python bench.py --impl reference [--steps K] [--warmup W]      # the reference's CPU path
 
-A *step* is one pass of the extraction hot path (pack -> 5 fused tcgen05 TDNN layers -> pooling +
-embed_layer-0) over one batch of synthetic MFCC: BASELINE.json configs[1], 256 utterances x 400
+A *step* is one pass of the extraction hot path (pack -> 5 fused tcgen05 TDNN layers, the last one pooling in its epilogue ->
+pool finalize + embed_layer-0) over one batch of synthetic MFCC: BASELINE.json configs[1], 256 utterances x 400
 frames x 23 ceps per GPU (weak scaling: every rank gets its own batch; for N > 1 the step ends
 with the NCCL gather of the [256, 512] embeddings to rank 0, the only collective on the path).
 
@@ -166,9 +166,8 @@ def run_b200(args):
     eng = _native.XvecEngine(topo["kernel_sizes"], topo["dilations"], topo["layer_sizes"], EMB_DIM, FEAT_DIM,
                              device=local_rank)
     eng.set_params(params)
-    if args.reuse_taps is not None:
-        eng.set_option("reuse_taps", args.reuse_taps)
-        eng.set_option("desc_base_offset", 0 if args.reuse_taps else 1)
+    if args.pipeline is not None:
+        eng.set_option("pipeline", args.pipeline)
 
     B, T = args.batch, args.frames
     lens = np.full(B, T, np.int32)
@@ -268,7 +267,7 @@ def run_b200(args):
     kms = np.asarray(per_launch, dtype=np.float64).mean(axis=0)        # [7]
     peaks = load_peaks()
     fl = flop_per_frame(topo)
-    names = ["pack_im2col_kernel"] + ["tdnn_layer_kernel[L%d]" % i for i in range(len(fl))] + ["pool_embed_kernel"]
+    names = ["pack_im2col_kernel"] + ["tdnn_pair_kernel[L%d]" % i for i in range(len(fl))] + ["pool_finalize_embed_kernel"]
     c_last = topo["layer_sizes"][-1]
     k0_pad = -(-topo["kernel_sizes"][0] * FEAT_DIM // 64) * 64
     launches = []
@@ -281,14 +280,14 @@ def run_b200(args):
         else:
             if name.startswith("pack"):       # fp32 features in, fp16 spliced rows + row map out
                 nbytes = frames * (FEAT_DIM * 4 + k0_pad * 2 + 1)
-            else:                             # fp16 [frames, 1536] in, W0 once, embeddings out
-                nbytes = frames * c_last * 2 + 2 * c_last * EMB_DIM * 4 + B * EMB_DIM * 4
+            else:                             # per-32-row-block partial sums in, W0 once, embeddings out
+                nbytes = B * (-(-T // 32)) * 2 * c_last * 4 + 2 * c_last * EMB_DIM * 4 + B * EMB_DIM * 4
             gbs = nbytes / (kms[i] * 1e-3) / 1e9
             d.update(bound="hbm", achieved=round(gbs, 1), unit="GB/s", frac=round(gbs / peaks["hbm_gbs"], 4))
         launches.append(d)
     tdnn_ms = float(kms[1:1 + len(fl)].sum())
     tdnn_tf = frames * sum(fl) / (tdnn_ms * 1e-3) / 1e12
-    roofline = dict(kernel="tdnn_layer_kernel (%d launches/step, figures are per-step sums / averages)" % len(fl),
+    roofline = dict(kernel="tdnn_pair_kernel (%d launches/step, figures are per-step sums / averages)" % len(fl),
                     bound="tensor", achieved=round(tdnn_tf, 1), peak=peaks["tflops"], unit="TFLOP/s",
                     frac=round(tdnn_tf / peaks["tflops"], 4), traffic=None,
                     peak_source="%s bf16/fp16 burst (MEASURED_PEAKS.json)" % peaks["source"],
@@ -432,7 +431,7 @@ def main():
     ap.add_argument("--weight-set", choices=["A", "B"], default="B")
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--frames", type=int, default=400)
-    ap.add_argument("--reuse-taps", type=int, default=None, help="override the library's tap-addressing mode (0/1)")
+    ap.add_argument("--pipeline", type=int, default=None, help="library kernel generation (diagnostics; default: newest)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--step-seconds", type=float, default=1.5, help="reference arm: CPU seconds per step (calibrated)")
     args = ap.parse_args()

@@ -7,6 +7,9 @@
 //   pool_embed_kernel  : statistics pooling (tf.nn.moments over time + sqrt(var + 1e-5), concat;
 //                        reference models.py:485-486) fused with the first segment-level affine
 //                        layer embed_layer-0 (tf.nn.xw_plus_b, models.py:495) = the x-vector.
+//   pool_finalize_embed_kernel : the production form of the above: combines the per-32-row-block
+//                        partial sums written by the last frame layer's epilogue (the [frames,1536]
+//                        activation is never materialised), then the same embed_layer-0 product.
 //   unpack_rows_kernel : debug/parity only: fp16 packed rows -> fp32 [total_frames, C].
 #pragma once
 #include <cuda_fp16.h>
@@ -32,8 +35,10 @@ __device__ __forceinline__ int find_segment(const int32_t* __restrict__ row_star
   return lo - 1;
 }
 
-constexpr int PACK_ROWS_PER_BLOCK = 16;
+constexpr int PACK_ROWS_PER_BLOCK = 32;      // = one aligned pooling block: rows of ONE segment (or gap)
 constexpr int PACK_THREADS = 256;
+constexpr int PACK_MAX_STAGE_FLOATS = 4096; // (32 + 2*halo0) * feat_dim floats staged per CTA
+constexpr int PACK_MAX_K0 = 512;
 
 struct PackArgs {
   const float* feats;        // [total_frames, D]
@@ -43,54 +48,71 @@ struct PackArgs {
   int32_t k0_pad;            // multiple of 64
   __half* x0;                // [r_pad, k0_pad]
   uint8_t* row_valid;        // [r_pad]
-  uint32_t* counters;        // [n_counters] zeroed here for pool_embed_kernel
+  uint8_t* blk_valid;        // [r_pad / 32] valid rows of each aligned 32-row block
+  uint32_t* counters;        // [n_counters] zeroed here for pool_finalize_embed_kernel
   int32_t n_counters;
 };
 
+// One CTA per aligned 32-row block.  The block's feature rows (plus the first layer's context)
+// are staged in shared memory with coalesced loads; out-of-segment rows are staged as zeros,
+// which is TF's SAME padding (models.py:476).  Each thread then emits 16-byte pieces of the
+// spliced fp16 rows through a per-column lookup table (tap offset, ceps index).
 __global__ void __launch_bounds__(PACK_THREADS) pack_im2col_kernel(const PackArgs a) {
-  __shared__ int s_seg[PACK_ROWS_PER_BLOCK], s_t[PACK_ROWS_PER_BLOCK];
+  __shared__ float s_feat[PACK_MAX_STAGE_FLOATS];
+  __shared__ int16_t s_lut[PACK_MAX_K0];
+  __shared__ int s_info[3];                          // segment, first frame of the block, valid rows
   const int r0 = blockIdx.x * PACK_ROWS_PER_BLOCK;
   const int gtid = blockIdx.x * PACK_THREADS + threadIdx.x;
   if (gtid < a.n_counters) a.counters[gtid] = 0u;
-  if (threadIdx.x < PACK_ROWS_PER_BLOCK) {
-    const int r = r0 + threadIdx.x;
-    int seg = -1, t = 0;
-    if (r < a.r_pad) {
-      const int s = find_segment(a.seg.row_start, a.seg.n_seg, r);
-      if (s >= 0) {
-        t = r - __ldg(a.seg.row_start + s);
-        if (t < __ldg(a.seg.len + s)) seg = s;
-      }
-      a.row_valid[r] = seg >= 0 ? 1 : 0;
+  if (r0 >= a.r_pad) return;
+  const int D = a.feat_dim;
+  const int halo = ((a.taps - 1) >> 1) * a.dilation;
+  if (threadIdx.x == 0) {
+    const int s = find_segment(a.seg.row_start, a.seg.n_seg, r0);
+    int t0 = 0, nv = 0;
+    if (s >= 0) {
+      t0 = r0 - __ldg(a.seg.row_start + s);
+      nv = max(0, min(PACK_ROWS_PER_BLOCK, __ldg(a.seg.len + s) - t0));
     }
-    s_seg[threadIdx.x] = seg;
-    s_t[threadIdx.x] = t;
+    s_info[0] = s; s_info[1] = t0; s_info[2] = nv;
+    a.blk_valid[blockIdx.x] = uint8_t(nv);
+  }
+  const int k_real = a.taps * D;
+  for (int ch = threadIdx.x; ch < a.k0_pad; ch += PACK_THREADS) {
+    const int j = ch / D, c = ch - j * D;
+    s_lut[ch] = (ch < k_real) ? int16_t(j * a.dilation * D + c) : int16_t(-1);
   }
   __syncthreads();
-  const int pairs = a.k0_pad >> 1;
-  const int half_ctx = (a.taps - 1) >> 1;
-  const int k_real = a.taps * a.feat_dim;
-  for (int idx = threadIdx.x; idx < PACK_ROWS_PER_BLOCK * pairs; idx += PACK_THREADS) {
-    const int lr = idx / pairs, pr = idx - lr * pairs;
-    const int r = r0 + lr;
-    if (r >= a.r_pad) break;
-    const int seg = s_seg[lr];
-    float v[2] = {0.f, 0.f};
-    if (seg >= 0) {
-      const int t = s_t[lr];
-      const int len = __ldg(a.seg.len + seg);
-      const int64_t fs = __ldg(a.seg.feat_start + seg);
+  const int seg = s_info[0], t0 = s_info[1], nv = s_info[2];
+  if (threadIdx.x < PACK_ROWS_PER_BLOCK) a.row_valid[r0 + threadIdx.x] = threadIdx.x < nv ? 1 : 0;
+  const int pieces = a.k0_pad >> 3;                                   // 16-byte pieces per row
+  if (nv == 0) {                                                      // gap / tail block: zero rows
+    for (int idx = threadIdx.x; idx < PACK_ROWS_PER_BLOCK * pieces; idx += PACK_THREADS)
+      reinterpret_cast<uint4*>(a.x0 + int64_t(r0) * a.k0_pad)[idx] = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
+  const int len = __ldg(a.seg.len + seg);
+  const int64_t fs = __ldg(a.seg.feat_start + seg);
+  const int stage_rows = PACK_ROWS_PER_BLOCK + 2 * halo;              // frames t0-halo .. t0+31+halo
+  for (int idx = threadIdx.x; idx < stage_rows * D; idx += PACK_THREADS) {
+    const int sr = idx / D;
+    const int tt = t0 - halo + sr;
+    s_feat[idx] = (tt >= 0 && tt < len) ? __ldg(a.feats + (fs + tt) * D + (idx - sr * D)) : 0.f;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < PACK_ROWS_PER_BLOCK * pieces; idx += PACK_THREADS) {
+    const int lr = idx / pieces, pc = idx - lr * pieces;
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    if (lr < nv) {
+      const float* src = s_feat + lr * D;
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int ch = 2 * pr + e;
-        if (ch < k_real) {
-          const int j = ch / a.feat_dim, c = ch - j * a.feat_dim;
-          const int tt = t + (j - half_ctx) * a.dilation;     // SAME padding: outside the segment -> 0
-          if (tt >= 0 && tt < len) v[e] = __ldg(a.feats + (fs + tt) * a.feat_dim + c);
-        }
+      for (int e = 0; e < 4; ++e) {
+        const int l0 = s_lut[pc * 8 + 2 * e], l1 = s_lut[pc * 8 + 2 * e + 1];
+        const __half2 h = __floats2half2_rn(l0 >= 0 ? src[l0] : 0.f, l1 >= 0 ? src[l1] : 0.f);
+        w[e] = *reinterpret_cast<const uint32_t*>(&h);
       }
     }
-    reinterpret_cast<__half2*>(a.x0 + int64_t(r) * a.k0_pad)[pr] = __floats2half2_rn(v[0], v[1]);
+    reinterpret_cast<uint4*>(a.x0 + int64_t(r0 + lr) * a.k0_pad)[pc] = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -230,6 +252,121 @@ __global__ void __launch_bounds__(POOL_THREADS) pool_embed_kernel(const PoolArgs
       for (int o = tid; o < E; o += POOL_THREADS) {
         float sum = __ldg(a.b0 + o);
         for (int s = 0; s < n_slabs; ++s) sum += __ldcg(a.partial + (int64_t(s) * a.seg.n_seg + g0 + gi) * E + o);
+        a.emb[int64_t(g0 + gi) * E + o] = sum;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Second half of statistics pooling + embed_layer-0, fed by the per-block partial sums that the
+// last frame layer's epilogue (tdnn_pair_kernel mode 1) wrote:
+//   partial[block][0][c] = sum of y over the block's valid rows, partial[block][1][c] = sum of y*y.
+// The blocks of a segment are combined in a fixed order in fp64 (mean = S1/n, var = S2/n - mean^2:
+// population variance, tf.nn.moments; std = sqrt(var + 1e-5), models.py:485-486), then
+// stats @ W0 + b0 (tf.nn.xw_plus_b, models.py:495) exactly as pool_embed_kernel does.
+struct FinalizeArgs {
+  const float* partial;       // [r_pad/32][2][C]
+  SegMeta seg;
+  int32_t channels;           // C (multiple of 128)
+  int32_t emb_dim;            // E (multiple of 256, <= 1024)
+  int32_t group;              // segments per CTA, 1..POOL_MAX_G
+  const float* w0;            // [2C, E]  embed_layer-0/w
+  const float* b0;            // [E]
+  float* fc_partial;          // [n_slabs, n_seg, E]
+  uint32_t* counters;         // [n_groups], zero on entry
+  float* emb;                 // [n_seg, E]
+  float* stats_out;           // optional [n_seg, 2C]
+  float var_eps;
+};
+
+__global__ void __launch_bounds__(POOL_THREADS) pool_finalize_embed_kernel(const FinalizeArgs a) {
+  __shared__ double s_sum[2][POOL_SLAB];                        // S1 | S2 of the current segment
+  __shared__ float s_stats[POOL_MAX_G][2 * POOL_SLAB];          // mean | std per segment
+  __shared__ int s_last;
+  const int tid = threadIdx.x;
+  const int g0 = blockIdx.x * a.group;
+  const int n_in_group = min(a.group, a.seg.n_seg - g0);
+  const int slab = blockIdx.y, n_slabs = gridDim.y;
+  const int c0 = slab * POOL_SLAB;
+  const int C = a.channels, E = a.emb_dim;
+  const int which = tid >> 7, cl = tid & (POOL_SLAB - 1);       // threads 0..127: S1, 128..255: S2
+
+  for (int gi = 0; gi < n_in_group; ++gi) {
+    const int seg = g0 + gi;
+    const int len = __ldg(a.seg.len + seg);
+    const int blk0 = __ldg(a.seg.row_start + seg) >> 5;
+    const int n_blk = (len + 31) >> 5;
+    const float* p = a.partial + (int64_t(blk0) * 2 + which) * C + c0 + cl;
+    double acc = 0.0;
+    int b = 0;
+    for (; b + 4 <= n_blk; b += 4) {                            // 4 independent loads in flight, fixed order
+      const float x0 = __ldg(p + int64_t(b) * 2 * C), x1 = __ldg(p + int64_t(b + 1) * 2 * C);
+      const float x2 = __ldg(p + int64_t(b + 2) * 2 * C), x3 = __ldg(p + int64_t(b + 3) * 2 * C);
+      acc += double(x0); acc += double(x1); acc += double(x2); acc += double(x3);
+    }
+    for (; b < n_blk; ++b) acc += double(__ldg(p + int64_t(b) * 2 * C));
+    __syncthreads();                                            // s_sum free (previous segment consumed)
+    s_sum[which][cl] = acc;
+    __syncthreads();
+    if (tid < POOL_SLAB) {
+      const double inv_n = 1.0 / double(len);
+      const double mean = s_sum[0][tid] * inv_n;
+      const double var = fmax(s_sum[1][tid] * inv_n - mean * mean, 0.0);   // population variance (tf.nn.moments)
+      const float sd = float(sqrt(var + double(a.var_eps)));               // models.py:486
+      s_stats[gi][tid] = float(mean);
+      s_stats[gi][POOL_SLAB + tid] = sd;
+      if (a.stats_out != nullptr) {
+        a.stats_out[int64_t(seg) * 2 * C + c0 + tid] = float(mean);
+        a.stats_out[int64_t(seg) * 2 * C + C + c0 + tid] = sd;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- embed_layer-0 partial product for this channel slab -------------------------------
+  const int ept = E / POOL_THREADS;                             // outputs per thread
+  float acc[POOL_MAX_G][POOL_MAX_EPT];
+#pragma unroll
+  for (int gi = 0; gi < POOL_MAX_G; ++gi)
+#pragma unroll
+    for (int i = 0; i < POOL_MAX_EPT; ++i) acc[gi][i] = 0.f;
+#pragma unroll 4
+  for (int r = 0; r < 2 * POOL_SLAB; ++r) {
+    const int wrow = (r < POOL_SLAB) ? (c0 + r) : (C + c0 + r - POOL_SLAB);     // mean rows, then std rows
+    const float* wp = a.w0 + int64_t(wrow) * E + tid;
+    float w[POOL_MAX_EPT];
+#pragma unroll
+    for (int i = 0; i < POOL_MAX_EPT; ++i) w[i] = (i < ept) ? __ldg(wp + i * POOL_THREADS) : 0.f;
+#pragma unroll
+    for (int gi = 0; gi < POOL_MAX_G; ++gi) {
+      if (gi < n_in_group) {
+        const float s = s_stats[gi][r];
+#pragma unroll
+        for (int i = 0; i < POOL_MAX_EPT; ++i) acc[gi][i] = fmaf(s, w[i], acc[gi][i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int gi = 0; gi < POOL_MAX_G; ++gi) {
+    if (gi < n_in_group) {
+#pragma unroll
+      for (int i = 0; i < POOL_MAX_EPT; ++i)
+        if (i < ept) a.fc_partial[(int64_t(slab) * a.seg.n_seg + g0 + gi) * E + tid + i * POOL_THREADS] = acc[gi][i];
+    }
+  }
+
+  // ---- the last CTA of the group sums the slabs in a fixed order (deterministic) ------------
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(a.counters + blockIdx.x, 1u) == uint32_t(n_slabs - 1));
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int gi = 0; gi < n_in_group; ++gi) {
+      for (int o = tid; o < E; o += POOL_THREADS) {
+        float sum = __ldg(a.b0 + o);
+        for (int s = 0; s < n_slabs; ++s) sum += __ldcg(a.fc_partial + (int64_t(s) * a.seg.n_seg + g0 + gi) * E + o);
         a.emb[int64_t(g0 + gi) * E + o] = sum;
       }
     }

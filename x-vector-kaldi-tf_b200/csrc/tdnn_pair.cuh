@@ -1,0 +1,354 @@
+// tdnn_pair.cuh -- the fused frame-level TDNN layer kernel, CTA-pair edition (sm_100a).
+//
+// Replaces, for a whole batch of segments at once, the five TensorFlow ops the reference runs per
+// layer (local/tf/models.py:476-480: conv1d/convolution SAME -> bias_add -> relu ->
+// batch_norm_wrapper(eval)), and for the LAST frame layer also the first half of statistics
+// pooling (tf.nn.moments over time, models.py:485) -- so the [frames, 1536] activation of the last
+// layer never touches HBM.
+//
+// Data layout ("packed rows"): all segments are stacked along the row axis of one [R_pad, C]
+// fp16 matrix.  A segment starts at a row that is a multiple of 32 and is followed by >= gap
+// all-zero rows (gap >= largest half-context (k-1)/2*d), so a tap reaching outside its segment
+// reads zeros -- TF's SAME padding -- and every aligned 32-row block holds rows of ONE segment.
+//
+// One tile = 256 activation rows x 256 output channels, computed by a CTA PAIR (cluster of 2,
+// tcgen05 cta_group::2, UMMA 256x256x16): CTA r stages activation rows [r*128, r*128+128) and
+// weight rows (channels) [r*128, r*128+128) of the tile -- half the operand bytes per SM of a
+// single-CTA 128x256 tile -- the leader issues the MMAs, completion is multicast to both CTAs.
+//   mode 0 (store):  A = activations (M = rows), B = weights.  TMEM lane = row; the epilogue
+//                    applies relu(acc+b)*scale+shift, zeroes gap rows, converts to fp16 and
+//                    TMA-stores [32 rows x 32 ch] boxes per warp.
+//   mode 1 (pool):   operands swapped: A = weights (M = channels), B = activations.  TMEM lane =
+//                    channel and the 32 registers of one tcgen05.ld are 32 consecutive FRAMES of
+//                    that channel, so the per-block sum / sum of squares is a private register
+//                    reduction (no shuffles, fixed order -> bit-reproducible).  Output:
+//                    partial[block][{sum,sumsq}][channel] fp32, one aligned 32-row block each.
+// Temporal taps: the activation slab [136 rows x 64 ch] is loaded ONCE per channel chunk and tap
+// j is addressed by advancing the UMMA descriptor start by j*d rows (reuse = 1); for half
+// contexts > 4 rows one box per tap is loaded instead (reuse = 0).
+//
+// Warp roles (320 threads): warp 0 = TMA producer (both CTAs), warp 1 = TMEM allocator (both) +
+// MMA issuer (leader), warps 2..9 = epilogue (TMEM lane quarter = warp % 4, column half =
+// (warp-2)/4).  Pipelines: activation ring, weight ring (full barriers in the leader, empty
+// barriers per CTA), double-buffered 128x256 fp32 accumulators in TMEM.
+#pragma once
+#include "ptx.cuh"
+
+namespace tdnn2 {
+
+constexpr int TILE_ROWS = 256;                     // activation rows per tile (pair)
+constexpr int TILE_CH = 256;                       // output channels per tile (pair)
+constexpr int CTA_ROWS = 128;
+constexpr int CTA_CH = 128;
+constexpr int BLOCK_K = 64;                        // fp16 elements = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int ACT_BOX_ROWS_PLAIN = CTA_ROWS;
+constexpr int ACT_BOX_ROWS_REUSE = CTA_ROWS + 8;   // supports half contexts <= 4 rows
+constexpr int MAX_REUSE_HALO = 4;
+constexpr int ACT_STAGE_BYTES = ACT_BOX_ROWS_REUSE * 128;   // 17408
+constexpr int WGT_STAGE_BYTES = CTA_CH * 128;               // 16384
+constexpr int RING_BYTES = 184320;                 // activation + weight rings (carved at run time)
+constexpr int MAX_STAGES = 8;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_THREADS = NUM_EPI_WARPS * 32;
+constexpr int NUM_THREADS = 64 + NUM_EPI_THREADS;  // 320
+constexpr int C_CHUNK = 32;                        // output columns per epilogue step
+constexpr int C_BUF_BYTES = 32 * C_CHUNK * 2;      // 2048: one warp's [32 rows x 32 ch] fp16 box
+constexpr int TMEM_COLS = 512;                     // 2 accumulators x 256 fp32 columns
+constexpr int POOL_BLOCK = 32;                     // rows per pooled partial block
+
+constexpr int OFF_RING = 0;
+constexpr int OFF_C = OFF_RING + RING_BYTES;
+constexpr int OFF_PARAMS = OFF_C + NUM_EPI_WARPS * 2 * C_BUF_BYTES;     // + 32768
+constexpr int OFF_BARS = OFF_PARAMS + 2 * 3 * TILE_CH * 4;              // + 6144
+constexpr int NUM_BARS = 4 * MAX_STAGES + 4;
+constexpr int OFF_TMEM_PTR = OFF_BARS + NUM_BARS * 8;
+constexpr int SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;                    // + slack for 1024-byte alignment
+static_assert(RING_BYTES % 1024 == 0 && OFF_C % 1024 == 0, "swizzled stages must be 1024-byte aligned");
+static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of dynamic shared memory");
+
+struct PairArgs {
+  int32_t n_row_tiles;      // R_pad / 256
+  int32_t n_ch_tiles;       // C_out / 256
+  int32_t c_chunks;         // C_in_pad / 64
+  int32_t taps;
+  int32_t dilation;
+  int32_t c_in_pad;         // column stride between taps in the packed weight matrix
+  int32_t reuse;            // 0 / 1 (see header comment)
+  int32_t n_act_stages;     // n_act * 17408 + n_wgt * 16384 <= RING_BYTES
+  int32_t n_wgt_stages;
+  int32_t mode;             // 0 store, 1 pool
+  int32_t c_out;
+  const float* bias;        // [C_out]  conv bias b
+  const float* scale;       // [C_out]  gamma * rsqrt(var + eps)
+  const float* shift;       // [C_out]  beta - mean * scale
+  const uint8_t* row_valid; // [R_pad]     mode 0: 1 = row belongs to a segment, 0 = gap / tail
+  const uint8_t* blk_valid; // [R_pad/32]  mode 1: valid rows in the block (they are its first rows)
+  float* partial;           // [R_pad/32][2][C_out]  mode 1
+  uint32_t* overflow_flag;  // set to 1 if an fp16 output overflowed to inf
+};
+
+// One tcgen05.ld chunk of the store epilogue: 32 channels of one row -> 16 packed half2.
+__device__ __forceinline__ void epi_store_math(const uint32_t (&v)[32], const float* s_bias, const float* s_scale,
+                                               const float* s_shift, int c, bool valid, uint32_t (&p)[16],
+                                               uint32_t& hmax) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c + g * 4);
+    const float4 s4 = *reinterpret_cast<const float4*>(s_scale + c + g * 4);
+    const float4 h4 = *reinterpret_cast<const float4*>(s_shift + c + g * 4);
+    // relu(acc + b) * inv + shift      (models.py:477-480, tf_block.py:26)
+    const float y0 = fmaf(fmaxf(__uint_as_float(v[g * 4 + 0]) + b4.x, 0.f), s4.x, h4.x);
+    const float y1 = fmaf(fmaxf(__uint_as_float(v[g * 4 + 1]) + b4.y, 0.f), s4.y, h4.y);
+    const float y2 = fmaf(fmaxf(__uint_as_float(v[g * 4 + 2]) + b4.z, 0.f), s4.z, h4.z);
+    const float y3 = fmaf(fmaxf(__uint_as_float(v[g * 4 + 3]) + b4.w, 0.f), s4.w, h4.w);
+    const uint32_t p0 = ptx::pack_half2(y0, y1), p1 = ptx::pack_half2(y2, y3);
+    hmax = ptx::habs2_max(ptx::habs2_max(hmax, p0), p1);
+    p[g * 2 + 0] = valid ? p0 : 0u;                  // gap rows stay exact zeros
+    p[g * 2 + 1] = valid ? p1 : 0u;
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations in  [R_pad, C_in_pad] fp16
+                 const __grid_constant__ CUtensorMap tmap_wgt,   // weights [C_out, taps*C_in_pad] fp16 (K-major)
+                 const __grid_constant__ CUtensorMap tmap_out,   // activations out [R_pad, C_out] fp16 (mode 0)
+                 const PairArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t smem_base = ptx::smem_u32(smem);
+  const uint32_t sAct = smem_base + OFF_RING;
+  const uint32_t sWgt = sAct + uint32_t(args.n_act_stages) * ACT_STAGE_BYTES;   // 17408 = 17 * 1024: stays aligned
+  const uint32_t bar0 = smem_base + OFF_BARS;
+  auto act_full = [&](uint32_t s) { return bar0 + 8u * s; };
+  auto act_empty = [&](uint32_t s) { return bar0 + 8u * (MAX_STAGES + s); };
+  auto wgt_full = [&](uint32_t s) { return bar0 + 8u * (2 * MAX_STAGES + s); };
+  auto wgt_empty = [&](uint32_t s) { return bar0 + 8u * (3 * MAX_STAGES + s); };
+  auto t_full = [&](uint32_t s) { return bar0 + 8u * (4 * MAX_STAGES + s); };
+  auto t_empty = [&](uint32_t s) { return bar0 + 8u * (4 * MAX_STAGES + 2 + s); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM_PTR);
+
+  const int warp = threadIdx.x >> 5;          // warp-uniform
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int n_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_act);
+    ptx::prefetch_tmap(&tmap_wgt);
+    if (args.mode == 0) ptx::prefetch_tmap(&tmap_out);
+    for (uint32_t s = 0; s < MAX_STAGES; ++s) {
+      ptx::mbar_init(act_full(s), 1); ptx::mbar_init(act_empty(s), 1);
+      ptx::mbar_init(wgt_full(s), 1); ptx::mbar_init(wgt_empty(s), 1);
+    }
+    for (uint32_t s = 0; s < 2; ++s) { ptx::mbar_init(t_full(s), 1); ptx::mbar_init(t_empty(s), 2 * NUM_EPI_WARPS); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_2sm(ptx::smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), TMEM_COLS);
+    ptx::tmem_relinquish_2sm();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();                    // barrier inits + TMEM allocation visible to both CTAs
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int total_tiles = args.n_row_tiles * args.n_ch_tiles;
+  const int half_ctx = (args.taps - 1) >> 1;
+  const int halo = half_ctx * args.dilation;
+  const bool reuse = args.reuse != 0;
+  const uint32_t act_box_bytes = (reuse ? ACT_BOX_ROWS_REUSE : ACT_BOX_ROWS_PLAIN) * 128u;
+  const uint32_t n_act = uint32_t(args.n_act_stages), n_wgt = uint32_t(args.n_wgt_stages);
+
+  if (warp == 0) {
+    // ============================ TMA producer (one thread per CTA) ====================
+    if (lane == 0) {
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;       // stage index / phase of each ring
+      const uint32_t act_full_leader = ptx::mapa_cluster(act_full(0), 0);   // transaction bytes are counted there
+      const uint32_t wgt_full_leader = ptx::mapa_cluster(wgt_full(0), 0);
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+        const int r0 = (tile / args.n_ch_tiles) * TILE_ROWS + int(rank) * CTA_ROWS;
+        const int c0 = (tile % args.n_ch_tiles) * TILE_CH + int(rank) * CTA_CH;
+        for (int cc = 0; cc < args.c_chunks; ++cc) {
+          for (int j = 0; j < args.taps; ++j) {
+            if (!reuse || j == 0) {
+              ptx::mbar_wait(act_empty(sa), pa ^ 1u);
+              if (leader) ptx::mbar_arrive_expect_tx(act_full(sa), 2u * act_box_bytes);   // both CTAs' boxes
+              const int row = reuse ? (r0 - halo) : (r0 + (j - half_ctx) * args.dilation);
+              ptx::tma_load_2d_2sm(sAct + sa * ACT_STAGE_BYTES, &tmap_act, act_full_leader + 8u * sa, cc * BLOCK_K, row);
+              if (++sa == n_act) { sa = 0; pa ^= 1u; }
+            }
+            ptx::mbar_wait(wgt_empty(sb), pb ^ 1u);
+            if (leader) ptx::mbar_arrive_expect_tx(wgt_full(sb), 2u * WGT_STAGE_BYTES);
+            ptx::tma_load_2d_2sm(sWgt + sb * WGT_STAGE_BYTES, &tmap_wgt, wgt_full_leader + 8u * sb,
+                                 j * args.c_in_pad + cc * BLOCK_K, c0);
+            if (++sb == n_wgt) { sb = 0; pb ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer (leader CTA, one thread) ==================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16_f32(TILE_ROWS, TILE_CH);   // 256 x 256 either orientation
+      const bool swapped = args.mode == 1;
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
+        const uint32_t acc = it & 1u;
+        ptx::mbar_wait_cluster(t_empty(acc), ((it >> 1) & 1u) ^ 1u);   // both CTAs' epilogues drained it
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * TILE_CH;
+        uint32_t accumulate = 0;
+        for (int cc = 0; cc < args.c_chunks; ++cc) {
+          for (int j = 0; j < args.taps; ++j) {
+            if (!reuse || j == 0) ptx::mbar_wait(act_full(sa), pa);
+            ptx::mbar_wait(wgt_full(sb), pb);
+            ptx::tc_fence_after();
+            const uint32_t act_addr = sAct + sa * ACT_STAGE_BYTES + (reuse ? uint32_t(j * args.dilation) * 128u : 0u);
+            const uint32_t wgt_addr = sWgt + sb * WGT_STAGE_BYTES;
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              // base-offset bits stay 0: the hardware swizzles on absolute smem address bits, which
+              // is what lets a tap start at any 128-byte row of the slab
+              const uint64_t d_act = ptx::make_sw128_kmajor_desc(act_addr + k * (UMMA_K * 2)) & ~(0x7ull << 49);
+              const uint64_t d_wgt = ptx::make_sw128_kmajor_desc(wgt_addr + k * (UMMA_K * 2)) & ~(0x7ull << 49);
+              if (swapped) ptx::umma_f16_2sm(d_tmem, d_wgt, d_act, idesc, accumulate);
+              else ptx::umma_f16_2sm(d_tmem, d_act, d_wgt, idesc, accumulate);
+              accumulate = 1;
+            }
+            ptx::umma_commit_2sm(wgt_empty(sb));                       // weight slot free in both CTAs
+            if (++sb == n_wgt) { sb = 0; pb ^= 1u; }
+            if (!reuse || j == args.taps - 1) {
+              ptx::umma_commit_2sm(act_empty(sa));
+              if (++sa == n_act) { sa = 0; pa ^= 1u; }
+            }
+          }
+        }
+        ptx::umma_commit_2sm(t_full(acc));                             // accumulator ready in both CTAs
+      }
+    }
+  } else {
+    // ============================ epilogue (8 warps per CTA) ===========================
+    const int e = warp - 2;                          // 0..7
+    const int q = warp & 3;                          // TMEM lane quarter this warp may read
+    const int colh = e >> 2;                         // which 128-column half of the accumulator
+    const int te = threadIdx.x - 64;                 // 0..255
+    const uint32_t t_empty_leader = ptx::mapa_cluster(t_empty(0), 0);   // + 8 * acc
+    uint32_t it = 0;
+    if (args.mode == 0) {
+      float* s_par = reinterpret_cast<float*>(smem + OFF_PARAMS);
+      const uint32_t sC = smem_base + OFF_C + uint32_t(e) * 2 * C_BUF_BYTES;
+      const uint32_t swz = (uint32_t(lane) >> 1) & 3u;   // SWIZZLE_64B phase of this row in the staging box
+      uint32_t hmax = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
+        const uint32_t acc = it & 1u;
+        const int r_cta = (tile / args.n_ch_tiles) * TILE_ROWS + int(rank) * CTA_ROWS;
+        const int ch0 = (tile % args.n_ch_tiles) * TILE_CH;
+        float* s_bias = s_par + acc * 3 * TILE_CH;
+        float* s_scale = s_bias + TILE_CH;
+        float* s_shift = s_scale + TILE_CH;
+        s_bias[te] = __ldg(args.bias + ch0 + te);
+        s_scale[te] = __ldg(args.scale + ch0 + te);
+        s_shift[te] = __ldg(args.shift + ch0 + te);
+        const bool valid = args.row_valid[r_cta + q * 32 + lane] != 0;
+        ptx::named_bar_sync(1, NUM_EPI_THREADS);       // parameters of this tile visible (double-buffered by acc)
+        ptx::mbar_wait(t_full(acc), (it >> 1) & 1u);
+        ptx::tc_fence_after();
+        const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * TILE_CH + uint32_t(colh) * 128u;
+        uint32_t v[2][32];
+        ptx::tmem_ld_32x32(t_row, v[0]);
+#pragma unroll
+        for (int chunk = 0; chunk < 4; ++chunk) {
+          ptx::tmem_ld_wait_dep(v[chunk & 1]);
+          if (chunk < 3) {
+            ptx::tmem_ld_32x32(t_row + (chunk + 1) * C_CHUNK, v[(chunk + 1) & 1]);
+          } else {                                   // all of this warp's loads done: hand the accumulator back
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(t_empty_leader + 8u * acc);
+          }
+          uint32_t p[16];
+          epi_store_math(v[chunk & 1], s_bias, s_scale, s_shift, colh * 128 + chunk * C_CHUNK, valid, p, hmax);
+          const uint32_t buf = sC + uint32_t(chunk & 1) * C_BUF_BYTES;
+          if (lane == 0) ptx::tma_store_wait_read<1>();   // the store that last used this buffer has read it
+          __syncwarp();
+          const uint32_t dst = buf + uint32_t(lane) * (C_CHUNK * 2);
+#pragma unroll
+          for (uint32_t c16 = 0; c16 < 4; ++c16) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((c16 ^ swz) << 4)),
+                         "r"(p[c16 * 4 + 0]), "r"(p[c16 * 4 + 1]), "r"(p[c16 * 4 + 2]), "r"(p[c16 * 4 + 3])
+                         : "memory");
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&tmap_out, buf, ch0 + colh * 128 + chunk * C_CHUNK, r_cta + q * 32);
+            ptx::tma_store_commit();
+          }
+        }
+      }
+      if (lane == 0) ptx::tma_store_wait_all<0>();
+      if ((hmax & 0x7fffu) >= 0x7c00u || ((hmax >> 16) & 0x7fffu) >= 0x7c00u) atomicOr(args.overflow_flag, 1u);
+    } else {
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
+        const uint32_t acc = it & 1u;
+        const int r_tile = (tile / args.n_ch_tiles) * TILE_ROWS;
+        const int ch = (tile % args.n_ch_tiles) * TILE_CH + int(rank) * CTA_CH + q * 32 + lane;
+        const float b = __ldg(args.bias + ch), sc = __ldg(args.scale + ch), sh = __ldg(args.shift + ch);
+        const int blk0 = (r_tile + colh * 128) / POOL_BLOCK;
+        const uint32_t nv4 = *reinterpret_cast<const uint32_t*>(args.blk_valid + blk0);   // 4 blocks, 1 byte each
+        ptx::mbar_wait(t_full(acc), (it >> 1) & 1u);
+        ptx::tc_fence_after();
+        const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * TILE_CH + uint32_t(colh) * 128u;
+        uint32_t v[2][32];
+        ptx::tmem_ld_32x32(t_row, v[0]);
+#pragma unroll
+        for (int chunk = 0; chunk < 4; ++chunk) {
+          ptx::tmem_ld_wait_dep(v[chunk & 1]);
+          if (chunk < 3) {
+            ptx::tmem_ld_32x32(t_row + (chunk + 1) * C_CHUNK, v[(chunk + 1) & 1]);
+          } else {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(t_empty_leader + 8u * acc);
+          }
+          const int nv = int((nv4 >> (8 * chunk)) & 0xffu);          // warp-uniform
+          if (nv > 0) {
+            float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+            if (nv >= POOL_BLOCK) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float y = fmaf(fmaxf(__uint_as_float(v[chunk & 1][i]) + b, 0.f), sc, sh);
+                s1[i & 3] += y;
+                s2[i & 3] = fmaf(y, y, s2[i & 3]);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                float y = fmaf(fmaxf(__uint_as_float(v[chunk & 1][i]) + b, 0.f), sc, sh);
+                y = (i < nv) ? y : 0.f;                              // rows past the segment end do not count
+                s1[i & 3] += y;
+                s2[i & 3] = fmaf(y, y, s2[i & 3]);
+              }
+            }
+            float* dst = args.partial + size_t(blk0 + chunk) * 2 * args.c_out + ch;
+            dst[0] = (s1[0] + s1[1]) + (s1[2] + s1[3]);
+            dst[args.c_out] = (s2[0] + s2[1]) + (s2[2] + s2[3]);
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();                    // the peer may still be reading our smem / signalling our barriers
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace tdnn2

@@ -16,6 +16,7 @@
 
 #include "pack_pool.cuh"
 #include "tdnn_layer.cuh"
+#include "tdnn_pair.cuh"
 
 namespace {
 
@@ -53,8 +54,8 @@ struct Plan {
   int32_t n_seg = 0;
   int64_t r_pad = 0;
   int32_t group = 1, n_groups = 0, n_slabs = 0;
-  size_t off_meta = 0, off_counters = 0, off_valid = 0, off_x0 = 0, off_ha = 0, off_hb = 0, off_hlast = 0,
-         off_partial = 0, bytes = 0;
+  size_t off_meta = 0, off_counters = 0, off_valid = 0, off_blk_valid = 0, off_x0 = 0, off_ha = 0, off_hb = 0,
+         off_hlast = 0, off_pool_partial = 0, off_partial = 0, bytes = 0;
 };
 
 constexpr int META_SLOTS = 4;
@@ -91,6 +92,8 @@ struct xv_model {
   // options
   int opt_reuse = 0;
   int opt_desc_base_offset = 1;
+  int opt_pipeline = 2;              // 2: CTA-pair kernels + pooled last layer; 1: first-generation single-CTA kernels
+  int num_clusters = 74;             // co-resident CTA pairs of tdnn_pair_kernel
   int opt_profile = 0;               // 1: bracket every kernel launch with CUDA events (bench / diagnostics)
   std::vector<cudaEvent_t> prof_events;   // 2 per launch, in launch order
   int prof_used = 0;
@@ -102,8 +105,9 @@ Plan make_plan(const xv_model* m, int64_t total_frames, int32_t n_seg) {
   Plan p;
   p.total_frames = total_frames;
   p.n_seg = n_seg;
-  const int64_t rows = m->gap + total_frames + int64_t(n_seg) * m->gap;
-  p.r_pad = round_up(std::max<int64_t>(rows, 1), tdnn::BLOCK_M);
+  // upper bound of the packed rows: every segment starts at a multiple of 32 and is followed by >= gap zero rows
+  const int64_t rows = total_frames + int64_t(n_seg) * (m->gap + tdnn2::POOL_BLOCK - 1);
+  p.r_pad = round_up(std::max<int64_t>(rows, 1), tdnn2::TILE_ROWS);
   const int c_last = m->topo.width[m->topo.n_frame_layers - 1];
   p.n_slabs = c_last / xvk::POOL_SLAB;
   p.group = int(std::min<int64_t>(xvk::POOL_MAX_G, std::max<int64_t>(1, n_seg / 64)));
@@ -113,10 +117,12 @@ Plan make_plan(const xv_model* m, int64_t total_frames, int32_t n_seg) {
   p.off_meta = take(size_t(3) * n_seg * 4);
   p.off_counters = take(size_t(p.n_groups) * 4);
   p.off_valid = take(size_t(p.r_pad));
+  p.off_blk_valid = take(size_t(p.r_pad / tdnn2::POOL_BLOCK));
   p.off_x0 = take(size_t(p.r_pad) * m->k0_pad * 2);
   p.off_ha = take(size_t(p.r_pad) * m->w_mid * 2);
   p.off_hb = take(size_t(p.r_pad) * m->w_mid * 2);
-  p.off_hlast = take(size_t(p.r_pad) * c_last * 2);
+  p.off_hlast = take(size_t(p.r_pad) * c_last * 2);          // only written by the debug / v1 paths
+  p.off_pool_partial = take(size_t(p.r_pad / tdnn2::POOL_BLOCK) * 2 * c_last * 4);
   p.off_partial = take(size_t(p.n_slabs) * n_seg * m->topo.emb_dim * 4);
   p.bytes = off;
   return p;
@@ -245,7 +251,7 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
     if (seg_len_host[i] <= 0) return fail(XV_EINVAL, "segment " + std::to_string(i) + " has non-positive length");
     total += seg_len_host[i];
   }
-  if (m->gap + total + int64_t(n_seg) * m->gap > (int64_t(1) << 31) - 4096)
+  if (total + int64_t(n_seg) * (m->gap + 32) > (int64_t(1) << 31) - 4096)
     return fail(XV_EINVAL, "batch too large: packed rows exceed int32 range");
   const Plan p = make_plan(m, total, n_seg);
   if (workspace_bytes < p.bytes)
@@ -253,54 +259,59 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
   if (reinterpret_cast<uintptr_t>(workspace_dev) % 1024 != 0) return fail(XV_EINVAL, "workspace must be 1024-byte aligned");
   uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
 
-  // ---- segment metadata: packed row starts, feature row starts, lengths ------------------
+  // ---- segment metadata: packed row starts (multiples of 32), feature row starts, lengths ----
   rc = ensure_meta_capacity(m, n_seg);
   if (rc != XV_OK) return rc;
   const int slot = m->meta_next;
   m->meta_next = (m->meta_next + 1) % META_SLOTS;
   XV_CUDA(cudaEventSynchronize(m->meta_event[slot]));      // previous copy out of this slot finished
   int32_t* mh = m->meta_host[slot];
+  int64_t rows_used = 0;
   {
-    int64_t row = m->gap, fs = 0;
+    int64_t row = 0, fs = 0;
     for (int i = 0; i < n_seg; ++i) {
       mh[i] = int32_t(row);
       mh[n_seg + i] = int32_t(fs);
       mh[2 * n_seg + i] = seg_len_host[i];
-      row += seg_len_host[i] + m->gap;
+      row += round_up(int64_t(seg_len_host[i]) + m->gap, tdnn2::POOL_BLOCK);
       fs += seg_len_host[i];
     }
+    rows_used = row;
   }
+  const int64_t r_pad = round_up(rows_used, tdnn2::TILE_ROWS);      // <= p.r_pad (the plan's upper bound)
   int32_t* meta_dev = reinterpret_cast<int32_t*>(ws + p.off_meta);
   XV_CUDA(cudaMemcpyAsync(meta_dev, mh, size_t(3) * n_seg * 4, cudaMemcpyHostToDevice, stream));
   XV_CUDA(cudaEventRecord(m->meta_event[slot], stream));
   xvk::SegMeta seg{meta_dev, meta_dev + n_seg, meta_dev + 2 * n_seg, n_seg};
 
   uint8_t* row_valid = ws + p.off_valid;
+  uint8_t* blk_valid = ws + p.off_blk_valid;
   uint32_t* counters = reinterpret_cast<uint32_t*>(ws + p.off_counters);
   __half* x0 = reinterpret_cast<__half*>(ws + p.off_x0);
   __half* ha = reinterpret_cast<__half*>(ws + p.off_ha);
   __half* hb = reinterpret_cast<__half*>(ws + p.off_hb);
   __half* hlast = reinterpret_cast<__half*>(ws + p.off_hlast);
+  float* pool_partial = reinterpret_cast<float*>(ws + p.off_pool_partial);
   int launches = 0;
   m->prof_used = 0;
 #define XV_PROF() do { int prc_ = prof_mark(m, stream); if (prc_ != XV_OK) return prc_; } while (0)
 
-  // ---- pack: fp32 features -> spliced fp16 packed rows + row map ---------------------------
+  // ---- pack: fp32 features -> spliced fp16 packed rows + row / block maps --------------------
   {
     xvk::PackArgs a{};
     a.feats = feats_dev;
     a.seg = seg;
-    a.r_pad = int32_t(p.r_pad);
+    a.r_pad = int32_t(r_pad);
     a.feat_dim = m->topo.feat_dim;
     a.taps = m->layers[0].taps;
     a.dilation = m->layers[0].dilation;
     a.k0_pad = m->k0_pad;
     a.x0 = x0;
     a.row_valid = row_valid;
+    a.blk_valid = blk_valid;
     a.counters = counters;
     a.n_counters = p.n_groups;
-    const int blocks = int(std::max<int64_t>(p.r_pad / xvk::PACK_ROWS_PER_BLOCK,
-                                             (p.n_groups + xvk::PACK_THREADS - 1) / xvk::PACK_THREADS));
+    const int blocks = int(r_pad / xvk::PACK_ROWS_PER_BLOCK);      // >= n_seg >= n_groups
     XV_PROF();
     xvk::pack_im2col_kernel<<<blocks, xvk::PACK_THREADS, 0, stream>>>(a);
     XV_PROF();
@@ -310,44 +321,90 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
 
   // ---- frame-level TDNN stack: one fused tcgen05 kernel per layer --------------------------
   const int nl = m->topo.n_frame_layers;
+  const bool pair = m->opt_pipeline == 2;
+  const bool want_last = layer_out_dev && layer_out_dev[nl - 1];
   const __half* in = x0;
   for (int i = 0; i < nl; ++i) {
     const FrameLayer& L = m->layers[i];
-    __half* out = (i == nl - 1) ? hlast : ((i & 1) ? hb : ha);
+    const bool last = i == nl - 1;
+    __half* out = last ? hlast : ((i & 1) ? hb : ha);
     const int halo = (L.gemm_taps - 1) / 2 * L.dilation;
-    const bool reuse = m->opt_reuse && L.gemm_taps > 1 && halo <= tdnn::MAX_REUSE_HALO;
     const int c_in_gemm = (i == 0) ? L.k_total : L.c_in_pad;       // row width of the input matrix
-    CUtensorMap ta, tw, tc;
-    rc = encode_2d(m, &ta, const_cast<__half*>(in), uint64_t(c_in_gemm), uint64_t(p.r_pad), tdnn::BLOCK_K,
-                   reuse ? tdnn::A_BOX_ROWS_REUSE : tdnn::A_BOX_ROWS_PLAIN, CU_TENSOR_MAP_SWIZZLE_128B);
-    if (rc != XV_OK) return rc;
-    rc = encode_2d(m, &tw, L.w_dev, uint64_t(L.k_total), uint64_t(L.c_out), tdnn::BLOCK_K, tdnn::BLOCK_N,
-                   CU_TENSOR_MAP_SWIZZLE_128B);
-    if (rc != XV_OK) return rc;
-    rc = encode_2d(m, &tc, out, uint64_t(L.c_out), uint64_t(p.r_pad), tdnn::C_CHUNK, tdnn::BLOCK_M,
-                   CU_TENSOR_MAP_SWIZZLE_64B);
-    if (rc != XV_OK) return rc;
-    tdnn::LayerArgs a{};
-    a.n_m_tiles = int32_t(p.r_pad / tdnn::BLOCK_M);
-    a.n_n_tiles = L.c_out / tdnn::BLOCK_N;
-    a.c_chunks = c_in_gemm / tdnn::BLOCK_K;
-    a.taps = L.gemm_taps;
-    a.dilation = L.dilation;
-    a.c_in_pad = c_in_gemm;
-    a.reuse = reuse ? 1 : 0;
-    a.desc_base_offset = m->opt_desc_base_offset;
-    a.bias = L.bias_dev;
-    a.scale = L.scale_dev;
-    a.shift = L.shift_dev;
-    a.row_valid = row_valid;
-    a.overflow_flag = m->overflow_dev;
-    const int64_t tiles = int64_t(a.n_m_tiles) * a.n_n_tiles;
-    const int grid = int(std::min<int64_t>(tiles, m->num_sms));
-    XV_PROF();
-    tdnn::tdnn_layer_kernel<<<grid, tdnn::NUM_THREADS, tdnn::SMEM_BYTES, stream>>>(ta, tw, tc, a);
-    XV_PROF();
-    XV_CUDA(cudaGetLastError());
-    ++launches;
+    if (pair) {
+      const bool reuse = L.gemm_taps > 1 && halo <= tdnn2::MAX_REUSE_HALO;
+      CUtensorMap ta, tw, tc;
+      rc = encode_2d(m, &ta, const_cast<__half*>(in), uint64_t(c_in_gemm), uint64_t(r_pad), tdnn2::BLOCK_K,
+                     reuse ? tdnn2::ACT_BOX_ROWS_REUSE : tdnn2::ACT_BOX_ROWS_PLAIN, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc != XV_OK) return rc;
+      rc = encode_2d(m, &tw, L.w_dev, uint64_t(L.k_total), uint64_t(L.c_out), tdnn2::BLOCK_K, tdnn2::CTA_CH,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc != XV_OK) return rc;
+      rc = encode_2d(m, &tc, out, uint64_t(L.c_out), uint64_t(r_pad), tdnn2::C_CHUNK, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc != XV_OK) return rc;
+      tdnn2::PairArgs a{};
+      a.n_row_tiles = int32_t(r_pad / tdnn2::TILE_ROWS);
+      a.n_ch_tiles = L.c_out / tdnn2::TILE_CH;
+      a.c_chunks = c_in_gemm / tdnn2::BLOCK_K;
+      a.taps = L.gemm_taps;
+      a.dilation = L.dilation;
+      a.c_in_pad = c_in_gemm;
+      a.reuse = reuse ? 1 : 0;
+      a.n_act_stages = reuse ? 3 : 5;
+      a.n_wgt_stages = reuse ? 8 : 5;
+      a.c_out = L.c_out;
+      a.bias = L.bias_dev;
+      a.scale = L.scale_dev;
+      a.shift = L.shift_dev;
+      a.row_valid = row_valid;
+      a.blk_valid = blk_valid;
+      a.partial = pool_partial;
+      a.overflow_flag = m->overflow_dev;
+      const int64_t tiles = int64_t(a.n_row_tiles) * a.n_ch_tiles;
+      const int grid = 2 * int(std::min<int64_t>(tiles, m->num_clusters));
+      // last layer: pooled partial sums (mode 1); its activation is only stored when a caller asks for it
+      for (int mode = last ? 1 : 0; mode >= 0; --mode) {
+        if (last && mode == 0 && !want_last) break;
+        a.mode = mode;
+        XV_PROF();
+        tdnn2::tdnn_pair_kernel<<<grid, tdnn2::NUM_THREADS, tdnn2::SMEM_BYTES, stream>>>(ta, tw, tc, a);
+        XV_PROF();
+        XV_CUDA(cudaGetLastError());
+        ++launches;
+      }
+    } else {
+      const bool reuse = m->opt_reuse && L.gemm_taps > 1 && halo <= tdnn::MAX_REUSE_HALO;
+      CUtensorMap ta, tw, tc;
+      rc = encode_2d(m, &ta, const_cast<__half*>(in), uint64_t(c_in_gemm), uint64_t(r_pad), tdnn::BLOCK_K,
+                     reuse ? tdnn::A_BOX_ROWS_REUSE : tdnn::A_BOX_ROWS_PLAIN, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc != XV_OK) return rc;
+      rc = encode_2d(m, &tw, L.w_dev, uint64_t(L.k_total), uint64_t(L.c_out), tdnn::BLOCK_K, tdnn::BLOCK_N,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc != XV_OK) return rc;
+      rc = encode_2d(m, &tc, out, uint64_t(L.c_out), uint64_t(r_pad), tdnn::C_CHUNK, tdnn::BLOCK_M,
+                     CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc != XV_OK) return rc;
+      tdnn::LayerArgs a{};
+      a.n_m_tiles = int32_t(r_pad / tdnn::BLOCK_M);
+      a.n_n_tiles = L.c_out / tdnn::BLOCK_N;
+      a.c_chunks = c_in_gemm / tdnn::BLOCK_K;
+      a.taps = L.gemm_taps;
+      a.dilation = L.dilation;
+      a.c_in_pad = c_in_gemm;
+      a.reuse = reuse ? 1 : 0;
+      a.desc_base_offset = reuse ? 0 : m->opt_desc_base_offset;
+      a.bias = L.bias_dev;
+      a.scale = L.scale_dev;
+      a.shift = L.shift_dev;
+      a.row_valid = row_valid;
+      a.overflow_flag = m->overflow_dev;
+      const int64_t tiles = int64_t(a.n_m_tiles) * a.n_n_tiles;
+      const int grid = int(std::min<int64_t>(tiles, m->num_sms));
+      XV_PROF();
+      tdnn::tdnn_layer_kernel<<<grid, tdnn::NUM_THREADS, tdnn::SMEM_BYTES, stream>>>(ta, tw, tc, a);
+      XV_PROF();
+      XV_CUDA(cudaGetLastError());
+      ++launches;
+    }
     if (layer_out_dev && layer_out_dev[i]) {
       xvk::unpack_rows_kernel<<<n_seg, 256, 0, stream>>>(out, seg, L.c_out, layer_out_dev[i]);
       XV_CUDA(cudaGetLastError());
@@ -357,7 +414,27 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
   }
 
   // ---- statistics pooling + embed_layer-0 -----------------------------------------------
-  {
+  if (pair) {
+    xvk::FinalizeArgs a{};
+    a.partial = pool_partial;
+    a.seg = seg;
+    a.channels = m->topo.width[nl - 1];
+    a.emb_dim = m->topo.emb_dim;
+    a.group = p.group;
+    a.w0 = m->w0_dev;
+    a.b0 = m->b0_dev;
+    a.fc_partial = reinterpret_cast<float*>(ws + p.off_partial);
+    a.counters = counters;
+    a.emb = emb_dev;
+    a.stats_out = stats_out_dev;
+    a.var_eps = m->topo.var_eps;
+    dim3 grid(p.n_groups, p.n_slabs);
+    XV_PROF();
+    xvk::pool_finalize_embed_kernel<<<grid, xvk::POOL_THREADS, 0, stream>>>(a);
+    XV_PROF();
+    XV_CUDA(cudaGetLastError());
+    ++launches;
+  } else {
     xvk::PoolArgs a{};
     a.h = hlast;
     a.seg = seg;
@@ -450,6 +527,24 @@ int xv_create(xv_model** out, int device, const xv_topology* topo) {
   }
   m->encode = reinterpret_cast<EncodeTiledFn>(fn);
   e = cudaFuncSetAttribute(tdnn::tdnn_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn::SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(tdnn2::tdnn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
+  if (e == cudaSuccess) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * (prop.multiProcessorCount / 2));
+    cfg.blockDim = dim3(tdnn2::NUM_THREADS);
+    cfg.dynamicSmemBytes = tdnn2::SMEM_BYTES;
+    int n_clusters = 0;
+    // the kernel carries __cluster_dims__(2,1,1); ask how many pairs can be co-resident
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    cudaError_t qe = cudaOccupancyMaxActiveClusters(&n_clusters, tdnn2::tdnn_pair_kernel, &cfg);
+    if (qe != cudaSuccess || n_clusters <= 0) { (void)cudaGetLastError(); n_clusters = prop.multiProcessorCount / 2; }
+    m->num_clusters = std::min(n_clusters, prop.multiProcessorCount / 2);
+  }
   if (e == cudaSuccess) e = cudaMalloc(&m->overflow_dev, 4);
   if (e == cudaSuccess) e = cudaMemset(m->overflow_dev, 0, 4);
   if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&m->overflow_host), 4, cudaHostAllocDefault);
@@ -616,6 +711,10 @@ int xv_set_option(xv_model* m, const char* name, int64_t value) {
   if (n == "reuse_taps") m->opt_reuse = value != 0;
   else if (n == "desc_base_offset") m->opt_desc_base_offset = value != 0;
   else if (n == "profile") m->opt_profile = value != 0;
+  else if (n == "pipeline") {
+    if (value != 1 && value != 2) return fail(XV_EINVAL, "pipeline must be 1 or 2");
+    m->opt_pipeline = int(value);
+  }
   else return fail(XV_EINVAL, "unknown option: " + n);
   return XV_OK;
 }
