@@ -5,7 +5,7 @@
     python bench.py --impl reference [--steps K] [--warmup W]      # the reference's CPU path
 
 A *step* is one pass of the extraction hot path (pack -> 5 fused tcgen05 TDNN layers, the last one pooling in its epilogue ->
-pool finalize + embed_layer-0) over one batch of synthetic MFCC: BASELINE.json configs[1], 256 utterances x 400
+pool statistics -> embed_layer-0) over one batch of synthetic MFCC: BASELINE.json configs[1], 256 utterances x 400
 frames x 23 ceps per GPU (weak scaling: every rank gets its own batch; for N > 1 the step ends
 with the NCCL gather of the [256, 512] embeddings to rank 0, the only collective on the path).
 
@@ -15,7 +15,7 @@ with the NCCL gather of the [256, 512] embeddings to rank 0, the only collective
          boundary, reference local/tf/models.py:412-415): pinned HOST features in, HOST
          embeddings out, H2D + D2H inside the timed region.
   roofline      the fused TDNN layer kernel (5 launches/step) against the measured tensor peak;
-                per-launch figures for all 7 launches in roofline.launches.
+                per-launch figures for all 8 launches in roofline.launches.
   cpu_baseline  the reference's CPU path restated in torch fp32 (oracle/xvector_torch_cpu.py --
                 TensorFlow 1.x cannot be installed here), run the way the reference runs it: one
                 utterance per call, 2 threads per process, cores/2 processes
@@ -267,7 +267,7 @@ def run_b200(args):
     kms = np.asarray(per_launch, dtype=np.float64).mean(axis=0)        # [7]
     peaks = load_peaks()
     fl = flop_per_frame(topo)
-    names = ["pack_im2col_kernel"] + ["tdnn_pair_kernel[L%d]" % i for i in range(len(fl))] + ["pool_finalize_embed_kernel"]
+    names = ["pack_im2col_kernel"] + ["tdnn_pair_kernel[L%d]" % i for i in range(len(fl))] + ["pool_stats_kernel", "embed_fc_kernel"]
     c_last = topo["layer_sizes"][-1]
     k0_pad = -(-topo["kernel_sizes"][0] * FEAT_DIM // 64) * 64
     launches = []
@@ -280,8 +280,10 @@ def run_b200(args):
         else:
             if name.startswith("pack"):       # fp32 features in, fp16 spliced rows + row map out
                 nbytes = frames * (FEAT_DIM * 4 + k0_pad * 2 + 1)
-            else:                             # per-32-row-block partial sums in, W0 once, embeddings out
-                nbytes = B * (-(-T // 32)) * 2 * c_last * 4 + 2 * c_last * EMB_DIM * 4 + B * EMB_DIM * 4
+            elif name.startswith("pool"):     # per-32-row-block partial sums in, [mean|std] out
+                nbytes = B * (-(-T // 32)) * 2 * c_last * 4 + B * 2 * c_last * 4
+            else:                             # [mean|std] in, W0 once, embeddings out (fp32 SIMT GEMM, tiny)
+                nbytes = B * 2 * c_last * 4 + 2 * c_last * EMB_DIM * 4 + B * EMB_DIM * 4
             gbs = nbytes / (kms[i] * 1e-3) / 1e9
             d.update(bound="hbm", achieved=round(gbs, 1), unit="GB/s", frac=round(gbs / peaks["hbm_gbs"], 4))
         launches.append(d)

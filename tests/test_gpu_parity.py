@@ -144,7 +144,7 @@ def test_extract_host_equals_device_forward():
     dev = _run(eng, feats, lens)
     host = eng.extract_host(feats, lens)
     assert np.array_equal(dev, host)
-    assert eng.last_launch_count == 7          # pack + 5 layers + pool/embed
+    assert eng.last_launch_count == 8          # pack + 5 layers + pool stats + embed_layer-0
     eng.close()
 
 

@@ -7,9 +7,10 @@
 //   pool_embed_kernel  : statistics pooling (tf.nn.moments over time + sqrt(var + 1e-5), concat;
 //                        reference models.py:485-486) fused with the first segment-level affine
 //                        layer embed_layer-0 (tf.nn.xw_plus_b, models.py:495) = the x-vector.
-//   pool_finalize_embed_kernel : the production form of the above: combines the per-32-row-block
-//                        partial sums written by the last frame layer's epilogue (the [frames,1536]
-//                        activation is never materialised), then the same embed_layer-0 product.
+//   pool_stats_kernel  : production pooling: combines the per-32-row-block partial sums written by
+//                        the last frame layer's epilogue (the [frames,1536] activation is never
+//                        materialised) into [mean | std] per segment.
+//   embed_fc_kernel    : embed_layer-0 as an fp32 split-K GEMM over the whole batch of segments.
 //   unpack_rows_kernel : debug/parity only: fp16 packed rows -> fp32 [total_frames, C].
 #pragma once
 #include <cuda_fp16.h>
@@ -49,7 +50,7 @@ struct PackArgs {
   __half* x0;                // [r_pad, k0_pad]
   uint8_t* row_valid;        // [r_pad]
   uint8_t* blk_valid;        // [r_pad / 32] valid rows of each aligned 32-row block
-  uint32_t* counters;        // [n_counters] zeroed here for pool_finalize_embed_kernel
+  uint32_t* counters;        // [n_counters] zeroed here for embed_fc_kernel / pool_embed_kernel
   int32_t n_counters;
 };
 
@@ -259,116 +260,144 @@ __global__ void __launch_bounds__(POOL_THREADS) pool_embed_kernel(const PoolArgs
 }
 
 // ------------------------------------------------------------------------------------------
-// Second half of statistics pooling + embed_layer-0, fed by the per-block partial sums that the
-// last frame layer's epilogue (tdnn_pair_kernel mode 1) wrote:
+// Second half of statistics pooling, fed by the per-block partial sums that the last frame
+// layer's epilogue (tdnn_pair_kernel mode 1) wrote:
 //   partial[block][0][c] = sum of y over the block's valid rows, partial[block][1][c] = sum of y*y.
-// The blocks of a segment are combined in a fixed order in fp64 (mean = S1/n, var = S2/n - mean^2:
-// population variance, tf.nn.moments; std = sqrt(var + 1e-5), models.py:485-486), then
-// stats @ W0 + b0 (tf.nn.xw_plus_b, models.py:495) exactly as pool_embed_kernel does.
-struct FinalizeArgs {
+// The blocks of a segment are combined in a fixed order in fp64: mean = S1/n, var = S2/n - mean^2
+// (population variance, tf.nn.moments), std = sqrt(var + 1e-5) (models.py:485-486); the result is
+// stats[seg] = [mean(C) | std(C)] (the tf.concat of models.py:486).
+constexpr int STATS_THREADS = 256;
+
+struct StatsArgs {
   const float* partial;       // [r_pad/32][2][C]
   SegMeta seg;
-  int32_t channels;           // C (multiple of 128)
-  int32_t emb_dim;            // E (multiple of 256, <= 1024)
-  int32_t group;              // segments per CTA, 1..POOL_MAX_G
-  const float* w0;            // [2C, E]  embed_layer-0/w
-  const float* b0;            // [E]
-  float* fc_partial;          // [n_slabs, n_seg, E]
-  uint32_t* counters;         // [n_groups], zero on entry
-  float* emb;                 // [n_seg, E]
-  float* stats_out;           // optional [n_seg, 2C]
+  int32_t channels;           // C
+  float* stats;               // [n_seg, 2C]
   float var_eps;
 };
 
-__global__ void __launch_bounds__(POOL_THREADS) pool_finalize_embed_kernel(const FinalizeArgs a) {
-  __shared__ double s_sum[2][POOL_SLAB];                        // S1 | S2 of the current segment
-  __shared__ float s_stats[POOL_MAX_G][2 * POOL_SLAB];          // mean | std per segment
+__global__ void __launch_bounds__(STATS_THREADS) pool_stats_kernel(const StatsArgs a) {
+  const int seg = blockIdx.y;
+  const int c = blockIdx.x * STATS_THREADS + threadIdx.x;
+  const int C = a.channels;
+  if (c >= C) return;
+  const int len = __ldg(a.seg.len + seg);
+  const int blk0 = __ldg(a.seg.row_start + seg) >> 5;
+  const int n_blk = (len + 31) >> 5;
+  const float* p = a.partial + int64_t(blk0) * 2 * C + c;
+  double s1 = 0.0, s2 = 0.0;
+  int b = 0;
+  for (; b + 4 <= n_blk; b += 4) {                              // 8 independent loads in flight, fixed order
+    float x[4], y[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      x[u] = __ldg(p + int64_t(b + u) * 2 * C);
+      y[u] = __ldg(p + int64_t(b + u) * 2 * C + C);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { s1 += double(x[u]); s2 += double(y[u]); }
+  }
+  for (; b < n_blk; ++b) {
+    s1 += double(__ldg(p + int64_t(b) * 2 * C));
+    s2 += double(__ldg(p + int64_t(b) * 2 * C + C));
+  }
+  const double inv_n = 1.0 / double(len);
+  const double mean = s1 * inv_n;
+  const double var = fmax(s2 * inv_n - mean * mean, 0.0);
+  a.stats[int64_t(seg) * 2 * C + c] = float(mean);
+  a.stats[int64_t(seg) * 2 * C + C + c] = float(sqrt(var + double(a.var_eps)));
+}
+
+// ------------------------------------------------------------------------------------------
+// embed_layer-0 (tf.nn.xw_plus_b, models.py:495): emb[n_seg, E] = stats[n_seg, K] @ W0[K, E] + b0,
+// the x-vector.  fp32 SIMT GEMM (the 1e-3 parity budget leaves no room for 16-bit statistics):
+// 32 x 128 output tile per CTA, 4 x 4 outputs per thread, split over K; the last CTA of a tile
+// adds the K-splits in a fixed order, so every output is summed in one order whatever the batch.
+constexpr int FC_BM = 32, FC_BN = 128, FC_BK = 32, FC_THREADS = 256;
+
+struct FcArgs {
+  const float* stats;         // [n_seg, K]
+  const float* w0;            // [K, E]  embed_layer-0/w
+  const float* b0;            // [E]
+  float* fc_partial;          // [splits][n_seg][E]
+  uint32_t* counters;         // [m_tiles * n_tiles], zero on entry
+  float* emb;                 // [n_seg, E]
+  int32_t n_seg, K, E, k_per_split;   // k_per_split % FC_BK == 0
+};
+
+__global__ void __launch_bounds__(FC_THREADS) embed_fc_kernel(const FcArgs a) {
+  __shared__ __align__(16) float As[FC_BK][FC_BM + 4];          // k-major: a thread's 4 segments are one float4
+  __shared__ __align__(16) float Bs[FC_BK][FC_BN];
   __shared__ int s_last;
-  const int tid = threadIdx.x;
-  const int g0 = blockIdx.x * a.group;
-  const int n_in_group = min(a.group, a.seg.n_seg - g0);
-  const int slab = blockIdx.y, n_slabs = gridDim.y;
-  const int c0 = slab * POOL_SLAB;
-  const int C = a.channels, E = a.emb_dim;
-  const int which = tid >> 7, cl = tid & (POOL_SLAB - 1);       // threads 0..127: S1, 128..255: S2
-
-  for (int gi = 0; gi < n_in_group; ++gi) {
-    const int seg = g0 + gi;
-    const int len = __ldg(a.seg.len + seg);
-    const int blk0 = __ldg(a.seg.row_start + seg) >> 5;
-    const int n_blk = (len + 31) >> 5;
-    const float* p = a.partial + (int64_t(blk0) * 2 + which) * C + c0 + cl;
-    double acc = 0.0;
-    int b = 0;
-    for (; b + 4 <= n_blk; b += 4) {                            // 4 independent loads in flight, fixed order
-      const float x0 = __ldg(p + int64_t(b) * 2 * C), x1 = __ldg(p + int64_t(b + 1) * 2 * C);
-      const float x2 = __ldg(p + int64_t(b + 2) * 2 * C), x3 = __ldg(p + int64_t(b + 3) * 2 * C);
-      acc += double(x0); acc += double(x1); acc += double(x2); acc += double(x3);
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int seg0 = blockIdx.x * FC_BM, o0 = blockIdx.y * FC_BN;
+  const int split = blockIdx.z, n_splits = gridDim.z;
+  const int k_begin = split * a.k_per_split, k_end = min(a.K, k_begin + a.k_per_split);
+  const int ar = tid >> 3, ak = (tid & 7) * 4;                  // A loader: segment row, k offset
+  float4 a_reg, b_reg[4];
+  auto load = [&](int k0) {
+    const int sg = seg0 + ar;
+    a_reg = (sg < a.n_seg && k0 + ak < k_end) ? __ldg(reinterpret_cast<const float4*>(a.stats + int64_t(sg) * a.K + k0 + ak))
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * FC_THREADS, kr = idx >> 5, c4 = (idx & 31) * 4;
+      b_reg[i] = (k0 + kr < k_end) ? __ldg(reinterpret_cast<const float4*>(a.w0 + int64_t(k0 + kr) * a.E + o0 + c4))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (; b < n_blk; ++b) acc += double(__ldg(p + int64_t(b) * 2 * C));
-    __syncthreads();                                            // s_sum free (previous segment consumed)
-    s_sum[which][cl] = acc;
+  };
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  load(k_begin);
+  for (int k0 = k_begin; k0 < k_end; k0 += FC_BK) {
+    __syncthreads();                                            // previous chunk consumed
+    As[ak + 0][ar] = a_reg.x; As[ak + 1][ar] = a_reg.y; As[ak + 2][ar] = a_reg.z; As[ak + 3][ar] = a_reg.w;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * FC_THREADS;
+      *reinterpret_cast<float4*>(&Bs[idx >> 5][(idx & 31) * 4]) = b_reg[i];
+    }
     __syncthreads();
-    if (tid < POOL_SLAB) {
-      const double inv_n = 1.0 / double(len);
-      const double mean = s_sum[0][tid] * inv_n;
-      const double var = fmax(s_sum[1][tid] * inv_n - mean * mean, 0.0);   // population variance (tf.nn.moments)
-      const float sd = float(sqrt(var + double(a.var_eps)));               // models.py:486
-      s_stats[gi][tid] = float(mean);
-      s_stats[gi][POOL_SLAB + tid] = sd;
-      if (a.stats_out != nullptr) {
-        a.stats_out[int64_t(seg) * 2 * C + c0 + tid] = float(mean);
-        a.stats_out[int64_t(seg) * 2 * C + C + c0 + tid] = sd;
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- embed_layer-0 partial product for this channel slab -------------------------------
-  const int ept = E / POOL_THREADS;                             // outputs per thread
-  float acc[POOL_MAX_G][POOL_MAX_EPT];
+    if (k0 + FC_BK < k_end) load(k0 + FC_BK);                   // prefetch the next chunk into registers
 #pragma unroll
-  for (int gi = 0; gi < POOL_MAX_G; ++gi)
+    for (int k = 0; k < FC_BK; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float am[4] = {av.x, av.y, av.z, av.w}, bm[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-    for (int i = 0; i < POOL_MAX_EPT; ++i) acc[gi][i] = 0.f;
-#pragma unroll 4
-  for (int r = 0; r < 2 * POOL_SLAB; ++r) {
-    const int wrow = (r < POOL_SLAB) ? (c0 + r) : (C + c0 + r - POOL_SLAB);     // mean rows, then std rows
-    const float* wp = a.w0 + int64_t(wrow) * E + tid;
-    float w[POOL_MAX_EPT];
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int i = 0; i < POOL_MAX_EPT; ++i) w[i] = (i < ept) ? __ldg(wp + i * POOL_THREADS) : 0.f;
-#pragma unroll
-    for (int gi = 0; gi < POOL_MAX_G; ++gi) {
-      if (gi < n_in_group) {
-        const float s = s_stats[gi][r];
-#pragma unroll
-        for (int i = 0; i < POOL_MAX_EPT; ++i) acc[gi][i] = fmaf(s, w[i], acc[gi][i]);
-      }
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(am[i], bm[j], acc[i][j]);
     }
   }
 #pragma unroll
-  for (int gi = 0; gi < POOL_MAX_G; ++gi) {
-    if (gi < n_in_group) {
-#pragma unroll
-      for (int i = 0; i < POOL_MAX_EPT; ++i)
-        if (i < ept) a.fc_partial[(int64_t(slab) * a.seg.n_seg + g0 + gi) * E + tid + i * POOL_THREADS] = acc[gi][i];
-    }
+  for (int i = 0; i < 4; ++i) {
+    const int sg = seg0 + ty * 4 + i;
+    if (sg < a.n_seg)
+      *reinterpret_cast<float4*>(a.fc_partial + (int64_t(split) * a.n_seg + sg) * a.E + o0 + tx * 4) =
+          make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
   }
-
-  // ---- the last CTA of the group sums the slabs in a fixed order (deterministic) ------------
+  // ---- the last CTA of this output tile adds the K-splits in a fixed order ---------------------
   __threadfence();
   __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(a.counters + blockIdx.x, 1u) == uint32_t(n_slabs - 1));
+  if (tid == 0) s_last = (atomicAdd(a.counters + blockIdx.y * gridDim.x + blockIdx.x, 1u) == uint32_t(n_splits - 1));
   __syncthreads();
   if (s_last) {
     __threadfence();
-    for (int gi = 0; gi < n_in_group; ++gi) {
-      for (int o = tid; o < E; o += POOL_THREADS) {
-        float sum = __ldg(a.b0 + o);
-        for (int s = 0; s < n_slabs; ++s) sum += __ldcg(a.fc_partial + (int64_t(s) * a.seg.n_seg + g0 + gi) * E + o);
-        a.emb[int64_t(g0 + gi) * E + o] = sum;
+    const float4 bias = __ldg(reinterpret_cast<const float4*>(a.b0 + o0 + tx * 4));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int sg = seg0 + ty * 4 + i;
+      if (sg >= a.n_seg) continue;
+      float4 sum = bias;
+      for (int s = 0; s < n_splits; ++s) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(a.fc_partial + (int64_t(s) * a.n_seg + sg) * a.E + o0 + tx * 4));
+        sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
       }
+      *reinterpret_cast<float4*>(a.emb + int64_t(sg) * a.E + o0 + tx * 4) = sum;
     }
   }
 }

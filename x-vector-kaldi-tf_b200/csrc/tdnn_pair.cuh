@@ -109,6 +109,7 @@ __device__ __forceinline__ void epi_store_math(const uint32_t (&v)[32], const fl
   }
 }
 
+template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations in  [R_pad, C_in_pad] fp16
                  const __grid_constant__ CUtensorMap tmap_wgt,   // weights [C_out, taps*C_in_pad] fp16 (K-major)
@@ -138,7 +139,7 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_act);
     ptx::prefetch_tmap(&tmap_wgt);
-    if (args.mode == 0) ptx::prefetch_tmap(&tmap_out);
+    if (MODE == 0) ptx::prefetch_tmap(&tmap_out);
     for (uint32_t s = 0; s < MAX_STAGES; ++s) {
       ptx::mbar_init(act_full(s), 1); ptx::mbar_init(act_empty(s), 1);
       ptx::mbar_init(wgt_full(s), 1); ptx::mbar_init(wgt_empty(s), 1);
@@ -163,37 +164,44 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
   const uint32_t n_act = uint32_t(args.n_act_stages), n_wgt = uint32_t(args.n_wgt_stages);
 
   if (warp == 0) {
-    // ============================ TMA producer (one thread per CTA) ====================
-    if (lane == 0) {
-      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;       // stage index / phase of each ring
-      const uint32_t act_full_leader = ptx::mapa_cluster(act_full(0), 0);   // transaction bytes are counted there
-      const uint32_t wgt_full_leader = ptx::mapa_cluster(wgt_full(0), 0);
-      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
-        const int r0 = (tile / args.n_ch_tiles) * TILE_ROWS + int(rank) * CTA_ROWS;
-        const int c0 = (tile % args.n_ch_tiles) * TILE_CH + int(rank) * CTA_CH;
-        for (int cc = 0; cc < args.c_chunks; ++cc) {
-          for (int j = 0; j < args.taps; ++j) {
-            if (!reuse || j == 0) {
-              ptx::mbar_wait(act_empty(sa), pa ^ 1u);
+    // ============================ TMA producer (warp 0 of each CTA; one elected lane issues) ====
+    uint32_t sa = 0, pa = 0, sb = 0, pb = 0;         // stage index / phase of each ring
+    const uint32_t act_full_leader = ptx::mapa_cluster(act_full(0), 0);   // transaction bytes are counted there
+    const uint32_t wgt_full_leader = ptx::mapa_cluster(wgt_full(0), 0);
+    for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+      const int r0 = (tile / args.n_ch_tiles) * TILE_ROWS + int(rank) * CTA_ROWS;
+      const int c0 = (tile % args.n_ch_tiles) * TILE_CH + int(rank) * CTA_CH;
+      for (int cc = 0; cc < args.c_chunks; ++cc) {
+        for (int j = 0; j < args.taps; ++j) {
+          if (!reuse || j == 0) {
+            ptx::mbar_wait(act_empty(sa), pa ^ 1u);
+            if (ptx::elect_one()) {
               if (leader) ptx::mbar_arrive_expect_tx(act_full(sa), 2u * act_box_bytes);   // both CTAs' boxes
               const int row = reuse ? (r0 - halo) : (r0 + (j - half_ctx) * args.dilation);
               ptx::tma_load_2d_2sm(sAct + sa * ACT_STAGE_BYTES, &tmap_act, act_full_leader + 8u * sa, cc * BLOCK_K, row);
-              if (++sa == n_act) { sa = 0; pa ^= 1u; }
             }
-            ptx::mbar_wait(wgt_empty(sb), pb ^ 1u);
+            __syncwarp();
+            if (++sa == n_act) { sa = 0; pa ^= 1u; }
+          }
+          ptx::mbar_wait(wgt_empty(sb), pb ^ 1u);
+          if (ptx::elect_one()) {
             if (leader) ptx::mbar_arrive_expect_tx(wgt_full(sb), 2u * WGT_STAGE_BYTES);
             ptx::tma_load_2d_2sm(sWgt + sb * WGT_STAGE_BYTES, &tmap_wgt, wgt_full_leader + 8u * sb,
                                  j * args.c_in_pad + cc * BLOCK_K, c0);
-            if (++sb == n_wgt) { sb = 0; pb ^= 1u; }
           }
+          __syncwarp();
+          if (++sb == n_wgt) { sb = 0; pb ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ============================ MMA issuer (leader CTA, one thread) ==================
-    if (leader && lane == 0) {
+    // ============================ MMA issuer (warp 1 of the leader CTA; one elected lane issues) =
+    if (leader) {
       constexpr uint32_t idesc = ptx::make_idesc_f16_f32(TILE_ROWS, TILE_CH);   // 256 x 256 either orientation
-      const bool swapped = args.mode == 1;
+      // descriptor without the start address: SBO = 1024 B, version 1, SWIZZLE_128B; the base-offset bits
+      // stay 0: the hardware swizzles on absolute smem address bits, which is what lets a tap start at
+      // any 128-byte row of the activation slab
+      const uint64_t desc_hi = ptx::make_sw128_kmajor_desc(0);
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
         const uint32_t acc = it & 1u;
@@ -208,25 +216,27 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
             ptx::tc_fence_after();
             const uint32_t act_addr = sAct + sa * ACT_STAGE_BYTES + (reuse ? uint32_t(j * args.dilation) * 128u : 0u);
             const uint32_t wgt_addr = sWgt + sb * WGT_STAGE_BYTES;
+            const uint64_t d_act = desc_hi | uint64_t((act_addr >> 4) & 0x3fffu);
+            const uint64_t d_wgt = desc_hi | uint64_t((wgt_addr >> 4) & 0x3fffu);
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              // base-offset bits stay 0: the hardware swizzles on absolute smem address bits, which
-              // is what lets a tap start at any 128-byte row of the slab
-              const uint64_t d_act = ptx::make_sw128_kmajor_desc(act_addr + k * (UMMA_K * 2)) & ~(0x7ull << 49);
-              const uint64_t d_wgt = ptx::make_sw128_kmajor_desc(wgt_addr + k * (UMMA_K * 2)) & ~(0x7ull << 49);
-              if (swapped) ptx::umma_f16_2sm(d_tmem, d_wgt, d_act, idesc, accumulate);
-              else ptx::umma_f16_2sm(d_tmem, d_act, d_wgt, idesc, accumulate);
-              accumulate = 1;
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {           // +32 bytes of K per UMMA: +2 in the address field
+                if (MODE == 1) ptx::umma_f16_2sm(d_tmem, d_wgt + 2u * k, d_act + 2u * k, idesc, accumulate | uint32_t(k));
+                else ptx::umma_f16_2sm(d_tmem, d_act + 2u * k, d_wgt + 2u * k, idesc, accumulate | uint32_t(k));
+              }
+              ptx::umma_commit_2sm(wgt_empty(sb));                     // weight slot free in both CTAs
+              if (!reuse || j == args.taps - 1) ptx::umma_commit_2sm(act_empty(sa));
             }
-            ptx::umma_commit_2sm(wgt_empty(sb));                       // weight slot free in both CTAs
+            __syncwarp();
+            accumulate = 1;
             if (++sb == n_wgt) { sb = 0; pb ^= 1u; }
             if (!reuse || j == args.taps - 1) {
-              ptx::umma_commit_2sm(act_empty(sa));
               if (++sa == n_act) { sa = 0; pa ^= 1u; }
             }
           }
         }
-        ptx::umma_commit_2sm(t_full(acc));                             // accumulator ready in both CTAs
+        if (ptx::elect_one()) ptx::umma_commit_2sm(t_full(acc));       // accumulator ready in both CTAs
+        __syncwarp();
       }
     }
   } else {
@@ -237,7 +247,7 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
     const int te = threadIdx.x - 64;                 // 0..255
     const uint32_t t_empty_leader = ptx::mapa_cluster(t_empty(0), 0);   // + 8 * acc
     uint32_t it = 0;
-    if (args.mode == 0) {
+    if (MODE == 0) {
       float* s_par = reinterpret_cast<float*>(smem + OFF_PARAMS);
       const uint32_t sC = smem_base + OFF_C + uint32_t(e) * 2 * C_BUF_BYTES;
       const uint32_t swz = (uint32_t(lane) >> 1) & 3u;   // SWIZZLE_64B phase of this row in the staging box

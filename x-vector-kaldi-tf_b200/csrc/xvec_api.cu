@@ -53,9 +53,10 @@ struct Plan {
   int64_t total_frames = 0;
   int32_t n_seg = 0;
   int64_t r_pad = 0;
-  int32_t group = 1, n_groups = 0, n_slabs = 0;
+  int32_t group = 1, n_groups = 0, n_slabs = 0;      // first-generation pool_embed_kernel grid
+  int32_t fc_m_tiles = 0, fc_n_tiles = 0, fc_splits = 1, fc_k_per_split = 0, n_counters = 0;
   size_t off_meta = 0, off_counters = 0, off_valid = 0, off_blk_valid = 0, off_x0 = 0, off_ha = 0, off_hb = 0,
-         off_hlast = 0, off_pool_partial = 0, off_partial = 0, bytes = 0;
+         off_hlast = 0, off_pool_partial = 0, off_stats = 0, off_partial = 0, bytes = 0;
 };
 
 constexpr int META_SLOTS = 4;
@@ -112,10 +113,16 @@ Plan make_plan(const xv_model* m, int64_t total_frames, int32_t n_seg) {
   p.n_slabs = c_last / xvk::POOL_SLAB;
   p.group = int(std::min<int64_t>(xvk::POOL_MAX_G, std::max<int64_t>(1, n_seg / 64)));
   p.n_groups = (n_seg + p.group - 1) / p.group;
+  const int K = 2 * c_last;
+  p.fc_m_tiles = (n_seg + xvk::FC_BM - 1) / xvk::FC_BM;
+  p.fc_n_tiles = m->topo.emb_dim / xvk::FC_BN;
+  p.fc_splits = (K % 512 == 0) ? K / 512 : K / 256;            // C_last is a multiple of 128
+  p.fc_k_per_split = K / p.fc_splits;
+  p.n_counters = std::max(p.n_groups, p.fc_m_tiles * p.fc_n_tiles);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = size_t(round_up(int64_t(off + bytes), 1024)); return o; };
   p.off_meta = take(size_t(3) * n_seg * 4);
-  p.off_counters = take(size_t(p.n_groups) * 4);
+  p.off_counters = take(size_t(p.n_counters) * 4);
   p.off_valid = take(size_t(p.r_pad));
   p.off_blk_valid = take(size_t(p.r_pad / tdnn2::POOL_BLOCK));
   p.off_x0 = take(size_t(p.r_pad) * m->k0_pad * 2);
@@ -123,7 +130,8 @@ Plan make_plan(const xv_model* m, int64_t total_frames, int32_t n_seg) {
   p.off_hb = take(size_t(p.r_pad) * m->w_mid * 2);
   p.off_hlast = take(size_t(p.r_pad) * c_last * 2);          // only written by the debug / v1 paths
   p.off_pool_partial = take(size_t(p.r_pad / tdnn2::POOL_BLOCK) * 2 * c_last * 4);
-  p.off_partial = take(size_t(p.n_slabs) * n_seg * m->topo.emb_dim * 4);
+  p.off_stats = take(size_t(n_seg) * K * 4);
+  p.off_partial = take(size_t(std::max(p.n_slabs, p.fc_splits)) * n_seg * m->topo.emb_dim * 4);
   p.bytes = off;
   return p;
 }
@@ -310,8 +318,8 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
     a.row_valid = row_valid;
     a.blk_valid = blk_valid;
     a.counters = counters;
-    a.n_counters = p.n_groups;
-    const int blocks = int(r_pad / xvk::PACK_ROWS_PER_BLOCK);      // >= n_seg >= n_groups
+    a.n_counters = p.n_counters;
+    const int blocks = int(r_pad / xvk::PACK_ROWS_PER_BLOCK);      // >= n_seg: covers n_counters with 256 threads each
     XV_PROF();
     xvk::pack_im2col_kernel<<<blocks, xvk::PACK_THREADS, 0, stream>>>(a);
     XV_PROF();
@@ -366,7 +374,8 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
         if (last && mode == 0 && !want_last) break;
         a.mode = mode;
         XV_PROF();
-        tdnn2::tdnn_pair_kernel<<<grid, tdnn2::NUM_THREADS, tdnn2::SMEM_BYTES, stream>>>(ta, tw, tc, a);
+        if (mode == 1) tdnn2::tdnn_pair_kernel<1><<<grid, tdnn2::NUM_THREADS, tdnn2::SMEM_BYTES, stream>>>(ta, tw, tc, a);
+        else tdnn2::tdnn_pair_kernel<0><<<grid, tdnn2::NUM_THREADS, tdnn2::SMEM_BYTES, stream>>>(ta, tw, tc, a);
         XV_PROF();
         XV_CUDA(cudaGetLastError());
         ++launches;
@@ -415,25 +424,40 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
 
   // ---- statistics pooling + embed_layer-0 -----------------------------------------------
   if (pair) {
-    xvk::FinalizeArgs a{};
-    a.partial = pool_partial;
-    a.seg = seg;
-    a.channels = m->topo.width[nl - 1];
-    a.emb_dim = m->topo.emb_dim;
-    a.group = p.group;
-    a.w0 = m->w0_dev;
-    a.b0 = m->b0_dev;
-    a.fc_partial = reinterpret_cast<float*>(ws + p.off_partial);
-    a.counters = counters;
-    a.emb = emb_dev;
-    a.stats_out = stats_out_dev;
-    a.var_eps = m->topo.var_eps;
-    dim3 grid(p.n_groups, p.n_slabs);
-    XV_PROF();
-    xvk::pool_finalize_embed_kernel<<<grid, xvk::POOL_THREADS, 0, stream>>>(a);
-    XV_PROF();
-    XV_CUDA(cudaGetLastError());
-    ++launches;
+    float* stats = stats_out_dev ? stats_out_dev : reinterpret_cast<float*>(ws + p.off_stats);
+    {
+      xvk::StatsArgs a{};
+      a.partial = pool_partial;
+      a.seg = seg;
+      a.channels = m->topo.width[nl - 1];
+      a.stats = stats;
+      a.var_eps = m->topo.var_eps;
+      dim3 grid((a.channels + xvk::STATS_THREADS - 1) / xvk::STATS_THREADS, n_seg);
+      XV_PROF();
+      xvk::pool_stats_kernel<<<grid, xvk::STATS_THREADS, 0, stream>>>(a);
+      XV_PROF();
+      XV_CUDA(cudaGetLastError());
+      ++launches;
+    }
+    {
+      xvk::FcArgs a{};
+      a.stats = stats;
+      a.w0 = m->w0_dev;
+      a.b0 = m->b0_dev;
+      a.fc_partial = reinterpret_cast<float*>(ws + p.off_partial);
+      a.counters = counters;
+      a.emb = emb_dev;
+      a.n_seg = n_seg;
+      a.K = 2 * m->topo.width[nl - 1];
+      a.E = m->topo.emb_dim;
+      a.k_per_split = p.fc_k_per_split;
+      dim3 grid(p.fc_m_tiles, p.fc_n_tiles, p.fc_splits);
+      XV_PROF();
+      xvk::embed_fc_kernel<<<grid, xvk::FC_THREADS, 0, stream>>>(a);
+      XV_PROF();
+      XV_CUDA(cudaGetLastError());
+      ++launches;
+    }
   } else {
     xvk::PoolArgs a{};
     a.h = hlast;
@@ -482,6 +506,13 @@ int xv_create(xv_model** out, int device, const xv_topology* topo) {
     if (t.width[i] <= 0 || t.width[i] % tdnn::BLOCK_N != 0) return fail(XV_EINVAL, "layer widths must be multiples of 256");
   }
   if (t.width[t.n_frame_layers - 1] % xvk::POOL_SLAB != 0) return fail(XV_EINVAL, "last width must be a multiple of 128");
+  {
+    const int halo0 = (t.taps[0] - 1) / 2 * t.dilation[0];
+    const int64_t k0 = round_up(int64_t(t.taps[0]) * t.feat_dim, tdnn2::BLOCK_K);
+    if ((xvk::PACK_ROWS_PER_BLOCK + 2 * halo0) * int64_t(t.feat_dim) > xvk::PACK_MAX_STAGE_FLOATS || k0 > xvk::PACK_MAX_K0 ||
+        int64_t(t.taps[0]) * t.dilation[0] * t.feat_dim > 32000)
+      return fail(XV_EINVAL, "first layer too wide for the pack kernel (taps*feat_dim must be <= 512)");
+  }
   int n_dev = 0;
   XV_CUDA(cudaGetDeviceCount(&n_dev));
   if (device < 0 || device >= n_dev) return fail(XV_EINVAL, "no such CUDA device");
@@ -528,7 +559,9 @@ int xv_create(xv_model** out, int device, const xv_topology* topo) {
   m->encode = reinterpret_cast<EncodeTiledFn>(fn);
   e = cudaFuncSetAttribute(tdnn::tdnn_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn::SMEM_BYTES);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(tdnn2::tdnn_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
+    e = cudaFuncSetAttribute(tdnn2::tdnn_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(tdnn2::tdnn_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
   if (e == cudaSuccess) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * (prop.multiProcessorCount / 2));
@@ -541,7 +574,7 @@ int xv_create(xv_model** out, int device, const xv_topology* topo) {
     attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    cudaError_t qe = cudaOccupancyMaxActiveClusters(&n_clusters, tdnn2::tdnn_pair_kernel, &cfg);
+    cudaError_t qe = cudaOccupancyMaxActiveClusters(&n_clusters, tdnn2::tdnn_pair_kernel<0>, &cfg);
     if (qe != cudaSuccess || n_clusters <= 0) { (void)cudaGetLastError(); n_clusters = prop.multiProcessorCount / 2; }
     m->num_clusters = std::min(n_clusters, prop.multiProcessorCount / 2);
   }
