@@ -89,14 +89,14 @@ struct PairArgs {
 };
 
 // One tcgen05.ld chunk of the store epilogue: 32 channels of one row -> 16 packed half2.
-__device__ __forceinline__ void epi_store_math(const uint32_t (&v)[32], const float* s_bias, const float* s_scale,
-                                               const float* s_shift, int c, bool valid, uint32_t (&p)[16],
-                                               uint32_t& hmax) {
+// s_par: shared-memory address of this tile's [bias(256) | scale(256) | shift(256)] floats.
+__device__ __forceinline__ void epi_store_math(const uint32_t (&v)[32], uint32_t s_par, int c, bool valid,
+                                               uint32_t (&p)[16], uint32_t& hmax) {
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
-    const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c + g * 4);
-    const float4 s4 = *reinterpret_cast<const float4*>(s_scale + c + g * 4);
-    const float4 h4 = *reinterpret_cast<const float4*>(s_shift + c + g * 4);
+    const float4 b4 = ptx::lds_f4(s_par + uint32_t(c + g * 4) * 4u);
+    const float4 s4 = ptx::lds_f4(s_par + uint32_t(TILE_CH + c + g * 4) * 4u);
+    const float4 h4 = ptx::lds_f4(s_par + uint32_t(2 * TILE_CH + c + g * 4) * 4u);
     // relu(acc + b) * inv + shift      (models.py:477-480, tf_block.py:26)
     const float y0 = fmaf(fmaxf(__uint_as_float(v[g * 4 + 0]) + b4.x, 0.f), s4.x, h4.x);
     const float y1 = fmaf(fmaxf(__uint_as_float(v[g * 4 + 1]) + b4.y, 0.f), s4.y, h4.y);
@@ -248,7 +248,6 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
     const uint32_t t_empty_leader = ptx::mapa_cluster(t_empty(0), 0);   // + 8 * acc
     uint32_t it = 0;
     if (MODE == 0) {
-      float* s_par = reinterpret_cast<float*>(smem + OFF_PARAMS);
       const uint32_t sC = smem_base + OFF_C + uint32_t(e) * 2 * C_BUF_BYTES;
       const uint32_t swz = (uint32_t(lane) >> 1) & 3u;   // SWIZZLE_64B phase of this row in the staging box
       uint32_t hmax = 0;
@@ -256,12 +255,10 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
         const uint32_t acc = it & 1u;
         const int r_cta = (tile / args.n_ch_tiles) * TILE_ROWS + int(rank) * CTA_ROWS;
         const int ch0 = (tile % args.n_ch_tiles) * TILE_CH;
-        float* s_bias = s_par + acc * 3 * TILE_CH;
-        float* s_scale = s_bias + TILE_CH;
-        float* s_shift = s_scale + TILE_CH;
-        s_bias[te] = __ldg(args.bias + ch0 + te);
-        s_scale[te] = __ldg(args.scale + ch0 + te);
-        s_shift[te] = __ldg(args.shift + ch0 + te);
+        const uint32_t s_par = smem_base + OFF_PARAMS + acc * (3 * TILE_CH * 4);
+        ptx::sts_f(s_par + uint32_t(te) * 4u, __ldg(args.bias + ch0 + te));
+        ptx::sts_f(s_par + uint32_t(TILE_CH + te) * 4u, __ldg(args.scale + ch0 + te));
+        ptx::sts_f(s_par + uint32_t(2 * TILE_CH + te) * 4u, __ldg(args.shift + ch0 + te));
         const bool valid = args.row_valid[r_cta + q * 32 + lane] != 0;
         ptx::named_bar_sync(1, NUM_EPI_THREADS);       // parameters of this tile visible (double-buffered by acc)
         ptx::mbar_wait(t_full(acc), (it >> 1) & 1u);
@@ -280,7 +277,7 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
             if (lane == 0) ptx::mbar_arrive_cluster(t_empty_leader + 8u * acc);
           }
           uint32_t p[16];
-          epi_store_math(v[chunk & 1], s_bias, s_scale, s_shift, colh * 128 + chunk * C_CHUNK, valid, p, hmax);
+          epi_store_math(v[chunk & 1], s_par, colh * 128 + chunk * C_CHUNK, valid, p, hmax);
           const uint32_t buf = sC + uint32_t(chunk & 1) * C_BUF_BYTES;
           if (lane == 0) ptx::tma_store_wait_read<1>();   // the store that last used this buffer has read it
           __syncwarp();

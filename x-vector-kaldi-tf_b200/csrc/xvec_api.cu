@@ -116,7 +116,7 @@ Plan make_plan(const xv_model* m, int64_t total_frames, int32_t n_seg) {
   const int K = 2 * c_last;
   p.fc_m_tiles = (n_seg + xvk::FC_BM - 1) / xvk::FC_BM;
   p.fc_n_tiles = m->topo.emb_dim / xvk::FC_BN;
-  p.fc_splits = (K % 512 == 0) ? K / 512 : K / 256;            // C_last is a multiple of 128
+  p.fc_splits = K / 256;                                       // C_last is a multiple of 128
   p.fc_k_per_split = K / p.fc_splits;
   p.n_counters = std::max(p.n_groups, p.fc_m_tiles * p.fc_n_tiles);
   size_t off = 0;
