@@ -100,11 +100,24 @@ int xv_forward_layers(xv_model* m, const float* feats_dev, const int32_t* seg_le
 int xv_extract_host(xv_model* m, const float* feats_host, const int32_t* seg_len_host,
                     int32_t n_seg, float* emb_host);
 
+/* Pipelined form of xv_extract_host.  xv_submit_host enqueues (copy in, forward, copy out) on one
+ * of XV_HOST_SLOTS internal streams and returns at once with a ticket; xv_collect waits for that
+ * submission and reports XV_EOVERFLOW like xv_extract_host.  With two submissions in flight the
+ * host->device copy of one batch overlaps the kernels of the previous one.  Both host buffers of
+ * a submission must stay valid (and should be page-locked) until it is collected; tickets must
+ * be collected before their slot is reused (XV_ESTATE otherwise).  xv_extract_host is
+ * xv_submit_host + xv_collect.  (The reference overlaps nothing: one blocking sess.run per
+ * utterance, models.py:401-419.) */
+#define XV_HOST_SLOTS 2
+int xv_submit_host(xv_model* m, const float* feats_host, const int32_t* seg_len_host,
+                   int32_t n_seg, float* emb_host, int32_t* ticket);
+int xv_collect(xv_model* m, int32_t ticket);
+
 /* Returns XV_OK, or XV_EOVERFLOW if any activation exceeded the fp16 range since the last
  * call (synchronises `stream`; clears the flag). */
 int xv_check_overflow(xv_model* m, void* stream);
 
-/* Number of kernels the last xv_forward / xv_extract_host launched (for bench.py's
+/* Number of kernels the last xv_forward / xv_extract_host / xv_submit_host launched (for bench.py's
  * "gpu_launches" claim). */
 int32_t xv_last_launch_count(const xv_model* m);
 

@@ -148,6 +148,31 @@ def test_extract_host_equals_device_forward():
     eng.close()
 
 
+def test_pipelined_submit_collect_equals_blocking_call():
+    import torch
+    from xvector_b200 import _native
+    eng, _ = _engine("ModelWithoutDropoutTdnn", "B")
+    sets = []
+    for seed, lens in ((31, [200, 64, 333]), (32, [25, 1000]), (33, [400] * 7)):
+        lens = np.asarray(lens, np.int32)
+        f = torch.from_numpy(synthetic.mfcc_batch(seed, lens)).pin_memory()
+        sets.append((f, lens, torch.empty((len(lens), 512), dtype=torch.float32).pin_memory()))
+    blocking = [eng.extract_host(f, lens).copy() for f, lens, _ in sets]
+    t0 = eng.submit_host(*sets[0])
+    t1 = eng.submit_host(*sets[1])
+    with pytest.raises(_native.XvecError):                      # both slots in flight
+        eng.submit_host(*sets[2])
+    eng.collect(t0)
+    t2 = eng.submit_host(*sets[2])
+    eng.collect(t1)
+    eng.collect(t2)
+    with pytest.raises(_native.XvecError):                      # nothing in flight any more
+        eng.collect(t2)
+    for want, (_, _, got) in zip(blocking, sets):
+        assert np.array_equal(want, got.numpy())
+    eng.close()
+
+
 def test_error_paths_do_not_crash():
     from xvector_b200 import _native
     t = orc.TOPOLOGIES["ModelWithoutDropout"]

@@ -83,6 +83,10 @@ def load_library():
     lib.xv_forward_layers.restype = ctypes.c_int
     lib.xv_extract_host.argtypes = [P, P, P, I32, P]
     lib.xv_extract_host.restype = ctypes.c_int
+    lib.xv_submit_host.argtypes = [P, P, P, I32, P, ctypes.POINTER(I32)]
+    lib.xv_submit_host.restype = ctypes.c_int
+    lib.xv_collect.argtypes = [P, I32]
+    lib.xv_collect.restype = ctypes.c_int
     lib.xv_check_overflow.argtypes = [P, P]
     lib.xv_check_overflow.restype = ctypes.c_int
     lib.xv_last_launch_count.argtypes = [P]
@@ -100,7 +104,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = ["xv_create", "xv_destroy", "xv_set_param", "xv_workspace_bytes", "xv_forward",
-                    "xv_forward_layers", "xv_extract_host", "xv_check_overflow", "xv_last_launch_count",
+                    "xv_forward_layers", "xv_extract_host", "xv_submit_host", "xv_collect", "xv_check_overflow", "xv_last_launch_count",
                     "xv_last_kernel_ms", "xv_set_option", "xv_last_error", "xv_version"]
 
 
@@ -212,6 +216,26 @@ class XvecEngine:
         eptr = emb_host.data_ptr() if hasattr(emb_host, "data_ptr") else emb_host.ctypes.data
         _check(self.lib, self.lib.xv_extract_host(self.handle, fptr, lens.ctypes.data_as(ctypes.c_void_p), n_seg, eptr))
         return emb_host
+
+    def submit_host(self, feats_host, seg_lens, emb_host):
+        """Asynchronous extract_host: returns a ticket at once; ``collect(ticket)`` waits for it.  Both buffers
+        must stay alive (and should be pinned) until collected; at most two submissions may be in flight."""
+        lens = np.ascontiguousarray(seg_lens, dtype=np.int32)
+        n_seg = int(lens.shape[0])
+        if hasattr(feats_host, "data_ptr"):
+            assert feats_host.is_contiguous() and feats_host.shape[0] == int(lens.sum())
+            fptr = feats_host.data_ptr()
+        else:
+            assert feats_host.dtype == np.float32 and feats_host.flags.c_contiguous and feats_host.shape[0] == int(lens.sum())
+            fptr = feats_host.ctypes.data
+        eptr = emb_host.data_ptr() if hasattr(emb_host, "data_ptr") else emb_host.ctypes.data
+        ticket = ctypes.c_int32(-1)
+        _check(self.lib, self.lib.xv_submit_host(self.handle, fptr, lens.ctypes.data_as(ctypes.c_void_p), n_seg, eptr,
+                                                 ctypes.byref(ticket)))
+        return int(ticket.value)
+
+    def collect(self, ticket):
+        _check(self.lib, self.lib.xv_collect(self.handle, int(ticket)))
 
     def last_kernel_ms(self):
         """Device duration (ms) of every launch of the last forward (option ``profile`` must be 1);

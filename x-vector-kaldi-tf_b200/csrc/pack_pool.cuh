@@ -50,6 +50,7 @@ struct PackArgs {
   __half* x0;                // [r_pad, k0_pad]
   uint8_t* row_valid;        // [r_pad]
   uint8_t* blk_valid;        // [r_pad / 32] valid rows of each aligned 32-row block
+  const int32_t* blk_seg;    // [r_pad / 32] segment that owns the block, -1 = gap / tail (host-built)
   uint32_t* counters;        // [n_counters] zeroed here for embed_fc_kernel / pool_embed_kernel
   int32_t n_counters;
 };
@@ -61,30 +62,27 @@ struct PackArgs {
 __global__ void __launch_bounds__(PACK_THREADS) pack_im2col_kernel(const PackArgs a) {
   __shared__ float s_feat[PACK_MAX_STAGE_FLOATS];
   __shared__ int16_t s_lut[PACK_MAX_K0];
-  __shared__ int s_info[3];                          // segment, first frame of the block, valid rows
   const int r0 = blockIdx.x * PACK_ROWS_PER_BLOCK;
   const int gtid = blockIdx.x * PACK_THREADS + threadIdx.x;
   if (gtid < a.n_counters) a.counters[gtid] = 0u;
   if (r0 >= a.r_pad) return;
   const int D = a.feat_dim;
   const int halo = ((a.taps - 1) >> 1) * a.dilation;
-  if (threadIdx.x == 0) {
-    const int s = find_segment(a.seg.row_start, a.seg.n_seg, r0);
-    int t0 = 0, nv = 0;
-    if (s >= 0) {
-      t0 = r0 - __ldg(a.seg.row_start + s);
-      nv = max(0, min(PACK_ROWS_PER_BLOCK, __ldg(a.seg.len + s) - t0));
-    }
-    s_info[0] = s; s_info[1] = t0; s_info[2] = nv;
-    a.blk_valid[blockIdx.x] = uint8_t(nv);
+  const int seg = __ldg(a.blk_seg + blockIdx.x);     // block-uniform
+  int t0 = 0, nv = 0, len = 0;
+  int64_t fs = 0;
+  if (seg >= 0) {
+    len = __ldg(a.seg.len + seg);
+    fs = __ldg(a.seg.feat_start + seg);
+    t0 = r0 - __ldg(a.seg.row_start + seg);
+    nv = min(PACK_ROWS_PER_BLOCK, len - t0);         // >= 1 by construction of blk_seg
   }
+  if (threadIdx.x == 0) a.blk_valid[blockIdx.x] = uint8_t(nv);
   const int k_real = a.taps * D;
   for (int ch = threadIdx.x; ch < a.k0_pad; ch += PACK_THREADS) {
     const int j = ch / D, c = ch - j * D;
     s_lut[ch] = (ch < k_real) ? int16_t(j * a.dilation * D + c) : int16_t(-1);
   }
-  __syncthreads();
-  const int seg = s_info[0], t0 = s_info[1], nv = s_info[2];
   if (threadIdx.x < PACK_ROWS_PER_BLOCK) a.row_valid[r0 + threadIdx.x] = threadIdx.x < nv ? 1 : 0;
   const int pieces = a.k0_pad >> 3;                                   // 16-byte pieces per row
   if (nv == 0) {                                                      // gap / tail block: zero rows
@@ -92,8 +90,6 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_im2col_kernel(const PackArg
       reinterpret_cast<uint4*>(a.x0 + int64_t(r0) * a.k0_pad)[idx] = make_uint4(0u, 0u, 0u, 0u);
     return;
   }
-  const int len = __ldg(a.seg.len + seg);
-  const int64_t fs = __ldg(a.seg.feat_start + seg);
   const int stage_rows = PACK_ROWS_PER_BLOCK + 2 * halo;              // frames t0-halo .. t0+31+halo
   for (int idx = threadIdx.x; idx < stage_rows * D; idx += PACK_THREADS) {
     const int sr = idx / D;
@@ -311,9 +307,9 @@ __global__ void __launch_bounds__(STATS_THREADS) pool_stats_kernel(const StatsAr
 // ------------------------------------------------------------------------------------------
 // embed_layer-0 (tf.nn.xw_plus_b, models.py:495): emb[n_seg, E] = stats[n_seg, K] @ W0[K, E] + b0,
 // the x-vector.  fp32 SIMT GEMM (the 1e-3 parity budget leaves no room for 16-bit statistics):
-// 32 x 128 output tile per CTA, 4 x 4 outputs per thread, split over K; the last CTA of a tile
-// adds the K-splits in a fixed order, so every output is summed in one order whatever the batch.
-constexpr int FC_BM = 32, FC_BN = 128, FC_BK = 32, FC_THREADS = 256;
+// split over K; the last CTA of a tile adds the K-splits in a fixed order, so every output is
+// summed in one order whatever the batch.
+constexpr int FC_BM = 64, FC_BN = 128, FC_BK = 32, FC_THREADS = 256;
 
 struct FcArgs {
   const float* stats;         // [n_seg, K]
@@ -325,20 +321,24 @@ struct FcArgs {
   int32_t n_seg, K, E, k_per_split;   // k_per_split % FC_BK == 0
 };
 
+// 64 x 128 output tile per CTA, 8 segments x 4 outputs per thread (per k: 3 LDS.128 feed 32 FFMA, so
+// the FP32 pipe, not shared memory, is the limit).
 __global__ void __launch_bounds__(FC_THREADS) embed_fc_kernel(const FcArgs a) {
-  __shared__ __align__(16) float As[FC_BK][FC_BM + 4];          // k-major: a thread's 4 segments are one float4
+  __shared__ __align__(16) float As[FC_BK][FC_BM + 4];          // k-major: a thread's 8 segments are two float4
   __shared__ __align__(16) float Bs[FC_BK][FC_BN];
   __shared__ int s_last;
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
   const int seg0 = blockIdx.x * FC_BM, o0 = blockIdx.y * FC_BN;
   const int split = blockIdx.z, n_splits = gridDim.z;
   const int k_begin = split * a.k_per_split, k_end = min(a.K, k_begin + a.k_per_split);
-  const int ar = tid >> 3, ak = (tid & 7) * 4;                  // A loader: segment row, k offset
-  float4 a_reg, b_reg[4];
+  float4 a_reg[2], b_reg[4];
   auto load = [&](int k0) {
-    const int sg = seg0 + ar;
-    a_reg = (sg < a.n_seg && k0 + ak < k_end) ? __ldg(reinterpret_cast<const float4*>(a.stats + int64_t(sg) * a.K + k0 + ak))
-                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = tid + i * FC_THREADS, sg = seg0 + (idx >> 3), ak = (idx & 7) * 4;
+      a_reg[i] = (sg < a.n_seg && k0 + ak < k_end) ? __ldg(reinterpret_cast<const float4*>(a.stats + int64_t(sg) * a.K + k0 + ak))
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int idx = tid + i * FC_THREADS, kr = idx >> 5, c4 = (idx & 31) * 4;
@@ -346,15 +346,19 @@ __global__ void __launch_bounds__(FC_THREADS) embed_fc_kernel(const FcArgs a) {
                                    : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
-  float acc[4][4];
+  float acc[8][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   load(k_begin);
   for (int k0 = k_begin; k0 < k_end; k0 += FC_BK) {
     __syncthreads();                                            // previous chunk consumed
-    As[ak + 0][ar] = a_reg.x; As[ak + 1][ar] = a_reg.y; As[ak + 2][ar] = a_reg.z; As[ak + 3][ar] = a_reg.w;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = tid + i * FC_THREADS, ar = idx >> 3, ak = (idx & 7) * 4;
+      As[ak + 0][ar] = a_reg[i].x; As[ak + 1][ar] = a_reg[i].y; As[ak + 2][ar] = a_reg[i].z; As[ak + 3][ar] = a_reg[i].w;
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int idx = tid + i * FC_THREADS;
@@ -364,18 +368,19 @@ __global__ void __launch_bounds__(FC_THREADS) embed_fc_kernel(const FcArgs a) {
     if (k0 + FC_BK < k_end) load(k0 + FC_BK);                   // prefetch the next chunk into registers
 #pragma unroll
     for (int k = 0; k < FC_BK; ++k) {
-      const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
       const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      const float am[4] = {av.x, av.y, av.z, av.w}, bm[4] = {bv.x, bv.y, bv.z, bv.w};
+      const float am[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, bm[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(am[i], bm[j], acc[i][j]);
     }
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int sg = seg0 + ty * 4 + i;
+  for (int i = 0; i < 8; ++i) {
+    const int sg = seg0 + ty * 8 + i;
     if (sg < a.n_seg)
       *reinterpret_cast<float4*>(a.fc_partial + (int64_t(split) * a.n_seg + sg) * a.E + o0 + tx * 4) =
           make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
@@ -388,9 +393,9 @@ __global__ void __launch_bounds__(FC_THREADS) embed_fc_kernel(const FcArgs a) {
   if (s_last) {
     __threadfence();
     const float4 bias = __ldg(reinterpret_cast<const float4*>(a.b0 + o0 + tx * 4));
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int sg = seg0 + ty * 4 + i;
+#pragma unroll 2
+    for (int i = 0; i < 8; ++i) {
+      const int sg = seg0 + ty * 8 + i;
       if (sg >= a.n_seg) continue;
       float4 sum = bias;
       for (int s = 0; s < n_splits; ++s) {

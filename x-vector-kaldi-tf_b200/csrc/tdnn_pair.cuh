@@ -23,7 +23,7 @@
 //                    that channel, so the per-block sum / sum of squares is a private register
 //                    reduction (no shuffles, fixed order -> bit-reproducible).  Output:
 //                    partial[block][{sum,sumsq}][channel] fp32, one aligned 32-row block each.
-// Temporal taps: the activation slab [136 rows x 64 ch] is loaded ONCE per channel chunk and tap
+// Temporal taps: the activation slab [136 rows x 128 ch] is loaded ONCE per channel chunk and tap
 // j is addressed by advancing the UMMA descriptor start by j*d rows (reuse = 1); for half
 // contexts > 4 rows one box per tap is loaded instead (reuse = 0).
 //
@@ -40,14 +40,19 @@ constexpr int TILE_ROWS = 256;                     // activation rows per tile (
 constexpr int TILE_CH = 256;                       // output channels per tile (pair)
 constexpr int CTA_ROWS = 128;
 constexpr int CTA_CH = 128;
-constexpr int BLOCK_K = 64;                        // fp16 elements = one 128-byte swizzle row
+constexpr int BLOCK_K = 64;                        // fp16 elements = one 128-byte swizzle row (one TMA box / UMMA atom)
+constexpr int STAGE_K = 128;                       // K per pipeline stage = 2 atoms: 8 UMMAs per barrier round trip
+constexpr int ATOMS = STAGE_K / BLOCK_K;
 constexpr int UMMA_K = 16;
 constexpr int ACT_BOX_ROWS_PLAIN = CTA_ROWS;
 constexpr int ACT_BOX_ROWS_REUSE = CTA_ROWS + 8;   // supports half contexts <= 4 rows
 constexpr int MAX_REUSE_HALO = 4;
-constexpr int ACT_STAGE_BYTES = ACT_BOX_ROWS_REUSE * 128;   // 17408
-constexpr int WGT_STAGE_BYTES = CTA_CH * 128;               // 16384
-constexpr int RING_BYTES = 184320;                 // activation + weight rings (carved at run time)
+constexpr int ACT_ATOM_BYTES = ACT_BOX_ROWS_REUSE * 128;    // 17408
+constexpr int WGT_ATOM_BYTES = CTA_CH * 128;                // 16384
+constexpr int ACT_STAGE_BYTES = ATOMS * ACT_ATOM_BYTES;     // 34816
+constexpr int WGT_STAGE_BYTES = ATOMS * WGT_ATOM_BYTES;     // 32768
+constexpr int RING_BYTES = 184320;                 // activation + weight rings (carved at run time); the pooled
+                                                   // mode has no output staging and may also use the 32 KB after it
 constexpr int MAX_STAGES = 8;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_EPI_THREADS = NUM_EPI_WARPS * 32;
@@ -70,12 +75,12 @@ static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of dynamic shared memory");
 struct PairArgs {
   int32_t n_row_tiles;      // R_pad / 256
   int32_t n_ch_tiles;       // C_out / 256
-  int32_t c_chunks;         // C_in_pad / 64
+  int32_t c_chunks;         // C_in_pad / 128
   int32_t taps;
   int32_t dilation;
   int32_t c_in_pad;         // column stride between taps in the packed weight matrix
   int32_t reuse;            // 0 / 1 (see header comment)
-  int32_t n_act_stages;     // n_act * 17408 + n_wgt * 16384 <= RING_BYTES
+  int32_t n_act_stages;     // n_act * 34816 + n_wgt * 32768 <= RING_BYTES (+ 32768 in mode 1)
   int32_t n_wgt_stages;
   int32_t mode;             // 0 store, 1 pool
   int32_t c_out;
@@ -119,7 +124,7 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t smem_base = ptx::smem_u32(smem);
   const uint32_t sAct = smem_base + OFF_RING;
-  const uint32_t sWgt = sAct + uint32_t(args.n_act_stages) * ACT_STAGE_BYTES;   // 17408 = 17 * 1024: stays aligned
+  const uint32_t sWgt = sAct + uint32_t(args.n_act_stages) * ACT_STAGE_BYTES;   // 34816 = 34 * 1024: stays aligned
   const uint32_t bar0 = smem_base + OFF_BARS;
   auto act_full = [&](uint32_t s) { return bar0 + 8u * s; };
   auto act_empty = [&](uint32_t s) { return bar0 + 8u * (MAX_STAGES + s); };
@@ -176,9 +181,12 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
           if (!reuse || j == 0) {
             ptx::mbar_wait(act_empty(sa), pa ^ 1u);
             if (ptx::elect_one()) {
-              if (leader) ptx::mbar_arrive_expect_tx(act_full(sa), 2u * act_box_bytes);   // both CTAs' boxes
+              if (leader) ptx::mbar_arrive_expect_tx(act_full(sa), 2u * ATOMS * act_box_bytes);   // both CTAs' boxes
               const int row = reuse ? (r0 - halo) : (r0 + (j - half_ctx) * args.dilation);
-              ptx::tma_load_2d_2sm(sAct + sa * ACT_STAGE_BYTES, &tmap_act, act_full_leader + 8u * sa, cc * BLOCK_K, row);
+#pragma unroll
+              for (int h = 0; h < ATOMS; ++h)
+                ptx::tma_load_2d_2sm(sAct + sa * ACT_STAGE_BYTES + h * ACT_ATOM_BYTES, &tmap_act, act_full_leader + 8u * sa,
+                                     cc * STAGE_K + h * BLOCK_K, row);
             }
             __syncwarp();
             if (++sa == n_act) { sa = 0; pa ^= 1u; }
@@ -186,8 +194,10 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
           ptx::mbar_wait(wgt_empty(sb), pb ^ 1u);
           if (ptx::elect_one()) {
             if (leader) ptx::mbar_arrive_expect_tx(wgt_full(sb), 2u * WGT_STAGE_BYTES);
-            ptx::tma_load_2d_2sm(sWgt + sb * WGT_STAGE_BYTES, &tmap_wgt, wgt_full_leader + 8u * sb,
-                                 j * args.c_in_pad + cc * BLOCK_K, c0);
+#pragma unroll
+            for (int h = 0; h < ATOMS; ++h)
+              ptx::tma_load_2d_2sm(sWgt + sb * WGT_STAGE_BYTES + h * WGT_ATOM_BYTES, &tmap_wgt, wgt_full_leader + 8u * sb,
+                                   j * args.c_in_pad + cc * STAGE_K + h * BLOCK_K, c0);
           }
           __syncwarp();
           if (++sb == n_wgt) { sb = 0; pb ^= 1u; }
@@ -220,9 +230,14 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
             const uint64_t d_wgt = desc_hi | uint64_t((wgt_addr >> 4) & 0x3fffu);
             if (ptx::elect_one()) {
 #pragma unroll
-              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {           // +32 bytes of K per UMMA: +2 in the address field
-                if (MODE == 1) ptx::umma_f16_2sm(d_tmem, d_wgt + 2u * k, d_act + 2u * k, idesc, accumulate | uint32_t(k));
-                else ptx::umma_f16_2sm(d_tmem, d_act + 2u * k, d_wgt + 2u * k, idesc, accumulate | uint32_t(k));
+              for (int h = 0; h < ATOMS; ++h) {
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {         // +32 bytes of K per UMMA: +2 in the address field
+                  const uint64_t da = d_act + uint64_t(h * (ACT_ATOM_BYTES >> 4) + 2 * k);
+                  const uint64_t dw = d_wgt + uint64_t(h * (WGT_ATOM_BYTES >> 4) + 2 * k);
+                  if (MODE == 1) ptx::umma_f16_2sm(d_tmem, dw, da, idesc, accumulate | uint32_t(h | k));
+                  else ptx::umma_f16_2sm(d_tmem, da, dw, idesc, accumulate | uint32_t(h | k));
+                }
               }
               ptx::umma_commit_2sm(wgt_empty(sb));                     // weight slot free in both CTAs
               if (!reuse || j == args.taps - 1) ptx::umma_commit_2sm(act_empty(sa));

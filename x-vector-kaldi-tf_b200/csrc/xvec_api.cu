@@ -84,11 +84,17 @@ struct xv_model {
   cudaEvent_t meta_event[META_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
   int64_t meta_cap = 0;
   int meta_next = 0;
-  // xv_extract_host state
-  cudaStream_t stream = nullptr;
-  float* feats_dev = nullptr; size_t feats_cap = 0;
-  float* emb_dev = nullptr; size_t emb_cap = 0;
-  void* ws_dev = nullptr; size_t ws_cap = 0;
+  // xv_extract_host / xv_submit_host state: two independent submission slots (own stream and device
+  // buffers) so that the host->device copy of one batch overlaps the kernels of the previous one
+  struct HostSlot {
+    cudaStream_t stream = nullptr;
+    float* feats_dev = nullptr; size_t feats_cap = 0;
+    float* emb_dev = nullptr; size_t emb_cap = 0;
+    void* ws_dev = nullptr; size_t ws_cap = 0;
+    uint32_t* overflow_host = nullptr;   // pinned
+    bool busy = false;
+  } slots[XV_HOST_SLOTS];
+  int slot_next = 0;
   int32_t last_launches = 0;
   // options
   int opt_reuse = 0;
@@ -121,7 +127,7 @@ Plan make_plan(const xv_model* m, int64_t total_frames, int32_t n_seg) {
   p.n_counters = std::max(p.n_groups, p.fc_m_tiles * p.fc_n_tiles);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = size_t(round_up(int64_t(off + bytes), 1024)); return o; };
-  p.off_meta = take(size_t(3) * n_seg * 4);
+  p.off_meta = take((size_t(3) * n_seg + size_t(p.r_pad / tdnn2::POOL_BLOCK)) * 4);
   p.off_counters = take(size_t(p.n_counters) * 4);
   p.off_valid = take(size_t(p.r_pad));
   p.off_blk_valid = take(size_t(p.r_pad / tdnn2::POOL_BLOCK));
@@ -220,14 +226,14 @@ int finalize_params(xv_model* m) {
   return XV_OK;
 }
 
-int ensure_meta_capacity(xv_model* m, int64_t n_seg) {
-  if (n_seg <= m->meta_cap) return XV_OK;
-  const int64_t cap = std::max<int64_t>(n_seg * 2, 1024);
+int ensure_meta_capacity(xv_model* m, int64_t n_ints) {
+  if (n_ints <= m->meta_cap) return XV_OK;
+  const int64_t cap = std::max<int64_t>(n_ints * 2, 4096);
   for (int s = 0; s < META_SLOTS; ++s) {
     if (m->meta_event[s]) XV_CUDA(cudaEventSynchronize(m->meta_event[s]));
     if (m->meta_host[s]) XV_CUDA(cudaFreeHost(m->meta_host[s]));
     m->meta_host[s] = nullptr;
-    XV_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&m->meta_host[s]), size_t(3) * cap * 4, cudaHostAllocDefault));
+    XV_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&m->meta_host[s]), size_t(cap) * 4, cudaHostAllocDefault));
     if (!m->meta_event[s]) XV_CUDA(cudaEventCreateWithFlags(&m->meta_event[s], cudaEventDisableTiming));
   }
   m->meta_cap = cap;
@@ -268,7 +274,7 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
   uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
 
   // ---- segment metadata: packed row starts (multiples of 32), feature row starts, lengths ----
-  rc = ensure_meta_capacity(m, n_seg);
+  rc = ensure_meta_capacity(m, int64_t(3) * n_seg + p.r_pad / tdnn2::POOL_BLOCK);
   if (rc != XV_OK) return rc;
   const int slot = m->meta_next;
   m->meta_next = (m->meta_next + 1) % META_SLOTS;
@@ -277,20 +283,27 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
   int64_t rows_used = 0;
   {
     int64_t row = 0, fs = 0;
+    int32_t* blk_seg = mh + 3 * int64_t(n_seg);                     // segment of every aligned 32-row block, -1 = none
     for (int i = 0; i < n_seg; ++i) {
       mh[i] = int32_t(row);
       mh[n_seg + i] = int32_t(fs);
       mh[2 * n_seg + i] = seg_len_host[i];
-      row += round_up(int64_t(seg_len_host[i]) + m->gap, tdnn2::POOL_BLOCK);
+      const int64_t next = row + round_up(int64_t(seg_len_host[i]) + m->gap, tdnn2::POOL_BLOCK);
+      const int64_t b_data_end = (row + seg_len_host[i] + tdnn2::POOL_BLOCK - 1) / tdnn2::POOL_BLOCK;
+      for (int64_t b = row / tdnn2::POOL_BLOCK; b < next / tdnn2::POOL_BLOCK; ++b) blk_seg[b] = b < b_data_end ? i : -1;
+      row = next;
       fs += seg_len_host[i];
     }
     rows_used = row;
   }
   const int64_t r_pad = round_up(rows_used, tdnn2::TILE_ROWS);      // <= p.r_pad (the plan's upper bound)
+  const int64_t n_blocks = r_pad / tdnn2::POOL_BLOCK;
+  for (int64_t b = rows_used / tdnn2::POOL_BLOCK; b < n_blocks; ++b) mh[3 * int64_t(n_seg) + b] = -1;
   int32_t* meta_dev = reinterpret_cast<int32_t*>(ws + p.off_meta);
-  XV_CUDA(cudaMemcpyAsync(meta_dev, mh, size_t(3) * n_seg * 4, cudaMemcpyHostToDevice, stream));
+  XV_CUDA(cudaMemcpyAsync(meta_dev, mh, (size_t(3) * n_seg + size_t(n_blocks)) * 4, cudaMemcpyHostToDevice, stream));
   XV_CUDA(cudaEventRecord(m->meta_event[slot], stream));
   xvk::SegMeta seg{meta_dev, meta_dev + n_seg, meta_dev + 2 * n_seg, n_seg};
+  const int32_t* blk_seg_dev = meta_dev + 3 * int64_t(n_seg);
 
   uint8_t* row_valid = ws + p.off_valid;
   uint8_t* blk_valid = ws + p.off_blk_valid;
@@ -317,6 +330,7 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
     a.x0 = x0;
     a.row_valid = row_valid;
     a.blk_valid = blk_valid;
+    a.blk_seg = blk_seg_dev;
     a.counters = counters;
     a.n_counters = p.n_counters;
     const int blocks = int(r_pad / xvk::PACK_ROWS_PER_BLOCK);      // >= n_seg: covers n_counters with 256 threads each
@@ -352,13 +366,13 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       tdnn2::PairArgs a{};
       a.n_row_tiles = int32_t(r_pad / tdnn2::TILE_ROWS);
       a.n_ch_tiles = L.c_out / tdnn2::TILE_CH;
-      a.c_chunks = c_in_gemm / tdnn2::BLOCK_K;
+      a.c_chunks = c_in_gemm / tdnn2::STAGE_K;
       a.taps = L.gemm_taps;
       a.dilation = L.dilation;
       a.c_in_pad = c_in_gemm;
       a.reuse = reuse ? 1 : 0;
-      a.n_act_stages = reuse ? 3 : 5;
-      a.n_wgt_stages = reuse ? 8 : 5;
+      a.n_act_stages = 2;                                  // 2 x 34816 + 3 x 32768 = 167936 <= RING_BYTES
+      a.n_wgt_stages = 3;
       a.c_out = L.c_out;
       a.bias = L.bias_dev;
       a.scale = L.scale_dev;
@@ -373,6 +387,7 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       for (int mode = last ? 1 : 0; mode >= 0; --mode) {
         if (last && mode == 0 && !want_last) break;
         a.mode = mode;
+        a.n_act_stages = mode == 1 ? 3 : 2;                // the pooled mode has no output staging: 32 KB more ring
         XV_PROF();
         if (mode == 1) tdnn2::tdnn_pair_kernel<1><<<grid, tdnn2::NUM_THREADS, tdnn2::SMEM_BYTES, stream>>>(ta, tw, tc, a);
         else tdnn2::tdnn_pair_kernel<0><<<grid, tdnn2::NUM_THREADS, tdnn2::SMEM_BYTES, stream>>>(ta, tw, tc, a);
@@ -503,12 +518,12 @@ int xv_create(xv_model** out, int device, const xv_topology* topo) {
   for (int i = 0; i < t.n_frame_layers; ++i) {
     if (t.taps[i] < 1 || t.taps[i] % 2 == 0) return fail(XV_EINVAL, "taps must be odd and >= 1");
     if (t.dilation[i] < 1) return fail(XV_EINVAL, "dilation must be >= 1");
-    if (t.width[i] <= 0 || t.width[i] % tdnn::BLOCK_N != 0) return fail(XV_EINVAL, "layer widths must be multiples of 256");
+    if (t.width[i] <= 0 || t.width[i] % tdnn2::TILE_CH != 0) return fail(XV_EINVAL, "layer widths must be multiples of 256");
   }
   if (t.width[t.n_frame_layers - 1] % xvk::POOL_SLAB != 0) return fail(XV_EINVAL, "last width must be a multiple of 128");
   {
     const int halo0 = (t.taps[0] - 1) / 2 * t.dilation[0];
-    const int64_t k0 = round_up(int64_t(t.taps[0]) * t.feat_dim, tdnn2::BLOCK_K);
+    const int64_t k0 = round_up(int64_t(t.taps[0]) * t.feat_dim, tdnn2::STAGE_K);
     if ((xvk::PACK_ROWS_PER_BLOCK + 2 * halo0) * int64_t(t.feat_dim) > xvk::PACK_MAX_STAGE_FLOATS || k0 > xvk::PACK_MAX_K0 ||
         int64_t(t.taps[0]) * t.dilation[0] * t.feat_dim > 32000)
       return fail(XV_EINVAL, "first layer too wide for the pack kernel (taps*feat_dim must be <= 512)");
@@ -536,7 +551,7 @@ int xv_create(xv_model** out, int device, const xv_topology* topo) {
     L.c_out = t.width[i];
     if (i == 0) {                          // spliced (im2col) input: dense K, padded to a multiple of 64
       L.c_in_pad = prev;
-      L.k_total = int(round_up(int64_t(L.taps) * prev, tdnn::BLOCK_K));
+      L.k_total = int(round_up(int64_t(L.taps) * prev, tdnn2::STAGE_K));
       L.gemm_taps = 1;
       m->k0_pad = L.k_total;
     } else {
@@ -581,7 +596,10 @@ int xv_create(xv_model** out, int device, const xv_topology* topo) {
   if (e == cudaSuccess) e = cudaMalloc(&m->overflow_dev, 4);
   if (e == cudaSuccess) e = cudaMemset(m->overflow_dev, 0, 4);
   if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&m->overflow_host), 4, cudaHostAllocDefault);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+  for (int i = 0; i < XV_HOST_SLOTS && e == cudaSuccess; ++i) {
+    e = cudaStreamCreateWithFlags(&m->slots[i].stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&m->slots[i].overflow_host), 4, cudaHostAllocDefault);
+  }
   if (e != cudaSuccess) {
     std::string msg = std::string("xv_create: ") + cudaGetErrorName(e) + ": " + cudaGetErrorString(e);
     xv_destroy(m);
@@ -603,8 +621,11 @@ void xv_destroy(xv_model* m) {
   for (cudaEvent_t e : m->prof_events) cudaEventDestroy(e);
   cudaFree(m->overflow_dev);
   if (m->overflow_host) cudaFreeHost(m->overflow_host);
-  cudaFree(m->feats_dev); cudaFree(m->emb_dev); cudaFree(m->ws_dev);
-  if (m->stream) cudaStreamDestroy(m->stream);
+  for (auto& sl : m->slots) {
+    cudaFree(sl.feats_dev); cudaFree(sl.emb_dev); cudaFree(sl.ws_dev);
+    if (sl.overflow_host) cudaFreeHost(sl.overflow_host);
+    if (sl.stream) cudaStreamDestroy(sl.stream);
+  }
   delete m;
 }
 
@@ -674,8 +695,9 @@ int xv_forward_layers(xv_model* m, const float* feats_dev, const int32_t* seg_le
                       static_cast<cudaStream_t>(stream), layer_out_dev, stats_out_dev);
 }
 
-int xv_extract_host(xv_model* m, const float* feats_host, const int32_t* seg_len_host, int32_t n_seg, float* emb_host) {
-  if (!m || !feats_host || !seg_len_host || !emb_host) return fail(XV_EINVAL, "null argument");
+int xv_submit_host(xv_model* m, const float* feats_host, const int32_t* seg_len_host, int32_t n_seg, float* emb_host,
+                   int32_t* ticket) {
+  if (!m || !feats_host || !seg_len_host || !emb_host || !ticket) return fail(XV_EINVAL, "null argument");
   if (n_seg <= 0) return fail(XV_EINVAL, "n_seg must be >= 1");
   XV_CUDA(cudaSetDevice(m->device));
   int64_t total = 0;
@@ -683,12 +705,15 @@ int xv_extract_host(xv_model* m, const float* feats_host, const int32_t* seg_len
     if (seg_len_host[i] <= 0) return fail(XV_EINVAL, "segment " + std::to_string(i) + " has non-positive length");
     total += seg_len_host[i];
   }
+  const int si = m->slot_next;
+  xv_model::HostSlot& sl = m->slots[si];
+  if (sl.busy) return fail(XV_ESTATE, "all submission slots are in flight: xv_collect the oldest ticket first");
   const size_t feat_bytes = size_t(total) * m->topo.feat_dim * 4;
   const size_t emb_bytes = size_t(n_seg) * m->topo.emb_dim * 4;
   const size_t ws_bytes = xv_workspace_bytes(m, total, n_seg);
   auto grow = [&](void** p, size_t* cap, size_t need) -> cudaError_t {
     if (need <= *cap) return cudaSuccess;
-    cudaStreamSynchronize(m->stream);
+    cudaStreamSynchronize(sl.stream);
     cudaFree(*p);
     *p = nullptr; *cap = 0;
     const size_t want = need + need / 4;
@@ -696,20 +721,39 @@ int xv_extract_host(xv_model* m, const float* feats_host, const int32_t* seg_len
     if (e == cudaSuccess) *cap = want;
     return e;
   };
-  XV_CUDA(grow(reinterpret_cast<void**>(&m->feats_dev), &m->feats_cap, feat_bytes));
-  XV_CUDA(grow(reinterpret_cast<void**>(&m->emb_dev), &m->emb_cap, emb_bytes));
-  XV_CUDA(grow(&m->ws_dev, &m->ws_cap, ws_bytes));
-  XV_CUDA(cudaMemcpyAsync(m->feats_dev, feats_host, feat_bytes, cudaMemcpyHostToDevice, m->stream));
-  int rc = forward_impl(m, m->feats_dev, seg_len_host, n_seg, m->emb_dev, m->ws_dev, m->ws_cap, m->stream, nullptr, nullptr);
+  XV_CUDA(grow(reinterpret_cast<void**>(&sl.feats_dev), &sl.feats_cap, feat_bytes));
+  XV_CUDA(grow(reinterpret_cast<void**>(&sl.emb_dev), &sl.emb_cap, emb_bytes));
+  XV_CUDA(grow(&sl.ws_dev, &sl.ws_cap, ws_bytes));
+  XV_CUDA(cudaMemcpyAsync(sl.feats_dev, feats_host, feat_bytes, cudaMemcpyHostToDevice, sl.stream));
+  int rc = forward_impl(m, sl.feats_dev, seg_len_host, n_seg, sl.emb_dev, sl.ws_dev, sl.ws_cap, sl.stream, nullptr, nullptr);
   if (rc != XV_OK) return rc;
-  XV_CUDA(cudaMemcpyAsync(emb_host, m->emb_dev, emb_bytes, cudaMemcpyDeviceToHost, m->stream));
-  XV_CUDA(cudaMemcpyAsync(m->overflow_host, m->overflow_dev, 4, cudaMemcpyDeviceToHost, m->stream));
-  XV_CUDA(cudaStreamSynchronize(m->stream));
-  if (*m->overflow_host != 0) {
-    XV_CUDA(cudaMemsetAsync(m->overflow_dev, 0, 4, m->stream));
+  XV_CUDA(cudaMemcpyAsync(emb_host, sl.emb_dev, emb_bytes, cudaMemcpyDeviceToHost, sl.stream));
+  XV_CUDA(cudaMemcpyAsync(sl.overflow_host, m->overflow_dev, 4, cudaMemcpyDeviceToHost, sl.stream));
+  sl.busy = true;
+  m->slot_next = (si + 1) % XV_HOST_SLOTS;
+  *ticket = si;
+  return XV_OK;
+}
+
+int xv_collect(xv_model* m, int32_t ticket) {
+  if (!m || ticket < 0 || ticket >= XV_HOST_SLOTS) return fail(XV_EINVAL, "bad ticket");
+  xv_model::HostSlot& sl = m->slots[ticket];
+  if (!sl.busy) return fail(XV_ESTATE, "ticket is not in flight");
+  XV_CUDA(cudaSetDevice(m->device));
+  sl.busy = false;
+  XV_CUDA(cudaStreamSynchronize(sl.stream));
+  if (*sl.overflow_host != 0) {
+    XV_CUDA(cudaMemsetAsync(m->overflow_dev, 0, 4, sl.stream));
     return fail(XV_EOVERFLOW, "an activation exceeded the fp16 range (|x| > 65504); results are not trustworthy");
   }
   return XV_OK;
+}
+
+int xv_extract_host(xv_model* m, const float* feats_host, const int32_t* seg_len_host, int32_t n_seg, float* emb_host) {
+  int32_t ticket = -1;
+  int rc = xv_submit_host(m, feats_host, seg_len_host, n_seg, emb_host, &ticket);
+  if (rc != XV_OK) return rc;
+  return xv_collect(m, ticket);
 }
 
 int xv_check_overflow(xv_model* m, void* stream) {

@@ -204,10 +204,10 @@ class Model(object):
         batch_frames = int(os.environ.get("XVEC_BATCH_FRAMES", "400000"))
         rank, world = sharding.dist_info()
 
-        # two page-locked staging buffers: the reader thread fills one while the GPU works on the other
+        # page-locked staging buffers: the reader thread fills one while two batches are in flight on the GPU
         staging = _Staging(feat_dim, batch_frames)
         counters = dict(total_segments=0, total_segments_len=0, num_fail=0, num_success=0)
-        work = queue.Queue(maxsize=2)
+        work = queue.Queue(maxsize=_Staging.SLOTS)
         failure = []
 
         def reader():
@@ -224,22 +224,33 @@ class Model(object):
 
         total_gpu_waiting = 0.0
         local_index, local_emb, local_keys = [], [], []
+        pending = None                       # (ticket, batch, pinned embedding buffer) of the submission in flight
         while True:
             batch = work.get()
+            submitted = None
+            if batch is not None:
+                feats = staging.view(batch.slot, batch.n_frames)
+                emb_buf = staging.emb_view(batch.slot, len(batch.seg_lens), emb_dim)
+                gpu_waiting = time.time()
+                ticket = engine.submit_host(feats, np.asarray(batch.seg_lens, dtype=np.int32), emb_buf)
+                total_gpu_waiting += time.time() - gpu_waiting
+                submitted = (ticket, batch, emb_buf)
+            if pending is not None:          # batch k-1 finishes while batch k copies in / computes
+                ticket, done, seg_emb = pending
+                gpu_waiting = time.time()
+                engine.collect(ticket)
+                total_gpu_waiting += time.time() - gpu_waiting
+                out = _average_chunks(seg_emb, done.utts)
+                staging.release(done.slot)
+                if world == 1:
+                    _write_vectors(output_stream, [u[1] for u in done.utts], out)
+                else:
+                    local_index.extend(u[0] for u in done.utts)
+                    local_keys.extend(u[1] for u in done.utts)
+                    local_emb.append(out)
+            pending = submitted
             if batch is None:
                 break
-            feats = staging.view(batch.slot, batch.n_frames)
-            gpu_waiting = time.time()
-            seg_emb = engine.extract_host(feats, np.asarray(batch.seg_lens, dtype=np.int32))
-            total_gpu_waiting += time.time() - gpu_waiting
-            staging.release(batch.slot)
-            out = _average_chunks(seg_emb, batch.utts)
-            if world == 1:
-                _write_vectors(output_stream, [u[1] for u in batch.utts], out)
-            else:
-                local_index.extend(u[0] for u in batch.utts)
-                local_keys.extend(u[1] for u in batch.utts)
-                local_emb.append(out)
         thread.join()
         if failure:
             raise failure[0]
@@ -338,29 +349,37 @@ def _average_chunks(seg_emb, utts):
 
 
 class _Staging(object):
-    """Two page-locked [cap, feat_dim] float32 buffers cycled between reader and GPU loop."""
+    """Three page-locked [cap, feat_dim] float32 buffers (+ one pinned embedding buffer each) cycled
+    between the reader thread and the GPU loop: one being filled, two in flight."""
+    SLOTS = 3
 
     def __init__(self, feat_dim, cap_frames):
         self.feat_dim = feat_dim
         self.free = queue.Queue()
-        self.bufs = [None, None]
-        self.caps = [0, 0]
-        for s in (0, 1):
+        self.bufs = [None] * self.SLOTS
+        self.caps = [0] * self.SLOTS
+        self.embs = [None] * self.SLOTS
+        for s in range(self.SLOTS):
             self.free.put(s)
         self._cap0 = cap_frames
 
-    def _alloc(self, frames):
+    def _alloc(self, rows, cols):
         try:
             import torch
-            return torch.empty((frames, self.feat_dim), dtype=torch.float32, pin_memory=torch.cuda.is_available()).numpy()
+            return torch.empty((rows, cols), dtype=torch.float32, pin_memory=torch.cuda.is_available()).numpy()
         except ImportError:
-            return np.empty((frames, self.feat_dim), dtype=np.float32)
+            return np.empty((rows, cols), dtype=np.float32)
+
+    def emb_view(self, slot, n_seg, emb_dim):
+        if self.embs[slot] is None or self.embs[slot].shape[0] < n_seg or self.embs[slot].shape[1] != emb_dim:
+            self.embs[slot] = self._alloc(max(n_seg * 2, 1024), emb_dim)
+        return self.embs[slot][:n_seg]
 
     def acquire(self, need_frames):
         slot = self.free.get()
         if self.caps[slot] < need_frames:
             cap = max(need_frames, self._cap0)
-            self.bufs[slot] = self._alloc(cap)
+            self.bufs[slot] = self._alloc(cap, self.feat_dim)
             self.caps[slot] = cap
         return slot
 
