@@ -92,6 +92,24 @@ def test_embedding_parity_ragged_batch(topology, weight_set):
     eng.close()
 
 
+@pytest.mark.parametrize("opts", [dict(resident=1), dict(pipeline=1)])
+def test_alternative_kernel_schedules_give_the_same_embeddings(opts):
+    # weight-stationary schedule of the CTA-pair kernel / first-generation single-CTA kernels: same arithmetic
+    # per output element, so results must stay within the parity gate (and very close to the default path)
+    eng, params = _engine("ModelWithoutDropoutTdnn", "B")
+    lens = np.array([300, 90, 411, 25, 640], np.int32)
+    feats = synthetic.mfcc_batch(6, lens)
+    base = _run(eng, feats, lens)
+    for k, v in opts.items():
+        eng.set_option(k, v)
+    alt = _run(eng, feats, lens)
+    want = _oracle_batch(feats, lens, params, "ModelWithoutDropoutTdnn")
+    m = orc.parity_metrics(alt, want)
+    assert m["max_rel"] <= TOL and m["l2_rel"] <= TOL, m
+    assert orc.parity_metrics(alt, base)["max_rel"] <= 2e-4
+    eng.close()
+
+
 def test_config1_single_200_frame_utterance():
     # BASELINE.json configs[0]: one 200 x 23 utterance, seed 1
     eng, params = _engine("ModelWithoutDropout", "A")

@@ -39,7 +39,7 @@ __device__ __forceinline__ int find_segment(const int32_t* __restrict__ row_star
 constexpr int PACK_ROWS_PER_BLOCK = 32;      // = one aligned pooling block: rows of ONE segment (or gap)
 constexpr int PACK_THREADS = 256;
 constexpr int PACK_MAX_STAGE_FLOATS = 4096; // (32 + 2*halo0) * feat_dim floats staged per CTA
-constexpr int PACK_MAX_K0 = 512;
+constexpr int PACK_MAX_K0 = 512;             // k0_pad / 8 pieces per row must divide into 256 threads
 
 struct PackArgs {
   const float* feats;        // [total_frames, D]
@@ -55,13 +55,13 @@ struct PackArgs {
   int32_t n_counters;
 };
 
-// One CTA per aligned 32-row block.  The block's feature rows (plus the first layer's context)
-// are staged in shared memory with coalesced loads; out-of-segment rows are staged as zeros,
-// which is TF's SAME padding (models.py:476).  Each thread then emits 16-byte pieces of the
-// spliced fp16 rows through a per-column lookup table (tap offset, ceps index).
+// One CTA per aligned 32-row block.  The block's feature rows (plus the first layer's context) are
+// one contiguous span of the caller's matrix: they are staged in shared memory with coalesced
+// loads, out-of-segment rows as zeros, which is TF's SAME padding (models.py:476).  Thread
+// (row, piece) then emits 16-byte pieces of the spliced fp16 rows; the (tap, ceps) -> staged
+// offset table of its piece lives in registers.
 __global__ void __launch_bounds__(PACK_THREADS) pack_im2col_kernel(const PackArgs a) {
   __shared__ float s_feat[PACK_MAX_STAGE_FLOATS];
-  __shared__ int16_t s_lut[PACK_MAX_K0];
   const int r0 = blockIdx.x * PACK_ROWS_PER_BLOCK;
   const int gtid = blockIdx.x * PACK_THREADS + threadIdx.x;
   if (gtid < a.n_counters) a.counters[gtid] = 0u;
@@ -78,11 +78,6 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_im2col_kernel(const PackArg
     nv = min(PACK_ROWS_PER_BLOCK, len - t0);         // >= 1 by construction of blk_seg
   }
   if (threadIdx.x == 0) a.blk_valid[blockIdx.x] = uint8_t(nv);
-  const int k_real = a.taps * D;
-  for (int ch = threadIdx.x; ch < a.k0_pad; ch += PACK_THREADS) {
-    const int j = ch / D, c = ch - j * D;
-    s_lut[ch] = (ch < k_real) ? int16_t(j * a.dilation * D + c) : int16_t(-1);
-  }
   if (threadIdx.x < PACK_ROWS_PER_BLOCK) a.row_valid[r0 + threadIdx.x] = threadIdx.x < nv ? 1 : 0;
   const int pieces = a.k0_pad >> 3;                                   // 16-byte pieces per row
   if (nv == 0) {                                                      // gap / tail block: zero rows
@@ -90,26 +85,34 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_im2col_kernel(const PackArg
       reinterpret_cast<uint4*>(a.x0 + int64_t(r0) * a.k0_pad)[idx] = make_uint4(0u, 0u, 0u, 0u);
     return;
   }
-  const int stage_rows = PACK_ROWS_PER_BLOCK + 2 * halo;              // frames t0-halo .. t0+31+halo
-  for (int idx = threadIdx.x; idx < stage_rows * D; idx += PACK_THREADS) {
-    const int sr = idx / D;
-    const int tt = t0 - halo + sr;
-    s_feat[idx] = (tt >= 0 && tt < len) ? __ldg(a.feats + (fs + tt) * D + (idx - sr * D)) : 0.f;
+  // stage frames t0-halo .. t0+31+halo: staged float i is feats[(fs + t0 - halo) * D + i] when its frame exists
+  const int n_stage = (PACK_ROWS_PER_BLOCK + 2 * halo) * D;
+  const int lo = max(0, halo - t0) * D, hi = min(PACK_ROWS_PER_BLOCK + 2 * halo, len - t0 + halo) * D;
+  const float* src0 = a.feats + (fs + t0 - halo) * D;
+  for (int i = threadIdx.x; i < n_stage; i += PACK_THREADS) s_feat[i] = (i >= lo && i < hi) ? __ldg(src0 + i) : 0.f;
+  const int k_real = a.taps * D;
+  const int rows_per_pass = PACK_THREADS / pieces;                    // k0_pad <= 512 -> pieces <= 64
+  const int pc = threadIdx.x % pieces, lr0 = threadIdx.x / pieces;
+  int lut[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int ch = pc * 8 + e, j = ch / D;
+    lut[e] = ch < k_real ? j * a.dilation * D + (ch - j * D) : -1;
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < PACK_ROWS_PER_BLOCK * pieces; idx += PACK_THREADS) {
-    const int lr = idx / pieces, pc = idx - lr * pieces;
-    uint32_t w[4] = {0u, 0u, 0u, 0u};
-    if (lr < nv) {
-      const float* src = s_feat + lr * D;
+  if (lr0 < rows_per_pass) {
+    for (int lr = lr0; lr < PACK_ROWS_PER_BLOCK; lr += rows_per_pass) {
+      uint32_t w[4] = {0u, 0u, 0u, 0u};
+      if (lr < nv) {
+        const float* src = s_feat + lr * D;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int l0 = s_lut[pc * 8 + 2 * e], l1 = s_lut[pc * 8 + 2 * e + 1];
-        const __half2 h = __floats2half2_rn(l0 >= 0 ? src[l0] : 0.f, l1 >= 0 ? src[l1] : 0.f);
-        w[e] = *reinterpret_cast<const uint32_t*>(&h);
+        for (int e = 0; e < 4; ++e) {
+          const __half2 h = __floats2half2_rn(lut[2 * e] >= 0 ? src[lut[2 * e]] : 0.f, lut[2 * e + 1] >= 0 ? src[lut[2 * e + 1]] : 0.f);
+          w[e] = *reinterpret_cast<const uint32_t*>(&h);
+        }
       }
+      reinterpret_cast<uint4*>(a.x0 + int64_t(r0 + lr) * a.k0_pad)[pc] = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    reinterpret_cast<uint4*>(a.x0 + int64_t(r0 + lr) * a.k0_pad)[pc] = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 

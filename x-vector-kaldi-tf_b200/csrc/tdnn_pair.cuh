@@ -41,16 +41,14 @@ constexpr int TILE_CH = 256;                       // output channels per tile (
 constexpr int CTA_ROWS = 128;
 constexpr int CTA_CH = 128;
 constexpr int BLOCK_K = 64;                        // fp16 elements = one 128-byte swizzle row (one TMA box / UMMA atom)
-constexpr int STAGE_K = 128;                       // K per pipeline stage = 2 atoms: 8 UMMAs per barrier round trip
-constexpr int ATOMS = STAGE_K / BLOCK_K;
-constexpr int UMMA_K = 16;
+constexpr int UMMA_K = 16;                         // K per pipeline stage = ATOMS x 64 (template parameter):
+                                                   //   2 atoms (8 UMMAs per barrier round trip) when weights stream,
+                                                   //   1 atom when the weights of the channel tile stay resident
 constexpr int ACT_BOX_ROWS_PLAIN = CTA_ROWS;
 constexpr int ACT_BOX_ROWS_REUSE = CTA_ROWS + 8;   // supports half contexts <= 4 rows
 constexpr int MAX_REUSE_HALO = 4;
 constexpr int ACT_ATOM_BYTES = ACT_BOX_ROWS_REUSE * 128;    // 17408
 constexpr int WGT_ATOM_BYTES = CTA_CH * 128;                // 16384
-constexpr int ACT_STAGE_BYTES = ATOMS * ACT_ATOM_BYTES;     // 34816
-constexpr int WGT_STAGE_BYTES = ATOMS * WGT_ATOM_BYTES;     // 32768
 constexpr int RING_BYTES = 184320;                 // activation + weight rings (carved at run time); the pooled
                                                    // mode has no output staging and may also use the 32 KB after it
 constexpr int MAX_STAGES = 8;
@@ -75,14 +73,16 @@ static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of dynamic shared memory");
 struct PairArgs {
   int32_t n_row_tiles;      // R_pad / 256
   int32_t n_ch_tiles;       // C_out / 256
-  int32_t c_chunks;         // C_in_pad / 128
+  int32_t c_chunks;         // C_in_pad / (ATOMS * 64)
   int32_t taps;
   int32_t dilation;
   int32_t c_in_pad;         // column stride between taps in the packed weight matrix
   int32_t reuse;            // 0 / 1 (see header comment)
-  int32_t n_act_stages;     // n_act * 34816 + n_wgt * 32768 <= RING_BYTES (+ 32768 in mode 1)
+  int32_t n_act_stages;     // n_act * ATOMS * 17408 + n_wgt * ATOMS * 16384 <= RING_BYTES (+ 32768 in mode 1)
   int32_t n_wgt_stages;
   int32_t mode;             // 0 store, 1 pool
+  int32_t wgt_resident;     // 1: n_wgt_stages == taps * c_chunks; every cluster owns ONE channel tile, loads its
+                            //    weights once and streams activations only (halves the bytes an SM must ingest)
   int32_t c_out;
   const float* bias;        // [C_out]  conv bias b
   const float* scale;       // [C_out]  gamma * rsqrt(var + eps)
@@ -114,17 +114,20 @@ __device__ __forceinline__ void epi_store_math(const uint32_t (&v)[32], uint32_t
   }
 }
 
-template <int MODE>
+template <int MODE, int ATOMS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations in  [R_pad, C_in_pad] fp16
                  const __grid_constant__ CUtensorMap tmap_wgt,   // weights [C_out, taps*C_in_pad] fp16 (K-major)
                  const __grid_constant__ CUtensorMap tmap_out,   // activations out [R_pad, C_out] fp16 (mode 0)
                  const PairArgs args) {
+  constexpr int STAGE_K = ATOMS * BLOCK_K;
+  constexpr int ACT_STAGE_BYTES = ATOMS * ACT_ATOM_BYTES;     // multiples of 1024: stages stay swizzle-aligned
+  constexpr int WGT_STAGE_BYTES = ATOMS * WGT_ATOM_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t smem_base = ptx::smem_u32(smem);
   const uint32_t sAct = smem_base + OFF_RING;
-  const uint32_t sWgt = sAct + uint32_t(args.n_act_stages) * ACT_STAGE_BYTES;   // 34816 = 34 * 1024: stays aligned
+  const uint32_t sWgt = sAct + uint32_t(args.n_act_stages) * ACT_STAGE_BYTES;
   const uint32_t bar0 = smem_base + OFF_BARS;
   auto act_full = [&](uint32_t s) { return bar0 + 8u * s; };
   auto act_empty = [&](uint32_t s) { return bar0 + 8u * (MAX_STAGES + s); };
@@ -161,7 +164,16 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const int total_tiles = args.n_row_tiles * args.n_ch_tiles;
+  // Work items of this cluster.  Streaming weights: item = tile index (channel tile fastest, so that
+  // neighbouring clusters share activation rows in L2).  Resident weights: the cluster keeps channel tile
+  // cluster_id % n_ch_tiles and its items are row tiles.
+  const bool resident = args.wgt_resident != 0;
+  const int my_ch_tile = cluster_id % args.n_ch_tiles;
+  const int n_items = resident ? args.n_row_tiles : args.n_row_tiles * args.n_ch_tiles;
+  const int item_first = resident ? cluster_id / args.n_ch_tiles : cluster_id;
+  const int item_step = resident ? n_clusters / args.n_ch_tiles : n_clusters;     // host: n_clusters % n_ch_tiles == 0
+  auto row_tile_of = [&](int item) { return resident ? item : item / args.n_ch_tiles; };
+  auto ch_tile_of = [&](int item) { return resident ? my_ch_tile : item % args.n_ch_tiles; };
   const int half_ctx = (args.taps - 1) >> 1;
   const int halo = half_ctx * args.dilation;
   const bool reuse = args.reuse != 0;
@@ -173,9 +185,10 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
     uint32_t sa = 0, pa = 0, sb = 0, pb = 0;         // stage index / phase of each ring
     const uint32_t act_full_leader = ptx::mapa_cluster(act_full(0), 0);   // transaction bytes are counted there
     const uint32_t wgt_full_leader = ptx::mapa_cluster(wgt_full(0), 0);
-    for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
-      const int r0 = (tile / args.n_ch_tiles) * TILE_ROWS + int(rank) * CTA_ROWS;
-      const int c0 = (tile % args.n_ch_tiles) * TILE_CH + int(rank) * CTA_CH;
+    for (int item = item_first; item < n_items; item += item_step) {
+      const int r0 = row_tile_of(item) * TILE_ROWS + int(rank) * CTA_ROWS;
+      const int c0 = ch_tile_of(item) * TILE_CH + int(rank) * CTA_CH;
+      const bool load_wgt = !resident || item == item_first;
       for (int cc = 0; cc < args.c_chunks; ++cc) {
         for (int j = 0; j < args.taps; ++j) {
           if (!reuse || j == 0) {
@@ -191,15 +204,17 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
             __syncwarp();
             if (++sa == n_act) { sa = 0; pa ^= 1u; }
           }
-          ptx::mbar_wait(wgt_empty(sb), pb ^ 1u);
-          if (ptx::elect_one()) {
-            if (leader) ptx::mbar_arrive_expect_tx(wgt_full(sb), 2u * WGT_STAGE_BYTES);
+          if (load_wgt) {
+            ptx::mbar_wait(wgt_empty(sb), pb ^ 1u);
+            if (ptx::elect_one()) {
+              if (leader) ptx::mbar_arrive_expect_tx(wgt_full(sb), 2u * WGT_STAGE_BYTES);
 #pragma unroll
-            for (int h = 0; h < ATOMS; ++h)
-              ptx::tma_load_2d_2sm(sWgt + sb * WGT_STAGE_BYTES + h * WGT_ATOM_BYTES, &tmap_wgt, wgt_full_leader + 8u * sb,
-                                   j * args.c_in_pad + cc * STAGE_K + h * BLOCK_K, c0);
+              for (int h = 0; h < ATOMS; ++h)
+                ptx::tma_load_2d_2sm(sWgt + sb * WGT_STAGE_BYTES + h * WGT_ATOM_BYTES, &tmap_wgt, wgt_full_leader + 8u * sb,
+                                     j * args.c_in_pad + cc * STAGE_K + h * BLOCK_K, c0);
+            }
+            __syncwarp();
           }
-          __syncwarp();
           if (++sb == n_wgt) { sb = 0; pb ^= 1u; }
         }
       }
@@ -213,8 +228,9 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
       // any 128-byte row of the activation slab
       const uint64_t desc_hi = ptx::make_sw128_kmajor_desc(0);
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
-      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
+      for (int item = item_first; item < n_items; item += item_step, ++it) {
         const uint32_t acc = it & 1u;
+        const bool wait_wgt = !resident || it == 0;                    // resident weights land once, in phase 0
         ptx::mbar_wait_cluster(t_empty(acc), ((it >> 1) & 1u) ^ 1u);   // both CTAs' epilogues drained it
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * TILE_CH;
@@ -222,7 +238,7 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
         for (int cc = 0; cc < args.c_chunks; ++cc) {
           for (int j = 0; j < args.taps; ++j) {
             if (!reuse || j == 0) ptx::mbar_wait(act_full(sa), pa);
-            ptx::mbar_wait(wgt_full(sb), pb);
+            if (wait_wgt) ptx::mbar_wait(wgt_full(sb), pb);
             ptx::tc_fence_after();
             const uint32_t act_addr = sAct + sa * ACT_STAGE_BYTES + (reuse ? uint32_t(j * args.dilation) * 128u : 0u);
             const uint32_t wgt_addr = sWgt + sb * WGT_STAGE_BYTES;
@@ -239,7 +255,7 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
                   else ptx::umma_f16_2sm(d_tmem, da, dw, idesc, accumulate | uint32_t(h | k));
                 }
               }
-              ptx::umma_commit_2sm(wgt_empty(sb));                     // weight slot free in both CTAs
+              if (!resident) ptx::umma_commit_2sm(wgt_empty(sb));      // weight slot free in both CTAs
               if (!reuse || j == args.taps - 1) ptx::umma_commit_2sm(act_empty(sa));
             }
             __syncwarp();
@@ -266,10 +282,10 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
       const uint32_t sC = smem_base + OFF_C + uint32_t(e) * 2 * C_BUF_BYTES;
       const uint32_t swz = (uint32_t(lane) >> 1) & 3u;   // SWIZZLE_64B phase of this row in the staging box
       uint32_t hmax = 0;
-      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
+      for (int item = item_first; item < n_items; item += item_step, ++it) {
         const uint32_t acc = it & 1u;
-        const int r_cta = (tile / args.n_ch_tiles) * TILE_ROWS + int(rank) * CTA_ROWS;
-        const int ch0 = (tile % args.n_ch_tiles) * TILE_CH;
+        const int r_cta = row_tile_of(item) * TILE_ROWS + int(rank) * CTA_ROWS;
+        const int ch0 = ch_tile_of(item) * TILE_CH;
         const uint32_t s_par = smem_base + OFF_PARAMS + acc * (3 * TILE_CH * 4);
         ptx::sts_f(s_par + uint32_t(te) * 4u, __ldg(args.bias + ch0 + te));
         ptx::sts_f(s_par + uint32_t(TILE_CH + te) * 4u, __ldg(args.scale + ch0 + te));
@@ -314,10 +330,10 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
       if (lane == 0) ptx::tma_store_wait_all<0>();
       if ((hmax & 0x7fffu) >= 0x7c00u || ((hmax >> 16) & 0x7fffu) >= 0x7c00u) atomicOr(args.overflow_flag, 1u);
     } else {
-      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
+      for (int item = item_first; item < n_items; item += item_step, ++it) {
         const uint32_t acc = it & 1u;
-        const int r_tile = (tile / args.n_ch_tiles) * TILE_ROWS;
-        const int ch = (tile % args.n_ch_tiles) * TILE_CH + int(rank) * CTA_CH + q * 32 + lane;
+        const int r_tile = row_tile_of(item) * TILE_ROWS;
+        const int ch = ch_tile_of(item) * TILE_CH + int(rank) * CTA_CH + q * 32 + lane;
         const float b = __ldg(args.bias + ch), sc = __ldg(args.scale + ch), sh = __ldg(args.shift + ch);
         const int blk0 = (r_tile + colh * 128) / POOL_BLOCK;
         const uint32_t nv4 = *reinterpret_cast<const uint32_t*>(args.blk_valid + blk0);   // 4 blocks, 1 byte each

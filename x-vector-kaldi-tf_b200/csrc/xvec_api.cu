@@ -101,6 +101,8 @@ struct xv_model {
   int opt_desc_base_offset = 1;
   int opt_pipeline = 2;              // 2: CTA-pair kernels + pooled last layer; 1: first-generation single-CTA kernels
   int num_clusters = 74;             // co-resident CTA pairs of tdnn_pair_kernel
+  int opt_resident = 0;              // 1: keep a channel tile's weights resident in shared memory when they fit
+                                     // (measured on B200: no faster than streaming 128-wide stages; kept as an option)
   int opt_profile = 0;               // 1: bracket every kernel launch with CUDA events (bench / diagnostics)
   std::vector<cudaEvent_t> prof_events;   // 2 per launch, in launch order
   int prof_used = 0;
@@ -363,16 +365,20 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       if (rc != XV_OK) return rc;
       rc = encode_2d(m, &tc, out, uint64_t(L.c_out), uint64_t(r_pad), tdnn2::C_CHUNK, 32, CU_TENSOR_MAP_SWIZZLE_64B);
       if (rc != XV_OK) return rc;
+      // Weights of one channel tile fit in shared memory next to an activation ring when K_total <= 512
+      // (every k=1 layer and the spliced first layer): keep them resident, stream activations in 64-wide
+      // stages.  Otherwise stream both operands in 128-wide stages.
+      const int64_t ring_cap = tdnn2::RING_BYTES;
+      const int n_ch_tiles = L.c_out / tdnn2::TILE_CH;
+      const int k_atoms = L.gemm_taps * (c_in_gemm / tdnn2::BLOCK_K);
+      bool resident = m->opt_resident && k_atoms <= tdnn2::MAX_STAGES && m->num_clusters >= n_ch_tiles;
       tdnn2::PairArgs a{};
       a.n_row_tiles = int32_t(r_pad / tdnn2::TILE_ROWS);
-      a.n_ch_tiles = L.c_out / tdnn2::TILE_CH;
-      a.c_chunks = c_in_gemm / tdnn2::STAGE_K;
+      a.n_ch_tiles = n_ch_tiles;
       a.taps = L.gemm_taps;
       a.dilation = L.dilation;
       a.c_in_pad = c_in_gemm;
       a.reuse = reuse ? 1 : 0;
-      a.n_act_stages = 2;                                  // 2 x 34816 + 3 x 32768 = 167936 <= RING_BYTES
-      a.n_wgt_stages = 3;
       a.c_out = L.c_out;
       a.bias = L.bias_dev;
       a.scale = L.scale_dev;
@@ -381,16 +387,29 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       a.blk_valid = blk_valid;
       a.partial = pool_partial;
       a.overflow_flag = m->overflow_dev;
+      a.wgt_resident = resident ? 1 : 0;
+      const int atoms = resident ? 1 : 2;
+      a.c_chunks = c_in_gemm / (atoms * tdnn2::BLOCK_K);
       const int64_t tiles = int64_t(a.n_row_tiles) * a.n_ch_tiles;
-      const int grid = 2 * int(std::min<int64_t>(tiles, m->num_clusters));
+      const int n_cl = resident ? (m->num_clusters / n_ch_tiles) * n_ch_tiles : int(std::min<int64_t>(tiles, m->num_clusters));
+      const int grid = 2 * n_cl;
       // last layer: pooled partial sums (mode 1); its activation is only stored when a caller asks for it
       for (int mode = last ? 1 : 0; mode >= 0; --mode) {
         if (last && mode == 0 && !want_last) break;
         a.mode = mode;
-        a.n_act_stages = mode == 1 ? 3 : 2;                // the pooled mode has no output staging: 32 KB more ring
+        const int64_t cap = ring_cap + (mode == 1 ? 32768 : 0);          // the pooled mode has no output staging
+        if (resident) {
+          a.n_wgt_stages = k_atoms;
+          a.n_act_stages = int(std::min<int64_t>(tdnn2::MAX_STAGES, (cap - int64_t(k_atoms) * tdnn2::WGT_ATOM_BYTES) / tdnn2::ACT_ATOM_BYTES));
+        } else {
+          a.n_act_stages = mode == 1 ? 3 : 2;
+          a.n_wgt_stages = 3;
+        }
         XV_PROF();
-        if (mode == 1) tdnn2::tdnn_pair_kernel<1><<<grid, tdnn2::NUM_THREADS, tdnn2::SMEM_BYTES, stream>>>(ta, tw, tc, a);
-        else tdnn2::tdnn_pair_kernel<0><<<grid, tdnn2::NUM_THREADS, tdnn2::SMEM_BYTES, stream>>>(ta, tw, tc, a);
+        if (mode == 1 && resident) tdnn2::tdnn_pair_kernel<1, 1><<<grid, tdnn2::NUM_THREADS, tdnn2::SMEM_BYTES, stream>>>(ta, tw, tc, a);
+        else if (mode == 1) tdnn2::tdnn_pair_kernel<1, 2><<<grid, tdnn2::NUM_THREADS, tdnn2::SMEM_BYTES, stream>>>(ta, tw, tc, a);
+        else if (resident) tdnn2::tdnn_pair_kernel<0, 1><<<grid, tdnn2::NUM_THREADS, tdnn2::SMEM_BYTES, stream>>>(ta, tw, tc, a);
+        else tdnn2::tdnn_pair_kernel<0, 2><<<grid, tdnn2::NUM_THREADS, tdnn2::SMEM_BYTES, stream>>>(ta, tw, tc, a);
         XV_PROF();
         XV_CUDA(cudaGetLastError());
         ++launches;
@@ -523,7 +542,7 @@ int xv_create(xv_model** out, int device, const xv_topology* topo) {
   if (t.width[t.n_frame_layers - 1] % xvk::POOL_SLAB != 0) return fail(XV_EINVAL, "last width must be a multiple of 128");
   {
     const int halo0 = (t.taps[0] - 1) / 2 * t.dilation[0];
-    const int64_t k0 = round_up(int64_t(t.taps[0]) * t.feat_dim, tdnn2::STAGE_K);
+    const int64_t k0 = round_up(int64_t(t.taps[0]) * t.feat_dim, (2 * tdnn2::BLOCK_K));
     if ((xvk::PACK_ROWS_PER_BLOCK + 2 * halo0) * int64_t(t.feat_dim) > xvk::PACK_MAX_STAGE_FLOATS || k0 > xvk::PACK_MAX_K0 ||
         int64_t(t.taps[0]) * t.dilation[0] * t.feat_dim > 32000)
       return fail(XV_EINVAL, "first layer too wide for the pack kernel (taps*feat_dim must be <= 512)");
@@ -551,7 +570,7 @@ int xv_create(xv_model** out, int device, const xv_topology* topo) {
     L.c_out = t.width[i];
     if (i == 0) {                          // spliced (im2col) input: dense K, padded to a multiple of 64
       L.c_in_pad = prev;
-      L.k_total = int(round_up(int64_t(L.taps) * prev, tdnn2::STAGE_K));
+      L.k_total = int(round_up(int64_t(L.taps) * prev, (2 * tdnn2::BLOCK_K)));
       L.gemm_taps = 1;
       m->k0_pad = L.k_total;
     } else {
@@ -574,9 +593,13 @@ int xv_create(xv_model** out, int device, const xv_topology* topo) {
   m->encode = reinterpret_cast<EncodeTiledFn>(fn);
   e = cudaFuncSetAttribute(tdnn::tdnn_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn::SMEM_BYTES);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(tdnn2::tdnn_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
+    e = cudaFuncSetAttribute(tdnn2::tdnn_pair_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(tdnn2::tdnn_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
+    e = cudaFuncSetAttribute(tdnn2::tdnn_pair_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(tdnn2::tdnn_pair_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(tdnn2::tdnn_pair_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
   if (e == cudaSuccess) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * (prop.multiProcessorCount / 2));
@@ -589,7 +612,7 @@ int xv_create(xv_model** out, int device, const xv_topology* topo) {
     attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    cudaError_t qe = cudaOccupancyMaxActiveClusters(&n_clusters, tdnn2::tdnn_pair_kernel<0>, &cfg);
+    cudaError_t qe = cudaOccupancyMaxActiveClusters(&n_clusters, tdnn2::tdnn_pair_kernel<0, 2>, &cfg);
     if (qe != cudaSuccess || n_clusters <= 0) { (void)cudaGetLastError(); n_clusters = prop.multiProcessorCount / 2; }
     m->num_clusters = std::min(n_clusters, prop.multiProcessorCount / 2);
   }
@@ -788,6 +811,7 @@ int xv_set_option(xv_model* m, const char* name, int64_t value) {
   if (n == "reuse_taps") m->opt_reuse = value != 0;
   else if (n == "desc_base_offset") m->opt_desc_base_offset = value != 0;
   else if (n == "profile") m->opt_profile = value != 0;
+  else if (n == "resident") m->opt_resident = value != 0;
   else if (n == "pipeline") {
     if (value != 1 && value != 2) return fail(XV_EINVAL, "pipeline must be 1 or 2");
     m->opt_pipeline = int(value);
