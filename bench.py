@@ -72,6 +72,19 @@ def load_peaks():
     return dict(hbm_gbs=6650.0, tflops=1590.0, tflops_sustained=1400.0, source="fallback")
 
 
+def ncu_traffic_bytes():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the fused TDNN layer kernel, averaged
+    over its captured launches, from the committed `ncu --set full` summary under profiles/ (None if absent)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_summary.json")))
+    if not files:
+        return None, None
+    with open(files[-1]) as f:
+        rows = [r for r in json.load(f) if "tdnn_pair_kernel" in r.get("kernel", "")]
+    vals = [(r["dram_read_MB"] + r["dram_write_MB"]) * 1e6 for r in rows if r.get("dram_read_MB") is not None]
+    return (round(sum(vals) / len(vals)) if vals else None), os.path.basename(files[-1])
+
+
 # ------------------------------------------------------------------------------------ clocks
 BAD_REASONS = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown")
 
@@ -299,9 +312,13 @@ def run_b200(args):
         launches.append(d)
     tdnn_ms = float(kms[1:1 + len(fl)].sum())
     tdnn_tf = frames * sum(fl) / (tdnn_ms * 1e-3) / 1e12
+    traffic, traffic_src = ncu_traffic_bytes()
     roofline = dict(kernel="tdnn_pair_kernel (%d launches/step, figures are per-step sums / averages)" % len(fl),
                     bound="tensor", achieved=round(tdnn_tf, 1), peak=peaks["tflops"], unit="TFLOP/s",
-                    frac=round(tdnn_tf / peaks["tflops"], 4), traffic=None,
+                    frac=round(tdnn_tf / peaks["tflops"], 4), traffic=traffic,
+                    traffic_source="profiles/%s: mean DRAM bytes per launch over the kernel's 5 launches (tdnn splice, config 2)"
+                                   % traffic_src if traffic_src else None,
+                    flop_per_launch_avg=round(frames * sum(fl) / len(fl)),
                     peak_source="%s bf16/fp16 burst (MEASURED_PEAKS.json)" % peaks["source"],
                     share_of_step=round(tdnn_ms / float(kms.sum()), 4),
                     step_frac_of_tensor_peak=round(value / world * sum(fl) / 1e12 / peaks["tflops"], 4),
