@@ -49,8 +49,8 @@ constexpr int ACT_BOX_ROWS_REUSE = CTA_ROWS + 8;   // supports half contexts <= 
 constexpr int MAX_REUSE_HALO = 4;
 constexpr int ACT_ATOM_BYTES = ACT_BOX_ROWS_REUSE * 128;    // 17408
 constexpr int WGT_ATOM_BYTES = CTA_CH * 128;                // 16384
-constexpr int RING_BYTES = 184320;                 // activation + weight rings (carved at run time); the pooled
-                                                   // mode has no output staging and may also use the 32 KB after it
+constexpr int RING_BYTES = 200704;                 // activation + weight rings (carved at run time); the pooled
+                                                   // mode has no output staging and may also use the 16 KB after it
 constexpr int MAX_STAGES = 8;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_EPI_THREADS = NUM_EPI_WARPS * 32;
@@ -62,7 +62,7 @@ constexpr int POOL_BLOCK = 32;                     // rows per pooled partial bl
 
 constexpr int OFF_RING = 0;
 constexpr int OFF_C = OFF_RING + RING_BYTES;
-constexpr int OFF_PARAMS = OFF_C + NUM_EPI_WARPS * 2 * C_BUF_BYTES;     // + 32768
+constexpr int OFF_PARAMS = OFF_C + NUM_EPI_WARPS * C_BUF_BYTES;         // + 16384 (one staging box per epilogue warp)
 constexpr int OFF_BARS = OFF_PARAMS + 2 * 3 * TILE_CH * 4;              // + 6144
 constexpr int NUM_BARS = 4 * MAX_STAGES + 4;
 constexpr int OFF_TMEM_PTR = OFF_BARS + NUM_BARS * 8;
@@ -78,9 +78,10 @@ struct PairArgs {
   int32_t dilation;
   int32_t c_in_pad;         // column stride between taps in the packed weight matrix
   int32_t reuse;            // 0 / 1 (see header comment)
-  int32_t n_act_stages;     // n_act * ATOMS * 17408 + n_wgt * ATOMS * 16384 <= RING_BYTES (+ 32768 in mode 1)
+  int32_t n_act_stages;     // n_act * ATOMS * (reuse ? 17408 : 16384) + n_wgt * ATOMS * 16384 <= RING_BYTES (+ 16384 in mode 1)
   int32_t n_wgt_stages;
   int32_t mode;             // 0 store, 1 pool
+  int32_t prefetch;         // 1: warm L2 with the activation boxes of this cluster's next work item
   int32_t wgt_resident;     // 1: n_wgt_stages == taps * c_chunks; every cluster owns ONE channel tile, loads its
                             //    weights once and streams activations only (halves the bytes an SM must ingest)
   int32_t c_out;
@@ -91,7 +92,15 @@ struct PairArgs {
   const uint8_t* blk_valid; // [R_pad/32]  mode 1: valid rows in the block (they are its first rows)
   float* partial;           // [R_pad/32][2][C_out]  mode 1
   uint32_t* overflow_flag;  // set to 1 if an fp16 output overflowed to inf
+  long long* trace;         // diagnostics (tools/trace_tiles.py): [cluster][rank][TRACE_TILES][8] SM clock stamps, or null
 };
+constexpr int TRACE_TILES = 16;
+// slots: 0 producer first load issued, 1 producer last load issued, 2 MMA start (accumulator free),
+//        3 MMA all issued, 4 epilogue sees accumulator, 5 epilogue released accumulator, 6 epilogue done
+__device__ __forceinline__ void trace_stamp(const PairArgs& a, int cluster, uint32_t rank, uint32_t it, int slot) {
+  if (a.trace != nullptr && it < TRACE_TILES)
+    a.trace[((size_t(cluster) * 2 + rank) * TRACE_TILES + it) * 8 + slot] = clock64();
+}
 
 // One tcgen05.ld chunk of the store epilogue: 32 channels of one row -> 16 packed half2.
 // s_par: shared-memory address of this tile's [bias(256) | scale(256) | shift(256)] floats.
@@ -121,12 +130,14 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
                  const __grid_constant__ CUtensorMap tmap_out,   // activations out [R_pad, C_out] fp16 (mode 0)
                  const PairArgs args) {
   constexpr int STAGE_K = ATOMS * BLOCK_K;
-  constexpr int ACT_STAGE_BYTES = ATOMS * ACT_ATOM_BYTES;     // multiples of 1024: stages stay swizzle-aligned
   constexpr int WGT_STAGE_BYTES = ATOMS * WGT_ATOM_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t smem_base = ptx::smem_u32(smem);
   const uint32_t sAct = smem_base + OFF_RING;
+  // activation atom stride: 136 rows when taps are addressed inside the slab, else 128 (both multiples of 1024 B)
+  const uint32_t ACT_ATOM_STRIDE = args.reuse ? uint32_t(ACT_ATOM_BYTES) : uint32_t(ACT_BOX_ROWS_PLAIN * 128);
+  const uint32_t ACT_STAGE_BYTES = ATOMS * ACT_ATOM_STRIDE;
   const uint32_t sWgt = sAct + uint32_t(args.n_act_stages) * ACT_STAGE_BYTES;
   const uint32_t bar0 = smem_base + OFF_BARS;
   auto act_full = [&](uint32_t s) { return bar0 + 8u * s; };
@@ -189,17 +200,27 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
       const int r0 = row_tile_of(item) * TILE_ROWS + int(rank) * CTA_ROWS;
       const int c0 = ch_tile_of(item) * TILE_CH + int(rank) * CTA_CH;
       const bool load_wgt = !resident || item == item_first;
+      const uint32_t pit = uint32_t((item - item_first) / item_step);
       for (int cc = 0; cc < args.c_chunks; ++cc) {
         for (int j = 0; j < args.taps; ++j) {
           if (!reuse || j == 0) {
             ptx::mbar_wait(act_empty(sa), pa ^ 1u);
             if (ptx::elect_one()) {
+              if (cc == 0 && j == 0) trace_stamp(args, cluster_id, rank, pit, 0);
+              if (cc == args.c_chunks - 1) trace_stamp(args, cluster_id, rank, pit, 1);
               if (leader) ptx::mbar_arrive_expect_tx(act_full(sa), 2u * ATOMS * act_box_bytes);   // both CTAs' boxes
               const int row = reuse ? (r0 - halo) : (r0 + (j - half_ctx) * args.dilation);
 #pragma unroll
               for (int h = 0; h < ATOMS; ++h)
-                ptx::tma_load_2d_2sm(sAct + sa * ACT_STAGE_BYTES + h * ACT_ATOM_BYTES, &tmap_act, act_full_leader + 8u * sa,
+                ptx::tma_load_2d_2sm(sAct + sa * ACT_STAGE_BYTES + h * ACT_ATOM_STRIDE, &tmap_act, act_full_leader + 8u * sa,
                                      cc * STAGE_K + h * BLOCK_K, row);
+              // the same boxes of this cluster's NEXT item -> L2 now: with resident weights the ring holds too few
+              // bytes to cover an HBM round trip (~2000 cycles), an L2 hit (~700) it does cover
+              if (args.prefetch && item + item_step < n_items) {
+                const int row_next = row + (row_tile_of(item + item_step) - row_tile_of(item)) * TILE_ROWS;
+#pragma unroll
+                for (int h = 0; h < ATOMS; ++h) ptx::tma_prefetch_l2_2d(&tmap_act, cc * STAGE_K + h * BLOCK_K, row_next);
+              }
             }
             __syncwarp();
             if (++sa == n_act) { sa = 0; pa ^= 1u; }
@@ -228,11 +249,56 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
       // any 128-byte row of the activation slab
       const uint64_t desc_hi = ptx::make_sw128_kmajor_desc(0);
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
+      if (ATOMS == 1 && resident) {
+        // Weight-stationary schedule (host guarantees taps == 1, an even number of 64-wide chunks, weight stage
+        // index == chunk index).  Two activation stages per trip: 8 UMMAs amortise the fixed cost of a trip
+        // (barrier round trip, election, descriptor arithmetic ~ 600 cycles), which 4 UMMAs (512 cycles) do not.
+        for (int item = item_first; item < n_items; item += item_step, ++it) {
+          const uint32_t acc = it & 1u;
+          ptx::mbar_wait_cluster(t_empty(acc), ((it >> 1) & 1u) ^ 1u);
+          ptx::tc_fence_after();
+          if (lane == 0) trace_stamp(args, cluster_id, rank, it, 2);
+          const uint32_t d_tmem = tmem_base + acc * TILE_CH;
+          for (int cc = 0; cc < args.c_chunks; cc += 2) {
+            const bool wrap = sa + 1 == n_act;
+            const uint32_t sa2 = wrap ? 0u : sa + 1u, pa2 = wrap ? pa ^ 1u : pa;
+            ptx::mbar_wait(act_full(sa), pa);
+            ptx::mbar_wait(act_full(sa2), pa2);
+            if (it == 0) { ptx::mbar_wait(wgt_full(cc), 0); ptx::mbar_wait(wgt_full(cc + 1), 0); }
+            ptx::tc_fence_after();
+            const uint64_t d_a0 = desc_hi | uint64_t(((sAct + sa * ACT_STAGE_BYTES) >> 4) & 0x3fffu);
+            const uint64_t d_a1 = desc_hi | uint64_t(((sAct + sa2 * ACT_STAGE_BYTES) >> 4) & 0x3fffu);
+            const uint64_t d_w0 = desc_hi | uint64_t(((sWgt + uint32_t(cc) * WGT_STAGE_BYTES) >> 4) & 0x3fffu);
+            const uint64_t d_w1 = d_w0 + uint64_t(WGT_STAGE_BYTES >> 4);
+            if (ptx::elect_one()) {
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                if (MODE == 1) ptx::umma_f16_2sm(d_tmem, d_w0 + 2u * k, d_a0 + 2u * k, idesc, uint32_t(cc | k));
+                else ptx::umma_f16_2sm(d_tmem, d_a0 + 2u * k, d_w0 + 2u * k, idesc, uint32_t(cc | k));
+              }
+              ptx::umma_commit_2sm(act_empty(sa));
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                if (MODE == 1) ptx::umma_f16_2sm(d_tmem, d_w1 + 2u * k, d_a1 + 2u * k, idesc, 1u);
+                else ptx::umma_f16_2sm(d_tmem, d_a1 + 2u * k, d_w1 + 2u * k, idesc, 1u);
+              }
+              ptx::umma_commit_2sm(act_empty(sa2));
+            }
+            __syncwarp();
+            sa = sa2; pa = pa2;
+            if (++sa == n_act) { sa = 0; pa ^= 1u; }
+          }
+          if (ptx::elect_one()) ptx::umma_commit_2sm(t_full(acc));
+          __syncwarp();
+          if (lane == 0) trace_stamp(args, cluster_id, rank, it, 3);
+        }
+      } else
       for (int item = item_first; item < n_items; item += item_step, ++it) {
         const uint32_t acc = it & 1u;
         const bool wait_wgt = !resident || it == 0;                    // resident weights land once, in phase 0
         ptx::mbar_wait_cluster(t_empty(acc), ((it >> 1) & 1u) ^ 1u);   // both CTAs' epilogues drained it
         ptx::tc_fence_after();
+        if (lane == 0) trace_stamp(args, cluster_id, rank, it, 2);
         const uint32_t d_tmem = tmem_base + acc * TILE_CH;
         uint32_t accumulate = 0;
         for (int cc = 0; cc < args.c_chunks; ++cc) {
@@ -249,7 +315,7 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
               for (int h = 0; h < ATOMS; ++h) {
 #pragma unroll
                 for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {         // +32 bytes of K per UMMA: +2 in the address field
-                  const uint64_t da = d_act + uint64_t(h * (ACT_ATOM_BYTES >> 4) + 2 * k);
+                  const uint64_t da = d_act + uint64_t(h * (ACT_ATOM_STRIDE >> 4) + 2 * k);
                   const uint64_t dw = d_wgt + uint64_t(h * (WGT_ATOM_BYTES >> 4) + 2 * k);
                   if (MODE == 1) ptx::umma_f16_2sm(d_tmem, dw, da, idesc, accumulate | uint32_t(h | k));
                   else ptx::umma_f16_2sm(d_tmem, da, dw, idesc, accumulate | uint32_t(h | k));
@@ -268,6 +334,7 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
         }
         if (ptx::elect_one()) ptx::umma_commit_2sm(t_full(acc));       // accumulator ready in both CTAs
         __syncwarp();
+        if (lane == 0) trace_stamp(args, cluster_id, rank, it, 3);
       }
     }
   } else {
@@ -279,7 +346,7 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
     const uint32_t t_empty_leader = ptx::mapa_cluster(t_empty(0), 0);   // + 8 * acc
     uint32_t it = 0;
     if (MODE == 0) {
-      const uint32_t sC = smem_base + OFF_C + uint32_t(e) * 2 * C_BUF_BYTES;
+      const uint32_t sC = smem_base + OFF_C + uint32_t(e) * C_BUF_BYTES;
       const uint32_t swz = (uint32_t(lane) >> 1) & 3u;   // SWIZZLE_64B phase of this row in the staging box
       uint32_t hmax = 0;
       for (int item = item_first; item < n_items; item += item_step, ++it) {
@@ -294,6 +361,7 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
         ptx::named_bar_sync(1, NUM_EPI_THREADS);       // parameters of this tile visible (double-buffered by acc)
         ptx::mbar_wait(t_full(acc), (it >> 1) & 1u);
         ptx::tc_fence_after();
+        if (e == 0 && lane == 0) trace_stamp(args, cluster_id, rank, it, 4);
         const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * TILE_CH + uint32_t(colh) * 128u;
         uint32_t v[2][32];
         ptx::tmem_ld_32x32(t_row, v[0]);
@@ -306,11 +374,12 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(t_empty_leader + 8u * acc);
+            if (e == 0 && lane == 0) trace_stamp(args, cluster_id, rank, it, 5);
           }
           uint32_t p[16];
           epi_store_math(v[chunk & 1], s_par, colh * 128 + chunk * C_CHUNK, valid, p, hmax);
-          const uint32_t buf = sC + uint32_t(chunk & 1) * C_BUF_BYTES;
-          if (lane == 0) ptx::tma_store_wait_read<1>();   // the store that last used this buffer has read it
+          const uint32_t buf = sC;                        // one box per warp: the previous chunk's store has had the
+          if (lane == 0) ptx::tma_store_wait_read<0>();   // whole tcgen05.ld + math of this chunk to read it
           __syncwarp();
           const uint32_t dst = buf + uint32_t(lane) * (C_CHUNK * 2);
 #pragma unroll
@@ -326,6 +395,7 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
             ptx::tma_store_commit();
           }
         }
+        if (e == 0 && lane == 0) trace_stamp(args, cluster_id, rank, it, 6);
       }
       if (lane == 0) ptx::tma_store_wait_all<0>();
       if ((hmax & 0x7fffu) >= 0x7c00u || ((hmax >> 16) & 0x7fffu) >= 0x7c00u) atomicOr(args.overflow_flag, 1u);
@@ -339,6 +409,7 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
         const uint32_t nv4 = *reinterpret_cast<const uint32_t*>(args.blk_valid + blk0);   // 4 blocks, 1 byte each
         ptx::mbar_wait(t_full(acc), (it >> 1) & 1u);
         ptx::tc_fence_after();
+        if (e == 0 && lane == 0) trace_stamp(args, cluster_id, rank, it, 4);
         const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * TILE_CH + uint32_t(colh) * 128u;
         uint32_t v[2][32];
         ptx::tmem_ld_32x32(t_row, v[0]);
@@ -351,6 +422,7 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(t_empty_leader + 8u * acc);
+            if (e == 0 && lane == 0) trace_stamp(args, cluster_id, rank, it, 5);
           }
           const int nv = int((nv4 >> (8 * chunk)) & 0xffu);          // warp-uniform
           if (nv > 0) {
@@ -376,6 +448,7 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
             dst[args.c_out] = (s2[0] + s2[1]) + (s2[2] + s2[3]);
           }
         }
+        if (e == 0 && lane == 0) trace_stamp(args, cluster_id, rank, it, 6);
       }
     }
   }

@@ -103,6 +103,9 @@ struct xv_model {
   int num_clusters = 74;             // co-resident CTA pairs of tdnn_pair_kernel
   int opt_resident = 0;              // 1: keep a channel tile's weights resident in shared memory when they fit
                                      // (measured on B200: no faster than streaming 128-wide stages; kept as an option)
+  int opt_prefetch = 0;              // L2 prefetch of the next work item's activation boxes
+  long long* opt_trace = nullptr;    // diagnostics: per-tile clock stamps of ONE layer (opt_trace_layer)
+  int opt_trace_layer = -1;
   int opt_profile = 0;               // 1: bracket every kernel launch with CUDA events (bench / diagnostics)
   std::vector<cudaEvent_t> prof_events;   // 2 per launch, in launch order
   int prof_used = 0;
@@ -371,7 +374,8 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       const int64_t ring_cap = tdnn2::RING_BYTES;
       const int n_ch_tiles = L.c_out / tdnn2::TILE_CH;
       const int k_atoms = L.gemm_taps * (c_in_gemm / tdnn2::BLOCK_K);
-      bool resident = m->opt_resident && k_atoms <= tdnn2::MAX_STAGES && m->num_clusters >= n_ch_tiles;
+      bool resident = m->opt_resident && L.gemm_taps == 1 && k_atoms % 2 == 0 && k_atoms <= tdnn2::MAX_STAGES &&
+                      m->num_clusters >= n_ch_tiles;
       tdnn2::PairArgs a{};
       a.n_row_tiles = int32_t(r_pad / tdnn2::TILE_ROWS);
       a.n_ch_tiles = n_ch_tiles;
@@ -387,9 +391,9 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       a.blk_valid = blk_valid;
       a.partial = pool_partial;
       a.overflow_flag = m->overflow_dev;
+      a.trace = (i == m->opt_trace_layer) ? m->opt_trace : nullptr;
       a.wgt_resident = resident ? 1 : 0;
-      const int atoms = resident ? 1 : 2;
-      a.c_chunks = c_in_gemm / (atoms * tdnn2::BLOCK_K);
+      a.prefetch = m->opt_prefetch;
       const int64_t tiles = int64_t(a.n_row_tiles) * a.n_ch_tiles;
       const int n_cl = resident ? (m->num_clusters / n_ch_tiles) * n_ch_tiles : int(std::min<int64_t>(tiles, m->num_clusters));
       const int grid = 2 * n_cl;
@@ -397,18 +401,25 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       for (int mode = last ? 1 : 0; mode >= 0; --mode) {
         if (last && mode == 0 && !want_last) break;
         a.mode = mode;
-        const int64_t cap = ring_cap + (mode == 1 ? 32768 : 0);          // the pooled mode has no output staging
+        const int64_t cap = ring_cap + (mode == 1 ? 16384 : 0);          // the pooled mode has no output staging
+        const int64_t act_atom = reuse ? tdnn2::ACT_ATOM_BYTES : tdnn2::ACT_BOX_ROWS_PLAIN * 128;
+        // resident weights: 64-wide stages (opt_resident == 1) or 128-wide stages when two of them still fit (== 2)
+        int atoms = 2;
         if (resident) {
-          a.n_wgt_stages = k_atoms;
-          a.n_act_stages = int(std::min<int64_t>(tdnn2::MAX_STAGES, (cap - int64_t(k_atoms) * tdnn2::WGT_ATOM_BYTES) / tdnn2::ACT_ATOM_BYTES));
-        } else {
-          a.n_act_stages = mode == 1 ? 3 : 2;
-          a.n_wgt_stages = 3;
+          atoms = (m->opt_resident == 2 && cap - int64_t(k_atoms) * tdnn2::WGT_ATOM_BYTES >= 4 * act_atom) ? 2 : 1;
+          a.n_wgt_stages = k_atoms / atoms;
+          a.n_act_stages = int(std::min<int64_t>(tdnn2::MAX_STAGES, (cap - int64_t(k_atoms) * tdnn2::WGT_ATOM_BYTES) / (atoms * act_atom)));
+        } else if (reuse) {                                              // one activation slab feeds `taps` weight stages
+          a.n_act_stages = 2;
+          a.n_wgt_stages = int(std::min<int64_t>(tdnn2::MAX_STAGES, (cap - 2 * 2 * act_atom) / (2 * tdnn2::WGT_ATOM_BYTES)));
+        } else {                                                         // k = 1: activations and weights advance together
+          a.n_act_stages = a.n_wgt_stages = int(std::min<int64_t>(tdnn2::MAX_STAGES, cap / (2 * (act_atom + tdnn2::WGT_ATOM_BYTES))));
         }
+        a.c_chunks = c_in_gemm / (atoms * tdnn2::BLOCK_K);
         XV_PROF();
-        if (mode == 1 && resident) tdnn2::tdnn_pair_kernel<1, 1><<<grid, tdnn2::NUM_THREADS, tdnn2::SMEM_BYTES, stream>>>(ta, tw, tc, a);
+        if (mode == 1 && atoms == 1) tdnn2::tdnn_pair_kernel<1, 1><<<grid, tdnn2::NUM_THREADS, tdnn2::SMEM_BYTES, stream>>>(ta, tw, tc, a);
         else if (mode == 1) tdnn2::tdnn_pair_kernel<1, 2><<<grid, tdnn2::NUM_THREADS, tdnn2::SMEM_BYTES, stream>>>(ta, tw, tc, a);
-        else if (resident) tdnn2::tdnn_pair_kernel<0, 1><<<grid, tdnn2::NUM_THREADS, tdnn2::SMEM_BYTES, stream>>>(ta, tw, tc, a);
+        else if (atoms == 1) tdnn2::tdnn_pair_kernel<0, 1><<<grid, tdnn2::NUM_THREADS, tdnn2::SMEM_BYTES, stream>>>(ta, tw, tc, a);
         else tdnn2::tdnn_pair_kernel<0, 2><<<grid, tdnn2::NUM_THREADS, tdnn2::SMEM_BYTES, stream>>>(ta, tw, tc, a);
         XV_PROF();
         XV_CUDA(cudaGetLastError());
@@ -811,7 +822,10 @@ int xv_set_option(xv_model* m, const char* name, int64_t value) {
   if (n == "reuse_taps") m->opt_reuse = value != 0;
   else if (n == "desc_base_offset") m->opt_desc_base_offset = value != 0;
   else if (n == "profile") m->opt_profile = value != 0;
-  else if (n == "resident") m->opt_resident = value != 0;
+  else if (n == "resident") m->opt_resident = int(value);
+  else if (n == "prefetch") m->opt_prefetch = value != 0;
+  else if (n == "trace_ptr") m->opt_trace = reinterpret_cast<long long*>(static_cast<intptr_t>(value));   // device buffer
+  else if (n == "trace_layer") m->opt_trace_layer = int(value);
   else if (n == "pipeline") {
     if (value != 1 && value != 2) return fail(XV_EINVAL, "pipeline must be 1 or 2");
     m->opt_pipeline = int(value);
