@@ -16,7 +16,7 @@ with the NCCL gather of the [256, 512] embeddings to rank 0, the only collective
          features in, HOST embeddings out, every step's H2D + D2H inside the timed region, two
          steps in flight so the copy of one overlaps the kernels of the previous one.
   roofline      the fused TDNN layer kernel (5 launches/step) against the measured tensor peak;
-                per-launch figures for all 8 launches in roofline.launches.
+                per-launch figures for all launches in roofline.launches.
   cpu_baseline  the reference's CPU path restated in torch fp32 (oracle/xvector_torch_cpu.py --
                 TensorFlow 1.x cannot be installed here), run the way the reference runs it: one
                 utterance per call, 2 threads per process, cores/2 processes
@@ -290,25 +290,27 @@ def run_b200(args):
     kms = np.asarray(per_launch, dtype=np.float64).mean(axis=0)        # [7]
     peaks = load_peaks()
     fl = flop_per_frame(topo)
-    names = ["pack_im2col_kernel"] + ["tdnn_pair_kernel[L%d]" % i for i in range(len(fl))] + ["pool_stats_kernel", "embed_fc_kernel"]
     c_last = topo["layer_sizes"][-1]
-    k0_pad = -(-topo["kernel_sizes"][0] * FEAT_DIM // 64) * 64
+    k0_pad = -(-topo["kernel_sizes"][0] * FEAT_DIM // 128) * 128
+    n_blk = B * (-(-T // 32))
+    # (kernel, bound, algorithmic FLOP or bytes per launch) in launch order
+    table = [("pack_im2col_kernel", "hbm", frames * (FEAT_DIM * 4 + k0_pad * 2 + 1))]
+    table += [("tdnn_pair_kernel[L%d]" % i, "tensor", frames * f) for i, f in enumerate(fl)]
+    table += [("pool_stats_kernel", "hbm", n_blk * 2 * c_last * 4 + B * 2 * c_last * 6)]
+    if len(kms) == len(table) + 2:      # embed_layer-0 on tensor cores: split-fp16 GEMM (3 products) + K-split reduction
+        table += [("tdnn_pair_kernel<2>[embed_layer-0]", "tensor", 2 * B * 2 * c_last * EMB_DIM),
+                  ("embed_reduce_kernel", "hbm", B * EMB_DIM * 4 * 2)]
+    else:
+        table += [("embed_fc_kernel", "hbm", B * 2 * c_last * 4 + 2 * c_last * EMB_DIM * 4 + B * EMB_DIM * 4)]
     launches = []
-    for i, name in enumerate(names):
-        d = dict(kernel=name, ms=round(float(kms[i]), 5))
-        if name.startswith("tdnn"):
-            li = i - 1
-            tf = frames * fl[li] / (kms[i] * 1e-3) / 1e12
-            d.update(bound="tensor", achieved=round(tf, 1), unit="TFLOP/s", frac=round(tf / peaks["tflops"], 4))
+    for (name, bound, work), ms in zip(table, kms):
+        d = dict(kernel=name, ms=round(float(ms), 5), bound=bound)
+        if bound == "tensor":
+            tf = work / (ms * 1e-3) / 1e12
+            d.update(achieved=round(tf, 1), unit="TFLOP/s", frac=round(tf / peaks["tflops"], 4))
         else:
-            if name.startswith("pack"):       # fp32 features in, fp16 spliced rows + row map out
-                nbytes = frames * (FEAT_DIM * 4 + k0_pad * 2 + 1)
-            elif name.startswith("pool"):     # per-32-row-block partial sums in, [mean|std] out
-                nbytes = B * (-(-T // 32)) * 2 * c_last * 4 + B * 2 * c_last * 4
-            else:                             # [mean|std] in, W0 once, embeddings out (fp32 SIMT GEMM, tiny)
-                nbytes = B * 2 * c_last * 4 + 2 * c_last * EMB_DIM * 4 + B * EMB_DIM * 4
-            gbs = nbytes / (kms[i] * 1e-3) / 1e9
-            d.update(bound="hbm", achieved=round(gbs, 1), unit="GB/s", frac=round(gbs / peaks["hbm_gbs"], 4))
+            gbs = work / (ms * 1e-3) / 1e9
+            d.update(achieved=round(gbs, 1), unit="GB/s", frac=round(gbs / peaks["hbm_gbs"], 4))
         launches.append(d)
     tdnn_ms = float(kms[1:1 + len(fl)].sum())
     tdnn_tf = frames * sum(fl) / (tdnn_ms * 1e-3) / 1e12

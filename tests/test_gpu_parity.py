@@ -92,7 +92,7 @@ def test_embedding_parity_ragged_batch(topology, weight_set):
     eng.close()
 
 
-@pytest.mark.parametrize("opts", [dict(resident=1), dict(pipeline=1)])
+@pytest.mark.parametrize("opts", [dict(resident=1), dict(resident=2), dict(fc=0), dict(pipeline=1)])
 def test_alternative_kernel_schedules_give_the_same_embeddings(opts):
     # weight-stationary schedule of the CTA-pair kernel / first-generation single-CTA kernels: same arithmetic
     # per output element, so results must stay within the parity gate (and very close to the default path)
@@ -162,7 +162,7 @@ def test_extract_host_equals_device_forward():
     dev = _run(eng, feats, lens)
     host = eng.extract_host(feats, lens)
     assert np.array_equal(dev, host)
-    assert eng.last_launch_count == 8          # pack + 5 layers + pool stats + embed_layer-0
+    assert eng.last_launch_count == 9          # pack + 5 layers + pool stats + embed GEMM + K-split reduction
     eng.close()
 
 

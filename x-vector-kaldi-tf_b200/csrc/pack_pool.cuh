@@ -271,9 +271,17 @@ struct StatsArgs {
   const float* partial;       // [r_pad/32][2][C]
   SegMeta seg;
   int32_t channels;           // C
-  float* stats;               // [n_seg, 2C]
+  float* stats;               // [n_seg, 2C]  (may be null)
+  __half* split;              // [n_seg, 3 * 2C] fp16 [hi | hi | lo] of the same statistics (may be null): the A operand
+                              // of the split-precision embedding GEMM, x = hi + lo to ~2^-22
   float var_eps;
 };
+
+__device__ __forceinline__ void store_split(__half* row, int K, int k, float x) {
+  const __half hi = __float2half_rn(x);
+  const __half lo = __float2half_rn(x - __half2float(hi));
+  row[k] = hi; row[K + k] = hi; row[2 * K + k] = lo;
+}
 
 __global__ void __launch_bounds__(STATS_THREADS) pool_stats_kernel(const StatsArgs a) {
   const int seg = blockIdx.y;
@@ -303,8 +311,48 @@ __global__ void __launch_bounds__(STATS_THREADS) pool_stats_kernel(const StatsAr
   const double inv_n = 1.0 / double(len);
   const double mean = s1 * inv_n;
   const double var = fmax(s2 * inv_n - mean * mean, 0.0);
-  a.stats[int64_t(seg) * 2 * C + c] = float(mean);
-  a.stats[int64_t(seg) * 2 * C + C + c] = float(sqrt(var + double(a.var_eps)));
+  const float fm = float(mean), fs = float(sqrt(var + double(a.var_eps)));
+  if (a.stats != nullptr) {
+    a.stats[int64_t(seg) * 2 * C + c] = fm;
+    a.stats[int64_t(seg) * 2 * C + C + c] = fs;
+  }
+  if (a.split != nullptr) {
+    __half* row = a.split + int64_t(seg) * 6 * C;
+    store_split(row, 2 * C, c, fm);
+    store_split(row, 2 * C, C + c, fs);
+  }
+}
+
+// embed_layer-0 epilogue of the tensor-core path: emb = b0 + sum over K-splits (fixed order) of the raw
+// accumulators tdnn_pair_kernel<2> wrote.
+struct FcReduceArgs {
+  const float* partial;       // [splits][n_seg][E]
+  const float* b0;            // [E]
+  float* emb;                 // [n_seg, E]
+  int32_t n_seg, E, splits;
+};
+
+__global__ void __launch_bounds__(256) embed_reduce_kernel(const FcReduceArgs a) {
+  const int64_t i4 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;          // one float4 of the output
+  const int64_t n4 = int64_t(a.n_seg) * a.E / 4;
+  if (i4 >= n4) return;
+  const int o4 = int(i4 % (a.E / 4));
+  float4 sum = __ldg(reinterpret_cast<const float4*>(a.b0) + o4);
+  const float4* p = reinterpret_cast<const float4*>(a.partial) + i4;
+  int s = 0;
+  for (; s + 4 <= a.splits; s += 4) {                                          // 4 loads in flight, fixed order
+    const float4 v0 = __ldcg(p + int64_t(s) * n4), v1 = __ldcg(p + int64_t(s + 1) * n4);
+    const float4 v2 = __ldcg(p + int64_t(s + 2) * n4), v3 = __ldcg(p + int64_t(s + 3) * n4);
+    sum.x += v0.x; sum.y += v0.y; sum.z += v0.z; sum.w += v0.w;
+    sum.x += v1.x; sum.y += v1.y; sum.z += v1.z; sum.w += v1.w;
+    sum.x += v2.x; sum.y += v2.y; sum.z += v2.z; sum.w += v2.w;
+    sum.x += v3.x; sum.y += v3.y; sum.z += v3.z; sum.w += v3.w;
+  }
+  for (; s < a.splits; ++s) {
+    const float4 v = __ldcg(p + int64_t(s) * n4);
+    sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+  }
+  reinterpret_cast<float4*>(a.emb)[i4] = sum;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -23,6 +23,8 @@
 //                    that channel, so the per-block sum / sum of squares is a private register
 //                    reduction (no shuffles, fixed order -> bit-reproducible).  Output:
 //                    partial[block][{sum,sumsq}][channel] fp32, one aligned 32-row block each.
+//   mode 2 (GEMM):   store orientation, no activation function: the raw fp32 accumulators of one K-split go to
+//                    out_f32[split][row][channel] (embed_layer-0 as a split-fp16 tensor-core GEMM, see xvec_api.cu).
 // Temporal taps: the activation slab [136 rows x 128 ch] is loaded ONCE per channel chunk and tap
 // j is addressed by advancing the UMMA descriptor start by j*d rows (reuse = 1); for half
 // contexts > 4 rows one box per tap is loaded instead (reuse = 0).
@@ -80,7 +82,9 @@ struct PairArgs {
   int32_t reuse;            // 0 / 1 (see header comment)
   int32_t n_act_stages;     // n_act * ATOMS * (reuse ? 17408 : 16384) + n_wgt * ATOMS * 16384 <= RING_BYTES (+ 16384 in mode 1)
   int32_t n_wgt_stages;
-  int32_t mode;             // 0 store, 1 pool
+  int32_t mode;             // 0 store, 1 pool, 2 raw fp32 split-K partials (embedding GEMM)
+  int32_t k_splits;         // mode 2: the K range [0, k_splits * c_chunks * 128) is cut into k_splits work items
+  int32_t n_rows;           // mode 2: rows that exist (stores beyond are skipped)
   int32_t prefetch;         // 1: warm L2 with the activation boxes of this cluster's next work item
   int32_t wgt_resident;     // 1: n_wgt_stages == taps * c_chunks; every cluster owns ONE channel tile, loads its
                             //    weights once and streams activations only (halves the bytes an SM must ingest)
@@ -91,6 +95,7 @@ struct PairArgs {
   const uint8_t* row_valid; // [R_pad]     mode 0: 1 = row belongs to a segment, 0 = gap / tail
   const uint8_t* blk_valid; // [R_pad/32]  mode 1: valid rows in the block (they are its first rows)
   float* partial;           // [R_pad/32][2][C_out]  mode 1
+  float* out_f32;           // [k_splits][n_rows][C_out]  mode 2: raw accumulators
   uint32_t* overflow_flag;  // set to 1 if an fp16 output overflowed to inf
   long long* trace;         // diagnostics (tools/trace_tiles.py): [cluster][rank][TRACE_TILES][8] SM clock stamps, or null
 };
@@ -180,11 +185,13 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
   // cluster_id % n_ch_tiles and its items are row tiles.
   const bool resident = args.wgt_resident != 0;
   const int my_ch_tile = cluster_id % args.n_ch_tiles;
-  const int n_items = resident ? args.n_row_tiles : args.n_row_tiles * args.n_ch_tiles;
+  const int k_splits = MODE == 2 ? args.k_splits : 1;
+  const int n_items = resident ? args.n_row_tiles : args.n_row_tiles * k_splits * args.n_ch_tiles;
   const int item_first = resident ? cluster_id / args.n_ch_tiles : cluster_id;
   const int item_step = resident ? n_clusters / args.n_ch_tiles : n_clusters;     // host: n_clusters % n_ch_tiles == 0
-  auto row_tile_of = [&](int item) { return resident ? item : item / args.n_ch_tiles; };
+  auto row_tile_of = [&](int item) { return resident ? item : item / (args.n_ch_tiles * k_splits); };
   auto ch_tile_of = [&](int item) { return resident ? my_ch_tile : item % args.n_ch_tiles; };
+  auto split_of = [&](int item) { return MODE == 2 ? (item / args.n_ch_tiles) % k_splits : 0; };
   const int half_ctx = (args.taps - 1) >> 1;
   const int halo = half_ctx * args.dilation;
   const bool reuse = args.reuse != 0;
@@ -200,6 +207,7 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
       const int r0 = row_tile_of(item) * TILE_ROWS + int(rank) * CTA_ROWS;
       const int c0 = ch_tile_of(item) * TILE_CH + int(rank) * CTA_CH;
       const bool load_wgt = !resident || item == item_first;
+      const int k_base = split_of(item) * args.c_chunks;               // first K chunk of this item (mode 2 split-K)
       const uint32_t pit = uint32_t((item - item_first) / item_step);
       for (int cc = 0; cc < args.c_chunks; ++cc) {
         for (int j = 0; j < args.taps; ++j) {
@@ -213,7 +221,7 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
 #pragma unroll
               for (int h = 0; h < ATOMS; ++h)
                 ptx::tma_load_2d_2sm(sAct + sa * ACT_STAGE_BYTES + h * ACT_ATOM_STRIDE, &tmap_act, act_full_leader + 8u * sa,
-                                     cc * STAGE_K + h * BLOCK_K, row);
+                                     (k_base + cc) * STAGE_K + h * BLOCK_K, row);
               // the same boxes of this cluster's NEXT item -> L2 now: with resident weights the ring holds too few
               // bytes to cover an HBM round trip (~2000 cycles), an L2 hit (~700) it does cover
               if (args.prefetch && item + item_step < n_items) {
@@ -232,7 +240,7 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
 #pragma unroll
               for (int h = 0; h < ATOMS; ++h)
                 ptx::tma_load_2d_2sm(sWgt + sb * WGT_STAGE_BYTES + h * WGT_ATOM_BYTES, &tmap_wgt, wgt_full_leader + 8u * sb,
-                                     j * args.c_in_pad + cc * STAGE_K + h * BLOCK_K, c0);
+                                     j * args.c_in_pad + (k_base + cc) * STAGE_K + h * BLOCK_K, c0);
             }
             __syncwarp();
           }
@@ -345,7 +353,36 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
     const int te = threadIdx.x - 64;                 // 0..255
     const uint32_t t_empty_leader = ptx::mapa_cluster(t_empty(0), 0);   // + 8 * acc
     uint32_t it = 0;
-    if (MODE == 0) {
+    if (MODE == 2) {
+      for (int item = item_first; item < n_items; item += item_step, ++it) {
+        const uint32_t acc = it & 1u;
+        const int row = row_tile_of(item) * TILE_ROWS + int(rank) * CTA_ROWS + q * 32 + lane;
+        const int ch0 = ch_tile_of(item) * TILE_CH + colh * 128;
+        float* dst = args.out_f32 + (size_t(split_of(item)) * args.n_rows + row) * args.c_out + ch0;
+        ptx::mbar_wait(t_full(acc), (it >> 1) & 1u);
+        ptx::tc_fence_after();
+        const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * TILE_CH + uint32_t(colh) * 128u;
+        uint32_t v[2][32];
+        ptx::tmem_ld_32x32(t_row, v[0]);
+#pragma unroll
+        for (int chunk = 0; chunk < 4; ++chunk) {
+          ptx::tmem_ld_wait_dep(v[chunk & 1]);
+          if (chunk < 3) {
+            ptx::tmem_ld_32x32(t_row + (chunk + 1) * C_CHUNK, v[(chunk + 1) & 1]);
+          } else {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(t_empty_leader + 8u * acc);
+          }
+          if (row < args.n_rows) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              *reinterpret_cast<uint4*>(dst + chunk * C_CHUNK + g * 4) =
+                  make_uint4(v[chunk & 1][g * 4], v[chunk & 1][g * 4 + 1], v[chunk & 1][g * 4 + 2], v[chunk & 1][g * 4 + 3]);
+          }
+        }
+      }
+    } else if (MODE == 0) {
       const uint32_t sC = smem_base + OFF_C + uint32_t(e) * C_BUF_BYTES;
       const uint32_t swz = (uint32_t(lane) >> 1) & 3u;   // SWIZZLE_64B phase of this row in the staging box
       uint32_t hmax = 0;

@@ -55,6 +55,8 @@ struct Plan {
   int64_t r_pad = 0;
   int32_t group = 1, n_groups = 0, n_slabs = 0;      // first-generation pool_embed_kernel grid
   int32_t fc_m_tiles = 0, fc_n_tiles = 0, fc_splits = 1, fc_k_per_split = 0, n_counters = 0;
+  int32_t tc_splits = 1;             // K-splits of the tensor-core embedding GEMM
+  size_t off_split = 0;
   size_t off_meta = 0, off_counters = 0, off_valid = 0, off_blk_valid = 0, off_x0 = 0, off_ha = 0, off_hb = 0,
          off_hlast = 0, off_pool_partial = 0, off_stats = 0, off_partial = 0, bytes = 0;
 };
@@ -74,6 +76,9 @@ struct xv_model {
   std::map<std::string, std::vector<int64_t>> host_shapes;
   bool dirty = true;
   std::vector<FrameLayer> layers;
+  __half* w0_split_dev = nullptr;    // [E, 3 * 2C] fp16 K-major [hi | lo | hi]: B operand of the split-precision GEMM
+  int opt_fc_max_splits = 36;        // cap on the K-splits of the tensor-core embedding GEMM
+  int opt_fc = 1;                    // 1: embed_layer-0 on tensor cores (split fp16), 0: fp32 SIMT GEMM
   float* w0_dev = nullptr;           // [2C, E]
   float* b0_dev = nullptr;           // [E]
   uint32_t* overflow_dev = nullptr;
@@ -130,6 +135,16 @@ Plan make_plan(const xv_model* m, int64_t total_frames, int32_t n_seg) {
   p.fc_splits = K / 256;                                       // C_last is a multiple of 128
   p.fc_k_per_split = K / p.fc_splits;
   p.n_counters = std::max(p.n_groups, p.fc_m_tiles * p.fc_n_tiles);
+  {
+    // tensor-core embedding GEMM: K' = 3K in 128-wide chunks, cut into as many K-splits as keep all CTA pairs busy
+    const int chunks = 3 * K / 128;
+    const int64_t tiles = int64_t((n_seg + tdnn2::TILE_ROWS - 1) / tdnn2::TILE_ROWS) * (m->topo.emb_dim / tdnn2::TILE_CH);
+    const int want = int(std::max<int64_t>(1, m->num_clusters / std::max<int64_t>(tiles, 1)));
+    int best = 1;
+    for (int d = 1; d <= chunks / 2; ++d)
+      if (chunks % d == 0 && d <= want && d <= m->opt_fc_max_splits) best = d;   // largest admissible divisor of the chunk count
+    p.tc_splits = best;
+  }
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = size_t(round_up(int64_t(off + bytes), 1024)); return o; };
   p.off_meta = take((size_t(3) * n_seg + size_t(p.r_pad / tdnn2::POOL_BLOCK)) * 4);
@@ -142,7 +157,8 @@ Plan make_plan(const xv_model* m, int64_t total_frames, int32_t n_seg) {
   p.off_hlast = take(size_t(p.r_pad) * c_last * 2);          // only written by the debug / v1 paths
   p.off_pool_partial = take(size_t(p.r_pad / tdnn2::POOL_BLOCK) * 2 * c_last * 4);
   p.off_stats = take(size_t(n_seg) * K * 4);
-  p.off_partial = take(size_t(std::max(p.n_slabs, p.fc_splits)) * n_seg * m->topo.emb_dim * 4);
+  p.off_split = take(size_t(round_up(n_seg, tdnn2::CTA_ROWS)) * 3 * K * 2);   // rows padded to the TMA box (never read back)
+  p.off_partial = take(size_t(std::max(std::max(p.n_slabs, p.fc_splits), p.tc_splits)) * n_seg * m->topo.emb_dim * 4);
   p.bytes = off;
   return p;
 }
@@ -165,8 +181,9 @@ void free_layers(xv_model* m) {
     cudaFree(L.w_dev); cudaFree(L.bias_dev); cudaFree(L.scale_dev); cudaFree(L.shift_dev);
     L.w_dev = nullptr; L.bias_dev = L.scale_dev = L.shift_dev = nullptr;
   }
-  cudaFree(m->w0_dev); cudaFree(m->b0_dev);
+  cudaFree(m->w0_dev); cudaFree(m->b0_dev); cudaFree(m->w0_split_dev);
   m->w0_dev = m->b0_dev = nullptr;
+  m->w0_split_dev = nullptr;
 }
 
 const std::vector<float>* find_param(const xv_model* m, const std::string& name, std::initializer_list<int64_t> shape) {
@@ -227,6 +244,22 @@ int finalize_params(xv_model* m) {
   XV_CUDA(cudaMalloc(&m->b0_dev, b0->size() * 4));
   XV_CUDA(cudaMemcpy(m->w0_dev, w0->data(), w0->size() * 4, cudaMemcpyHostToDevice));
   XV_CUDA(cudaMemcpy(m->b0_dev, b0->data(), b0->size() * 4, cudaMemcpyHostToDevice));
+  {
+    // split-precision copy for the tensor-core embedding GEMM: w = hi + lo (fp16 each, |w - hi - lo| ~ 2^-22 |w|);
+    // emb = s_hi*w_hi + s_hi*w_lo + s_lo*w_hi with K' = 3 * 2C, operands [s_hi | s_hi | s_lo] x [w_hi | w_lo | w_hi]
+    const int K = 2 * c_last, E = t.emb_dim;
+    std::vector<__half> ws(size_t(E) * 3 * K);
+    for (int k = 0; k < K; ++k)
+      for (int o = 0; o < E; ++o) {
+        const float w = (*w0)[size_t(k) * E + o];
+        const __half hi = __float2half_rn(w);
+        const __half lo = __float2half_rn(w - __half2float(hi));
+        __half* row = ws.data() + size_t(o) * 3 * K;
+        row[k] = hi; row[K + k] = lo; row[2 * K + k] = hi;
+      }
+    XV_CUDA(cudaMalloc(&m->w0_split_dev, ws.size() * sizeof(__half)));
+    XV_CUDA(cudaMemcpy(m->w0_split_dev, ws.data(), ws.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  }
   m->dirty = false;
   return XV_OK;
 }
@@ -469,13 +502,18 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
 
   // ---- statistics pooling + embed_layer-0 -----------------------------------------------
   if (pair) {
-    float* stats = stats_out_dev ? stats_out_dev : reinterpret_cast<float*>(ws + p.off_stats);
+    const bool fc_tc = m->opt_fc == 1 && (2 * m->topo.width[nl - 1]) % 128 == 0 && m->topo.emb_dim % tdnn2::TILE_CH == 0;
+    float* stats = stats_out_dev ? stats_out_dev : (fc_tc ? nullptr : reinterpret_cast<float*>(ws + p.off_stats));
+    __half* split = fc_tc ? reinterpret_cast<__half*>(ws + p.off_split) : nullptr;
+    float* fc_partial = reinterpret_cast<float*>(ws + p.off_partial);
+    const int K = 2 * m->topo.width[nl - 1], E = m->topo.emb_dim;
     {
       xvk::StatsArgs a{};
       a.partial = pool_partial;
       a.seg = seg;
       a.channels = m->topo.width[nl - 1];
       a.stats = stats;
+      a.split = split;
       a.var_eps = m->topo.var_eps;
       dim3 grid((a.channels + xvk::STATS_THREADS - 1) / xvk::STATS_THREADS, n_seg);
       XV_PROF();
@@ -484,17 +522,61 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       XV_CUDA(cudaGetLastError());
       ++launches;
     }
-    {
+    if (fc_tc) {
+      // embed_layer-0 (models.py:495) on the tensor cores: [n_seg, 3K] x [E, 3K]^T, split over K across the CTA pairs
+      CUtensorMap ta, tw, tc;
+      rc = encode_2d(m, &ta, split, uint64_t(3 * K), uint64_t(round_up(n_seg, tdnn2::CTA_ROWS)), tdnn2::BLOCK_K, tdnn2::ACT_BOX_ROWS_PLAIN,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc != XV_OK) return rc;
+      rc = encode_2d(m, &tw, m->w0_split_dev, uint64_t(3 * K), uint64_t(E), tdnn2::BLOCK_K, tdnn2::CTA_CH, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc != XV_OK) return rc;
+      tc = tw;                                                        // unused in mode 2
+      tdnn2::PairArgs a{};
+      a.n_row_tiles = (n_seg + tdnn2::TILE_ROWS - 1) / tdnn2::TILE_ROWS;
+      a.n_ch_tiles = E / tdnn2::TILE_CH;
+      a.k_splits = p.tc_splits;
+      a.c_chunks = (3 * K / 128) / p.tc_splits;
+      a.taps = 1;
+      a.dilation = 1;
+      a.c_in_pad = 3 * K;
+      a.reuse = 0;
+      a.n_act_stages = a.n_wgt_stages = 3;
+      a.mode = 2;
+      a.c_out = E;
+      a.n_rows = n_seg;
+      a.out_f32 = fc_partial;
+      a.overflow_flag = m->overflow_dev;
+      const int64_t tiles = int64_t(a.n_row_tiles) * a.n_ch_tiles * a.k_splits;
+      const int grid = 2 * int(std::min<int64_t>(tiles, m->num_clusters));
+      XV_PROF();
+      tdnn2::tdnn_pair_kernel<2, 2><<<grid, tdnn2::NUM_THREADS, tdnn2::SMEM_BYTES, stream>>>(ta, tw, tc, a);
+      XV_PROF();
+      XV_CUDA(cudaGetLastError());
+      ++launches;
+      xvk::FcReduceArgs r{};
+      r.partial = fc_partial;
+      r.b0 = m->b0_dev;
+      r.emb = emb_dev;
+      r.n_seg = n_seg;
+      r.E = E;
+      r.splits = p.tc_splits;
+      const int64_t n4 = int64_t(n_seg) * E / 4;
+      XV_PROF();
+      xvk::embed_reduce_kernel<<<int((n4 + 255) / 256), 256, 0, stream>>>(r);
+      XV_PROF();
+      XV_CUDA(cudaGetLastError());
+      ++launches;
+    } else {
       xvk::FcArgs a{};
       a.stats = stats;
       a.w0 = m->w0_dev;
       a.b0 = m->b0_dev;
-      a.fc_partial = reinterpret_cast<float*>(ws + p.off_partial);
+      a.fc_partial = fc_partial;
       a.counters = counters;
       a.emb = emb_dev;
       a.n_seg = n_seg;
-      a.K = 2 * m->topo.width[nl - 1];
-      a.E = m->topo.emb_dim;
+      a.K = K;
+      a.E = E;
       a.k_per_split = p.fc_k_per_split;
       dim3 grid(p.fc_m_tiles, p.fc_n_tiles, p.fc_splits);
       XV_PROF();
@@ -611,6 +693,8 @@ int xv_create(xv_model** out, int device, const xv_topology* topo) {
     e = cudaFuncSetAttribute(tdnn2::tdnn_pair_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(tdnn2::tdnn_pair_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(tdnn2::tdnn_pair_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
   if (e == cudaSuccess) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * (prop.multiProcessorCount / 2));
@@ -824,6 +908,8 @@ int xv_set_option(xv_model* m, const char* name, int64_t value) {
   else if (n == "profile") m->opt_profile = value != 0;
   else if (n == "resident") m->opt_resident = int(value);
   else if (n == "prefetch") m->opt_prefetch = value != 0;
+  else if (n == "fc") m->opt_fc = int(value);
+  else if (n == "fc_max_splits") m->opt_fc_max_splits = std::max(1, int(value));
   else if (n == "trace_ptr") m->opt_trace = reinterpret_cast<long long*>(static_cast<intptr_t>(value));   // device buffer
   else if (n == "trace_layer") m->opt_trace_layer = int(value);
   else if (n == "pipeline") {
