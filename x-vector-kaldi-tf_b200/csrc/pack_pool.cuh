@@ -43,14 +43,14 @@ constexpr int PACK_MAX_K0 = 512;             // k0_pad / 8 pieces per row must d
 
 struct PackArgs {
   const float* feats;        // [total_frames, D]
-  SegMeta seg;
   int32_t r_pad;
   int32_t feat_dim, taps, dilation;
   int32_t k0_pad;            // multiple of 64
   __half* x0;                // [r_pad, k0_pad]
   uint8_t* row_valid;        // [r_pad]
   uint8_t* blk_valid;        // [r_pad / 32] valid rows of each aligned 32-row block
-  const int32_t* blk_seg;    // [r_pad / 32] segment that owns the block, -1 = gap / tail (host-built)
+  const int32_t* lut;        // [k0_pad] staged-float offset of spliced column ch: tap * dilation * D + ceps, or -1 (padding)
+  const int4* blk_info;      // [r_pad / 32] host-built: {first feature row, first frame in segment, segment length, valid rows}
   uint32_t* counters;        // [n_counters] zeroed here for embed_fc_kernel / pool_embed_kernel
   int32_t n_counters;
 };
@@ -68,15 +68,8 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_im2col_kernel(const PackArg
   if (r0 >= a.r_pad) return;
   const int D = a.feat_dim;
   const int halo = ((a.taps - 1) >> 1) * a.dilation;
-  const int seg = __ldg(a.blk_seg + blockIdx.x);     // block-uniform
-  int t0 = 0, nv = 0, len = 0;
-  int64_t fs = 0;
-  if (seg >= 0) {
-    len = __ldg(a.seg.len + seg);
-    fs = __ldg(a.seg.feat_start + seg);
-    t0 = r0 - __ldg(a.seg.row_start + seg);
-    nv = min(PACK_ROWS_PER_BLOCK, len - t0);         // >= 1 by construction of blk_seg
-  }
+  const int4 bi = __ldg(a.blk_info + blockIdx.x);    // block-uniform; one hop to everything the block needs
+  const int t0 = bi.y, len = bi.z, nv = bi.w;
   if (threadIdx.x == 0) a.blk_valid[blockIdx.x] = uint8_t(nv);
   if (threadIdx.x < PACK_ROWS_PER_BLOCK) a.row_valid[r0 + threadIdx.x] = threadIdx.x < nv ? 1 : 0;
   const int pieces = a.k0_pad >> 3;                                   // 16-byte pieces per row
@@ -88,16 +81,14 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_im2col_kernel(const PackArg
   // stage frames t0-halo .. t0+31+halo: staged float i is feats[(fs + t0 - halo) * D + i] when its frame exists
   const int n_stage = (PACK_ROWS_PER_BLOCK + 2 * halo) * D;
   const int lo = max(0, halo - t0) * D, hi = min(PACK_ROWS_PER_BLOCK + 2 * halo, len - t0 + halo) * D;
-  const float* src0 = a.feats + (fs + t0 - halo) * D;
+  const float* src0 = a.feats + (int64_t(bi.x) - halo) * D;
   for (int i = threadIdx.x; i < n_stage; i += PACK_THREADS) s_feat[i] = (i >= lo && i < hi) ? __ldg(src0 + i) : 0.f;
-  const int k_real = a.taps * D;
   const int rows_per_pass = PACK_THREADS / pieces;                    // k0_pad <= 512 -> pieces <= 64
   const int pc = threadIdx.x % pieces, lr0 = threadIdx.x / pieces;
   int lut[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int ch = pc * 8 + e, j = ch / D;
-    lut[e] = ch < k_real ? j * a.dilation * D + (ch - j * D) : -1;
+  {
+    const int4 l0 = __ldg(reinterpret_cast<const int4*>(a.lut) + pc * 2), l1 = __ldg(reinterpret_cast<const int4*>(a.lut) + pc * 2 + 1);
+    lut[0] = l0.x; lut[1] = l0.y; lut[2] = l0.z; lut[3] = l0.w; lut[4] = l1.x; lut[5] = l1.y; lut[6] = l1.z; lut[7] = l1.w;
   }
   __syncthreads();
   if (lr0 < rows_per_pass) {

@@ -81,6 +81,7 @@ struct xv_model {
   int opt_fc = 1;                    // 1: embed_layer-0 on tensor cores (split fp16), 0: fp32 SIMT GEMM
   float* w0_dev = nullptr;           // [2C, E]
   float* b0_dev = nullptr;           // [E]
+  int32_t* pack_lut_dev = nullptr;   // [k0_pad] spliced column -> staged feature offset (pack kernel)
   uint32_t* overflow_dev = nullptr;
   uint32_t* overflow_host = nullptr; // pinned
   EncodeTiledFn encode = nullptr;
@@ -147,7 +148,7 @@ Plan make_plan(const xv_model* m, int64_t total_frames, int32_t n_seg) {
   }
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = size_t(round_up(int64_t(off + bytes), 1024)); return o; };
-  p.off_meta = take((size_t(3) * n_seg + size_t(p.r_pad / tdnn2::POOL_BLOCK)) * 4);
+  p.off_meta = take((size_t(4) * n_seg + size_t(4) * size_t(p.r_pad / tdnn2::POOL_BLOCK)) * 4);   // 3 n_seg (+ pad to 16 B) + int4 per block
   p.off_counters = take(size_t(p.n_counters) * 4);
   p.off_valid = take(size_t(p.r_pad));
   p.off_blk_valid = take(size_t(p.r_pad / tdnn2::POOL_BLOCK));
@@ -312,36 +313,46 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
   uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
 
   // ---- segment metadata: packed row starts (multiples of 32), feature row starts, lengths ----
-  rc = ensure_meta_capacity(m, int64_t(3) * n_seg + p.r_pad / tdnn2::POOL_BLOCK);
+  rc = ensure_meta_capacity(m, int64_t(4) * n_seg + 4 * (p.r_pad / tdnn2::POOL_BLOCK) + 4);
   if (rc != XV_OK) return rc;
   const int slot = m->meta_next;
   m->meta_next = (m->meta_next + 1) % META_SLOTS;
   XV_CUDA(cudaEventSynchronize(m->meta_event[slot]));      // previous copy out of this slot finished
   int32_t* mh = m->meta_host[slot];
   int64_t rows_used = 0;
+  const int64_t blk_info_off = round_up(int64_t(3) * n_seg, 4);   // int4-aligned
   {
     int64_t row = 0, fs = 0;
-    int32_t* blk_seg = mh + 3 * int64_t(n_seg);                     // segment of every aligned 32-row block, -1 = none
+    // per aligned 32-row block: {first feature row, first frame of the block in its segment, segment length, valid rows}
+    int32_t* blk_info = mh + blk_info_off;
     for (int i = 0; i < n_seg; ++i) {
+      const int32_t len = seg_len_host[i];
       mh[i] = int32_t(row);
       mh[n_seg + i] = int32_t(fs);
-      mh[2 * n_seg + i] = seg_len_host[i];
-      const int64_t next = row + round_up(int64_t(seg_len_host[i]) + m->gap, tdnn2::POOL_BLOCK);
-      const int64_t b_data_end = (row + seg_len_host[i] + tdnn2::POOL_BLOCK - 1) / tdnn2::POOL_BLOCK;
-      for (int64_t b = row / tdnn2::POOL_BLOCK; b < next / tdnn2::POOL_BLOCK; ++b) blk_seg[b] = b < b_data_end ? i : -1;
+      mh[2 * n_seg + i] = len;
+      const int64_t next = row + round_up(int64_t(len) + m->gap, tdnn2::POOL_BLOCK);
+      int32_t t0 = 0;
+      for (int64_t b = row / tdnn2::POOL_BLOCK; b < next / tdnn2::POOL_BLOCK; ++b, t0 += tdnn2::POOL_BLOCK) {
+        int32_t* e = blk_info + 4 * b;
+        const int32_t nv = std::max(0, std::min(tdnn2::POOL_BLOCK, len - t0));
+        e[0] = int32_t(fs + t0); e[1] = t0; e[2] = len; e[3] = nv;
+      }
       row = next;
-      fs += seg_len_host[i];
+      fs += len;
     }
     rows_used = row;
   }
   const int64_t r_pad = round_up(rows_used, tdnn2::TILE_ROWS);      // <= p.r_pad (the plan's upper bound)
   const int64_t n_blocks = r_pad / tdnn2::POOL_BLOCK;
-  for (int64_t b = rows_used / tdnn2::POOL_BLOCK; b < n_blocks; ++b) mh[3 * int64_t(n_seg) + b] = -1;
+  for (int64_t b = rows_used / tdnn2::POOL_BLOCK; b < n_blocks; ++b) {
+    int32_t* e = mh + blk_info_off + 4 * b;
+    e[0] = e[1] = e[2] = e[3] = 0;
+  }
   int32_t* meta_dev = reinterpret_cast<int32_t*>(ws + p.off_meta);
-  XV_CUDA(cudaMemcpyAsync(meta_dev, mh, (size_t(3) * n_seg + size_t(n_blocks)) * 4, cudaMemcpyHostToDevice, stream));
+  XV_CUDA(cudaMemcpyAsync(meta_dev, mh, (size_t(blk_info_off) + size_t(4) * n_blocks) * 4, cudaMemcpyHostToDevice, stream));
   XV_CUDA(cudaEventRecord(m->meta_event[slot], stream));
   xvk::SegMeta seg{meta_dev, meta_dev + n_seg, meta_dev + 2 * n_seg, n_seg};
-  const int32_t* blk_seg_dev = meta_dev + 3 * int64_t(n_seg);
+  const int4* blk_info_dev = reinterpret_cast<const int4*>(meta_dev + blk_info_off);
 
   uint8_t* row_valid = ws + p.off_valid;
   uint8_t* blk_valid = ws + p.off_blk_valid;
@@ -359,7 +370,6 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
   {
     xvk::PackArgs a{};
     a.feats = feats_dev;
-    a.seg = seg;
     a.r_pad = int32_t(r_pad);
     a.feat_dim = m->topo.feat_dim;
     a.taps = m->layers[0].taps;
@@ -368,7 +378,8 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
     a.x0 = x0;
     a.row_valid = row_valid;
     a.blk_valid = blk_valid;
-    a.blk_seg = blk_seg_dev;
+    a.blk_info = blk_info_dev;
+    a.lut = m->pack_lut_dev;
     a.counters = counters;
     a.n_counters = p.n_counters;
     const int blocks = int(r_pad / xvk::PACK_ROWS_PER_BLOCK);      // >= n_seg: covers n_counters with 256 threads each
@@ -711,6 +722,13 @@ int xv_create(xv_model** out, int device, const xv_topology* topo) {
     if (qe != cudaSuccess || n_clusters <= 0) { (void)cudaGetLastError(); n_clusters = prop.multiProcessorCount / 2; }
     m->num_clusters = std::min(n_clusters, prop.multiProcessorCount / 2);
   }
+  if (e == cudaSuccess) {
+    std::vector<int32_t> lut(m->k0_pad, -1);
+    const FrameLayer& L0 = m->layers[0];
+    for (int ch = 0; ch < L0.taps * t.feat_dim; ++ch) lut[ch] = (ch / t.feat_dim) * L0.dilation * t.feat_dim + ch % t.feat_dim;
+    e = cudaMalloc(&m->pack_lut_dev, lut.size() * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(m->pack_lut_dev, lut.data(), lut.size() * 4, cudaMemcpyHostToDevice);
+  }
   if (e == cudaSuccess) e = cudaMalloc(&m->overflow_dev, 4);
   if (e == cudaSuccess) e = cudaMemset(m->overflow_dev, 0, 4);
   if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&m->overflow_host), 4, cudaHostAllocDefault);
@@ -738,6 +756,7 @@ void xv_destroy(xv_model* m) {
   }
   for (cudaEvent_t e : m->prof_events) cudaEventDestroy(e);
   cudaFree(m->overflow_dev);
+  cudaFree(m->pack_lut_dev);
   if (m->overflow_host) cudaFreeHost(m->overflow_host);
   for (auto& sl : m->slots) {
     cudaFree(sl.feats_dev); cudaFree(sl.emb_dev); cudaFree(sl.ws_dev);
