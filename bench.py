@@ -6,8 +6,9 @@
 
 A *step* is one pass of the extraction hot path (pack -> 5 fused tcgen05 TDNN layers, the last one pooling in its epilogue ->
 pool statistics -> embed_layer-0) over one batch of synthetic MFCC: BASELINE.json configs[1], 256 utterances x 400
-frames x 23 ceps per GPU (weak scaling: every rank gets its own batch; for N > 1 the step ends
-with the NCCL gather of the [256, 512] embeddings to rank 0, the only collective on the path).
+frames x 23 ceps per GPU (weak scaling: every rank gets its own batch; for N > 1,
+like the product, ONE NCCL gather of all embeddings to rank 0 ends the job, inside the timed region:
+the only collective on the path).
 
   value  frames/s with the features already resident in HBM (CUDA events around each step on the
          launching stream, L2 flushed between steps, max over ranks).
@@ -192,7 +193,10 @@ def run_b200(args):
     emb_host = torch.empty((B, EMB_DIM), dtype=torch.float32, pin_memory=True)
     feats_dev = feats_host.to(dev)
     emb_dev = torch.empty((B, EMB_DIM), dtype=torch.float32, device=dev)
-    gathered = [torch.empty_like(emb_dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    # N > 1: like make_embedding, every rank keeps its embeddings and ONE gather to rank 0 ends the job
+    # (models.py gathers once per extraction, not per batch); the gather is inside the timed region.
+    emb_all = torch.empty((args.steps, B, EMB_DIM), dtype=torch.float32, device=dev) if world > 1 else None
+    gathered = [torch.empty_like(emb_all) for _ in range(world)] if (world > 1 and rank == 0) else None
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
 
@@ -200,22 +204,16 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
 
-    def step_resident():
-        eng.forward(feats_dev, lens, emb_dev=emb_dev, stream=stream)
-        if world > 1:
-            dist.gather(emb_dev, gathered, dst=0)
+    def step_resident(i=None):
+        eng.forward(feats_dev, lens, emb_dev=(emb_dev if (i is None or world == 1) else emb_all[i]), stream=stream)
 
     feats_host2 = [feats_host, feats_host.clone().pin_memory()]
     emb_host2 = [emb_host, torch.empty_like(emb_host).pin_memory()]
 
-    def finish_e2e(ticket, slot):
+    def finish_e2e(ticket, slot, i):
         eng.collect(ticket)                                            # embeddings of that step are in emb_host2[slot]
-        if world > 1:
-            emb_dev.copy_(emb_host2[slot], non_blocking=True)
-            dist.gather(emb_dev, gathered, dst=0)
-            if rank == 0:
-                gathered[-1].cpu()
-            torch.cuda.synchronize(dev)
+        if world > 1 and i is not None:
+            emb_all[i].copy_(emb_host2[slot], non_blocking=True)       # staged for the single end-of-job gather
 
     def run_e2e(steps):
         """K steps through xv_submit_host / xv_collect (pinned host in, pinned host out), two in flight:
@@ -227,19 +225,29 @@ def run_b200(args):
             ticket = eng.submit_host(feats_host2[slot], lens, emb_host2[slot])
             if prev is not None:
                 finish_e2e(*prev)
-            prev = (ticket, slot)
+            prev = (ticket, slot, i if steps == args.steps else None)
         finish_e2e(*prev)
+        if world > 1 and steps == args.steps:
+            dist.gather(emb_all, gathered, dst=0)
+            if rank == 0:
+                gathered[-1][-1].cpu()                                 # rank 0 reads the job's result
+            torch.cuda.synchronize(dev)
         return time.perf_counter() - t0
 
     def timed_resident(steps):
         barrier(); torch.cuda.synchronize(dev)
         sampler = ClockSampler(local_rank); sampler.start()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        for s, e in evs:
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps + 1)]
+        for i, (s, e) in enumerate(evs[:steps]):
             flush.zero_()                                              # evict L2 between steps (untimed)
             s.record(stream)
-            step_resident()
+            step_resident(i)
             e.record(stream)
+        s, e = evs[steps]                                              # the end-of-job gather (N > 1), timed too
+        s.record(stream)
+        if world > 1:
+            dist.gather(emb_all, gathered, dst=0)
+        e.record(stream)
         torch.cuda.synchronize(dev); barrier()
         clocks = sampler.finish()
         ms = [s.elapsed_time(e) for s, e in evs]
@@ -261,6 +269,8 @@ def run_b200(args):
     # ---- warm-up, then the timed regions ------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    if world > 1:                                  # warm-up of the collective too (communicator / channel set-up)
+        dist.gather(emb_all, gathered, dst=0)
     torch.cuda.synchronize(dev)
     eng.check_overflow()
     ms, clocks = timed_resident(args.steps)
@@ -275,6 +285,25 @@ def run_b200(args):
     run_e2e(max(args.warmup, 3))
     e2e_total = max_over_ranks(timed_e2e(args.steps))
     e2e_value = world * frames * args.steps / (e2e_total * 1e-3)
+
+    # ---- configs[2]-like ragged batch (200-1000 frames per utterance), device-resident, same frame budget ----
+    rag_lens = synthetic.lengths_uniform(3, 4096)
+    rag_lens = rag_lens[:int(np.searchsorted(np.cumsum(rag_lens), frames))].astype(np.int32)
+    rag_feats = torch.from_numpy(synthetic.mfcc_batch(3 + 1000 * rank, rag_lens)).to(dev)
+    rag_emb = torch.empty((len(rag_lens), EMB_DIM), dtype=torch.float32, device=dev)
+    for _ in range(3):
+        eng.forward(rag_feats, rag_lens, emb_dev=rag_emb, stream=stream)
+    rag_evs = []
+    for _ in range(min(args.steps, 50)):
+        flush.zero_()
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_.record(stream); eng.forward(rag_feats, rag_lens, emb_dev=rag_emb, stream=stream); e_.record(stream)
+        rag_evs.append((s_, e_))
+    torch.cuda.synchronize(dev)
+    rag_ms = float(np.mean([s_.elapsed_time(e_) for s_, e_ in rag_evs]))
+    ragged = dict(workload="configs[2]-like: %d utterances of 200-1000 frames in one call (packed rows, no bucketing needed)"
+                           % len(rag_lens), frames_per_step_per_gpu=int(rag_lens.sum()), ms_per_step=round(rag_ms, 5),
+                  value_per_gpu=round(float(rag_lens.sum()) / (rag_ms * 1e-3), 1), unit=UNIT)
 
     # ---- per-launch durations (CUDA events on the launching stream, inside the library) -------
     eng.set_option("profile", 1)
@@ -334,13 +363,13 @@ def run_b200(args):
                                                        "taps %s dil %s" % (topo["kernel_sizes"], topo["dilations"]),
                                                        args.weight_set),
                            frames_per_step_per_gpu=frames, l2="flushed between steps (%d MiB write)" % (L2_FLUSH_BYTES >> 20),
-                           parallelism="utterance sharding x%d, NCCL gather to rank 0" % world if world > 1 else "single GPU",
+                           parallelism="utterance sharding x%d, one NCCL gather to rank 0 at the end of the job" % world if world > 1 else "single GPU",
                            arithmetic="fp16 operands (RN), fp32 accumulate (tcgen05 kind::f16), fp32 epilogue/pooling"),
                e2e=dict(value=round(e2e_value, 1), unit=UNIT, h2d_bytes_per_step=frames * FEAT_DIM * 4 + B * 3 * 4,
                         d2h_bytes_per_step=B * EMB_DIM * 4 + 4, ms_per_step=round(e2e_total / args.steps, 5),
                         api="xv_submit_host / xv_collect, 2 in flight (pinned host buffers; xv_extract_host is the blocking form)"),
                gpu_launches=int(launches_per_step * args.steps),
-               clocks=clocks, roofline=roofline)
+               clocks=clocks, roofline=roofline, ragged=ragged)
     if remeasured:
         out["clocks"]["note"] = "first measurement rejected (throttle reason / low clocks); this is the re-measurement"
 
