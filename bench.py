@@ -181,8 +181,8 @@ def run_b200(args):
     eng = _native.XvecEngine(topo["kernel_sizes"], topo["dilations"], topo["layer_sizes"], EMB_DIM, FEAT_DIM,
                              device=local_rank)
     eng.set_params(params)
-    if args.pipeline is not None:
-        eng.set_option("pipeline", args.pipeline)
+    for kv in args.option:
+        eng.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 
     B, T = args.batch, args.frames
     lens = np.full(B, T, np.int32)
@@ -491,7 +491,7 @@ def main():
     ap.add_argument("--weight-set", choices=["A", "B"], default="B")
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--frames", type=int, default=400)
-    ap.add_argument("--pipeline", type=int, default=None, help="library kernel generation (diagnostics; default: newest)")
+    ap.add_argument("--option", action="append", default=[], help="xv_set_option name=value (diagnostics)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--step-seconds", type=float, default=1.5, help="reference arm: CPU seconds per step (calibrated)")
     args = ap.parse_args()

@@ -92,10 +92,10 @@ def test_embedding_parity_ragged_batch(topology, weight_set):
     eng.close()
 
 
-@pytest.mark.parametrize("opts", [dict(resident=1), dict(resident=2), dict(fc=0), dict(pipeline=1)])
+@pytest.mark.parametrize("opts", [dict(resident=1), dict(resident=2), dict(fc=0), dict(pdl=0)])
 def test_alternative_kernel_schedules_give_the_same_embeddings(opts):
-    # weight-stationary schedule of the CTA-pair kernel / first-generation single-CTA kernels: same arithmetic
-    # per output element, so results must stay within the parity gate (and very close to the default path)
+    # weight-stationary schedules of the layer kernel, fp32 SIMT embedding GEMM, plain stream-ordered launches:
+    # results must stay within the parity gate and very close to the default path
     eng, params = _engine("ModelWithoutDropoutTdnn", "B")
     lens = np.array([300, 90, 411, 25, 640], np.int32)
     feats = synthetic.mfcc_batch(6, lens)

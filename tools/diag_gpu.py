@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """GPU diagnostic: per-layer error of the sm_100a path vs the fp64 oracle (prints, never asserts).
-usage: python tools/diag_gpu.py [topology] [weight_set] [pipeline]"""
+usage: python tools/diag_gpu.py [topology] [weight_set] [option=value ...]"""
 import os
 import sys
 
@@ -13,15 +13,15 @@ from xvector_b200 import _native, synthetic       # noqa: E402
 
 topology = sys.argv[1] if len(sys.argv) > 1 else "ModelWithoutDropout"
 ws = sys.argv[2] if len(sys.argv) > 2 else "B"
-pipeline = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 t = orc.TOPOLOGIES[topology]
 params = synthetic.make_params(t["kernel_sizes"], t["layer_sizes"], t["embedding_sizes"], weight_set=ws)
 eng = _native.XvecEngine(t["kernel_sizes"], t["dilations"], t["layer_sizes"], 512, 23, device=0)
 eng.set_params(params)
-eng.set_option("pipeline", pipeline)
+for kv in sys.argv[3:]:
+    eng.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 lens = np.array([200, 37, 131, 25, 300], np.int32)
 feats = synthetic.mfcc_batch(11, lens)
-print("diag: %s set %s pipeline=%d" % (topology, ws, pipeline), flush=True)
+print("diag: %s set %s %s" % (topology, ws, " ".join(sys.argv[3:])), flush=True)
 emb, layers, stats = eng.forward(torch.from_numpy(feats).cuda(), lens, return_layers=True)
 torch.cuda.synchronize()
 off = 0

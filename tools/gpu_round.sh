@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,driver_version,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
 nproc >> gpurun_out/gpu.txt
-for cfg in "ModelWithoutDropoutTdnn B 2" "ModelWithoutDropout B 2" "ModelWithoutDropoutTdnn B 1"; do
+for cfg in "ModelWithoutDropoutTdnn B" "ModelWithoutDropout B" "ModelWithoutDropoutTdnn A"; do
   timeout 120 python tools/diag_gpu.py $cfg 2>&1 | tail -12
 done | tee gpurun_out/diag.log
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/pytest_gpu.log

@@ -4,13 +4,11 @@
 //                        [R_pad, K0_pad] holding, per row, the taps0*D spliced input of the first
 //                        layer (so layer 0 is a plain K = K0_pad GEMM), zero rows in the gaps,
 //                        plus the row_valid map every later epilogue uses.
-//   pool_embed_kernel  : statistics pooling (tf.nn.moments over time + sqrt(var + 1e-5), concat;
-//                        reference models.py:485-486) fused with the first segment-level affine
-//                        layer embed_layer-0 (tf.nn.xw_plus_b, models.py:495) = the x-vector.
-//   pool_stats_kernel  : production pooling: combines the per-32-row-block partial sums written by
+//   pool_stats_kernel  : combines the per-32-row-block partial sums written by
 //                        the last frame layer's epilogue (the [frames,1536] activation is never
 //                        materialised) into [mean | std] per segment.
-//   embed_fc_kernel    : embed_layer-0 as an fp32 split-K GEMM over the whole batch of segments.
+//   embed_reduce_kernel: adds the K-splits of the tensor-core embedding GEMM (tdnn_pair_kernel<2>) + bias.
+//   embed_fc_kernel    : embed_layer-0 as an fp32 SIMT split-K GEMM (option "fc" = 0; the cross-check of the above).
 //   unpack_rows_kernel : debug/parity only: fp16 packed rows -> fp32 [total_frames, C].
 #pragma once
 #include <cuda_fp16.h>
@@ -25,16 +23,6 @@ struct SegMeta {
   const int32_t* len;          // [n_seg] rows
   int32_t n_seg;
 };
-
-// largest s with row_start[s] <= r, or -1
-__device__ __forceinline__ int find_segment(const int32_t* __restrict__ row_start, int n_seg, int r) {
-  int lo = 0, hi = n_seg;                      // invariant: row_start[lo-1] <= r < row_start[hi]
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (__ldg(row_start + mid) <= r) lo = mid + 1; else hi = mid;
-  }
-  return lo - 1;
-}
 
 constexpr int PACK_ROWS_PER_BLOCK = 32;      // = one aligned pooling block: rows of ONE segment (or gap)
 constexpr int PACK_THREADS = 256;
@@ -51,7 +39,7 @@ struct PackArgs {
   uint8_t* blk_valid;        // [r_pad / 32] valid rows of each aligned 32-row block
   const int32_t* lut;        // [k0_pad] staged-float offset of spliced column ch: tap * dilation * D + ceps, or -1 (padding)
   const int4* blk_info;      // [r_pad / 32] host-built: {first feature row, first frame in segment, segment length, valid rows}
-  uint32_t* counters;        // [n_counters] zeroed here for embed_fc_kernel / pool_embed_kernel
+  uint32_t* counters;        // [n_counters] zeroed here for embed_fc_kernel
   int32_t n_counters;
 };
 
@@ -62,6 +50,8 @@ struct PackArgs {
 // offset table of its piece lives in registers.
 __global__ void __launch_bounds__(PACK_THREADS) pack_im2col_kernel(const PackArgs a) {
   __shared__ float s_feat[PACK_MAX_STAGE_FLOATS];
+  cudaTriggerProgrammaticLaunchCompletion();         // programmatic dependent launch: the next kernel may get scheduled
+  cudaGridDependencySynchronize();                   // ... and this one touches global memory only after its predecessor
   const int r0 = blockIdx.x * PACK_ROWS_PER_BLOCK;
   const int gtid = blockIdx.x * PACK_THREADS + threadIdx.x;
   if (gtid < a.n_counters) a.counters[gtid] = 0u;
@@ -108,148 +98,6 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_im2col_kernel(const PackArg
 }
 
 // ------------------------------------------------------------------------------------------
-constexpr int POOL_THREADS = 256;
-constexpr int POOL_SLAB = 128;          // channels per CTA
-constexpr int POOL_MAX_G = 8;           // segments per CTA (amortises the W0 slab read)
-constexpr int POOL_MAX_EPT = 4;         // embedding outputs per thread (emb_dim <= 1024)
-
-struct PoolArgs {
-  const __half* h;            // [r_pad, C] last frame layer output
-  SegMeta seg;
-  int32_t channels;           // C (multiple of 128)
-  int32_t emb_dim;            // E (multiple of 256, <= 1024)
-  int32_t group;              // segments per CTA, 1..POOL_MAX_G
-  const float* w0;            // [2C, E]  embed_layer-0/w
-  const float* b0;            // [E]
-  float* partial;             // [n_slabs, n_seg, E]
-  uint32_t* counters;         // [n_groups], zero on entry
-  float* emb;                 // [n_seg, E]
-  float* stats_out;           // optional [n_seg, 2C]
-  float var_eps;
-};
-
-__global__ void __launch_bounds__(POOL_THREADS) pool_embed_kernel(const PoolArgs a) {
-  __shared__ float s_red[2][POOL_THREADS / 32][POOL_SLAB];      // 8 KB: per-warp S1 / S2
-  __shared__ float s_stats[POOL_MAX_G][2 * POOL_SLAB];          // 8 KB: mean | std per segment
-  __shared__ int s_last;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int g0 = blockIdx.x * a.group;
-  const int n_in_group = min(a.group, a.seg.n_seg - g0);
-  const int slab = blockIdx.y, n_slabs = gridDim.y;
-  const int c0 = slab * POOL_SLAB;
-  const int C = a.channels, E = a.emb_dim;
-
-  // ---- statistics pooling: each lane owns 4 channels, each warp strides over rows -----------
-  for (int gi = 0; gi < n_in_group; ++gi) {
-    const int seg = g0 + gi;
-    const int len = __ldg(a.seg.len + seg);
-    const __half* base = a.h + int64_t(__ldg(a.seg.row_start + seg)) * C + c0 + lane * 4;
-    // shifted sums: k = first frame (a sample of the data) keeps S2 - S1^2/n well conditioned
-    const uint2 kraw = __ldg(reinterpret_cast<const uint2*>(base));
-    const float2 k01 = __half22float2(*reinterpret_cast<const __half2*>(&kraw.x));
-    const float2 k23 = __half22float2(*reinterpret_cast<const __half2*>(&kraw.y));
-    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-    int t = warp;
-    for (; t + 24 < len; t += 32) {                            // 4 independent 8-byte loads in flight
-      uint2 raw[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) raw[u] = __ldg(reinterpret_cast<const uint2*>(base + int64_t(t + 8 * u) * C));
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float2 x01 = __half22float2(*reinterpret_cast<const __half2*>(&raw[u].x));
-        const float2 x23 = __half22float2(*reinterpret_cast<const __half2*>(&raw[u].y));
-        const float d0 = x01.x - k01.x, d1 = x01.y - k01.y, d2 = x23.x - k23.x, d3 = x23.y - k23.y;
-        s1[0] += d0; s1[1] += d1; s1[2] += d2; s1[3] += d3;
-        s2[0] = fmaf(d0, d0, s2[0]); s2[1] = fmaf(d1, d1, s2[1]);
-        s2[2] = fmaf(d2, d2, s2[2]); s2[3] = fmaf(d3, d3, s2[3]);
-      }
-    }
-    for (; t < len; t += 8) {
-      const uint2 raw = __ldg(reinterpret_cast<const uint2*>(base + int64_t(t) * C));
-      const float2 x01 = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
-      const float2 x23 = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-      const float d0 = x01.x - k01.x, d1 = x01.y - k01.y, d2 = x23.x - k23.x, d3 = x23.y - k23.y;
-      s1[0] += d0; s1[1] += d1; s1[2] += d2; s1[3] += d3;
-      s2[0] = fmaf(d0, d0, s2[0]); s2[1] = fmaf(d1, d1, s2[1]);
-      s2[2] = fmaf(d2, d2, s2[2]); s2[3] = fmaf(d3, d3, s2[3]);
-    }
-    __syncthreads();                                            // s_red free (previous segment consumed)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      s_red[0][warp][lane * 4 + e] = s1[e];
-      s_red[1][warp][lane * 4 + e] = s2[e];
-    }
-    __syncthreads();
-    if (tid < POOL_SLAB) {
-      float S1 = 0.f, S2 = 0.f;
-#pragma unroll
-      for (int w = 0; w < POOL_THREADS / 32; ++w) { S1 += s_red[0][w][tid]; S2 += s_red[1][w][tid]; }
-      const float k = __half2float(__ldg(a.h + int64_t(__ldg(a.seg.row_start + seg)) * C + c0 + tid));
-      const float inv_n = 1.f / float(len);
-      const float dm = S1 * inv_n;
-      const float mean = k + dm;
-      const float var = fmaxf(S2 * inv_n - dm * dm, 0.f);       // population variance (tf.nn.moments)
-      const float sd = sqrtf(var + a.var_eps);                  // models.py:486
-      s_stats[gi][tid] = mean;
-      s_stats[gi][POOL_SLAB + tid] = sd;
-      if (a.stats_out != nullptr) {
-        a.stats_out[int64_t(seg) * 2 * C + c0 + tid] = mean;
-        a.stats_out[int64_t(seg) * 2 * C + C + c0 + tid] = sd;
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- embed_layer-0 partial product for this channel slab -------------------------------
-  const int ept = E / POOL_THREADS;                             // outputs per thread
-  float acc[POOL_MAX_G][POOL_MAX_EPT];
-#pragma unroll
-  for (int gi = 0; gi < POOL_MAX_G; ++gi)
-#pragma unroll
-    for (int i = 0; i < POOL_MAX_EPT; ++i) acc[gi][i] = 0.f;
-#pragma unroll 4
-  for (int r = 0; r < 2 * POOL_SLAB; ++r) {
-    const int wrow = (r < POOL_SLAB) ? (c0 + r) : (C + c0 + r - POOL_SLAB);     // mean rows, then std rows
-    const float* wp = a.w0 + int64_t(wrow) * E + tid;
-    float w[POOL_MAX_EPT];
-#pragma unroll
-    for (int i = 0; i < POOL_MAX_EPT; ++i) w[i] = (i < ept) ? __ldg(wp + i * POOL_THREADS) : 0.f;
-#pragma unroll
-    for (int gi = 0; gi < POOL_MAX_G; ++gi) {
-      if (gi < n_in_group) {
-        const float s = s_stats[gi][r];
-#pragma unroll
-        for (int i = 0; i < POOL_MAX_EPT; ++i) acc[gi][i] = fmaf(s, w[i], acc[gi][i]);
-      }
-    }
-  }
-#pragma unroll
-  for (int gi = 0; gi < POOL_MAX_G; ++gi) {
-    if (gi < n_in_group) {
-#pragma unroll
-      for (int i = 0; i < POOL_MAX_EPT; ++i)
-        if (i < ept) a.partial[(int64_t(slab) * a.seg.n_seg + g0 + gi) * E + tid + i * POOL_THREADS] = acc[gi][i];
-    }
-  }
-
-  // ---- the last CTA of the group sums the slabs in a fixed order (deterministic) ------------
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(a.counters + blockIdx.x, 1u) == uint32_t(n_slabs - 1));
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    for (int gi = 0; gi < n_in_group; ++gi) {
-      for (int o = tid; o < E; o += POOL_THREADS) {
-        float sum = __ldg(a.b0 + o);
-        for (int s = 0; s < n_slabs; ++s) sum += __ldcg(a.partial + (int64_t(s) * a.seg.n_seg + g0 + gi) * E + o);
-        a.emb[int64_t(g0 + gi) * E + o] = sum;
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 // Second half of statistics pooling, fed by the per-block partial sums that the last frame
 // layer's epilogue (tdnn_pair_kernel mode 1) wrote:
 //   partial[block][0][c] = sum of y over the block's valid rows, partial[block][1][c] = sum of y*y.
@@ -275,6 +123,8 @@ __device__ __forceinline__ void store_split(__half* row, int K, int k, float x) 
 }
 
 __global__ void __launch_bounds__(STATS_THREADS) pool_stats_kernel(const StatsArgs a) {
+  cudaTriggerProgrammaticLaunchCompletion();
+  cudaGridDependencySynchronize();
   const int seg = blockIdx.y;
   const int c = blockIdx.x * STATS_THREADS + threadIdx.x;
   const int C = a.channels;
@@ -324,6 +174,8 @@ struct FcReduceArgs {
 };
 
 __global__ void __launch_bounds__(256) embed_reduce_kernel(const FcReduceArgs a) {
+  cudaTriggerProgrammaticLaunchCompletion();
+  cudaGridDependencySynchronize();
   const int64_t i4 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;          // one float4 of the output
   const int64_t n4 = int64_t(a.n_seg) * a.E / 4;
   if (i4 >= n4) return;
@@ -369,6 +221,8 @@ __global__ void __launch_bounds__(FC_THREADS) embed_fc_kernel(const FcArgs a) {
   __shared__ __align__(16) float As[FC_BK][FC_BM + 4];          // k-major: a thread's 8 segments are two float4
   __shared__ __align__(16) float Bs[FC_BK][FC_BN];
   __shared__ int s_last;
+  cudaTriggerProgrammaticLaunchCompletion();
+  cudaGridDependencySynchronize();
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
   const int seg0 = blockIdx.x * FC_BM, o0 = blockIdx.y * FC_BN;
   const int split = blockIdx.z, n_splits = gridDim.z;
@@ -452,6 +306,8 @@ __global__ void __launch_bounds__(FC_THREADS) embed_fc_kernel(const FcArgs a) {
 // ------------------------------------------------------------------------------------------
 __global__ void unpack_rows_kernel(const __half* __restrict__ h, SegMeta seg, int32_t channels,
                                    float* __restrict__ out) {
+  cudaTriggerProgrammaticLaunchCompletion();
+  cudaGridDependencySynchronize();
   const int s = blockIdx.x;
   const int len = seg.len[s];
   const int64_t src0 = int64_t(seg.row_start[s]) * channels, dst0 = int64_t(seg.feat_start[s]) * channels;

@@ -179,6 +179,10 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
   ptx::cluster_sync_all();                    // barrier inits + TMEM allocation visible to both CTAs
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // Programmatic dependent launch: everything above (barriers, TMEM, tensor-map prefetch) overlapped the tail of
+  // the previous kernel; its output is read -- and ours written -- only after this point.
+  cudaTriggerProgrammaticLaunchCompletion();
+  cudaGridDependencySynchronize();
 
   // Work items of this cluster.  Streaming weights: item = tile index (channel tile fastest, so that
   // neighbouring clusters share activation rows in L2).  Resident weights: the cluster keeps channel tile

@@ -15,7 +15,6 @@
 #include <vector>
 
 #include "pack_pool.cuh"
-#include "tdnn_layer.cuh"
 #include "tdnn_pair.cuh"
 
 namespace {
@@ -53,7 +52,6 @@ struct Plan {
   int64_t total_frames = 0;
   int32_t n_seg = 0;
   int64_t r_pad = 0;
-  int32_t group = 1, n_groups = 0, n_slabs = 0;      // first-generation pool_embed_kernel grid
   int32_t fc_m_tiles = 0, fc_n_tiles = 0, fc_splits = 1, fc_k_per_split = 0, n_counters = 0;
   int32_t tc_splits = 1;             // K-splits of the tensor-core embedding GEMM
   size_t off_split = 0;
@@ -78,6 +76,7 @@ struct xv_model {
   std::vector<FrameLayer> layers;
   __half* w0_split_dev = nullptr;    // [E, 3 * 2C] fp16 K-major [hi | lo | hi]: B operand of the split-precision GEMM
   int opt_fc_max_splits = 36;        // cap on the K-splits of the tensor-core embedding GEMM
+  int opt_pdl = 1;                   // programmatic dependent launch between the kernels of a forward
   int opt_fc = 1;                    // 1: embed_layer-0 on tensor cores (split fp16), 0: fp32 SIMT GEMM
   float* w0_dev = nullptr;           // [2C, E]
   float* b0_dev = nullptr;           // [E]
@@ -103,9 +102,6 @@ struct xv_model {
   int slot_next = 0;
   int32_t last_launches = 0;
   // options
-  int opt_reuse = 0;
-  int opt_desc_base_offset = 1;
-  int opt_pipeline = 2;              // 2: CTA-pair kernels + pooled last layer; 1: first-generation single-CTA kernels
   int num_clusters = 74;             // co-resident CTA pairs of tdnn_pair_kernel
   int opt_resident = 0;              // 1: keep a channel tile's weights resident in shared memory when they fit
                                      // (measured on B200: no faster than streaming 128-wide stages; kept as an option)
@@ -127,15 +123,12 @@ Plan make_plan(const xv_model* m, int64_t total_frames, int32_t n_seg) {
   const int64_t rows = total_frames + int64_t(n_seg) * (m->gap + tdnn2::POOL_BLOCK - 1);
   p.r_pad = round_up(std::max<int64_t>(rows, 1), tdnn2::TILE_ROWS);
   const int c_last = m->topo.width[m->topo.n_frame_layers - 1];
-  p.n_slabs = c_last / xvk::POOL_SLAB;
-  p.group = int(std::min<int64_t>(xvk::POOL_MAX_G, std::max<int64_t>(1, n_seg / 64)));
-  p.n_groups = (n_seg + p.group - 1) / p.group;
   const int K = 2 * c_last;
   p.fc_m_tiles = (n_seg + xvk::FC_BM - 1) / xvk::FC_BM;
   p.fc_n_tiles = m->topo.emb_dim / xvk::FC_BN;
   p.fc_splits = K / 256;                                       // C_last is a multiple of 128
   p.fc_k_per_split = K / p.fc_splits;
-  p.n_counters = std::max(p.n_groups, p.fc_m_tiles * p.fc_n_tiles);
+  p.n_counters = p.fc_m_tiles * p.fc_n_tiles;
   {
     // tensor-core embedding GEMM: K' = 3K in 128-wide chunks, cut into as many K-splits as keep all CTA pairs busy
     const int chunks = 3 * K / 128;
@@ -155,11 +148,11 @@ Plan make_plan(const xv_model* m, int64_t total_frames, int32_t n_seg) {
   p.off_x0 = take(size_t(p.r_pad) * m->k0_pad * 2);
   p.off_ha = take(size_t(p.r_pad) * m->w_mid * 2);
   p.off_hb = take(size_t(p.r_pad) * m->w_mid * 2);
-  p.off_hlast = take(size_t(p.r_pad) * c_last * 2);          // only written by the debug / v1 paths
+  p.off_hlast = take(size_t(p.r_pad) * c_last * 2);          // only written when a caller asks for the last layer's activations
   p.off_pool_partial = take(size_t(p.r_pad / tdnn2::POOL_BLOCK) * 2 * c_last * 4);
   p.off_stats = take(size_t(n_seg) * K * 4);
   p.off_split = take(size_t(round_up(n_seg, tdnn2::CTA_ROWS)) * 3 * K * 2);   // rows padded to the TMA box (never read back)
-  p.off_partial = take(size_t(std::max(std::max(p.n_slabs, p.fc_splits), p.tc_splits)) * n_seg * m->topo.emb_dim * 4);
+  p.off_partial = take(size_t(std::max(p.fc_splits, p.tc_splits)) * n_seg * m->topo.emb_dim * 4);
   p.bytes = off;
   return p;
 }
@@ -291,6 +284,25 @@ int prof_mark(xv_model* m, cudaStream_t stream) {
   return XV_OK;
 }
 
+
+// Every kernel is launched with the programmatic-stream-serialization attribute (PDL): the kernels call
+// cudaGridDependencySynchronize() before touching global memory, so a kernel's prologue overlaps its
+// predecessor's tail.  opt_pdl = 0 falls back to plain stream order.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
 int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_host, int32_t n_seg, float* emb_dev,
                  void* workspace_dev, size_t workspace_bytes, cudaStream_t stream, float* const* layer_out_dev,
                  float* stats_out_dev) {
@@ -363,6 +375,7 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
   __half* hlast = reinterpret_cast<__half*>(ws + p.off_hlast);
   float* pool_partial = reinterpret_cast<float*>(ws + p.off_pool_partial);
   int launches = 0;
+  const bool pdl = m->opt_pdl != 0 && !m->opt_profile;
   m->prof_used = 0;
 #define XV_PROF() do { int prc_ = prof_mark(m, stream); if (prc_ != XV_OK) return prc_; } while (0)
 
@@ -384,7 +397,7 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
     a.n_counters = p.n_counters;
     const int blocks = int(r_pad / xvk::PACK_ROWS_PER_BLOCK);      // >= n_seg: covers n_counters with 256 threads each
     XV_PROF();
-    xvk::pack_im2col_kernel<<<blocks, xvk::PACK_THREADS, 0, stream>>>(a);
+    XV_CUDA(launch_k(pdl, xvk::pack_im2col_kernel, dim3(blocks), dim3(xvk::PACK_THREADS), 0, stream, a));
     XV_PROF();
     XV_CUDA(cudaGetLastError());
     ++launches;
@@ -392,7 +405,6 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
 
   // ---- frame-level TDNN stack: one fused tcgen05 kernel per layer --------------------------
   const int nl = m->topo.n_frame_layers;
-  const bool pair = m->opt_pipeline == 2;
   const bool want_last = layer_out_dev && layer_out_dev[nl - 1];
   const __half* in = x0;
   for (int i = 0; i < nl; ++i) {
@@ -401,7 +413,7 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
     __half* out = last ? hlast : ((i & 1) ? hb : ha);
     const int halo = (L.gemm_taps - 1) / 2 * L.dilation;
     const int c_in_gemm = (i == 0) ? L.k_total : L.c_in_pad;       // row width of the input matrix
-    if (pair) {
+    {
       const bool reuse = L.gemm_taps > 1 && halo <= tdnn2::MAX_REUSE_HALO;
       CUtensorMap ta, tw, tc;
       rc = encode_2d(m, &ta, const_cast<__half*>(in), uint64_t(c_in_gemm), uint64_t(r_pad), tdnn2::BLOCK_K,
@@ -461,50 +473,17 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
         }
         a.c_chunks = c_in_gemm / (atoms * tdnn2::BLOCK_K);
         XV_PROF();
-        if (mode == 1 && atoms == 1) tdnn2::tdnn_pair_kernel<1, 1><<<grid, tdnn2::NUM_THREADS, tdnn2::SMEM_BYTES, stream>>>(ta, tw, tc, a);
-        else if (mode == 1) tdnn2::tdnn_pair_kernel<1, 2><<<grid, tdnn2::NUM_THREADS, tdnn2::SMEM_BYTES, stream>>>(ta, tw, tc, a);
-        else if (atoms == 1) tdnn2::tdnn_pair_kernel<0, 1><<<grid, tdnn2::NUM_THREADS, tdnn2::SMEM_BYTES, stream>>>(ta, tw, tc, a);
-        else tdnn2::tdnn_pair_kernel<0, 2><<<grid, tdnn2::NUM_THREADS, tdnn2::SMEM_BYTES, stream>>>(ta, tw, tc, a);
+        if (mode == 1 && atoms == 1) XV_CUDA(launch_k(pdl, tdnn2::tdnn_pair_kernel<1, 1>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
+        else if (mode == 1) XV_CUDA(launch_k(pdl, tdnn2::tdnn_pair_kernel<1, 2>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
+        else if (atoms == 1) XV_CUDA(launch_k(pdl, tdnn2::tdnn_pair_kernel<0, 1>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
+        else XV_CUDA(launch_k(pdl, tdnn2::tdnn_pair_kernel<0, 2>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
         XV_PROF();
         XV_CUDA(cudaGetLastError());
         ++launches;
       }
-    } else {
-      const bool reuse = m->opt_reuse && L.gemm_taps > 1 && halo <= tdnn::MAX_REUSE_HALO;
-      CUtensorMap ta, tw, tc;
-      rc = encode_2d(m, &ta, const_cast<__half*>(in), uint64_t(c_in_gemm), uint64_t(r_pad), tdnn::BLOCK_K,
-                     reuse ? tdnn::A_BOX_ROWS_REUSE : tdnn::A_BOX_ROWS_PLAIN, CU_TENSOR_MAP_SWIZZLE_128B);
-      if (rc != XV_OK) return rc;
-      rc = encode_2d(m, &tw, L.w_dev, uint64_t(L.k_total), uint64_t(L.c_out), tdnn::BLOCK_K, tdnn::BLOCK_N,
-                     CU_TENSOR_MAP_SWIZZLE_128B);
-      if (rc != XV_OK) return rc;
-      rc = encode_2d(m, &tc, out, uint64_t(L.c_out), uint64_t(r_pad), tdnn::C_CHUNK, tdnn::BLOCK_M,
-                     CU_TENSOR_MAP_SWIZZLE_64B);
-      if (rc != XV_OK) return rc;
-      tdnn::LayerArgs a{};
-      a.n_m_tiles = int32_t(r_pad / tdnn::BLOCK_M);
-      a.n_n_tiles = L.c_out / tdnn::BLOCK_N;
-      a.c_chunks = c_in_gemm / tdnn::BLOCK_K;
-      a.taps = L.gemm_taps;
-      a.dilation = L.dilation;
-      a.c_in_pad = c_in_gemm;
-      a.reuse = reuse ? 1 : 0;
-      a.desc_base_offset = reuse ? 0 : m->opt_desc_base_offset;
-      a.bias = L.bias_dev;
-      a.scale = L.scale_dev;
-      a.shift = L.shift_dev;
-      a.row_valid = row_valid;
-      a.overflow_flag = m->overflow_dev;
-      const int64_t tiles = int64_t(a.n_m_tiles) * a.n_n_tiles;
-      const int grid = int(std::min<int64_t>(tiles, m->num_sms));
-      XV_PROF();
-      tdnn::tdnn_layer_kernel<<<grid, tdnn::NUM_THREADS, tdnn::SMEM_BYTES, stream>>>(ta, tw, tc, a);
-      XV_PROF();
-      XV_CUDA(cudaGetLastError());
-      ++launches;
     }
     if (layer_out_dev && layer_out_dev[i]) {
-      xvk::unpack_rows_kernel<<<n_seg, 256, 0, stream>>>(out, seg, L.c_out, layer_out_dev[i]);
+      XV_CUDA(launch_k(pdl, xvk::unpack_rows_kernel, dim3(n_seg), dim3(256), 0, stream, static_cast<const __half*>(out), seg, int32_t(L.c_out), layer_out_dev[i]));
       XV_CUDA(cudaGetLastError());
       ++launches;
     }
@@ -512,7 +491,7 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
   }
 
   // ---- statistics pooling + embed_layer-0 -----------------------------------------------
-  if (pair) {
+  {
     const bool fc_tc = m->opt_fc == 1 && (2 * m->topo.width[nl - 1]) % 128 == 0 && m->topo.emb_dim % tdnn2::TILE_CH == 0;
     float* stats = stats_out_dev ? stats_out_dev : (fc_tc ? nullptr : reinterpret_cast<float*>(ws + p.off_stats));
     __half* split = fc_tc ? reinterpret_cast<__half*>(ws + p.off_split) : nullptr;
@@ -528,7 +507,7 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       a.var_eps = m->topo.var_eps;
       dim3 grid((a.channels + xvk::STATS_THREADS - 1) / xvk::STATS_THREADS, n_seg);
       XV_PROF();
-      xvk::pool_stats_kernel<<<grid, xvk::STATS_THREADS, 0, stream>>>(a);
+      XV_CUDA(launch_k(pdl, xvk::pool_stats_kernel, grid, dim3(xvk::STATS_THREADS), 0, stream, a));
       XV_PROF();
       XV_CUDA(cudaGetLastError());
       ++launches;
@@ -560,7 +539,7 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       const int64_t tiles = int64_t(a.n_row_tiles) * a.n_ch_tiles * a.k_splits;
       const int grid = 2 * int(std::min<int64_t>(tiles, m->num_clusters));
       XV_PROF();
-      tdnn2::tdnn_pair_kernel<2, 2><<<grid, tdnn2::NUM_THREADS, tdnn2::SMEM_BYTES, stream>>>(ta, tw, tc, a);
+      XV_CUDA(launch_k(pdl, tdnn2::tdnn_pair_kernel<2, 2>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
       XV_PROF();
       XV_CUDA(cudaGetLastError());
       ++launches;
@@ -573,7 +552,7 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       r.splits = p.tc_splits;
       const int64_t n4 = int64_t(n_seg) * E / 4;
       XV_PROF();
-      xvk::embed_reduce_kernel<<<int((n4 + 255) / 256), 256, 0, stream>>>(r);
+      XV_CUDA(launch_k(pdl, xvk::embed_reduce_kernel, dim3(unsigned((n4 + 255) / 256)), dim3(256), 0, stream, r));
       XV_PROF();
       XV_CUDA(cudaGetLastError());
       ++launches;
@@ -591,31 +570,11 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       a.k_per_split = p.fc_k_per_split;
       dim3 grid(p.fc_m_tiles, p.fc_n_tiles, p.fc_splits);
       XV_PROF();
-      xvk::embed_fc_kernel<<<grid, xvk::FC_THREADS, 0, stream>>>(a);
+      XV_CUDA(launch_k(pdl, xvk::embed_fc_kernel, grid, dim3(xvk::FC_THREADS), 0, stream, a));
       XV_PROF();
       XV_CUDA(cudaGetLastError());
       ++launches;
     }
-  } else {
-    xvk::PoolArgs a{};
-    a.h = hlast;
-    a.seg = seg;
-    a.channels = m->topo.width[nl - 1];
-    a.emb_dim = m->topo.emb_dim;
-    a.group = p.group;
-    a.w0 = m->w0_dev;
-    a.b0 = m->b0_dev;
-    a.partial = reinterpret_cast<float*>(ws + p.off_partial);
-    a.counters = counters;
-    a.emb = emb_dev;
-    a.stats_out = stats_out_dev;
-    a.var_eps = m->topo.var_eps;
-    dim3 grid(p.n_groups, p.n_slabs);
-    XV_PROF();
-    xvk::pool_embed_kernel<<<grid, xvk::POOL_THREADS, 0, stream>>>(a);
-    XV_PROF();
-    XV_CUDA(cudaGetLastError());
-    ++launches;
   }
   m->last_launches = launches;
 #undef XV_PROF
@@ -636,14 +595,13 @@ int xv_create(xv_model** out, int device, const xv_topology* topo) {
   if (t.n_frame_layers < 2 || t.n_frame_layers > XV_MAX_FRAME_LAYERS) return fail(XV_EINVAL, "n_frame_layers out of range");
   if (t.feat_dim <= 0) return fail(XV_EINVAL, "feat_dim must be positive");
   if (t.act != XV_ACT_RELU) return fail(XV_EINVAL, "only XV_ACT_RELU is implemented");
-  if (t.emb_dim <= 0 || t.emb_dim % xvk::POOL_THREADS != 0 || t.emb_dim > xvk::POOL_THREADS * xvk::POOL_MAX_EPT)
-    return fail(XV_EINVAL, "emb_dim must be a multiple of 256 and <= 1024");
+  if (t.emb_dim <= 0 || t.emb_dim % tdnn2::TILE_CH != 0 || t.emb_dim > 4096)
+    return fail(XV_EINVAL, "emb_dim must be a multiple of 256 and <= 4096");
   for (int i = 0; i < t.n_frame_layers; ++i) {
     if (t.taps[i] < 1 || t.taps[i] % 2 == 0) return fail(XV_EINVAL, "taps must be odd and >= 1");
     if (t.dilation[i] < 1) return fail(XV_EINVAL, "dilation must be >= 1");
     if (t.width[i] <= 0 || t.width[i] % tdnn2::TILE_CH != 0) return fail(XV_EINVAL, "layer widths must be multiples of 256");
   }
-  if (t.width[t.n_frame_layers - 1] % xvk::POOL_SLAB != 0) return fail(XV_EINVAL, "last width must be a multiple of 128");
   {
     const int halo0 = (t.taps[0] - 1) / 2 * t.dilation[0];
     const int64_t k0 = round_up(int64_t(t.taps[0]) * t.feat_dim, (2 * tdnn2::BLOCK_K));
@@ -695,9 +653,7 @@ int xv_create(xv_model** out, int device, const xv_topology* topo) {
     return fail(XV_ECUDA, "cuTensorMapEncodeTiled is not available from the CUDA driver");
   }
   m->encode = reinterpret_cast<EncodeTiledFn>(fn);
-  e = cudaFuncSetAttribute(tdnn::tdnn_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn::SMEM_BYTES);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(tdnn2::tdnn_pair_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
+  e = cudaFuncSetAttribute(tdnn2::tdnn_pair_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(tdnn2::tdnn_pair_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
   if (e == cudaSuccess)
@@ -922,19 +878,14 @@ int32_t xv_last_kernel_ms(xv_model* m, float* ms_out, int32_t cap) {
 int xv_set_option(xv_model* m, const char* name, int64_t value) {
   if (!m || !name) return fail(XV_EINVAL, "null argument");
   const std::string n(name);
-  if (n == "reuse_taps") m->opt_reuse = value != 0;
-  else if (n == "desc_base_offset") m->opt_desc_base_offset = value != 0;
-  else if (n == "profile") m->opt_profile = value != 0;
+  if (n == "profile") m->opt_profile = value != 0;
   else if (n == "resident") m->opt_resident = int(value);
   else if (n == "prefetch") m->opt_prefetch = value != 0;
   else if (n == "fc") m->opt_fc = int(value);
+  else if (n == "pdl") m->opt_pdl = value != 0;
   else if (n == "fc_max_splits") m->opt_fc_max_splits = std::max(1, int(value));
   else if (n == "trace_ptr") m->opt_trace = reinterpret_cast<long long*>(static_cast<intptr_t>(value));   // device buffer
   else if (n == "trace_layer") m->opt_trace_layer = int(value);
-  else if (n == "pipeline") {
-    if (value != 1 && value != 2) return fail(XV_EINVAL, "pipeline must be 1 or 2");
-    m->opt_pipeline = int(value);
-  }
   else return fail(XV_EINVAL, "unknown option: " + n);
   return XV_OK;
 }
