@@ -34,7 +34,7 @@ eng.forward(feats, lens)
 torch.cuda.synchronize()
 eng.set_option("trace_layer", -1)
 t = trace.cpu().numpy()
-names = ["ld_first", "ld_last", "mma_start", "mma_issued", "epi_sees", "epi_release", "epi_done"]
+names = ["ld_first", "ld_last", "mma_start", "mma_issued", "epi_sees", "epi_release", "epi_done", "epi_done_all"]
 for rank in (0, 1):
     x = t[cluster, rank].astype(np.int64)
     base = x[x > 0].min() if (x > 0).any() else 0
@@ -43,7 +43,7 @@ for rank in (0, 1):
     for it in range(TT):
         if not (x[it] > 0).any():
             break
-        print("%4d " % it + " ".join("%11d" % (v - base) if v > 0 else "%11s" % "-" for v in x[it, :7]))
+        print("%4d " % it + " ".join("%11d" % (v - base) if v > 0 else "%11s" % "-" for v in x[it, :8]))
 x = t[cluster, 0].astype(np.int64)
 n = int((x[:, 4] > 0).sum())
 if n > 3:

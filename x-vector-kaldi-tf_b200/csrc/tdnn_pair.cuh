@@ -128,6 +128,27 @@ __device__ __forceinline__ void epi_store_math(const uint32_t (&v)[32], uint32_t
   }
 }
 
+// Walks one cluster's work items (item, item + step, ...) keeping (row tile, K split, channel tile) as mixed-radix
+// digits, so that no integer division sits on any role's per-tile path (they cost ~1500 cycles per tile there).
+struct TileCursor {
+  int item, row, split, ch;
+  int step, d_row, d_split, d_ch, n_ch, n_split;
+  __device__ __forceinline__ void init(int first, int step_, int n_ch_, int n_split_, bool resident, int my_ch) {
+    item = first; step = step_; n_ch = n_ch_; n_split = n_split_;
+    if (resident) {                       // items are row tiles of a fixed channel tile
+      row = first; split = 0; ch = my_ch; d_row = step_; d_split = 0; d_ch = 0;
+    } else {                              // item = (row * n_split + split) * n_ch + ch
+      ch = first % n_ch_; split = (first / n_ch_) % n_split_; row = first / (n_ch_ * n_split_);
+      d_ch = step_ % n_ch_; d_split = (step_ / n_ch_) % n_split_; d_row = step_ / (n_ch_ * n_split_);
+    }
+  }
+  __device__ __forceinline__ void next() {
+    item += step; ch += d_ch; split += d_split; row += d_row;
+    if (ch >= n_ch) { ch -= n_ch; ++split; }
+    if (split >= n_split) { split -= n_split; ++row; }
+  }
+};
+
 template <int MODE, int ATOMS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations in  [R_pad, C_in_pad] fp16
@@ -193,9 +214,8 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
   const int n_items = resident ? args.n_row_tiles : args.n_row_tiles * k_splits * args.n_ch_tiles;
   const int item_first = resident ? cluster_id / args.n_ch_tiles : cluster_id;
   const int item_step = resident ? n_clusters / args.n_ch_tiles : n_clusters;     // host: n_clusters % n_ch_tiles == 0
-  auto row_tile_of = [&](int item) { return resident ? item : item / (args.n_ch_tiles * k_splits); };
-  auto ch_tile_of = [&](int item) { return resident ? my_ch_tile : item % args.n_ch_tiles; };
-  auto split_of = [&](int item) { return MODE == 2 ? (item / args.n_ch_tiles) % k_splits : 0; };
+  TileCursor cur0;
+  cur0.init(item_first, item_step, args.n_ch_tiles, k_splits, resident, my_ch_tile);
   const int half_ctx = (args.taps - 1) >> 1;
   const int halo = half_ctx * args.dilation;
   const bool reuse = args.reuse != 0;
@@ -207,12 +227,12 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
     uint32_t sa = 0, pa = 0, sb = 0, pb = 0;         // stage index / phase of each ring
     const uint32_t act_full_leader = ptx::mapa_cluster(act_full(0), 0);   // transaction bytes are counted there
     const uint32_t wgt_full_leader = ptx::mapa_cluster(wgt_full(0), 0);
-    for (int item = item_first; item < n_items; item += item_step) {
-      const int r0 = row_tile_of(item) * TILE_ROWS + int(rank) * CTA_ROWS;
-      const int c0 = ch_tile_of(item) * TILE_CH + int(rank) * CTA_CH;
-      const bool load_wgt = !resident || item == item_first;
-      const int k_base = split_of(item) * args.c_chunks;               // first K chunk of this item (mode 2 split-K)
-      const uint32_t pit = uint32_t((item - item_first) / item_step);
+    uint32_t pit = 0;
+    for (TileCursor tc = cur0; tc.item < n_items; tc.next(), ++pit) {
+      const int r0 = tc.row * TILE_ROWS + int(rank) * CTA_ROWS;
+      const int c0 = tc.ch * TILE_CH + int(rank) * CTA_CH;
+      const bool load_wgt = !resident || pit == 0;
+      const int k_base = tc.split * args.c_chunks;                     // first K chunk of this item (mode 2 split-K)
       for (int cc = 0; cc < args.c_chunks; ++cc) {
         for (int j = 0; j < args.taps; ++j) {
           if (!reuse || j == 0) {
@@ -228,8 +248,10 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
                                      (k_base + cc) * STAGE_K + h * BLOCK_K, row);
               // the same boxes of this cluster's NEXT item -> L2 now: with resident weights the ring holds too few
               // bytes to cover an HBM round trip (~2000 cycles), an L2 hit (~700) it does cover
-              if (args.prefetch && item + item_step < n_items) {
-                const int row_next = row + (row_tile_of(item + item_step) - row_tile_of(item)) * TILE_ROWS;
+              if (args.prefetch && tc.item + tc.step < n_items) {
+                TileCursor nx = tc;
+                nx.next();
+                const int row_next = row + (nx.row - tc.row) * TILE_ROWS;
 #pragma unroll
                 for (int h = 0; h < ATOMS; ++h) ptx::tma_prefetch_l2_2d(&tmap_act, cc * STAGE_K + h * BLOCK_K, row_next);
               }
@@ -358,11 +380,11 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
     const uint32_t t_empty_leader = ptx::mapa_cluster(t_empty(0), 0);   // + 8 * acc
     uint32_t it = 0;
     if (MODE == 2) {
-      for (int item = item_first; item < n_items; item += item_step, ++it) {
+      for (TileCursor tc = cur0; tc.item < n_items; tc.next(), ++it) {
         const uint32_t acc = it & 1u;
-        const int row = row_tile_of(item) * TILE_ROWS + int(rank) * CTA_ROWS + q * 32 + lane;
-        const int ch0 = ch_tile_of(item) * TILE_CH + colh * 128;
-        float* dst = args.out_f32 + (size_t(split_of(item)) * args.n_rows + row) * args.c_out + ch0;
+        const int row = tc.row * TILE_ROWS + int(rank) * CTA_ROWS + q * 32 + lane;
+        const int ch0 = tc.ch * TILE_CH + colh * 128;
+        float* dst = args.out_f32 + (size_t(tc.split) * args.n_rows + row) * args.c_out + ch0;
         ptx::mbar_wait(t_full(acc), (it >> 1) & 1u);
         ptx::tc_fence_after();
         const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * TILE_CH + uint32_t(colh) * 128u;
@@ -390,16 +412,38 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
       const uint32_t sC = smem_base + OFF_C + uint32_t(e) * C_BUF_BYTES;
       const uint32_t swz = (uint32_t(lane) >> 1) & 3u;   // SWIZZLE_64B phase of this row in the staging box
       uint32_t hmax = 0;
-      for (int item = item_first; item < n_items; item += item_step, ++it) {
-        const uint32_t acc = it & 1u;
-        const int r_cta = row_tile_of(item) * TILE_ROWS + int(rank) * CTA_ROWS;
-        const int ch0 = ch_tile_of(item) * TILE_CH;
+      // Per-tile parameters (bias | scale | shift of the tile's 256 channels) live in shared memory, double-buffered
+      // by accumulator; the NEXT tile's are fetched into registers at the top of a tile and stored at its end, so
+      // no global-load latency sits between two tiles.
+      auto fetch_params = [&](const TileCursor& tc, float& b, float& sc, float& sh, uint32_t& valid) {   // loads only: no use
+        const int ch = tc.ch * TILE_CH + te;
+        b = __ldg(args.bias + ch); sc = __ldg(args.scale + ch); sh = __ldg(args.shift + ch);
+        valid = args.row_valid[tc.row * TILE_ROWS + int(rank) * CTA_ROWS + q * 32 + lane];
+      };
+      auto store_params = [&](uint32_t acc, float b, float sc, float sh) {
         const uint32_t s_par = smem_base + OFF_PARAMS + acc * (3 * TILE_CH * 4);
-        ptx::sts_f(s_par + uint32_t(te) * 4u, __ldg(args.bias + ch0 + te));
-        ptx::sts_f(s_par + uint32_t(TILE_CH + te) * 4u, __ldg(args.scale + ch0 + te));
-        ptx::sts_f(s_par + uint32_t(2 * TILE_CH + te) * 4u, __ldg(args.shift + ch0 + te));
-        const bool valid = args.row_valid[r_cta + q * 32 + lane] != 0;
-        ptx::named_bar_sync(1, NUM_EPI_THREADS);       // parameters of this tile visible (double-buffered by acc)
+        ptx::sts_f(s_par + uint32_t(te) * 4u, b);
+        ptx::sts_f(s_par + uint32_t(TILE_CH + te) * 4u, sc);
+        ptx::sts_f(s_par + uint32_t(2 * TILE_CH + te) * 4u, sh);
+      };
+      float nb = 0.f, nsc = 0.f, nsh = 0.f;
+      uint32_t nvalid = 0;
+      if (item_first < n_items) {
+        fetch_params(cur0, nb, nsc, nsh, nvalid);
+        store_params(0, nb, nsc, nsh);
+      }
+      TileCursor nx = cur0;
+      for (TileCursor tc = cur0; tc.item < n_items; tc.next(), ++it) {
+        const uint32_t acc = it & 1u;
+        const int r_cta = tc.row * TILE_ROWS + int(rank) * CTA_ROWS;
+        const int ch0 = tc.ch * TILE_CH;
+        const uint32_t s_par = smem_base + OFF_PARAMS + acc * (3 * TILE_CH * 4);
+        const bool valid = nvalid != 0;
+        ptx::named_bar_sync(1, NUM_EPI_THREADS);       // this tile's parameters visible; the other buffer is free
+        if (e == 0 && lane == 0) trace_stamp(args, cluster_id, rank, it, 5);
+        nx.next();                                     // nx is always one item ahead of tc
+        const bool has_next = nx.item < n_items;
+        if (has_next) fetch_params(nx, nb, nsc, nsh, nvalid);
         ptx::mbar_wait(t_full(acc), (it >> 1) & 1u);
         ptx::tc_fence_after();
         if (e == 0 && lane == 0) trace_stamp(args, cluster_id, rank, it, 4);
@@ -415,7 +459,6 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(t_empty_leader + 8u * acc);
-            if (e == 0 && lane == 0) trace_stamp(args, cluster_id, rank, it, 5);
           }
           uint32_t p[16];
           epi_store_math(v[chunk & 1], s_par, colh * 128 + chunk * C_CHUNK, valid, p, hmax);
@@ -436,15 +479,19 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
             ptx::tma_store_commit();
           }
         }
+        if (has_next) store_params(acc ^ 1u, nb, nsc, nsh);
         if (e == 0 && lane == 0) trace_stamp(args, cluster_id, rank, it, 6);
+        if (lane == 0 && args.trace != nullptr && it < TRACE_TILES)      // slot 7: when the slowest epilogue warp finished
+          atomicMax(reinterpret_cast<unsigned long long*>(args.trace) + ((size_t(cluster_id) * 2 + rank) * TRACE_TILES + it) * 8 + 7,
+                    static_cast<unsigned long long>(clock64()));
       }
       if (lane == 0) ptx::tma_store_wait_all<0>();
       if ((hmax & 0x7fffu) >= 0x7c00u || ((hmax >> 16) & 0x7fffu) >= 0x7c00u) atomicOr(args.overflow_flag, 1u);
     } else {
-      for (int item = item_first; item < n_items; item += item_step, ++it) {
+      for (TileCursor tc = cur0; tc.item < n_items; tc.next(), ++it) {
         const uint32_t acc = it & 1u;
-        const int r_tile = row_tile_of(item) * TILE_ROWS;
-        const int ch = ch_tile_of(item) * TILE_CH + int(rank) * CTA_CH + q * 32 + lane;
+        const int r_tile = tc.row * TILE_ROWS;
+        const int ch = tc.ch * TILE_CH + int(rank) * CTA_CH + q * 32 + lane;
         const float b = __ldg(args.bias + ch), sc = __ldg(args.scale + ch), sh = __ldg(args.shift + ch);
         const int blk0 = (r_tile + colh * 128) / POOL_BLOCK;
         const uint32_t nv4 = *reinterpret_cast<const uint32_t*>(args.blk_valid + blk0);   // 4 blocks, 1 byte each
