@@ -81,7 +81,7 @@ def ncu_traffic_bytes():
     if not files:
         return None, None
     with open(files[-1]) as f:
-        rows = [r for r in json.load(f) if "tdnn_pair_kernel" in r.get("kernel", "")]
+        rows = [r for r in json.load(f) if "tdnn_pair_kernel<0" in r.get("kernel", "") or "tdnn_pair_kernel<1" in r.get("kernel", "")]
     vals = [(r["dram_read_MB"] + r["dram_write_MB"]) * 1e6 for r in rows if r.get("dram_read_MB") is not None]
     return (round(sum(vals) / len(vals)) if vals else None), os.path.basename(files[-1])
 
@@ -347,7 +347,7 @@ def run_b200(args):
     roofline = dict(kernel="tdnn_pair_kernel (%d launches/step, figures are per-step sums / averages)" % len(fl),
                     bound="tensor", achieved=round(tdnn_tf, 1), peak=peaks["tflops"], unit="TFLOP/s",
                     frac=round(tdnn_tf / peaks["tflops"], 4), traffic=traffic,
-                    traffic_source="profiles/%s: mean DRAM bytes per launch over the kernel's 5 launches (tdnn splice, config 2)"
+                    traffic_source="profiles/%s: mean DRAM bytes per launch over the captured frame-layer launches (tdnn splice, config 2)"
                                    % traffic_src if traffic_src else None,
                     flop_per_launch_avg=round(frames * sum(fl) / len(fl)),
                     peak_source="%s bf16/fp16 burst (MEASURED_PEAKS.json)" % peaks["source"],

@@ -25,9 +25,9 @@ struct SegMeta {
 };
 
 constexpr int PACK_ROWS_PER_BLOCK = 32;      // = one aligned pooling block: rows of ONE segment (or gap)
-constexpr int PACK_THREADS = 256;
-constexpr int PACK_MAX_STAGE_FLOATS = 4096; // (32 + 2*halo0) * feat_dim floats staged per CTA
-constexpr int PACK_MAX_K0 = 512;             // k0_pad / 8 pieces per row must divide into 256 threads
+constexpr int PACK_THREADS = 128;
+constexpr int PACK_MAX_STAGE_FLOATS = 2048; // (32 + 2*halo0) * feat_dim floats staged per CTA (8 KB: 16 CTAs per SM)
+constexpr int PACK_MAX_K0 = 512;             // k0_pad / 8 = 16-byte pieces per row, at most 64 <= PACK_THREADS
 
 struct PackArgs {
   const float* feats;        // [total_frames, D]
@@ -135,15 +135,15 @@ __global__ void __launch_bounds__(STATS_THREADS) pool_stats_kernel(const StatsAr
   const float* p = a.partial + int64_t(blk0) * 2 * C + c;
   double s1 = 0.0, s2 = 0.0;
   int b = 0;
-  for (; b + 4 <= n_blk; b += 4) {                              // 8 independent loads in flight, fixed order
-    float x[4], y[4];
+  for (; b + 8 <= n_blk; b += 8) {                              // 16 independent loads in flight, fixed order
+    float x[8], y[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       x[u] = __ldg(p + int64_t(b + u) * 2 * C);
       y[u] = __ldg(p + int64_t(b + u) * 2 * C + C);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { s1 += double(x[u]); s2 += double(y[u]); }
+    for (int u = 0; u < 8; ++u) { s1 += double(x[u]); s2 += double(y[u]); }
   }
   for (; b < n_blk; ++b) {
     s1 += double(__ldg(p + int64_t(b) * 2 * C));
@@ -173,7 +173,7 @@ struct FcReduceArgs {
   int32_t n_seg, E, splits;
 };
 
-__global__ void __launch_bounds__(256) embed_reduce_kernel(const FcReduceArgs a) {
+__global__ void __launch_bounds__(64) embed_reduce_kernel(const FcReduceArgs a) {
   cudaTriggerProgrammaticLaunchCompletion();
   cudaGridDependencySynchronize();
   const int64_t i4 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;          // one float4 of the output
@@ -183,13 +183,12 @@ __global__ void __launch_bounds__(256) embed_reduce_kernel(const FcReduceArgs a)
   float4 sum = __ldg(reinterpret_cast<const float4*>(a.b0) + o4);
   const float4* p = reinterpret_cast<const float4*>(a.partial) + i4;
   int s = 0;
-  for (; s + 4 <= a.splits; s += 4) {                                          // 4 loads in flight, fixed order
-    const float4 v0 = __ldcg(p + int64_t(s) * n4), v1 = __ldcg(p + int64_t(s + 1) * n4);
-    const float4 v2 = __ldcg(p + int64_t(s + 2) * n4), v3 = __ldcg(p + int64_t(s + 3) * n4);
-    sum.x += v0.x; sum.y += v0.y; sum.z += v0.z; sum.w += v0.w;
-    sum.x += v1.x; sum.y += v1.y; sum.z += v1.z; sum.w += v1.w;
-    sum.x += v2.x; sum.y += v2.y; sum.z += v2.z; sum.w += v2.w;
-    sum.x += v3.x; sum.y += v3.y; sum.z += v3.z; sum.w += v3.w;
+  for (; s + 12 <= a.splits; s += 12) {                                        // 12 loads in flight, fixed order
+    float4 v[12];
+#pragma unroll
+    for (int u = 0; u < 12; ++u) v[u] = __ldcg(p + int64_t(s + u) * n4);
+#pragma unroll
+    for (int u = 0; u < 12; ++u) { sum.x += v[u].x; sum.y += v[u].y; sum.z += v[u].z; sum.w += v[u].w; }
   }
   for (; s < a.splits; ++s) {
     const float4 v = __ldcg(p + int64_t(s) * n4);

@@ -552,7 +552,7 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       r.splits = p.tc_splits;
       const int64_t n4 = int64_t(n_seg) * E / 4;
       XV_PROF();
-      XV_CUDA(launch_k(pdl, xvk::embed_reduce_kernel, dim3(unsigned((n4 + 255) / 256)), dim3(256), 0, stream, r));
+      XV_CUDA(launch_k(pdl, xvk::embed_reduce_kernel, dim3(unsigned((n4 + 63) / 64)), dim3(64), 0, stream, r));
       XV_PROF();
       XV_CUDA(cudaGetLastError());
       ++launches;
