@@ -51,6 +51,11 @@ TOPOLOGIES = {   # reference local/tf/models.py:443-445 and :545-548
                                     layer_sizes=[512, 512, 512, 512, 1536], embedding_sizes=[512, 512]),
     "ModelWithoutDropout": dict(kernel_sizes=[5, 5, 7, 1, 1], dilations=[1, 1, 1, 1, 1],
                                 layer_sizes=[512, 512, 512, 512, 1536], embedding_sizes=[512, 512]),
+    # nonlinearity variants of the dense topology (models.py:643-744 per-channel PReLU, :866-983 leaky_relu 0.2)
+    "ModelWithoutDropoutPRelu": dict(kernel_sizes=[5, 5, 7, 1, 1], dilations=[1, 1, 1, 1, 1],
+                                     layer_sizes=[512, 512, 512, 512, 1536], embedding_sizes=[512, 512], act="prelu"),
+    "ModelL2LossWithoutDropoutLRelu": dict(kernel_sizes=[5, 5, 7, 1, 1], dilations=[1, 1, 1, 1, 1],
+                                           layer_sizes=[512, 512, 512, 512, 1536], embedding_sizes=[512, 512], act="lrelu"),
 }
 
 
@@ -177,9 +182,9 @@ def run_b200(args):
 
     topo = TOPOLOGIES[args.topology]
     params = synthetic.make_params(topo["kernel_sizes"], topo["layer_sizes"], topo["embedding_sizes"],
-                                   weight_set=args.weight_set)
+                                   weight_set=args.weight_set, activation=topo.get("act", "relu"))
     eng = _native.XvecEngine(topo["kernel_sizes"], topo["dilations"], topo["layer_sizes"], EMB_DIM, FEAT_DIM,
-                             device=local_rank)
+                             device=local_rank, activation=topo.get("act", "relu"))
     eng.set_params(params)
     for kv in args.option:
         eng.set_option(kv.split("=")[0], int(kv.split("=")[1]))
@@ -432,7 +437,7 @@ def run_reference(args):
     threads = 2
     procs = max(1, min(cores // threads, 64))
     params = synthetic.make_params(topo["kernel_sizes"], topo["layer_sizes"], topo["embedding_sizes"],
-                                   weight_set=args.weight_set)
+                                   weight_set=args.weight_set, activation=topo.get("act", "relu"))
     frames = args.frames
     n_utts_max = 16
     feats = synthetic.mfcc_batch(2, np.full(n_utts_max, frames, np.int32))

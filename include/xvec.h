@@ -41,7 +41,11 @@ enum {
   XV_EOVERFLOW = -5    /* an activation left the fp16 range (reported by xv_check_overflow)*/
 };
 
-enum { XV_ACT_RELU = 0 };
+/* Frame-layer nonlinearity (between bias_add and BatchNorm):
+ *   XV_ACT_RELU   tf.nn.relu                    (models.py:479; Model, ModelWithoutDropout[Tdnn], ...ReluHeInit)
+ *   XV_ACT_LRELU  tf.nn.leaky_relu(alpha=0.2)   (models.py:912; ModelL2LossWithoutDropoutLRelu)
+ *   XV_ACT_PRELU  prelu(h, shared=False)        (tf_block.py:38-47; per-channel slope "<scope>/prelu/prelu:0") */
+enum { XV_ACT_RELU = 0, XV_ACT_LRELU = 1, XV_ACT_PRELU = 2 };
 
 /* Topology = the constants hard-coded in each build_model body
  * (kernel_sizes / dilation_rates / layer_sizes: models.py:443-445, :545-548). */
@@ -65,7 +69,7 @@ void xv_destroy(xv_model* m);
 
 /* Replaces saver.restore's per-variable assignment (models.py:147).  `tf_var_name` is the
  * reference's variable name, e.g. "frame_level_info_layer-2/w:0" [k,Cin,Cout],
- * ".../b:0", ".../gamma:0", ".../beta:0", ".../mean:0", ".../variance:0",
+ * ".../b:0", ".../gamma:0", ".../beta:0", ".../mean:0", ".../variance:0", ".../prelu/prelu:0" (XV_ACT_PRELU),
  * "embed_layer-0/w:0" [2*C,emb], "embed_layer-0/b:0".  `host` is fp32, C-contiguous, and is
  * copied.  Names of variables the extraction path never reads (embed_layer-1/..., output/...)
  * are accepted and ignored. */

@@ -50,6 +50,11 @@ TOPOLOGIES = {
                                 layer_sizes=[512, 512, 512, 512, 1536], embedding_sizes=[512, 512]),
     "ModelWithoutDropoutTdnn": dict(kernel_sizes=[5, 3, 3, 1, 1], dilations=[1, 2, 3, 1, 1],
                                     layer_sizes=[512, 512, 512, 512, 1536], embedding_sizes=[512, 512]),
+    # frame-layer nonlinearity variants (local/tf/models.py:643-744 prelu, :866-983 leaky_relu(0.2))
+    "ModelWithoutDropoutPRelu": dict(kernel_sizes=[5, 5, 7, 1, 1], dilations=[1, 1, 1, 1, 1],
+                                     layer_sizes=[512, 512, 512, 512, 1536], embedding_sizes=[512, 512], act="prelu"),
+    "ModelL2LossWithoutDropoutLRelu": dict(kernel_sizes=[5, 5, 7, 1, 1], dilations=[1, 1, 1, 1, 1],
+                                           layer_sizes=[512, 512, 512, 512, 1536], embedding_sizes=[512, 512], act="lrelu"),
 }
 
 

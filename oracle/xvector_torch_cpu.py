@@ -27,6 +27,7 @@ class TorchCpuXvector:
     def __init__(self, params, topology="ModelWithoutDropout", dtype=torch.float32):
         topo = TOPOLOGIES[topology] if isinstance(topology, str) else topology
         self.dtype = dtype
+        self.act = topo.get("act", "relu")       # relu | lrelu (0.2, models.py:912) | prelu (tf_block.py:38-47)
         self.layers = []
         for i, d in enumerate(topo["dilations"]):
             s = "frame_level_info_layer-%d/" % i
@@ -37,6 +38,7 @@ class TorchCpuXvector:
             self.layers.append(dict(
                 w=w.permute(2, 1, 0).contiguous(),                               # torch wants [Cout, Cin, k]
                 b=g("b:0"), inv=inv, shift=g("beta:0") - g("mean:0") * inv,
+                alpha=(g("prelu/prelu:0") if self.act == "prelu" else None),
                 dilation=d, pad=((k - 1) * d) // 2))
         self.w0 = torch.as_tensor(np.asarray(params["embed_layer-0/w:0"])).to(dtype)
         self.b0 = torch.as_tensor(np.asarray(params["embed_layer-0/b:0"])).to(dtype)
@@ -47,7 +49,12 @@ class TorchCpuXvector:
         h = torch.as_tensor(x).to(self.dtype).transpose(1, 2)                    # NWC -> NCW
         for L in self.layers:
             h = F.conv1d(h, L["w"], L["b"], padding=L["pad"], dilation=L["dilation"])
-            h = torch.relu(h)
+            if self.act == "relu":
+                h = torch.relu(h)
+            elif self.act == "lrelu":
+                h = F.leaky_relu(h, 0.2)
+            else:
+                h = torch.clamp(h, min=0) + L["alpha"][None, :, None] * torch.clamp(h, max=0)
             h = h * L["inv"][None, :, None] + L["shift"][None, :, None]
         mean = h.mean(dim=2)
         var = ((h - mean[:, :, None]) ** 2).mean(dim=2)

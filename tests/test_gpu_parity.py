@@ -22,8 +22,10 @@ TOL = 1e-3
 def _engine(topology, weight_set, **opts):
     from xvector_b200 import _native
     t = orc.TOPOLOGIES[topology]
-    params = synthetic.make_params(t["kernel_sizes"], t["layer_sizes"], t["embedding_sizes"], weight_set=weight_set)
-    eng = _native.XvecEngine(t["kernel_sizes"], t["dilations"], t["layer_sizes"], 512, 23, device=0)
+    params = synthetic.make_params(t["kernel_sizes"], t["layer_sizes"], t["embedding_sizes"], weight_set=weight_set,
+                                   activation=t.get("act", "relu"))
+    eng = _native.XvecEngine(t["kernel_sizes"], t["dilations"], t["layer_sizes"], 512, 23, device=0,
+                             activation=t.get("act", "relu"))
     eng.set_params(params)
     for k, v in opts.items():
         eng.set_option(k, v)
@@ -107,6 +109,31 @@ def test_alternative_kernel_schedules_give_the_same_embeddings(opts):
     m = orc.parity_metrics(alt, want)
     assert m["max_rel"] <= TOL and m["l2_rel"] <= TOL, m
     assert orc.parity_metrics(alt, base)["max_rel"] <= 2e-4
+    eng.close()
+
+
+@pytest.mark.parametrize("topology", ["ModelWithoutDropoutPRelu", "ModelL2LossWithoutDropoutLRelu"])
+@pytest.mark.parametrize("weight_set", ["A", "B"])
+def test_activation_variants_match_the_oracle(topology, weight_set):
+    # reference models.py:643-744 (per-channel PReLU) and :866-983 (leaky_relu 0.2): same fused kernel, other epilogue
+    import torch
+    eng, params = _engine(topology, weight_set)
+    lens = np.array([200, 37, 131, 25, 411], np.int32)
+    feats = synthetic.mfcc_batch(12, lens)
+    emb, layers, stats = eng.forward(torch.from_numpy(feats).cuda(), lens, return_layers=True)
+    torch.cuda.synchronize()
+    eng.check_overflow()
+    off = 0
+    for s, n in enumerate(lens):
+        ref_emb, ref_layers, ref_stats = orc.forward(feats[off:off + n], params, topology, return_layers=True)
+        for i, (got, want) in enumerate(zip(layers, ref_layers)):
+            g = got[off:off + n].cpu().numpy().astype(np.float64)
+            assert np.abs(g - want).max() / np.abs(want).max() < 2e-3, (s, i)
+        m = orc.parity_metrics(emb[s].cpu().numpy(), ref_emb)
+        assert m["max_rel"] <= TOL, (s, m)
+        off += n
+    plain = _run(eng, feats, lens)                              # production path (pooled last layer) == debug path
+    assert np.array_equal(plain, emb.cpu().numpy())
     eng.close()
 
 

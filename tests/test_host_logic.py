@@ -119,6 +119,23 @@ def test_make_embedding_semantics_match_the_reference_loop(model_dir, monkeypatc
         assert engines[0].calls >= 4
 
 
+def test_topology_variants_keep_the_reference_variable_names(tmp_path, monkeypatch):
+    monkeypatch.setenv("XVEC_SEED", "3")
+    for cls, act in ((models.ModelWithoutDropoutPRelu, "prelu"), (models.ModelL2LossWithoutDropoutLRelu, "lrelu"),
+                     (models.ModelL2LossWithoutDropoutReluHeInit, "relu"), (models.ModelL2LossWithoutDropoutPRelu, "prelu")):
+        d = str(tmp_path / cls.__name__)
+        cls().build_model(5, 23, d, None)
+        m = models.Model()
+        w = m.get_models_weights(d)
+        assert m.meta["activation"] == act and m.meta["model_class"] == cls.__name__
+        assert ("frame_level_info_layer-3/prelu/prelu:0" in w) == (act == "prelu")       # tf_block.py:40-46
+        if act == "prelu":
+            assert np.allclose(w["frame_level_info_layer-0/prelu/prelu:0"], 0.1)           # constant_initializer(0.1)
+        if cls is models.ModelL2LossWithoutDropoutReluHeInit:                               # he_normal, models.py:1160
+            assert abs(w["frame_level_info_layer-1/w:0"].std() - np.sqrt(2.0 / (5 * 512)) * 0.88) < 0.002
+            assert not np.allclose(w["frame_level_info_layer-1/b:0"], 0.1)
+
+
 def test_chunk_plan_edges():
     cp = models.chunk_plan
     assert cp(0, 25, 10000) is None and cp(24, 25, 10000) is None

@@ -11,10 +11,12 @@ from xvector_b200 import synthetic
 
 def _params(topology, weight_set):
     t = orc.TOPOLOGIES[topology]
-    return synthetic.make_params(t["kernel_sizes"], t["layer_sizes"], t["embedding_sizes"], weight_set=weight_set)
+    return synthetic.make_params(t["kernel_sizes"], t["layer_sizes"], t["embedding_sizes"], weight_set=weight_set,
+                                 activation=t.get("act", "relu"))
 
 
-@pytest.mark.parametrize("topology", ["ModelWithoutDropout", "ModelWithoutDropoutTdnn"])
+@pytest.mark.parametrize("topology", ["ModelWithoutDropout", "ModelWithoutDropoutTdnn", "ModelWithoutDropoutPRelu",
+                                      "ModelL2LossWithoutDropoutLRelu"])
 @pytest.mark.parametrize("weight_set", ["A", "B"])
 def test_two_restatements_agree(topology, weight_set):
     # BASELINE config 1: single 200-frame x 23 utterance, seed 1
@@ -113,3 +115,11 @@ def test_chunk_average_is_frame_weighted():
     want = (50 * parts[0] + 50 * parts[1] + 30 * parts[2]) / 130.0
     assert np.allclose(got, want, rtol=1e-12)
     assert orc.make_embedding_one(x[:10], p, "ModelWithoutDropoutTdnn", 25, 50) is None
+
+
+def test_leaky_and_parametric_relu_definitions():
+    # tf.nn.leaky_relu(x, 0.2) = max(x, 0.2 x); prelu = max(0,x) + alpha*min(0,x) per channel (tf_block.py:47)
+    y = np.array([[-2.0, 3.0], [0.5, -1.0]])
+    assert np.allclose(orc.activation(y, "lrelu"), [[-0.4, 3.0], [0.5, -0.2]])
+    assert np.allclose(orc.activation(y, "prelu", np.array([0.1, -0.5])), [[-0.2, 3.0], [0.5, 0.5]])
+    assert np.allclose(orc.activation(y, "relu"), [[0.0, 3.0], [0.5, 0.0]])

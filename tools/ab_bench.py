@@ -23,8 +23,10 @@ ap.add_argument("--frames", type=int, default=400)
 ap.add_argument("configs", nargs="+")
 args = ap.parse_args()
 topo = bench.TOPOLOGIES[args.topology]
-params = synthetic.make_params(topo["kernel_sizes"], topo["layer_sizes"], topo["embedding_sizes"], weight_set="B")
-eng = _native.XvecEngine(topo["kernel_sizes"], topo["dilations"], topo["layer_sizes"], 512, 23, device=0)
+params = synthetic.make_params(topo["kernel_sizes"], topo["layer_sizes"], topo["embedding_sizes"], weight_set="B",
+                               activation=topo.get("act", "relu"))
+eng = _native.XvecEngine(topo["kernel_sizes"], topo["dilations"], topo["layer_sizes"], 512, 23, device=0,
+                         activation=topo.get("act", "relu"))
 eng.set_params(params)
 lens = np.full(args.batch, args.frames, np.int32)
 feats = torch.from_numpy(synthetic.mfcc_batch(2, lens)).cuda()

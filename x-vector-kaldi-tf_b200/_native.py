@@ -117,8 +117,10 @@ class XvecEngine:
     """One xv_model on one CUDA device: the replacement for the reference's TF session +
     restored graph (models.py:365-366) on the extraction path."""
 
+    ACTIVATIONS = {"relu": 0, "lrelu": 1, "prelu": 2}      # XV_ACT_* (include/xvec.h)
+
     def __init__(self, kernel_sizes, dilations, layer_sizes, emb_dim, feat_dim, device=0,
-                 bn_eps=1e-3, var_eps=1e-5):
+                 bn_eps=1e-3, var_eps=1e-5, activation="relu"):
         self.lib = load_library()
         topo = XvTopology()
         topo.feat_dim = feat_dim
@@ -126,7 +128,7 @@ class XvecEngine:
         for i, (k, d, w) in enumerate(zip(kernel_sizes, dilations, layer_sizes)):
             topo.taps[i], topo.dilation[i], topo.width[i] = k, d, w
         topo.emb_dim = emb_dim
-        topo.act = 0
+        topo.act = self.ACTIVATIONS[activation]
         topo.bn_eps = bn_eps
         topo.var_eps = var_eps
         self.handle = ctypes.c_void_p()

@@ -65,7 +65,8 @@ constexpr int POOL_BLOCK = 32;                     // rows per pooled partial bl
 constexpr int OFF_RING = 0;
 constexpr int OFF_C = OFF_RING + RING_BYTES;
 constexpr int OFF_PARAMS = OFF_C + NUM_EPI_WARPS * C_BUF_BYTES;         // + 16384 (one staging box per epilogue warp)
-constexpr int OFF_BARS = OFF_PARAMS + 2 * 3 * TILE_CH * 4;              // + 6144
+constexpr int PAR_ARRAYS = 4;                      // bias | scale | shift | negative slope
+constexpr int OFF_BARS = OFF_PARAMS + 2 * PAR_ARRAYS * TILE_CH * 4;     // + 8192
 constexpr int NUM_BARS = 4 * MAX_STAGES + 4;
 constexpr int OFF_TMEM_PTR = OFF_BARS + NUM_BARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;                    // + slack for 1024-byte alignment
@@ -92,6 +93,8 @@ struct PairArgs {
   const float* bias;        // [C_out]  conv bias b
   const float* scale;       // [C_out]  gamma * rsqrt(var + eps)
   const float* shift;       // [C_out]  beta - mean * scale
+  const float* alpha;       // [C_out]  LEAKY kernels: negative slope (0.2 everywhere = leaky_relu models.py:912; PReLU's
+                            //          learned per-channel slope tf_block.py:38-47)
   const uint8_t* row_valid; // [R_pad]     mode 0: 1 = row belongs to a segment, 0 = gap / tail
   const uint8_t* blk_valid; // [R_pad/32]  mode 1: valid rows in the block (they are its first rows)
   float* partial;           // [R_pad/32][2][C_out]  mode 1
@@ -108,7 +111,16 @@ __device__ __forceinline__ void trace_stamp(const PairArgs& a, int cluster, uint
 }
 
 // One tcgen05.ld chunk of the store epilogue: 32 channels of one row -> 16 packed half2.
-// s_par: shared-memory address of this tile's [bias(256) | scale(256) | shift(256)] floats.
+// act(a): relu (models.py:479), or with LEAKY max(0,a) + alpha*min(0,a) (tf_block.py:47 / tf.nn.leaky_relu)
+template <bool LEAKY>
+__device__ __forceinline__ float act_bn(float acc, float b, float sc, float sh, float al) {
+  const float a = acc + b;
+  const float r = LEAKY ? fmaf(al, fminf(a, 0.f), fmaxf(a, 0.f)) : fmaxf(a, 0.f);
+  return fmaf(r, sc, sh);                           // BatchNorm eval branch folded: r * inv + shift (tf_block.py:26)
+}
+
+// s_par: shared-memory address of this tile's [bias(256) | scale(256) | shift(256) | alpha(256)] floats.
+template <bool LEAKY>
 __device__ __forceinline__ void epi_store_math(const uint32_t (&v)[32], uint32_t s_par, int c, bool valid,
                                                uint32_t (&p)[16], uint32_t& hmax) {
 #pragma unroll
@@ -116,11 +128,12 @@ __device__ __forceinline__ void epi_store_math(const uint32_t (&v)[32], uint32_t
     const float4 b4 = ptx::lds_f4(s_par + uint32_t(c + g * 4) * 4u);
     const float4 s4 = ptx::lds_f4(s_par + uint32_t(TILE_CH + c + g * 4) * 4u);
     const float4 h4 = ptx::lds_f4(s_par + uint32_t(2 * TILE_CH + c + g * 4) * 4u);
-    // relu(acc + b) * inv + shift      (models.py:477-480, tf_block.py:26)
-    const float y0 = fmaf(fmaxf(__uint_as_float(v[g * 4 + 0]) + b4.x, 0.f), s4.x, h4.x);
-    const float y1 = fmaf(fmaxf(__uint_as_float(v[g * 4 + 1]) + b4.y, 0.f), s4.y, h4.y);
-    const float y2 = fmaf(fmaxf(__uint_as_float(v[g * 4 + 2]) + b4.z, 0.f), s4.z, h4.z);
-    const float y3 = fmaf(fmaxf(__uint_as_float(v[g * 4 + 3]) + b4.w, 0.f), s4.w, h4.w);
+    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (LEAKY) a4 = ptx::lds_f4(s_par + uint32_t(3 * TILE_CH + c + g * 4) * 4u);
+    const float y0 = act_bn<LEAKY>(__uint_as_float(v[g * 4 + 0]), b4.x, s4.x, h4.x, a4.x);
+    const float y1 = act_bn<LEAKY>(__uint_as_float(v[g * 4 + 1]), b4.y, s4.y, h4.y, a4.y);
+    const float y2 = act_bn<LEAKY>(__uint_as_float(v[g * 4 + 2]), b4.z, s4.z, h4.z, a4.z);
+    const float y3 = act_bn<LEAKY>(__uint_as_float(v[g * 4 + 3]), b4.w, s4.w, h4.w, a4.w);
     const uint32_t p0 = ptx::pack_half2(y0, y1), p1 = ptx::pack_half2(y2, y3);
     hmax = ptx::habs2_max(ptx::habs2_max(hmax, p0), p1);
     p[g * 2 + 0] = valid ? p0 : 0u;                  // gap rows stay exact zeros
@@ -149,7 +162,7 @@ struct TileCursor {
   }
 };
 
-template <int MODE, int ATOMS>
+template <int MODE, int ATOMS, bool LEAKY>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations in  [R_pad, C_in_pad] fp16
                  const __grid_constant__ CUtensorMap tmap_wgt,   // weights [C_out, taps*C_in_pad] fp16 (K-major)
@@ -415,35 +428,37 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
       // Per-tile parameters (bias | scale | shift of the tile's 256 channels) live in shared memory, double-buffered
       // by accumulator; the NEXT tile's are fetched into registers at the top of a tile and stored at its end, so
       // no global-load latency sits between two tiles.
-      auto fetch_params = [&](const TileCursor& tc, float& b, float& sc, float& sh, uint32_t& valid) {   // loads only: no use
+      auto fetch_params = [&](const TileCursor& tc, float& b, float& sc, float& sh, float& al, uint32_t& valid) {   // loads only
         const int ch = tc.ch * TILE_CH + te;
         b = __ldg(args.bias + ch); sc = __ldg(args.scale + ch); sh = __ldg(args.shift + ch);
+        if (LEAKY) al = __ldg(args.alpha + ch);
         valid = args.row_valid[tc.row * TILE_ROWS + int(rank) * CTA_ROWS + q * 32 + lane];
       };
-      auto store_params = [&](uint32_t acc, float b, float sc, float sh) {
-        const uint32_t s_par = smem_base + OFF_PARAMS + acc * (3 * TILE_CH * 4);
+      auto store_params = [&](uint32_t acc, float b, float sc, float sh, float al) {
+        const uint32_t s_par = smem_base + OFF_PARAMS + acc * (PAR_ARRAYS * TILE_CH * 4);
         ptx::sts_f(s_par + uint32_t(te) * 4u, b);
         ptx::sts_f(s_par + uint32_t(TILE_CH + te) * 4u, sc);
         ptx::sts_f(s_par + uint32_t(2 * TILE_CH + te) * 4u, sh);
+        if (LEAKY) ptx::sts_f(s_par + uint32_t(3 * TILE_CH + te) * 4u, al);
       };
-      float nb = 0.f, nsc = 0.f, nsh = 0.f;
+      float nb = 0.f, nsc = 0.f, nsh = 0.f, nal = 0.f;
       uint32_t nvalid = 0;
       if (item_first < n_items) {
-        fetch_params(cur0, nb, nsc, nsh, nvalid);
-        store_params(0, nb, nsc, nsh);
+        fetch_params(cur0, nb, nsc, nsh, nal, nvalid);
+        store_params(0, nb, nsc, nsh, nal);
       }
       TileCursor nx = cur0;
       for (TileCursor tc = cur0; tc.item < n_items; tc.next(), ++it) {
         const uint32_t acc = it & 1u;
         const int r_cta = tc.row * TILE_ROWS + int(rank) * CTA_ROWS;
         const int ch0 = tc.ch * TILE_CH;
-        const uint32_t s_par = smem_base + OFF_PARAMS + acc * (3 * TILE_CH * 4);
+        const uint32_t s_par = smem_base + OFF_PARAMS + acc * (PAR_ARRAYS * TILE_CH * 4);
         const bool valid = nvalid != 0;
         ptx::named_bar_sync(1, NUM_EPI_THREADS);       // this tile's parameters visible; the other buffer is free
         if (e == 0 && lane == 0) trace_stamp(args, cluster_id, rank, it, 5);
         nx.next();                                     // nx is always one item ahead of tc
         const bool has_next = nx.item < n_items;
-        if (has_next) fetch_params(nx, nb, nsc, nsh, nvalid);
+        if (has_next) fetch_params(nx, nb, nsc, nsh, nal, nvalid);
         ptx::mbar_wait(t_full(acc), (it >> 1) & 1u);
         ptx::tc_fence_after();
         if (e == 0 && lane == 0) trace_stamp(args, cluster_id, rank, it, 4);
@@ -461,7 +476,7 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
             if (lane == 0) ptx::mbar_arrive_cluster(t_empty_leader + 8u * acc);
           }
           uint32_t p[16];
-          epi_store_math(v[chunk & 1], s_par, colh * 128 + chunk * C_CHUNK, valid, p, hmax);
+          epi_store_math<LEAKY>(v[chunk & 1], s_par, colh * 128 + chunk * C_CHUNK, valid, p, hmax);
           const uint32_t buf = sC;                        // one box per warp: the previous chunk's store has had the
           if (lane == 0) ptx::tma_store_wait_read<0>();   // whole tcgen05.ld + math of this chunk to read it
           __syncwarp();
@@ -479,7 +494,7 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
             ptx::tma_store_commit();
           }
         }
-        if (has_next) store_params(acc ^ 1u, nb, nsc, nsh);
+        if (has_next) store_params(acc ^ 1u, nb, nsc, nsh, nal);
         if (e == 0 && lane == 0) trace_stamp(args, cluster_id, rank, it, 6);
         if (lane == 0 && args.trace != nullptr && it < TRACE_TILES)      // slot 7: when the slowest epilogue warp finished
           atomicMax(reinterpret_cast<unsigned long long*>(args.trace) + ((size_t(cluster_id) * 2 + rank) * TRACE_TILES + it) * 8 + 7,
@@ -493,6 +508,7 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
         const int r_tile = tc.row * TILE_ROWS;
         const int ch = tc.ch * TILE_CH + int(rank) * CTA_CH + q * 32 + lane;
         const float b = __ldg(args.bias + ch), sc = __ldg(args.scale + ch), sh = __ldg(args.shift + ch);
+        const float al = LEAKY ? __ldg(args.alpha + ch) : 0.f;
         const int blk0 = (r_tile + colh * 128) / POOL_BLOCK;
         const uint32_t nv4 = *reinterpret_cast<const uint32_t*>(args.blk_valid + blk0);   // 4 blocks, 1 byte each
         ptx::mbar_wait(t_full(acc), (it >> 1) & 1u);
@@ -518,14 +534,14 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
             if (nv >= POOL_BLOCK) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
-                const float y = fmaf(fmaxf(__uint_as_float(v[chunk & 1][i]) + b, 0.f), sc, sh);
+                const float y = act_bn<LEAKY>(__uint_as_float(v[chunk & 1][i]), b, sc, sh, al);
                 s1[i & 3] += y;
                 s2[i & 3] = fmaf(y, y, s2[i & 3]);
               }
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
-                float y = fmaf(fmaxf(__uint_as_float(v[chunk & 1][i]) + b, 0.f), sc, sh);
+                float y = act_bn<LEAKY>(__uint_as_float(v[chunk & 1][i]), b, sc, sh, al);
                 y = (i < nv) ? y : 0.f;                              // rows past the segment end do not count
                 s1[i & 3] += y;
                 s2[i & 3] = fmaf(y, y, s2[i & 3]);

@@ -46,6 +46,7 @@ struct FrameLayer {
   float* bias_dev = nullptr;   // [c_out]
   float* scale_dev = nullptr;  // [c_out]
   float* shift_dev = nullptr;  // [c_out]
+  float* alpha_dev = nullptr;  // [c_out] negative slope (leaky / PReLU topologies), else null
 };
 
 struct Plan {
@@ -172,8 +173,8 @@ int encode_2d(const xv_model* m, CUtensorMap* map, void* base, uint64_t inner, u
 
 void free_layers(xv_model* m) {
   for (auto& L : m->layers) {
-    cudaFree(L.w_dev); cudaFree(L.bias_dev); cudaFree(L.scale_dev); cudaFree(L.shift_dev);
-    L.w_dev = nullptr; L.bias_dev = L.scale_dev = L.shift_dev = nullptr;
+    cudaFree(L.w_dev); cudaFree(L.bias_dev); cudaFree(L.scale_dev); cudaFree(L.shift_dev); cudaFree(L.alpha_dev);
+    L.w_dev = nullptr; L.bias_dev = L.scale_dev = L.shift_dev = L.alpha_dev = nullptr;
   }
   cudaFree(m->w0_dev); cudaFree(m->b0_dev); cudaFree(m->w0_split_dev);
   m->w0_dev = m->b0_dev = nullptr;
@@ -229,6 +230,16 @@ int finalize_params(xv_model* m) {
     XV_CUDA(cudaMemcpy(L.bias_dev, b->data(), L.c_out * 4, cudaMemcpyHostToDevice));
     XV_CUDA(cudaMemcpy(L.scale_dev, scale.data(), L.c_out * 4, cudaMemcpyHostToDevice));
     XV_CUDA(cudaMemcpy(L.shift_dev, shift.data(), L.c_out * 4, cudaMemcpyHostToDevice));
+    if (t.act != XV_ACT_RELU) {
+      std::vector<float> alpha(L.c_out, 0.2f);                       // tf.nn.leaky_relu(h, alpha=0.2)  (models.py:912)
+      if (t.act == XV_ACT_PRELU) {                                   // prelu(h, shared=False)  (tf_block.py:38-47)
+        const auto* al = find_param(m, s + "prelu/prelu:0", {L.c_out});
+        if (!al) return fail(XV_ESTATE, "missing or mis-shaped parameter '" + s + "prelu/prelu:0'");
+        alpha = *al;
+      }
+      XV_CUDA(cudaMalloc(&L.alpha_dev, L.c_out * 4));
+      XV_CUDA(cudaMemcpy(L.alpha_dev, alpha.data(), L.c_out * 4, cudaMemcpyHostToDevice));
+    }
   }
   const int c_last = t.width[t.n_frame_layers - 1];
   const auto* w0 = find_param(m, "embed_layer-0/w:0", {2 * c_last, t.emb_dim});
@@ -443,6 +454,7 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       a.bias = L.bias_dev;
       a.scale = L.scale_dev;
       a.shift = L.shift_dev;
+      a.alpha = L.alpha_dev;
       a.row_valid = row_valid;
       a.blk_valid = blk_valid;
       a.partial = pool_partial;
@@ -473,10 +485,15 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
         }
         a.c_chunks = c_in_gemm / (atoms * tdnn2::BLOCK_K);
         XV_PROF();
-        if (mode == 1 && atoms == 1) XV_CUDA(launch_k(pdl, tdnn2::tdnn_pair_kernel<1, 1>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
-        else if (mode == 1) XV_CUDA(launch_k(pdl, tdnn2::tdnn_pair_kernel<1, 2>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
-        else if (atoms == 1) XV_CUDA(launch_k(pdl, tdnn2::tdnn_pair_kernel<0, 1>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
-        else XV_CUDA(launch_k(pdl, tdnn2::tdnn_pair_kernel<0, 2>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
+        {
+          void (*kern)(CUtensorMap, CUtensorMap, CUtensorMap, tdnn2::PairArgs) = nullptr;
+          const bool leaky = L.alpha_dev != nullptr;
+#define XV_PICK(MO, AT) (leaky ? tdnn2::tdnn_pair_kernel<MO, AT, true> : tdnn2::tdnn_pair_kernel<MO, AT, false>)
+          if (mode == 1) kern = atoms == 1 ? XV_PICK(1, 1) : XV_PICK(1, 2);
+          else kern = atoms == 1 ? XV_PICK(0, 1) : XV_PICK(0, 2);
+#undef XV_PICK
+          XV_CUDA(launch_k(pdl, kern, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
+        }
         XV_PROF();
         XV_CUDA(cudaGetLastError());
         ++launches;
@@ -539,7 +556,7 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       const int64_t tiles = int64_t(a.n_row_tiles) * a.n_ch_tiles * a.k_splits;
       const int grid = 2 * int(std::min<int64_t>(tiles, m->num_clusters));
       XV_PROF();
-      XV_CUDA(launch_k(pdl, tdnn2::tdnn_pair_kernel<2, 2>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
+      XV_CUDA(launch_k(pdl, tdnn2::tdnn_pair_kernel<2, 2, false>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
       XV_PROF();
       XV_CUDA(cudaGetLastError());
       ++launches;
@@ -594,7 +611,7 @@ int xv_create(xv_model** out, int device, const xv_topology* topo) {
   const xv_topology& t = *topo;
   if (t.n_frame_layers < 2 || t.n_frame_layers > XV_MAX_FRAME_LAYERS) return fail(XV_EINVAL, "n_frame_layers out of range");
   if (t.feat_dim <= 0) return fail(XV_EINVAL, "feat_dim must be positive");
-  if (t.act != XV_ACT_RELU) return fail(XV_EINVAL, "only XV_ACT_RELU is implemented");
+  if (t.act != XV_ACT_RELU && t.act != XV_ACT_LRELU && t.act != XV_ACT_PRELU) return fail(XV_EINVAL, "unknown activation");
   if (t.emb_dim <= 0 || t.emb_dim % tdnn2::TILE_CH != 0 || t.emb_dim > 4096)
     return fail(XV_EINVAL, "emb_dim must be a multiple of 256 and <= 4096");
   for (int i = 0; i < t.n_frame_layers; ++i) {
@@ -653,15 +670,15 @@ int xv_create(xv_model** out, int device, const xv_topology* topo) {
     return fail(XV_ECUDA, "cuTensorMapEncodeTiled is not available from the CUDA driver");
   }
   m->encode = reinterpret_cast<EncodeTiledFn>(fn);
-  e = cudaFuncSetAttribute(tdnn2::tdnn_pair_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(tdnn2::tdnn_pair_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(tdnn2::tdnn_pair_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(tdnn2::tdnn_pair_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(tdnn2::tdnn_pair_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
+  e = cudaSuccess;
+  {
+    void (*kernels[])(CUtensorMap, CUtensorMap, CUtensorMap, tdnn2::PairArgs) = {
+        tdnn2::tdnn_pair_kernel<0, 1, false>, tdnn2::tdnn_pair_kernel<0, 2, false>, tdnn2::tdnn_pair_kernel<1, 1, false>,
+        tdnn2::tdnn_pair_kernel<1, 2, false>, tdnn2::tdnn_pair_kernel<0, 1, true>,  tdnn2::tdnn_pair_kernel<0, 2, true>,
+        tdnn2::tdnn_pair_kernel<1, 1, true>,  tdnn2::tdnn_pair_kernel<1, 2, true>,  tdnn2::tdnn_pair_kernel<2, 2, false>};
+    for (auto k : kernels)
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
+  }
   if (e == cudaSuccess) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * (prop.multiProcessorCount / 2));
@@ -674,7 +691,7 @@ int xv_create(xv_model** out, int device, const xv_topology* topo) {
     attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    cudaError_t qe = cudaOccupancyMaxActiveClusters(&n_clusters, tdnn2::tdnn_pair_kernel<0, 2>, &cfg);
+    cudaError_t qe = cudaOccupancyMaxActiveClusters(&n_clusters, tdnn2::tdnn_pair_kernel<0, 2, false>, &cfg);
     if (qe != cudaSuccess || n_clusters <= 0) { (void)cudaGetLastError(); n_clusters = prop.multiProcessorCount / 2; }
     m->num_clusters = std::min(n_clusters, prop.multiProcessorCount / 2);
   }
@@ -743,10 +760,11 @@ int xv_set_param(xv_model* m, const char* tf_var_name, const float* host, const 
     const FrameLayer& L = m->layers[idx];
     known = used = true;
     if (leaf == "w:0") want = {L.taps, L.c_in, L.c_out};
-    else if (leaf == "b:0" || leaf == "gamma:0" || leaf == "beta:0" || leaf == "mean:0" || leaf == "variance:0") want = {L.c_out};
+    else if (leaf == "b:0" || leaf == "gamma:0" || leaf == "beta:0" || leaf == "mean:0" || leaf == "variance:0" ||
+             leaf == "prelu/prelu:0") want = {L.c_out};
     else known = used = false;
   } else if (scope_of("embed_layer-", idx, leaf)) {
-    known = true;
+    known = true;                            // embed_layer-*/prelu/prelu:0 etc.: training-only, ignored
     if (idx == 0 && leaf == "w:0") { used = true; want = {2 * t.width[t.n_frame_layers - 1], t.emb_dim}; }
     else if (idx == 0 && leaf == "b:0") { used = true; want = {t.emb_dim}; }
   } else if (name.compare(0, 7, "output/") == 0 || name.compare(0, 10, "attention/") == 0) {

@@ -50,7 +50,7 @@ def _create_engine(meta, params, device):
     from ._native import XvecEngine
     eng = XvecEngine(meta["kernel_sizes"], meta["dilation_rates"], meta["layer_sizes"],
                      meta["embedding_sizes"][0], meta["input_feature_dim"], device=device,
-                     bn_eps=BN_EPSILON, var_eps=VAR2STD_EPSILON)
+                     bn_eps=BN_EPSILON, var_eps=VAR2STD_EPSILON, activation=meta.get("activation", "relu"))
     eng.set_params(params)
     return eng
 
@@ -93,6 +93,8 @@ class Model(object):
     kernel_sizes = [5, 5, 7, 1, 1]
     dilation_rates = [1, 1, 1, 1, 1]
     embedding_sizes = [512, 512]
+    activation = "relu"            # frame-layer nonlinearity: relu | lrelu (0.2) | prelu (per-channel)
+    init = "trunc_normal"          # model_0 initialisation: trunc_normal (sigma 0.1) | he
 
     def __init__(self):
         self.graph = None
@@ -112,11 +114,12 @@ class Model(object):
         seed = os.environ.get("XVEC_SEED")
         seed = int(seed) if seed is not None else int(np.random.SeedSequence().entropy % (2 ** 31))
         params = make_params(self.kernel_sizes, self.layer_sizes, self.embedding_sizes,
-                             feat_dim=input_feature_dim, num_classes=num_classes, weight_set="A", seed=seed)
+                             feat_dim=input_feature_dim, num_classes=num_classes, weight_set="A", seed=seed,
+                             activation=self.activation, init=self.init)
         meta = dict(format=META_FORMAT, model_class=type(self).__name__, num_classes=int(num_classes),
                     input_feature_dim=int(input_feature_dim), kernel_sizes=list(self.kernel_sizes),
                     dilation_rates=list(self.dilation_rates), layer_sizes=list(self.layer_sizes),
-                    embedding_sizes=list(self.embedding_sizes), activation="relu")
+                    embedding_sizes=list(self.embedding_sizes), activation=self.activation)
         if logger is not None:
             logger.info("Start initializing the graph ...")
         Model.save_model(_Session(params, meta), output_dir, logger)
@@ -160,6 +163,7 @@ class Model(object):
         self.dilation_rates = list(meta["dilation_rates"])
         self.layer_sizes = list(meta["layer_sizes"])
         self.embedding_sizes = list(meta["embedding_sizes"])
+        self.activation = meta.get("activation", "relu")
         self.graph = meta
         if sess is not None:
             sess.params, sess.meta = params, meta
@@ -406,3 +410,31 @@ class ModelWithoutDropoutTdnn(Model):
     kernel_sizes = [5, 3, 3, 1, 1]
     dilation_rates = [1, 2, 3, 1, 1]
     embedding_sizes = [512, 512]
+
+
+# The remaining topologies of the reference differ from ModelWithoutDropout only in the frame-layer
+# nonlinearity, the initialisation and (for training, out of scope here) an L2 term in the loss; their
+# extraction forward is the same fused kernel with another activation.
+
+
+# noinspection PyAttributeOutsideInit
+class ModelWithoutDropoutPRelu(ModelWithoutDropout):
+    """prelu(h, shared=False) after bias_add (reference models.py:643-744, tf_block.py:38-47)."""
+    activation = "prelu"
+
+
+# noinspection PyAttributeOutsideInit
+class ModelL2LossWithoutDropoutPRelu(ModelWithoutDropoutPRelu):
+    """Same forward as ModelWithoutDropoutPRelu; adds an L2 loss term for training (reference models.py:746-864)."""
+
+
+# noinspection PyAttributeOutsideInit
+class ModelL2LossWithoutDropoutLRelu(ModelWithoutDropout):
+    """tf.nn.leaky_relu(h, alpha=0.2) (reference models.py:866-983)."""
+    activation = "lrelu"
+
+
+# noinspection PyAttributeOutsideInit
+class ModelL2LossWithoutDropoutReluHeInit(ModelWithoutDropout):
+    """ReLU with He-normal weights / He-uniform biases at model_0 (reference models.py:1118-1244)."""
+    init = "he"

@@ -45,7 +45,7 @@ def _trunc_normal(rng, shape, sigma):
 
 
 def make_params(kernel_sizes, layer_sizes, embedding_sizes, feat_dim=FEAT_DIM, num_classes=0,
-                weight_set="A", seed=100):
+                weight_set="A", seed=100, activation="relu", init="trunc_normal"):
     """Parameter dict keyed by the reference's TF variable names (models.py:199-210)."""
     p = {}
     prev = feat_dim
@@ -65,19 +65,33 @@ def make_params(kernel_sizes, layer_sizes, embedding_sizes, feat_dim=FEAT_DIM, n
     for i, (k, width) in enumerate(zip(kernel_sizes, layer_sizes)):
         rng = np.random.Generator(np.random.PCG64(seed + i))
         s = "frame_level_info_layer-%d/" % i
-        if weight_set == "A":
+        if weight_set == "A" and init == "he":       # ...ReluHeInit: models.py:1155-1163 (he_normal w, he_uniform b)
+            fan_in = k * prev
+            p[s + "w:0"] = _trunc_normal(rng, (k, prev, width), np.sqrt(2.0 / fan_in))
+            lim = np.sqrt(6.0 / fan_in)
+            p[s + "b:0"] = rng.uniform(-lim, lim, width).astype(np.float32)
+        elif weight_set == "A":
             p[s + "w:0"] = _trunc_normal(rng, (k, prev, width), 0.1)
             p[s + "b:0"] = np.full(width, 0.1, np.float32)
         else:
             p[s + "w:0"] = (rng.standard_normal((k, prev, width)) * np.sqrt(2.0 / (k * prev))).astype(np.float32)
             p[s + "b:0"] = rng.uniform(-0.1, 0.1, width).astype(np.float32)
+        if activation == "prelu":      # tf_block.py:38-47: per-channel slope, constant_initializer(0.1)
+            p[s + "prelu/prelu:0"] = (np.full(width, 0.1, np.float32) if weight_set == "A"
+                                      else rng.uniform(-0.2, 0.5, width).astype(np.float32))
         bn(s, width, rng)
         prev = width
     prev *= 2
     for i, width in enumerate(embedding_sizes):
         rng = np.random.Generator(np.random.PCG64(seed + 50 + i))
         s = "embed_layer-%d/" % i
-        if weight_set == "A":
+        if activation == "prelu":
+            p[s + "prelu/prelu:0"] = np.full(width, 0.1, np.float32)
+        if weight_set == "A" and init == "he":
+            p[s + "w:0"] = _trunc_normal(rng, (prev, width), np.sqrt(2.0 / prev))
+            lim = np.sqrt(6.0 / prev)
+            p[s + "b:0"] = rng.uniform(-lim, lim, width).astype(np.float32)
+        elif weight_set == "A":
             p[s + "w:0"] = _trunc_normal(rng, (prev, width), 0.1)
             p[s + "b:0"] = np.full(width, 0.1, np.float32)
         else:
