@@ -257,3 +257,39 @@ def test_make_embedding_end_to_end_with_chunking_and_skips(tmp_path):
         m = orc.parity_metrics(got[k], want)
         assert m["max_rel"] <= TOL, (k, m)
         assert got[k].dtype == np.float32 and got[k].shape == (512,)
+
+
+def test_config3_ragged_ark_through_make_embedding(tmp_path):
+    # BASELINE.json configs[2] (scaled to 1500 utterances): 200-1000 frame utterances from a binary matrix ark through
+    # the product entry point; no bucketing is needed (packed rows).  Output order, count and sampled parity are checked,
+    # wall-clock throughput of the whole ark -> ark path is printed.
+    import time
+    from xvector_b200 import kaldi_io
+    from xvector_b200.models import Model, ModelWithoutDropout
+
+    os.environ["XVEC_SEED"] = "9"
+    model_dir = str(tmp_path / "model_0")
+    ModelWithoutDropout().build_model(10, 23, model_dir, None)
+    params = Model().get_models_weights(model_dir)
+    lens = synthetic.lengths_uniform(3, 1500)
+    feats = synthetic.mfcc_batch(3, lens)
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    buf = io.BytesIO()
+    for i in range(len(lens)):
+        kaldi_io.write_mat(buf, feats[offs[i]:offs[i + 1]], key="utt%07d" % i)
+    data = buf.getvalue()
+    model = Model()
+    out = io.BytesIO()
+    model.make_embedding(io.BytesIO(data), out, model_dir, 25, 10000, True, None)     # includes library / weight set-up
+    out = io.BytesIO()
+    t0 = time.time()
+    model.make_embedding(io.BytesIO(data), out, model_dir, 25, 10000, True, None)
+    dt = time.time() - t0
+    got = list(kaldi_io.read_vec_flt_ark(io.BytesIO(out.getvalue())))
+    assert [k for k, _ in got] == ["utt%07d" % i for i in range(len(lens))]
+    pick = [0, 1, 749, 1498, 1499, int(np.argmax(lens)), int(np.argmin(lens))]
+    want = np.stack([orc.forward(feats[offs[i]:offs[i + 1]], params) for i in pick])
+    m = orc.parity_metrics(np.stack([got[i][1] for i in pick]), want)
+    print("config3: %d utterances, %d frames, ark->ark %.3f s = %.1f M frames/s, parity %s" %
+          (len(lens), int(lens.sum()), dt, lens.sum() / dt / 1e6, m))
+    assert m["max_rel"] <= TOL and m["l2_rel"] <= TOL, m

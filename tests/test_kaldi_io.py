@@ -145,3 +145,58 @@ def test_open_or_fd_prefix_offset_gzip_and_pipes(tmp_path):
             break
         time.sleep(0.05)
     assert np.array_equal(dict(kaldi_io.read_vec_flt_ark(str(out)))["v"], np.ones(4, np.float32))
+
+
+@pytest.mark.parametrize("fname", ["mat_f32.ark", "mat_f64.ark", "cm.ark"])
+def test_entry_reader_equals_read_mat_ark(fname):
+    # the extractor's zero-copy reader must see exactly what read_mat_ark (reference kaldi_io.py:372-392) sees
+    path = os.path.join(GOLD, fname)
+    want = list(kaldi_io.read_mat_ark(path))
+    got = []
+    for e in kaldi_io.read_mat_ark_entries(path):
+        assert (e.rows, e.cols) == (want[len(got)][1].shape if want[len(got)][1].ndim == 2 else (0, 0)) or e.rows == 0
+        dst = np.full((e.rows, e.cols), np.nan, np.float32)
+        e.read_into(dst)
+        got.append((e.key, dst))
+    assert [k for k, _ in got] == [k for k, _ in want]
+    for (_, g), (_, w) in zip(got, want):
+        assert np.array_equal(g, w.astype(np.float32).reshape(g.shape))
+    # skipping payloads (utterances of other ranks / too short) keeps the stream aligned
+    keys = [e.key for e in kaldi_io.read_mat_ark_entries(path)]
+    assert keys == [k for k, _ in want]
+    mixed = []
+    for i, e in enumerate(kaldi_io.read_mat_ark_entries(path)):
+        mixed.append(e.read() if i % 2 else None)
+    for i, (_, w) in enumerate(want):
+        if i % 2:
+            assert np.array_equal(np.asarray(mixed[i], dtype=np.float64).reshape(w.shape), w.astype(np.float64))
+
+
+def test_entry_reader_on_unbuffered_pipe_and_truncation():
+    m = np.arange(7 * 23, dtype=np.float32).reshape(7, 23)
+    buf = io.BytesIO()
+    kaldi_io.write_mat(buf, m, key="a")
+    kaldi_io.write_mat(buf, m * 2, key="b")
+
+    class Dribble(io.RawIOBase):                 # a stream that returns at most 5 bytes per read, no peek()
+        def __init__(self, data):
+            self.data, self.pos = data, 0
+
+        def readable(self):
+            return True
+
+        def readinto(self, b):
+            n = min(5, len(b), len(self.data) - self.pos)
+            b[:n] = self.data[self.pos:self.pos + n]
+            self.pos += n
+            return n
+
+    got = {}
+    for e in kaldi_io.read_mat_ark_entries(Dribble(buf.getvalue())):
+        dst = np.empty((e.rows, e.cols), np.float32)
+        e.read_into(dst)
+        got[e.key] = dst
+    assert np.array_equal(got["a"], m) and np.array_equal(got["b"], m * 2)
+    with pytest.raises(kaldi_io.BadInputFormat):
+        for e in kaldi_io.read_mat_ark_entries(io.BytesIO(buf.getvalue()[:-10])):
+            e.read_into(np.empty((e.rows, e.cols), np.float32))

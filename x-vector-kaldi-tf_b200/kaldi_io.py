@@ -326,6 +326,85 @@ def read_mat_ark(file_or_fd):
             fd.close()
 
 
+class MatArkEntry(object):
+    """One entry of ``read_mat_ark_entries``: header known, payload not consumed yet.  Exactly one of
+    ``read_into`` / ``read`` / ``skip`` must be called before the generator is advanced."""
+    __slots__ = ("key", "rows", "cols", "_fd", "_kind", "_mat", "_done")
+
+    def __init__(self, key, rows, cols, fd, kind, mat=None):
+        self.key, self.rows, self.cols, self._fd, self._kind, self._mat, self._done = key, rows, cols, fd, kind, mat, False
+
+    def read(self):
+        """The matrix as read_mat would return it."""
+        assert not self._done
+        self._done = True
+        if self._kind == "FM":
+            buf = _read_exact(self._fd, self.rows * self.cols * 4)
+            return np.frombuffer(buf, dtype="<f4").reshape(self.rows, self.cols)
+        if self._kind == "DM":
+            buf = _read_exact(self._fd, self.rows * self.cols * 8)
+            return np.frombuffer(buf, dtype="<f8").reshape(self.rows, self.cols)
+        return self._mat                                    # already decoded (compressed / text)
+
+    def read_into(self, dst):
+        """Payload straight into ``dst`` (C-contiguous float32 [rows, cols], e.g. a slice of a page-locked
+        staging buffer): for binary float32 matrices no intermediate copy is made."""
+        assert dst.shape == (self.rows, self.cols) and dst.dtype == np.float32 and dst.flags.c_contiguous
+        if self._kind == "FM" and self.rows * self.cols > 0:
+            assert not self._done
+            self._done = True
+            view = memoryview(dst).cast("B")
+            got, need = 0, len(view)
+            readinto = getattr(self._fd, "readinto", None)
+            while got < need:
+                if readinto is not None:
+                    n = readinto(view[got:])
+                else:
+                    chunk = self._fd.read(need - got)
+                    n = len(chunk)
+                    view[got:got + n] = chunk
+                if not n:
+                    raise BadInputFormat("truncated matrix for key %r" % self.key)
+                got += n
+        else:
+            dst[...] = self.read()
+
+    def skip(self):
+        if not self._done:
+            self.read()
+
+
+def read_mat_ark_entries(file_or_fd):
+    """Generator of MatArkEntry over a matrix ark: like read_mat_ark (reference kaldi_io.py:372-392), but the
+    shape is known before the payload is read, so the extractor can skip short utterances (models.py:378-387)
+    cheaply and place the rows directly in its staging buffer."""
+    fd = open_or_fd(file_or_fd)
+    try:
+        key = read_key(fd)
+        while key:
+            flag = _read_exact(fd, 2).decode()
+            if flag == "\0B":
+                header = _read_exact(fd, 3).decode()
+                if header in ("FM ", "DM "):
+                    _, rows, _, cols = struct.unpack("<bibi", _read_exact(fd, 10))
+                    entry = MatArkEntry(key, rows, cols, fd, header[:2])
+                elif header.startswith("CM"):
+                    m = _read_compressed_mat(fd, header)
+                    entry = MatArkEntry(key, m.shape[0], m.shape[1], fd, "decoded", m)
+                else:
+                    raise UnknownMatrixHeader("The header contained '%s'" % header)
+            else:
+                assert flag == " ["
+                m = _read_mat_ascii(fd)
+                entry = MatArkEntry(key, m.shape[0], m.shape[1] if m.ndim == 2 else 0, fd, "decoded", m)
+            yield entry
+            entry.skip()
+            key = read_key(fd)
+    finally:
+        if fd is not file_or_fd:
+            fd.close()
+
+
 def read_mat_scp(file_or_fd):
     """Generator of (key, matrix) following an scp file."""
     fd = open_or_fd(file_or_fd)

@@ -285,11 +285,11 @@ class Model(object):
         counters["keys_in_order"] = keys_in_order
         batch = None
         ok_index = 0
-        for key, mat in kaldi_io.read_mat_ark(input_stream):
+        for entry in kaldi_io.read_mat_ark_entries(input_stream):
+            key, num_rows = entry.key, entry.rows
             if logger is not None:
-                logger.debug("Processing features with key '%s' which have shape '%s'" % (key, str(mat.shape)))
+                logger.debug("Processing features with key '%s' which have shape '%s'" % (key, str((entry.rows, entry.cols))))
             counters["total_segments"] += 1
-            num_rows = mat.shape[0]
             if num_rows == 0:
                 if logger is not None:
                     logger.warning("Zero-length utterance: '%s'" % key)
@@ -305,25 +305,26 @@ class Model(object):
             this_index = ok_index
             ok_index += 1
             counters["num_success"] += 1
-            used = sum(n for _, n in plan)
+            used = sum(n for _, n in plan)                   # chunks are contiguous from row 0; only a short tail is dropped
             counters["total_segments_len"] += used
             if world > 1:
                 keys_in_order.append(key)
                 if sharding.block_cyclic_rank(this_index, world) != rank:
-                    continue
-            if mat.shape[1] != staging.feat_dim:
-                raise ValueError("utterance %s has feature dim %d, model expects %d" % (key, mat.shape[1], staging.feat_dim))
-            if batch is not None and batch.n_frames + used > max(batch_frames, used):
+                    continue                                 # another rank's utterance: payload skipped unread
+            if entry.cols != staging.feat_dim:
+                raise ValueError("utterance %s has feature dim %d, model expects %d" % (key, entry.cols, staging.feat_dim))
+            if batch is not None and batch.n_frames + num_rows > max(batch_frames, num_rows):
                 work.put(batch)
                 batch = None
             if batch is None:
-                batch = _Batch(staging.acquire(max(batch_frames, used)))
-            dst = staging.view(batch.slot, batch.n_frames + used)
+                batch = _Batch(staging.acquire(max(batch_frames, num_rows)))
+            # the payload goes straight from the stream into the page-locked buffer (no intermediate copy); rows of a
+            # dropped tail are overwritten by the next utterance
+            entry.read_into(staging.view(batch.slot, batch.n_frames + num_rows)[batch.n_frames:])
             first_seg = len(batch.seg_lens)
-            for start, length in plan:
-                dst[batch.n_frames:batch.n_frames + length] = mat[start:start + length]
-                batch.n_frames += length
+            for _, length in plan:
                 batch.seg_lens.append(length)
+            batch.n_frames += used
             batch.utts.append((this_index, key, first_seg, [n for _, n in plan]))
         if batch is not None and batch.utts:
             work.put(batch)
