@@ -342,7 +342,15 @@ def _average_chunks(seg_emb, utts):
     """Frame-weighted average of the chunk x-vectors of each utterance, in the reference's own
     float32 arithmetic (models.py:398-421): ``avg = sum(offset * xvector) / sum(offset)``."""
     out = np.empty((len(utts), seg_emb.shape[1]), dtype=np.float32)
+    single = [i for i, u in enumerate(utts) if len(u[3]) == 1]
+    if single:                                   # one chunk per utterance (every utterance <= chunk_size): same float32
+        idx = np.asarray(single)                 # arithmetic as the loop below -- (offset * x) / offset -- vectorised
+        first = np.asarray([utts[i][2] for i in single])
+        w = np.asarray([utts[i][3][0] for i in single], dtype=np.float32)[:, None]
+        out[idx] = (w * seg_emb[first]) / w
     for i, (_, _, first, lengths) in enumerate(utts):
+        if len(lengths) == 1:
+            continue
         xvector_avg = 0
         tot_weight = 0.0
         for c, offset in enumerate(lengths):
