@@ -358,6 +358,8 @@ def run_b200(args):
                     peak_source="%s bf16/fp16 burst (MEASURED_PEAKS.json)" % peaks["source"],
                     share_of_step=round(tdnn_ms / float(kms.sum()), 4),
                     step_frac_of_tensor_peak=round(value / world * sum(fl) / 1e12 / peaks["tflops"], 4),
+                    step_frac_of_sustained_peak=round(value / world * sum(fl) / 1e12 / peaks["tflops_sustained"], 4),
+                    peak_sustained=peaks["tflops_sustained"],
                     launches=launches)
 
     out = dict(metric=METRIC, value=round(value, 1), unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),

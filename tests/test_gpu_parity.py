@@ -94,7 +94,7 @@ def test_embedding_parity_ragged_batch(topology, weight_set):
     eng.close()
 
 
-@pytest.mark.parametrize("opts", [dict(resident=1), dict(resident=2), dict(fc=0), dict(pdl=0)])
+@pytest.mark.parametrize("opts", [dict(resident=1), dict(resident=2), dict(fc=0), dict(pdl=0), dict(stack=1)])
 def test_alternative_kernel_schedules_give_the_same_embeddings(opts):
     # weight-stationary schedules of the layer kernel, fp32 SIMT embedding GEMM, plain stream-ordered launches:
     # results must stay within the parity gate and very close to the default path
@@ -109,6 +109,8 @@ def test_alternative_kernel_schedules_give_the_same_embeddings(opts):
     m = orc.parity_metrics(alt, want)
     assert m["max_rel"] <= TOL and m["l2_rel"] <= TOL, m
     assert orc.parity_metrics(alt, base)["max_rel"] <= 2e-4
+    if "stack" in opts or "pdl" in opts:             # same arithmetic, different scheduling: bit-identical
+        assert np.array_equal(alt, base)
     eng.close()
 
 
@@ -190,6 +192,9 @@ def test_extract_host_equals_device_forward():
     host = eng.extract_host(feats, lens)
     assert np.array_equal(dev, host)
     assert eng.last_launch_count == 9          # pack + 5 layers + pool stats + embed GEMM + K-split reduction
+    eng.set_option("stack", 1)
+    assert np.array_equal(eng.extract_host(feats, lens), host)     # whole stack in one launch: bit-identical arithmetic
+    assert eng.last_launch_count == 5
     eng.close()
 
 

@@ -16,6 +16,7 @@
 
 #include "pack_pool.cuh"
 #include "tdnn_pair.cuh"
+#include "tdnn_stack.cuh"
 
 namespace {
 
@@ -54,6 +55,7 @@ struct Plan {
   int32_t n_seg = 0;
   int64_t r_pad = 0;
   int32_t fc_m_tiles = 0, fc_n_tiles = 0, fc_splits = 1, fc_k_per_split = 0, n_counters = 0;
+  int32_t fc_counters = 0;
   int32_t tc_splits = 1;             // K-splits of the tensor-core embedding GEMM
   size_t off_split = 0;
   size_t off_meta = 0, off_counters = 0, off_valid = 0, off_blk_valid = 0, off_x0 = 0, off_ha = 0, off_hb = 0,
@@ -77,6 +79,11 @@ struct xv_model {
   std::vector<FrameLayer> layers;
   __half* w0_split_dev = nullptr;    // [E, 3 * 2C] fp16 K-major [hi | lo | hi]: B operand of the split-precision GEMM
   int opt_fc_max_splits = 36;        // cap on the K-splits of the tensor-core embedding GEMM
+  int opt_stack_debug = 0;
+  int opt_stack = 0;                 // 1: all frame layers in ONE persistent launch (tdnn_stack_kernel).  Bit-identical
+                                     // to one launch per layer but measured 10-18 % SLOWER on B200: the step is bound by
+                                     // the 1 kW power cap, so removing idle gaps buys nothing and the dependency
+                                     // counters cost ~40 us; kept as an option and as a cross-check
   int opt_pdl = 1;                   // programmatic dependent launch between the kernels of a forward
   int opt_fc = 1;                    // 1: embed_layer-0 on tensor cores (split fp16), 0: fp32 SIMT GEMM
   float* w0_dev = nullptr;           // [2C, E]
@@ -129,7 +136,9 @@ Plan make_plan(const xv_model* m, int64_t total_frames, int32_t n_seg) {
   p.fc_n_tiles = m->topo.emb_dim / xvk::FC_BN;
   p.fc_splits = K / 256;                                       // C_last is a multiple of 128
   p.fc_k_per_split = K / p.fc_splits;
-  p.n_counters = p.fc_m_tiles * p.fc_n_tiles;
+  p.fc_counters = p.fc_m_tiles * p.fc_n_tiles;
+  // + per-layer row-tile completion counters of the whole-stack kernel (zeroed by the pack kernel with the rest)
+  p.n_counters = p.fc_counters + m->topo.n_frame_layers * int32_t(p.r_pad / tdnn2::TILE_ROWS);
   {
     // tensor-core embedding GEMM: K' = 3K in 128-wide chunks, cut into as many K-splits as keep all CTA pairs busy
     const int chunks = 3 * K / 128;
@@ -418,7 +427,67 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
   const int nl = m->topo.n_frame_layers;
   const bool want_last = layer_out_dev && layer_out_dev[nl - 1];
   const __half* in = x0;
-  for (int i = 0; i < nl; ++i) {
+  const bool use_stack = m->opt_stack && !layer_out_dev && !m->opt_profile && !m->opt_resident && nl <= tdnn2::MAX_STACK_LAYERS;
+  if (use_stack) {
+    // ---- all frame layers in one persistent launch; layers are chained by per-row-tile completion counters ----
+    tdnn2::StackArgs sa{};
+    sa.n_layers = nl;
+    sa.n_row_tiles = int32_t(r_pad / tdnn2::TILE_ROWS);
+    sa.row_valid = row_valid;
+    sa.blk_valid = blk_valid;
+    sa.partial = pool_partial;
+    sa.overflow_flag = m->overflow_dev;
+    sa.done = counters + p.fc_counters;
+    sa.debug = m->opt_stack_debug;
+    const __half* lin = x0;
+    for (int i = 0; i < nl; ++i) {
+      const FrameLayer& L = m->layers[i];
+      const bool last = i == nl - 1;
+      __half* out = last ? hlast : ((i & 1) ? hb : ha);
+      const int halo = (L.gemm_taps - 1) / 2 * L.dilation;
+      const int c_in_gemm = (i == 0) ? L.k_total : L.c_in_pad;
+      const bool reuse = L.gemm_taps > 1 && halo <= tdnn2::MAX_REUSE_HALO;
+      if (halo > tdnn2::TILE_ROWS) return fail(XV_EINVAL, "temporal context wider than one row tile");
+      tdnn2::StackLayer& S = sa.layer[i];
+      rc = encode_2d(m, &S.tmap_act, const_cast<__half*>(lin), uint64_t(c_in_gemm), uint64_t(r_pad), tdnn2::BLOCK_K,
+                     reuse ? tdnn2::ACT_BOX_ROWS_REUSE : tdnn2::ACT_BOX_ROWS_PLAIN, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc != XV_OK) return rc;
+      rc = encode_2d(m, &S.tmap_wgt, L.w_dev, uint64_t(L.k_total), uint64_t(L.c_out), tdnn2::BLOCK_K, tdnn2::CTA_CH,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc != XV_OK) return rc;
+      rc = encode_2d(m, &S.tmap_out, out, uint64_t(L.c_out), uint64_t(r_pad), tdnn2::C_CHUNK, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc != XV_OK) return rc;
+      S.n_ch_tiles = L.c_out / tdnn2::TILE_CH;
+      S.c_chunks = c_in_gemm / (2 * tdnn2::BLOCK_K);
+      S.taps = L.gemm_taps;
+      S.dilation = L.dilation;
+      S.c_in_pad = c_in_gemm;
+      S.reuse = reuse ? 1 : 0;
+      const int64_t act_atom = reuse ? tdnn2::ACT_ATOM_BYTES : tdnn2::ACT_BOX_ROWS_PLAIN * 128;
+      if (reuse) {
+        S.n_act_stages = 2;
+        S.n_wgt_stages = int(std::min<int64_t>(tdnn2::MAX_STAGES, (tdnn2::RING_BYTES - 2 * 2 * act_atom) / (2 * tdnn2::WGT_ATOM_BYTES)));
+      } else {
+        S.n_act_stages = S.n_wgt_stages =
+            int(std::min<int64_t>(tdnn2::MAX_STAGES, tdnn2::RING_BYTES / (2 * (act_atom + tdnn2::WGT_ATOM_BYTES))));
+      }
+      S.mode = last ? 1 : 0;
+      S.c_out = L.c_out;
+      S.bias = L.bias_dev;
+      S.scale = L.scale_dev;
+      S.shift = L.shift_dev;
+      S.alpha = L.alpha_dev;
+      lin = out;
+    }
+    const int grid = 2 * int(std::min<int64_t>(int64_t(sa.n_row_tiles) * sa.layer[0].n_ch_tiles, m->num_clusters));
+    if (m->layers[0].alpha_dev != nullptr)
+      XV_CUDA(launch_k(pdl, tdnn2::tdnn_stack_kernel<true>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, sa));
+    else
+      XV_CUDA(launch_k(pdl, tdnn2::tdnn_stack_kernel<false>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, sa));
+    XV_CUDA(cudaGetLastError());
+    ++launches;
+  }
+  for (int i = 0; i < nl && !use_stack; ++i) {
     const FrameLayer& L = m->layers[i];
     const bool last = i == nl - 1;
     __half* out = last ? hlast : ((i & 1) ? hb : ha);
@@ -678,6 +747,10 @@ int xv_create(xv_model** out, int device, const xv_topology* topo) {
         tdnn2::tdnn_pair_kernel<1, 1, true>,  tdnn2::tdnn_pair_kernel<1, 2, true>,  tdnn2::tdnn_pair_kernel<2, 2, false>};
     for (auto k : kernels)
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tdnn2::tdnn_stack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tdnn2::tdnn_stack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
   }
   if (e == cudaSuccess) {
     cudaLaunchConfig_t cfg{};
@@ -901,6 +974,8 @@ int xv_set_option(xv_model* m, const char* name, int64_t value) {
   else if (n == "prefetch") m->opt_prefetch = value != 0;
   else if (n == "fc") m->opt_fc = int(value);
   else if (n == "pdl") m->opt_pdl = value != 0;
+  else if (n == "stack") m->opt_stack = value != 0;
+  else if (n == "stack_debug") m->opt_stack_debug = int(value);
   else if (n == "fc_max_splits") m->opt_fc_max_splits = std::max(1, int(value));
   else if (n == "trace_ptr") m->opt_trace = reinterpret_cast<long long*>(static_cast<intptr_t>(value));   // device buffer
   else if (n == "trace_layer") m->opt_trace_layer = int(value);
