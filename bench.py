@@ -103,7 +103,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, cuda_index, period=0.004):
         super().__init__(daemon=True)
         self.period = period
-        self.samples, self.reasons = [], set()
+        self.samples, self.reasons, self.power = [], set(), []
         self.sm_max = None
         self._stop_evt = threading.Event()
         self.ok = False
@@ -131,6 +131,7 @@ class ClockSampler(threading.Thread):
         while not self._stop_evt.is_set():
             try:
                 self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
                 mask = int(get_reasons(self.h))
                 for bit, name in self.BITS.items():
                     if mask & bit:
@@ -145,8 +146,11 @@ class ClockSampler(threading.Thread):
             self.join()
         if not self.ok or not self.samples:
             return dict(sm_mhz=None, sm_max_mhz=self.sm_max, reasons=[], note=getattr(self, "err", "no samples"))
-        return dict(sm_mhz=int(statistics.median(self.samples)), sm_max_mhz=self.sm_max,
-                    reasons=sorted(self.reasons), samples=len(self.samples))
+        out = dict(sm_mhz=int(statistics.median(self.samples)), sm_max_mhz=self.sm_max,
+                   reasons=sorted(self.reasons), samples=len(self.samples))
+        if self.power:
+            out.update(power_w_median=round(statistics.median(self.power), 1), power_w_max=round(max(self.power), 1))
+        return out
 
 
 def clocks_rejected(c):
