@@ -298,3 +298,34 @@ def test_config3_ragged_ark_through_make_embedding(tmp_path):
     print("config3: %d utterances, %d frames, ark->ark %.3f s = %.1f M frames/s, parity %s" %
           (len(lens), int(lens.sum()), dt, lens.sum() / dt / 1e6, m))
     assert m["max_rel"] <= TOL and m["l2_rel"] <= TOL, m
+
+
+def test_extreme_batch_shapes():
+    # edge cases of the packed-row layout and of the embedding GEMM's row tiling:
+    # one minimal segment; thousands of short segments (n_seg >> 256: several GEMM row tiles, fewer K-splits);
+    # one maximal 10000-frame chunk (run_xvector.sh:70) next to a short one
+    eng, params = _engine("ModelWithoutDropoutTdnn", "B")
+    x = synthetic.mfcc(51, 25)
+    got = _run(eng, x, [25])
+    assert orc.parity_metrics(got, orc.forward(x, params, "ModelWithoutDropoutTdnn")[None])["max_rel"] <= TOL
+
+    lens = synthetic.lengths_uniform(52, 3000, 25, 40)
+    feats = synthetic.mfcc_batch(52, lens)
+    got = _run(eng, feats, lens)
+    assert got.shape == (3000, 512) and np.isfinite(got).all()
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    pick = [0, 1, 255, 256, 257, 1499, 2998, 2999]
+    want = np.stack([orc.forward(feats[offs[i]:offs[i + 1]], params, "ModelWithoutDropoutTdnn") for i in pick])
+    m = orc.parity_metrics(got[pick], want)
+    assert m["max_rel"] <= TOL and m["l2_rel"] <= TOL, m
+    alone = _run(eng, feats[offs[257]:offs[258]], lens[257:258])
+    assert np.array_equal(alone[0], got[257])                   # still independent of batch composition
+
+    lens = np.array([10000, 31], np.int32)
+    feats = synthetic.mfcc_batch(53, lens)
+    got = _run(eng, feats, lens)
+    want = np.stack([orc.forward(feats[:10000], params, "ModelWithoutDropoutTdnn"),
+                     orc.forward(feats[10000:], params, "ModelWithoutDropoutTdnn")])
+    m = orc.parity_metrics(got, want)
+    assert m["max_rel"] <= TOL and m["l2_rel"] <= TOL, m
+    eng.close()

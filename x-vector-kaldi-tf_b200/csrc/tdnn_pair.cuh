@@ -68,7 +68,7 @@ constexpr int OFF_PARAMS = OFF_C + NUM_EPI_WARPS * C_BUF_BYTES;         // + 163
 constexpr int PAR_ARRAYS = 4;                      // bias | scale | shift | negative slope
 constexpr int OFF_BARS = OFF_PARAMS + 2 * PAR_ARRAYS * TILE_CH * 4;     // + 8192
 constexpr int NUM_BARS = 4 * MAX_STAGES + 4;
-constexpr int OFF_TMEM_PTR = OFF_BARS + NUM_BARS * 8;
+constexpr int OFF_TMEM_PTR = OFF_BARS + (NUM_BARS + 2) * 8 + 32;        // its own 16-byte slot, away from the barriers
 constexpr int SMEM_BYTES = OFF_TMEM_PTR + 16 + 1024;                    // + slack for 1024-byte alignment
 static_assert(RING_BYTES % 1024 == 0 && OFF_C % 1024 == 0, "swizzled stages must be 1024-byte aligned");
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of dynamic shared memory");
@@ -212,6 +212,7 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
   ptx::tc_fence_before();
   ptx::cluster_sync_all();                    // barrier inits + TMEM allocation visible to both CTAs
   ptx::tc_fence_after();
+  __syncthreads();                            // (the cluster barrier already orders this; racecheck only models bar.sync)
   const uint32_t tmem_base = *tmem_ptr_smem;
   // Programmatic dependent launch: everything above (barriers, TMEM, tensor-map prefetch) overlapped the tail of
   // the previous kernel; its output is read -- and ours written -- only after this point.

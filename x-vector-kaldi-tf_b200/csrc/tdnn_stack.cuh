@@ -77,7 +77,7 @@ tdnn_stack_kernel(const __grid_constant__ StackArgs args) {
   constexpr int STAGE_K = ATOMS * BLOCK_K;
   constexpr int WGT_STAGE_BYTES = ATOMS * WGT_ATOM_BYTES;
   constexpr int BAR_DRAINED = 4 * MAX_STAGES + 4;    // one more barrier than tdnn_pair_kernel (fits: see static_assert)
-  static_assert(OFF_BARS + (NUM_BARS + 1) * 8 <= OFF_TMEM_PTR + 8, "barrier area");
+  static_assert(OFF_BARS + (NUM_BARS + 1) * 8 <= OFF_TMEM_PTR, "barrier area");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t smem_base = ptx::smem_u32(smem);
@@ -90,7 +90,7 @@ tdnn_stack_kernel(const __grid_constant__ StackArgs args) {
   auto t_full = [&](uint32_t s) { return bar0 + 8u * (4 * MAX_STAGES + s); };
   auto t_empty = [&](uint32_t s) { return bar0 + 8u * (4 * MAX_STAGES + 2 + s); };
   const uint32_t drained = bar0 + 8u * BAR_DRAINED;
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM_PTR + 8);
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM_PTR);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -120,6 +120,7 @@ tdnn_stack_kernel(const __grid_constant__ StackArgs args) {
   ptx::tc_fence_before();
   ptx::cluster_sync_all();
   ptx::tc_fence_after();
+  __syncthreads();                            // (the cluster barrier already orders this; racecheck only models bar.sync)
   const uint32_t tmem_base = *tmem_ptr_smem;
   cudaTriggerProgrammaticLaunchCompletion();
   cudaGridDependencySynchronize();

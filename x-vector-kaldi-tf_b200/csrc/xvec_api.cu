@@ -63,6 +63,7 @@ struct Plan {
 };
 
 constexpr int META_SLOTS = 4;
+constexpr int64_t FC_GROUP = 1024;   // segments per launch of the tensor-core embedding GEMM (bounds its K-split partials)
 
 }  // namespace
 
@@ -140,13 +141,13 @@ Plan make_plan(const xv_model* m, int64_t total_frames, int32_t n_seg) {
   // + per-layer row-tile completion counters of the whole-stack kernel (zeroed by the pack kernel with the rest)
   p.n_counters = p.fc_counters + m->topo.n_frame_layers * int32_t(p.r_pad / tdnn2::TILE_ROWS);
   {
-    // tensor-core embedding GEMM: K' = 3K in 128-wide chunks, cut into as many K-splits as keep all CTA pairs busy
+    // tensor-core embedding GEMM: K' = 3K in 128-wide chunks, always cut into the same number of K-splits (the
+    // largest divisor of the chunk count that leaves >= 2 chunks per split) whatever the batch: the summation order
+    // of an embedding must not depend on how many other segments are in the call
     const int chunks = 3 * K / 128;
-    const int64_t tiles = int64_t((n_seg + tdnn2::TILE_ROWS - 1) / tdnn2::TILE_ROWS) * (m->topo.emb_dim / tdnn2::TILE_CH);
-    const int want = int(std::max<int64_t>(1, m->num_clusters / std::max<int64_t>(tiles, 1)));
     int best = 1;
     for (int d = 1; d <= chunks / 2; ++d)
-      if (chunks % d == 0 && d <= want && d <= m->opt_fc_max_splits) best = d;   // largest admissible divisor of the chunk count
+      if (chunks % d == 0 && d <= m->opt_fc_max_splits) best = d;
     p.tc_splits = best;
   }
   size_t off = 0;
@@ -162,7 +163,8 @@ Plan make_plan(const xv_model* m, int64_t total_frames, int32_t n_seg) {
   p.off_pool_partial = take(size_t(p.r_pad / tdnn2::POOL_BLOCK) * 2 * c_last * 4);
   p.off_stats = take(size_t(n_seg) * K * 4);
   p.off_split = take(size_t(round_up(n_seg, tdnn2::CTA_ROWS)) * 3 * K * 2);   // rows padded to the TMA box (never read back)
-  p.off_partial = take(size_t(std::max(p.fc_splits, p.tc_splits)) * n_seg * m->topo.emb_dim * 4);
+  p.off_partial = take(std::max(size_t(p.fc_splits) * n_seg, size_t(p.tc_splits) * std::min<int64_t>(n_seg, FC_GROUP)) *
+                       m->topo.emb_dim * 4);
   p.bytes = off;
   return p;
 }
@@ -599,49 +601,53 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       ++launches;
     }
     if (fc_tc) {
-      // embed_layer-0 (models.py:495) on the tensor cores: [n_seg, 3K] x [E, 3K]^T, split over K across the CTA pairs
-      CUtensorMap ta, tw, tc;
-      rc = encode_2d(m, &ta, split, uint64_t(3 * K), uint64_t(round_up(n_seg, tdnn2::CTA_ROWS)), tdnn2::BLOCK_K, tdnn2::ACT_BOX_ROWS_PLAIN,
-                     CU_TENSOR_MAP_SWIZZLE_128B);
-      if (rc != XV_OK) return rc;
+      // embed_layer-0 (models.py:495) on the tensor cores: [n_seg, 3K] x [E, 3K]^T, split over K across the CTA pairs;
+      // segments are taken FC_GROUP at a time so that the K-split partials stay small (one group for usual batches)
+      CUtensorMap tw;
       rc = encode_2d(m, &tw, m->w0_split_dev, uint64_t(3 * K), uint64_t(E), tdnn2::BLOCK_K, tdnn2::CTA_CH, CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc != XV_OK) return rc;
-      tc = tw;                                                        // unused in mode 2
-      tdnn2::PairArgs a{};
-      a.n_row_tiles = (n_seg + tdnn2::TILE_ROWS - 1) / tdnn2::TILE_ROWS;
-      a.n_ch_tiles = E / tdnn2::TILE_CH;
-      a.k_splits = p.tc_splits;
-      a.c_chunks = (3 * K / 128) / p.tc_splits;
-      a.taps = 1;
-      a.dilation = 1;
-      a.c_in_pad = 3 * K;
-      a.reuse = 0;
-      a.n_act_stages = a.n_wgt_stages = 3;
-      a.mode = 2;
-      a.c_out = E;
-      a.n_rows = n_seg;
-      a.out_f32 = fc_partial;
-      a.overflow_flag = m->overflow_dev;
-      const int64_t tiles = int64_t(a.n_row_tiles) * a.n_ch_tiles * a.k_splits;
-      const int grid = 2 * int(std::min<int64_t>(tiles, m->num_clusters));
-      XV_PROF();
-      XV_CUDA(launch_k(pdl, tdnn2::tdnn_pair_kernel<2, 2, false>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
-      XV_PROF();
-      XV_CUDA(cudaGetLastError());
-      ++launches;
-      xvk::FcReduceArgs r{};
-      r.partial = fc_partial;
-      r.b0 = m->b0_dev;
-      r.emb = emb_dev;
-      r.n_seg = n_seg;
-      r.E = E;
-      r.splits = p.tc_splits;
-      const int64_t n4 = int64_t(n_seg) * E / 4;
-      XV_PROF();
-      XV_CUDA(launch_k(pdl, xvk::embed_reduce_kernel, dim3(unsigned((n4 + 63) / 64)), dim3(64), 0, stream, r));
-      XV_PROF();
-      XV_CUDA(cudaGetLastError());
-      ++launches;
+      for (int64_t g0 = 0; g0 < n_seg; g0 += FC_GROUP) {
+        const int32_t gn = int32_t(std::min<int64_t>(FC_GROUP, n_seg - g0));
+        CUtensorMap ta;
+        rc = encode_2d(m, &ta, split + g0 * 3 * K, uint64_t(3 * K), uint64_t(round_up(gn, tdnn2::CTA_ROWS)), tdnn2::BLOCK_K,
+                       tdnn2::ACT_BOX_ROWS_PLAIN, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc != XV_OK) return rc;
+        tdnn2::PairArgs a{};
+        a.n_row_tiles = (gn + tdnn2::TILE_ROWS - 1) / tdnn2::TILE_ROWS;
+        a.n_ch_tiles = E / tdnn2::TILE_CH;
+        a.k_splits = p.tc_splits;
+        a.c_chunks = (3 * K / 128) / p.tc_splits;
+        a.taps = 1;
+        a.dilation = 1;
+        a.c_in_pad = 3 * K;
+        a.reuse = 0;
+        a.n_act_stages = a.n_wgt_stages = 3;
+        a.mode = 2;
+        a.c_out = E;
+        a.n_rows = gn;
+        a.out_f32 = fc_partial;
+        a.overflow_flag = m->overflow_dev;
+        const int64_t tiles = int64_t(a.n_row_tiles) * a.n_ch_tiles * a.k_splits;
+        const int grid = 2 * int(std::min<int64_t>(tiles, m->num_clusters));
+        XV_PROF();
+        XV_CUDA(launch_k(pdl, tdnn2::tdnn_pair_kernel<2, 2, false>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tw, a));
+        XV_PROF();
+        XV_CUDA(cudaGetLastError());
+        ++launches;
+        xvk::FcReduceArgs r{};
+        r.partial = fc_partial;
+        r.b0 = m->b0_dev;
+        r.emb = emb_dev + g0 * E;
+        r.n_seg = gn;
+        r.E = E;
+        r.splits = p.tc_splits;
+        const int64_t n4 = int64_t(gn) * E / 4;
+        XV_PROF();
+        XV_CUDA(launch_k(pdl, xvk::embed_reduce_kernel, dim3(unsigned((n4 + 63) / 64)), dim3(64), 0, stream, r));
+        XV_PROF();
+        XV_CUDA(cudaGetLastError());
+        ++launches;
+      }
     } else {
       xvk::FcArgs a{};
       a.stats = stats;
