@@ -1,0 +1,89 @@
+/* xvec_train.h -- C ABI of the training step in libxvec_b200.so (B200, sm_100a).
+ *
+ * Drop-in boundary for the ONE operator call the reference makes into its runtime per minibatch:
+ *
+ *     _, loss, accuracy = sess.run([self.optimizer, self.loss, self.accuracy],
+ *                                  feed_dict={input_x: batch[B,T,D], input_y: one_hot[B,C],
+ *                                             dropout_keep_prob, learning_rate, phase: True})
+ *                                                       -- reference local/tf/models.py:258-263
+ *
+ * on the graph of ModelWithoutDropout / ModelWithoutDropoutTdnn.build_model (models.py:441-534 / :543-639):
+ * frame layers conv -> +b -> relu -> BatchNorm(training branch, tf_block.py:18-23), statistics pooling,
+ * two segment layers, softmax cross-entropy over num_classes (models.py:512-514), tf.train.AdamOptimizer
+ * (models.py:516-519).  The call is split in two so that a data-parallel caller can all-reduce the flat
+ * gradient between the halves (torch.distributed / NCCL on the Python side):
+ *
+ *     xv_train_forward_backward  ->  [all-reduce grad]  ->  xv_train_apply
+ *
+ * State lives in flat fp32 device vectors addressed by TF variable name through xv_train_span:
+ *     which = XV_TRAIN_PARAMS   trainable variables, in graph order (w, b, gamma, beta per layer; output/w, output/b)
+ *             XV_TRAIN_ADAM_M / XV_TRAIN_ADAM_V   the "<var>/Adam" and "<var>/Adam_1" slots, same offsets
+ *             XV_TRAIN_MOVING   the non-trainable "<scope>/mean:0", "<scope>/variance:0" moving statistics
+ *             XV_TRAIN_GRAD     the gradient of the last xv_train_forward_backward into the trainer's own buffer
+ * Conventions as in xvec.h: plain C, 0 / negative XV_E*, xv_last_error(); ReLU topologies only.
+ */
+#ifndef XVEC_B200_TRAIN_H_
+#define XVEC_B200_TRAIN_H_
+
+#include "xvec.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct xv_trainer xv_trainer;
+
+enum { XV_TRAIN_PARAMS = 0, XV_TRAIN_ADAM_M = 1, XV_TRAIN_ADAM_V = 2, XV_TRAIN_MOVING = 3, XV_TRAIN_GRAD = 4 };
+
+/* Replaces Model.build_model's graph construction for training (models.py:441-534): the frame-level topology is
+ * the xv_model's; emb1_dim = embedding_sizes[1] (512), num_classes = width of "output/w".  The xv_model supplies
+ * the device, the kernels' launch state and the overflow flag; it must outlive the trainer. */
+int xv_train_create(xv_trainer** out, xv_model* model, int32_t num_classes, int32_t emb1_dim);
+void xv_train_destroy(xv_trainer* t);
+
+/* Number of floats in the flat vector `which`. */
+int64_t xv_train_size(const xv_trainer* t, int32_t which);
+/* Where variable `tf_var_name` (e.g. "frame_level_info_layer-1/w:0", "embed_layer-0/mean:0") lives:
+ * *which = XV_TRAIN_PARAMS or XV_TRAIN_MOVING, [*offset, *offset + *count).  Replaces the by-name binding of
+ * Saver.restore / graph.get_tensor_by_name (models.py:143-162). */
+int xv_train_span(const xv_trainer* t, const char* tf_var_name, int32_t* which, int64_t* offset, int64_t* count);
+/* Host <-> device copies of a range of a flat vector (synchronous).  After an upload into XV_TRAIN_PARAMS the
+ * fp16 operand copies are rebuilt on the next step. */
+int xv_train_upload(xv_trainer* t, int32_t which, const float* host, int64_t offset, int64_t count);
+int xv_train_download(xv_trainer* t, int32_t which, float* host, int64_t offset, int64_t count);
+/* Adam's step counter t (TF keeps beta1_power = b1^t, beta2_power = b2^t). */
+int xv_train_set_step(xv_trainer* t, int64_t step);
+int64_t xv_train_get_step(const xv_trainer* t);
+
+/* Forward + backward of one minibatch (the loss/accuracy/gradient half of models.py:263).
+ *   feats_dev   [n_seg * seg_len, feat_dim] fp32 on the device (input_x, every segment seg_len rows)
+ *   labels_dev  [n_seg] int32 class ids on the device (the argmax of input_y's one-hot rows, models.py:164-169)
+ *   grad_dev    [xv_train_size(PARAMS)] fp32 out, or NULL to use the trainer's own buffer (XV_TRAIN_GRAD)
+ *   loss_acc_dev [2] fp32 out: mean cross-entropy, accuracy
+ * Also applies the moving-statistics update of every BatchNorm (tf_block.py:20-21).  Enqueue only. */
+int xv_train_forward_backward(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, int32_t n_seg,
+                              int32_t seg_len, float* grad_dev, float* loss_acc_dev, void* stream);
+/* Adam update (the optimizer half of models.py:263) with gradient grad_dev * grad_scale (NULL = own buffer;
+ * grad_scale = 1/world_size after a sum all-reduce), then refreshes the fp16 operand copies.  Enqueue only. */
+int xv_train_apply(xv_trainer* t, const float* grad_dev, float learning_rate, float grad_scale, void* stream);
+
+/* Copies the current variables and moving statistics into the xv_model (so that xv_forward / xv_extract_host
+ * evaluate the trained network: what Model.save_model + load_model do between train and extract). */
+int xv_train_sync_model(xv_trainer* t);
+
+/* Parity hook: fp32 copy of an intermediate of the last forward_backward.  Packed fp16 tensors come back as
+ * [n_seg * seg_len, C]:  "r<i>" relu output and "y<i>" BatchNorm output of frame layer i, "dz<i>" / "dy<i>"
+ * loss-scaled gradients w.r.t. the pre-activation / the BatchNorm output; fp32 arrays as stored: "h0" (pooled
+ * statistics), "z5", "y5", "z6", "y6", "logits", "dlogits", "dh0".  Returns the number of floats (or < 0). */
+int64_t xv_train_debug_tensor(xv_trainer* t, const char* name, float* host_out, int64_t capacity);
+/* Options: "loss_scale" (0 = automatic: 8 * frames rounded to a power of two), "wgrad_lbo", "wgrad_sbo". */
+int xv_train_set_option(xv_trainer* t, const char* name, double value);
+int32_t xv_train_last_launch_count(const xv_trainer* t);
+/* With the xv_model option "profile" on, every launch of a step is bracketed by CUDA events: read the times with
+ * xv_last_kernel_ms(model, ...) and the kernel names, ';'-separated and in the same order, here.  Returns the count. */
+int64_t xv_train_last_kernel_names(const xv_trainer* t, char* buf, int64_t capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XVEC_B200_TRAIN_H_ */

@@ -46,6 +46,7 @@ def build_library(verbose=False):
     without a GPU).  Skips the compile when the library is newer than every source."""
     sources = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
     sources.append(os.path.join(REPO_ROOT, "include", "xvec.h"))
+    sources.append(os.path.join(REPO_ROOT, "include", "xvec_train.h"))
     if os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in sources):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
@@ -99,13 +100,50 @@ def load_library():
     lib.xv_last_error.restype = ctypes.c_char_p
     lib.xv_version.argtypes = []
     lib.xv_version.restype = ctypes.c_char_p
+    # training step (include/xvec_train.h)
+    F32, F64 = ctypes.c_float, ctypes.c_double
+    lib.xv_train_create.argtypes = [ctypes.POINTER(P), P, I32, I32]
+    lib.xv_train_create.restype = ctypes.c_int
+    lib.xv_train_destroy.argtypes = [P]
+    lib.xv_train_destroy.restype = None
+    lib.xv_train_size.argtypes = [P, I32]
+    lib.xv_train_size.restype = I64
+    lib.xv_train_span.argtypes = [P, ctypes.c_char_p, ctypes.POINTER(I32), ctypes.POINTER(I64), ctypes.POINTER(I64)]
+    lib.xv_train_span.restype = ctypes.c_int
+    lib.xv_train_upload.argtypes = [P, I32, P, I64, I64]
+    lib.xv_train_upload.restype = ctypes.c_int
+    lib.xv_train_download.argtypes = [P, I32, P, I64, I64]
+    lib.xv_train_download.restype = ctypes.c_int
+    lib.xv_train_set_step.argtypes = [P, I64]
+    lib.xv_train_set_step.restype = ctypes.c_int
+    lib.xv_train_get_step.argtypes = [P]
+    lib.xv_train_get_step.restype = I64
+    lib.xv_train_forward_backward.argtypes = [P, P, P, I32, I32, P, P, P]
+    lib.xv_train_forward_backward.restype = ctypes.c_int
+    lib.xv_train_apply.argtypes = [P, P, F32, F32, P]
+    lib.xv_train_apply.restype = ctypes.c_int
+    lib.xv_train_sync_model.argtypes = [P]
+    lib.xv_train_sync_model.restype = ctypes.c_int
+    lib.xv_train_debug_tensor.argtypes = [P, ctypes.c_char_p, P, I64]
+    lib.xv_train_debug_tensor.restype = I64
+    lib.xv_train_set_option.argtypes = [P, ctypes.c_char_p, F64]
+    lib.xv_train_set_option.restype = ctypes.c_int
+    lib.xv_train_last_launch_count.argtypes = [P]
+    lib.xv_train_last_launch_count.restype = I32
+    lib.xv_train_last_kernel_names.argtypes = [P, ctypes.c_char_p, I64]
+    lib.xv_train_last_kernel_names.restype = I64
     _lib = lib
     return lib
 
 
 EXPORTED_SYMBOLS = ["xv_create", "xv_destroy", "xv_set_param", "xv_workspace_bytes", "xv_forward",
                     "xv_forward_layers", "xv_extract_host", "xv_submit_host", "xv_collect", "xv_check_overflow", "xv_last_launch_count",
-                    "xv_last_kernel_ms", "xv_set_option", "xv_last_error", "xv_version"]
+                    "xv_last_kernel_ms", "xv_set_option", "xv_last_error", "xv_version",
+                    # include/xvec_train.h
+                    "xv_train_create", "xv_train_destroy", "xv_train_size", "xv_train_span", "xv_train_upload",
+                    "xv_train_download", "xv_train_set_step", "xv_train_get_step", "xv_train_forward_backward",
+                    "xv_train_apply", "xv_train_sync_model", "xv_train_debug_tensor", "xv_train_set_option",
+                    "xv_train_last_launch_count", "xv_train_last_kernel_names"]
 
 
 def _check(lib, rc):
@@ -242,12 +280,128 @@ class XvecEngine:
     def last_kernel_ms(self):
         """Device duration (ms) of every launch of the last forward (option ``profile`` must be 1);
         order: pack, frame layers 0..n-1, pool+embed."""
-        buf = (ctypes.c_float * 32)()
-        n = int(self.lib.xv_last_kernel_ms(self.handle, buf, 32))
+        buf = (ctypes.c_float * 256)()
+        n = int(self.lib.xv_last_kernel_ms(self.handle, buf, 256))
         if n < 0:
             _check(self.lib, n)
-        return [float(buf[i]) for i in range(min(n, 32))]
+        return [float(buf[i]) for i in range(min(n, 256))]
 
     @property
     def last_launch_count(self):
         return int(self.lib.xv_last_launch_count(self.handle))
+
+
+TRAIN_PARAMS, TRAIN_ADAM_M, TRAIN_ADAM_V, TRAIN_MOVING, TRAIN_GRAD = 0, 1, 2, 3, 4
+
+
+class XvecTrainer:
+    """One xv_trainer bound to an XvecEngine: the replacement for the reference's TF session on the training path
+    (``sess.run([optimizer, loss, accuracy])``, models.py:263).  State is addressed by TF variable name."""
+
+    def __init__(self, engine, num_classes, emb1_dim=512):
+        self.engine = engine
+        self.lib = engine.lib
+        self.num_classes = int(num_classes)
+        self.handle = ctypes.c_void_p()
+        _check(self.lib, self.lib.xv_train_create(ctypes.byref(self.handle), engine.handle, int(num_classes), int(emb1_dim)))
+        self.n_params = int(self.lib.xv_train_size(self.handle, TRAIN_PARAMS))
+        self.n_moving = int(self.lib.xv_train_size(self.handle, TRAIN_MOVING))
+        self._loss_acc = None
+        self._geom = None
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self.lib.xv_train_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def span(self, name):
+        which, off, cnt = ctypes.c_int32(), ctypes.c_int64(), ctypes.c_int64()
+        _check(self.lib, self.lib.xv_train_span(self.handle, name.encode(), ctypes.byref(which), ctypes.byref(off), ctypes.byref(cnt)))
+        return int(which.value), int(off.value), int(cnt.value)
+
+    def upload(self, which, arr, offset=0):
+        a = np.ascontiguousarray(np.asarray(arr).reshape(-1), dtype=np.float32)
+        _check(self.lib, self.lib.xv_train_upload(self.handle, int(which), a.ctypes.data_as(ctypes.c_void_p), int(offset), a.size))
+
+    def download(self, which, offset=0, count=None):
+        if count is None:
+            count = int(self.lib.xv_train_size(self.handle, int(which))) - offset
+        out = np.empty(int(count), dtype=np.float32)
+        _check(self.lib, self.lib.xv_train_download(self.handle, int(which), out.ctypes.data_as(ctypes.c_void_p), int(offset), int(count)))
+        return out
+
+    def set_params(self, params, slots=None):
+        """params: dict TF-variable-name -> array (trainable variables and moving statistics)."""
+        for name, arr in params.items():
+            which, off, cnt = self.span(name)
+            a = np.asarray(arr)
+            if a.size != cnt:
+                raise XvecError(XV_EINVAL, "shape mismatch for %s: %d values, expected %d" % (name, a.size, cnt))
+            self.upload(which, a, off)
+
+    def get_param(self, name, which=None, shape=None):
+        w, off, cnt = self.span(name)
+        out = self.download(w if which is None else which, off, cnt)
+        return out.reshape(shape) if shape is not None else out
+
+    def set_option(self, name, value):
+        _check(self.lib, self.lib.xv_train_set_option(self.handle, name.encode(), float(value)))
+
+    @property
+    def step(self):
+        return int(self.lib.xv_train_get_step(self.handle))
+
+    @step.setter
+    def step(self, value):
+        _check(self.lib, self.lib.xv_train_set_step(self.handle, int(value)))
+
+    def forward_backward(self, feats_dev, labels_dev, n_seg, seg_len, grad_dev=None, stream=None):
+        """feats_dev: torch float32 CUDA [n_seg*seg_len, feat_dim]; labels_dev: torch int32 CUDA [n_seg].
+        Enqueues on ``stream``; returns the device tensor [loss, accuracy] (read it after a synchronize)."""
+        import torch
+        assert feats_dev.is_cuda and feats_dev.dtype == torch.float32 and feats_dev.is_contiguous()
+        assert feats_dev.numel() == n_seg * seg_len * self.engine.feat_dim
+        assert labels_dev.is_cuda and labels_dev.dtype == torch.int32 and labels_dev.numel() == n_seg
+        if self._loss_acc is None:
+            self._loss_acc = torch.zeros(2, dtype=torch.float32, device=feats_dev.device)
+        s = torch.cuda.current_stream(feats_dev.device) if stream is None else stream
+        gptr = None if grad_dev is None else grad_dev.data_ptr()
+        _check(self.lib, self.lib.xv_train_forward_backward(self.handle, feats_dev.data_ptr(), labels_dev.data_ptr(), int(n_seg),
+                                                            int(seg_len), gptr, self._loss_acc.data_ptr(), s.cuda_stream))
+        self._geom = (int(n_seg), int(seg_len))
+        return self._loss_acc
+
+    def apply(self, learning_rate, grad_dev=None, grad_scale=1.0, stream=None):
+        import torch
+        s = torch.cuda.current_stream(self.engine.device) if stream is None else stream
+        gptr = None if grad_dev is None else grad_dev.data_ptr()
+        _check(self.lib, self.lib.xv_train_apply(self.handle, gptr, float(learning_rate), float(grad_scale), s.cuda_stream))
+
+    def sync_model(self):
+        _check(self.lib, self.lib.xv_train_sync_model(self.handle))
+
+    def debug_tensor(self, name, cols=None):
+        n_seg, seg_len = self._geom
+        cap = max(n_seg * seg_len * 1536, n_seg * max(self.num_classes, 3072)) + 16
+        out = np.empty(cap, dtype=np.float32)
+        n = int(self.lib.xv_train_debug_tensor(self.handle, name.encode(), out.ctypes.data_as(ctypes.c_void_p), cap))
+        if n < 0:
+            _check(self.lib, n)
+        return out[:n].copy()
+
+    def last_kernel_names(self):
+        buf = ctypes.create_string_buffer(16384)
+        n = int(self.lib.xv_train_last_kernel_names(self.handle, buf, 16384))
+        if n < 0:
+            _check(self.lib, n)
+        return [x for x in buf.value.decode().split(";") if x]
+
+    @property
+    def last_launch_count(self):
+        return int(self.lib.xv_train_last_launch_count(self.handle))

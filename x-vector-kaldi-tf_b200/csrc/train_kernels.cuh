@@ -1,0 +1,589 @@
+// train_kernels.cuh -- the HBM-bound / small kernels of one training minibatch (sm_100a), i.e. everything of
+// ``sess.run([optimizer, loss, accuracy])`` (local/tf/models.py:263) that is not a frame-level contraction:
+//
+//   frame level  blk_col_sums_kernel      per aligned 32-row block: column sums (BatchNorm batch moments,
+//                                         tf_block.py:19; per-segment pooling sums, models.py:485; BN backward sums)
+//                bn_fwd_finalize_kernel   batch mean / population variance -> scale, shift; moving statistics
+//                                         pop*decay + batch*(1-decay) (tf_block.py:20-21)
+//                bn_apply_kernel          y = r*scale + shift on segment rows, exact zeros on gap rows
+//                bn_bwd_finalize_kernel   d gamma, d beta and the three per-channel coefficients of dL/dz
+//                bn_relu_bwd_kernel       dz = (r > 0) * (cA*dy + cB*r + cC)  (BN backward + ReLU backward fused)
+//                pool_*                   statistics pooling forward / backward fused with the LAST layer's BN:
+//                                         dz4 = (r4 > 0) * (A[seg,c] + G[seg,c] * r4) needs no dy tensor at all
+//   segment level sgemm64_kernel (+ splitk_reduce_kernel), seg_relu_bn_{fwd,bwd}_kernel, softmax_ce_kernel
+//   optimizer    adam_kernel (tf.train.AdamOptimizer, models.py:518), repack_* (fp32 master -> fp16 operand layouts)
+//
+// All reductions run in a fixed order (bit-reproducible).  Gradients of the frame level are carried in fp16 scaled
+// by the loss scale S; every kernel that emits a parameter gradient multiplies by 1/S.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace trk {
+
+constexpr int BLK_ROWS = 32;
+constexpr int COLS_PER_CTA = 256;
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 v = __half22float2(h[i]);
+    f[2 * i] = v.x; f[2 * i + 1] = v.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Column sums of one aligned 32-row block x 256 channels per CTA.
+//   OP 0: partial[blk][0][c] = sum x,        partial[blk][1][c] = sum x*x
+//   OP 1: partial[blk][0][c] = sum x (= dy), partial[blk][1][c] = sum x*y (= dy * r)
+// Gap rows hold exact zeros in every tensor this is applied to, so no row mask is needed.
+template <int OP>
+__global__ void __launch_bounds__(256)
+blk_col_sums_kernel(const __half* __restrict__ x, const __half* __restrict__ y, int32_t C, float* __restrict__ partial) {
+  __shared__ float red[8][2][COLS_PER_CTA];
+  const int blk = blockIdx.x, c0 = blockIdx.y * COLS_PER_CTA;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const int64_t off = (int64_t(blk) * BLK_ROWS + w * 4 + rr) * C + c0 + lane * 8;
+    float a[8], b[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + off)), a);
+    if (OP == 1) unpack8(__ldg(reinterpret_cast<const uint4*>(y + off)), b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s1[i] += a[i];
+      s2[i] = fmaf(a[i], OP == 1 ? b[i] : a[i], s2[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { red[w][0][lane * 8 + i] = s1[i]; red[w][1][lane * 8 + i] = s2[i]; }
+  __syncthreads();
+  const int t = threadIdx.x;
+  float a = 0.f, b = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { a += red[k][0][t]; b += red[k][1][t]; }
+  partial[(int64_t(blk) * 2 + 0) * C + c0 + t] = a;
+  partial[(int64_t(blk) * 2 + 1) * C + c0 + t] = b;
+}
+
+// Sum partial[blk][j][c] over blk for 32 channels per CTA (block 32 x 8), fp64, fixed order.
+template <int NSUM>
+__device__ __forceinline__ void reduce_blocks(const float* __restrict__ partial, int32_t n_blk, int32_t C, int c, double (&out)[NSUM],
+                                              double (*sred)[NSUM][32]) {
+  double s[NSUM];
+#pragma unroll
+  for (int j = 0; j < NSUM; ++j) s[j] = 0.0;
+  for (int b = threadIdx.y; b < n_blk; b += 8) {
+#pragma unroll
+    for (int j = 0; j < NSUM; ++j) s[j] += double(partial[(int64_t(b) * NSUM + j) * C + c]);
+  }
+#pragma unroll
+  for (int j = 0; j < NSUM; ++j) sred[threadIdx.y][j][threadIdx.x] = s[j];
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < NSUM; ++j) {
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += sred[k][j][threadIdx.x];
+    out[j] = t;
+  }
+}
+
+struct BnFwdArgs {
+  const float* partial;      // [n_blk][2][C]
+  int32_t n_blk, C;
+  float n_rows;              // frames in the minibatch (B*T)
+  float eps, decay;
+  const float* gamma; const float* beta;
+  float* moving_mean; float* moving_var;     // updated in place (tf_block.py:20-21)
+  float* mean; float* inv;                   // batch mean, rsqrt(var + eps)
+  float* scale; float* shift;                // gamma*inv, beta - mean*gamma*inv   (tf.nn.batch_normalization)
+};
+__global__ void __launch_bounds__(256) bn_fwd_finalize_kernel(const BnFwdArgs a) {
+  __shared__ double sred[8][2][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s[2];
+  reduce_blocks<2>(a.partial, a.n_blk, a.C, c, s, sred);
+  if (threadIdx.y != 0) return;
+  const double mean = s[0] / double(a.n_rows);
+  double var = s[1] / double(a.n_rows) - mean * mean;       // population variance (tf.nn.moments)
+  if (var < 0.0) var = 0.0;
+  const double inv = 1.0 / sqrt(var + double(a.eps));
+  const double sc = double(a.gamma[c]) * inv;
+  a.mean[c] = float(mean);
+  a.inv[c] = float(inv);
+  a.scale[c] = float(sc);
+  a.shift[c] = float(double(a.beta[c]) - mean * sc);
+  a.moving_mean[c] = float(double(a.moving_mean[c]) * double(a.decay) + mean * (1.0 - double(a.decay)));
+  a.moving_var[c] = float(double(a.moving_var[c]) * double(a.decay) + var * (1.0 - double(a.decay)));
+}
+
+// y = valid ? r * scale + shift : 0      (8 channels per thread)
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const __half* __restrict__ r, const uint8_t* __restrict__ row_valid, const float* __restrict__ scale,
+                const float* __restrict__ shift, int64_t n8, int32_t c8, __half* __restrict__ y, uint32_t* overflow_flag) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const int64_t row = i / c8;
+  const int c = int(i - row * c8) * 8;
+  uint4 out = make_uint4(0u, 0u, 0u, 0u);
+  if (row_valid[row]) {
+    float v[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(r) + i), v);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c)), s1 = __ldg(reinterpret_cast<const float4*>(scale + c + 4));
+    const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + c)), h1 = __ldg(reinterpret_cast<const float4*>(shift + c + 4));
+    v[0] = fmaf(v[0], s0.x, h0.x); v[1] = fmaf(v[1], s0.y, h0.y); v[2] = fmaf(v[2], s0.z, h0.z); v[3] = fmaf(v[3], s0.w, h0.w);
+    v[4] = fmaf(v[4], s1.x, h1.x); v[5] = fmaf(v[5], s1.y, h1.y); v[6] = fmaf(v[6], s1.z, h1.z); v[7] = fmaf(v[7], s1.w, h1.w);
+    float mx = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mx = fmaxf(mx, fabsf(v[k]));
+    if (!(mx <= 65504.f)) atomicOr(overflow_flag, 1u);
+    out = pack8(v);
+  }
+  reinterpret_cast<uint4*>(y)[i] = out;
+}
+
+struct BnBwdArgs {
+  const float* partial;      // [n_blk][2][C]: sum dy, sum dy*r   (scaled by S)
+  int32_t n_blk, C;
+  float n_rows, inv_loss_scale;
+  const float* gamma; const float* mean; const float* inv;
+  float* cA; float* cB; float* cC;           // dz = (r > 0) * (cA*dy + cB*r + cC)
+  float* d_gamma; float* d_beta;             // unscaled parameter gradients
+};
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const BnBwdArgs a) {
+  __shared__ double sred[8][2][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s[2];
+  reduce_blocks<2>(a.partial, a.n_blk, a.C, c, s, sred);
+  if (threadIdx.y != 0) return;
+  const double mu = a.mean[c], inv = a.inv[c], g = a.gamma[c], n = a.n_rows;
+  const double dbeta = s[0];
+  const double dgamma = inv * (s[1] - mu * s[0]);            // sum dy * (r - mu) * inv
+  const double cA = g * inv;
+  const double cB = -g * inv * inv * dgamma / n;
+  a.cA[c] = float(cA);
+  a.cB[c] = float(cB);
+  a.cC[c] = float(-cA * dbeta / n - cB * mu);
+  a.d_gamma[c] = float(dgamma * double(a.inv_loss_scale));
+  a.d_beta[c] = float(dbeta * double(a.inv_loss_scale));
+}
+
+// dz = (r > 0) ? cA*dy + cB*r + cC : 0 for one 32-row block x 256 channels; partial1[blk][c] = sum of dz (bias gradient)
+__global__ void __launch_bounds__(256)
+bn_relu_bwd_kernel(const __half* __restrict__ dy, const __half* __restrict__ r, int32_t C, const float* __restrict__ cA,
+                   const float* __restrict__ cB, const float* __restrict__ cC, __half* __restrict__ dz,
+                   float* __restrict__ partial1, uint32_t* overflow_flag) {
+  __shared__ float red[8][COLS_PER_CTA];
+  const int blk = blockIdx.x, c0 = blockIdx.y * COLS_PER_CTA;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = c0 + lane * 8;
+  float ka[8], kb[8], kc[8], s[8];
+  {
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(cA + c)), a1 = __ldg(reinterpret_cast<const float4*>(cA + c + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(cB + c)), b1 = __ldg(reinterpret_cast<const float4*>(cB + c + 4));
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(cC + c)), g1 = __ldg(reinterpret_cast<const float4*>(cC + c + 4));
+    ka[0] = a0.x; ka[1] = a0.y; ka[2] = a0.z; ka[3] = a0.w; ka[4] = a1.x; ka[5] = a1.y; ka[6] = a1.z; ka[7] = a1.w;
+    kb[0] = b0.x; kb[1] = b0.y; kb[2] = b0.z; kb[3] = b0.w; kb[4] = b1.x; kb[5] = b1.y; kb[6] = b1.z; kb[7] = b1.w;
+    kc[0] = g0.x; kc[1] = g0.y; kc[2] = g0.z; kc[3] = g0.w; kc[4] = g1.x; kc[5] = g1.y; kc[6] = g1.z; kc[7] = g1.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = 0.f;
+  float mx = 0.f;
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const int64_t off = (int64_t(blk) * BLK_ROWS + w * 4 + rr) * C + c;
+    float g[8], a[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + off)), g);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(r + off)), a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      o[i] = a[i] > 0.f ? fmaf(ka[i], g[i], fmaf(kb[i], a[i], kc[i])) : 0.f;
+      s[i] += o[i];
+      mx = fmaxf(mx, fabsf(o[i]));
+    }
+    *reinterpret_cast<uint4*>(dz + off) = pack8(o);
+  }
+  if (!(mx <= 65504.f)) atomicOr(overflow_flag, 1u);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[w][lane * 8 + i] = s[i];
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+  partial1[int64_t(blk) * C + c0 + threadIdx.x] = t;
+}
+
+// out[c] = scale * sum over blocks of partial1[blk][c]
+__global__ void __launch_bounds__(256)
+colsum_finalize_kernel(const float* __restrict__ partial1, int32_t n_blk, int32_t C, float scale, float* __restrict__ out) {
+  __shared__ double sred[8][1][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s[1];
+  reduce_blocks<1>(partial1, n_blk, C, c, s, sred);
+  if (threadIdx.y == 0) out[c] = float(s[0] * double(scale));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Statistics pooling of a training minibatch (all segments have seg_len rows, seg_stride packed rows each),
+// fused with the last frame layer's BatchNorm: y = r*scale + shift per channel, so
+//   mean_t(y) = scale*mean_t(r) + shift,  var_t(y) = scale^2 * var_t(r)        (models.py:485-486)
+struct PoolFwdArgs {
+  const float* partial;      // [n_blk][2][C] block sums of r (the ReLU output of the last frame layer)
+  int32_t C, n_seg, blks_per_seg;
+  float seg_len, var_eps;
+  const float* scale; const float* shift;
+  float* m_r; float* v_r;    // [n_seg][C] per-segment mean / population variance of r
+  float* h0;                 // [n_seg][2C]  [mean | sqrt(var + 1e-5)]
+};
+__global__ void __launch_bounds__(256) pool_train_fwd_kernel(const PoolFwdArgs a) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int seg = blockIdx.y;
+  if (c >= a.C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int b = 0; b < a.blks_per_seg; ++b) {
+    const int64_t blk = int64_t(seg) * a.blks_per_seg + b;
+    s1 += double(a.partial[(blk * 2 + 0) * a.C + c]);
+    s2 += double(a.partial[(blk * 2 + 1) * a.C + c]);
+  }
+  const double m = s1 / double(a.seg_len);
+  double v = s2 / double(a.seg_len) - m * m;
+  if (v < 0.0) v = 0.0;
+  const double sc = a.scale[c], sh = a.shift[c];
+  a.m_r[int64_t(seg) * a.C + c] = float(m);
+  a.v_r[int64_t(seg) * a.C + c] = float(v);
+  a.h0[int64_t(seg) * 2 * a.C + c] = float(sc * m + sh);
+  a.h0[int64_t(seg) * 2 * a.C + a.C + c] = float(sqrt(sc * sc * v + double(a.var_eps)));
+}
+
+// Backward of pooling + the last layer's BatchNorm, per channel.  With dmean, dstd = dL/d[mean_y | std_y] (fp32):
+//   dy[b,t,c] = a_bc + g_bc * r,   a = dmean/T - dstd*scale*m_r/(T*std_y),   g = dstd*scale/(T*std_y)
+// and BatchNorm backward (batch statistics over N = B*T rows)
+//   dr = gamma*inv*(dy - dbeta/N - (r-mu)*inv*dgamma/N)
+// everything stays affine in r:   dz = (r > 0) * (A_bc + G_bc * r)   (times the loss scale S).
+struct PoolBwdArgs {
+  const float* dh0;          // [n_seg][2C]
+  const float* m_r; const float* v_r;
+  int32_t C, n_seg;
+  float seg_len, var_eps, loss_scale;
+  const float* gamma; const float* mean; const float* inv; const float* scale;
+  float* coefA; float* coefG;        // [n_seg][C]
+  float* d_gamma; float* d_beta;     // [C]
+};
+__global__ void __launch_bounds__(128) pool_bwd_coef_kernel(const PoolBwdArgs p) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p.C) return;
+  const double T = p.seg_len, N = T * p.n_seg;
+  const double sc = p.scale[c], mu = p.mean[c], inv = p.inv[c], gam = p.gamma[c];
+  double dbeta = 0.0, dgamma = 0.0;
+  for (int b = 0; b < p.n_seg; ++b) {
+    const double m = p.m_r[int64_t(b) * p.C + c], v = p.v_r[int64_t(b) * p.C + c];
+    const double dm = p.dh0[int64_t(b) * 2 * p.C + c], ds = p.dh0[int64_t(b) * 2 * p.C + p.C + c];
+    const double std_y = sqrt(sc * sc * v + double(p.var_eps));
+    const double g = ds * sc / (T * std_y);
+    const double a = dm / T - g * m;
+    dbeta += T * a + g * T * m;
+    dgamma += a * (T * m - T * mu) + g * (T * (v + m * m) - mu * T * m);
+  }
+  dgamma *= inv;
+  for (int b = 0; b < p.n_seg; ++b) {
+    const double m = p.m_r[int64_t(b) * p.C + c], v = p.v_r[int64_t(b) * p.C + c];
+    const double dm = p.dh0[int64_t(b) * 2 * p.C + c], ds = p.dh0[int64_t(b) * 2 * p.C + p.C + c];
+    const double std_y = sqrt(sc * sc * v + double(p.var_eps));
+    const double g = ds * sc / (T * std_y);
+    const double a = dm / T - g * m;
+    p.coefA[int64_t(b) * p.C + c] = float(gam * inv * (a - dbeta / N + mu * inv * dgamma / N) * double(p.loss_scale));
+    p.coefG[int64_t(b) * p.C + c] = float(gam * inv * (g - inv * dgamma / N) * double(p.loss_scale));
+  }
+  p.d_gamma[c] = float(dgamma);
+  p.d_beta[c] = float(dbeta);
+}
+
+// dz4 = (r4 > 0) ? A[seg,c] + G[seg,c]*r4 : 0 ; partial1[blk][c] = column sums of dz4 (bias gradient, scaled by S)
+__global__ void __launch_bounds__(256)
+pool_relu_bwd_kernel(const __half* __restrict__ r, int32_t C, int32_t blks_per_seg, int32_t n_seg, const float* __restrict__ coefA,
+                     const float* __restrict__ coefG, __half* __restrict__ dz, float* __restrict__ partial1, uint32_t* overflow_flag) {
+  __shared__ float red[8][COLS_PER_CTA];
+  const int blk = blockIdx.x, c0 = blockIdx.y * COLS_PER_CTA;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = c0 + lane * 8;
+  const int seg = blk / blks_per_seg;
+  float ka[8], kg[8], s[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { ka[i] = 0.f; kg[i] = 0.f; s[i] = 0.f; }
+  if (seg < n_seg) {
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(coefA + int64_t(seg) * C + c)), a1 = __ldg(reinterpret_cast<const float4*>(coefA + int64_t(seg) * C + c + 4));
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(coefG + int64_t(seg) * C + c)), g1 = __ldg(reinterpret_cast<const float4*>(coefG + int64_t(seg) * C + c + 4));
+    ka[0] = a0.x; ka[1] = a0.y; ka[2] = a0.z; ka[3] = a0.w; ka[4] = a1.x; ka[5] = a1.y; ka[6] = a1.z; ka[7] = a1.w;
+    kg[0] = g0.x; kg[1] = g0.y; kg[2] = g0.z; kg[3] = g0.w; kg[4] = g1.x; kg[5] = g1.y; kg[6] = g1.z; kg[7] = g1.w;
+  }
+  float mx = 0.f;
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const int64_t off = (int64_t(blk) * BLK_ROWS + w * 4 + rr) * C + c;
+    float a[8], o[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(r + off)), a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      o[i] = a[i] > 0.f ? fmaf(kg[i], a[i], ka[i]) : 0.f;
+      s[i] += o[i];
+      mx = fmaxf(mx, fabsf(o[i]));
+    }
+    *reinterpret_cast<uint4*>(dz + off) = pack8(o);
+  }
+  if (!(mx <= 65504.f)) atomicOr(overflow_flag, 1u);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[w][lane * 8 + i] = s[i];
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+  partial1[int64_t(blk) * C + c0 + threadIdx.x] = t;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Segment level (64 rows): fp32 SIMT GEMM  C[m,n] = sum_k A(m,k) * B(k,n) (+ bias[n]) with arbitrary element strides,
+// 64 x 64 tile, split over K across gridDim.z (partials reduced in a fixed order by splitk_reduce_kernel).
+struct SgemmArgs {
+  const float* A; const float* B; float* C; const float* bias;
+  int32_t M, N, K;
+  int64_t sam, sak, sbk, sbn;
+  int32_t ldc;
+  int32_t k_per_split;         // multiple of 16
+  float* partial;              // [gridDim.z][M][N] when gridDim.z > 1
+};
+template <bool A_KFAST, bool B_NFAST>
+__global__ void __launch_bounds__(256) sgemm64_kernel(const SgemmArgs a) {
+  __shared__ float As[16][68];
+  __shared__ float Bs[16][68];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int k0 = blockIdx.z * a.k_per_split, k1 = min(a.K, k0 + a.k_per_split);
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int kb = k0; kb < k1; kb += 16) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 256;
+      {
+        const int kk = A_KFAST ? (idx & 15) : (idx >> 6), mm = A_KFAST ? (idx >> 4) : (idx & 63);
+        const int gm = m0 + mm, gk = kb + kk;
+        As[kk][mm] = (gm < a.M && gk < k1) ? __ldg(a.A + int64_t(gm) * a.sam + int64_t(gk) * a.sak) : 0.f;
+      }
+      {
+        const int kk = B_NFAST ? (idx >> 6) : (idx & 15), nn = B_NFAST ? (idx & 63) : (idx >> 4);
+        const int gn = n0 + nn, gk = kb + kk;
+        Bs[kk][nn] = (gn < a.N && gk < k1) ? __ldg(a.B + int64_t(gk) * a.sbk + int64_t(gn) * a.sbn) : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= a.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn >= a.N) continue;
+      if (gridDim.z == 1) a.C[int64_t(gm) * a.ldc + gn] = acc[i][j] + (a.bias ? __ldg(a.bias + gn) : 0.f);
+      else a.partial[(int64_t(blockIdx.z) * a.M + gm) * a.N + gn] = acc[i][j];
+    }
+  }
+}
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ partial, int32_t splits, int32_t M, int32_t N, const float* __restrict__ bias,
+                     float* __restrict__ C, int32_t ldc) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= int64_t(M) * N) return;
+  const int m = int(i / N), n = int(i - int64_t(m) * N);
+  float s = partial[i];
+  for (int k = 1; k < splits; ++k) s += partial[int64_t(k) * M * N + i];
+  C[int64_t(m) * ldc + n] = s + (bias ? __ldg(bias + n) : 0.f);
+}
+
+// r = relu(z); BatchNorm training branch over the B rows (tf_block.py:18-23); one thread per channel.
+struct SegBnArgs {
+  const float* z; int32_t B, C;
+  float eps, decay;
+  const float* gamma; const float* beta;
+  float* moving_mean; float* moving_var;
+  float* r; float* y; float* mean; float* inv;
+};
+__global__ void __launch_bounds__(128) seg_relu_bn_fwd_kernel(const SegBnArgs a) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.C) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int b = 0; b < a.B; ++b) {
+    const float r = fmaxf(a.z[int64_t(b) * a.C + c], 0.f);
+    a.r[int64_t(b) * a.C + c] = r;
+    s1 += r; s2 += double(r) * r;
+  }
+  const double mean = s1 / a.B;
+  double var = s2 / a.B - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const double inv = 1.0 / sqrt(var + double(a.eps));
+  const float sc = float(double(a.gamma[c]) * inv), sh = float(double(a.beta[c]) - mean * double(a.gamma[c]) * inv);
+  for (int b = 0; b < a.B; ++b) a.y[int64_t(b) * a.C + c] = fmaf(a.r[int64_t(b) * a.C + c], sc, sh);
+  a.mean[c] = float(mean);
+  a.inv[c] = float(inv);
+  a.moving_mean[c] = float(double(a.moving_mean[c]) * double(a.decay) + mean * (1.0 - double(a.decay)));
+  a.moving_var[c] = float(double(a.moving_var[c]) * double(a.decay) + var * (1.0 - double(a.decay)));
+}
+struct SegBnBwdArgs {
+  const float* dy; const float* r; int32_t B, C;
+  const float* gamma; const float* mean; const float* inv;
+  float* dz; float* d_gamma; float* d_beta; float* d_bias;
+};
+__global__ void __launch_bounds__(128) seg_relu_bn_bwd_kernel(const SegBnBwdArgs a) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.C) return;
+  const double mu = a.mean[c], inv = a.inv[c], g = a.gamma[c];
+  double dbeta = 0.0, dgamma = 0.0;
+  for (int b = 0; b < a.B; ++b) {
+    const double dy = a.dy[int64_t(b) * a.C + c], rh = (double(a.r[int64_t(b) * a.C + c]) - mu) * inv;
+    dbeta += dy; dgamma += dy * rh;
+  }
+  double db = 0.0;
+  for (int b = 0; b < a.B; ++b) {
+    const double r = a.r[int64_t(b) * a.C + c];
+    const double dy = a.dy[int64_t(b) * a.C + c], rh = (r - mu) * inv;
+    const double dr = g * inv * (dy - dbeta / a.B - rh * dgamma / a.B);
+    const float dz = r > 0.0 ? float(dr) : 0.f;
+    a.dz[int64_t(b) * a.C + c] = dz;
+    db += dz;
+  }
+  a.d_gamma[c] = float(dgamma);
+  a.d_beta[c] = float(dbeta);
+  a.d_bias[c] = float(db);
+}
+
+// Softmax cross-entropy of one row per CTA (models.py:512): loss_row, correct (argmax == label, first maximum as
+// tf.argmax), dlogits = (softmax - onehot) / B  (the gradient of reduce_mean, models.py:514).
+__global__ void __launch_bounds__(256)
+softmax_ce_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels, int32_t n_classes, float inv_batch,
+                  float* __restrict__ dlogits, float* __restrict__ loss_row, float* __restrict__ correct) {
+  __shared__ float s_val[256];
+  __shared__ int s_idx[256];
+  const int b = blockIdx.x, t = threadIdx.x;
+  const float* row = logits + int64_t(b) * n_classes;
+  float mx = -INFINITY; int mi = 0x7fffffff;
+  for (int j = t; j < n_classes; j += 256) { const float v = row[j]; if (v > mx) { mx = v; mi = j; } }
+  s_val[t] = mx; s_idx[t] = mi;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (t < s) {
+      const float v = s_val[t + s]; const int i = s_idx[t + s];
+      if (v > s_val[t] || (v == s_val[t] && i < s_idx[t])) { s_val[t] = v; s_idx[t] = i; }
+    }
+    __syncthreads();
+  }
+  mx = s_val[0]; mi = s_idx[0];
+  __syncthreads();
+  float se = 0.f;
+  for (int j = t; j < n_classes; j += 256) se += __expf(row[j] - mx);
+  s_val[t] = se;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) { if (t < s) s_val[t] += s_val[t + s]; __syncthreads(); }
+  se = s_val[0];
+  const int lab = labels[b];
+  const float inv_se = 1.f / se;
+  for (int j = t; j < n_classes; j += 256)
+    dlogits[int64_t(b) * n_classes + j] = (__expf(row[j] - mx) * inv_se - (j == lab ? 1.f : 0.f)) * inv_batch;
+  if (t == 0) {
+    loss_row[b] = logf(se) + mx - row[lab];
+    correct[b] = mi == lab ? 1.f : 0.f;
+  }
+}
+__global__ void loss_finalize_kernel(const float* loss_row, const float* correct, int32_t B, float* out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double l = 0.0, c = 0.0;
+  for (int b = 0; b < B; ++b) { l += loss_row[b]; c += correct[b]; }
+  out[0] = float(l / B);
+  out[1] = float(c / B);
+}
+// out[n] = sum over the B rows of x[b][n]
+__global__ void __launch_bounds__(256) colsum_rows_kernel(const float* __restrict__ x, int32_t B, int32_t N, float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s += x[int64_t(b) * N + n];
+  out[n] = s;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// tf.train.AdamOptimizer._apply_dense: m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr_t * m / (sqrt(v) + eps)
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+            float lr_t, float b1, float b2, float eps, float grad_scale) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i] * grad_scale;
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi; v[i] = vi;
+  p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+}
+
+// fp32 master conv weights W[taps][c_in][c_out] -> fp16 forward operand wf[c_out][k_total], K index = tap*c_in_pad + ci
+// (32 x 32 tile transposed through shared memory; grid (c_out/32, ceil(c_in/32), taps), block (32, 8))
+__global__ void __launch_bounds__(256)
+repack_fwd_kernel(const float* __restrict__ W, int32_t c_in, int32_t c_out, int32_t c_in_pad, int32_t k_total, __half* __restrict__ wf) {
+  __shared__ float tile[32][33];
+  const int o0 = blockIdx.x * 32, c0 = blockIdx.y * 32, j = blockIdx.z;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i;
+    tile[i][threadIdx.x] = c < c_in ? W[(int64_t(j) * c_in + c) * c_out + o0 + threadIdx.x] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + threadIdx.x;
+    if (c < c_in) wf[int64_t(o0 + i) * k_total + int64_t(j) * c_in_pad + c] = __float2half_rn(tile[threadIdx.x][i]);
+  }
+}
+// data-gradient operand wd[c_in][tap'*c_out + co] = W[taps-1-tap'][c_in][co]  (the conv of dz with the flipped kernel)
+__global__ void __launch_bounds__(256)
+repack_dgrad_kernel(const float* __restrict__ W, int32_t taps, int32_t c_in, int32_t c_out, __half* __restrict__ wd) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;      // pairs of output elements
+  const int64_t n2 = int64_t(taps) * c_in * c_out / 2;
+  if (i >= n2) return;
+  const int64_t e = i * 2;
+  const int co = int(e % c_out);
+  const int jp = int((e / c_out) % taps);
+  const int ci = int(e / (int64_t(c_out) * taps));
+  const float2 w = *reinterpret_cast<const float2*>(W + (int64_t(taps - 1 - jp) * c_in + ci) * c_out + co);
+  *reinterpret_cast<__half2*>(wd + e) = __floats2half2_rn(w.x, w.y);
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(float* p, int64_t n, float v) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+}  // namespace trk

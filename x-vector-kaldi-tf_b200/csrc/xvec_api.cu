@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -325,29 +326,16 @@ cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, 
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
 }
 
-int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_host, int32_t n_seg, float* emb_dev,
-                 void* workspace_dev, size_t workspace_bytes, cudaStream_t stream, float* const* layer_out_dev,
-                 float* stats_out_dev) {
-  if (!m || !feats_dev || !seg_len_host || !emb_dev || !workspace_dev) return fail(XV_EINVAL, "null argument");
-  if (n_seg <= 0) return fail(XV_EINVAL, "n_seg must be >= 1");
-  XV_CUDA(cudaSetDevice(m->device));
-  int rc = finalize_params(m);
-  if (rc != XV_OK) return rc;
-  int64_t total = 0;
-  for (int i = 0; i < n_seg; ++i) {
-    if (seg_len_host[i] <= 0) return fail(XV_EINVAL, "segment " + std::to_string(i) + " has non-positive length");
-    total += seg_len_host[i];
-  }
-  if (total + int64_t(n_seg) * (m->gap + 32) > (int64_t(1) << 31) - 4096)
-    return fail(XV_EINVAL, "batch too large: packed rows exceed int32 range");
-  const Plan p = make_plan(m, total, n_seg);
-  if (workspace_bytes < p.bytes)
-    return fail(XV_ENOMEM, "workspace too small: need " + std::to_string(p.bytes) + " bytes, got " + std::to_string(workspace_bytes));
-  if (reinterpret_cast<uintptr_t>(workspace_dev) % 1024 != 0) return fail(XV_EINVAL, "workspace must be 1024-byte aligned");
-  uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
-
-  // ---- segment metadata: packed row starts (multiples of 32), feature row starts, lengths ----
-  rc = ensure_meta_capacity(m, int64_t(4) * n_seg + 4 * (p.r_pad / tdnn2::POOL_BLOCK) + 4);
+// Segment metadata of one call, built on the host in a pinned staging slot and copied to meta_dev:
+// [row_start(n_seg) | feat_start(n_seg) | len(n_seg) | pad to int4 | blk_info(r_pad/32 x int4)].
+struct StagedMeta {
+  int64_t r_pad = 0;
+  xvk::SegMeta seg{};
+  const int4* blk_info_dev = nullptr;
+};
+int stage_meta(xv_model* m, const int32_t* seg_len_host, int32_t n_seg, int64_t plan_r_pad, int32_t* meta_dev,
+               cudaStream_t stream, StagedMeta* out) {
+  int rc = ensure_meta_capacity(m, int64_t(4) * n_seg + 4 * (plan_r_pad / tdnn2::POOL_BLOCK) + 4);
   if (rc != XV_OK) return rc;
   const int slot = m->meta_next;
   m->meta_next = (m->meta_next + 1) % META_SLOTS;
@@ -376,17 +364,48 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
     }
     rows_used = row;
   }
-  const int64_t r_pad = round_up(rows_used, tdnn2::TILE_ROWS);      // <= p.r_pad (the plan's upper bound)
+  const int64_t r_pad = round_up(rows_used, tdnn2::TILE_ROWS);
   const int64_t n_blocks = r_pad / tdnn2::POOL_BLOCK;
   for (int64_t b = rows_used / tdnn2::POOL_BLOCK; b < n_blocks; ++b) {
     int32_t* e = mh + blk_info_off + 4 * b;
     e[0] = e[1] = e[2] = e[3] = 0;
   }
-  int32_t* meta_dev = reinterpret_cast<int32_t*>(ws + p.off_meta);
   XV_CUDA(cudaMemcpyAsync(meta_dev, mh, (size_t(blk_info_off) + size_t(4) * n_blocks) * 4, cudaMemcpyHostToDevice, stream));
   XV_CUDA(cudaEventRecord(m->meta_event[slot], stream));
-  xvk::SegMeta seg{meta_dev, meta_dev + n_seg, meta_dev + 2 * n_seg, n_seg};
-  const int4* blk_info_dev = reinterpret_cast<const int4*>(meta_dev + blk_info_off);
+  out->r_pad = r_pad;
+  out->seg = xvk::SegMeta{meta_dev, meta_dev + n_seg, meta_dev + 2 * n_seg, n_seg};
+  out->blk_info_dev = reinterpret_cast<const int4*>(meta_dev + blk_info_off);
+  return XV_OK;
+}
+
+int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_host, int32_t n_seg, float* emb_dev,
+                 void* workspace_dev, size_t workspace_bytes, cudaStream_t stream, float* const* layer_out_dev,
+                 float* stats_out_dev) {
+  if (!m || !feats_dev || !seg_len_host || !emb_dev || !workspace_dev) return fail(XV_EINVAL, "null argument");
+  if (n_seg <= 0) return fail(XV_EINVAL, "n_seg must be >= 1");
+  XV_CUDA(cudaSetDevice(m->device));
+  int rc = finalize_params(m);
+  if (rc != XV_OK) return rc;
+  int64_t total = 0;
+  for (int i = 0; i < n_seg; ++i) {
+    if (seg_len_host[i] <= 0) return fail(XV_EINVAL, "segment " + std::to_string(i) + " has non-positive length");
+    total += seg_len_host[i];
+  }
+  if (total + int64_t(n_seg) * (m->gap + 32) > (int64_t(1) << 31) - 4096)
+    return fail(XV_EINVAL, "batch too large: packed rows exceed int32 range");
+  const Plan p = make_plan(m, total, n_seg);
+  if (workspace_bytes < p.bytes)
+    return fail(XV_ENOMEM, "workspace too small: need " + std::to_string(p.bytes) + " bytes, got " + std::to_string(workspace_bytes));
+  if (reinterpret_cast<uintptr_t>(workspace_dev) % 1024 != 0) return fail(XV_EINVAL, "workspace must be 1024-byte aligned");
+  uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
+
+  // ---- segment metadata: packed row starts (multiples of 32), feature row starts, lengths ----
+  StagedMeta sm;
+  rc = stage_meta(m, seg_len_host, n_seg, p.r_pad, reinterpret_cast<int32_t*>(ws + p.off_meta), stream, &sm);
+  if (rc != XV_OK) return rc;
+  const int64_t r_pad = sm.r_pad;                                   // <= p.r_pad (the plan's upper bound)
+  const xvk::SegMeta seg = sm.seg;
+  const int4* blk_info_dev = sm.blk_info_dev;
 
   uint8_t* row_valid = ws + p.off_valid;
   uint8_t* blk_valid = ws + p.off_blk_valid;
@@ -990,3 +1009,6 @@ int xv_set_option(xv_model* m, const char* name, int64_t value) {
 }
 
 }  // extern "C"
+
+// ---- training step (include/xvec_train.h) ----
+#include "train_api.cuh"
