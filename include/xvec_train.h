@@ -63,12 +63,16 @@ int64_t xv_train_get_step(const xv_trainer* t);
  * Also applies the moving-statistics update of every BatchNorm (tf_block.py:20-21).  Enqueue only. */
 int xv_train_forward_backward(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, int32_t n_seg,
                               int32_t seg_len, float* grad_dev, float* loss_acc_dev, void* stream);
+/* Loss and accuracy of one minibatch with phase = False (moving statistics, nothing is updated): the
+ * sess.run([self.loss, self.accuracy]) of Model.eval (models.py:338-339). */
+int xv_train_eval(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, int32_t n_seg, int32_t seg_len,
+                  float* loss_acc_dev, void* stream);
 /* Adam update (the optimizer half of models.py:263) with gradient grad_dev * grad_scale (NULL = own buffer;
  * grad_scale = 1/world_size after a sum all-reduce), then refreshes the fp16 operand copies.  Enqueue only. */
 int xv_train_apply(xv_trainer* t, const float* grad_dev, float learning_rate, float grad_scale, void* stream);
 
-/* Copies the current variables and moving statistics into the xv_model (so that xv_forward / xv_extract_host
- * evaluate the trained network: what Model.save_model + load_model do between train and extract). */
+/* Copies the current variables and moving statistics into the xv_model, so that xv_forward / xv_extract_host
+ * evaluate the trained network: what Model.save_model + load_model do between train and extract. */
 int xv_train_sync_model(xv_trainer* t);
 
 /* Parity hook: fp32 copy of an intermediate of the last forward_backward.  Packed fp16 tensors come back as

@@ -47,10 +47,10 @@ def trainable_names(topology, params):
     return [n for n in names if n in params]
 
 
-def _bn_train(h, gamma, beta, axes):
+def _bn_train(h, gamma, beta, axes, eps=BN_EPSILON):
     mean = h.mean(dim=axes)
     var = ((h - mean) ** 2).mean(dim=axes)                      # tf.nn.moments: population variance
-    inv = gamma / torch.sqrt(var + BN_EPSILON)
+    inv = gamma / torch.sqrt(var + eps)
     return h * inv + (beta - mean * inv), mean, var             # tf.nn.batch_normalization
 
 
@@ -62,13 +62,15 @@ def _fp16_storage(t):
 
 
 def forward_backward(x, labels, params, topology="ModelWithoutDropoutTdnn", dtype=torch.float64,
-                     return_intermediates=False, fp16_storage=False):
+                     return_intermediates=False, fp16_storage=False, bn_eps=BN_EPSILON):
     """One minibatch.  x: [B, T, D]; labels: [B] ints; params: dict of numpy arrays by TF variable name.
 
     Returns dict(loss, accuracy, grads{name: np}, batch_stats{scope: (mean, var)}, moving{name: np})
     where ``moving`` holds the updated moving mean/variance (tf_block.py:20-21).
     ``fp16_storage=True`` rounds the frame-level operands to fp16 at the points the CUDA path does (see
-    _fp16_storage); the default is the exact fp64 restatement of the reference.
+    _fp16_storage); the default is the exact fp64 restatement of the reference.  ``bn_eps`` is the reference's 1e-3;
+    tests also use a large value to make the gradient well conditioned (small-variance channels amplify any forward
+    rounding ~100x at 1e-3), which checks the backward arithmetic tightly.
     """
     q = _fp16_storage if fp16_storage else (lambda t: t)
     topo = TOPOLOGIES[topology] if isinstance(topology, str) else topology
@@ -85,7 +87,7 @@ def forward_backward(x, labels, params, topology="ModelWithoutDropoutTdnn", dtyp
         w = p[s + "w:0"]                                          # [k, Cin, Cout]
         z = F.conv1d(h.transpose(1, 2), q(w).permute(2, 1, 0), padding=(k - 1) // 2 * d, dilation=d).transpose(1, 2)
         r = q(torch.relu(z + p[s + "b:0"]))
-        h, mean, var = _bn_train(r, p[s + "gamma:0"], p[s + "beta:0"], (0, 1))
+        h, mean, var = _bn_train(r, p[s + "gamma:0"], p[s + "beta:0"], (0, 1), bn_eps)
         if i < n_frame - 1:
             h = q(h)
         batch_stats[s] = (mean.detach().numpy(), var.detach().numpy())
@@ -103,7 +105,7 @@ def forward_backward(x, labels, params, topology="ModelWithoutDropoutTdnn", dtyp
         s = "embed_layer-%d/" % i
         z = h @ p[s + "w:0"] + p[s + "b:0"]
         r = torch.relu(z)
-        h, mean, var = _bn_train(r, p[s + "gamma:0"], p[s + "beta:0"], (0,))
+        h, mean, var = _bn_train(r, p[s + "gamma:0"], p[s + "beta:0"], (0,), bn_eps)
         batch_stats[s] = (mean.detach().numpy(), var.detach().numpy())
         if return_intermediates:
             inter[s + "scores"] = z
@@ -163,3 +165,24 @@ def adam_step(params, grads, slots, lr):
         slots["v"][n] = ADAM_B2 * slots["v"][n] + (1 - ADAM_B2) * g * g
         params[n] = np.asarray(params[n], np.float64) - lr_t * slots["m"][n] / (np.sqrt(slots["v"][n]) + ADAM_EPS)
     return params
+
+
+def evaluate(x, labels, params, topology="ModelWithoutDropoutTdnn"):
+    """(loss, accuracy) with ``phase=False``: the moving statistics are used everywhere (tf_block.py:25-26) -- what
+    ``Model.eval`` fetches per minibatch (models.py:338-339).  fp64, no gradients."""
+    from .xvector_oracle import batch_norm_eval, forward
+    topo = TOPOLOGIES[topology] if isinstance(topology, str) else topology
+    p = {k: np.asarray(v, np.float64) for k, v in params.items()}
+    losses, correct = [], []
+    for xb, lab in zip(np.asarray(x, np.float64), np.asarray(labels)):
+        h = forward(xb, p, topo)                                   # embed_layer-0/scores
+        for i in range(len(topo["embedding_sizes"])):
+            s = "embed_layer-%d/" % i
+            if i > 0:
+                h = h @ p[s + "w:0"] + p[s + "b:0"]
+            h = batch_norm_eval(np.maximum(h, 0.0), p[s + "gamma:0"], p[s + "beta:0"], p[s + "mean:0"], p[s + "variance:0"])
+        logits = h @ p["output/w:0"] + p["output/b:0"]
+        m = logits.max()
+        losses.append(np.log(np.exp(logits - m).sum()) + m - logits[int(lab)])
+        correct.append(float(int(np.argmax(logits)) == int(lab)))
+    return float(np.mean(losses)), float(np.mean(correct))

@@ -233,7 +233,7 @@ def test_gather_to_rank0_single_process():
 
 def test_c_abi_library_exports_every_declared_symbol():
     from xvector_b200 import _native
-    header = open(os.path.join(ROOT, "include", "xvec.h")).read()
+    header = open(os.path.join(ROOT, "include", "xvec.h")).read() + open(os.path.join(ROOT, "include", "xvec_train.h")).read()
     declared = sorted(set(re.findall(r"\b(xv_[a-z_0-9]+)\s*\(", header)))
     assert declared and set(declared) == set(_native.EXPORTED_SYMBOLS)
     path = _native.build_library()                                    # nvcc cross-compiles without a GPU

@@ -1,0 +1,136 @@
+"""CPU tests of the training oracle and of the host-side training plumbing (no GPU)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import xvector_oracle as orc                      # noqa: E402
+from oracle import xvector_train_oracle as tro               # noqa: E402
+from xvector_b200 import examples_io, synthetic              # noqa: E402
+
+TOPO = "ModelWithoutDropoutTdnn"
+
+
+def _problem(B=4, T=40, NC=30, ws="B", seed=7):
+    topo = orc.TOPOLOGIES[TOPO]
+    P = synthetic.make_params(topo["kernel_sizes"], topo["layer_sizes"], topo["embedding_sizes"], num_classes=NC, weight_set=ws)
+    x = synthetic.mfcc(seed, B * T).reshape(B, T, 23)
+    labels = np.random.default_rng(seed).integers(0, NC, B)
+    return P, x, labels
+
+
+def test_autograd_gradients_match_finite_differences():
+    P, x, labels = _problem()
+    out = tro.forward_backward(x, labels, P, TOPO)
+    assert abs(out["loss"] - tro.loss_only(x, labels, P, TOPO)) < 1e-12
+    rng = np.random.default_rng(0)
+    for name in ["frame_level_info_layer-0/w:0", "frame_level_info_layer-2/w:0", "frame_level_info_layer-1/gamma:0",
+                 "frame_level_info_layer-3/b:0", "embed_layer-0/w:0", "embed_layer-1/beta:0", "output/w:0"]:
+        g = out["grads"][name]
+        flat = np.argsort(-np.abs(g).ravel())[:50]
+        idx = np.unravel_index(int(rng.choice(flat)), g.shape)      # a coordinate with a sizeable gradient
+        eps = 1e-5
+        Pp = {k: np.array(v, np.float64) for k, v in P.items()}
+        Pm = {k: np.array(v, np.float64) for k, v in P.items()}
+        Pp[name][idx] += eps
+        Pm[name][idx] -= eps
+        fd = (tro.loss_only(x, labels, Pp, TOPO) - tro.loss_only(x, labels, Pm, TOPO)) / (2 * eps)
+        assert abs(fd - g[idx]) <= 1e-5 * max(1.0, abs(g[idx]) * 100), (name, idx, fd, g[idx])
+
+
+def test_moving_statistics_update_and_population_variance():
+    P, x, labels = _problem(ws="B")
+    out = tro.forward_backward(x, labels, P, TOPO, return_intermediates=True)
+    r0 = out["intermediates"]["frame_level_info_layer-0/relu"]
+    mean, var = out["batch_stats"]["frame_level_info_layer-0/"]
+    np.testing.assert_allclose(mean, r0.reshape(-1, r0.shape[-1]).mean(0), rtol=1e-12)
+    np.testing.assert_allclose(var, r0.reshape(-1, r0.shape[-1]).var(0), rtol=1e-10)     # ddof = 0
+    want = 0.95 * np.asarray(P["frame_level_info_layer-0/variance:0"], np.float64) + 0.05 * var
+    np.testing.assert_allclose(out["moving"]["frame_level_info_layer-0/variance:0"], want, rtol=1e-12)
+    y0 = out["intermediates"]["frame_level_info_layer-0/bn"].reshape(-1, r0.shape[-1])
+    g = np.asarray(P["frame_level_info_layer-0/gamma:0"], np.float64)
+    b = np.asarray(P["frame_level_info_layer-0/beta:0"], np.float64)
+    np.testing.assert_allclose(y0.mean(0), b, atol=1e-9)                                   # BN output: mean beta ...
+    np.testing.assert_allclose(y0.var(0), g ** 2 * var / (var + 1e-3), rtol=1e-9)         # ... variance gamma^2 var/(var+eps)
+
+
+def test_eval_mode_matches_extraction_oracle_and_train_mode_when_stats_agree():
+    P, x, labels = _problem(B=3, T=30)
+    loss, acc = tro.evaluate(x, labels, P, TOPO)
+    assert np.isfinite(loss) and 0.0 <= acc <= 1.0
+    # substitute the batch statistics for the moving ones: eval forward == training forward (frame level, one segment batch)
+    out = tro.forward_backward(x, labels, P, TOPO, return_intermediates=True)
+    Q = dict(P)
+    for s, (mean, var) in out["batch_stats"].items():
+        Q[s + "mean:0"], Q[s + "variance:0"] = mean, var
+    loss2, _ = tro.evaluate(x, labels, Q, TOPO)
+    assert abs(loss2 - out["loss"]) < 1e-9
+
+
+def test_adam_known_answer():
+    p = {"w": np.array([1.0, -2.0])}
+    slots = tro.adam_init(p, ["w"])
+    g = {"w": np.array([0.5, -0.25])}
+    tro.adam_step(p, g, slots, 0.1)
+    # t = 1: m = 0.1 g, v = 0.001 g^2, lr_t = 0.1*sqrt(0.001)/0.1 -> step = lr_t * m/(sqrt(v)+eps) ~= 0.1*sign(g)
+    np.testing.assert_allclose(p["w"], [1.0 - 0.1, -2.0 + 0.1], atol=1e-6)
+    p1 = p["w"].copy()
+    tro.adam_step(p, g, slots, 0.1)
+    assert slots["t"] == 2
+    m = 0.9 * 0.1 * g["w"] + 0.1 * g["w"]
+    v = 0.999 * 0.001 * g["w"] ** 2 + 0.001 * g["w"] ** 2
+    lr_t = 0.1 * np.sqrt(1 - 0.999 ** 2) / (1 - 0.9 ** 2)
+    np.testing.assert_allclose(p["w"], p1 - lr_t * m / (np.sqrt(v) + 1e-8), rtol=1e-12)
+
+
+def test_fp16_storage_emulation_only_perturbs():
+    P, x, labels = _problem()
+    a = tro.forward_backward(x, labels, P, TOPO)
+    b = tro.forward_backward(x, labels, P, TOPO, fp16_storage=True)
+    assert abs(a["loss"] - b["loss"]) / a["loss"] < 1e-3
+    e = np.linalg.norm(a["grads"]["output/w:0"] - b["grads"]["output/w:0"]) / np.linalg.norm(a["grads"]["output/w:0"])
+    assert 0 < e < 5e-2
+
+
+def test_tar_loader_round_trip(tmp_path):
+    rng = np.random.default_rng(3)
+    mbs = [rng.standard_normal((4, 20 + 5 * i, 23)).astype(np.float32) for i in range(3)]
+    labs = [rng.integers(0, 50, 4) for _ in range(3)]
+    tar = str(tmp_path / "egs.1.tar")
+    examples_io.write_egs_tar(tar, mbs, labs)
+    dl = examples_io.TarFileDataLoader(tar, queue_size=2)
+    assert dl.count == 3
+    for i in range(3):
+        mat, lab = dl.pop(timeout=10)
+        assert mat.dtype == np.float16 and mat.shape == mbs[i].shape          # stored as float16 (examples_io.py:165)
+        np.testing.assert_array_equal(mat, mbs[i].astype(np.float16))
+        np.testing.assert_array_equal(lab, labs[i])
+    al = examples_io.ArrayDataLoader(mbs, labs)
+    m, l = al.pop()
+    assert m is mbs[2] and al.count == 3                                       # list.pop(): from the end
+    al.pop(); al.pop()
+    assert al.pop() == (None, None)
+
+
+def test_one_iteration_cli_rejects_bad_arguments(tmp_path):
+    from xvector_b200 import train_dnn_one_iteration as cli
+    base = ["--feature-dim", "23", "--minibatch-size", "4", "--minibatch-count", "2", "--output-dir", str(tmp_path / "out")]
+    with pytest.raises(Exception, match="expects the input model"):
+        cli.get_args(base + ["--input-dir", str(tmp_path / "nope"), "--tar-file", "x.tar"])
+    mdir = tmp_path / "model_0"
+    mdir.mkdir()
+    (mdir / "model.meta").write_text("{}")
+    with pytest.raises(Exception, match="tar file"):
+        cli.get_args(base + ["--input-dir", str(mdir), "--tar-file", str(tmp_path / "missing.tar")])
+    with pytest.raises(Exception, match="--tar-file archives only"):
+        cli.get_args(base + ["--input-dir", str(mdir)])
+    tar = str(tmp_path / "egs.1.tar")
+    examples_io.write_egs_tar(tar, [np.zeros((2, 5, 23))], [np.zeros(2, np.int32)])
+    with pytest.raises(Exception, match="dropout-proportion"):
+        cli.get_args(base + ["--input-dir", str(mdir), "--tar-file", tar, "--dropout-proportion", "1.5"])
+    args = cli.get_args(base + ["--input-dir", str(mdir), "--tar-file", tar, "--learning-rate", "0.001"])
+    assert args.learning_rate == 0.001 and args.print_interval == 10 and args.sequential_loading is True

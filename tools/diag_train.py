@@ -28,10 +28,11 @@ def main():
     P = synthetic.make_params(topo["kernel_sizes"], topo["layer_sizes"], topo["embedding_sizes"], num_classes=NC, weight_set=ws)
     x = synthetic.mfcc(5, B * T).reshape(B, T, 23)
     labels = np.random.default_rng(5).integers(0, NC, B).astype(np.int32)
-    ref = tro.forward_backward(x, labels, P, topology, return_intermediates=True, fp16_storage=bool(os.environ.get("FP16_ORACLE")))
+    ref = tro.forward_backward(x, labels, P, topology, return_intermediates=True, fp16_storage=bool(os.environ.get("FP16_ORACLE")),
+                               bn_eps=float(os.environ.get("BN_EPS", "1e-3")))
     print("diag_train: %s set %s B=%d T=%d classes=%d  oracle loss %.6f acc %.3f" % (topology, ws, B, T, NC, ref["loss"], ref["accuracy"]))
 
-    eng = _native.XvecEngine(topo["kernel_sizes"], topo["dilations"], topo["layer_sizes"], 512, 23, device=0)
+    eng = _native.XvecEngine(topo["kernel_sizes"], topo["dilations"], topo["layer_sizes"], 512, 23, device=0, bn_eps=float(os.environ.get("BN_EPS", "1e-3")))
     tr = _native.XvecTrainer(eng, NC, 512)
     tr.set_params(P)
     feats = torch.from_numpy(x.reshape(B * T, 23)).cuda()

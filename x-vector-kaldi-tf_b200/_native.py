@@ -120,6 +120,8 @@ def load_library():
     lib.xv_train_get_step.restype = I64
     lib.xv_train_forward_backward.argtypes = [P, P, P, I32, I32, P, P, P]
     lib.xv_train_forward_backward.restype = ctypes.c_int
+    lib.xv_train_eval.argtypes = [P, P, P, I32, I32, P, P]
+    lib.xv_train_eval.restype = ctypes.c_int
     lib.xv_train_apply.argtypes = [P, P, F32, F32, P]
     lib.xv_train_apply.restype = ctypes.c_int
     lib.xv_train_sync_model.argtypes = [P]
@@ -141,7 +143,7 @@ EXPORTED_SYMBOLS = ["xv_create", "xv_destroy", "xv_set_param", "xv_workspace_byt
                     "xv_last_kernel_ms", "xv_set_option", "xv_last_error", "xv_version",
                     # include/xvec_train.h
                     "xv_train_create", "xv_train_destroy", "xv_train_size", "xv_train_span", "xv_train_upload",
-                    "xv_train_download", "xv_train_set_step", "xv_train_get_step", "xv_train_forward_backward",
+                    "xv_train_download", "xv_train_set_step", "xv_train_get_step", "xv_train_forward_backward", "xv_train_eval",
                     "xv_train_apply", "xv_train_sync_model", "xv_train_debug_tensor", "xv_train_set_option",
                     "xv_train_last_launch_count", "xv_train_last_kernel_names"]
 
@@ -375,6 +377,18 @@ class XvecTrainer:
         _check(self.lib, self.lib.xv_train_forward_backward(self.handle, feats_dev.data_ptr(), labels_dev.data_ptr(), int(n_seg),
                                                             int(seg_len), gptr, self._loss_acc.data_ptr(), s.cuda_stream))
         self._geom = (int(n_seg), int(seg_len))
+        return self._loss_acc
+
+    def evaluate(self, feats_dev, labels_dev, n_seg, seg_len, stream=None):
+        """Loss / accuracy with phase=False (moving statistics); nothing is updated."""
+        import torch
+        assert feats_dev.is_cuda and feats_dev.dtype == torch.float32 and feats_dev.is_contiguous()
+        assert labels_dev.is_cuda and labels_dev.dtype == torch.int32 and labels_dev.numel() == n_seg
+        if self._loss_acc is None:
+            self._loss_acc = torch.zeros(2, dtype=torch.float32, device=feats_dev.device)
+        s = torch.cuda.current_stream(feats_dev.device) if stream is None else stream
+        _check(self.lib, self.lib.xv_train_eval(self.handle, feats_dev.data_ptr(), labels_dev.data_ptr(), int(n_seg), int(seg_len),
+                                                self._loss_acc.data_ptr(), s.cuda_stream))
         return self._loss_acc
 
     def apply(self, learning_rate, grad_dev=None, grad_scale=1.0, stream=None):

@@ -505,8 +505,14 @@ int xv_train_set_option(xv_trainer* t, const char* name, double value) {
   return XV_OK;
 }
 
-int xv_train_forward_backward(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, int32_t n_seg, int32_t seg_len,
-                              float* grad_dev, float* loss_acc_dev, void* stream_) {
+}  // extern "C"
+
+namespace {
+
+// training = true: forward (batch statistics, moving-statistics update) + backward.
+// training = false: forward only with the moving statistics (phase: False), loss and accuracy (Model.eval, models.py:307-354).
+int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, int32_t n_seg, int32_t seg_len,
+            float* grad_dev, float* loss_acc_dev, void* stream_, bool training) {
   if (!t || !feats_dev || !labels_dev || !loss_acc_dev) return fail(XV_EINVAL, "null argument");
   if (n_seg < 2 || seg_len < 1) return fail(XV_EINVAL, "need n_seg >= 2 and seg_len >= 1");
   xv_model* m = t->m;
@@ -557,7 +563,27 @@ int xv_train_forward_backward(xv_trainer* t, const float* feats_dev, const int32
 
   // ---- frame layers, training branch of BatchNorm ---------------------------------------------------
   const __half* in = t->x0;
-  for (int i = 0; i < nl; ++i) {
+  for (int i = 0; i < nl && !training; ++i) {
+    // evaluation branch of BatchNorm (tf_block.py:25-26) folded into the layer kernel's epilogue, as on the extraction path
+    TrFrame& L = t->frames[i];
+    float* scale = L.bn + 2 * L.c_out;
+    float* shift = L.bn + 3 * L.c_out;
+    TR_BEGIN("bn_fold_kernel");
+    trk::bn_fold_kernel<<<(L.c_out + 255) / 256, 256, 0, stream>>>(t->params + L.off_gamma, t->params + L.off_beta, t->moving + L.off_mov,
+                                                                 t->moving + L.off_mov + L.c_out, m->topo.bn_eps, L.c_out, scale, shift);
+    TR_END();
+    __half* out = (i < nl - 1) ? L.y : L.r;
+    rc = tr_pair_layer(t, stream, "tdnn_pair_kernel[fwd]", in, L.c_in_gemm, out, L.c_out, L.wf, L.k_total, L.gemm_taps, L.dil,
+                       t->params + L.off_b, scale, shift, nullptr);
+    if (rc != XV_OK) return rc;
+    in = out;
+    if (i == nl - 1) {
+      TR_BEGIN("blk_col_sums_kernel<0>");
+      trk::blk_col_sums_kernel<0><<<dim3(n_blk, L.c_out / trk::COLS_PER_CTA), 256, 0, stream>>>(out, nullptr, L.c_out, t->partial);
+      TR_END();
+    }
+  }
+  for (int i = 0; i < nl && training; ++i) {
     TrFrame& L = t->frames[i];
     rc = tr_pair_layer(t, stream, "tdnn_pair_kernel[fwd]", in, L.c_in_gemm, L.r, L.c_out, L.wf, L.k_total, L.gemm_taps, L.dil,
                        t->params + L.off_b, t->ones, t->zeros, nullptr);
@@ -588,7 +614,8 @@ int xv_train_forward_backward(xv_trainer* t, const float* feats_dev, const int32
     trk::PoolFwdArgs a{};
     a.partial = t->partial; a.C = C; a.n_seg = n_seg; a.blks_per_seg = t->seg_stride / 32;
     a.seg_len = float(seg_len); a.var_eps = m->topo.var_eps;
-    a.scale = LL.bn + 2 * C; a.shift = LL.bn + 3 * C;
+    a.scale = training ? LL.bn + 2 * C : t->ones;           // evaluation: the block sums are already those of y
+    a.shift = training ? LL.bn + 3 * C : t->zeros;
     a.m_r = t->m_r; a.v_r = t->v_r; a.h0 = t->h0;
     TR_BEGIN("pool_train_fwd_kernel");
     trk::pool_train_fwd_kernel<<<dim3((C + 255) / 256, n_seg), 256, 0, stream>>>(a);
@@ -607,6 +634,7 @@ int xv_train_forward_backward(xv_trainer* t, const float* feats_dev, const int32
     a.gamma = t->params + Sg.off_gamma; a.beta = t->params + Sg.off_beta;
     a.moving_mean = t->moving + Sg.off_mov; a.moving_var = t->moving + Sg.off_mov + Sg.out;
     a.r = Sg.r; a.y = Sg.y; a.mean = Sg.bn; a.inv = Sg.bn + Sg.out;
+    a.training = training ? 1 : 0;
     TR_BEGIN("seg_relu_bn_fwd_kernel");
     trk::seg_relu_bn_fwd_kernel<<<(Sg.out + 127) / 128, 128, 0, stream>>>(a);
     TR_END();
@@ -622,6 +650,7 @@ int xv_train_forward_backward(xv_trainer* t, const float* feats_dev, const int32
   TR_BEGIN("loss_finalize_kernel");
   trk::loss_finalize_kernel<<<1, 32, 0, stream>>>(t->loss_row, t->correct, n_seg, loss_acc_dev);
   TR_END();
+  if (!training) { t->debug.clear(); return XV_OK; }
 
   // ---- segment level backward -----------------------------------------------------------------------
   // output layer: dWo = y6^T dlogits, dbo = colsum(dlogits), dy6 = dlogits Wo^T
@@ -722,6 +751,20 @@ int xv_train_forward_backward(xv_trainer* t, const float* feats_dev, const int32
   t->debug["logits"] = TrDebug{t->logits, 0, 1, int64_t(n_seg) * NC};
   t->debug["dlogits"] = TrDebug{t->dlogits, 0, 1, int64_t(n_seg) * NC};
   return XV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int xv_train_forward_backward(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, int32_t n_seg, int32_t seg_len,
+                              float* grad_dev, float* loss_acc_dev, void* stream) {
+  return tr_step(t, feats_dev, labels_dev, n_seg, seg_len, grad_dev, loss_acc_dev, stream, true);
+}
+
+int xv_train_eval(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, int32_t n_seg, int32_t seg_len,
+                  float* loss_acc_dev, void* stream) {
+  return tr_step(t, feats_dev, labels_dev, n_seg, seg_len, nullptr, loss_acc_dev, stream, false);
 }
 
 int xv_train_apply(xv_trainer* t, const float* grad_dev, float learning_rate, float grad_scale, void* stream_) {

@@ -154,6 +154,17 @@ bn_apply_kernel(const __half* __restrict__ r, const uint8_t* __restrict__ row_va
   reinterpret_cast<uint4*>(y)[i] = out;
 }
 
+// evaluation branch: scale = gamma * rsqrt(moving_var + eps), shift = beta - moving_mean * scale  (tf_block.py:26)
+__global__ void __launch_bounds__(256)
+bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+               const float* __restrict__ var, float eps, int32_t C, float* __restrict__ scale, float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float inv = (1.0f / sqrtf(var[c] + eps)) * gamma[c];
+  scale[c] = inv;
+  shift[c] = beta[c] - mean[c] * inv;
+}
+
 struct BnBwdArgs {
   const float* partial;      // [n_blk][2][C]: sum dy, sum dy*r   (scaled by S)
   int32_t n_blk, C;
@@ -435,10 +446,20 @@ struct SegBnArgs {
   const float* gamma; const float* beta;
   float* moving_mean; float* moving_var;
   float* r; float* y; float* mean; float* inv;
+  int32_t training;          // 0: evaluation branch (moving statistics, no update; tf_block.py:25-26)
 };
 __global__ void __launch_bounds__(128) seg_relu_bn_fwd_kernel(const SegBnArgs a) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= a.C) return;
+  if (!a.training) {
+    const float sc = a.gamma[c] * (1.0f / sqrtf(a.moving_var[c] + a.eps)), sh = a.beta[c] - a.moving_mean[c] * sc;
+    for (int b = 0; b < a.B; ++b) {
+      const float r = fmaxf(a.z[int64_t(b) * a.C + c], 0.f);
+      a.r[int64_t(b) * a.C + c] = r;
+      a.y[int64_t(b) * a.C + c] = fmaf(r, sc, sh);
+    }
+    return;
+  }
   double s1 = 0.0, s2 = 0.0;
   for (int b = 0; b < a.B; ++b) {
     const float r = fmaxf(a.z[int64_t(b) * a.C + c], 0.f);

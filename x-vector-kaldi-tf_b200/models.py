@@ -51,7 +51,8 @@ def _create_engine(meta, params, device):
     eng = XvecEngine(meta["kernel_sizes"], meta["dilation_rates"], meta["layer_sizes"],
                      meta["embedding_sizes"][0], meta["input_feature_dim"], device=device,
                      bn_eps=BN_EPSILON, var_eps=VAR2STD_EPSILON, activation=meta.get("activation", "relu"))
-    eng.set_params(params)
+    # optimizer state saved by train_one_iteration ("<var>/Adam:0", "<var>/Adam_1:0", "beta*_power:0") is not a network variable
+    eng.set_params({k: v for k, v in params.items() if not k.endswith(("/Adam:0", "/Adam_1:0", "_power:0"))})
     return eng
 
 
@@ -183,14 +184,196 @@ class Model(object):
         self.load_model(None, input_dir, logger)
         return dict(self.params)
 
-    # ------------------------------------------------------------------ out of scope here
+    # ------------------------------------------------------------------ training / diagnostics
+    ADAM_SLOTS = ("/Adam:0", "/Adam_1:0")        # tf.train.AdamOptimizer slot names: "<var>/Adam", "<var>/Adam_1"
+
+    def _create_trainer(self, device):
+        """Engine + trainer holding this model's variables, moving statistics and (if saved) Adam state."""
+        from ._native import XvecTrainer, TRAIN_ADAM_M, TRAIN_ADAM_V
+        if self.activation != "relu":
+            raise NotImplementedError("the training step covers the ReLU topologies (Model, ModelWithoutDropout, "
+                                      "ModelWithoutDropoutTdnn); %s uses %s" % (type(self).__name__, self.activation))
+        eng = self._get_engine(device)
+        tr = XvecTrainer(eng, self.num_classes, self.embedding_sizes[1])
+        state = {k: v for k, v in self.params.items() if not k.endswith(self.ADAM_SLOTS) and not k.endswith("_power:0")}
+        tr.set_params(state)
+        for name in state:
+            base = name[:-2]
+            for suffix, which in zip(self.ADAM_SLOTS, (TRAIN_ADAM_M, TRAIN_ADAM_V)):
+                if base + suffix in self.params:
+                    _, off, cnt = tr.span(name)
+                    tr.upload(which, self.params[base + suffix], off)
+        if "beta1_power:0" in self.params:          # TF keeps b1^t; recover Adam's step counter t
+            b1p = float(np.asarray(self.params["beta1_power:0"]).reshape(-1)[0])
+            tr.step = int(round(np.log(b1p) / np.log(0.9))) if 0.0 < b1p < 1.0 else 0
+        return eng, tr
+
+    def _download_state(self, tr):
+        """Variables, moving statistics and Adam state of the trainer, keyed as the reference's checkpoint is."""
+        from ._native import TRAIN_ADAM_M, TRAIN_ADAM_V
+        out = {}
+        for name, arr in self.params.items():
+            if name.endswith(self.ADAM_SLOTS) or name.endswith("_power:0"):
+                continue
+            which, off, cnt = tr.span(name)
+            shape = np.asarray(arr).shape
+            out[name] = tr.download(which, off, cnt).reshape(shape)
+            if which == 0:
+                out[name[:-2] + self.ADAM_SLOTS[0]] = tr.download(TRAIN_ADAM_M, off, cnt).reshape(shape)
+                out[name[:-2] + self.ADAM_SLOTS[1]] = tr.download(TRAIN_ADAM_V, off, cnt).reshape(shape)
+        out["beta1_power:0"] = np.asarray([0.9 ** tr.step], dtype=np.float32)
+        out["beta2_power:0"] = np.asarray([0.999 ** tr.step], dtype=np.float32)
+        return out
+
+    def _run_minibatches(self, data_loader, tr, eng, logger, training, learning_rate=0.0, print_interval=10):
+        """The minibatch loop of train_one_iteration / eval (reference models.py:233-299 / :313-354): same skip rules,
+        counters and log lines; the host->device copy of minibatch k+1 overlaps the kernels of minibatch k, and
+        loss / accuracy are read back only when a log line needs them."""
+        import torch
+        dev = torch.device("cuda:%d" % eng.device)
+        world = sharding.dist_info()[1]
+        compute, copy = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        minibatch_count = data_loader.count
+        results = torch.zeros((max(minibatch_count, 1), 2), dtype=torch.float32, device=dev)
+        grad = torch.zeros(tr.n_params, dtype=torch.float32, device=dev) if (training and world > 1) else None
+        slots = [dict(feats=None, labels=None, ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
+        start_minibatch = 1
+        total_segments, minibatch_segments, total_segments_len = 0, 0, 0
+        total_gpu_waiting, total_disk_waiting = 0.0, 0.0
+        done = []                                   # indices into `results` of the minibatches that ran
+        window = []                                 # ... since the last log line
+        start_time = time.time()
+
+        def stage(k, batch_data, labels):
+            sl = slots[k % 2]
+            x = np.ascontiguousarray(batch_data, dtype=np.float32)
+            n = x.size
+            if sl["feats"] is None or sl["feats"].numel() < n:
+                sl["feats"] = torch.empty(n, dtype=torch.float32).pin_memory()
+                sl["feats_dev"] = torch.empty(n, dtype=torch.float32, device=dev)
+            if sl["labels"] is None or sl["labels"].numel() < x.shape[0]:
+                sl["labels"] = torch.empty(x.shape[0], dtype=torch.int32).pin_memory()
+                sl["labels_dev"] = torch.empty(x.shape[0], dtype=torch.int32, device=dev)
+            sl["free"].synchronize()                # the kernels that read this slot two minibatches ago are done
+            sl["feats"][:n].copy_(torch.from_numpy(x.reshape(-1)))
+            sl["labels"][:x.shape[0]].copy_(torch.from_numpy(np.ascontiguousarray(labels, dtype=np.int32)))
+            with torch.cuda.stream(copy):
+                sl["feats_dev"][:n].copy_(sl["feats"][:n], non_blocking=True)
+                sl["labels_dev"][:x.shape[0]].copy_(sl["labels"][:x.shape[0]], non_blocking=True)
+                sl["ready"].record(copy)
+            return sl, x.shape
+
+        for minibatch_idx in range(minibatch_count):
+            try:
+                disk_waiting = time.time()
+                batch_data, labels = data_loader.pop()
+                total_disk_waiting += time.time() - disk_waiting
+            except queue.Empty:
+                logger.warning('Timeout reach when reading the minibatch index %d' % minibatch_idx)
+                continue
+            if batch_data is None:
+                logger.warning('batch_data is None for the minibatch index %d' % minibatch_idx)
+                continue
+            minibatch_segments += batch_data.shape[0]
+            total_segments += batch_data.shape[0]
+            total_segments_len += batch_data.shape[1]
+            gpu_waiting = time.time()
+            sl, shape = stage(minibatch_idx, batch_data, labels)
+            n_seg, seg_len = int(shape[0]), int(shape[1])
+            with torch.cuda.stream(compute):
+                compute.wait_event(sl["ready"])
+                feats_dev = sl["feats_dev"][:n_seg * seg_len * shape[2]].view(n_seg * seg_len, shape[2])
+                if training:
+                    la = tr.forward_backward(feats_dev, sl["labels_dev"][:n_seg], n_seg, seg_len, grad_dev=grad, stream=compute)
+                    if grad is not None:            # data parallel: sum the flat gradient over the ranks (NCCL)
+                        import torch.distributed as dist
+                        dist.all_reduce(grad)
+                    tr.apply(learning_rate, grad_dev=grad, grad_scale=1.0 / world, stream=compute)
+                else:
+                    la = tr.evaluate(feats_dev, sl["labels_dev"][:n_seg], n_seg, seg_len, stream=compute)
+                results[minibatch_idx].copy_(la, non_blocking=True)
+                sl["free"].record(compute)
+            done.append(minibatch_idx)
+            window.append(minibatch_idx)
+            total_gpu_waiting += time.time() - gpu_waiting
+            end_minibatch = minibatch_idx + 1
+            if training and end_minibatch % print_interval == 0:
+                compute.synchronize()
+                eng.check_overflow(compute)
+                res = results[window].cpu().numpy().astype(np.float64)
+                cnt = end_minibatch - start_minibatch + 1
+                minibatch_loss, minibatch_accuracy = res[:, 0].sum(), res[:, 1].sum()
+                logger.info("Average training loss for minibatches %d-%d is %.4f over %d segments. Also, the "
+                            "average training accuracy for these minibatches is %.4f and the average "
+                            "objective function for these minibatches is %.4f. Average DISK waiting: %.1f "
+                            "secs and average GPU waiting: %.1f secs for each minibatch." %
+                            (start_minibatch, end_minibatch, minibatch_loss / cnt,
+                             minibatch_segments, minibatch_accuracy / cnt, -minibatch_loss / cnt,
+                             total_disk_waiting / cnt, total_gpu_waiting / cnt))
+                start_minibatch = end_minibatch + 1
+                minibatch_segments = 0
+                window = []
+                total_gpu_waiting = 0.0
+                total_disk_waiting = 0.0
+        compute.synchronize()
+        eng.check_overflow(compute)
+        res = results[done].cpu().numpy().astype(np.float64) if done else np.zeros((0, 2))
+        return dict(minibatch_count=minibatch_count, total_segments=total_segments, total_segments_len=total_segments_len,
+                    total_loss=float(res[:, 0].sum()), total_accuracy=float(res[:, 1].sum()), losses=res[:, 0],
+                    elapsed=time.time() - start_time)
+
     def train_one_iteration(self, data_loader, args, logger):
-        raise NotImplementedError("training (reference models.py:216-305) is outside the extraction hot path "
-                                  "this build covers; see DESIGN.md 'out of scope'")
+        """One pass over ``data_loader``'s minibatches with Adam (reference models.py:216-305): load the model of
+        ``args.input_dir``, per minibatch run the training step (``sess.run([optimizer, loss, accuracy])``,
+        models.py:263) at ``args.learning_rate``, log as the reference does, save to ``args.output_dir``.
+        ``args.dropout_proportion`` is accepted and ignored by the topologies without dropout (the default
+        ModelWithoutDropout family, run_xvector.sh:90); ``args.random_seed`` has nothing left to seed."""
+        learning_rate = args.learning_rate
+        print_interval = args.print_interval
+        device = set_cuda_visible_devices(use_gpu=True, logger=logger)
+        self.load_model(None, args.input_dir, logger)
+        eng, tr = self._create_trainer(device)
+        try:
+            st = self._run_minibatches(data_loader, tr, eng, logger, True, learning_rate, print_interval)
+            minibatch_count = max(st["minibatch_count"], 1)
+            logger.info("Processed %d segments of average size %d into %d minibatches. Avg minibatch size was %d." %
+                        (st["total_segments"], st["total_segments_len"] / minibatch_count, minibatch_count,
+                         st["total_segments"] / minibatch_count))
+            logger.info("Overall average training loss is %.4f over %d segments. Also, the overall "
+                        "average training accuracy is %.4f." % (st["total_loss"] / minibatch_count,
+                                                                st["total_segments"], st["total_accuracy"] / minibatch_count))
+            logger.info("Overall average objective function is %.4f over %d segments." %
+                        (-st["total_loss"] / minibatch_count, st["total_segments"]))
+            self.params = self._download_state(tr)
+            if sharding.dist_info()[0] == 0:
+                Model.save_model(_Session(self.params, self.meta), args.output_dir, logger)
+            logger.info("Elapsed time for processing whole training minibatches is %.2f minutes." % (st["elapsed"] / 60.0))
+            return st
+        finally:
+            tr.close()
+            eng.close()
+            self._engine = None
 
     def eval(self, data_loader, input_dir, use_gpu, logger):
-        raise NotImplementedError("diagnostic eval (reference models.py:307-354) is outside the extraction hot "
-                                  "path this build covers; see DESIGN.md 'out of scope'")
+        """Loss / accuracy over ``data_loader`` with phase=False (reference models.py:307-354)."""
+        device = set_cuda_visible_devices(use_gpu=use_gpu, logger=logger)
+        self.load_model(None, input_dir, logger)
+        eng, tr = self._create_trainer(device)
+        try:
+            st = self._run_minibatches(data_loader, tr, eng, logger, False)
+            minibatch_count = max(st["minibatch_count"], 1)
+            logger.info("Processed %d segments of average size %d into %d minibatches. Avg minibatch size was %d." %
+                        (st["total_segments"], st["total_segments_len"] / minibatch_count, minibatch_count,
+                         st["total_segments"] / minibatch_count))
+            logger.info("Overall average loss is %.4f over %d segments. Also, the overall "
+                        "average accuracy is %.4f." % (st["total_loss"] / minibatch_count, st["total_segments"],
+                                                       st["total_accuracy"] / minibatch_count))
+            logger.info("Elapsed time for processing whole training minibatches is %.2f minutes." % (st["elapsed"] / 60.0))
+            return st
+        finally:
+            tr.close()
+            eng.close()
+            self._engine = None
 
     # ------------------------------------------------------------------ extraction
     def _get_engine(self, device):
