@@ -384,14 +384,103 @@ def run_b200(args):
     if remeasured:
         out["clocks"]["note"] = "first measurement rejected (throttle reason / low clocks); this is the re-measurement"
 
+    eng.close()
+    if not args.no_train and topo.get("act", "relu") == "relu":
+        out["train_step"] = measure_train_step(args, dev, rank, world, peaks, topo)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_subprocess(args)
-    eng.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(out), flush=True)
+
+
+def measure_train_step(args, dev, rank, world, peaks, topo):
+    """BASELINE configs[4]: one data-parallel training step (TDNN + stats pooling + softmax over 5000 speakers,
+    64 x 400 frames per GPU): xv_train_forward_backward -> NCCL all-reduce of the flat gradient (N > 1) -> xv_train_apply.
+    Reported as an extra block of the JSON line (the headline metric stays extraction frames/s)."""
+    import torch
+    import torch.distributed as dist
+    from xvector_b200 import _native, synthetic
+    B, T, NC, steps, warm = 64, 400, 5000, 60, 5
+    P = synthetic.make_params(topo["kernel_sizes"], topo["layer_sizes"], topo["embedding_sizes"], num_classes=NC, weight_set="B")
+    eng = _native.XvecEngine(topo["kernel_sizes"], topo["dilations"], topo["layer_sizes"], EMB_DIM, FEAT_DIM, device=dev.index)
+    tr = _native.XvecTrainer(eng, NC, topo["embedding_sizes"][1])
+    tr.set_params(P)
+    feats_host = torch.empty((B * T, FEAT_DIM), dtype=torch.float32, pin_memory=True)
+    feats_host.numpy()[:] = synthetic.mfcc(5 + 1000 * rank, B * T)                      # configs[4]: seed 5
+    lab_host = torch.from_numpy(np.random.default_rng(5 + rank).integers(0, NC, B).astype(np.int32)).pin_memory()
+    feats, lab = feats_host.to(dev), lab_host.to(dev)
+    grad = torch.zeros(tr.n_params, dtype=torch.float32, device=dev) if world > 1 else None
+    la_host = torch.zeros(2, dtype=torch.float32, pin_memory=True)
+
+    def step(e2e):
+        if e2e:
+            feats.copy_(feats_host, non_blocking=True)
+            lab.copy_(lab_host, non_blocking=True)
+        la = tr.forward_backward(feats, lab, B, T, grad_dev=grad)
+        if world > 1:
+            dist.all_reduce(grad)
+        tr.apply(1e-4, grad_dev=grad, grad_scale=1.0 / world)
+        if e2e:
+            la_host.copy_(la, non_blocking=True)
+        return la
+
+    def timed(e2e):
+        for _ in range(warm):
+            step(e2e)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(e2e)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    ms_res = timed(False)
+    eng.check_overflow()
+    ms_e2e = timed(True)
+    loss = float(la_host[0])
+    launches = tr.last_launch_count
+    kernels = None
+    if world == 1:
+        eng.set_option("profile", 1)
+        agg = {}
+        for _ in range(3):
+            step(False)
+            torch.cuda.synchronize(dev)
+            for n, t_ in zip(tr.last_kernel_names(), eng.last_kernel_ms()):
+                agg[n] = agg.get(n, 0.0) + t_ / 3
+        eng.set_option("profile", 0)
+        kernels = {n: round(v, 4) for n, v in sorted(agg.items(), key=lambda kv: -kv[1])}
+    fl = sum(flop_per_frame(topo))
+    # forward + data gradient (all layers but the first) + weight gradient, frame level only
+    flop_step = B * T * (3 * fl - flop_per_frame(topo)[0])
+    tensor_ms = sum(v for n, v in (kernels or {}).items() if "pair_kernel" in n)
+    out = dict(workload="configs[4]: training step, %s + stats pooling + softmax over %d speakers, batch %d x %d frames per GPU, "
+                        "fp16 operands / fp32 accumulate + fp32 master weights, Adam" % (args.topology, NC, B, T),
+               ms_per_step=round(ms_res, 4), value=round(world * B * T / (ms_res * 1e-3), 1), unit="frames/s",
+               e2e=dict(ms_per_step=round(ms_e2e, 4), value=round(world * B * T / (ms_e2e * 1e-3), 1), unit="frames/s",
+                        h2d_bytes_per_step=B * T * FEAT_DIM * 4 + B * 4, d2h_bytes_per_step=8),
+               parallelism="data parallel x%d: NCCL all-reduce of the flat fp32 gradient (%.1f MB) per step" % (world, tr.n_params * 4 / 1e6)
+               if world > 1 else "single GPU",
+               gpu_launches_per_step=launches, loss_after=round(loss, 4),
+               frame_level_flop_per_step=flop_step,
+               step_frac_of_tensor_peak=round(flop_step / (ms_res * 1e-3) / 1e12 / peaks["tflops"], 4))
+    if kernels:
+        out["kernel_ms"] = kernels
+        out["tensor_kernels"] = dict(ms=round(tensor_ms, 4), achieved=round(flop_step / (tensor_ms * 1e-3) / 1e12, 1), unit="TFLOP/s",
+                                     frac=round(flop_step / (tensor_ms * 1e-3) / 1e12 / peaks["tflops"], 4))
+    tr.close()
+    eng.close()
+    return out
 
 
 def cpu_baseline_subprocess(args):
@@ -504,6 +593,7 @@ def main():
     ap.add_argument("--frames", type=int, default=400)
     ap.add_argument("--option", action="append", default=[], help="xv_set_option name=value (diagnostics)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the configs[4] training-step block")
     ap.add_argument("--step-seconds", type=float, default=1.5, help="reference arm: CPU seconds per step (calibrated)")
     args = ap.parse_args()
     if args.impl == "reference":

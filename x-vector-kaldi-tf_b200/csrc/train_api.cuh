@@ -315,15 +315,10 @@ int tr_repack(xv_trainer* t, cudaStream_t stream) {
     TrFrame& L = t->frames[i];
     const float* W = t->params + L.off_w;
     const int c_in_pad = (i == 0) ? L.c_in : L.c_in_gemm;          // first layer: densely spliced K index tap*D + c
-    TR_BEGIN("repack_fwd_kernel");
-    trk::repack_fwd_kernel<<<dim3(L.c_out / 32, (L.c_in + 31) / 32, L.taps), dim3(32, 8), 0, stream>>>(W, L.c_in, L.c_out, c_in_pad, L.k_total, L.wf);
+    TR_BEGIN("repack_kernel");
+    trk::repack_kernel<<<dim3(L.c_out / 32, (L.c_in + 31) / 32, L.taps), dim3(32, 8), 0, stream>>>(W, L.taps, L.c_in, L.c_out, c_in_pad, L.k_total,
+                                                                                                L.wf, i > 0 ? L.wd : nullptr);
     TR_END();
-    if (i > 0) {
-      const int64_t n2 = int64_t(L.taps) * L.c_in * L.c_out / 2;
-      TR_BEGIN("repack_dgrad_kernel");
-      trk::repack_dgrad_kernel<<<unsigned((n2 + 255) / 256), 256, 0, stream>>>(W, L.taps, L.c_in, L.c_out, L.wd);
-      TR_END();
-    }
   }
   t->operands_dirty = false;
   return XV_OK;
@@ -598,7 +593,7 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
     b.moving_mean = t->moving + L.off_mov; b.moving_var = t->moving + L.off_mov + L.c_out;
     b.mean = L.bn; b.inv = L.bn + L.c_out; b.scale = L.bn + 2 * L.c_out; b.shift = L.bn + 3 * L.c_out;
     TR_BEGIN("bn_fwd_finalize_kernel");
-    trk::bn_fwd_finalize_kernel<<<L.c_out / 32, dim3(32, 8), 0, stream>>>(b);
+    trk::bn_fwd_finalize_kernel<<<L.c_out / 32, dim3(32, trk::RED_Y), 0, stream>>>(b);
     TR_END();
     if (i < nl - 1) {
       const int64_t n8 = r_pad * L.c_out / 8;
@@ -636,7 +631,7 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
     a.r = Sg.r; a.y = Sg.y; a.mean = Sg.bn; a.inv = Sg.bn + Sg.out;
     a.training = training ? 1 : 0;
     TR_BEGIN("seg_relu_bn_fwd_kernel");
-    trk::seg_relu_bn_fwd_kernel<<<(Sg.out + 127) / 128, 128, 0, stream>>>(a);
+    trk::seg_relu_bn_fwd_kernel<<<(Sg.out + 31) / 32, dim3(32, trk::SEG_Y), 0, stream>>>(a);
     TR_END();
     hin = Sg.y;
   }
@@ -668,7 +663,7 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
     a.gamma = t->params + Sg.off_gamma; a.mean = Sg.bn; a.inv = Sg.bn + Sg.out;
     a.dz = Sg.dz; a.d_gamma = grad + Sg.off_gamma; a.d_beta = grad + Sg.off_beta; a.d_bias = grad + Sg.off_b;
     TR_BEGIN("seg_relu_bn_bwd_kernel");
-    trk::seg_relu_bn_bwd_kernel<<<(Sg.out + 127) / 128, 128, 0, stream>>>(a);
+    trk::seg_relu_bn_bwd_kernel<<<(Sg.out + 31) / 32, dim3(32, trk::SEG_Y), 0, stream>>>(a);
     TR_END();
     const float* xin = (i == 1) ? t->seg[0].y : t->h0;
     float* dxin = (i == 1) ? t->seg[0].dy : t->dh0;
@@ -686,14 +681,14 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
     a.gamma = t->params + LL.off_gamma; a.mean = LL.bn; a.inv = LL.bn + C; a.scale = LL.bn + 2 * C;
     a.coefA = t->coefA; a.coefG = t->coefG; a.d_gamma = grad + LL.off_gamma; a.d_beta = grad + LL.off_beta;
     TR_BEGIN("pool_bwd_coef_kernel");
-    trk::pool_bwd_coef_kernel<<<(C + 127) / 128, 128, 0, stream>>>(a);
+    trk::pool_bwd_coef_kernel<<<(C + 31) / 32, dim3(32, trk::SEG_Y), 0, stream>>>(a);
     TR_END();
     TR_BEGIN("pool_relu_bwd_kernel");
     trk::pool_relu_bwd_kernel<<<dim3(n_blk, C / trk::COLS_PER_CTA), 256, 0, stream>>>(LL.r, C, t->seg_stride / 32, n_seg, t->coefA, t->coefG,
                                                                                    LL.dz, t->partial1, m->overflow_dev);
     TR_END();
     TR_BEGIN("colsum_finalize_kernel");
-    trk::colsum_finalize_kernel<<<C / 32, dim3(32, 8), 0, stream>>>(t->partial1, n_blk, C, inv_S, grad + LL.off_b);
+    trk::colsum_finalize_kernel<<<C / 32, dim3(32, trk::RED_Y), 0, stream>>>(t->partial1, n_blk, C, inv_S, grad + LL.off_b);
     TR_END();
   }
 
@@ -711,14 +706,14 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
       b.cA = t->cA; b.cB = t->cB; b.cC = t->cC;
       b.d_gamma = grad + L.off_gamma; b.d_beta = grad + L.off_beta;
       TR_BEGIN("bn_bwd_finalize_kernel");
-      trk::bn_bwd_finalize_kernel<<<L.c_out / 32, dim3(32, 8), 0, stream>>>(b);
+      trk::bn_bwd_finalize_kernel<<<L.c_out / 32, dim3(32, trk::RED_Y), 0, stream>>>(b);
       TR_END();
       TR_BEGIN("bn_relu_bwd_kernel");
       trk::bn_relu_bwd_kernel<<<dim3(n_blk, L.c_out / trk::COLS_PER_CTA), 256, 0, stream>>>(L.dy, L.r, L.c_out, t->cA, t->cB, t->cC, L.dz,
                                                                                          t->partial1, m->overflow_dev);
       TR_END();
       TR_BEGIN("colsum_finalize_kernel");
-      trk::colsum_finalize_kernel<<<L.c_out / 32, dim3(32, 8), 0, stream>>>(t->partial1, n_blk, L.c_out, inv_S, grad + L.off_b);
+      trk::colsum_finalize_kernel<<<L.c_out / 32, dim3(32, trk::RED_Y), 0, stream>>>(t->partial1, n_blk, L.c_out, inv_S, grad + L.off_b);
       TR_END();
     }
     const __half* x = (i == 0) ? t->x0 : t->frames[i - 1].y;

@@ -78,25 +78,39 @@ blk_col_sums_kernel(const __half* __restrict__ x, const __half* __restrict__ y, 
   partial[(int64_t(blk) * 2 + 1) * C + c0 + t] = b;
 }
 
-// Sum partial[blk][j][c] over blk for 32 channels per CTA (block 32 x 8), fp64, fixed order.
+// Sum partial[blk][j][c] over blk for 32 channels per CTA (block 32 x RED_Y), fp64, fixed order.
+constexpr int RED_Y = 32;
+constexpr int SEG_Y = 8;      // row groups of the segment-level (<= 64 rows) kernels
 template <int NSUM>
 __device__ __forceinline__ void reduce_blocks(const float* __restrict__ partial, int32_t n_blk, int32_t C, int c, double (&out)[NSUM],
                                               double (*sred)[NSUM][32]) {
-  double s[NSUM];
+  double s[NSUM], u[NSUM];
 #pragma unroll
-  for (int j = 0; j < NSUM; ++j) s[j] = 0.0;
-  for (int b = threadIdx.y; b < n_blk; b += 8) {
+  for (int j = 0; j < NSUM; ++j) { s[j] = 0.0; u[j] = 0.0; }
+  int b = threadIdx.y;
+  for (; b + RED_Y < n_blk; b += 2 * RED_Y) {           // two loads in flight per sum
+#pragma unroll
+    for (int j = 0; j < NSUM; ++j) {
+      const float v0 = partial[(int64_t(b) * NSUM + j) * C + c];
+      const float v1 = partial[(int64_t(b + RED_Y) * NSUM + j) * C + c];
+      s[j] += double(v0);
+      u[j] += double(v1);
+    }
+  }
+  if (b < n_blk) {
 #pragma unroll
     for (int j = 0; j < NSUM; ++j) s[j] += double(partial[(int64_t(b) * NSUM + j) * C + c]);
   }
 #pragma unroll
-  for (int j = 0; j < NSUM; ++j) sred[threadIdx.y][j][threadIdx.x] = s[j];
+  for (int j = 0; j < NSUM; ++j) sred[threadIdx.y][j][threadIdx.x] = s[j] + u[j];
   __syncthreads();
+  if (threadIdx.y == 0) {
 #pragma unroll
-  for (int j = 0; j < NSUM; ++j) {
-    double t = 0.0;
-    for (int k = 0; k < 8; ++k) t += sred[k][j][threadIdx.x];
-    out[j] = t;
+    for (int j = 0; j < NSUM; ++j) {
+      double t = 0.0;
+      for (int k = 0; k < RED_Y; ++k) t += sred[k][j][threadIdx.x];
+      out[j] = t;
+    }
   }
 }
 
@@ -110,8 +124,8 @@ struct BnFwdArgs {
   float* mean; float* inv;                   // batch mean, rsqrt(var + eps)
   float* scale; float* shift;                // gamma*inv, beta - mean*gamma*inv   (tf.nn.batch_normalization)
 };
-__global__ void __launch_bounds__(256) bn_fwd_finalize_kernel(const BnFwdArgs a) {
-  __shared__ double sred[8][2][32];
+__global__ void __launch_bounds__(1024) bn_fwd_finalize_kernel(const BnFwdArgs a) {
+  __shared__ double sred[RED_Y][2][32];
   const int c = blockIdx.x * 32 + threadIdx.x;
   double s[2];
   reduce_blocks<2>(a.partial, a.n_blk, a.C, c, s, sred);
@@ -173,8 +187,8 @@ struct BnBwdArgs {
   float* cA; float* cB; float* cC;           // dz = (r > 0) * (cA*dy + cB*r + cC)
   float* d_gamma; float* d_beta;             // unscaled parameter gradients
 };
-__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const BnBwdArgs a) {
-  __shared__ double sred[8][2][32];
+__global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const BnBwdArgs a) {
+  __shared__ double sred[RED_Y][2][32];
   const int c = blockIdx.x * 32 + threadIdx.x;
   double s[2];
   reduce_blocks<2>(a.partial, a.n_blk, a.C, c, s, sred);
@@ -237,9 +251,9 @@ bn_relu_bwd_kernel(const __half* __restrict__ dy, const __half* __restrict__ r, 
 }
 
 // out[c] = scale * sum over blocks of partial1[blk][c]
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 colsum_finalize_kernel(const float* __restrict__ partial1, int32_t n_blk, int32_t C, float scale, float* __restrict__ out) {
-  __shared__ double sred[8][1][32];
+  __shared__ double sred[RED_Y][1][32];
   const int c = blockIdx.x * 32 + threadIdx.x;
   double s[1];
   reduce_blocks<1>(partial1, n_blk, C, c, s, sred);
@@ -292,23 +306,38 @@ struct PoolBwdArgs {
   float* coefA; float* coefG;        // [n_seg][C]
   float* d_gamma; float* d_beta;     // [C]
 };
-__global__ void __launch_bounds__(128) pool_bwd_coef_kernel(const PoolBwdArgs p) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= p.C) return;
+__global__ void __launch_bounds__(256) pool_bwd_coef_kernel(const PoolBwdArgs p) {       // block (32, SEG_Y)
+  __shared__ double sred[SEG_Y][2][32];
+  __shared__ double s_tot[2][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool live = c < p.C;
   const double T = p.seg_len, N = T * p.n_seg;
-  const double sc = p.scale[c], mu = p.mean[c], inv = p.inv[c], gam = p.gamma[c];
+  const double sc = live ? p.scale[c] : 0.0, mu = live ? p.mean[c] : 0.0, inv = live ? p.inv[c] : 0.0, gam = live ? p.gamma[c] : 0.0;
   double dbeta = 0.0, dgamma = 0.0;
-  for (int b = 0; b < p.n_seg; ++b) {
-    const double m = p.m_r[int64_t(b) * p.C + c], v = p.v_r[int64_t(b) * p.C + c];
-    const double dm = p.dh0[int64_t(b) * 2 * p.C + c], ds = p.dh0[int64_t(b) * 2 * p.C + p.C + c];
-    const double std_y = sqrt(sc * sc * v + double(p.var_eps));
-    const double g = ds * sc / (T * std_y);
-    const double a = dm / T - g * m;
-    dbeta += T * a + g * T * m;
-    dgamma += a * (T * m - T * mu) + g * (T * (v + m * m) - mu * T * m);
+  if (live) {
+    for (int b = threadIdx.y; b < p.n_seg; b += SEG_Y) {
+      const double m = p.m_r[int64_t(b) * p.C + c], v = p.v_r[int64_t(b) * p.C + c];
+      const double dm = p.dh0[int64_t(b) * 2 * p.C + c], ds = p.dh0[int64_t(b) * 2 * p.C + p.C + c];
+      const double std_y = sqrt(sc * sc * v + double(p.var_eps));
+      const double g = ds * sc / (T * std_y);
+      const double a = dm / T - g * m;
+      dbeta += T * a + g * T * m;
+      dgamma += a * (T * m - T * mu) + g * (T * (v + m * m) - mu * T * m);
+    }
   }
-  dgamma *= inv;
-  for (int b = 0; b < p.n_seg; ++b) {
+  sred[threadIdx.y][0][threadIdx.x] = dbeta;
+  sred[threadIdx.y][1][threadIdx.x] = dgamma;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    dbeta = 0.0; dgamma = 0.0;
+    for (int k = 0; k < SEG_Y; ++k) { dbeta += sred[k][0][threadIdx.x]; dgamma += sred[k][1][threadIdx.x]; }
+    s_tot[0][threadIdx.x] = dbeta;
+    s_tot[1][threadIdx.x] = dgamma * inv;
+  }
+  __syncthreads();
+  if (!live) return;
+  dbeta = s_tot[0][threadIdx.x]; dgamma = s_tot[1][threadIdx.x];
+  for (int b = threadIdx.y; b < p.n_seg; b += SEG_Y) {
     const double m = p.m_r[int64_t(b) * p.C + c], v = p.v_r[int64_t(b) * p.C + c];
     const double dm = p.dh0[int64_t(b) * 2 * p.C + c], ds = p.dh0[int64_t(b) * 2 * p.C + p.C + c];
     const double std_y = sqrt(sc * sc * v + double(p.var_eps));
@@ -317,8 +346,10 @@ __global__ void __launch_bounds__(128) pool_bwd_coef_kernel(const PoolBwdArgs p)
     p.coefA[int64_t(b) * p.C + c] = float(gam * inv * (a - dbeta / N + mu * inv * dgamma / N) * double(p.loss_scale));
     p.coefG[int64_t(b) * p.C + c] = float(gam * inv * (g - inv * dgamma / N) * double(p.loss_scale));
   }
-  p.d_gamma[c] = float(dgamma);
-  p.d_beta[c] = float(dbeta);
+  if (threadIdx.y == 0) {
+    p.d_gamma[c] = float(dgamma);
+    p.d_beta[c] = float(dbeta);
+  }
 }
 
 // dz4 = (r4 > 0) ? A[seg,c] + G[seg,c]*r4 : 0 ; partial1[blk][c] = column sums of dz4 (bias gradient, scaled by S)
@@ -448,61 +479,99 @@ struct SegBnArgs {
   float* r; float* y; float* mean; float* inv;
   int32_t training;          // 0: evaluation branch (moving statistics, no update; tf_block.py:25-26)
 };
-__global__ void __launch_bounds__(128) seg_relu_bn_fwd_kernel(const SegBnArgs a) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= a.C) return;
-  if (!a.training) {
-    const float sc = a.gamma[c] * (1.0f / sqrtf(a.moving_var[c] + a.eps)), sh = a.beta[c] - a.moving_mean[c] * sc;
-    for (int b = 0; b < a.B; ++b) {
+__global__ void __launch_bounds__(256) seg_relu_bn_fwd_kernel(const SegBnArgs a) {     // block (32, SEG_Y)
+  __shared__ double sred[SEG_Y][2][32];
+  __shared__ float s_sc[32], s_sh[32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool live = c < a.C;
+  double s1 = 0.0, s2 = 0.0;
+  if (live) {
+    for (int b = threadIdx.y; b < a.B; b += SEG_Y) {
       const float r = fmaxf(a.z[int64_t(b) * a.C + c], 0.f);
       a.r[int64_t(b) * a.C + c] = r;
-      a.y[int64_t(b) * a.C + c] = fmaf(r, sc, sh);
+      s1 += r; s2 += double(r) * r;
     }
-    return;
   }
-  double s1 = 0.0, s2 = 0.0;
-  for (int b = 0; b < a.B; ++b) {
-    const float r = fmaxf(a.z[int64_t(b) * a.C + c], 0.f);
-    a.r[int64_t(b) * a.C + c] = r;
-    s1 += r; s2 += double(r) * r;
+  sred[threadIdx.y][0][threadIdx.x] = s1;
+  sred[threadIdx.y][1][threadIdx.x] = s2;
+  __syncthreads();
+  if (threadIdx.y == 0 && live) {
+    float sc, sh;
+    if (a.training) {
+      s1 = 0.0; s2 = 0.0;
+      for (int k = 0; k < SEG_Y; ++k) { s1 += sred[k][0][threadIdx.x]; s2 += sred[k][1][threadIdx.x]; }
+      const double mean = s1 / a.B;
+      double var = s2 / a.B - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const double inv = 1.0 / sqrt(var + double(a.eps));
+      sc = float(double(a.gamma[c]) * inv);
+      sh = float(double(a.beta[c]) - mean * double(a.gamma[c]) * inv);
+      a.mean[c] = float(mean);
+      a.inv[c] = float(inv);
+      a.moving_mean[c] = float(double(a.moving_mean[c]) * double(a.decay) + mean * (1.0 - double(a.decay)));
+      a.moving_var[c] = float(double(a.moving_var[c]) * double(a.decay) + var * (1.0 - double(a.decay)));
+    } else {                                   // evaluation branch: moving statistics, nothing updated (tf_block.py:25-26)
+      sc = a.gamma[c] * (1.0f / sqrtf(a.moving_var[c] + a.eps));
+      sh = a.beta[c] - a.moving_mean[c] * sc;
+    }
+    s_sc[threadIdx.x] = sc;
+    s_sh[threadIdx.x] = sh;
   }
-  const double mean = s1 / a.B;
-  double var = s2 / a.B - mean * mean;
-  if (var < 0.0) var = 0.0;
-  const double inv = 1.0 / sqrt(var + double(a.eps));
-  const float sc = float(double(a.gamma[c]) * inv), sh = float(double(a.beta[c]) - mean * double(a.gamma[c]) * inv);
-  for (int b = 0; b < a.B; ++b) a.y[int64_t(b) * a.C + c] = fmaf(a.r[int64_t(b) * a.C + c], sc, sh);
-  a.mean[c] = float(mean);
-  a.inv[c] = float(inv);
-  a.moving_mean[c] = float(double(a.moving_mean[c]) * double(a.decay) + mean * (1.0 - double(a.decay)));
-  a.moving_var[c] = float(double(a.moving_var[c]) * double(a.decay) + var * (1.0 - double(a.decay)));
+  __syncthreads();
+  if (!live) return;
+  const float sc = s_sc[threadIdx.x], sh = s_sh[threadIdx.x];
+  for (int b = threadIdx.y; b < a.B; b += SEG_Y) a.y[int64_t(b) * a.C + c] = fmaf(a.r[int64_t(b) * a.C + c], sc, sh);
 }
 struct SegBnBwdArgs {
   const float* dy; const float* r; int32_t B, C;
   const float* gamma; const float* mean; const float* inv;
   float* dz; float* d_gamma; float* d_beta; float* d_bias;
 };
-__global__ void __launch_bounds__(128) seg_relu_bn_bwd_kernel(const SegBnBwdArgs a) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= a.C) return;
-  const double mu = a.mean[c], inv = a.inv[c], g = a.gamma[c];
+__global__ void __launch_bounds__(256) seg_relu_bn_bwd_kernel(const SegBnBwdArgs a) {   // block (32, SEG_Y)
+  __shared__ double sred[SEG_Y][2][32];
+  __shared__ double s_tot[2][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool live = c < a.C;
+  const double mu = live ? a.mean[c] : 0.0, inv = live ? a.inv[c] : 0.0, g = live ? a.gamma[c] : 0.0;
   double dbeta = 0.0, dgamma = 0.0;
-  for (int b = 0; b < a.B; ++b) {
-    const double dy = a.dy[int64_t(b) * a.C + c], rh = (double(a.r[int64_t(b) * a.C + c]) - mu) * inv;
-    dbeta += dy; dgamma += dy * rh;
+  if (live) {
+    for (int b = threadIdx.y; b < a.B; b += SEG_Y) {
+      const double dy = a.dy[int64_t(b) * a.C + c], rh = (double(a.r[int64_t(b) * a.C + c]) - mu) * inv;
+      dbeta += dy; dgamma += dy * rh;
+    }
   }
+  sred[threadIdx.y][0][threadIdx.x] = dbeta;
+  sred[threadIdx.y][1][threadIdx.x] = dgamma;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    dbeta = 0.0; dgamma = 0.0;
+    for (int k = 0; k < SEG_Y; ++k) { dbeta += sred[k][0][threadIdx.x]; dgamma += sred[k][1][threadIdx.x]; }
+    s_tot[0][threadIdx.x] = dbeta;
+    s_tot[1][threadIdx.x] = dgamma;
+  }
+  __syncthreads();
+  dbeta = s_tot[0][threadIdx.x]; dgamma = s_tot[1][threadIdx.x];
   double db = 0.0;
-  for (int b = 0; b < a.B; ++b) {
-    const double r = a.r[int64_t(b) * a.C + c];
-    const double dy = a.dy[int64_t(b) * a.C + c], rh = (r - mu) * inv;
-    const double dr = g * inv * (dy - dbeta / a.B - rh * dgamma / a.B);
-    const float dz = r > 0.0 ? float(dr) : 0.f;
-    a.dz[int64_t(b) * a.C + c] = dz;
-    db += dz;
+  if (live) {
+    for (int b = threadIdx.y; b < a.B; b += SEG_Y) {
+      const double r = a.r[int64_t(b) * a.C + c];
+      const double dy = a.dy[int64_t(b) * a.C + c], rh = (r - mu) * inv;
+      const double dr = g * inv * (dy - dbeta / a.B - rh * dgamma / a.B);
+      const float dz = r > 0.0 ? float(dr) : 0.f;
+      a.dz[int64_t(b) * a.C + c] = dz;
+      db += dz;
+    }
   }
-  a.d_gamma[c] = float(dgamma);
-  a.d_beta[c] = float(dbeta);
-  a.d_bias[c] = float(db);
+  __syncthreads();
+  sred[threadIdx.y][0][threadIdx.x] = db;
+  __syncthreads();
+  if (threadIdx.y == 0 && live) {
+    db = 0.0;
+    for (int k = 0; k < SEG_Y; ++k) db += sred[k][0][threadIdx.x];
+    a.d_gamma[c] = float(dgamma);
+    a.d_beta[c] = float(dbeta);
+    a.d_bias[c] = float(db);
+  }
 }
 
 // Softmax cross-entropy of one row per CTA (models.py:512): loss_row, correct (argmax == label, first maximum as
@@ -572,34 +641,26 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   p[i] -= lr_t * mi / (sqrtf(vi) + eps);
 }
 
-// fp32 master conv weights W[taps][c_in][c_out] -> fp16 forward operand wf[c_out][k_total], K index = tap*c_in_pad + ci
-// (32 x 32 tile transposed through shared memory; grid (c_out/32, ceil(c_in/32), taps), block (32, 8))
+// fp32 master conv weights W[taps][c_in][c_out] -> the two fp16 operand copies, one 32 x 32 tile per CTA
+// (grid (c_out/32, ceil(c_in/32), taps), block (32, 8)):
+//   forward       wf[c_out][k_total], K index = tap*c_in_pad + ci          (transposed through shared memory)
+//   data gradient wd[c_in][tap'*c_out + co] = W[taps-1-tap'][c_in][co]     (the conv of dz with the flipped kernel; may be null)
 __global__ void __launch_bounds__(256)
-repack_fwd_kernel(const float* __restrict__ W, int32_t c_in, int32_t c_out, int32_t c_in_pad, int32_t k_total, __half* __restrict__ wf) {
+repack_kernel(const float* __restrict__ W, int32_t taps, int32_t c_in, int32_t c_out, int32_t c_in_pad, int32_t k_total,
+              __half* __restrict__ wf, __half* __restrict__ wd) {
   __shared__ float tile[32][33];
   const int o0 = blockIdx.x * 32, c0 = blockIdx.y * 32, j = blockIdx.z;
   for (int i = threadIdx.y; i < 32; i += 8) {
     const int c = c0 + i;
-    tile[i][threadIdx.x] = c < c_in ? W[(int64_t(j) * c_in + c) * c_out + o0 + threadIdx.x] : 0.f;
+    const float w = c < c_in ? W[(int64_t(j) * c_in + c) * c_out + o0 + threadIdx.x] : 0.f;
+    tile[i][threadIdx.x] = w;
+    if (wd != nullptr && c < c_in) wd[(int64_t(c) * taps + (taps - 1 - j)) * c_out + o0 + threadIdx.x] = __float2half_rn(w);
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += 8) {
     const int c = c0 + threadIdx.x;
     if (c < c_in) wf[int64_t(o0 + i) * k_total + int64_t(j) * c_in_pad + c] = __float2half_rn(tile[threadIdx.x][i]);
   }
-}
-// data-gradient operand wd[c_in][tap'*c_out + co] = W[taps-1-tap'][c_in][co]  (the conv of dz with the flipped kernel)
-__global__ void __launch_bounds__(256)
-repack_dgrad_kernel(const float* __restrict__ W, int32_t taps, int32_t c_in, int32_t c_out, __half* __restrict__ wd) {
-  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;      // pairs of output elements
-  const int64_t n2 = int64_t(taps) * c_in * c_out / 2;
-  if (i >= n2) return;
-  const int64_t e = i * 2;
-  const int co = int(e % c_out);
-  const int jp = int((e / c_out) % taps);
-  const int ci = int(e / (int64_t(c_out) * taps));
-  const float2 w = *reinterpret_cast<const float2*>(W + (int64_t(taps - 1 - jp) * c_in + ci) * c_out + co);
-  *reinterpret_cast<__half2*>(wd + e) = __floats2half2_rn(w.x, w.y);
 }
 
 __global__ void __launch_bounds__(256) fill_kernel(float* p, int64_t n, float v) {
