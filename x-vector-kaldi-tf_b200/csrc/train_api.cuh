@@ -98,6 +98,13 @@ int tr_launch_check(xv_trainer* t) {
     int prc_ = prof_mark(t->m, stream);                                    \
     if (prc_ != XV_OK) return prc_;                                        \
   } while (0)
+// launch + count; programmatic dependent launch (every kernel starts with cudaGridDependencySynchronize()) unless profiling
+#define TR_LAUNCH(name, kernel, grid, block, smem, ...)                                                            \
+  do {                                                                                                             \
+    TR_BEGIN(name);                                                                                                \
+    TR_CUDA(launch_k(t->m->opt_pdl != 0 && !t->m->opt_profile, kernel, grid, block, smem, stream, __VA_ARGS__));   \
+    TR_END();                                                                                                      \
+  } while (0)
 #define TR_END()                                                           \
   do {                                                                     \
     int prc_ = prof_mark(t->m, stream);                                    \
@@ -185,6 +192,7 @@ int tr_ensure_workspace(xv_trainer* t, int32_t n_seg, int32_t seg_len) {
   t->sg_partial_floats = sg;
   want(reinterpret_cast<void**>(&t->sg_partial), std::max<size_t>(sg, 1) * 4);
   TR_CUDA(cudaMalloc(reinterpret_cast<void**>(&t->ws), off));
+  TR_CUDA(cudaMemset(t->ws, 0, off));       // rows past the last segment are never written by the elementwise kernels: exact zeros
   for (auto& c : carve) *c.first = t->ws + c.second;
   t->n_seg = n_seg;
   t->seg_len = seg_len;
@@ -237,9 +245,10 @@ int tr_pair_layer(xv_trainer* t, cudaStream_t stream, const char* name, const __
   a.c_chunks = c_in_gemm / (2 * tdnn2::BLOCK_K);
   const int64_t tiles = int64_t(a.n_row_tiles) * a.n_ch_tiles;
   const int grid = 2 * int(std::min<int64_t>(tiles, m->num_clusters));
+  const bool pdl = m->opt_pdl != 0 && !m->opt_profile;
   TR_BEGIN(name);
-  if (alpha) TR_CUDA(launch_k(false, tdnn2::tdnn_pair_kernel<0, 2, true>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
-  else TR_CUDA(launch_k(false, tdnn2::tdnn_pair_kernel<0, 2, false>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
+  if (alpha) TR_CUDA(launch_k(pdl, tdnn2::tdnn_pair_kernel<0, 2, true>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
+  else TR_CUDA(launch_k(pdl, tdnn2::tdnn_pair_kernel<0, 2, false>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
   TR_END();
   return XV_OK;
 }
@@ -271,13 +280,12 @@ int tr_wgrad(xv_trainer* t, cudaStream_t stream, const char* name, const TrFrame
   if (need > t->wg_partial_floats) return fail(XV_ESTATE, "wgrad partial buffer too small");
   const int items = a.k_splits * a.taps * a.n_mt * a.n_nt;
   const int grid = 2 * std::min(items, m->num_clusters);
+  const bool pdl = m->opt_pdl != 0 && !m->opt_profile;
   TR_BEGIN(name);
-  TR_CUDA(launch_k(false, wgrad::wgrad_pair_kernel, dim3(grid), dim3(wgrad::NUM_THREADS), wgrad::SMEM_BYTES, stream, tx, tz, a));
+  TR_CUDA(launch_k(pdl, wgrad::wgrad_pair_kernel, dim3(grid), dim3(wgrad::NUM_THREADS), wgrad::SMEM_BYTES, stream, tx, tz, a));
   TR_END();
   const int64_t n4 = int64_t(a.taps) * a.c_in * a.c_out / 4;
-  TR_BEGIN("wgrad_reduce_kernel");
-  wgrad::wgrad_reduce_kernel<<<unsigned((n4 + 255) / 256), 256, 0, stream>>>(t->wg_partial, grad_w, n4, a.k_splits, inv_loss_scale);
-  TR_END();
+  TR_LAUNCH("wgrad_reduce_kernel", wgrad::wgrad_reduce_kernel, dim3(unsigned((n4 + 255) / 256)), dim3(256), 0, t->wg_partial, grad_w, n4, a.k_splits, inv_loss_scale);
   return XV_OK;
 }
 
@@ -294,32 +302,36 @@ int tr_sgemm(xv_trainer* t, cudaStream_t stream, const char* name, const float* 
   a.partial = t->sg_partial;
   const dim3 grid((N + 63) / 64, (M + 63) / 64, sp.splits);
   const bool ak = sak == 1, bn = sbn == 1;
+  const bool pdl = t->m->opt_pdl != 0 && !t->m->opt_profile;
   TR_BEGIN(name);
-  if (ak && bn) trk::sgemm64_kernel<true, true><<<grid, 256, 0, stream>>>(a);
-  else if (!ak && bn) trk::sgemm64_kernel<false, true><<<grid, 256, 0, stream>>>(a);
-  else if (ak && !bn) trk::sgemm64_kernel<true, false><<<grid, 256, 0, stream>>>(a);
+  if (ak && bn) TR_CUDA(launch_k(pdl, trk::sgemm64_kernel<true, true>, grid, dim3(256), 0, stream, a));
+  else if (!ak && bn) TR_CUDA(launch_k(pdl, trk::sgemm64_kernel<false, true>, grid, dim3(256), 0, stream, a));
+  else if (ak && !bn) TR_CUDA(launch_k(pdl, trk::sgemm64_kernel<true, false>, grid, dim3(256), 0, stream, a));
   else return fail(XV_EINVAL, "sgemm: unsupported operand strides");
   TR_END();
   if (sp.splits > 1) {
     const int64_t n = int64_t(M) * N;
-    TR_BEGIN("splitk_reduce_kernel");
-    trk::splitk_reduce_kernel<<<unsigned((n + 255) / 256), 256, 0, stream>>>(t->sg_partial, sp.splits, M, N, bias, C, ldc);
-    TR_END();
+    TR_LAUNCH("splitk_reduce_kernel", trk::splitk_reduce_kernel, dim3(unsigned((n + 255) / 256)), dim3(256), 0,
+              static_cast<const float*>(t->sg_partial), sp.splits, M, N, bias, C, ldc);
   }
   return XV_OK;
 }
 
 // fp32 master weights -> fp16 operand copies of every frame layer
 int tr_repack(xv_trainer* t, cudaStream_t stream) {
+  trk::RepackTable tb{};
+  int tiles = 0;
+  tb.n_layers = int(t->frames.size());
   for (size_t i = 0; i < t->frames.size(); ++i) {
     TrFrame& L = t->frames[i];
-    const float* W = t->params + L.off_w;
-    const int c_in_pad = (i == 0) ? L.c_in : L.c_in_gemm;          // first layer: densely spliced K index tap*D + c
-    TR_BEGIN("repack_kernel");
-    trk::repack_kernel<<<dim3(L.c_out / 32, (L.c_in + 31) / 32, L.taps), dim3(32, 8), 0, stream>>>(W, L.taps, L.c_in, L.c_out, c_in_pad, L.k_total,
-                                                                                                L.wf, i > 0 ? L.wd : nullptr);
-    TR_END();
+    trk::RepackLayer& R = tb.layer[i];
+    R.W = t->params + L.off_w; R.wf = L.wf; R.wd = i > 0 ? L.wd : nullptr;
+    R.taps = L.taps; R.c_in = L.c_in; R.c_out = L.c_out; R.k_total = L.k_total;
+    R.c_in_pad = (i == 0) ? L.c_in : L.c_in_gemm;          // first layer: densely spliced K index tap*D + c
+    R.tile_begin = tiles;
+    tiles += (L.c_out / 32) * ((L.c_in + 31) / 32) * L.taps;
   }
+  TR_LAUNCH("repack_kernel", trk::repack_kernel, dim3(tiles), dim3(32, 8), 0, tb);
   t->operands_dirty = false;
   return XV_OK;
 }
@@ -522,7 +534,8 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
   if (t->operands_dirty) { rc = tr_repack(t, stream); if (rc != XV_OK) return rc; }
   const int nl = int(t->frames.size());
   const int64_t r_pad = t->r_pad;
-  const int32_t n_blk = int32_t(r_pad / 32);
+  constexpr int32_t ROWS_PER_PART = 128;                              // frame layers: rows per partial-sum CTA
+  const int32_t n_part = int32_t(r_pad / ROWS_PER_PART);
   const float n_rows = float(int64_t(n_seg) * seg_len);
   double S = t->opt_loss_scale;
   if (S <= 0.0) { S = 1.0; while (S < 8.0 * double(n_rows)) S *= 2.0; }
@@ -551,9 +564,7 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
     a.lut = m->pack_lut_dev;
     a.counters = nullptr;
     a.n_counters = 0;
-    TR_BEGIN("pack_im2col_kernel");
-    xvk::pack_im2col_kernel<<<unsigned(r_pad / xvk::PACK_ROWS_PER_BLOCK), xvk::PACK_THREADS, 0, stream>>>(a);
-    TR_END();
+    TR_LAUNCH("pack_im2col_kernel", xvk::pack_im2col_kernel, dim3(unsigned(r_pad / xvk::PACK_ROWS_PER_BLOCK)), dim3(xvk::PACK_THREADS), 0, a);
   }
 
   // ---- frame layers, training branch of BatchNorm ---------------------------------------------------
@@ -563,19 +574,14 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
     TrFrame& L = t->frames[i];
     float* scale = L.bn + 2 * L.c_out;
     float* shift = L.bn + 3 * L.c_out;
-    TR_BEGIN("bn_fold_kernel");
-    trk::bn_fold_kernel<<<(L.c_out + 255) / 256, 256, 0, stream>>>(t->params + L.off_gamma, t->params + L.off_beta, t->moving + L.off_mov,
-                                                                 t->moving + L.off_mov + L.c_out, m->topo.bn_eps, L.c_out, scale, shift);
-    TR_END();
+    TR_LAUNCH("bn_fold_kernel", trk::bn_fold_kernel, dim3((L.c_out + 255) / 256), dim3(256), 0, t->params + L.off_gamma, t->params + L.off_beta, t->moving + L.off_mov, t->moving + L.off_mov + L.c_out, m->topo.bn_eps, L.c_out, scale, shift);
     __half* out = (i < nl - 1) ? L.y : L.r;
     rc = tr_pair_layer(t, stream, "tdnn_pair_kernel[fwd]", in, L.c_in_gemm, out, L.c_out, L.wf, L.k_total, L.gemm_taps, L.dil,
                        t->params + L.off_b, scale, shift, nullptr);
     if (rc != XV_OK) return rc;
     in = out;
     if (i == nl - 1) {
-      TR_BEGIN("blk_col_sums_kernel<0>");
-      trk::blk_col_sums_kernel<0><<<dim3(n_blk, L.c_out / trk::COLS_PER_CTA), 256, 0, stream>>>(out, nullptr, L.c_out, t->partial);
-      TR_END();
+      TR_LAUNCH("blk_col_sums_kernel<0>", trk::blk_col_sums_kernel<0>, dim3(n_seg, L.c_out / trk::COLS_PER_CTA), dim3(256), 0, static_cast<const __half*>(out), static_cast<const __half*>(nullptr), L.c_out, t->seg_stride, t->partial);
     }
   }
   for (int i = 0; i < nl && training; ++i) {
@@ -583,23 +589,20 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
     rc = tr_pair_layer(t, stream, "tdnn_pair_kernel[fwd]", in, L.c_in_gemm, L.r, L.c_out, L.wf, L.k_total, L.gemm_taps, L.dil,
                        t->params + L.off_b, t->ones, t->zeros, nullptr);
     if (rc != XV_OK) return rc;
-    TR_BEGIN("blk_col_sums_kernel<0>");
-    trk::blk_col_sums_kernel<0><<<dim3(n_blk, L.c_out / trk::COLS_PER_CTA), 256, 0, stream>>>(L.r, nullptr, L.c_out, t->partial);
-    TR_END();
+    // the last layer sums per segment (= the pooling sums), the others per 128 rows
+    const bool last = i == nl - 1;
+    const int32_t parts = last ? n_seg : n_part;
+    TR_LAUNCH("blk_col_sums_kernel<0>", trk::blk_col_sums_kernel<0>, dim3(parts, L.c_out / trk::COLS_PER_CTA), dim3(256), 0, static_cast<const __half*>(L.r), static_cast<const __half*>(nullptr), L.c_out, last ? t->seg_stride : ROWS_PER_PART, t->partial);
     trk::BnFwdArgs b{};
-    b.partial = t->partial; b.n_blk = n_blk; b.C = L.c_out; b.n_rows = n_rows;
+    b.partial = t->partial; b.n_blk = parts; b.C = L.c_out; b.n_rows = n_rows;
     b.eps = m->topo.bn_eps; b.decay = BN_DECAY;
     b.gamma = t->params + L.off_gamma; b.beta = t->params + L.off_beta;
     b.moving_mean = t->moving + L.off_mov; b.moving_var = t->moving + L.off_mov + L.c_out;
     b.mean = L.bn; b.inv = L.bn + L.c_out; b.scale = L.bn + 2 * L.c_out; b.shift = L.bn + 3 * L.c_out;
-    TR_BEGIN("bn_fwd_finalize_kernel");
-    trk::bn_fwd_finalize_kernel<<<L.c_out / 32, dim3(32, trk::RED_Y), 0, stream>>>(b);
-    TR_END();
+    TR_LAUNCH("bn_fwd_finalize_kernel", trk::bn_fwd_finalize_kernel, dim3(L.c_out / 32), dim3(dim3(32, trk::RED_Y)), 0, b);
     if (i < nl - 1) {
       const int64_t n8 = r_pad * L.c_out / 8;
-      TR_BEGIN("bn_apply_kernel");
-      trk::bn_apply_kernel<<<unsigned((n8 + 255) / 256), 256, 0, stream>>>(L.r, t->row_valid, b.scale, b.shift, n8, L.c_out / 8, L.y, m->overflow_dev);
-      TR_END();
+      TR_LAUNCH("bn_apply_kernel", trk::bn_apply_kernel, dim3(unsigned((n8 + 255) / 256)), dim3(256), 0, L.r, t->row_valid, b.scale, b.shift, n8, L.c_out / 8, L.y, m->overflow_dev);
       in = L.y;
     }
   }
@@ -607,14 +610,12 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
   const int C = LL.c_out;
   {
     trk::PoolFwdArgs a{};
-    a.partial = t->partial; a.C = C; a.n_seg = n_seg; a.blks_per_seg = t->seg_stride / 32;
+    a.partial = t->partial; a.C = C; a.n_seg = n_seg; a.blks_per_seg = 1;
     a.seg_len = float(seg_len); a.var_eps = m->topo.var_eps;
     a.scale = training ? LL.bn + 2 * C : t->ones;           // evaluation: the block sums are already those of y
     a.shift = training ? LL.bn + 3 * C : t->zeros;
     a.m_r = t->m_r; a.v_r = t->v_r; a.h0 = t->h0;
-    TR_BEGIN("pool_train_fwd_kernel");
-    trk::pool_train_fwd_kernel<<<dim3((C + 255) / 256, n_seg), 256, 0, stream>>>(a);
-    TR_END();
+    TR_LAUNCH("pool_train_fwd_kernel", trk::pool_train_fwd_kernel, dim3(dim3((C + 255) / 256, n_seg)), dim3(256), 0, a);
   }
 
   // ---- segment level forward (fp32) ---------------------------------------------------------------
@@ -630,30 +631,22 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
     a.moving_mean = t->moving + Sg.off_mov; a.moving_var = t->moving + Sg.off_mov + Sg.out;
     a.r = Sg.r; a.y = Sg.y; a.mean = Sg.bn; a.inv = Sg.bn + Sg.out;
     a.training = training ? 1 : 0;
-    TR_BEGIN("seg_relu_bn_fwd_kernel");
-    trk::seg_relu_bn_fwd_kernel<<<(Sg.out + 31) / 32, dim3(32, trk::SEG_Y), 0, stream>>>(a);
-    TR_END();
+    TR_LAUNCH("seg_relu_bn_fwd_kernel", trk::seg_relu_bn_fwd_kernel, dim3((Sg.out + 31) / 32), dim3(dim3(32, trk::SEG_Y)), 0, a);
     hin = Sg.y;
   }
   const int NC = t->num_classes, E1 = t->seg[1].out;
   rc = tr_sgemm(t, stream, "sgemm64_kernel[fwd]", t->seg[1].y, t->params + t->off_wo, t->logits, t->params + t->off_bo, n_seg, NC, E1,
                 E1, 1, NC, 1, NC);
   if (rc != XV_OK) return rc;
-  TR_BEGIN("softmax_ce_kernel");
-  trk::softmax_ce_kernel<<<n_seg, 256, 0, stream>>>(t->logits, labels_dev, NC, 1.f / float(n_seg), t->dlogits, t->loss_row, t->correct);
-  TR_END();
-  TR_BEGIN("loss_finalize_kernel");
-  trk::loss_finalize_kernel<<<1, 32, 0, stream>>>(t->loss_row, t->correct, n_seg, loss_acc_dev);
-  TR_END();
+  TR_LAUNCH("softmax_ce_kernel", trk::softmax_ce_kernel, dim3(n_seg), dim3(256), 0, t->logits, labels_dev, NC, 1.f / float(n_seg), t->dlogits, t->loss_row, t->correct);
+  TR_LAUNCH("loss_finalize_kernel", trk::loss_finalize_kernel, dim3(1), dim3(32), 0, t->loss_row, t->correct, n_seg, loss_acc_dev);
   if (!training) { t->debug.clear(); return XV_OK; }
 
   // ---- segment level backward -----------------------------------------------------------------------
   // output layer: dWo = y6^T dlogits, dbo = colsum(dlogits), dy6 = dlogits Wo^T
   rc = tr_sgemm(t, stream, "sgemm64_kernel[dW]", t->seg[1].y, t->dlogits, grad + t->off_wo, nullptr, E1, NC, n_seg, 1, E1, NC, 1, NC);
   if (rc != XV_OK) return rc;
-  TR_BEGIN("colsum_rows_kernel");
-  trk::colsum_rows_kernel<<<(NC + 255) / 256, 256, 0, stream>>>(t->dlogits, n_seg, NC, grad + t->off_bo);
-  TR_END();
+  TR_LAUNCH("colsum_rows_kernel", trk::colsum_rows_kernel, dim3((NC + 255) / 256), dim3(256), 0, t->dlogits, n_seg, NC, grad + t->off_bo);
   rc = tr_sgemm(t, stream, "sgemm64_kernel[dX]", t->dlogits, t->params + t->off_wo, t->seg[1].dy, nullptr, n_seg, E1, NC, NC, 1, 1, NC, E1);
   if (rc != XV_OK) return rc;
   for (int i = 1; i >= 0; --i) {
@@ -662,9 +655,7 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
     a.dy = Sg.dy; a.r = Sg.r; a.B = n_seg; a.C = Sg.out;
     a.gamma = t->params + Sg.off_gamma; a.mean = Sg.bn; a.inv = Sg.bn + Sg.out;
     a.dz = Sg.dz; a.d_gamma = grad + Sg.off_gamma; a.d_beta = grad + Sg.off_beta; a.d_bias = grad + Sg.off_b;
-    TR_BEGIN("seg_relu_bn_bwd_kernel");
-    trk::seg_relu_bn_bwd_kernel<<<(Sg.out + 31) / 32, dim3(32, trk::SEG_Y), 0, stream>>>(a);
-    TR_END();
+    TR_LAUNCH("seg_relu_bn_bwd_kernel", trk::seg_relu_bn_bwd_kernel, dim3((Sg.out + 31) / 32), dim3(dim3(32, trk::SEG_Y)), 0, a);
     const float* xin = (i == 1) ? t->seg[0].y : t->h0;
     float* dxin = (i == 1) ? t->seg[0].dy : t->dh0;
     rc = tr_sgemm(t, stream, "sgemm64_kernel[dW]", xin, Sg.dz, grad + Sg.off_w, nullptr, Sg.in, Sg.out, n_seg, 1, Sg.in, Sg.out, 1, Sg.out);
@@ -680,16 +671,9 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
     a.seg_len = float(seg_len); a.var_eps = m->topo.var_eps; a.loss_scale = float(S);
     a.gamma = t->params + LL.off_gamma; a.mean = LL.bn; a.inv = LL.bn + C; a.scale = LL.bn + 2 * C;
     a.coefA = t->coefA; a.coefG = t->coefG; a.d_gamma = grad + LL.off_gamma; a.d_beta = grad + LL.off_beta;
-    TR_BEGIN("pool_bwd_coef_kernel");
-    trk::pool_bwd_coef_kernel<<<(C + 31) / 32, dim3(32, trk::SEG_Y), 0, stream>>>(a);
-    TR_END();
-    TR_BEGIN("pool_relu_bwd_kernel");
-    trk::pool_relu_bwd_kernel<<<dim3(n_blk, C / trk::COLS_PER_CTA), 256, 0, stream>>>(LL.r, C, t->seg_stride / 32, n_seg, t->coefA, t->coefG,
-                                                                                   LL.dz, t->partial1, m->overflow_dev);
-    TR_END();
-    TR_BEGIN("colsum_finalize_kernel");
-    trk::colsum_finalize_kernel<<<C / 32, dim3(32, trk::RED_Y), 0, stream>>>(t->partial1, n_blk, C, inv_S, grad + LL.off_b);
-    TR_END();
+    TR_LAUNCH("pool_bwd_coef_kernel", trk::pool_bwd_coef_kernel, dim3((C + 31) / 32), dim3(dim3(32, trk::SEG_Y)), 0, a);
+    TR_LAUNCH("pool_relu_bwd_kernel", trk::pool_relu_bwd_kernel, dim3(n_seg, C / trk::COLS_PER_CTA), dim3(256), 0, static_cast<const __half*>(LL.r), C, t->seg_stride, static_cast<const float*>(t->coefA), static_cast<const float*>(t->coefG), LL.dz, t->partial1, m->overflow_dev);
+    TR_LAUNCH("colsum_finalize_kernel", trk::colsum_finalize_kernel, dim3(C / 32), dim3(32, trk::RED_Y), 0, static_cast<const float*>(t->partial1), n_seg, C, inv_S, grad + LL.off_b);
   }
 
   // ---- frame layers backward ---------------------------------------------------------------------------
@@ -697,24 +681,15 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
     TrFrame& L = t->frames[i];
     if (i < nl - 1) {
       // dy_i (written by the data gradient of layer i+1) -> BatchNorm + ReLU backward -> dz_i
-      TR_BEGIN("blk_col_sums_kernel<1>");
-      trk::blk_col_sums_kernel<1><<<dim3(n_blk, L.c_out / trk::COLS_PER_CTA), 256, 0, stream>>>(L.dy, L.r, L.c_out, t->partial);
-      TR_END();
+      TR_LAUNCH("blk_col_sums_kernel<1>", trk::blk_col_sums_kernel<1>, dim3(n_part, L.c_out / trk::COLS_PER_CTA), dim3(256), 0, static_cast<const __half*>(L.dy), static_cast<const __half*>(L.r), L.c_out, ROWS_PER_PART, t->partial);
       trk::BnBwdArgs b{};
-      b.partial = t->partial; b.n_blk = n_blk; b.C = L.c_out; b.n_rows = n_rows; b.inv_loss_scale = inv_S;
+      b.partial = t->partial; b.n_blk = n_part; b.C = L.c_out; b.n_rows = n_rows; b.inv_loss_scale = inv_S;
       b.gamma = t->params + L.off_gamma; b.mean = L.bn; b.inv = L.bn + L.c_out;
       b.cA = t->cA; b.cB = t->cB; b.cC = t->cC;
       b.d_gamma = grad + L.off_gamma; b.d_beta = grad + L.off_beta;
-      TR_BEGIN("bn_bwd_finalize_kernel");
-      trk::bn_bwd_finalize_kernel<<<L.c_out / 32, dim3(32, trk::RED_Y), 0, stream>>>(b);
-      TR_END();
-      TR_BEGIN("bn_relu_bwd_kernel");
-      trk::bn_relu_bwd_kernel<<<dim3(n_blk, L.c_out / trk::COLS_PER_CTA), 256, 0, stream>>>(L.dy, L.r, L.c_out, t->cA, t->cB, t->cC, L.dz,
-                                                                                         t->partial1, m->overflow_dev);
-      TR_END();
-      TR_BEGIN("colsum_finalize_kernel");
-      trk::colsum_finalize_kernel<<<L.c_out / 32, dim3(32, trk::RED_Y), 0, stream>>>(t->partial1, n_blk, L.c_out, inv_S, grad + L.off_b);
-      TR_END();
+      TR_LAUNCH("bn_bwd_finalize_kernel", trk::bn_bwd_finalize_kernel, dim3(L.c_out / 32), dim3(dim3(32, trk::RED_Y)), 0, b);
+      TR_LAUNCH("bn_relu_bwd_kernel", trk::bn_relu_bwd_kernel, dim3(n_part, L.c_out / trk::COLS_PER_CTA), dim3(256), 0, static_cast<const __half*>(L.dy), static_cast<const __half*>(L.r), L.c_out, ROWS_PER_PART, static_cast<const float*>(t->cA), static_cast<const float*>(t->cB), static_cast<const float*>(t->cC), L.dz, t->partial1, m->overflow_dev);
+      TR_LAUNCH("colsum_finalize_kernel", trk::colsum_finalize_kernel, dim3(L.c_out / 32), dim3(32, trk::RED_Y), 0, static_cast<const float*>(t->partial1), n_part, L.c_out, inv_S, grad + L.off_b);
     }
     const __half* x = (i == 0) ? t->x0 : t->frames[i - 1].y;
     rc = tr_wgrad(t, stream, "wgrad_pair_kernel", L, x, L.dz, grad + L.off_w, inv_S);
@@ -770,10 +745,7 @@ int xv_train_apply(xv_trainer* t, const float* grad_dev, float learning_rate, fl
   t->step += 1;
   const double b1t = std::pow(double(ADAM_B1), double(t->step)), b2t = std::pow(double(ADAM_B2), double(t->step));
   const float lr_t = float(double(learning_rate) * std::sqrt(1.0 - b2t) / (1.0 - b1t));
-  TR_BEGIN("adam_kernel");
-  trk::adam_kernel<<<unsigned((t->n_params + 255) / 256), 256, 0, stream>>>(t->params, g, t->adam_m, t->adam_v, t->n_params, lr_t, ADAM_B1,
-                                                                           ADAM_B2, ADAM_EPS, grad_scale);
-  TR_END();
+  TR_LAUNCH("adam_kernel", trk::adam_kernel, dim3(unsigned((t->n_params + 255) / 256)), dim3(256), 0, t->params, g, t->adam_m, t->adam_v, t->n_params, lr_t, ADAM_B1, ADAM_B2, ADAM_EPS, grad_scale);
   return tr_repack(t, stream);
 }
 

@@ -42,29 +42,34 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Column sums of one aligned 32-row block x 256 channels per CTA.
-//   OP 0: partial[blk][0][c] = sum x,        partial[blk][1][c] = sum x*x
-//   OP 1: partial[blk][0][c] = sum x (= dy), partial[blk][1][c] = sum x*y (= dy * r)
-// Gap rows hold exact zeros in every tensor this is applied to, so no row mask is needed.
+// Column sums of `rows_per_cta` rows (a multiple of 32) x 256 channels per CTA -> ONE partial row per CTA.
+//   OP 0: partial[part][0][c] = sum x,        partial[part][1][c] = sum x*x
+//   OP 1: partial[part][0][c] = sum x (= dy), partial[part][1][c] = sum x*y (= dy * r)
+// Gap rows hold exact zeros in every tensor this is applied to, so no row mask is needed.  The frame layers use 128
+// rows per CTA; the last layer uses one CTA per segment, so that its partial rows are the pooling sums (models.py:485).
 template <int OP>
 __global__ void __launch_bounds__(256)
-blk_col_sums_kernel(const __half* __restrict__ x, const __half* __restrict__ y, int32_t C, float* __restrict__ partial) {
+blk_col_sums_kernel(const __half* __restrict__ x, const __half* __restrict__ y, int32_t C, int32_t rows_per_cta, float* __restrict__ partial) {
+  cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
+  cudaGridDependencySynchronize();
   __shared__ float red[8][2][COLS_PER_CTA];
-  const int blk = blockIdx.x, c0 = blockIdx.y * COLS_PER_CTA;
+  const int part = blockIdx.x, c0 = blockIdx.y * COLS_PER_CTA;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float s1[8], s2[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+  for (int r0 = 0; r0 < rows_per_cta; r0 += BLK_ROWS) {
 #pragma unroll
-  for (int rr = 0; rr < 4; ++rr) {
-    const int64_t off = (int64_t(blk) * BLK_ROWS + w * 4 + rr) * C + c0 + lane * 8;
-    float a[8], b[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(x + off)), a);
-    if (OP == 1) unpack8(__ldg(reinterpret_cast<const uint4*>(y + off)), b);
+    for (int rr = 0; rr < 4; ++rr) {
+      const int64_t off = (int64_t(part) * rows_per_cta + r0 + w * 4 + rr) * C + c0 + lane * 8;
+      float a[8], b[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + off)), a);
+      if (OP == 1) unpack8(__ldg(reinterpret_cast<const uint4*>(y + off)), b);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      s1[i] += a[i];
-      s2[i] = fmaf(a[i], OP == 1 ? b[i] : a[i], s2[i]);
+      for (int i = 0; i < 8; ++i) {
+        s1[i] += a[i];
+        s2[i] = fmaf(a[i], OP == 1 ? b[i] : a[i], s2[i]);
+      }
     }
   }
 #pragma unroll
@@ -74,8 +79,8 @@ blk_col_sums_kernel(const __half* __restrict__ x, const __half* __restrict__ y, 
   float a = 0.f, b = 0.f;
 #pragma unroll
   for (int k = 0; k < 8; ++k) { a += red[k][0][t]; b += red[k][1][t]; }
-  partial[(int64_t(blk) * 2 + 0) * C + c0 + t] = a;
-  partial[(int64_t(blk) * 2 + 1) * C + c0 + t] = b;
+  partial[(int64_t(part) * 2 + 0) * C + c0 + t] = a;
+  partial[(int64_t(part) * 2 + 1) * C + c0 + t] = b;
 }
 
 // Sum partial[blk][j][c] over blk for 32 channels per CTA (block 32 x RED_Y), fp64, fixed order.
@@ -125,6 +130,8 @@ struct BnFwdArgs {
   float* scale; float* shift;                // gamma*inv, beta - mean*gamma*inv   (tf.nn.batch_normalization)
 };
 __global__ void __launch_bounds__(1024) bn_fwd_finalize_kernel(const BnFwdArgs a) {
+  cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
+  cudaGridDependencySynchronize();
   __shared__ double sred[RED_Y][2][32];
   const int c = blockIdx.x * 32 + threadIdx.x;
   double s[2];
@@ -147,6 +154,8 @@ __global__ void __launch_bounds__(1024) bn_fwd_finalize_kernel(const BnFwdArgs a
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const __half* __restrict__ r, const uint8_t* __restrict__ row_valid, const float* __restrict__ scale,
                 const float* __restrict__ shift, int64_t n8, int32_t c8, __half* __restrict__ y, uint32_t* overflow_flag) {
+  cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
+  cudaGridDependencySynchronize();
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n8) return;
   const int64_t row = i / c8;
@@ -172,6 +181,8 @@ bn_apply_kernel(const __half* __restrict__ r, const uint8_t* __restrict__ row_va
 __global__ void __launch_bounds__(256)
 bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
                const float* __restrict__ var, float eps, int32_t C, float* __restrict__ scale, float* __restrict__ shift) {
+  cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
+  cudaGridDependencySynchronize();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float inv = (1.0f / sqrtf(var[c] + eps)) * gamma[c];
@@ -188,6 +199,8 @@ struct BnBwdArgs {
   float* d_gamma; float* d_beta;             // unscaled parameter gradients
 };
 __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const BnBwdArgs a) {
+  cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
+  cudaGridDependencySynchronize();
   __shared__ double sred[RED_Y][2][32];
   const int c = blockIdx.x * 32 + threadIdx.x;
   double s[2];
@@ -205,13 +218,15 @@ __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const BnBwdArgs a
   a.d_beta[c] = float(dbeta * double(a.inv_loss_scale));
 }
 
-// dz = (r > 0) ? cA*dy + cB*r + cC : 0 for one 32-row block x 256 channels; partial1[blk][c] = sum of dz (bias gradient)
+// dz = (r > 0) ? cA*dy + cB*r + cC : 0 for rows_per_cta rows x 256 channels; partial1[part][c] = sum of dz (bias gradient)
 __global__ void __launch_bounds__(256)
-bn_relu_bwd_kernel(const __half* __restrict__ dy, const __half* __restrict__ r, int32_t C, const float* __restrict__ cA,
+bn_relu_bwd_kernel(const __half* __restrict__ dy, const __half* __restrict__ r, int32_t C, int32_t rows_per_cta, const float* __restrict__ cA,
                    const float* __restrict__ cB, const float* __restrict__ cC, __half* __restrict__ dz,
                    float* __restrict__ partial1, uint32_t* overflow_flag) {
+  cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
+  cudaGridDependencySynchronize();
   __shared__ float red[8][COLS_PER_CTA];
-  const int blk = blockIdx.x, c0 = blockIdx.y * COLS_PER_CTA;
+  const int part = blockIdx.x, c0 = blockIdx.y * COLS_PER_CTA;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = c0 + lane * 8;
   float ka[8], kb[8], kc[8], s[8];
@@ -226,19 +241,21 @@ bn_relu_bwd_kernel(const __half* __restrict__ dy, const __half* __restrict__ r, 
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = 0.f;
   float mx = 0.f;
+  for (int r0 = 0; r0 < rows_per_cta; r0 += BLK_ROWS) {
 #pragma unroll
-  for (int rr = 0; rr < 4; ++rr) {
-    const int64_t off = (int64_t(blk) * BLK_ROWS + w * 4 + rr) * C + c;
-    float g[8], a[8], o[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + off)), g);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(r + off)), a);
+    for (int rr = 0; rr < 4; ++rr) {
+      const int64_t off = (int64_t(part) * rows_per_cta + r0 + w * 4 + rr) * C + c;
+      float g[8], a[8], o[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(dy + off)), g);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(r + off)), a);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      o[i] = a[i] > 0.f ? fmaf(ka[i], g[i], fmaf(kb[i], a[i], kc[i])) : 0.f;
-      s[i] += o[i];
-      mx = fmaxf(mx, fabsf(o[i]));
+      for (int i = 0; i < 8; ++i) {
+        o[i] = a[i] > 0.f ? fmaf(ka[i], g[i], fmaf(kb[i], a[i], kc[i])) : 0.f;
+        s[i] += o[i];
+        mx = fmaxf(mx, fabsf(o[i]));
+      }
+      *reinterpret_cast<uint4*>(dz + off) = pack8(o);
     }
-    *reinterpret_cast<uint4*>(dz + off) = pack8(o);
   }
   if (!(mx <= 65504.f)) atomicOr(overflow_flag, 1u);
 #pragma unroll
@@ -247,12 +264,14 @@ bn_relu_bwd_kernel(const __half* __restrict__ dy, const __half* __restrict__ r, 
   float t = 0.f;
 #pragma unroll
   for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
-  partial1[int64_t(blk) * C + c0 + threadIdx.x] = t;
+  partial1[int64_t(part) * C + c0 + threadIdx.x] = t;
 }
 
 // out[c] = scale * sum over blocks of partial1[blk][c]
 __global__ void __launch_bounds__(1024)
 colsum_finalize_kernel(const float* __restrict__ partial1, int32_t n_blk, int32_t C, float scale, float* __restrict__ out) {
+  cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
+  cudaGridDependencySynchronize();
   __shared__ double sred[RED_Y][1][32];
   const int c = blockIdx.x * 32 + threadIdx.x;
   double s[1];
@@ -273,6 +292,8 @@ struct PoolFwdArgs {
   float* h0;                 // [n_seg][2C]  [mean | sqrt(var + 1e-5)]
 };
 __global__ void __launch_bounds__(256) pool_train_fwd_kernel(const PoolFwdArgs a) {
+  cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
+  cudaGridDependencySynchronize();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int seg = blockIdx.y;
   if (c >= a.C) return;
@@ -307,6 +328,8 @@ struct PoolBwdArgs {
   float* d_gamma; float* d_beta;     // [C]
 };
 __global__ void __launch_bounds__(256) pool_bwd_coef_kernel(const PoolBwdArgs p) {       // block (32, SEG_Y)
+  cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
+  cudaGridDependencySynchronize();
   __shared__ double sred[SEG_Y][2][32];
   __shared__ double s_tot[2][32];
   const int c = blockIdx.x * 32 + threadIdx.x;
@@ -352,37 +375,41 @@ __global__ void __launch_bounds__(256) pool_bwd_coef_kernel(const PoolBwdArgs p)
   }
 }
 
-// dz4 = (r4 > 0) ? A[seg,c] + G[seg,c]*r4 : 0 ; partial1[blk][c] = column sums of dz4 (bias gradient, scaled by S)
+// dz4 = (r4 > 0) ? A[seg,c] + G[seg,c]*r4 : 0 for one segment (seg_stride packed rows) x 256 channels per CTA;
+// partial1[seg][c] = column sums of dz4 (bias gradient, scaled by S)
 __global__ void __launch_bounds__(256)
-pool_relu_bwd_kernel(const __half* __restrict__ r, int32_t C, int32_t blks_per_seg, int32_t n_seg, const float* __restrict__ coefA,
+pool_relu_bwd_kernel(const __half* __restrict__ r, int32_t C, int32_t seg_stride, const float* __restrict__ coefA,
                      const float* __restrict__ coefG, __half* __restrict__ dz, float* __restrict__ partial1, uint32_t* overflow_flag) {
+  cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
+  cudaGridDependencySynchronize();
   __shared__ float red[8][COLS_PER_CTA];
-  const int blk = blockIdx.x, c0 = blockIdx.y * COLS_PER_CTA;
+  const int seg = blockIdx.x, c0 = blockIdx.y * COLS_PER_CTA;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = c0 + lane * 8;
-  const int seg = blk / blks_per_seg;
   float ka[8], kg[8], s[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { ka[i] = 0.f; kg[i] = 0.f; s[i] = 0.f; }
-  if (seg < n_seg) {
+  {
     const float4 a0 = __ldg(reinterpret_cast<const float4*>(coefA + int64_t(seg) * C + c)), a1 = __ldg(reinterpret_cast<const float4*>(coefA + int64_t(seg) * C + c + 4));
     const float4 g0 = __ldg(reinterpret_cast<const float4*>(coefG + int64_t(seg) * C + c)), g1 = __ldg(reinterpret_cast<const float4*>(coefG + int64_t(seg) * C + c + 4));
     ka[0] = a0.x; ka[1] = a0.y; ka[2] = a0.z; ka[3] = a0.w; ka[4] = a1.x; ka[5] = a1.y; ka[6] = a1.z; ka[7] = a1.w;
     kg[0] = g0.x; kg[1] = g0.y; kg[2] = g0.z; kg[3] = g0.w; kg[4] = g1.x; kg[5] = g1.y; kg[6] = g1.z; kg[7] = g1.w;
   }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = 0.f;
   float mx = 0.f;
+  for (int r0 = 0; r0 < seg_stride; r0 += BLK_ROWS) {
 #pragma unroll
-  for (int rr = 0; rr < 4; ++rr) {
-    const int64_t off = (int64_t(blk) * BLK_ROWS + w * 4 + rr) * C + c;
-    float a[8], o[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(r + off)), a);
+    for (int rr = 0; rr < 4; ++rr) {
+      const int64_t off = (int64_t(seg) * seg_stride + r0 + w * 4 + rr) * C + c;
+      float a[8], o[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(r + off)), a);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      o[i] = a[i] > 0.f ? fmaf(kg[i], a[i], ka[i]) : 0.f;
-      s[i] += o[i];
-      mx = fmaxf(mx, fabsf(o[i]));
+      for (int i = 0; i < 8; ++i) {
+        o[i] = a[i] > 0.f ? fmaf(kg[i], a[i], ka[i]) : 0.f;
+        s[i] += o[i];
+        mx = fmaxf(mx, fabsf(o[i]));
+      }
+      *reinterpret_cast<uint4*>(dz + off) = pack8(o);
     }
-    *reinterpret_cast<uint4*>(dz + off) = pack8(o);
   }
   if (!(mx <= 65504.f)) atomicOr(overflow_flag, 1u);
 #pragma unroll
@@ -391,7 +418,7 @@ pool_relu_bwd_kernel(const __half* __restrict__ r, int32_t C, int32_t blks_per_s
   float t = 0.f;
 #pragma unroll
   for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
-  partial1[int64_t(blk) * C + c0 + threadIdx.x] = t;
+  partial1[int64_t(seg) * C + c0 + threadIdx.x] = t;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -407,6 +434,8 @@ struct SgemmArgs {
 };
 template <bool A_KFAST, bool B_NFAST>
 __global__ void __launch_bounds__(256) sgemm64_kernel(const SgemmArgs a) {
+  cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
+  cudaGridDependencySynchronize();
   __shared__ float As[16][68];
   __shared__ float Bs[16][68];
   const int tid = threadIdx.x;
@@ -459,9 +488,12 @@ __global__ void __launch_bounds__(256) sgemm64_kernel(const SgemmArgs a) {
     }
   }
 }
+// C = sum of the K-split partials (fixed order) + bias
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ partial, int32_t splits, int32_t M, int32_t N, const float* __restrict__ bias,
                      float* __restrict__ C, int32_t ldc) {
+  cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
+  cudaGridDependencySynchronize();
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= int64_t(M) * N) return;
   const int m = int(i / N), n = int(i - int64_t(m) * N);
@@ -480,6 +512,8 @@ struct SegBnArgs {
   int32_t training;          // 0: evaluation branch (moving statistics, no update; tf_block.py:25-26)
 };
 __global__ void __launch_bounds__(256) seg_relu_bn_fwd_kernel(const SegBnArgs a) {     // block (32, SEG_Y)
+  cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
+  cudaGridDependencySynchronize();
   __shared__ double sred[SEG_Y][2][32];
   __shared__ float s_sc[32], s_sh[32];
   const int c = blockIdx.x * 32 + threadIdx.x;
@@ -528,6 +562,8 @@ struct SegBnBwdArgs {
   float* dz; float* d_gamma; float* d_beta; float* d_bias;
 };
 __global__ void __launch_bounds__(256) seg_relu_bn_bwd_kernel(const SegBnBwdArgs a) {   // block (32, SEG_Y)
+  cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
+  cudaGridDependencySynchronize();
   __shared__ double sred[SEG_Y][2][32];
   __shared__ double s_tot[2][32];
   const int c = blockIdx.x * 32 + threadIdx.x;
@@ -579,6 +615,8 @@ __global__ void __launch_bounds__(256) seg_relu_bn_bwd_kernel(const SegBnBwdArgs
 __global__ void __launch_bounds__(256)
 softmax_ce_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels, int32_t n_classes, float inv_batch,
                   float* __restrict__ dlogits, float* __restrict__ loss_row, float* __restrict__ correct) {
+  cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
+  cudaGridDependencySynchronize();
   __shared__ float s_val[256];
   __shared__ int s_idx[256];
   const int b = blockIdx.x, t = threadIdx.x;
@@ -612,6 +650,8 @@ softmax_ce_kernel(const float* __restrict__ logits, const int32_t* __restrict__ 
   }
 }
 __global__ void loss_finalize_kernel(const float* loss_row, const float* correct, int32_t B, float* out) {
+  cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
+  cudaGridDependencySynchronize();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double l = 0.0, c = 0.0;
   for (int b = 0; b < B; ++b) { l += loss_row[b]; c += correct[b]; }
@@ -620,6 +660,8 @@ __global__ void loss_finalize_kernel(const float* loss_row, const float* correct
 }
 // out[n] = sum over the B rows of x[b][n]
 __global__ void __launch_bounds__(256) colsum_rows_kernel(const float* __restrict__ x, int32_t B, int32_t N, float* __restrict__ out) {
+  cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
+  cudaGridDependencySynchronize();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   float s = 0.f;
@@ -632,6 +674,8 @@ __global__ void __launch_bounds__(256) colsum_rows_kernel(const float* __restric
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
             float lr_t, float b1, float b2, float eps, float grad_scale) {
+  cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
+  cudaGridDependencySynchronize();
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float gi = g[i] * grad_scale;
@@ -641,29 +685,44 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   p[i] -= lr_t * mi / (sqrtf(vi) + eps);
 }
 
-// fp32 master conv weights W[taps][c_in][c_out] -> the two fp16 operand copies, one 32 x 32 tile per CTA
-// (grid (c_out/32, ceil(c_in/32), taps), block (32, 8)):
+// fp32 master conv weights W[taps][c_in][c_out] -> the two fp16 operand copies, one 32 x 32 tile per CTA, all frame
+// layers in ONE launch (grid = total tiles, block (32, 8)):
 //   forward       wf[c_out][k_total], K index = tap*c_in_pad + ci          (transposed through shared memory)
 //   data gradient wd[c_in][tap'*c_out + co] = W[taps-1-tap'][c_in][co]     (the conv of dz with the flipped kernel; may be null)
-__global__ void __launch_bounds__(256)
-repack_kernel(const float* __restrict__ W, int32_t taps, int32_t c_in, int32_t c_out, int32_t c_in_pad, int32_t k_total,
-              __half* __restrict__ wf, __half* __restrict__ wd) {
+struct RepackLayer {
+  const float* W; __half* wf; __half* wd;
+  int32_t taps, c_in, c_out, c_in_pad, k_total;
+  int32_t tile_begin;        // first tile index of this layer; tiles = (c_out/32) * ceil(c_in/32) * taps
+};
+struct RepackTable { RepackLayer layer[8]; int32_t n_layers; };
+__global__ void __launch_bounds__(256) repack_kernel(const RepackTable tb) {
+  cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
+  cudaGridDependencySynchronize();
   __shared__ float tile[32][33];
-  const int o0 = blockIdx.x * 32, c0 = blockIdx.y * 32, j = blockIdx.z;
+  int li = 0;
+  while (li + 1 < tb.n_layers && int(blockIdx.x) >= tb.layer[li + 1].tile_begin) ++li;
+  const RepackLayer& L = tb.layer[li];
+  int tix = int(blockIdx.x) - L.tile_begin;
+  const int n_o = L.c_out / 32, n_c = (L.c_in + 31) / 32;
+  const int o0 = (tix % n_o) * 32;
+  tix /= n_o;
+  const int c0 = (tix % n_c) * 32, j = tix / n_c;
   for (int i = threadIdx.y; i < 32; i += 8) {
     const int c = c0 + i;
-    const float w = c < c_in ? W[(int64_t(j) * c_in + c) * c_out + o0 + threadIdx.x] : 0.f;
+    const float w = c < L.c_in ? L.W[(int64_t(j) * L.c_in + c) * L.c_out + o0 + threadIdx.x] : 0.f;
     tile[i][threadIdx.x] = w;
-    if (wd != nullptr && c < c_in) wd[(int64_t(c) * taps + (taps - 1 - j)) * c_out + o0 + threadIdx.x] = __float2half_rn(w);
+    if (L.wd != nullptr && c < L.c_in) L.wd[(int64_t(c) * L.taps + (L.taps - 1 - j)) * L.c_out + o0 + threadIdx.x] = __float2half_rn(w);
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += 8) {
     const int c = c0 + threadIdx.x;
-    if (c < c_in) wf[int64_t(o0 + i) * k_total + int64_t(j) * c_in_pad + c] = __float2half_rn(tile[threadIdx.x][i]);
+    if (c < L.c_in) L.wf[int64_t(o0 + i) * L.k_total + int64_t(j) * L.c_in_pad + c] = __float2half_rn(tile[threadIdx.x][i]);
   }
 }
 
 __global__ void __launch_bounds__(256) fill_kernel(float* p, int64_t n, float v) {
+  cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
+  cudaGridDependencySynchronize();
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
