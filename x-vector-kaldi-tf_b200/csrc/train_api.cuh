@@ -602,7 +602,7 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
     TR_LAUNCH("bn_fwd_finalize_kernel", trk::bn_fwd_finalize_kernel, dim3(L.c_out / 32), dim3(dim3(32, trk::RED_Y)), 0, b);
     if (i < nl - 1) {
       const int64_t n8 = r_pad * L.c_out / 8;
-      TR_LAUNCH("bn_apply_kernel", trk::bn_apply_kernel, dim3(unsigned((n8 + 255) / 256)), dim3(256), 0, L.r, t->row_valid, b.scale, b.shift, n8, L.c_out / 8, L.y, m->overflow_dev);
+      TR_LAUNCH("bn_apply_kernel", trk::bn_apply_kernel, dim3(unsigned((n8 + 1023) / 1024)), dim3(256), 0, L.r, t->row_valid, b.scale, b.shift, n8, L.c_out / 8, L.y, m->overflow_dev);
       in = L.y;
     }
   }

@@ -58,13 +58,21 @@ blk_col_sums_kernel(const __half* __restrict__ x, const __half* __restrict__ y, 
   float s1[8], s2[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
-  for (int r0 = 0; r0 < rows_per_cta; r0 += BLK_ROWS) {
+  for (int r0 = 0; r0 < rows_per_cta; r0 += 2 * BLK_ROWS) {          // 64 rows per trip: 8 loads in flight per thread
+    uint4 va[8], vb[8];
 #pragma unroll
-    for (int rr = 0; rr < 4; ++rr) {
-      const int64_t off = (int64_t(part) * rows_per_cta + r0 + w * 4 + rr) * C + c0 + lane * 8;
+    for (int rr = 0; rr < 8; ++rr) {
+      const int row = r0 + w * 8 + rr;
+      const int64_t off = (int64_t(part) * rows_per_cta + row) * C + c0 + lane * 8;
+      const bool ok = row < rows_per_cta;
+      va[rr] = ok ? __ldg(reinterpret_cast<const uint4*>(x + off)) : make_uint4(0u, 0u, 0u, 0u);
+      if (OP == 1) vb[rr] = ok ? __ldg(reinterpret_cast<const uint4*>(y + off)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) {
       float a[8], b[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(x + off)), a);
-      if (OP == 1) unpack8(__ldg(reinterpret_cast<const uint4*>(y + off)), b);
+      unpack8(va[rr], a);
+      if (OP == 1) unpack8(vb[rr], b);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         s1[i] += a[i];
@@ -156,25 +164,40 @@ bn_apply_kernel(const __half* __restrict__ r, const uint8_t* __restrict__ row_va
                 const float* __restrict__ shift, int64_t n8, int32_t c8, __half* __restrict__ y, uint32_t* overflow_flag) {
   cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
   cudaGridDependencySynchronize();
-  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n8) return;
-  const int64_t row = i / c8;
-  const int c = int(i - row * c8) * 8;
-  uint4 out = make_uint4(0u, 0u, 0u, 0u);
-  if (row_valid[row]) {
-    float v[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(r) + i), v);
-    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c)), s1 = __ldg(reinterpret_cast<const float4*>(scale + c + 4));
-    const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + c)), h1 = __ldg(reinterpret_cast<const float4*>(shift + c + 4));
-    v[0] = fmaf(v[0], s0.x, h0.x); v[1] = fmaf(v[1], s0.y, h0.y); v[2] = fmaf(v[2], s0.z, h0.z); v[3] = fmaf(v[3], s0.w, h0.w);
-    v[4] = fmaf(v[4], s1.x, h1.x); v[5] = fmaf(v[5], s1.y, h1.y); v[6] = fmaf(v[6], s1.z, h1.z); v[7] = fmaf(v[7], s1.w, h1.w);
-    float mx = 0.f;
+  // 4 pieces of 8 channels per thread, loads issued before use
+  uint4 in[4];
+  uint8_t ok[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) mx = fmaxf(mx, fabsf(v[k]));
-    if (!(mx <= 65504.f)) atomicOr(overflow_flag, 1u);
-    out = pack8(v);
+  for (int k = 0; k < 4; ++k) {
+    const int64_t i = (int64_t(blockIdx.x) * 4 + k) * blockDim.x + threadIdx.x;
+    ok[k] = 0;
+    in[k] = make_uint4(0u, 0u, 0u, 0u);
+    if (i < n8) {
+      ok[k] = row_valid[i / c8];
+      in[k] = __ldg(reinterpret_cast<const uint4*>(r) + i);
+    }
   }
-  reinterpret_cast<uint4*>(y)[i] = out;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t i = (int64_t(blockIdx.x) * 4 + k) * blockDim.x + threadIdx.x;
+    if (i >= n8) continue;
+    const int c = int(i % c8) * 8;
+    uint4 out = make_uint4(0u, 0u, 0u, 0u);
+    if (ok[k]) {
+      float v[8];
+      unpack8(in[k], v);
+      const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c)), s1 = __ldg(reinterpret_cast<const float4*>(scale + c + 4));
+      const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + c)), h1 = __ldg(reinterpret_cast<const float4*>(shift + c + 4));
+      v[0] = fmaf(v[0], s0.x, h0.x); v[1] = fmaf(v[1], s0.y, h0.y); v[2] = fmaf(v[2], s0.z, h0.z); v[3] = fmaf(v[3], s0.w, h0.w);
+      v[4] = fmaf(v[4], s1.x, h1.x); v[5] = fmaf(v[5], s1.y, h1.y); v[6] = fmaf(v[6], s1.z, h1.z); v[7] = fmaf(v[7], s1.w, h1.w);
+      float mx = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) mx = fmaxf(mx, fabsf(v[q]));
+      if (!(mx <= 65504.f)) atomicOr(overflow_flag, 1u);
+      out = pack8(v);
+    }
+    reinterpret_cast<uint4*>(y)[i] = out;
+  }
 }
 
 // evaluation branch: scale = gamma * rsqrt(moving_var + eps), shift = beta - moving_mean * scale  (tf_block.py:26)
@@ -242,12 +265,19 @@ bn_relu_bwd_kernel(const __half* __restrict__ dy, const __half* __restrict__ r, 
   for (int i = 0; i < 8; ++i) s[i] = 0.f;
   float mx = 0.f;
   for (int r0 = 0; r0 < rows_per_cta; r0 += BLK_ROWS) {
+    uint4 vg[4], va[4];
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {                                     // 8 loads in flight per thread
+      const int64_t off = (int64_t(part) * rows_per_cta + r0 + w * 4 + rr) * C + c;
+      vg[rr] = __ldg(reinterpret_cast<const uint4*>(dy + off));
+      va[rr] = __ldg(reinterpret_cast<const uint4*>(r + off));
+    }
 #pragma unroll
     for (int rr = 0; rr < 4; ++rr) {
       const int64_t off = (int64_t(part) * rows_per_cta + r0 + w * 4 + rr) * C + c;
       float g[8], a[8], o[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(dy + off)), g);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(r + off)), a);
+      unpack8(vg[rr], g);
+      unpack8(va[rr], a);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         o[i] = a[i] > 0.f ? fmaf(ka[i], g[i], fmaf(kb[i], a[i], kc[i])) : 0.f;
@@ -396,19 +426,26 @@ pool_relu_bwd_kernel(const __half* __restrict__ r, int32_t C, int32_t seg_stride
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = 0.f;
   float mx = 0.f;
-  for (int r0 = 0; r0 < seg_stride; r0 += BLK_ROWS) {
+  for (int r0 = 0; r0 < seg_stride; r0 += 2 * BLK_ROWS) {
+    uint4 va[8];
 #pragma unroll
-    for (int rr = 0; rr < 4; ++rr) {
-      const int64_t off = (int64_t(seg) * seg_stride + r0 + w * 4 + rr) * C + c;
+    for (int rr = 0; rr < 8; ++rr) {                                     // 8 loads in flight per thread
+      const int row = r0 + w * 8 + rr;
+      va[rr] = row < seg_stride ? __ldg(reinterpret_cast<const uint4*>(r + (int64_t(seg) * seg_stride + row) * C + c)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) {
+      const int row = r0 + w * 8 + rr;
+      if (row >= seg_stride) continue;
       float a[8], o[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(r + off)), a);
+      unpack8(va[rr], a);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         o[i] = a[i] > 0.f ? fmaf(kg[i], a[i], ka[i]) : 0.f;
         s[i] += o[i];
         mx = fmaxf(mx, fabsf(o[i]));
       }
-      *reinterpret_cast<uint4*>(dz + off) = pack8(o);
+      *reinterpret_cast<uint4*>(dz + (int64_t(seg) * seg_stride + row) * C + c) = pack8(o);
     }
   }
   if (!(mx <= 65504.f)) atomicOr(overflow_flag, 1u);
@@ -447,22 +484,33 @@ __global__ void __launch_bounds__(256) sgemm64_kernel(const SgemmArgs a) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int kb = k0; kb < k1; kb += 16) {
+  float ra[4], rb[4];
+  auto gload = [&](int kb) {                       // this thread's 4 + 4 elements of the K tile starting at kb -> registers
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int idx = tid + e * 256;
       {
         const int kk = A_KFAST ? (idx & 15) : (idx >> 6), mm = A_KFAST ? (idx >> 4) : (idx & 63);
         const int gm = m0 + mm, gk = kb + kk;
-        As[kk][mm] = (gm < a.M && gk < k1) ? __ldg(a.A + int64_t(gm) * a.sam + int64_t(gk) * a.sak) : 0.f;
+        ra[e] = (gm < a.M && gk < k1) ? __ldg(a.A + int64_t(gm) * a.sam + int64_t(gk) * a.sak) : 0.f;
       }
       {
         const int kk = B_NFAST ? (idx >> 6) : (idx & 15), nn = B_NFAST ? (idx & 63) : (idx >> 4);
         const int gn = n0 + nn, gk = kb + kk;
-        Bs[kk][nn] = (gn < a.N && gk < k1) ? __ldg(a.B + int64_t(gk) * a.sbk + int64_t(gn) * a.sbn) : 0.f;
+        rb[e] = (gn < a.N && gk < k1) ? __ldg(a.B + int64_t(gk) * a.sbk + int64_t(gn) * a.sbn) : 0.f;
       }
     }
+  };
+  gload(k0);
+  for (int kb = k0; kb < k1; kb += 16) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 256;
+      As[A_KFAST ? (idx & 15) : (idx >> 6)][A_KFAST ? (idx >> 4) : (idx & 63)] = ra[e];
+      Bs[B_NFAST ? (idx >> 6) : (idx & 15)][B_NFAST ? (idx & 63) : (idx >> 4)] = rb[e];
+    }
     __syncthreads();
+    if (kb + 16 < k1) gload(kb + 16);             // the next tile's loads fly during this tile's FMAs
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
       const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
