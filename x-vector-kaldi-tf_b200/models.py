@@ -148,16 +148,39 @@ class Model(object):
         """``sess`` keeps the reference's positional slot (a TF session there); pass None."""
         if logger is not None:
             logger.info("Start loading graph ...")
-        with open(os.path.join(input_dir, "model.meta"), "rt") as fid:
-            try:
+        from . import tf_bundle
+        meta = None
+        try:
+            with open(os.path.join(input_dir, "model.meta"), "rt") as fid:
                 meta = json.load(fid)
-            except ValueError:
-                raise RuntimeError("%s/model.meta is not an %s header (TensorFlow checkpoints must be converted "
-                                   "first: see INTEGRATION.md)" % (input_dir, META_FORMAT))
-        if meta.get("format") != META_FORMAT:
-            raise RuntimeError("unsupported model.meta format %r" % meta.get("format"))
-        with np.load(os.path.join(input_dir, "model.npz")) as z:
-            params = {k: z[k] for k in z.files}
+        except (ValueError, UnicodeDecodeError):
+            meta = None                              # a TensorFlow MetaGraph: not ours
+        if meta is None and tf_bundle.is_bundle_dir(input_dir):
+            # a checkpoint written by the reference's tf.train.Saver (models.py:131-141): variables by name from the bundle,
+            # topology from this Model subclass (the MetaGraph is not needed) and the variable shapes
+            params = tf_bundle.read_bundle(os.path.join(input_dir, "model"))
+            w0, wo = params["frame_level_info_layer-0/w:0"], params.get("output/w:0")
+            n_layers = len([k for k in params if k.startswith("frame_level_info_layer-") and k.endswith("/w:0")])
+            taps = [int(params["frame_level_info_layer-%d/w:0" % i].shape[0]) for i in range(n_layers)]
+            if taps != list(self.kernel_sizes):
+                raise RuntimeError("%s holds kernel sizes %s but %s declares %s: load it with the Model subclass it was "
+                                   "trained with (model_name.txt, train_dnn.py:495)" % (input_dir, taps, type(self).__name__,
+                                                                                       list(self.kernel_sizes)))
+            meta = dict(format=META_FORMAT, model_class=type(self).__name__, source="tensorflow-bundle",
+                        num_classes=int(wo.shape[1]) if wo is not None else 0, input_feature_dim=int(w0.shape[1]),
+                        kernel_sizes=taps, dilation_rates=list(self.dilation_rates),
+                        layer_sizes=[int(params["frame_level_info_layer-%d/w:0" % i].shape[2]) for i in range(n_layers)],
+                        embedding_sizes=[int(params["embed_layer-%d/w:0" % i].shape[1]) for i in range(2)
+                                         if "embed_layer-%d/w:0" % i in params],
+                        activation=self.activation)
+        elif meta is None:
+            raise RuntimeError("%s/model.meta is not an %s header and there is no model.index checkpoint bundle beside it"
+                               % (input_dir, META_FORMAT))
+        else:
+            if meta.get("format") != META_FORMAT:
+                raise RuntimeError("unsupported model.meta format %r" % meta.get("format"))
+            with np.load(os.path.join(input_dir, "model.npz")) as z:
+                params = {k: z[k] for k in z.files}
         self.meta, self.params = meta, params
         self.num_classes = meta["num_classes"]
         self.kernel_sizes = list(meta["kernel_sizes"])
