@@ -13,6 +13,8 @@ Two kinds of checks:
     (fp16 operand products accumulated in fp32; results rounded to fp16 where they are stored).
 """
 import os
+import re
+import sys
 
 import numpy as np
 import pytest
@@ -22,6 +24,7 @@ from oracle import xvector_oracle as orc
 from oracle import xvector_train_oracle as tro
 from xvector_b200 import synthetic
 
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
@@ -345,3 +348,33 @@ def test_train_one_iteration_through_the_model_surface(tmp_path):
     torch.cuda.synchronize()
     assert np.isfinite(e.cpu().numpy()).all()
     eng.close()
+
+
+def test_train_dnn_driver_end_to_end(tmp_path):
+    """train_dnn.py over a synthetic egs directory: 3 archives, 2 epochs, jobs 1 -> 2 (model averaging), nnet-dir layout."""
+    from test_train_oracle import _make_egs_dir
+    from xvector_b200 import train_dnn, ze_utils
+    os.environ["XVEC_SEED"] = "7"
+    egs = _make_egs_dir(str(tmp_path / "egs"), num_archives=3, minibatches=5, B=16, T=48, classes=30)
+    nnet = str(tmp_path / "nnet")
+    args = train_dnn.get_args(["--tf-model-class", "ModelWithoutDropoutTdnn", "--dir", nnet, "--egs-dir", egs, "--num-targets", "30",
+                               "--minibatch-size", "16", "--num-epochs", "2", "--num-jobs-initial", "1", "--num-jobs-final", "2",
+                               "--initial-effective-lrate", "0.002", "--final-effective-lrate", "0.0005", "--cleanup", "false",
+                               "--print-interval", "2"])
+    num_iters = train_dnn.train(args)
+    assert num_iters == (int(2 * 3) * 2) // 3 == 4
+    assert open(os.path.join(nnet, "model_name.txt")).read() == "ModelWithoutDropoutTdnn"
+    assert os.path.islink(os.path.join(nnet, "model_final")) and os.readlink(os.path.join(nnet, "model_final")) == "model_4"
+    for it in range(5):
+        assert ze_utils.is_correct_model_dir(os.path.join(nnet, "model_%d" % it))
+    assert not [d for d in os.listdir(nnet) if re.match(r"model_\d+\.\d+$", d)]         # transient job dirs removed
+    rep = open(os.path.join(nnet, "accuracy.report")).read().strip().split("\n")
+    rows = [r.split("\t") for r in rep[1:]]
+    assert len(rows) == 1 + 1 + 2 + 2                                                    # jobs per iteration: 1, 1, 2, 2
+    assert float(rows[-1][2]) < 0.8 * float(rows[0][2])                                  # the loss goes down over the run
+    log0 = open(os.path.join(nnet, "log", "train.0.1.log")).read()
+    assert "Average training loss for minibatches 1-2 is" in log0 and "Overall average objective function is" in log0
+    # a second call resumes: every iteration's output exists, nothing is retrained
+    before = os.path.getmtime(os.path.join(nnet, "model_4", "model.npz"))
+    train_dnn.train(args)
+    assert os.path.getmtime(os.path.join(nnet, "model_4", "model.npz")) == before

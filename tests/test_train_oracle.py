@@ -134,3 +134,59 @@ def test_one_iteration_cli_rejects_bad_arguments(tmp_path):
         cli.get_args(base + ["--input-dir", str(mdir), "--tar-file", tar, "--dropout-proportion", "1.5"])
     args = cli.get_args(base + ["--input-dir", str(mdir), "--tar-file", tar, "--learning-rate", "0.001"])
     assert args.learning_rate == 0.001 and args.print_interval == 10 and args.sequential_loading is True
+
+
+def _make_egs_dir(root, num_archives=3, minibatches=4, B=8, T=40, classes=20, seed=0):
+    rng = np.random.default_rng(seed)
+    means = rng.standard_normal((classes, 23)) * 6.0
+    os.makedirs(os.path.join(root, "info"))
+    os.makedirs(os.path.join(root, "temp"))
+    open(os.path.join(root, "info", "feat_dim"), "w").write("23\n")
+    open(os.path.join(root, "info", "num_archives"), "w").write("%d\n" % num_archives)
+    with open(os.path.join(root, "temp", "archive_minibatch_count"), "w") as f:
+        for a in range(1, num_archives + 1):
+            f.write("%d %d\n" % (a, minibatches))
+            labs = [rng.integers(0, classes, B) for _ in range(minibatches)]
+            mbs = [(means[l][:, None, :] + synthetic.mfcc(1000 * a + i, B * T).reshape(B, T, 23)).astype(np.float32)
+                   for i, l in enumerate(labs)]
+            examples_io.write_egs_tar(os.path.join(root, "egs.%d.tar" % a), mbs, labs)
+    return root
+
+
+def test_train_dnn_schedules_and_bookkeeping(tmp_path):
+    from xvector_b200 import train_dnn
+    # learning-rate law (reference ze_utils.py:111-120): geometric in the archives processed, times the job count; last iter = final
+    lr0, lr1 = 1e-3, 1e-4
+    assert train_dnn.get_learning_rate(0, 1, 10, 0, 20, lr0, lr1) == pytest.approx(1e-3)
+    assert train_dnn.get_learning_rate(3, 2, 10, 10, 20, lr0, lr1) == pytest.approx(2 * 1e-3 * np.sqrt(0.1))
+    assert train_dnn.get_learning_rate(9, 3, 10, 19, 20, lr0, lr1) == pytest.approx(3 * 1e-4)
+    assert train_dnn.get_successful_models([-1.0, -0.5, -2.1]) == [[1, 2], 2]          # within 1.0 of the best
+    egs = _make_egs_dir(str(tmp_path / "egs"))
+    assert train_dnn.verify_egs_dir(egs) == [3, 23, {1: 4, 2: 4, 3: 4}]
+    with pytest.raises((IOError, ValueError)):
+        train_dnn.verify_egs_dir(str(tmp_path / "missing"))
+    # model averaging: element-wise mean of the jobs' arrays, Adam step counters from the first job
+    for j, val in ((1, 1.0), (2, 3.0)):
+        d = tmp_path / ("model_5.%d" % j)
+        d.mkdir()
+        np.savez(str(d / "model.npz"), **{"a/w:0": np.full((2, 3), val, np.float32), "beta1_power:0": np.float32([0.5 * j])})
+        (d / "model.meta").write_text('{"format": "xvec-b200-v1"}')
+    train_dnn.average_model_dirs([str(tmp_path / "model_5.1"), str(tmp_path / "model_5.2")], str(tmp_path / "model_5"))
+    with np.load(str(tmp_path / "model_5" / "model.npz")) as z:
+        np.testing.assert_array_equal(z["a/w:0"], np.full((2, 3), 2.0, np.float32))
+        assert float(z["beta1_power:0"][0]) == 0.5
+    from xvector_b200 import ze_utils
+    assert ze_utils.is_correct_model_dir(str(tmp_path / "model_5"))
+    # the report is parsed from the job logs' own summary line (reference models.py:290-292)
+    os.makedirs(str(tmp_path / "nnet" / "log"))
+    open(str(tmp_path / "nnet" / "log" / "train.0.1.log"), "w").write(
+        "2026 [x.py:1 - f - INFO ] Overall average training loss is 3.2100 over 64 segments. Also, the overall "
+        "average training accuracy is 0.2500.\n")
+    rep = train_dnn.generate_report(str(tmp_path / "nnet"))
+    assert "0\t1\t3.2100\t-3.2100\t0.2500" in rep
+    with pytest.raises(Exception, match="not implemented"):
+        train_dnn.get_args(["--tf-model-class", "Model", "--dir", "x", "--egs-dir", "y", "--num-targets", "5",
+                            "--minibatch-size", "8", "--do-final-combination", "true"])
+    a = train_dnn.get_args(["--tf-model-class", "ModelWithoutDropout", "--dir", "x", "--egs-dir", "y", "--num-targets", "5",
+                            "--minibatch-size", "8", "--num-epochs", "2", "--cmd", "run.pl --long 0", "--momentum", "0.5"])
+    assert a.num_epochs == 2.0 and a.cleanup is True and a.initial_effective_lrate == 0.0003

@@ -248,13 +248,14 @@ class Model(object):
         out["beta2_power:0"] = np.asarray([0.999 ** tr.step], dtype=np.float32)
         return out
 
-    def _run_minibatches(self, data_loader, tr, eng, logger, training, learning_rate=0.0, print_interval=10):
+    def _run_minibatches(self, data_loader, tr, eng, logger, training, learning_rate=0.0, print_interval=10, data_parallel=True):
         """The minibatch loop of train_one_iteration / eval (reference models.py:233-299 / :313-354): same skip rules,
         counters and log lines; the host->device copy of minibatch k+1 overlaps the kernels of minibatch k, and
         loss / accuracy are read back only when a log line needs them."""
         import torch
         dev = torch.device("cuda:%d" % eng.device)
-        world = sharding.dist_info()[1]
+        # data parallel (gradient all-reduce) unless the caller runs independent jobs per rank (train_dnn.py: args.data_parallel=False)
+        world = sharding.dist_info()[1] if data_parallel else 1
         compute, copy = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         minibatch_count = data_loader.count
         results = torch.zeros((max(minibatch_count, 1), 2), dtype=torch.float32, device=dev)
@@ -357,7 +358,8 @@ class Model(object):
         self.load_model(None, args.input_dir, logger)
         eng, tr = self._create_trainer(device)
         try:
-            st = self._run_minibatches(data_loader, tr, eng, logger, True, learning_rate, print_interval)
+            data_parallel = getattr(args, "data_parallel", True)
+            st = self._run_minibatches(data_loader, tr, eng, logger, True, learning_rate, print_interval, data_parallel)
             minibatch_count = max(st["minibatch_count"], 1)
             logger.info("Processed %d segments of average size %d into %d minibatches. Avg minibatch size was %d." %
                         (st["total_segments"], st["total_segments_len"] / minibatch_count, minibatch_count,
@@ -368,7 +370,7 @@ class Model(object):
             logger.info("Overall average objective function is %.4f over %d segments." %
                         (-st["total_loss"] / minibatch_count, st["total_segments"]))
             self.params = self._download_state(tr)
-            if sharding.dist_info()[0] == 0:
+            if sharding.dist_info()[0] == 0 or not data_parallel:
                 Model.save_model(_Session(self.params, self.meta), args.output_dir, logger)
             logger.info("Elapsed time for processing whole training minibatches is %.2f minutes." % (st["elapsed"] / 60.0))
             return st
@@ -383,7 +385,7 @@ class Model(object):
         self.load_model(None, input_dir, logger)
         eng, tr = self._create_trainer(device)
         try:
-            st = self._run_minibatches(data_loader, tr, eng, logger, False)
+            st = self._run_minibatches(data_loader, tr, eng, logger, False, data_parallel=False)
             minibatch_count = max(st["minibatch_count"], 1)
             logger.info("Processed %d segments of average size %d into %d minibatches. Avg minibatch size was %d." %
                         (st["total_segments"], st["total_segments_len"] / minibatch_count, minibatch_count,
