@@ -56,6 +56,10 @@ TOPOLOGIES = {   # reference local/tf/models.py:443-445 and :545-548
                                      layer_sizes=[512, 512, 512, 512, 1536], embedding_sizes=[512, 512], act="prelu"),
     "ModelL2LossWithoutDropoutLRelu": dict(kernel_sizes=[5, 5, 7, 1, 1], dilations=[1, 1, 1, 1, 1],
                                            layer_sizes=[512, 512, 512, 512, 1536], embedding_sizes=[512, 512], act="lrelu"),
+    # self-attention pooling (models.py:990-1051)
+    "ModelL2LossWithoutDropoutLReluAttention": dict(kernel_sizes=[5, 5, 7, 1, 1], dilations=[1, 1, 1, 1, 1],
+                                                    layer_sizes=[512, 512, 512, 512, 3072], embedding_sizes=[512, 512],
+                                                    act="lrelu", pooling="attention"),
 }
 
 
@@ -186,9 +190,10 @@ def run_b200(args):
 
     topo = TOPOLOGIES[args.topology]
     params = synthetic.make_params(topo["kernel_sizes"], topo["layer_sizes"], topo["embedding_sizes"],
-                                   weight_set=args.weight_set, activation=topo.get("act", "relu"))
+                                   weight_set=args.weight_set, activation=topo.get("act", "relu"),
+                                   pooling=topo.get("pooling", "stats"))
     eng = _native.XvecEngine(topo["kernel_sizes"], topo["dilations"], topo["layer_sizes"], EMB_DIM, FEAT_DIM,
-                             device=local_rank, activation=topo.get("act", "relu"))
+                             device=local_rank, activation=topo.get("act", "relu"), pooling=topo.get("pooling", "stats"))
     eng.set_params(params)
     for kv in args.option:
         eng.set_option(kv.split("=")[0], int(kv.split("=")[1]))
@@ -334,6 +339,11 @@ def run_b200(args):
     # (kernel, bound, algorithmic FLOP or bytes per launch) in launch order
     table = [("pack_im2col_kernel", "hbm", frames * (FEAT_DIM * 4 + k0_pad * 2 + 1))]
     table += [("tdnn_pair_kernel[L%d]" % i, "tensor", frames * f) for i, f in enumerate(fl)]
+    if topo.get("pooling") == "attention":       # models.py:1037-1051: score GEMM [frames, C] x [C, C], softmax over time, weighted sums
+        c_last //= 2
+        table += [("tdnn_pair_kernel<3>[attention scores]", "tensor", frames * 2 * c_last * c_last),
+                  ("attn_softmax_kernel", "hbm", frames * (2 * (c_last // 256) + 2) * 4),
+                  ("attn_pool_kernel", "hbm", frames * c_last * 2 + n_blk * 2 * c_last * 4)]
     table += [("pool_stats_kernel", "hbm", n_blk * 2 * c_last * 4 + B * 2 * c_last * 6)]
     if len(kms) == len(table) + 2:      # embed_layer-0 on tensor cores: split-fp16 GEMM (3 products) + K-split reduction
         table += [("tdnn_pair_kernel<2>[embed_layer-0]", "tensor", 2 * B * 2 * c_last * EMB_DIM),
@@ -385,7 +395,7 @@ def run_b200(args):
         out["clocks"]["note"] = "first measurement rejected (throttle reason / low clocks); this is the re-measurement"
 
     eng.close()
-    if not args.no_train and topo.get("act", "relu") == "relu":
+    if not args.no_train and topo.get("act", "relu") == "relu" and topo.get("pooling", "stats") == "stats":
         out["train_step"] = measure_train_step(args, dev, rank, world, peaks, topo)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_subprocess(args)
@@ -532,7 +542,8 @@ def run_reference(args):
     threads = 2
     procs = max(1, min(cores // threads, 64))
     params = synthetic.make_params(topo["kernel_sizes"], topo["layer_sizes"], topo["embedding_sizes"],
-                                   weight_set=args.weight_set, activation=topo.get("act", "relu"))
+                                   weight_set=args.weight_set, activation=topo.get("act", "relu"),
+                                   pooling=topo.get("pooling", "stats"))
     frames = args.frames
     n_utts_max = 16
     feats = synthetic.mfcc_batch(2, np.full(n_utts_max, frames, np.int32))

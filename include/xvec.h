@@ -47,6 +47,13 @@ enum {
  *   XV_ACT_PRELU  prelu(h, shared=False)        (tf_block.py:38-47; per-channel slope "<scope>/prelu/prelu:0") */
 enum { XV_ACT_RELU = 0, XV_ACT_LRELU = 1, XV_ACT_PRELU = 2 };
 
+/* Pooling between the frame level and the segment level:
+ *   XV_POOL_STATS      mean | sqrt(var + 1e-5) over time                        (models.py:485-486)
+ *   XV_POOL_ATTENTION  the last frame layer (width 2C) is split into h1 | h2; attention = softmax over time of
+ *                      v . tanh(h1 W + b) ("attention/w:0" [C,C], "attention/b:0", "attention/v:0" [C]); weighted mean and
+ *                      sqrt(weighted var + 1e-5) of h2       (ModelL2LossWithoutDropoutLReluAttention, models.py:1037-1051) */
+enum { XV_POOL_STATS = 0, XV_POOL_ATTENTION = 1 };
+
 /* Topology = the constants hard-coded in each build_model body
  * (kernel_sizes / dilation_rates / layer_sizes: models.py:443-445, :545-548). */
 typedef struct xv_topology {
@@ -59,6 +66,7 @@ typedef struct xv_topology {
   int32_t act;                              /* XV_ACT_*                                      */
   float bn_eps;                             /* 1e-3  (tf_block.py:9)                         */
   float var_eps;                            /* 1e-5  (models.py:16 VAR2STD_EPSILON)          */
+  int32_t pooling;                          /* XV_POOL_*                                     */
 } xv_topology;
 
 typedef struct xv_model xv_model;           /* opaque: device weights, metadata, tensor maps */

@@ -55,6 +55,10 @@ TOPOLOGIES = {
                                      layer_sizes=[512, 512, 512, 512, 1536], embedding_sizes=[512, 512], act="prelu"),
     "ModelL2LossWithoutDropoutLRelu": dict(kernel_sizes=[5, 5, 7, 1, 1], dilations=[1, 1, 1, 1, 1],
                                            layer_sizes=[512, 512, 512, 512, 1536], embedding_sizes=[512, 512], act="lrelu"),
+    # self-attention pooling (local/tf/models.py:990-1051): last frame layer 6*512 wide, split into scores input | pooled half
+    "ModelL2LossWithoutDropoutLReluAttention": dict(kernel_sizes=[5, 5, 7, 1, 1], dilations=[1, 1, 1, 1, 1],
+                                                    layer_sizes=[512, 512, 512, 512, 3072], embedding_sizes=[512, 512],
+                                                    act="lrelu", pooling="attention"),
 }
 
 
@@ -111,6 +115,23 @@ def stats_pool(h):
     return np.concatenate([mean, np.sqrt(var + VAR2STD_EPSILON)])
 
 
+def attention_pool(h, params):
+    """Self-attention statistics pooling (local/tf/models.py:1037-1051): [T, 2C] -> [2C].
+
+    ``h1, h2 = split(h, 2)``; ``attention = softmax_t( tanh(h1 @ w + b) @ v )``; ``h_m = sum_t a_t h2[t]``;
+    ``h_s = sum_t a_t h2[t]^2 - h_m^2``; result ``[h_m | sqrt(h_s + 1e-5)]``.
+    """
+    C = h.shape[1] // 2
+    h1, h2 = h[:, :C], h[:, C:]
+    non_linearity = np.tanh(h1 @ params["attention/w:0"] + params["attention/b:0"])
+    score = non_linearity @ params["attention/v:0"]
+    e = np.exp(score - score.max())
+    attention = e / e.sum()                                   # tf.nn.softmax over the time axis
+    h_m = attention @ h2
+    h_s = attention @ (h2 ** 2) - h_m ** 2
+    return np.concatenate([h_m, np.sqrt(h_s + VAR2STD_EPSILON)])
+
+
 def forward(x, params, topology="ModelWithoutDropout", dtype=np.float64, return_layers=False):
     """x-vector of ONE chunk: what ``sess.run(embedding[0])`` returns (models.py:158,414).
 
@@ -124,7 +145,7 @@ def forward(x, params, topology="ModelWithoutDropout", dtype=np.float64, return_
     for i, d in enumerate(topo["dilations"]):
         h = frame_layer(h, p, i, d, topo.get("act", "relu"))
         layers.append(h)
-    stats = stats_pool(h)
+    stats = attention_pool(h, p) if topo.get("pooling") == "attention" else stats_pool(h)
     emb = stats @ p["embed_layer-0/w:0"] + p["embed_layer-0/b:0"]     # tf.nn.xw_plus_b, models.py:495
     if return_layers:
         return emb, layers, stats

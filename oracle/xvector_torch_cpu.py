@@ -40,6 +40,9 @@ class TorchCpuXvector:
                 b=g("b:0"), inv=inv, shift=g("beta:0") - g("mean:0") * inv,
                 alpha=(g("prelu/prelu:0") if self.act == "prelu" else None),
                 dilation=d, pad=((k - 1) * d) // 2))
+        self.attention = None
+        if topo.get("pooling") == "attention":       # models.py:1037-1051
+            self.attention = tuple(torch.as_tensor(np.asarray(params["attention/" + n])).to(dtype) for n in ("w:0", "b:0", "v:0"))
         self.w0 = torch.as_tensor(np.asarray(params["embed_layer-0/w:0"])).to(dtype)
         self.b0 = torch.as_tensor(np.asarray(params["embed_layer-0/b:0"])).to(dtype)
 
@@ -56,6 +59,15 @@ class TorchCpuXvector:
             else:
                 h = torch.clamp(h, min=0) + L["alpha"][None, :, None] * torch.clamp(h, max=0)
             h = h * L["inv"][None, :, None] + L["shift"][None, :, None]
+        if self.attention is not None:
+            w, b, v = self.attention
+            C = h.shape[1] // 2
+            h1, h2 = h[:, :C, :].transpose(1, 2), h[:, C:, :].transpose(1, 2)        # [B, T, C]
+            att = torch.softmax(torch.einsum("ijk,k->ij", torch.tanh(torch.einsum("ijk,kl->ijl", h1, w) + b), v), dim=1)
+            h_m = torch.einsum("ijk,ij->ik", h2, att)
+            h_s = torch.einsum("ijk,ij->ik", h2 * h2, att) - h_m * h_m
+            stats = torch.cat([h_m, torch.sqrt(h_s + VAR2STD_EPSILON)], dim=1)
+            return stats @ self.w0 + self.b0
         mean = h.mean(dim=2)
         var = ((h - mean[:, :, None]) ** 2).mean(dim=2)
         stats = torch.cat([mean, torch.sqrt(var + VAR2STD_EPSILON)], dim=1)

@@ -12,11 +12,11 @@ from xvector_b200 import synthetic
 def _params(topology, weight_set):
     t = orc.TOPOLOGIES[topology]
     return synthetic.make_params(t["kernel_sizes"], t["layer_sizes"], t["embedding_sizes"], weight_set=weight_set,
-                                 activation=t.get("act", "relu"))
+                                 activation=t.get("act", "relu"), pooling=t.get("pooling", "stats"))
 
 
 @pytest.mark.parametrize("topology", ["ModelWithoutDropout", "ModelWithoutDropoutTdnn", "ModelWithoutDropoutPRelu",
-                                      "ModelL2LossWithoutDropoutLRelu"])
+                                      "ModelL2LossWithoutDropoutLRelu", "ModelL2LossWithoutDropoutLReluAttention"])
 @pytest.mark.parametrize("weight_set", ["A", "B"])
 def test_two_restatements_agree(topology, weight_set):
     # BASELINE config 1: single 200-frame x 23 utterance, seed 1
@@ -123,3 +123,24 @@ def test_leaky_and_parametric_relu_definitions():
     assert np.allclose(orc.activation(y, "lrelu"), [[-0.4, 3.0], [0.5, -0.2]])
     assert np.allclose(orc.activation(y, "prelu", np.array([0.1, -0.5])), [[-0.2, 3.0], [0.5, 0.5]])
     assert np.allclose(orc.activation(y, "relu"), [[0.0, 3.0], [0.5, 0.0]])
+
+
+def test_attention_pooling_definition():
+    # reference models.py:1037-1051
+    rng = np.random.default_rng(4)
+    T, C = 37, 6
+    h = rng.standard_normal((T, 2 * C))
+    p = {"attention/w:0": rng.standard_normal((C, C)), "attention/b:0": rng.standard_normal(C), "attention/v:0": rng.standard_normal(C)}
+    got = orc.attention_pool(h, p)
+    score = np.array([np.tanh(h[t, :C] @ p["attention/w:0"] + p["attention/b:0"]) @ p["attention/v:0"] for t in range(T)])
+    a = np.exp(score) / np.exp(score).sum()
+    assert abs(a.sum() - 1) < 1e-12
+    h_m = sum(a[t] * h[t, C:] for t in range(T))
+    h_s = sum(a[t] * h[t, C:] ** 2 for t in range(T)) - h_m ** 2
+    np.testing.assert_allclose(got, np.concatenate([h_m, np.sqrt(h_s + 1e-5)]), rtol=1e-12)
+    # v = 0 -> uniform attention -> plain statistics pooling of the second half
+    p0 = dict(p, **{"attention/v:0": np.zeros(C)})
+    np.testing.assert_allclose(orc.attention_pool(h, p0), orc.stats_pool(h[:, C:]), rtol=1e-10)
+    # constant frames -> zero weighted variance -> std = sqrt(1e-5)
+    hc = np.tile(rng.standard_normal(2 * C), (T, 1))
+    np.testing.assert_allclose(orc.attention_pool(hc, p)[C:], np.sqrt(1e-5), rtol=1e-6)

@@ -32,7 +32,7 @@ class XvTopology(ctypes.Structure):
                 ("dilation", ctypes.c_int32 * XV_MAX_FRAME_LAYERS),
                 ("width", ctypes.c_int32 * XV_MAX_FRAME_LAYERS),
                 ("emb_dim", ctypes.c_int32), ("act", ctypes.c_int32),
-                ("bn_eps", ctypes.c_float), ("var_eps", ctypes.c_float)]
+                ("bn_eps", ctypes.c_float), ("var_eps", ctypes.c_float), ("pooling", ctypes.c_int32)]
 
 
 class XvecError(RuntimeError):
@@ -158,9 +158,10 @@ class XvecEngine:
     restored graph (models.py:365-366) on the extraction path."""
 
     ACTIVATIONS = {"relu": 0, "lrelu": 1, "prelu": 2}      # XV_ACT_* (include/xvec.h)
+    POOLINGS = {"stats": 0, "attention": 1}                # XV_POOL_*
 
     def __init__(self, kernel_sizes, dilations, layer_sizes, emb_dim, feat_dim, device=0,
-                 bn_eps=1e-3, var_eps=1e-5, activation="relu"):
+                 bn_eps=1e-3, var_eps=1e-5, activation="relu", pooling="stats"):
         self.lib = load_library()
         topo = XvTopology()
         topo.feat_dim = feat_dim
@@ -171,6 +172,8 @@ class XvecEngine:
         topo.act = self.ACTIVATIONS[activation]
         topo.bn_eps = bn_eps
         topo.var_eps = var_eps
+        topo.pooling = self.POOLINGS[pooling]
+        self.pooling = pooling
         self.handle = ctypes.c_void_p()
         self.device = device
         self.feat_dim, self.emb_dim = feat_dim, emb_dim
@@ -229,7 +232,8 @@ class XvecEngine:
                                                  ws.data_ptr(), ws.numel(), s.cuda_stream))
             return emb_dev
         layers = [torch.empty((total, w), dtype=torch.float32, device=dev) for w in self.layer_sizes]
-        stats = torch.empty((n_seg, 2 * self.layer_sizes[-1]), dtype=torch.float32, device=dev)
+        c_pool = self.layer_sizes[-1] // 2 if self.pooling == "attention" else self.layer_sizes[-1]
+        stats = torch.empty((n_seg, 2 * c_pool), dtype=torch.float32, device=dev)
         ptrs = (ctypes.c_void_p * len(layers))(*[t.data_ptr() for t in layers])
         _check(self.lib, self.lib.xv_forward_layers(self.handle, feats_dev.data_ptr(), lens_p, n_seg,
                                                     emb_dev.data_ptr(), ws.data_ptr(), ws.numel(), s.cuda_stream,

@@ -114,6 +114,7 @@ struct StatsArgs {
   __half* split;              // [n_seg, 3 * 2C] fp16 [hi | hi | lo] of the same statistics (may be null): the A operand
                               // of the split-precision embedding GEMM, x = hi + lo to ~2^-22
   float var_eps;
+  int32_t weighted;           // 1: the partial sums are already weighted by attention weights that sum to 1 (n := 1)
 };
 
 __device__ __forceinline__ void store_split(__half* row, int K, int k, float x) {
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(STATS_THREADS) pool_stats_kernel(const StatsAr
     s1 += double(__ldg(p + int64_t(b) * 2 * C));
     s2 += double(__ldg(p + int64_t(b) * 2 * C + C));
   }
-  const double inv_n = 1.0 / double(len);
+  const double inv_n = a.weighted ? 1.0 : 1.0 / double(len);
   const double mean = s1 * inv_n;
   const double var = fmax(s2 * inv_n - mean * mean, 0.0);
   const float fm = float(mean), fs = float(sqrt(var + double(a.var_eps)));
@@ -312,6 +313,89 @@ __global__ void unpack_rows_kernel(const __half* __restrict__ h, SegMeta seg, in
   const int64_t src0 = int64_t(seg.row_start[s]) * channels, dst0 = int64_t(seg.feat_start[s]) * channels;
   const int64_t n = int64_t(len) * channels;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) out[dst0 + i] = __half2float(h[src0 + i]);
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Self-attention pooling (ModelL2LossWithoutDropoutLReluAttention, local/tf/models.py:1037-1051):
+//   attention = softmax over the frames of one segment of  sum_c v_c * tanh((h1 W)_c + b_c)
+//   h_m = sum_t a_t h2[t],  h_s = sum_t a_t h2[t]^2 - h_m^2,  stats = [h_m | sqrt(h_s + 1e-5)]
+// The score GEMM runs on the tensor cores (tdnn_pair_kernel mode 3) and leaves n_part partial sums per row.
+// attn_softmax_kernel: one CTA per segment; fixed-order reductions.
+constexpr int ATTN_THREADS = 256;
+__global__ void __launch_bounds__(ATTN_THREADS)
+attn_softmax_kernel(const float* __restrict__ score_partial, int32_t n_part, SegMeta seg, float* __restrict__ attn) {
+  __shared__ float red[ATTN_THREADS];
+  cudaTriggerProgrammaticLaunchCompletion();
+  cudaGridDependencySynchronize();
+  const int s = blockIdx.x, t = threadIdx.x;
+  const int row0 = __ldg(seg.row_start + s), len = __ldg(seg.len + s);
+  float mx = -INFINITY;
+  for (int i = t; i < len; i += ATTN_THREADS) {
+    const float* p = score_partial + int64_t(row0 + i) * n_part;
+    float sc = 0.f;
+    for (int k = 0; k < n_part; ++k) sc += p[k];
+    attn[row0 + i] = sc;
+    mx = fmaxf(mx, sc);
+  }
+  red[t] = mx;
+  __syncthreads();
+  for (int w = ATTN_THREADS / 2; w > 0; w >>= 1) { if (t < w) red[t] = fmaxf(red[t], red[t + w]); __syncthreads(); }
+  mx = red[0];
+  __syncthreads();
+  float z = 0.f;
+  for (int i = t; i < len; i += ATTN_THREADS) {
+    const float e = expf(attn[row0 + i] - mx);
+    attn[row0 + i] = e;
+    z += e;
+  }
+  red[t] = z;
+  __syncthreads();
+  for (int w = ATTN_THREADS / 2; w > 0; w >>= 1) { if (t < w) red[t] += red[t + w]; __syncthreads(); }
+  const float inv_z = 1.f / red[0];
+  for (int i = t; i < len; i += ATTN_THREADS) attn[row0 + i] *= inv_z;
+}
+
+// Per aligned 32-row block x 256 channels: partial[blk][0][c] = sum a_t h2[t,c], partial[blk][1][c] = sum a_t h2[t,c]^2
+// (the layout pool_stats_kernel combines; h2 = columns [col0, col0 + C) of the last layer's stored activation).
+__global__ void __launch_bounds__(256)
+attn_pool_kernel(const __half* __restrict__ h, int32_t row_stride, int32_t col0, int32_t C, const float* __restrict__ attn,
+                 const uint8_t* __restrict__ blk_valid, float* __restrict__ partial) {
+  __shared__ float red[8][2][256];
+  cudaTriggerProgrammaticLaunchCompletion();
+  cudaGridDependencySynchronize();
+  const int blk = blockIdx.x, c0 = blockIdx.y * 256;
+  const int nv = blk_valid[blk];
+  if (nv == 0) return;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const int r = w * 4 + rr;
+    if (r < nv) {
+      const int64_t row = int64_t(blk) * 32 + r;
+      const float a = __ldg(attn + row);
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(h + row * row_stride + col0 + c0 + lane * 8));
+      const __half2* hp = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(hp[i]);
+        s1[2 * i] = fmaf(a, f.x, s1[2 * i]);         s2[2 * i] = fmaf(a * f.x, f.x, s2[2 * i]);
+        s1[2 * i + 1] = fmaf(a, f.y, s1[2 * i + 1]); s2[2 * i + 1] = fmaf(a * f.y, f.y, s2[2 * i + 1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { red[w][0][lane * 8 + i] = s1[i]; red[w][1][lane * 8 + i] = s2[i]; }
+  __syncthreads();
+  const int t = threadIdx.x;
+  float x = 0.f, y = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { x += red[k][0][t]; y += red[k][1][t]; }
+  partial[(int64_t(blk) * 2 + 0) * C + c0 + t] = x;
+  partial[(int64_t(blk) * 2 + 1) * C + c0 + t] = y;
 }
 
 }  // namespace xvk

@@ -25,6 +25,9 @@
 //                    partial[block][{sum,sumsq}][channel] fp32, one aligned 32-row block each.
 //   mode 2 (GEMM):   store orientation, no activation function: the raw fp32 accumulators of one K-split go to
 //                    out_f32[split][row][channel] (embed_layer-0 as a split-fp16 tensor-core GEMM, see xvec_api.cu).
+//   mode 3 (score):  store orientation; self-attention scores of the attention-pooling topology (models.py:1043-1044):
+//                    per row, sum over the tile's channels of v_c * tanh(acc + b_c) -> partial[row][2*ch_tile + half]
+//                    (a private register reduction: lane = row, registers = channels); nothing else is stored.
 // Temporal taps: the activation slab [136 rows x 128 ch] is loaded ONCE per channel chunk and tap
 // j is addressed by advancing the UMMA descriptor start by j*d rows (reuse = 1); for half
 // contexts > 4 rows one box per tap is loaded instead (reuse = 0).
@@ -97,7 +100,7 @@ struct PairArgs {
                             //          learned per-channel slope tf_block.py:38-47)
   const uint8_t* row_valid; // [R_pad]     mode 0: 1 = row belongs to a segment, 0 = gap / tail
   const uint8_t* blk_valid; // [R_pad/32]  mode 1: valid rows in the block (they are its first rows)
-  float* partial;           // [R_pad/32][2][C_out]  mode 1
+  float* partial;           // [R_pad/32][2][C_out]  mode 1;  [R_pad][2 * n_ch_tiles]  mode 3 (score partials)
   float* out_f32;           // [k_splits][n_rows][C_out]  mode 2: raw accumulators
   uint32_t* overflow_flag;  // set to 1 if an fp16 output overflowed to inf
   long long* trace;         // diagnostics (tools/trace_tiles.py): [cluster][rank][TRACE_TILES][8] SM clock stamps, or null
@@ -421,6 +424,51 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
                   make_uint4(v[chunk & 1][g * 4], v[chunk & 1][g * 4 + 1], v[chunk & 1][g * 4 + 2], v[chunk & 1][g * 4 + 3]);
           }
         }
+      }
+    } else if (MODE == 3) {
+      // bias -> b, scale -> v of "attention/" (models.py:1038-1039), staged per tile in shared memory
+      const int n_part = 2 * args.n_ch_tiles;
+      for (TileCursor tc = cur0; tc.item < n_items; tc.next(), ++it) {
+        const uint32_t acc = it & 1u;
+        const int row = tc.row * TILE_ROWS + int(rank) * CTA_ROWS + q * 32 + lane;
+        const uint32_t s_par = smem_base + OFF_PARAMS + acc * (PAR_ARRAYS * TILE_CH * 4);
+        {
+          const int ch = tc.ch * TILE_CH + te;
+          ptx::sts_f(s_par + uint32_t(te) * 4u, __ldg(args.bias + ch));
+          ptx::sts_f(s_par + uint32_t(TILE_CH + te) * 4u, __ldg(args.scale + ch));
+        }
+        ptx::named_bar_sync(1, NUM_EPI_THREADS);       // parameters of this tile visible (double-buffered by accumulator)
+        ptx::mbar_wait(t_full(acc), (it >> 1) & 1u);
+        ptx::tc_fence_after();
+        const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * TILE_CH + uint32_t(colh) * 128u;
+        uint32_t v[2][32];
+        ptx::tmem_ld_32x32(t_row, v[0]);
+        float sum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int chunk = 0; chunk < 4; ++chunk) {
+          ptx::tmem_ld_wait_dep(v[chunk & 1]);
+          if (chunk < 3) {
+            ptx::tmem_ld_32x32(t_row + (chunk + 1) * C_CHUNK, v[(chunk + 1) & 1]);
+          } else {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(t_empty_leader + 8u * acc);
+          }
+          const int c = colh * 128 + chunk * C_CHUNK;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 b4 = ptx::lds_f4(s_par + uint32_t(c + g * 4) * 4u);
+            const float4 v4 = ptx::lds_f4(s_par + uint32_t(TILE_CH + c + g * 4) * 4u);
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float x = __uint_as_float(v[chunk & 1][g * 4 + k]) + bb[k];
+              const float th = 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f);      // tanh(x); saturates cleanly at +-1
+              sum[k] = fmaf(vv[k], th, sum[k]);
+            }
+          }
+        }
+        args.partial[size_t(row) * n_part + tc.ch * 2 + colh] = (sum[0] + sum[1]) + (sum[2] + sum[3]);
       }
     } else if (MODE == 0) {
       const uint32_t sC = smem_base + OFF_C + uint32_t(e) * C_BUF_BYTES;

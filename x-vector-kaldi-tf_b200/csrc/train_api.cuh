@@ -362,7 +362,8 @@ int xv_train_create(xv_trainer** out, xv_model* model, int32_t num_classes, int3
   if (!out || !model) return fail(XV_EINVAL, "null argument");
   *out = nullptr;
   if (num_classes < 2 || emb1_dim < 1) return fail(XV_EINVAL, "num_classes must be >= 2 and emb1_dim >= 1");
-  if (model->topo.act != XV_ACT_RELU) return fail(XV_EINVAL, "the training step supports the ReLU topologies only");
+  if (model->topo.act != XV_ACT_RELU || model->topo.pooling != XV_POOL_STATS)
+    return fail(XV_EINVAL, "the training step supports the ReLU topologies with statistics pooling only");
   XV_CUDA(cudaSetDevice(model->device));
   xv_trainer* t = new xv_trainer();
   t->m = model;

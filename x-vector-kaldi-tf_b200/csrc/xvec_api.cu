@@ -59,6 +59,7 @@ struct Plan {
   int32_t fc_counters = 0;
   int32_t tc_splits = 1;             // K-splits of the tensor-core embedding GEMM
   size_t off_split = 0;
+  size_t off_score = 0, off_attn = 0;
   size_t off_meta = 0, off_counters = 0, off_valid = 0, off_blk_valid = 0, off_x0 = 0, off_ha = 0, off_hb = 0,
          off_hlast = 0, off_pool_partial = 0, off_stats = 0, off_partial = 0, bytes = 0;
 };
@@ -88,6 +89,10 @@ struct xv_model {
                                      // counters cost ~40 us; kept as an option and as a cross-check
   int opt_pdl = 1;                   // programmatic dependent launch between the kernels of a forward
   int opt_fc = 1;                    // 1: embed_layer-0 on tensor cores (split fp16), 0: fp32 SIMT GEMM
+  int c_pool = 0;                    // channels that are pooled: width of the last frame layer (attention pooling: half of it)
+  __half* att_w_dev = nullptr;       // attention pooling: [C, C] fp16 K-major (out channel major) copy of "attention/w:0"
+  float* att_b_dev = nullptr;        // [C]
+  float* att_v_dev = nullptr;        // [C]
   float* w0_dev = nullptr;           // [2C, E]
   float* b0_dev = nullptr;           // [E]
   int32_t* pack_lut_dev = nullptr;   // [k0_pad] spliced column -> staged feature offset (pack kernel)
@@ -133,7 +138,7 @@ Plan make_plan(const xv_model* m, int64_t total_frames, int32_t n_seg) {
   const int64_t rows = total_frames + int64_t(n_seg) * (m->gap + tdnn2::POOL_BLOCK - 1);
   p.r_pad = round_up(std::max<int64_t>(rows, 1), tdnn2::TILE_ROWS);
   const int c_last = m->topo.width[m->topo.n_frame_layers - 1];
-  const int K = 2 * c_last;
+  const int K = 2 * m->c_pool;
   p.fc_m_tiles = (n_seg + xvk::FC_BM - 1) / xvk::FC_BM;
   p.fc_n_tiles = m->topo.emb_dim / xvk::FC_BN;
   p.fc_splits = K / 256;                                       // C_last is a multiple of 128
@@ -163,6 +168,10 @@ Plan make_plan(const xv_model* m, int64_t total_frames, int32_t n_seg) {
   p.off_hlast = take(size_t(p.r_pad) * c_last * 2);          // only written when a caller asks for the last layer's activations
   p.off_pool_partial = take(size_t(p.r_pad / tdnn2::POOL_BLOCK) * 2 * c_last * 4);
   p.off_stats = take(size_t(n_seg) * K * 4);
+  if (m->topo.pooling == XV_POOL_ATTENTION) {
+    p.off_score = take(size_t(p.r_pad) * 2 * (m->c_pool / tdnn2::TILE_CH) * 4);
+    p.off_attn = take(size_t(p.r_pad) * 4);
+  }
   p.off_split = take(size_t(round_up(n_seg, tdnn2::CTA_ROWS)) * 3 * K * 2);   // rows padded to the TMA box (never read back)
   p.off_partial = take(std::max(size_t(p.fc_splits) * n_seg, size_t(p.tc_splits) * std::min<int64_t>(n_seg, FC_GROUP)) *
                        m->topo.emb_dim * 4);
@@ -171,9 +180,9 @@ Plan make_plan(const xv_model* m, int64_t total_frames, int32_t n_seg) {
 }
 
 int encode_2d(const xv_model* m, CUtensorMap* map, void* base, uint64_t inner, uint64_t outer, uint32_t box_inner,
-              uint32_t box_outer, CUtensorMapSwizzle swz) {
+              uint32_t box_outer, CUtensorMapSwizzle swz, uint64_t row_stride_elems = 0) {
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {inner * 2};                   // bytes, fp16
+  cuuint64_t strides[1] = {(row_stride_elems ? row_stride_elems : inner) * 2};   // bytes, fp16
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = m->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr,
@@ -189,6 +198,8 @@ void free_layers(xv_model* m) {
     L.w_dev = nullptr; L.bias_dev = L.scale_dev = L.shift_dev = L.alpha_dev = nullptr;
   }
   cudaFree(m->w0_dev); cudaFree(m->b0_dev); cudaFree(m->w0_split_dev);
+  cudaFree(m->att_w_dev); cudaFree(m->att_b_dev); cudaFree(m->att_v_dev);
+  m->att_w_dev = nullptr; m->att_b_dev = m->att_v_dev = nullptr;
   m->w0_dev = m->b0_dev = nullptr;
   m->w0_split_dev = nullptr;
 }
@@ -253,7 +264,23 @@ int finalize_params(xv_model* m) {
       XV_CUDA(cudaMemcpy(L.alpha_dev, alpha.data(), L.c_out * 4, cudaMemcpyHostToDevice));
     }
   }
-  const int c_last = t.width[t.n_frame_layers - 1];
+  const int c_last = m->c_pool;
+  if (t.pooling == XV_POOL_ATTENTION) {
+    const int C = m->c_pool;
+    const auto* aw = find_param(m, "attention/w:0", {C, C});
+    const auto* ab = find_param(m, "attention/b:0", {C});
+    const auto* av = find_param(m, "attention/v:0", {C});
+    if (!aw || !ab || !av) return fail(XV_ESTATE, "missing or mis-shaped attention/w:0, attention/b:0 or attention/v:0");
+    std::vector<__half> wt(size_t(C) * C);                       // einsum('ijk,kl->ijl'): [k, l] -> [l][k], K-major
+    for (int k = 0; k < C; ++k)
+      for (int l = 0; l < C; ++l) wt[size_t(l) * C + k] = __float2half_rn((*aw)[size_t(k) * C + l]);
+    XV_CUDA(cudaMalloc(&m->att_w_dev, wt.size() * sizeof(__half)));
+    XV_CUDA(cudaMalloc(&m->att_b_dev, C * 4));
+    XV_CUDA(cudaMalloc(&m->att_v_dev, C * 4));
+    XV_CUDA(cudaMemcpy(m->att_w_dev, wt.data(), wt.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    XV_CUDA(cudaMemcpy(m->att_b_dev, ab->data(), C * 4, cudaMemcpyHostToDevice));
+    XV_CUDA(cudaMemcpy(m->att_v_dev, av->data(), C * 4, cudaMemcpyHostToDevice));
+  }
   const auto* w0 = find_param(m, "embed_layer-0/w:0", {2 * c_last, t.emb_dim});
   const auto* b0 = find_param(m, "embed_layer-0/b:0", {t.emb_dim});
   if (!w0 || !b0) return fail(XV_ESTATE, "missing or mis-shaped embed_layer-0/w:0 or embed_layer-0/b:0");
@@ -446,9 +473,10 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
 
   // ---- frame-level TDNN stack: one fused tcgen05 kernel per layer --------------------------
   const int nl = m->topo.n_frame_layers;
-  const bool want_last = layer_out_dev && layer_out_dev[nl - 1];
+  const bool attention = m->topo.pooling == XV_POOL_ATTENTION;
+  const bool want_last = attention || (layer_out_dev && layer_out_dev[nl - 1]);   // attention pooling reads the stored activation
   const __half* in = x0;
-  const bool use_stack = m->opt_stack && !layer_out_dev && !m->opt_profile && !m->opt_resident && nl <= tdnn2::MAX_STACK_LAYERS;
+  const bool use_stack = m->opt_stack && !attention && !layer_out_dev && !m->opt_profile && !m->opt_resident && nl <= tdnn2::MAX_STACK_LAYERS;
   if (use_stack) {
     // ---- all frame layers in one persistent launch; layers are chained by per-row-tile completion counters ----
     tdnn2::StackArgs sa{};
@@ -556,7 +584,7 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       const int n_cl = resident ? (m->num_clusters / n_ch_tiles) * n_ch_tiles : int(std::min<int64_t>(tiles, m->num_clusters));
       const int grid = 2 * n_cl;
       // last layer: pooled partial sums (mode 1); its activation is only stored when a caller asks for it
-      for (int mode = last ? 1 : 0; mode >= 0; --mode) {
+      for (int mode = (last && !attention) ? 1 : 0; mode >= 0; --mode) {
         if (last && mode == 0 && !want_last) break;
         a.mode = mode;
         const int64_t cap = ring_cap + (mode == 1 ? 16384 : 0);          // the pooled mode has no output staging
@@ -599,16 +627,58 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
 
   // ---- statistics pooling + embed_layer-0 -----------------------------------------------
   {
-    const bool fc_tc = m->opt_fc == 1 && (2 * m->topo.width[nl - 1]) % 128 == 0 && m->topo.emb_dim % tdnn2::TILE_CH == 0;
+    if (attention) {
+      // ---- self-attention pooling (models.py:1037-1051): score GEMM on the tensor cores, softmax over time, weighted sums
+      const int C = m->c_pool, W = m->topo.width[nl - 1];
+      float* score = reinterpret_cast<float*>(ws + p.off_score);
+      float* attn = reinterpret_cast<float*>(ws + p.off_attn);
+      CUtensorMap ta, tw;
+      rc = encode_2d(m, &ta, hlast, uint64_t(C), uint64_t(r_pad), tdnn2::BLOCK_K, tdnn2::ACT_BOX_ROWS_PLAIN, CU_TENSOR_MAP_SWIZZLE_128B, uint64_t(W));
+      if (rc != XV_OK) return rc;
+      rc = encode_2d(m, &tw, m->att_w_dev, uint64_t(C), uint64_t(C), tdnn2::BLOCK_K, tdnn2::CTA_CH, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc != XV_OK) return rc;
+      tdnn2::PairArgs a{};
+      a.n_row_tiles = int32_t(r_pad / tdnn2::TILE_ROWS);
+      a.n_ch_tiles = C / tdnn2::TILE_CH;
+      a.taps = 1; a.dilation = 1; a.c_in_pad = C; a.reuse = 0;
+      a.c_out = C;
+      a.bias = m->att_b_dev; a.scale = m->att_v_dev;
+      a.partial = score;
+      a.overflow_flag = m->overflow_dev;
+      a.mode = 3;
+      a.n_act_stages = a.n_wgt_stages = int(std::min<int64_t>(tdnn2::MAX_STAGES, tdnn2::RING_BYTES / (2 * (tdnn2::ACT_BOX_ROWS_PLAIN * 128 + tdnn2::WGT_ATOM_BYTES))));
+      a.c_chunks = C / (2 * tdnn2::BLOCK_K);
+      const int64_t tiles = int64_t(a.n_row_tiles) * a.n_ch_tiles;
+      const int grid = 2 * int(std::min<int64_t>(tiles, m->num_clusters));
+      XV_PROF();
+      XV_CUDA(launch_k(pdl, tdnn2::tdnn_pair_kernel<3, 2, false>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tw, a));
+      XV_PROF();
+      XV_CUDA(cudaGetLastError());
+      ++launches;
+      XV_PROF();
+      XV_CUDA(launch_k(pdl, xvk::attn_softmax_kernel, dim3(n_seg), dim3(xvk::ATTN_THREADS), 0, stream, static_cast<const float*>(score),
+                       int32_t(2 * a.n_ch_tiles), seg, attn));
+      XV_PROF();
+      XV_CUDA(cudaGetLastError());
+      ++launches;
+      XV_PROF();
+      XV_CUDA(launch_k(pdl, xvk::attn_pool_kernel, dim3(unsigned(r_pad / 32), C / 256), dim3(256), 0, stream, static_cast<const __half*>(hlast),
+                       int32_t(W), int32_t(C), int32_t(C), static_cast<const float*>(attn), static_cast<const uint8_t*>(blk_valid), pool_partial));
+      XV_PROF();
+      XV_CUDA(cudaGetLastError());
+      ++launches;
+    }
+    const bool fc_tc = m->opt_fc == 1 && (2 * m->c_pool) % 128 == 0 && m->topo.emb_dim % tdnn2::TILE_CH == 0;
     float* stats = stats_out_dev ? stats_out_dev : (fc_tc ? nullptr : reinterpret_cast<float*>(ws + p.off_stats));
     __half* split = fc_tc ? reinterpret_cast<__half*>(ws + p.off_split) : nullptr;
     float* fc_partial = reinterpret_cast<float*>(ws + p.off_partial);
-    const int K = 2 * m->topo.width[nl - 1], E = m->topo.emb_dim;
+    const int K = 2 * m->c_pool, E = m->topo.emb_dim;
     {
       xvk::StatsArgs a{};
       a.partial = pool_partial;
       a.seg = seg;
-      a.channels = m->topo.width[nl - 1];
+      a.channels = m->c_pool;
+      a.weighted = attention ? 1 : 0;
       a.stats = stats;
       a.split = split;
       a.var_eps = m->topo.var_eps;
@@ -706,6 +776,9 @@ int xv_create(xv_model** out, int device, const xv_topology* topo) {
   if (t.n_frame_layers < 2 || t.n_frame_layers > XV_MAX_FRAME_LAYERS) return fail(XV_EINVAL, "n_frame_layers out of range");
   if (t.feat_dim <= 0) return fail(XV_EINVAL, "feat_dim must be positive");
   if (t.act != XV_ACT_RELU && t.act != XV_ACT_LRELU && t.act != XV_ACT_PRELU) return fail(XV_EINVAL, "unknown activation");
+  if (t.pooling != XV_POOL_STATS && t.pooling != XV_POOL_ATTENTION) return fail(XV_EINVAL, "unknown pooling");
+  if (t.pooling == XV_POOL_ATTENTION && t.width[t.n_frame_layers - 1] % (2 * tdnn2::TILE_CH) != 0)
+    return fail(XV_EINVAL, "attention pooling needs a last frame layer whose width is a multiple of 512");
   if (t.emb_dim <= 0 || t.emb_dim % tdnn2::TILE_CH != 0 || t.emb_dim > 4096)
     return fail(XV_EINVAL, "emb_dim must be a multiple of 256 and <= 4096");
   for (int i = 0; i < t.n_frame_layers; ++i) {
@@ -756,6 +829,7 @@ int xv_create(xv_model** out, int device, const xv_topology* topo) {
     prev = L.c_out;
   }
   m->gap = std::max(m->gap, 1);
+  m->c_pool = t.pooling == XV_POOL_ATTENTION ? prev / 2 : prev;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -769,7 +843,8 @@ int xv_create(xv_model** out, int device, const xv_topology* topo) {
     void (*kernels[])(CUtensorMap, CUtensorMap, CUtensorMap, tdnn2::PairArgs) = {
         tdnn2::tdnn_pair_kernel<0, 1, false>, tdnn2::tdnn_pair_kernel<0, 2, false>, tdnn2::tdnn_pair_kernel<1, 1, false>,
         tdnn2::tdnn_pair_kernel<1, 2, false>, tdnn2::tdnn_pair_kernel<0, 1, true>,  tdnn2::tdnn_pair_kernel<0, 2, true>,
-        tdnn2::tdnn_pair_kernel<1, 1, true>,  tdnn2::tdnn_pair_kernel<1, 2, true>,  tdnn2::tdnn_pair_kernel<2, 2, false>};
+        tdnn2::tdnn_pair_kernel<1, 1, true>,  tdnn2::tdnn_pair_kernel<1, 2, true>,  tdnn2::tdnn_pair_kernel<2, 2, false>,
+        tdnn2::tdnn_pair_kernel<3, 2, false>};
     for (auto k : kernels)
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
     if (e == cudaSuccess)
@@ -863,8 +938,13 @@ int xv_set_param(xv_model* m, const char* tf_var_name, const float* host, const 
     else known = used = false;
   } else if (scope_of("embed_layer-", idx, leaf)) {
     known = true;                            // embed_layer-*/prelu/prelu:0 etc.: training-only, ignored
-    if (idx == 0 && leaf == "w:0") { used = true; want = {2 * t.width[t.n_frame_layers - 1], t.emb_dim}; }
+    if (idx == 0 && leaf == "w:0") { used = true; want = {2 * m->c_pool, t.emb_dim}; }
     else if (idx == 0 && leaf == "b:0") { used = true; want = {t.emb_dim}; }
+  } else if (name.compare(0, 10, "attention/") == 0 && t.pooling == XV_POOL_ATTENTION) {
+    known = used = true;
+    if (name == "attention/w:0") want = {m->c_pool, m->c_pool};
+    else if (name == "attention/b:0" || name == "attention/v:0") want = {m->c_pool};
+    else known = used = false;
   } else if (name.compare(0, 7, "output/") == 0 || name.compare(0, 10, "attention/") == 0) {
     known = true;
   }

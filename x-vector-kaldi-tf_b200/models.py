@@ -50,7 +50,8 @@ def _create_engine(meta, params, device):
     from ._native import XvecEngine
     eng = XvecEngine(meta["kernel_sizes"], meta["dilation_rates"], meta["layer_sizes"],
                      meta["embedding_sizes"][0], meta["input_feature_dim"], device=device,
-                     bn_eps=BN_EPSILON, var_eps=VAR2STD_EPSILON, activation=meta.get("activation", "relu"))
+                     bn_eps=BN_EPSILON, var_eps=VAR2STD_EPSILON, activation=meta.get("activation", "relu"),
+                     pooling=meta.get("pooling", "stats"))
     # optimizer state saved by train_one_iteration ("<var>/Adam:0", "<var>/Adam_1:0", "beta*_power:0") is not a network variable
     eng.set_params({k: v for k, v in params.items() if not k.endswith(("/Adam:0", "/Adam_1:0", "_power:0"))})
     return eng
@@ -94,6 +95,7 @@ class Model(object):
     kernel_sizes = [5, 5, 7, 1, 1]
     dilation_rates = [1, 1, 1, 1, 1]
     embedding_sizes = [512, 512]
+    pooling = "stats"              # stats (mean | std over time) | attention (models.py:1037-1051)
     activation = "relu"            # frame-layer nonlinearity: relu | lrelu (0.2) | prelu (per-channel)
     init = "trunc_normal"          # model_0 initialisation: trunc_normal (sigma 0.1) | he
 
@@ -116,8 +118,8 @@ class Model(object):
         seed = int(seed) if seed is not None else int(np.random.SeedSequence().entropy % (2 ** 31))
         params = make_params(self.kernel_sizes, self.layer_sizes, self.embedding_sizes,
                              feat_dim=input_feature_dim, num_classes=num_classes, weight_set="A", seed=seed,
-                             activation=self.activation, init=self.init)
-        meta = dict(format=META_FORMAT, model_class=type(self).__name__, num_classes=int(num_classes),
+                             activation=self.activation, init=self.init, pooling=self.pooling)
+        meta = dict(pooling=self.pooling, format=META_FORMAT, model_class=type(self).__name__, num_classes=int(num_classes),
                     input_feature_dim=int(input_feature_dim), kernel_sizes=list(self.kernel_sizes),
                     dilation_rates=list(self.dilation_rates), layer_sizes=list(self.layer_sizes),
                     embedding_sizes=list(self.embedding_sizes), activation=self.activation)
@@ -172,7 +174,7 @@ class Model(object):
                         layer_sizes=[int(params["frame_level_info_layer-%d/w:0" % i].shape[2]) for i in range(n_layers)],
                         embedding_sizes=[int(params["embed_layer-%d/w:0" % i].shape[1]) for i in range(2)
                                          if "embed_layer-%d/w:0" % i in params],
-                        activation=self.activation)
+                        activation=self.activation, pooling=self.pooling)
         elif meta is None:
             raise RuntimeError("%s/model.meta is not an %s header and there is no model.index checkpoint bundle beside it"
                                % (input_dir, META_FORMAT))
@@ -188,6 +190,7 @@ class Model(object):
         self.layer_sizes = list(meta["layer_sizes"])
         self.embedding_sizes = list(meta["embedding_sizes"])
         self.activation = meta.get("activation", "relu")
+        self.pooling = meta.get("pooling", "stats")
         self.graph = meta
         if sess is not None:
             sess.params, sess.meta = params, meta
@@ -213,7 +216,7 @@ class Model(object):
     def _create_trainer(self, device):
         """Engine + trainer holding this model's variables, moving statistics and (if saved) Adam state."""
         from ._native import XvecTrainer, TRAIN_ADAM_M, TRAIN_ADAM_V
-        if self.activation != "relu":
+        if self.activation != "relu" or self.pooling != "stats":
             raise NotImplementedError("the training step covers the ReLU topologies (Model, ModelWithoutDropout, "
                                       "ModelWithoutDropoutTdnn); %s uses %s" % (type(self).__name__, self.activation))
         eng = self._get_engine(device)
@@ -655,3 +658,10 @@ class ModelL2LossWithoutDropoutLRelu(ModelWithoutDropout):
 class ModelL2LossWithoutDropoutReluHeInit(ModelWithoutDropout):
     """ReLU with He-normal weights / He-uniform biases at model_0 (reference models.py:1118-1244)."""
     init = "he"
+
+
+class ModelL2LossWithoutDropoutLReluAttention(ModelL2LossWithoutDropoutLRelu):
+    """Self-attention statistics pooling (reference models.py:983-1100): the last frame layer is 6*512 wide and split
+    into the score input h1 and the pooled half h2; ``attention/{w,b,v}``; leaky ReLU 0.2 frame layers."""
+    layer_sizes = [512, 512, 512, 512, 6 * 512]
+    pooling = "attention"

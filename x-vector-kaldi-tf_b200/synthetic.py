@@ -45,7 +45,7 @@ def _trunc_normal(rng, shape, sigma):
 
 
 def make_params(kernel_sizes, layer_sizes, embedding_sizes, feat_dim=FEAT_DIM, num_classes=0,
-                weight_set="A", seed=100, activation="relu", init="trunc_normal"):
+                weight_set="A", seed=100, activation="relu", init="trunc_normal", pooling="stats"):
     """Parameter dict keyed by the reference's TF variable names (models.py:199-210)."""
     p = {}
     prev = feat_dim
@@ -81,7 +81,19 @@ def make_params(kernel_sizes, layer_sizes, embedding_sizes, feat_dim=FEAT_DIM, n
                                       else rng.uniform(-0.2, 0.5, width).astype(np.float32))
         bn(s, width, rng)
         prev = width
-    prev *= 2
+    if pooling == "attention":       # models.py:1035-1041: square "attention/w" (trunc normal 0.1), b = v = 0.1; stats width = prev
+        C = prev // 2
+        rng = np.random.Generator(np.random.PCG64(seed + 40))
+        if weight_set == "A":
+            p["attention/w:0"] = _trunc_normal(rng, (C, C), 0.1)
+            p["attention/b:0"] = np.full(C, 0.1, np.float32)
+            p["attention/v:0"] = np.full(C, 0.1, np.float32)
+        else:
+            p["attention/w:0"] = (rng.standard_normal((C, C)) * np.sqrt(1.0 / C)).astype(np.float32)
+            p["attention/b:0"] = rng.uniform(-0.1, 0.1, C).astype(np.float32)
+            p["attention/v:0"] = (rng.standard_normal(C) * 0.05).astype(np.float32)
+    else:
+        prev *= 2
     for i, width in enumerate(embedding_sizes):
         rng = np.random.Generator(np.random.PCG64(seed + 50 + i))
         s = "embed_layer-%d/" % i
