@@ -364,27 +364,31 @@ attn_pool_kernel(const __half* __restrict__ h, int32_t row_stride, int32_t col0,
   __shared__ float red[8][2][256];
   cudaTriggerProgrammaticLaunchCompletion();
   cudaGridDependencySynchronize();
-  const int blk = blockIdx.x, c0 = blockIdx.y * 256;
+  const int n_slab = C / 256;                                   // 1-D grid, channel slab fastest: the CTAs that share a
+  const int blk = blockIdx.x / n_slab, c0 = (blockIdx.x % n_slab) * 256;   // row block run together (whole DRAM rows)
   const int nv = blk_valid[blk];
   if (nv == 0) return;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float s1[8], s2[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+  uint4 u[4];
+  float a[4];
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {                    // all loads first (rows past nv are gap rows: zeros, weight 0)
+    const int r = w * 4 + rr;
+    const int64_t row = int64_t(blk) * 32 + r;
+    u[rr] = __ldg(reinterpret_cast<const uint4*>(h + row * row_stride + col0 + c0 + lane * 8));
+    a[rr] = r < nv ? __ldg(attn + row) : 0.f;
+  }
 #pragma unroll
   for (int rr = 0; rr < 4; ++rr) {
-    const int r = w * 4 + rr;
-    if (r < nv) {
-      const int64_t row = int64_t(blk) * 32 + r;
-      const float a = __ldg(attn + row);
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(h + row * row_stride + col0 + c0 + lane * 8));
-      const __half2* hp = reinterpret_cast<const __half2*>(&u);
+    const __half2* hp = reinterpret_cast<const __half2*>(&u[rr]);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = __half22float2(hp[i]);
-        s1[2 * i] = fmaf(a, f.x, s1[2 * i]);         s2[2 * i] = fmaf(a * f.x, f.x, s2[2 * i]);
-        s1[2 * i + 1] = fmaf(a, f.y, s1[2 * i + 1]); s2[2 * i + 1] = fmaf(a * f.y, f.y, s2[2 * i + 1]);
-      }
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(hp[i]);
+      s1[2 * i] = fmaf(a[rr], f.x, s1[2 * i]);         s2[2 * i] = fmaf(a[rr] * f.x, f.x, s2[2 * i]);
+      s1[2 * i + 1] = fmaf(a[rr], f.y, s1[2 * i + 1]); s2[2 * i + 1] = fmaf(a[rr] * f.y, f.y, s2[2 * i + 1]);
     }
   }
 #pragma unroll

@@ -582,7 +582,7 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
     if (rc != XV_OK) return rc;
     in = out;
     if (i == nl - 1) {
-      TR_LAUNCH("blk_col_sums_kernel<0>", trk::blk_col_sums_kernel<0>, dim3(n_seg, L.c_out / trk::COLS_PER_CTA), dim3(256), 0, static_cast<const __half*>(out), static_cast<const __half*>(nullptr), L.c_out, t->seg_stride, t->partial);
+      TR_LAUNCH("blk_col_sums_kernel<0>", trk::blk_col_sums_kernel<0>, dim3(L.c_out / trk::COLS_PER_CTA, n_seg), dim3(256), 0, static_cast<const __half*>(out), static_cast<const __half*>(nullptr), L.c_out, t->seg_stride, t->partial);
     }
   }
   for (int i = 0; i < nl && training; ++i) {
@@ -593,7 +593,7 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
     // the last layer sums per segment (= the pooling sums), the others per 128 rows
     const bool last = i == nl - 1;
     const int32_t parts = last ? n_seg : n_part;
-    TR_LAUNCH("blk_col_sums_kernel<0>", trk::blk_col_sums_kernel<0>, dim3(parts, L.c_out / trk::COLS_PER_CTA), dim3(256), 0, static_cast<const __half*>(L.r), static_cast<const __half*>(nullptr), L.c_out, last ? t->seg_stride : ROWS_PER_PART, t->partial);
+    TR_LAUNCH("blk_col_sums_kernel<0>", trk::blk_col_sums_kernel<0>, dim3(L.c_out / trk::COLS_PER_CTA, parts), dim3(256), 0, static_cast<const __half*>(L.r), static_cast<const __half*>(nullptr), L.c_out, last ? t->seg_stride : ROWS_PER_PART, t->partial);
     trk::BnFwdArgs b{};
     b.partial = t->partial; b.n_blk = parts; b.C = L.c_out; b.n_rows = n_rows;
     b.eps = m->topo.bn_eps; b.decay = BN_DECAY;
@@ -673,7 +673,7 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
     a.gamma = t->params + LL.off_gamma; a.mean = LL.bn; a.inv = LL.bn + C; a.scale = LL.bn + 2 * C;
     a.coefA = t->coefA; a.coefG = t->coefG; a.d_gamma = grad + LL.off_gamma; a.d_beta = grad + LL.off_beta;
     TR_LAUNCH("pool_bwd_coef_kernel", trk::pool_bwd_coef_kernel, dim3((C + 31) / 32), dim3(dim3(32, trk::SEG_Y)), 0, a);
-    TR_LAUNCH("pool_relu_bwd_kernel", trk::pool_relu_bwd_kernel, dim3(n_seg, C / trk::COLS_PER_CTA), dim3(256), 0, static_cast<const __half*>(LL.r), C, t->seg_stride, static_cast<const float*>(t->coefA), static_cast<const float*>(t->coefG), LL.dz, t->partial1, m->overflow_dev);
+    TR_LAUNCH("pool_relu_bwd_kernel", trk::pool_relu_bwd_kernel, dim3(C / trk::COLS_PER_CTA, n_seg), dim3(256), 0, static_cast<const __half*>(LL.r), C, t->seg_stride, static_cast<const float*>(t->coefA), static_cast<const float*>(t->coefG), LL.dz, t->partial1, m->overflow_dev);
     TR_LAUNCH("colsum_finalize_kernel", trk::colsum_finalize_kernel, dim3(C / 32), dim3(32, trk::RED_Y), 0, static_cast<const float*>(t->partial1), n_seg, C, inv_S, grad + LL.off_b);
   }
 
@@ -682,14 +682,14 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
     TrFrame& L = t->frames[i];
     if (i < nl - 1) {
       // dy_i (written by the data gradient of layer i+1) -> BatchNorm + ReLU backward -> dz_i
-      TR_LAUNCH("blk_col_sums_kernel<1>", trk::blk_col_sums_kernel<1>, dim3(n_part, L.c_out / trk::COLS_PER_CTA), dim3(256), 0, static_cast<const __half*>(L.dy), static_cast<const __half*>(L.r), L.c_out, ROWS_PER_PART, t->partial);
+      TR_LAUNCH("blk_col_sums_kernel<1>", trk::blk_col_sums_kernel<1>, dim3(L.c_out / trk::COLS_PER_CTA, n_part), dim3(256), 0, static_cast<const __half*>(L.dy), static_cast<const __half*>(L.r), L.c_out, ROWS_PER_PART, t->partial);
       trk::BnBwdArgs b{};
       b.partial = t->partial; b.n_blk = n_part; b.C = L.c_out; b.n_rows = n_rows; b.inv_loss_scale = inv_S;
       b.gamma = t->params + L.off_gamma; b.mean = L.bn; b.inv = L.bn + L.c_out;
       b.cA = t->cA; b.cB = t->cB; b.cC = t->cC;
       b.d_gamma = grad + L.off_gamma; b.d_beta = grad + L.off_beta;
       TR_LAUNCH("bn_bwd_finalize_kernel", trk::bn_bwd_finalize_kernel, dim3(L.c_out / 32), dim3(dim3(32, trk::RED_Y)), 0, b);
-      TR_LAUNCH("bn_relu_bwd_kernel", trk::bn_relu_bwd_kernel, dim3(n_part, L.c_out / trk::COLS_PER_CTA), dim3(256), 0, static_cast<const __half*>(L.dy), static_cast<const __half*>(L.r), L.c_out, ROWS_PER_PART, static_cast<const float*>(t->cA), static_cast<const float*>(t->cB), static_cast<const float*>(t->cC), L.dz, t->partial1, m->overflow_dev);
+      TR_LAUNCH("bn_relu_bwd_kernel", trk::bn_relu_bwd_kernel, dim3(L.c_out / trk::COLS_PER_CTA, n_part), dim3(256), 0, static_cast<const __half*>(L.dy), static_cast<const __half*>(L.r), L.c_out, ROWS_PER_PART, static_cast<const float*>(t->cA), static_cast<const float*>(t->cB), static_cast<const float*>(t->cC), L.dz, t->partial1, m->overflow_dev);
       TR_LAUNCH("colsum_finalize_kernel", trk::colsum_finalize_kernel, dim3(L.c_out / 32), dim3(32, trk::RED_Y), 0, static_cast<const float*>(t->partial1), n_part, L.c_out, inv_S, grad + L.off_b);
     }
     const __half* x = (i == 0) ? t->x0 : t->frames[i - 1].y;

@@ -53,7 +53,7 @@ blk_col_sums_kernel(const __half* __restrict__ x, const __half* __restrict__ y, 
   cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
   cudaGridDependencySynchronize();
   __shared__ float red[8][2][COLS_PER_CTA];
-  const int part = blockIdx.x, c0 = blockIdx.y * COLS_PER_CTA;
+  const int part = blockIdx.y, c0 = blockIdx.x * COLS_PER_CTA;      // slab fastest: CTAs sharing rows run together
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float s1[8], s2[8];
 #pragma unroll
@@ -249,7 +249,7 @@ bn_relu_bwd_kernel(const __half* __restrict__ dy, const __half* __restrict__ r, 
   cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
   cudaGridDependencySynchronize();
   __shared__ float red[8][COLS_PER_CTA];
-  const int part = blockIdx.x, c0 = blockIdx.y * COLS_PER_CTA;
+  const int part = blockIdx.y, c0 = blockIdx.x * COLS_PER_CTA;      // slab fastest: CTAs sharing rows run together
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = c0 + lane * 8;
   float ka[8], kb[8], kc[8], s[8];
@@ -413,7 +413,7 @@ pool_relu_bwd_kernel(const __half* __restrict__ r, int32_t C, int32_t seg_stride
   cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
   cudaGridDependencySynchronize();
   __shared__ float red[8][COLS_PER_CTA];
-  const int seg = blockIdx.x, c0 = blockIdx.y * COLS_PER_CTA;
+  const int seg = blockIdx.y, c0 = blockIdx.x * COLS_PER_CTA;       // slab fastest: CTAs sharing rows run together
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = c0 + lane * 8;
   float ka[8], kg[8], s[8];

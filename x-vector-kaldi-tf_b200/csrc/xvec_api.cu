@@ -662,7 +662,7 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       XV_CUDA(cudaGetLastError());
       ++launches;
       XV_PROF();
-      XV_CUDA(launch_k(pdl, xvk::attn_pool_kernel, dim3(unsigned(r_pad / 32), C / 256), dim3(256), 0, stream, static_cast<const __half*>(hlast),
+      XV_CUDA(launch_k(pdl, xvk::attn_pool_kernel, dim3(unsigned(r_pad / 32) * (C / 256)), dim3(256), 0, stream, static_cast<const __half*>(hlast),
                        int32_t(W), int32_t(C), int32_t(C), static_cast<const float*>(attn), static_cast<const uint8_t*>(blk_valid), pool_partial));
       XV_PROF();
       XV_CUDA(cudaGetLastError());
