@@ -80,7 +80,8 @@ int xv_train_sync_model(xv_trainer* t);
  * loss-scaled gradients w.r.t. the pre-activation / the BatchNorm output; fp32 arrays as stored: "h0" (pooled
  * statistics), "z5", "y5", "z6", "y6", "logits", "dlogits", "dh0".  Returns the number of floats (or < 0). */
 int64_t xv_train_debug_tensor(xv_trainer* t, const char* name, float* host_out, int64_t capacity);
-/* Options: "loss_scale" (0 = automatic: 8 * frames rounded to a power of two), "wgrad_lbo", "wgrad_sbo". */
+/* Options: "loss_scale" (0 = automatic: 8 * frames rounded to a power of two), "wgrad_lbo", "wgrad_sbo" (diagnostics),
+ * "seg_fused" (1: the segment level of a step as one cooperative kernel instead of chained launches), "seg_ctas". */
 int xv_train_set_option(xv_trainer* t, const char* name, double value);
 int32_t xv_train_last_launch_count(const xv_trainer* t);
 /* With the xv_model option "profile" on, every launch of a step is bracketed by CUDA events: read the times with

@@ -26,6 +26,9 @@ def main():
     eng = _native.XvecEngine(topo["kernel_sizes"], topo["dilations"], topo["layer_sizes"], 512, 23, device=0)
     tr = _native.XvecTrainer(eng, NC, 512)
     tr.set_params(P)
+    for kv in os.environ.get("XVEC_TRAIN_OPTS", "").split(","):
+        if "=" in kv:
+            tr.set_option(kv.split("=")[0], float(kv.split("=")[1]))
     feats = torch.from_numpy(synthetic.mfcc(5, B * T)).cuda()
     lab = torch.from_numpy(np.random.default_rng(5).integers(0, NC, B).astype(np.int32)).cuda()
     for _ in range(5):
