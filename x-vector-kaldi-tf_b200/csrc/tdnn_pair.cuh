@@ -165,7 +165,10 @@ struct TileCursor {
   }
 };
 
-template <int MODE, int ATOMS, bool LEAKY>
+// STATS (mode 0 only, training): the epilogue also leaves the column sums of every [32 rows x 32 channels] box it stores --
+// of the fp16 values as stored -- in partial[row_block][{sum, sum of squares}][channel]: the batch-norm moments of the training
+// branch (tf_block.py:19) and the pooling sums of the last layer come out of the layer kernel instead of a second pass over HBM.
+template <int MODE, int ATOMS, bool LEAKY, bool STATS = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations in  [R_pad, C_in_pad] fp16
                  const __grid_constant__ CUtensorMap tmap_wgt,   // weights [C_out, taps*C_in_pad] fp16 (K-major)
@@ -541,6 +544,22 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
           if (lane == 0) {
             ptx::tma_store_2d(&tmap_out, buf, ch0 + colh * 128 + chunk * C_CHUNK, r_cta + q * 32);
             ptx::tma_store_commit();
+          }
+          if (STATS) {
+            // lane = channel: read the staged box column-wise (row r is one 64-byte line whose 16-byte pieces are XOR-swizzled
+            // by (r >> 1) & 3, so the 32 lanes of a step read one whole line: conflict free), fixed order over the rows
+            float c1 = 0.f, c2 = 0.f;
+            const uint32_t piece = uint32_t(lane) >> 3, within = (uint32_t(lane) & 7u) * 2u;
+#pragma unroll
+            for (uint32_t r = 0; r < 32; ++r) {
+              const uint32_t h = ptx::lds_u16(buf + r * (C_CHUNK * 2) + ((piece ^ ((r >> 1) & 3u)) << 4) + within);
+              const float f = __half2float(__ushort_as_half(static_cast<unsigned short>(h)));
+              c1 += f;
+              c2 = fmaf(f, f, c2);
+            }
+            float* dstp = args.partial + size_t((r_cta + q * 32) >> 5) * 2 * args.c_out + ch0 + colh * 128 + chunk * C_CHUNK + lane;
+            dstp[0] = c1;
+            dstp[args.c_out] = c2;
           }
         }
         if (has_next) store_params(acc ^ 1u, nb, nsc, nsh, nal);

@@ -63,6 +63,7 @@ struct xv_trainer {
   bool operands_dirty = true;
   double opt_loss_scale = 0.0;
   int opt_wgrad_lbo = wgrad::BOX_BYTES, opt_wgrad_sbo = 1024;
+  int opt_fused_stats = 1;           // 1: BatchNorm / pooling column sums come out of the layer kernel's epilogue (STATS instantiation)
   int opt_seg_ctas = 0, seg_ctas_per_sm = 0;
   int opt_seg_fused = 0;             // 1: the whole segment level of a training step in ONE cooperative kernel (seg_level.cuh).
                                      // Same results to fp32 rounding, but measured no faster on B200 (0.226 ms vs ~0.2 ms for the
@@ -218,7 +219,7 @@ int tr_ensure_workspace(xv_trainer* t, int32_t n_seg, int32_t seg_len) {
 // One frame-level contraction through tdnn_pair_kernel<0, 2, LEAKY> (store mode): out = act(in (*) w + bias)*scale + shift
 int tr_pair_layer(xv_trainer* t, cudaStream_t stream, const char* name, const __half* in, int c_in_gemm, __half* out, int c_out,
                   const __half* w, int k_total, int gemm_taps, int dilation, const float* bias, const float* scale,
-                  const float* shift, const float* alpha) {
+                  const float* shift, const float* alpha, float* col_partial = nullptr) {
   xv_model* m = t->m;
   const int64_t r_pad = t->r_pad;
   const int halo = (gemm_taps - 1) / 2 * dilation;
@@ -244,7 +245,7 @@ int tr_pair_layer(xv_trainer* t, cudaStream_t stream, const char* name, const __
   a.bias = bias; a.scale = scale; a.shift = shift; a.alpha = alpha;
   a.row_valid = t->row_valid;
   a.blk_valid = t->blk_valid;
-  a.partial = nullptr;
+  a.partial = col_partial;           // STATS instantiation: per 32-row block column sums of the stored output
   a.overflow_flag = m->overflow_dev;
   a.mode = 0;
   const int64_t cap = tdnn2::RING_BYTES;
@@ -260,7 +261,8 @@ int tr_pair_layer(xv_trainer* t, cudaStream_t stream, const char* name, const __
   const int grid = 2 * int(std::min<int64_t>(tiles, m->num_clusters));
   const bool pdl = m->opt_pdl != 0 && !m->opt_profile;
   TR_BEGIN(name);
-  if (alpha) TR_CUDA(launch_k(pdl, tdnn2::tdnn_pair_kernel<0, 2, true>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
+  if (col_partial) TR_CUDA(launch_k(pdl, tdnn2::tdnn_pair_kernel<0, 2, false, true>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
+  else if (alpha) TR_CUDA(launch_k(pdl, tdnn2::tdnn_pair_kernel<0, 2, true>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
   else TR_CUDA(launch_k(pdl, tdnn2::tdnn_pair_kernel<0, 2, false>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
   TR_END();
   return XV_OK;
@@ -453,6 +455,7 @@ int xv_train_create(xv_trainer** out, xv_model* model, int32_t num_classes, int3
   }
   for (auto& S : t->seg) alloc0(&S.bn, 2 * int64_t(S.out));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad::wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wgrad::SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tdnn2::tdnn_pair_kernel<0, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     std::string msg = std::string("xv_train_create: ") + cudaGetErrorName(e) + ": " + cudaGetErrorString(e);
@@ -523,6 +526,7 @@ int xv_train_set_option(xv_trainer* t, const char* name, double value) {
   else if (n == "wgrad_lbo") t->opt_wgrad_lbo = int(value);
   else if (n == "wgrad_sbo") t->opt_wgrad_sbo = int(value);
   else if (n == "seg_fused") t->opt_seg_fused = value != 0.0;
+  else if (n == "fused_stats") t->opt_fused_stats = value != 0.0;
   else if (n == "seg_ctas") { t->opt_seg_ctas = int(value); t->seg_ctas_per_sm = 0; }
   else return fail(XV_EINVAL, "unknown option: " + n);
   return XV_OK;
@@ -602,13 +606,17 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
   }
   for (int i = 0; i < nl && training; ++i) {
     TrFrame& L = t->frames[i];
+    // the layer kernel's epilogue leaves the per-32-row-block column sums of r in t->partial (no second pass over HBM)
     rc = tr_pair_layer(t, stream, "tdnn_pair_kernel[fwd]", in, L.c_in_gemm, L.r, L.c_out, L.wf, L.k_total, L.gemm_taps, L.dil,
-                       t->params + L.off_b, t->ones, t->zeros, nullptr);
+                       t->params + L.off_b, t->ones, t->zeros, nullptr, t->opt_fused_stats ? t->partial : nullptr);
     if (rc != XV_OK) return rc;
-    // the last layer sums per segment (= the pooling sums), the others per 128 rows
     const bool last = i == nl - 1;
-    const int32_t parts = last ? n_seg : n_part;
-    TR_LAUNCH("blk_col_sums_kernel<0>", trk::blk_col_sums_kernel<0>, dim3(L.c_out / trk::COLS_PER_CTA, parts), dim3(256), 0, static_cast<const __half*>(L.r), static_cast<const __half*>(nullptr), L.c_out, last ? t->seg_stride : ROWS_PER_PART, t->partial);
+    int32_t parts = int32_t(r_pad / 32);
+    if (!t->opt_fused_stats) {
+      // separate pass: the last layer sums per segment (= the pooling sums), the others per 128 rows
+      parts = last ? n_seg : n_part;
+      TR_LAUNCH("blk_col_sums_kernel<0>", trk::blk_col_sums_kernel<0>, dim3(L.c_out / trk::COLS_PER_CTA, parts), dim3(256), 0, static_cast<const __half*>(L.r), static_cast<const __half*>(nullptr), L.c_out, last ? t->seg_stride : ROWS_PER_PART, t->partial);
+    }
     trk::BnFwdArgs b{};
     b.partial = t->partial; b.n_blk = parts; b.C = L.c_out; b.n_rows = n_rows;
     b.eps = m->topo.bn_eps; b.decay = BN_DECAY;
@@ -626,7 +634,7 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
   const int C = LL.c_out;
   {
     trk::PoolFwdArgs a{};
-    a.partial = t->partial; a.C = C; a.n_seg = n_seg; a.blks_per_seg = 1;
+    a.partial = t->partial; a.C = C; a.n_seg = n_seg; a.blks_per_seg = (training && t->opt_fused_stats) ? t->seg_stride / 32 : 1;
     a.seg_len = float(seg_len); a.var_eps = m->topo.var_eps;
     a.scale = training ? LL.bn + 2 * C : t->ones;           // evaluation: the block sums are already those of y
     a.shift = training ? LL.bn + 3 * C : t->zeros;
