@@ -68,7 +68,9 @@ int xv_train_forward_backward(xv_trainer* t, const float* feats_dev, const int32
 int xv_train_eval(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, int32_t n_seg, int32_t seg_len,
                   float* loss_acc_dev, void* stream);
 /* Adam update (the optimizer half of models.py:263) with gradient grad_dev * grad_scale (NULL = own buffer;
- * grad_scale = 1/world_size after a sum all-reduce), then refreshes the fp16 operand copies.  Enqueue only. */
+ * grad_scale = 1/world_size after a sum all-reduce), then refreshes the fp16 operand copies.  Enqueue only.
+ * If a loss-scaled fp16 gradient overflowed since the last xv_check_overflow(model), the update is skipped on the device
+ * (variables and slots untouched); the caller sees XV_EOVERFLOW from xv_check_overflow and lowers "loss_scale". */
 int xv_train_apply(xv_trainer* t, const float* grad_dev, float learning_rate, float grad_scale, void* stream);
 
 /* Copies the current variables and moving statistics into the xv_model, so that xv_forward / xv_extract_host

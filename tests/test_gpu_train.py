@@ -411,3 +411,25 @@ def test_train_dnn_driver_end_to_end(tmp_path):
     before = os.path.getmtime(os.path.join(nnet, "model_4", "model.npz"))
     train_dnn.train(args)
     assert os.path.getmtime(os.path.join(nnet, "model_4", "model.npz")) == before
+
+
+def test_overflowing_gradients_skip_the_update_and_a_lower_loss_scale_recovers():
+    p = Problem("ModelWithoutDropoutTdnn", "B", 8, 64, 50)
+    try:
+        before = p.tr.download(p.native.TRAIN_PARAMS)
+        p.tr.set_option("loss_scale", 2.0 ** 40)                 # absurd: every frame-level gradient overflows fp16
+        p.tr.forward_backward(p.feats, p.lab, p.B, p.T)
+        p.tr.apply(1e-3)
+        torch.cuda.synchronize()
+        with pytest.raises(p.native.XvecError) as ei:
+            p.eng.check_overflow()
+        assert ei.value.code == p.native.XV_EOVERFLOW
+        assert np.array_equal(p.tr.download(p.native.TRAIN_PARAMS), before)       # adam_kernel left everything alone
+        assert not p.tr.download(p.native.TRAIN_ADAM_M).any()
+        p.tr.set_option("loss_scale", 0)                         # automatic again; the flag was cleared by check_overflow
+        la = p.step()
+        p.tr.apply(1e-3)
+        torch.cuda.synchronize()
+        assert np.isfinite(la).all() and not np.array_equal(p.tr.download(p.native.TRAIN_PARAMS), before)
+    finally:
+        p.close()

@@ -541,7 +541,7 @@ namespace {
 int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, int32_t n_seg, int32_t seg_len,
             float* grad_dev, float* loss_acc_dev, void* stream_, bool training) {
   if (!t || !feats_dev || !labels_dev || !loss_acc_dev) return fail(XV_EINVAL, "null argument");
-  if (n_seg < 2 || seg_len < 1) return fail(XV_EINVAL, "need n_seg >= 2 and seg_len >= 1");
+  if (n_seg < 1 || seg_len < 1) return fail(XV_EINVAL, "need n_seg >= 1 and seg_len >= 1");
   xv_model* m = t->m;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   XV_CUDA(cudaSetDevice(m->device));
@@ -815,7 +815,8 @@ int xv_train_apply(xv_trainer* t, const float* grad_dev, float learning_rate, fl
   t->step += 1;
   const double b1t = std::pow(double(ADAM_B1), double(t->step)), b2t = std::pow(double(ADAM_B2), double(t->step));
   const float lr_t = float(double(learning_rate) * std::sqrt(1.0 - b2t) / (1.0 - b1t));
-  TR_LAUNCH("adam_kernel", trk::adam_kernel, dim3(unsigned((t->n_params + 255) / 256)), dim3(256), 0, t->params, g, t->adam_m, t->adam_v, t->n_params, lr_t, ADAM_B1, ADAM_B2, ADAM_EPS, grad_scale);
+  TR_LAUNCH("adam_kernel", trk::adam_kernel, dim3(unsigned((t->n_params + 255) / 256)), dim3(256), 0, t->params, g, t->adam_m, t->adam_v, t->n_params, lr_t, ADAM_B1, ADAM_B2, ADAM_EPS, grad_scale,
+            static_cast<const uint32_t*>(t->m->overflow_dev));
   return tr_repack(t, stream);
 }
 

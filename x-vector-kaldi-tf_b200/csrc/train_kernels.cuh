@@ -721,9 +721,12 @@ __global__ void __launch_bounds__(256) colsum_rows_kernel(const float* __restric
 // tf.train.AdamOptimizer._apply_dense: m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr_t * m / (sqrt(v) + eps)
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
-            float lr_t, float b1, float b2, float eps, float grad_scale) {
+            float lr_t, float b1, float b2, float eps, float grad_scale, const uint32_t* __restrict__ skip_flag) {
   cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
   cudaGridDependencySynchronize();
+  // a loss-scaled fp16 gradient overflowed somewhere in this step (the flag xv_check_overflow reports): the gradient is not
+  // trustworthy, leave variables and slots alone (what a dynamic loss scaler does) -- the caller lowers the loss scale
+  if (skip_flag != nullptr && *skip_flag != 0u) return;
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float gi = g[i] * grad_scale;

@@ -267,6 +267,7 @@ class Model(object):
         start_minibatch = 1
         total_segments, minibatch_segments, total_segments_len = 0, 0, 0
         total_gpu_waiting, total_disk_waiting = 0.0, 0.0
+        loss_scale = None                           # None: the library's automatic loss scale
         done = []                                   # indices into `results` of the minibatches that ran
         window = []                                 # ... since the last log line
         start_time = time.time()
@@ -326,7 +327,17 @@ class Model(object):
             end_minibatch = minibatch_idx + 1
             if training and end_minibatch % print_interval == 0:
                 compute.synchronize()
-                eng.check_overflow(compute)
+                try:
+                    eng.check_overflow(compute)
+                except Exception as e:                                   # noqa: BLE001
+                    if getattr(e, "code", None) != -5:                   # XV_EOVERFLOW
+                        raise
+                    # a loss-scaled fp16 gradient left the fp16 range: the optimizer skipped every update since (adam_kernel
+                    # tests the same flag); lower the loss scale and go on, as a dynamic loss scaler does
+                    loss_scale = (loss_scale or float(2 ** int(np.ceil(np.log2(8.0 * n_seg * seg_len))))) / 16.0
+                    tr.set_option("loss_scale", loss_scale)
+                    logger.warning("fp16 overflow in the gradients of minibatches %d-%d: their updates were skipped; loss scale "
+                                   "lowered to %g" % (start_minibatch, end_minibatch, loss_scale))
                 res = results[window].cpu().numpy().astype(np.float64)
                 cnt = end_minibatch - start_minibatch + 1
                 minibatch_loss, minibatch_accuracy = res[:, 0].sum(), res[:, 1].sum()
