@@ -236,6 +236,23 @@ def test_step_is_bit_reproducible(prob):
     assert np.array_equal(g1, g2) and np.array_equal(la, prob.la)
 
 
+def test_tap_reuse_weight_gradient_kernel_agrees():
+    """Option wgrad_reuse: x slab loaded once per K chunk, taps addressed by descriptor row offsets (MN-major operands)."""
+    for topology, ws in (("ModelWithoutDropoutTdnn", "B"), ("ModelWithoutDropout", "A")):
+        p = Problem(topology, ws, 8, 64, 40)
+        try:
+            p.step()
+            g0 = {i: p.grad("frame_level_info_layer-%d/w:0" % i) for i in range(5)}
+            p.tr.set_params({k: v for k, v in p.P.items() if k.endswith(("mean:0", "variance:0"))})
+            p.tr.set_option("wgrad_reuse", 1)
+            p.step()
+            for i in range(5):
+                # same fp16 operands, fp32 accumulation in another order (other K-split count)
+                assert rel_l2(p.grad("frame_level_info_layer-%d/w:0" % i), g0[i]) <= 2e-5, (topology, i)
+        finally:
+            p.close()
+
+
 def test_fused_segment_level_kernel_agrees_with_the_chained_launches():
     """Option seg_fused: the whole segment level in one cooperative kernel (seg_level.cuh) vs the default 22 launches."""
     p = Problem("ModelWithoutDropoutTdnn", "B", 16, 64, 700)

@@ -63,6 +63,10 @@ struct xv_trainer {
   bool operands_dirty = true;
   double opt_loss_scale = 0.0;
   int opt_wgrad_lbo = wgrad::BOX_BYTES, opt_wgrad_sbo = 1024;
+  int opt_wgrad_reuse = 0;           // 1: tap-reuse weight-gradient kernel for layers with temporal context (wgrad_reuse_kernel):
+                                     // halves the operand bytes per FLOP but needs UMMA 256x128x16 (three taps share the 512 TMEM
+                                     // columns) whose A-operand reads per FLOP double -- measured 83 vs 75 us (tdnn), 142 vs 129 us
+                                     // (dense) for the two layers it applies to: not faster, kept as a tested option
   int opt_fused_stats = 1;           // 1: BatchNorm / pooling column sums come out of the layer kernel's epilogue (STATS instantiation)
   int opt_seg_ctas = 0, seg_ctas_per_sm = 0;
   int opt_seg_fused = 0;             // 1: the whole segment level of a training step in ONE cooperative kernel (seg_level.cuh).
@@ -120,14 +124,29 @@ int tr_launch_check(xv_trainer* t) {
     if (prc_ != XV_OK) return prc_;                                        \
   } while (0)
 
-int tr_wgrad_splits(const xv_trainer* t, const TrFrame& L, int64_t r_pad, int* cps_out) {
+// Work decomposition of one layer's weight gradient.  Layers with temporal context use the tap-reuse kernel (groups of <= 3
+// taps whose row span fits the 136-row x slab); k = 1 layers and the spliced first layer use one item per 256 x 256 tile.
+struct WgradPlan { bool reuse; int group, n_groups, splits, cps; };
+WgradPlan tr_wgrad_plan(const xv_trainer* t, const TrFrame& L, int64_t r_pad) {
+  WgradPlan p{};
   const int n_chunks = int(r_pad / wgrad::STAGE_ROWS);
-  const int tiles = L.gemm_taps * ((L.c_in_gemm + wgrad::TILE - 1) / wgrad::TILE) * (L.c_out / wgrad::TILE);
-  int splits = std::max(1, std::min(t->m->num_clusters / tiles, n_chunks));
-  const int cps = (n_chunks + splits - 1) / splits;
-  splits = (n_chunks + cps - 1) / cps;
-  *cps_out = cps;
-  return splits;
+  const int n_mt = (L.c_in_gemm + wgrad::TILE - 1) / wgrad::TILE;
+  p.reuse = t->opt_wgrad_reuse && L.gemm_taps > 1 && L.c_out % wgrad::reuse::TILE_N == 0;
+  int tiles;
+  if (p.reuse) {
+    p.group = std::min(L.gemm_taps, wgrad::reuse::MAX_GROUP);
+    while (p.group > 1 && (p.group - 1) * L.dil > 8) --p.group;
+    p.n_groups = (L.gemm_taps + p.group - 1) / p.group;
+    tiles = p.n_groups * n_mt * (L.c_out / wgrad::reuse::TILE_N);
+  } else {
+    p.group = 1;
+    p.n_groups = L.gemm_taps;
+    tiles = L.gemm_taps * n_mt * (L.c_out / wgrad::TILE);
+  }
+  p.splits = std::max(1, std::min(t->m->num_clusters / tiles, n_chunks));
+  p.cps = (n_chunks + p.splits - 1) / p.splits;
+  p.splits = (n_chunks + p.cps - 1) / p.cps;
+  return p;
 }
 
 int tr_ensure_workspace(xv_trainer* t, int32_t n_seg, int32_t seg_len) {
@@ -181,9 +200,8 @@ int tr_ensure_workspace(xv_trainer* t, int32_t n_seg, int32_t seg_len) {
   want(reinterpret_cast<void**>(&t->correct), size_t(n_seg) * 4);
   size_t wg = 0;
   for (auto& L : t->frames) {
-    int cps = 0;
-    const int splits = tr_wgrad_splits(t, L, r_pad, &cps);
-    wg = std::max(wg, size_t(splits) * L.gemm_taps * L.wg_rows * L.c_out);
+    const WgradPlan wp = tr_wgrad_plan(t, L, r_pad);
+    wg = std::max(wg, size_t(wp.splits) * L.gemm_taps * L.wg_rows * L.c_out);
   }
   t->wg_partial_floats = wg;
   want(reinterpret_cast<void**>(&t->wg_partial), wg * 4);
@@ -272,33 +290,56 @@ int tr_pair_layer(xv_trainer* t, cudaStream_t stream, const char* name, const __
 int tr_wgrad(xv_trainer* t, cudaStream_t stream, const char* name, const TrFrame& L, const __half* x, const __half* dz, float* grad_w,
              float inv_loss_scale) {
   xv_model* m = t->m;
+  const WgradPlan wp = tr_wgrad_plan(t, L, t->r_pad);
+  const bool pdl = m->opt_pdl != 0 && !m->opt_profile;
   CUtensorMap tx, tz;
-  int rc = encode_2d(m, &tx, const_cast<__half*>(x), uint64_t(L.c_in_gemm), uint64_t(t->r_pad), wgrad::BOX_CH, wgrad::STAGE_ROWS, CU_TENSOR_MAP_SWIZZLE_128B);
+  int rc = encode_2d(m, &tx, const_cast<__half*>(x), uint64_t(L.c_in_gemm), uint64_t(t->r_pad), wgrad::BOX_CH,
+                     wp.reuse ? wgrad::reuse::X_BOX_ROWS : wgrad::STAGE_ROWS, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != XV_OK) return rc;
   rc = encode_2d(m, &tz, const_cast<__half*>(dz), uint64_t(L.c_out), uint64_t(t->r_pad), wgrad::BOX_CH, wgrad::STAGE_ROWS, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != XV_OK) return rc;
-  wgrad::WgradArgs a{};
-  a.n_chunks = int32_t(t->r_pad / wgrad::STAGE_ROWS);
-  int cps = 0;
-  a.k_splits = tr_wgrad_splits(t, L, t->r_pad, &cps);
-  a.chunks_per_split = cps;
-  a.taps = L.gemm_taps;
-  a.dilation = L.dil;
-  a.n_mt = (L.c_in_gemm + wgrad::TILE - 1) / wgrad::TILE;
-  a.n_nt = L.c_out / wgrad::TILE;
-  a.c_in = L.wg_rows;
-  a.c_out = L.c_out;
-  a.lbo_bytes = t->opt_wgrad_lbo;
-  a.sbo_bytes = t->opt_wgrad_sbo;
-  a.partial = t->wg_partial;
+  struct { int32_t taps, c_in, c_out, k_splits; } a{L.gemm_taps, L.wg_rows, L.c_out, wp.splits};
   const size_t need = size_t(a.k_splits) * a.taps * a.c_in * a.c_out;
   if (need > t->wg_partial_floats) return fail(XV_ESTATE, "wgrad partial buffer too small");
-  const int items = a.k_splits * a.taps * a.n_mt * a.n_nt;
-  const int grid = 2 * std::min(items, m->num_clusters);
-  const bool pdl = m->opt_pdl != 0 && !m->opt_profile;
-  TR_BEGIN(name);
-  TR_CUDA(launch_k(pdl, wgrad::wgrad_pair_kernel, dim3(grid), dim3(wgrad::NUM_THREADS), wgrad::SMEM_BYTES, stream, tx, tz, a));
-  TR_END();
+  if (wp.reuse) {
+    wgrad::WgradReuseArgs r{};
+    r.n_chunks = int32_t(t->r_pad / wgrad::STAGE_ROWS);
+    r.chunks_per_split = wp.cps;
+    r.k_splits = wp.splits;
+    r.taps = L.gemm_taps;
+    r.dilation = L.dil;
+    r.n_groups = wp.n_groups;
+    r.group = wp.group;
+    r.n_mt = (L.c_in_gemm + wgrad::TILE - 1) / wgrad::TILE;
+    r.n_nt = L.c_out / wgrad::reuse::TILE_N;
+    r.c_in = L.wg_rows;
+    r.c_out = L.c_out;
+    r.partial = t->wg_partial;
+    const int items = r.k_splits * r.n_groups * r.n_mt * r.n_nt;
+    const int grid = 2 * std::min(items, m->num_clusters);
+    TR_BEGIN("wgrad_reuse_kernel");
+    TR_CUDA(launch_k(pdl, wgrad::wgrad_reuse_kernel, dim3(grid), dim3(wgrad::NUM_THREADS), wgrad::reuse::SMEM_BYTES, stream, tx, tz, r));
+    TR_END();
+  } else {
+    wgrad::WgradArgs w{};
+    w.n_chunks = int32_t(t->r_pad / wgrad::STAGE_ROWS);
+    w.k_splits = wp.splits;
+    w.chunks_per_split = wp.cps;
+    w.taps = L.gemm_taps;
+    w.dilation = L.dil;
+    w.n_mt = (L.c_in_gemm + wgrad::TILE - 1) / wgrad::TILE;
+    w.n_nt = L.c_out / wgrad::TILE;
+    w.c_in = L.wg_rows;
+    w.c_out = L.c_out;
+    w.lbo_bytes = t->opt_wgrad_lbo;
+    w.sbo_bytes = t->opt_wgrad_sbo;
+    w.partial = t->wg_partial;
+    const int items = w.k_splits * w.taps * w.n_mt * w.n_nt;
+    const int grid = 2 * std::min(items, m->num_clusters);
+    TR_BEGIN(name);
+    TR_CUDA(launch_k(pdl, wgrad::wgrad_pair_kernel, dim3(grid), dim3(wgrad::NUM_THREADS), wgrad::SMEM_BYTES, stream, tx, tz, w));
+    TR_END();
+  }
   const int64_t n4 = int64_t(a.taps) * a.c_in * a.c_out / 4;
   TR_LAUNCH("wgrad_reduce_kernel", wgrad::wgrad_reduce_kernel, dim3(unsigned((n4 + 255) / 256)), dim3(256), 0, t->wg_partial, grad_w, n4, a.k_splits, inv_loss_scale);
   return XV_OK;
@@ -455,6 +496,7 @@ int xv_train_create(xv_trainer** out, xv_model* model, int32_t num_classes, int3
   }
   for (auto& S : t->seg) alloc0(&S.bn, 2 * int64_t(S.out));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad::wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wgrad::SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad::wgrad_reuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wgrad::reuse::SMEM_BYTES);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(tdnn2::tdnn_pair_kernel<0, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
@@ -527,6 +569,7 @@ int xv_train_set_option(xv_trainer* t, const char* name, double value) {
   else if (n == "wgrad_sbo") t->opt_wgrad_sbo = int(value);
   else if (n == "seg_fused") t->opt_seg_fused = value != 0.0;
   else if (n == "fused_stats") t->opt_fused_stats = value != 0.0;
+  else if (n == "wgrad_reuse") { t->opt_wgrad_reuse = value != 0.0; t->n_seg = 0; }     // the partial buffer is re-planned
   else if (n == "seg_ctas") { t->opt_seg_ctas = int(value); t->seg_ctas_per_sm = 0; }
   else return fail(XV_EINVAL, "unknown option: " + n);
   return XV_OK;
