@@ -490,6 +490,19 @@ def measure_train_step(args, dev, rank, world, peaks, topo):
                                      frac=round(flop_step / (tensor_ms * 1e-3) / 1e12 / peaks["tflops"], 4))
     tr.close()
     eng.close()
+    if world == 1 and not args.no_cpu_baseline:
+        # the torch-CPU restatement of the same training step (fp32, all host threads) on a bounded sample: 16 of the 64 segments
+        import time
+        from oracle import xvector_train_oracle as tro
+        Bc = 16
+        x = synthetic.mfcc(5, Bc * T).reshape(Bc, T, FEAT_DIM)
+        labels = np.random.default_rng(5).integers(0, NC, Bc)
+        tro.forward_backward(x[:2], labels[:2], P, topo, dtype=torch.float32)          # warm-up
+        t0 = time.time()
+        tro.forward_backward(x, labels, P, topo, dtype=torch.float32)
+        dt = time.time() - t0
+        out["cpu_baseline"] = dict(value=round(Bc * T / dt, 1), unit="frames/s", cores=torch.get_num_threads(), kind="port",
+                                   sample="1 step of %d x %d frames (forward + backward, no optimizer), torch fp32 autograd restatement" % (Bc, T))
     return out
 
 

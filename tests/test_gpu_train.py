@@ -450,3 +450,35 @@ def test_overflowing_gradients_skip_the_update_and_a_lower_loss_scale_recovers()
         assert np.isfinite(la).all() and not np.array_equal(p.tr.download(p.native.TRAIN_PARAMS), before)
     finally:
         p.close()
+
+
+def test_config5_full_size_properties():
+    """BASELINE configs[4] size (64 x 400 frames, 5000 speakers): size-independent identities instead of an oracle run."""
+    p = Problem("ModelWithoutDropoutTdnn", "A", 64, 400, 5000)
+    try:
+        la = p.step()
+        assert abs(la[0] - np.log(5000.0)) < 0.5 and 0.0 <= la[1] <= 1.0          # model_0 initialisation: near-uniform softmax
+        gbo, gWo = p.grad("output/b:0").astype(np.float64), p.grad("output/w:0").astype(np.float64)
+        # every row of (softmax - onehot) sums to zero -> so do d output/b and every row of d output/w
+        assert abs(gbo.sum()) <= 1e-5 * np.abs(gbo).sum()
+        assert np.abs(gWo.sum(axis=1)).max() <= 1e-4 * np.abs(gWo).sum(axis=1).max()
+        dl = p.dbg("dlogits").astype(np.float64)
+        assert np.abs(dl.sum(axis=1)).max() <= 1e-6 and abs(np.abs(dl).sum() - 2.0 * (1.0 - np.exp(-la[0]))) < 0.2
+        # BatchNorm output of a training step: per channel, mean beta and variance gamma^2 var/(var+eps) over the valid frames
+        y3 = p.dbg("y3", 512).reshape(-1, 512).astype(np.float64)
+        np.testing.assert_allclose(y3.mean(0), np.asarray(p.P["frame_level_info_layer-3/beta:0"], np.float64), atol=2e-3)
+        r3 = p.dbg("r3", 512).reshape(-1, 512).astype(np.float64)
+        want_var = np.asarray(p.P["frame_level_info_layer-3/gamma:0"], np.float64) ** 2 * r3.var(0) / (r3.var(0) + 1e-3)
+        np.testing.assert_allclose(y3.var(0), want_var, rtol=5e-3, atol=1e-4)
+        # pooled statistics: second half is a standard deviation (>= sqrt(1e-5)); moving statistics moved 5 % towards the batch
+        h0 = p.dbg("h0")
+        assert (h0[:, 1536:] >= np.sqrt(1e-5) * 0.999).all()
+        mm = p.tr.get_param("frame_level_info_layer-3/mean:0")
+        np.testing.assert_allclose(mm, 0.05 * r3.mean(0), rtol=2e-3, atol=1e-5)      # set A starts from mean 0
+        g1 = p.tr.download(p.native.TRAIN_GRAD)
+        assert np.isfinite(g1).all()
+        p.tr.set_params({k: v for k, v in p.P.items() if k.endswith(("mean:0", "variance:0"))})
+        p.step()
+        assert np.array_equal(g1, p.tr.download(p.native.TRAIN_GRAD))                # bit-reproducible at full size
+    finally:
+        p.close()
