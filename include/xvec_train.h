@@ -82,6 +82,9 @@ int xv_train_sync_model(xv_trainer* t);
  * loss-scaled gradients w.r.t. the pre-activation / the BatchNorm output; fp32 arrays as stored: "h0" (pooled
  * statistics), "z5", "y5", "z6", "y6", "logits", "dlogits", "dh0".  Returns the number of floats (or < 0). */
 int64_t xv_train_debug_tensor(xv_trainer* t, const char* name, float* host_out, int64_t capacity);
+/* float16 -> float32 on the device (the egs archives store minibatches as float16, examples_io.py:165; input_x is float32):
+ * lets the host ship half the bytes and skip its own conversion.  Both pointers 16-byte aligned.  Enqueue only. */
+int xv_convert_f16_to_f32(const void* src_dev, float* dst_dev, int64_t n, void* stream);
 /* Options: "loss_scale" (0 = automatic: 8 * frames rounded to a power of two), "wgrad_lbo", "wgrad_sbo" (diagnostics),
  * "seg_fused" (1: the segment level of a step as one cooperative kernel instead of chained launches), "seg_ctas". */
 int xv_train_set_option(xv_trainer* t, const char* name, double value);

@@ -132,6 +132,8 @@ def load_library():
     lib.xv_train_set_option.restype = ctypes.c_int
     lib.xv_train_last_launch_count.argtypes = [P]
     lib.xv_train_last_launch_count.restype = I32
+    lib.xv_convert_f16_to_f32.argtypes = [P, P, I64, P]
+    lib.xv_convert_f16_to_f32.restype = ctypes.c_int
     lib.xv_train_last_kernel_names.argtypes = [P, ctypes.c_char_p, I64]
     lib.xv_train_last_kernel_names.restype = I64
     _lib = lib
@@ -145,7 +147,7 @@ EXPORTED_SYMBOLS = ["xv_create", "xv_destroy", "xv_set_param", "xv_workspace_byt
                     "xv_train_create", "xv_train_destroy", "xv_train_size", "xv_train_span", "xv_train_upload",
                     "xv_train_download", "xv_train_set_step", "xv_train_get_step", "xv_train_forward_backward", "xv_train_eval",
                     "xv_train_apply", "xv_train_sync_model", "xv_train_debug_tensor", "xv_train_set_option",
-                    "xv_train_last_launch_count", "xv_train_last_kernel_names"]
+                    "xv_train_last_launch_count", "xv_train_last_kernel_names", "xv_convert_f16_to_f32"]
 
 
 def _check(lib, rc):
@@ -400,6 +402,12 @@ class XvecTrainer:
         s = torch.cuda.current_stream(self.engine.device) if stream is None else stream
         gptr = None if grad_dev is None else grad_dev.data_ptr()
         _check(self.lib, self.lib.xv_train_apply(self.handle, gptr, float(learning_rate), float(grad_scale), s.cuda_stream))
+
+    def convert_f16(self, src_dev, dst_dev, n, stream=None):
+        """float16 CUDA tensor -> float32 CUDA tensor (first n values), on ``stream``."""
+        import torch
+        s = torch.cuda.current_stream(self.engine.device) if stream is None else stream
+        _check(self.lib, self.lib.xv_convert_f16_to_f32(src_dev.data_ptr(), dst_dev.data_ptr(), int(n), s.cuda_stream))
 
     def sync_model(self):
         _check(self.lib, self.lib.xv_train_sync_model(self.handle))

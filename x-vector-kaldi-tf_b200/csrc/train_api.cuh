@@ -879,6 +879,15 @@ int xv_train_sync_model(xv_trainer* t) {
   return XV_OK;
 }
 
+int xv_convert_f16_to_f32(const void* src_dev, float* dst_dev, int64_t n, void* stream_) {
+  if (!src_dev || !dst_dev || n < 0) return fail(XV_EINVAL, "bad argument");
+  if ((reinterpret_cast<uintptr_t>(src_dev) & 15) || (reinterpret_cast<uintptr_t>(dst_dev) & 15)) return fail(XV_EINVAL, "buffers must be 16-byte aligned");
+  if (n == 0) return XV_OK;
+  trk::f16_to_f32_kernel<<<unsigned((n / 8 + 256) / 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(static_cast<const __half*>(src_dev), dst_dev, n);
+  XV_CUDA(cudaGetLastError());
+  return XV_OK;
+}
+
 int64_t xv_train_last_kernel_names(const xv_trainer* t, char* buf, int64_t capacity) {
   if (!t || !buf || capacity < 1) return fail(XV_EINVAL, "bad argument");
   std::string all;

@@ -771,6 +771,21 @@ __global__ void __launch_bounds__(256) repack_kernel(const RepackTable tb) {
   }
 }
 
+// float16 minibatch as stored in the egs archives (examples_io.py:165) -> float32 features, 8 values per thread
+__global__ void __launch_bounds__(256) f16_to_f32_kernel(const __half* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  cudaTriggerProgrammaticLaunchCompletion();
+  cudaGridDependencySynchronize();
+  const int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(src + i)), f);
+    reinterpret_cast<float4*>(dst + i)[0] = make_float4(f[0], f[1], f[2], f[3]);
+    reinterpret_cast<float4*>(dst + i)[1] = make_float4(f[4], f[5], f[6], f[7]);
+  } else {
+    for (int64_t k = i; k < n; ++k) dst[k] = __half2float(src[k]);
+  }
+}
+
 __global__ void __launch_bounds__(256) fill_kernel(float* p, int64_t n, float v) {
   cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
   cudaGridDependencySynchronize();

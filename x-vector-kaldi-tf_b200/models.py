@@ -273,22 +273,34 @@ class Model(object):
         start_time = time.time()
 
         def stage(k, batch_data, labels):
+            """Minibatch -> page-locked staging -> device.  float16 minibatches (the egs archives' storage type) travel as
+            float16 and are widened on the device; anything else is converted to float32 here."""
             sl = slots[k % 2]
-            x = np.ascontiguousarray(batch_data, dtype=np.float32)
+            half = batch_data.dtype == np.float16
+            x = np.ascontiguousarray(batch_data) if half else np.ascontiguousarray(batch_data, dtype=np.float32)
             n = x.size
             if sl["feats"] is None or sl["feats"].numel() < n:
                 sl["feats"] = torch.empty(n, dtype=torch.float32).pin_memory()
                 sl["feats_dev"] = torch.empty(n, dtype=torch.float32, device=dev)
+                sl["half"] = torch.empty(n, dtype=torch.float16).pin_memory()
+                sl["half_dev"] = torch.empty(n, dtype=torch.float16, device=dev)
             if sl["labels"] is None or sl["labels"].numel() < x.shape[0]:
                 sl["labels"] = torch.empty(x.shape[0], dtype=torch.int32).pin_memory()
                 sl["labels_dev"] = torch.empty(x.shape[0], dtype=torch.int32, device=dev)
             sl["free"].synchronize()                # the kernels that read this slot two minibatches ago are done
-            sl["feats"][:n].copy_(torch.from_numpy(x.reshape(-1)))
-            sl["labels"][:x.shape[0]].copy_(torch.from_numpy(np.ascontiguousarray(labels, dtype=np.int32)))
+            if half:
+                sl["half"].numpy()[:n] = x.reshape(-1)
+            else:
+                sl["feats"].numpy()[:n] = x.reshape(-1)
+            sl["labels"].numpy()[:x.shape[0]] = np.asarray(labels, dtype=np.int32)
             with torch.cuda.stream(copy):
-                sl["feats_dev"][:n].copy_(sl["feats"][:n], non_blocking=True)
+                if half:
+                    sl["half_dev"][:n].copy_(sl["half"][:n], non_blocking=True)
+                else:
+                    sl["feats_dev"][:n].copy_(sl["feats"][:n], non_blocking=True)
                 sl["labels_dev"][:x.shape[0]].copy_(sl["labels"][:x.shape[0]], non_blocking=True)
                 sl["ready"].record(copy)
+            sl["is_half"] = half
             return sl, x.shape
 
         for minibatch_idx in range(minibatch_count):
@@ -310,6 +322,8 @@ class Model(object):
             n_seg, seg_len = int(shape[0]), int(shape[1])
             with torch.cuda.stream(compute):
                 compute.wait_event(sl["ready"])
+                if sl["is_half"]:
+                    tr.convert_f16(sl["half_dev"], sl["feats_dev"], n_seg * seg_len * shape[2], stream=compute)
                 feats_dev = sl["feats_dev"][:n_seg * seg_len * shape[2]].view(n_seg * seg_len, shape[2])
                 if training:
                     la = tr.forward_backward(feats_dev, sl["labels_dev"][:n_seg], n_seg, seg_len, grad_dev=grad, stream=compute)
