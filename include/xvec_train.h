@@ -20,7 +20,8 @@
  *             XV_TRAIN_ADAM_M / XV_TRAIN_ADAM_V   the "<var>/Adam" and "<var>/Adam_1" slots, same offsets
  *             XV_TRAIN_MOVING   the non-trainable "<scope>/mean:0", "<scope>/variance:0" moving statistics
  *             XV_TRAIN_GRAD     the gradient of the last xv_train_forward_backward into the trainer's own buffer
- * Conventions as in xvec.h: plain C, 0 / negative XV_E*, xv_last_error(); ReLU topologies only.
+ * Conventions as in xvec.h: plain C, 0 / negative XV_E*, xv_last_error().  Topologies: ReLU and leaky-ReLU (XV_ACT_RELU /
+ * XV_ACT_LRELU) with statistics pooling; option "l2_beta" adds the L2 term of the ModelL2Loss* graphs (models.py:930-962).
  */
 #ifndef XVEC_B200_TRAIN_H_
 #define XVEC_B200_TRAIN_H_
@@ -85,8 +86,9 @@ int64_t xv_train_debug_tensor(xv_trainer* t, const char* name, float* host_out, 
 /* float16 -> float32 on the device (the egs archives store minibatches as float16, examples_io.py:165; input_x is float32):
  * lets the host ship half the bytes and skip its own conversion.  Both pointers 16-byte aligned.  Enqueue only. */
 int xv_convert_f16_to_f32(const void* src_dev, float* dst_dev, int64_t n, void* stream);
-/* Options: "loss_scale" (0 = automatic: 8 * frames rounded to a power of two), "wgrad_lbo", "wgrad_sbo" (diagnostics),
- * "seg_fused" (1: the segment level of a step as one cooperative kernel instead of chained launches), "seg_ctas". */
+/* Options: "loss_scale" (0 = automatic: 8 * frames rounded to a power of two), "l2_beta" (0; 0.0002 for ModelL2Loss*),
+ * "wgrad_lbo", "wgrad_sbo" (diagnostics), "seg_fused" (1: the segment level of a step as one cooperative kernel instead of
+ * chained launches; relu only), "seg_ctas", "wgrad_reuse", "fused_stats" (alternative schedules). */
 int xv_train_set_option(xv_trainer* t, const char* name, double value);
 int32_t xv_train_last_launch_count(const xv_trainer* t);
 /* With the xv_model option "profile" on, every launch of a step is bracketed by CUDA events: read the times with

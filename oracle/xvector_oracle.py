@@ -54,7 +54,8 @@ TOPOLOGIES = {
     "ModelWithoutDropoutPRelu": dict(kernel_sizes=[5, 5, 7, 1, 1], dilations=[1, 1, 1, 1, 1],
                                      layer_sizes=[512, 512, 512, 512, 1536], embedding_sizes=[512, 512], act="prelu"),
     "ModelL2LossWithoutDropoutLRelu": dict(kernel_sizes=[5, 5, 7, 1, 1], dilations=[1, 1, 1, 1, 1],
-                                           layer_sizes=[512, 512, 512, 512, 1536], embedding_sizes=[512, 512], act="lrelu"),
+                                           layer_sizes=[512, 512, 512, 512, 1536], embedding_sizes=[512, 512], act="lrelu",
+                                           l2_beta=0.0002),          # training only: models.py:876,961
     # self-attention pooling (local/tf/models.py:990-1051): last frame layer 6*512 wide, split into scores input | pooled half
     "ModelL2LossWithoutDropoutLReluAttention": dict(kernel_sizes=[5, 5, 7, 1, 1], dilations=[1, 1, 1, 1, 1],
                                                     layer_sizes=[512, 512, 512, 512, 3072], embedding_sizes=[512, 512],

@@ -47,6 +47,23 @@ def trainable_names(topology, params):
     return [n for n in names if n in params]
 
 
+def _act(h, act):
+    """relu (models.py:479) or tf.nn.leaky_relu(alpha=0.2) (models.py:912), frame and segment layers alike."""
+    if act == "relu":
+        return torch.relu(h)
+    if act == "lrelu":
+        return F.leaky_relu(h, 0.2)
+    raise ValueError("the training oracle covers relu / lrelu, not %r" % act)
+
+
+def l2_term(p, beta):
+    """ModelL2Loss* (models.py:930-951, 962): beta * (0.1 l2(embed-0 w, b) + l2(embed-1 w, b) + l2(output w, b)), l2 = sum(x^2)/2."""
+    l2 = 0.1 * ((p["embed_layer-0/w:0"] ** 2).sum() + (p["embed_layer-0/b:0"] ** 2).sum()) / 2
+    l2 = l2 + ((p["embed_layer-1/w:0"] ** 2).sum() + (p["embed_layer-1/b:0"] ** 2).sum()) / 2
+    l2 = l2 + ((p["output/w:0"] ** 2).sum() + (p["output/b:0"] ** 2).sum()) / 2
+    return beta * l2
+
+
 def _bn_train(h, gamma, beta, axes, eps=BN_EPSILON):
     mean = h.mean(dim=axes)
     var = ((h - mean) ** 2).mean(dim=axes)                      # tf.nn.moments: population variance
@@ -62,7 +79,7 @@ def _fp16_storage(t):
 
 
 def forward_backward(x, labels, params, topology="ModelWithoutDropoutTdnn", dtype=torch.float64,
-                     return_intermediates=False, fp16_storage=False, bn_eps=BN_EPSILON):
+                     return_intermediates=False, fp16_storage=False, bn_eps=BN_EPSILON, l2_beta=None):
     """One minibatch.  x: [B, T, D]; labels: [B] ints; params: dict of numpy arrays by TF variable name.
 
     Returns dict(loss, accuracy, grads{name: np}, batch_stats{scope: (mean, var)}, moving{name: np})
@@ -73,6 +90,9 @@ def forward_backward(x, labels, params, topology="ModelWithoutDropoutTdnn", dtyp
     rounding ~100x at 1e-3), which checks the backward arithmetic tightly.
     """
     q = _fp16_storage if fp16_storage else (lambda t: t)
+    act = (TOPOLOGIES[topology] if isinstance(topology, str) else topology).get("act", "relu")
+    if l2_beta is None:
+        l2_beta = (TOPOLOGIES[topology] if isinstance(topology, str) else topology).get("l2_beta", 0.0)
     topo = TOPOLOGIES[topology] if isinstance(topology, str) else topology
     names = trainable_names(topo, params)
     p = {k: torch.tensor(np.asarray(v), dtype=dtype) for k, v in params.items()}
@@ -86,7 +106,7 @@ def forward_backward(x, labels, params, topology="ModelWithoutDropoutTdnn", dtyp
         s = "frame_level_info_layer-%d/" % i
         w = p[s + "w:0"]                                          # [k, Cin, Cout]
         z = F.conv1d(h.transpose(1, 2), q(w).permute(2, 1, 0), padding=(k - 1) // 2 * d, dilation=d).transpose(1, 2)
-        r = q(torch.relu(z + p[s + "b:0"]))
+        r = q(_act(z + p[s + "b:0"], act))
         h, mean, var = _bn_train(r, p[s + "gamma:0"], p[s + "beta:0"], (0, 1), bn_eps)
         if i < n_frame - 1:
             h = q(h)
@@ -104,7 +124,7 @@ def forward_backward(x, labels, params, topology="ModelWithoutDropoutTdnn", dtyp
     for i in range(len(topo["embedding_sizes"])):
         s = "embed_layer-%d/" % i
         z = h @ p[s + "w:0"] + p[s + "b:0"]
-        r = torch.relu(z)
+        r = _act(z, act)
         h, mean, var = _bn_train(r, p[s + "gamma:0"], p[s + "beta:0"], (0,), bn_eps)
         batch_stats[s] = (mean.detach().numpy(), var.detach().numpy())
         if return_intermediates:
@@ -113,6 +133,8 @@ def forward_backward(x, labels, params, topology="ModelWithoutDropoutTdnn", dtyp
     logits = h @ p["output/w:0"] + p["output/b:0"]
     lab = torch.tensor(np.asarray(labels), dtype=torch.long)
     loss = F.cross_entropy(logits, lab, reduction="mean")       # one-hot labels (models.py:164-169)
+    if l2_beta:
+        loss = loss + l2_term(p, l2_beta)                       # tf.reduce_mean(loss + beta * l2_loss), models.py:961
     acc = (logits.argmax(dim=1) == lab).double().mean()
     loss.backward()
     grads = {n: p[n].grad.detach().numpy().copy() for n in names}
@@ -129,24 +151,30 @@ def forward_backward(x, labels, params, topology="ModelWithoutDropoutTdnn", dtyp
     return out
 
 
-def loss_only(x, labels, params, topology):
+def loss_only(x, labels, params, topology, l2_beta=None):
     """Loss of the restated graph, numpy fp64, no autograd (for finite differences)."""
     with torch.no_grad():
         topo = TOPOLOGIES[topology] if isinstance(topology, str) else topology
+        act = topo.get("act", "relu")
+        if l2_beta is None:
+            l2_beta = topo.get("l2_beta", 0.0)
         p = {k: torch.tensor(np.asarray(v), dtype=torch.float64) for k, v in params.items()}
         h = torch.tensor(np.asarray(x), dtype=torch.float64)
         for i, (k, d) in enumerate(zip(topo["kernel_sizes"], topo["dilations"])):
             s = "frame_level_info_layer-%d/" % i
             z = F.conv1d(h.transpose(1, 2), p[s + "w:0"].permute(2, 1, 0), padding=(k - 1) // 2 * d, dilation=d).transpose(1, 2)
-            h, _, _ = _bn_train(torch.relu(z + p[s + "b:0"]), p[s + "gamma:0"], p[s + "beta:0"], (0, 1))
+            h, _, _ = _bn_train(_act(z + p[s + "b:0"], act), p[s + "gamma:0"], p[s + "beta:0"], (0, 1))
         mean_t = h.mean(dim=1)
         var_t = ((h - mean_t[:, None, :]) ** 2).mean(dim=1)
         h = torch.cat([mean_t, torch.sqrt(var_t + VAR2STD_EPSILON)], dim=1)
         for i in range(len(topo["embedding_sizes"])):
             s = "embed_layer-%d/" % i
-            h, _, _ = _bn_train(torch.relu(h @ p[s + "w:0"] + p[s + "b:0"]), p[s + "gamma:0"], p[s + "beta:0"], (0,))
+            h, _, _ = _bn_train(_act(h @ p[s + "w:0"] + p[s + "b:0"], act), p[s + "gamma:0"], p[s + "beta:0"], (0,))
         logits = h @ p["output/w:0"] + p["output/b:0"]
-        return float(F.cross_entropy(logits, torch.tensor(np.asarray(labels), dtype=torch.long)))
+        loss = F.cross_entropy(logits, torch.tensor(np.asarray(labels), dtype=torch.long))
+        if l2_beta:
+            loss = loss + l2_term(p, l2_beta)
+        return float(loss)
 
 
 def adam_init(params, names):

@@ -47,10 +47,11 @@ class Problem:
         self.topology, self.B, self.T, self.NC = topology, B, T, NC
         self.topo = orc.TOPOLOGIES[topology]
         self.P = synthetic.make_params(self.topo["kernel_sizes"], self.topo["layer_sizes"], self.topo["embedding_sizes"],
-                                       num_classes=NC, weight_set=ws)
+                                       num_classes=NC, weight_set=ws, activation=self.topo.get("act", "relu"))
         self.x = synthetic.mfcc(seed, B * T).reshape(B, T, 23)
         self.labels = np.random.default_rng(seed).integers(0, NC, B).astype(np.int32)
-        self.eng = _native.XvecEngine(self.topo["kernel_sizes"], self.topo["dilations"], self.topo["layer_sizes"], 512, 23, device=0)
+        self.eng = _native.XvecEngine(self.topo["kernel_sizes"], self.topo["dilations"], self.topo["layer_sizes"], 512, 23, device=0,
+                                      activation=self.topo.get("act", "relu"))
         if os.environ.get("XVEC_TEST_PDL") is not None:                   # diagnostics: programmatic dependent launch on / off
             self.eng.set_option("pdl", int(os.environ["XVEC_TEST_PDL"]))
         self.tr = _native.XvecTrainer(self.eng, NC, 512)
@@ -480,5 +481,42 @@ def test_config5_full_size_properties():
         p.tr.set_params({k: v for k, v in p.P.items() if k.endswith(("mean:0", "variance:0"))})
         p.step()
         assert np.array_equal(g1, p.tr.download(p.native.TRAIN_GRAD))                # bit-reproducible at full size
+    finally:
+        p.close()
+
+
+def test_leaky_relu_l2_loss_topology_trains():
+    """ModelL2LossWithoutDropoutLRelu (reference models.py:866-983): leaky_relu(0.2) everywhere + beta * L2 of the segment weights."""
+    topology = "ModelL2LossWithoutDropoutLRelu"
+    p = Problem(topology, "B", 12, 70, 200)
+    try:
+        p.tr.set_option("l2_beta", 0.0002)
+        la = p.step()
+        ref = tro.forward_backward(p.x, p.labels, p.P, topology, return_intermediates=True)       # l2_beta from the topology table
+        assert abs(la[0] - ref["loss"]) / ref["loss"] <= 1e-3
+        plain = tro.forward_backward(p.x, p.labels, p.P, topology, l2_beta=0.0)["loss"]
+        assert ref["loss"] - plain > 1e-3                                                          # the L2 term is really in the loss
+        inter = ref["intermediates"]
+        for i in range(5):
+            C = p.topo["layer_sizes"][i]
+            r = p.dbg("r%d" % i, C)
+            assert (r < 0).any()                                                                   # negative half kept (slope 0.2)
+            assert rel_l2(r, inter["frame_level_info_layer-%d/relu" % i]) <= 3e-3
+        assert rel_l2(p.dbg("h0"), inter["stats"]) <= 1e-3
+        # tight, from the GPU's own stored tensors: BatchNorm + leaky backward of layer 2, and the weight gradient of layer 3
+        s = "frame_level_info_layer-2/"
+        r2 = torch.tensor(p.dbg("r2", 512), dtype=torch.float64, requires_grad=True)
+        y, _, _ = tro._bn_train(r2, torch.tensor(np.asarray(p.P[s + "gamma:0"]), dtype=torch.float64),
+                                torch.tensor(np.asarray(p.P[s + "beta:0"]), dtype=torch.float64), (0, 1))
+        y.backward(torch.tensor(p.dbg("dy2", 512) / p.S, dtype=torch.float64))
+        want = (r2.grad * torch.where(r2.detach() > 0, 1.0, 0.2)).numpy()
+        assert rel_l2(p.dbg("dz2", 512) / p.S, want) <= 1e-3
+        x = p.dbg("y2", 512).astype(np.float64)
+        dz3 = p.dbg("dz3", 512).astype(np.float64) / p.S
+        assert rel_l2(p.grad("frame_level_info_layer-3/w:0")[0], np.einsum("btc,bto->co", x, dz3)) <= 1e-4
+        # end to end (sanity bound, see module doc) incl. the L2 gradient of the output layer
+        worst = max(rel_l2(p.grad(n), ref["grads"][n]) for n in tro.trainable_names(p.topo, p.P))
+        assert worst <= 2e-1, worst
+        assert rel_l2(p.grad("output/b:0"), ref["grads"]["output/b:0"]) <= 1e-2
     finally:
         p.close()

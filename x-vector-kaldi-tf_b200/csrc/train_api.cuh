@@ -63,6 +63,9 @@ struct xv_trainer {
   bool operands_dirty = true;
   double opt_loss_scale = 0.0;
   int opt_wgrad_lbo = wgrad::BOX_BYTES, opt_wgrad_sbo = 1024;
+  float neg_slope = 0.f;             // activation: 0 = relu, 0.2 = tf.nn.leaky_relu(alpha=0.2) (models.py:912), from the xv_model's topology
+  float* slope_dev = nullptr;        // [max width] filled with neg_slope (the LEAKY layer kernel's per-channel slope)
+  double opt_l2_beta = 0.0;          // ModelL2Loss*: loss += beta * (0.1 l2(embed-0 w,b) + l2(embed-1 w,b) + l2(output w,b))
   int opt_wgrad_reuse = 0;           // 1: tap-reuse weight-gradient kernel for layers with temporal context (wgrad_reuse_kernel):
                                      // halves the operand bytes per FLOP but needs UMMA 256x128x16 (three taps share the 512 TMEM
                                      // columns) whose A-operand reads per FLOP double -- measured 83 vs 75 us (tdnn), 142 vs 129 us
@@ -279,7 +282,8 @@ int tr_pair_layer(xv_trainer* t, cudaStream_t stream, const char* name, const __
   const int grid = 2 * int(std::min<int64_t>(tiles, m->num_clusters));
   const bool pdl = m->opt_pdl != 0 && !m->opt_profile;
   TR_BEGIN(name);
-  if (col_partial) TR_CUDA(launch_k(pdl, tdnn2::tdnn_pair_kernel<0, 2, false, true>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
+  if (col_partial && alpha) TR_CUDA(launch_k(pdl, tdnn2::tdnn_pair_kernel<0, 2, true, true>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
+  else if (col_partial) TR_CUDA(launch_k(pdl, tdnn2::tdnn_pair_kernel<0, 2, false, true>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
   else if (alpha) TR_CUDA(launch_k(pdl, tdnn2::tdnn_pair_kernel<0, 2, true>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
   else TR_CUDA(launch_k(pdl, tdnn2::tdnn_pair_kernel<0, 2, false>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
   TR_END();
@@ -418,8 +422,8 @@ int xv_train_create(xv_trainer** out, xv_model* model, int32_t num_classes, int3
   if (!out || !model) return fail(XV_EINVAL, "null argument");
   *out = nullptr;
   if (num_classes < 2 || emb1_dim < 1) return fail(XV_EINVAL, "num_classes must be >= 2 and emb1_dim >= 1");
-  if (model->topo.act != XV_ACT_RELU || model->topo.pooling != XV_POOL_STATS)
-    return fail(XV_EINVAL, "the training step supports the ReLU topologies with statistics pooling only");
+  if ((model->topo.act != XV_ACT_RELU && model->topo.act != XV_ACT_LRELU) || model->topo.pooling != XV_POOL_STATS)
+    return fail(XV_EINVAL, "the training step supports the ReLU / leaky-ReLU topologies with statistics pooling only");
   XV_CUDA(cudaSetDevice(model->device));
   xv_trainer* t = new xv_trainer();
   t->m = model;
@@ -483,6 +487,12 @@ int xv_train_create(xv_trainer** out, xv_model* model, int32_t num_classes, int3
   alloc0(&t->moving, t->n_moving);
   alloc0(&t->zeros, c_max);
   alloc0(&t->ones, c_max);
+  t->neg_slope = model->topo.act == XV_ACT_LRELU ? 0.2f : 0.f;
+  alloc0(&t->slope_dev, c_max);
+  if (e == cudaSuccess && t->neg_slope != 0.f) {
+    trk::fill_kernel<<<(c_max + 255) / 256, 256>>>(t->slope_dev, c_max, t->neg_slope);
+    e = cudaGetLastError();
+  }
   if (e == cudaSuccess) {
     trk::fill_kernel<<<(c_max + 255) / 256, 256>>>(t->ones, c_max, 1.f);
     e = cudaGetLastError();
@@ -498,6 +508,7 @@ int xv_train_create(xv_trainer** out, xv_model* model, int32_t num_classes, int3
   if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad::wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wgrad::SMEM_BYTES);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad::wgrad_reuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wgrad::reuse::SMEM_BYTES);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(tdnn2::tdnn_pair_kernel<0, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tdnn2::tdnn_pair_kernel<0, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     std::string msg = std::string("xv_train_create: ") + cudaGetErrorName(e) + ": " + cudaGetErrorString(e);
@@ -515,7 +526,7 @@ void xv_train_destroy(xv_trainer* t) {
   for (auto& L : t->frames) { cudaFree(L.wf); cudaFree(L.wd); cudaFree(L.bn); }
   for (auto& S : t->seg) cudaFree(S.bn);
   cudaFree(t->params); cudaFree(t->adam_m); cudaFree(t->adam_v); cudaFree(t->grad); cudaFree(t->moving);
-  cudaFree(t->ones); cudaFree(t->zeros); cudaFree(t->ws);
+  cudaFree(t->ones); cudaFree(t->zeros); cudaFree(t->ws); cudaFree(t->slope_dev);
   delete t;
 }
 
@@ -569,6 +580,7 @@ int xv_train_set_option(xv_trainer* t, const char* name, double value) {
   else if (n == "wgrad_sbo") t->opt_wgrad_sbo = int(value);
   else if (n == "seg_fused") t->opt_seg_fused = value != 0.0;
   else if (n == "fused_stats") t->opt_fused_stats = value != 0.0;
+  else if (n == "l2_beta") t->opt_l2_beta = value;
   else if (n == "wgrad_reuse") { t->opt_wgrad_reuse = value != 0.0; t->n_seg = 0; }     // the partial buffer is re-planned
   else if (n == "seg_ctas") { t->opt_seg_ctas = int(value); t->seg_ctas_per_sm = 0; }
   else return fail(XV_EINVAL, "unknown option: " + n);
@@ -631,6 +643,7 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
   }
 
   // ---- frame layers, training branch of BatchNorm ---------------------------------------------------
+  const float* act_alpha = t->neg_slope != 0.f ? t->slope_dev : nullptr;       // leaky topologies: LEAKY layer kernel
   const __half* in = t->x0;
   for (int i = 0; i < nl && !training; ++i) {
     // evaluation branch of BatchNorm (tf_block.py:25-26) folded into the layer kernel's epilogue, as on the extraction path
@@ -640,7 +653,7 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
     TR_LAUNCH("bn_fold_kernel", trk::bn_fold_kernel, dim3((L.c_out + 255) / 256), dim3(256), 0, t->params + L.off_gamma, t->params + L.off_beta, t->moving + L.off_mov, t->moving + L.off_mov + L.c_out, m->topo.bn_eps, L.c_out, scale, shift);
     __half* out = (i < nl - 1) ? L.y : L.r;
     rc = tr_pair_layer(t, stream, "tdnn_pair_kernel[fwd]", in, L.c_in_gemm, out, L.c_out, L.wf, L.k_total, L.gemm_taps, L.dil,
-                       t->params + L.off_b, scale, shift, nullptr);
+                       t->params + L.off_b, scale, shift, act_alpha);
     if (rc != XV_OK) return rc;
     in = out;
     if (i == nl - 1) {
@@ -651,7 +664,7 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
     TrFrame& L = t->frames[i];
     // the layer kernel's epilogue leaves the per-32-row-block column sums of r in t->partial (no second pass over HBM)
     rc = tr_pair_layer(t, stream, "tdnn_pair_kernel[fwd]", in, L.c_in_gemm, L.r, L.c_out, L.wf, L.k_total, L.gemm_taps, L.dil,
-                       t->params + L.off_b, t->ones, t->zeros, nullptr, t->opt_fused_stats ? t->partial : nullptr);
+                       t->params + L.off_b, t->ones, t->zeros, act_alpha, t->opt_fused_stats ? t->partial : nullptr);
     if (rc != XV_OK) return rc;
     const bool last = i == nl - 1;
     int32_t parts = int32_t(r_pad / 32);
@@ -686,7 +699,7 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
   }
 
   const int NC = t->num_classes, E1 = t->seg[1].out;
-  const bool seg_fused = training && t->opt_seg_fused;
+  const bool seg_fused = training && t->opt_seg_fused && t->neg_slope == 0.f;     // the cooperative kernel is relu only
   if (seg_fused) {
     // ---- the whole segment level (forward, loss, backward) in one persistent cooperative kernel -----------------------
     segk::Args a{};
@@ -744,6 +757,7 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
     a.moving_mean = t->moving + Sg.off_mov; a.moving_var = t->moving + Sg.off_mov + Sg.out;
     a.r = Sg.r; a.y = Sg.y; a.mean = Sg.bn; a.inv = Sg.bn + Sg.out;
     a.training = training ? 1 : 0;
+    a.neg_slope = t->neg_slope;
     TR_LAUNCH("seg_relu_bn_fwd_kernel", trk::seg_relu_bn_fwd_kernel, dim3((Sg.out + 31) / 32), dim3(dim3(32, trk::SEG_Y)), 0, a);
     hin = Sg.y;
   }
@@ -767,6 +781,7 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
     a.dy = Sg.dy; a.r = Sg.r; a.B = n_seg; a.C = Sg.out;
     a.gamma = t->params + Sg.off_gamma; a.mean = Sg.bn; a.inv = Sg.bn + Sg.out;
     a.dz = Sg.dz; a.d_gamma = grad + Sg.off_gamma; a.d_beta = grad + Sg.off_beta; a.d_bias = grad + Sg.off_b;
+    a.neg_slope = t->neg_slope;
     TR_LAUNCH("seg_relu_bn_bwd_kernel", trk::seg_relu_bn_bwd_kernel, dim3((Sg.out + 31) / 32), dim3(dim3(32, trk::SEG_Y)), 0, a);
     const float* xin = (i == 1) ? t->seg[0].y : t->h0;
     float* dxin = (i == 1) ? t->seg[0].dy : t->dh0;
@@ -777,6 +792,17 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
   }
   }
 
+  if (t->opt_l2_beta != 0.0) {
+    // ModelL2Loss* (models.py:930-951,962): loss += beta*(0.1 l2(embed-0 w, b) + l2(embed-1 w, b) + l2(output w, b)), l2 = sum(p^2)/2
+    const float beta = float(t->opt_l2_beta);
+    struct { int64_t off, n; float coef; } terms[6] = {
+        {t->seg[0].off_w, int64_t(t->seg[0].in) * t->seg[0].out, 0.1f * beta}, {t->seg[0].off_b, t->seg[0].out, 0.1f * beta},
+        {t->seg[1].off_w, int64_t(t->seg[1].in) * t->seg[1].out, beta},        {t->seg[1].off_b, t->seg[1].out, beta},
+        {t->off_wo, int64_t(t->seg[1].out) * t->num_classes, beta},            {t->off_bo, t->num_classes, beta}};
+    for (auto& tm : terms)
+      TR_LAUNCH("l2_term_kernel", trk::l2_term_kernel, dim3(1), dim3(1024), 0, static_cast<const float*>(t->params + tm.off), grad + tm.off, tm.n, tm.coef, loss_acc_dev);
+  }
+
   // ---- pooling + last layer's BatchNorm + ReLU backward ---------------------------------------------------
   {
     trk::PoolBwdArgs a{};
@@ -785,7 +811,7 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
     a.gamma = t->params + LL.off_gamma; a.mean = LL.bn; a.inv = LL.bn + C; a.scale = LL.bn + 2 * C;
     a.coefA = t->coefA; a.coefG = t->coefG; a.d_gamma = grad + LL.off_gamma; a.d_beta = grad + LL.off_beta;
     TR_LAUNCH("pool_bwd_coef_kernel", trk::pool_bwd_coef_kernel, dim3((C + 31) / 32), dim3(dim3(32, trk::SEG_Y)), 0, a);
-    TR_LAUNCH("pool_relu_bwd_kernel", trk::pool_relu_bwd_kernel, dim3(C / trk::COLS_PER_CTA, n_seg), dim3(256), 0, static_cast<const __half*>(LL.r), C, t->seg_stride, static_cast<const float*>(t->coefA), static_cast<const float*>(t->coefG), LL.dz, t->partial1, m->overflow_dev);
+    TR_LAUNCH("pool_relu_bwd_kernel", trk::pool_relu_bwd_kernel, dim3(C / trk::COLS_PER_CTA, n_seg), dim3(256), 0, static_cast<const __half*>(LL.r), C, t->seg_stride, seg_len, static_cast<const float*>(t->coefA), static_cast<const float*>(t->coefG), LL.dz, t->partial1, m->overflow_dev, t->neg_slope);
     TR_LAUNCH("colsum_finalize_kernel", trk::colsum_finalize_kernel, dim3(C / 32), dim3(32, trk::RED_Y), 0, static_cast<const float*>(t->partial1), n_seg, C, inv_S, grad + LL.off_b);
   }
 
@@ -801,7 +827,7 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
       b.cA = t->cA; b.cB = t->cB; b.cC = t->cC;
       b.d_gamma = grad + L.off_gamma; b.d_beta = grad + L.off_beta;
       TR_LAUNCH("bn_bwd_finalize_kernel", trk::bn_bwd_finalize_kernel, dim3(L.c_out / 32), dim3(dim3(32, trk::RED_Y)), 0, b);
-      TR_LAUNCH("bn_relu_bwd_kernel", trk::bn_relu_bwd_kernel, dim3(L.c_out / trk::COLS_PER_CTA, n_part), dim3(256), 0, static_cast<const __half*>(L.dy), static_cast<const __half*>(L.r), L.c_out, ROWS_PER_PART, static_cast<const float*>(t->cA), static_cast<const float*>(t->cB), static_cast<const float*>(t->cC), L.dz, t->partial1, m->overflow_dev);
+      TR_LAUNCH("bn_relu_bwd_kernel", trk::bn_relu_bwd_kernel, dim3(L.c_out / trk::COLS_PER_CTA, n_part), dim3(256), 0, static_cast<const __half*>(L.dy), static_cast<const __half*>(L.r), L.c_out, ROWS_PER_PART, static_cast<const float*>(t->cA), static_cast<const float*>(t->cB), static_cast<const float*>(t->cC), L.dz, t->partial1, m->overflow_dev, t->neg_slope, static_cast<const uint8_t*>(t->row_valid));
       TR_LAUNCH("colsum_finalize_kernel", trk::colsum_finalize_kernel, dim3(L.c_out / 32), dim3(32, trk::RED_Y), 0, static_cast<const float*>(t->partial1), n_part, L.c_out, inv_S, grad + L.off_b);
     }
     const __half* x = (i == 0) ? t->x0 : t->frames[i - 1].y;

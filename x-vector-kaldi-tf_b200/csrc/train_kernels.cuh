@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const BnBwdArgs a
 __global__ void __launch_bounds__(256)
 bn_relu_bwd_kernel(const __half* __restrict__ dy, const __half* __restrict__ r, int32_t C, int32_t rows_per_cta, const float* __restrict__ cA,
                    const float* __restrict__ cB, const float* __restrict__ cC, __half* __restrict__ dz,
-                   float* __restrict__ partial1, uint32_t* overflow_flag) {
+                   float* __restrict__ partial1, uint32_t* overflow_flag, float neg_slope, const uint8_t* __restrict__ row_valid) {
   cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
   cudaGridDependencySynchronize();
   __shared__ float red[8][COLS_PER_CTA];
@@ -278,9 +278,12 @@ bn_relu_bwd_kernel(const __half* __restrict__ dy, const __half* __restrict__ r, 
       float g[8], a[8], o[8];
       unpack8(vg[rr], g);
       unpack8(va[rr], a);
+      // gap rows carry no gradient (r = 0 there: relu masks them by itself, a leaky slope would not)
+      const float live = row_valid[int64_t(part) * rows_per_cta + r0 + w * 4 + rr] ? 1.f : 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        o[i] = a[i] > 0.f ? fmaf(ka[i], g[i], fmaf(kb[i], a[i], kc[i])) : 0.f;
+        // activation backward: slope 1 where the output is positive, else neg_slope (0 = relu, 0.2 = tf.nn.leaky_relu)
+        o[i] = fmaf(ka[i], g[i], fmaf(kb[i], a[i], kc[i])) * (a[i] > 0.f ? live : neg_slope * live);
         s[i] += o[i];
         mx = fmaxf(mx, fabsf(o[i]));
       }
@@ -408,8 +411,9 @@ __global__ void __launch_bounds__(256) pool_bwd_coef_kernel(const PoolBwdArgs p)
 // dz4 = (r4 > 0) ? A[seg,c] + G[seg,c]*r4 : 0 for one segment (seg_stride packed rows) x 256 channels per CTA;
 // partial1[seg][c] = column sums of dz4 (bias gradient, scaled by S)
 __global__ void __launch_bounds__(256)
-pool_relu_bwd_kernel(const __half* __restrict__ r, int32_t C, int32_t seg_stride, const float* __restrict__ coefA,
-                     const float* __restrict__ coefG, __half* __restrict__ dz, float* __restrict__ partial1, uint32_t* overflow_flag) {
+pool_relu_bwd_kernel(const __half* __restrict__ r, int32_t C, int32_t seg_stride, int32_t seg_len, const float* __restrict__ coefA,
+                     const float* __restrict__ coefG, __half* __restrict__ dz, float* __restrict__ partial1, uint32_t* overflow_flag,
+                     float neg_slope) {
   cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
   cudaGridDependencySynchronize();
   __shared__ float red[8][COLS_PER_CTA];
@@ -439,9 +443,10 @@ pool_relu_bwd_kernel(const __half* __restrict__ r, int32_t C, int32_t seg_stride
       if (row >= seg_stride) continue;
       float a[8], o[8];
       unpack8(va[rr], a);
+      const float live = row < seg_len ? 1.f : 0.f;             // gap rows carry no gradient (with a leaky slope A would leak into them)
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        o[i] = a[i] > 0.f ? fmaf(kg[i], a[i], ka[i]) : 0.f;
+        o[i] = fmaf(kg[i], a[i], ka[i]) * (a[i] > 0.f ? 1.f : neg_slope) * live;
         s[i] += o[i];
         mx = fmaxf(mx, fabsf(o[i]));
       }
@@ -558,6 +563,7 @@ struct SegBnArgs {
   float* moving_mean; float* moving_var;
   float* r; float* y; float* mean; float* inv;
   int32_t training;          // 0: evaluation branch (moving statistics, no update; tf_block.py:25-26)
+  float neg_slope;           // 0 = relu, 0.2 = tf.nn.leaky_relu (models.py:912)
 };
 __global__ void __launch_bounds__(256) seg_relu_bn_fwd_kernel(const SegBnArgs a) {     // block (32, SEG_Y)
   cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
@@ -569,7 +575,8 @@ __global__ void __launch_bounds__(256) seg_relu_bn_fwd_kernel(const SegBnArgs a)
   double s1 = 0.0, s2 = 0.0;
   if (live) {
     for (int b = threadIdx.y; b < a.B; b += SEG_Y) {
-      const float r = fmaxf(a.z[int64_t(b) * a.C + c], 0.f);
+      const float z = a.z[int64_t(b) * a.C + c];
+      const float r = z > 0.f ? z : a.neg_slope * z;
       a.r[int64_t(b) * a.C + c] = r;
       s1 += r; s2 += double(r) * r;
     }
@@ -608,6 +615,7 @@ struct SegBnBwdArgs {
   const float* dy; const float* r; int32_t B, C;
   const float* gamma; const float* mean; const float* inv;
   float* dz; float* d_gamma; float* d_beta; float* d_bias;
+  float neg_slope;
 };
 __global__ void __launch_bounds__(256) seg_relu_bn_bwd_kernel(const SegBnBwdArgs a) {   // block (32, SEG_Y)
   cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
@@ -641,7 +649,7 @@ __global__ void __launch_bounds__(256) seg_relu_bn_bwd_kernel(const SegBnBwdArgs
       const double r = a.r[int64_t(b) * a.C + c];
       const double dy = a.dy[int64_t(b) * a.C + c], rh = (r - mu) * inv;
       const double dr = g * inv * (dy - dbeta / a.B - rh * dgamma / a.B);
-      const float dz = r > 0.0 ? float(dr) : 0.f;
+      const float dz = float(dr) * (r > 0.0 ? 1.f : a.neg_slope);
       a.dz[int64_t(b) * a.C + c] = dz;
       db += dz;
     }
@@ -769,6 +777,25 @@ __global__ void __launch_bounds__(256) repack_kernel(const RepackTable tb) {
     const int c = c0 + threadIdx.x;
     if (c < L.c_in) L.wf[int64_t(o0 + i) * L.k_total + int64_t(j) * L.c_in_pad + c] = __float2half_rn(tile[threadIdx.x][i]);
   }
+}
+
+// L2 term of the ModelL2Loss* graphs (models.py:930-951,962: loss += beta * coef * tf.nn.l2_loss(p) = beta*coef*sum(p^2)/2):
+// grad += beta*coef*p and loss_acc[0] += beta*coef*sum(p^2)/2.  ONE CTA per tensor (fixed-order reduction).
+__global__ void __launch_bounds__(1024)
+l2_term_kernel(const float* __restrict__ p, float* __restrict__ g, int64_t n, float coef, float* __restrict__ loss_acc) {
+  __shared__ double red[1024];
+  cudaTriggerProgrammaticLaunchCompletion();
+  cudaGridDependencySynchronize();
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) {
+    const float v = p[i];
+    g[i] = fmaf(coef, v, g[i]);
+    s += double(v) * v;
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 512; w > 0; w >>= 1) { if (int(threadIdx.x) < w) red[threadIdx.x] += red[threadIdx.x + w]; __syncthreads(); }
+  if (threadIdx.x == 0) loss_acc[0] += float(0.5 * double(coef) * red[0]);
 }
 
 // float16 minibatch as stored in the egs archives (examples_io.py:165) -> float32 features, 8 values per thread

@@ -96,6 +96,7 @@ class Model(object):
     dilation_rates = [1, 1, 1, 1, 1]
     embedding_sizes = [512, 512]
     pooling = "stats"              # stats (mean | std over time) | attention (models.py:1037-1051)
+    l2_beta = 0.0                  # ModelL2Loss*: weight of the L2 term of the training loss (models.py:876, 961)
     activation = "relu"            # frame-layer nonlinearity: relu | lrelu (0.2) | prelu (per-channel)
     init = "trunc_normal"          # model_0 initialisation: trunc_normal (sigma 0.1) | he
 
@@ -216,11 +217,13 @@ class Model(object):
     def _create_trainer(self, device):
         """Engine + trainer holding this model's variables, moving statistics and (if saved) Adam state."""
         from ._native import XvecTrainer, TRAIN_ADAM_M, TRAIN_ADAM_V
-        if self.activation != "relu" or self.pooling != "stats":
-            raise NotImplementedError("the training step covers the ReLU topologies (Model, ModelWithoutDropout, "
-                                      "ModelWithoutDropoutTdnn); %s uses %s" % (type(self).__name__, self.activation))
+        if self.activation not in ("relu", "lrelu") or self.pooling != "stats":
+            raise NotImplementedError("the training step covers the ReLU / leaky-ReLU topologies with statistics pooling; "
+                                      "%s uses %s / %s" % (type(self).__name__, self.activation, self.pooling))
         eng = self._get_engine(device)
         tr = XvecTrainer(eng, self.num_classes, self.embedding_sizes[1])
+        if self.l2_beta:
+            tr.set_option("l2_beta", self.l2_beta)
         state = {k: v for k, v in self.params.items() if not k.endswith(self.ADAM_SLOTS) and not k.endswith("_power:0")}
         tr.set_params(state)
         for name in state:
@@ -677,12 +680,14 @@ class ModelL2LossWithoutDropoutPRelu(ModelWithoutDropoutPRelu):
 class ModelL2LossWithoutDropoutLRelu(ModelWithoutDropout):
     """tf.nn.leaky_relu(h, alpha=0.2) (reference models.py:866-983)."""
     activation = "lrelu"
+    l2_beta = 0.0002
 
 
 # noinspection PyAttributeOutsideInit
 class ModelL2LossWithoutDropoutReluHeInit(ModelWithoutDropout):
     """ReLU with He-normal weights / He-uniform biases at model_0 (reference models.py:1118-1244)."""
     init = "he"
+    l2_beta = 0.0002
 
 
 class ModelL2LossWithoutDropoutLReluAttention(ModelL2LossWithoutDropoutLRelu):
