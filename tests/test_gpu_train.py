@@ -386,6 +386,12 @@ def test_train_one_iteration_through_the_model_surface(tmp_path):
         assert not np.array_equal(z["frame_level_info_layer-0/mean:0"], np.zeros(512, np.float32))
     ev = models.ModelWithoutDropoutTdnn().eval(examples_io.TarFileDataLoader(tar), args.output_dir, True, logger)
     assert np.isfinite(ev["total_loss"]) and ev["minibatch_count"] == 12
+    # the eval_dnn.py command line writes the same summary to its --log-file
+    from xvector_b200 import eval_dnn
+    log_file = str(tmp_path / "compute_prob_valid.1.log")
+    ev2 = eval_dnn.eval_dnn(eval_dnn.get_args(["--tar-file", tar, "--input-dir", args.output_dir, "--log-file", log_file]))
+    assert ev2["total_loss"] == ev["total_loss"]
+    assert "Overall average loss is %.4f over 192 segments." % (ev["total_loss"] / 12) in open(log_file).read()
     # resume: Adam's step counter and slots continue from the checkpoint
     args2 = SimpleNamespace(**{**vars(args), "input_dir": args.output_dir, "output_dir": str(tmp_path / "model_2")})
     models.ModelWithoutDropoutTdnn().train_one_iteration(examples_io.TarFileDataLoader(tar), args2, logger)

@@ -190,3 +190,14 @@ def test_train_dnn_schedules_and_bookkeeping(tmp_path):
     a = train_dnn.get_args(["--tf-model-class", "ModelWithoutDropout", "--dir", "x", "--egs-dir", "y", "--num-targets", "5",
                             "--minibatch-size", "8", "--num-epochs", "2", "--cmd", "run.pl --long 0", "--momentum", "0.5"])
     assert a.num_epochs == 2.0 and a.cleanup is True and a.initial_effective_lrate == 0.0003
+
+
+def test_eval_dnn_cli_rejects_bad_arguments(tmp_path):
+    from xvector_b200 import eval_dnn
+    with pytest.raises(Exception, match="expects the input model"):
+        eval_dnn.get_args(["--tar-file", "x.tar", "--input-dir", str(tmp_path / "nope"), "--log-file", str(tmp_path / "l.log")])
+    mdir = tmp_path / "model_3"
+    mdir.mkdir()
+    (mdir / "model.meta").write_text("{}")
+    with pytest.raises(Exception, match="tar file"):
+        eval_dnn.get_args(["--tar-file", str(tmp_path / "valid_egs.1.tar"), "--input-dir", str(mdir), "--log-file", str(tmp_path / "l.log")])
