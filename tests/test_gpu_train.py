@@ -429,6 +429,9 @@ def test_train_dnn_driver_end_to_end(tmp_path):
     rows = [r.split("\t") for r in rep[1:]]
     assert len(rows) == 1 + 1 + 2 + 2                                                    # jobs per iteration: 1, 1, 2, 2
     assert float(rows[-1][2]) < 0.8 * float(rows[0][2])                                  # the loss goes down over the run
+    valid = [open(os.path.join(nnet, "log", "compute_prob_valid.%d.log" % it)).read() for it in range(4)]
+    assert all("Overall average loss is" in v for v in valid)                           # eval_trained_dnn, every iteration
+    assert not os.path.exists(os.path.join(nnet, "log", "compute_prob_train_subset.0.log"))   # no such archive in this egs dir
     log0 = open(os.path.join(nnet, "log", "train.0.1.log")).read()
     assert "Average training loss for minibatches 1-2 is" in log0 and "Overall average objective function is" in log0
     # a second call resumes: every iteration's output exists, nothing is retrained

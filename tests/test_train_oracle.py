@@ -150,6 +150,8 @@ def _make_egs_dir(root, num_archives=3, minibatches=4, B=8, T=40, classes=20, se
             mbs = [(means[l][:, None, :] + synthetic.mfcc(1000 * a + i, B * T).reshape(B, T, 23)).astype(np.float32)
                    for i, l in enumerate(labs)]
             examples_io.write_egs_tar(os.path.join(root, "egs.%d.tar" % a), mbs, labs)
+            if a == 1:                                       # diagnostics archive (get_egs.sh writes valid_egs.1.tar)
+                examples_io.write_egs_tar(os.path.join(root, "valid_egs.1.tar"), mbs[:2], labs[:2])
     return root
 
 

@@ -146,6 +146,30 @@ def average_model_dirs(job_dirs, out_dir):
         fid.write("done")
 
 
+def eval_trained_dnn(args, _iter, egs_dir):
+    """Diagnostics of model_<iter> on the validation and train-subset archives (reference train_dnn.py:429-460 starts two
+    eval_dnn.py background commands; here Model.eval runs in this process, same log files and summary lines)."""
+    input_model_dir = "{0}/model_{1}".format(args.dir, _iter)
+    for name in ("valid", "train_subset"):
+        tar_file = "{0}/{1}_egs.1.tar".format(egs_dir, name)
+        if not os.path.exists(tar_file):
+            continue                                         # the reference's command would fail; the archive is optional here
+        log_path = "{0}/log/compute_prob_{1}.{2}.log".format(args.dir, name, _iter)
+        ev_logger = logging.getLogger("train_dnn.eval.%s.%d" % (name, _iter))
+        ev_logger.setLevel(logging.INFO)
+        ev_logger.propagate = False
+        fh = logging.FileHandler(log_path, mode="w")
+        fh.setFormatter(logging.Formatter("%(asctime)s [%(pathname)s:%(lineno)s - %(funcName)s - %(levelname)s ] %(message)s"))
+        ev_logger.addHandler(fh)
+        try:
+            ev_logger.info('Starting DNN evaluation (eval_dnn.py)')
+            getattr(models, args.tf_model_class)().eval(TarFileDataLoader(tar_file, logger=None, queue_size=16), input_model_dir,
+                                                        True, ev_logger)
+        finally:
+            ev_logger.removeHandler(fh)
+            fh.close()
+
+
 def train_one_iteration(args, _iter, egs_dir, num_jobs, num_archives_processed, num_archives, learning_rate,
                         archives_minibatch_count):
     model_dir = args.dir
@@ -154,6 +178,8 @@ def train_one_iteration(args, _iter, egs_dir, num_jobs, num_archives_processed, 
     if rank == 0 and not os.path.exists(random_seed_file):
         with open(random_seed_file, 'w') as fid:
             fid.write(str(args.random_seed))
+    if rank == 0:
+        eval_trained_dnn(args, _iter, egs_dir)               # computes train and validation set objectives
     if utils.is_correct_model_dir("{0}/model_{1}".format(model_dir, _iter + 1)):
         logger.info('The output model {0}/model_{1}/model.meta was exist and so I do not continue this iteration.'.format(model_dir, _iter + 1))
         return
