@@ -264,6 +264,14 @@ class Model(object):
         world = sharding.dist_info()[1] if data_parallel else 1
         compute, copy = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         minibatch_count = data_loader.count
+        if training and world > 1:
+            # every rank must step the same number of times (one gradient all-reduce per minibatch): check before the loop
+            import torch.distributed as dist
+            lo = torch.tensor([minibatch_count, -minibatch_count], dtype=torch.int64, device=dev)
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            if int(lo[0]) != -int(lo[1]):
+                raise ValueError("data-parallel training needs the same number of minibatches on every rank: this rank has %d, "
+                                 "the ranks hold between %d and %d" % (minibatch_count, int(lo[0]), -int(lo[1])))
         results = torch.zeros((max(minibatch_count, 1), 2), dtype=torch.float32, device=dev)
         grad = torch.zeros(tr.n_params, dtype=torch.float32, device=dev) if (training and world > 1) else None
         slots = [dict(feats=None, labels=None, ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
