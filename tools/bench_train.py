@@ -37,13 +37,17 @@ def main():
     torch.cuda.synchronize()
     eng.check_overflow()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import time
     e0.record()
+    h0 = time.perf_counter()
     for _ in range(steps):
         la = tr.forward_backward(feats, lab, B, T)
         tr.apply(1e-4)
+    host_ms = (time.perf_counter() - h0) * 1e3 / steps        # time the host needs to ENQUEUE one step
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+    print("host enqueue time %.3f ms/step" % host_ms)
     print("train step %s B=%d T=%d classes=%d: %.3f ms/step, %.1f M frames/s, loss %.4f, launches/step %d" %
           (topology, B, T, NC, ms, B * T / ms / 1e3, float(la[0]), tr.last_launch_count))
     eng.set_option("profile", 1)
