@@ -529,3 +529,33 @@ def test_leaky_relu_l2_loss_topology_trains():
         assert rel_l2(p.grad("output/b:0"), ref["grads"]["output/b:0"]) <= 1e-2
     finally:
         p.close()
+
+
+def test_changing_minibatch_geometry_leaves_no_stale_state():
+    """Egs archives mix minibatch lengths: a geometry run again after other (larger and smaller) geometries gives the same bits
+    (workspace re-laid-out without re-allocation, device-written metadata, graph captured on the second visit)."""
+    p = Problem("ModelWithoutDropoutTdnn", "B", 8, 96, 60)
+    try:
+        moving = {k: v for k, v in p.P.items() if k.endswith(("mean:0", "variance:0"))}
+        rng = np.random.default_rng(3)
+
+        def run(B, T):
+            x = torch.from_numpy(synthetic.mfcc(40 + T, B * T)).cuda()
+            lab = torch.from_numpy(rng.integers(0, 60, B).astype(np.int32)).cuda()
+            p.tr.set_params(moving)
+            la = p.tr.forward_backward(x, lab, B, T)
+            torch.cuda.synchronize()
+            p.eng.check_overflow()
+            return la.cpu().numpy().copy(), p.tr.download(p.native.TRAIN_GRAD)
+
+        la0, g0 = p.step(), p.tr.download(p.native.TRAIN_GRAD)
+        for B, T in ((16, 200), (4, 33), (8, 95), (16, 200), (4, 33)):
+            la, g = run(B, T)
+            assert np.isfinite(la).all() and np.isfinite(g).all()
+        p.tr.set_params(moving)
+        for _ in range(3):                                            # plain launch, capture, replay
+            p.tr.set_params(moving)
+            la1 = p.step()
+            assert np.array_equal(la0, la1) and np.array_equal(g0, p.tr.download(p.native.TRAIN_GRAD))
+    finally:
+        p.close()

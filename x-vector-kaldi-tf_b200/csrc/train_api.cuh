@@ -90,9 +90,13 @@ struct xv_trainer {
   float *wg_partial = nullptr, *sg_partial = nullptr;
   size_t wg_partial_floats = 0, sg_partial_floats = 0;
   xvk::SegMeta seg_meta{};
-  const int4* blk_info_dev = nullptr;           // staged once per geometry (all segments have seg_len rows)
+  const int4* blk_info_dev = nullptr;           // written by train_meta_kernel at the start of every step
+  int32_t blk_info_off = 0;
+  size_t ws_cap = 0;
+  std::vector<std::pair<int32_t, int32_t>> seen_geometries;   // a step is captured into a graph the second time its geometry shows up
   // CUDA graph of one forward_backward (74 launches): captured once per (geometry, buffer pointers), replayed afterwards
-  struct StepGraph { const void* feats; const void* labels; const void* grad; const void* loss; cudaGraphExec_t exec; int32_t launches; };
+  struct StepGraph { const void* feats; const void* labels; const void* grad; const void* loss; int32_t n_seg, seg_len;
+                     cudaGraphExec_t exec; int32_t launches; };
   std::vector<StepGraph> graphs;
   cudaStream_t gstream = nullptr;
   cudaEvent_t g_in = nullptr, g_out = nullptr;
@@ -164,12 +168,12 @@ void tr_drop_graphs(xv_trainer* t) {
   t->graphs.clear();
 }
 
+// Lays the workspace out for a minibatch geometry.  Egs archives mix minibatch lengths (200..400 frames), so a change of
+// geometry must be cheap: the buffer is only re-allocated when it has to grow, nothing is staged from the host (the segment
+// metadata is written by train_meta_kernel inside every step) and no buffer relies on having been zeroed.
 int tr_ensure_workspace(xv_trainer* t, int32_t n_seg, int32_t seg_len) {
   if (t->ws && t->n_seg == n_seg && t->seg_len == seg_len) return XV_OK;
   xv_model* m = t->m;
-  TR_CUDA(cudaDeviceSynchronize());
-  cudaFree(t->ws);
-  t->ws = nullptr;
   const int32_t stride = int32_t(round_up(int64_t(seg_len) + m->gap, tdnn2::POOL_BLOCK));
   const int64_t r_pad = round_up(int64_t(n_seg) * stride, tdnn2::TILE_ROWS);
   if (r_pad > (int64_t(1) << 31) - 4096) return fail(XV_EINVAL, "minibatch too large");
@@ -238,25 +242,27 @@ int tr_ensure_workspace(xv_trainer* t, int32_t n_seg, int32_t seg_len) {
   }
   t->sg_partial_floats = sg;
   want(reinterpret_cast<void**>(&t->sg_partial), std::max<size_t>(sg, 1) * 4);
-  TR_CUDA(cudaMalloc(reinterpret_cast<void**>(&t->ws), off));
-  TR_CUDA(cudaMemset(t->ws, 0, off));       // rows past the last segment are never written by the elementwise kernels: exact zeros
+  if (off > t->ws_cap) {
+    TR_CUDA(cudaDeviceSynchronize());
+    tr_drop_graphs(t);                        // captured steps hold pointers into the old buffer
+    cudaFree(t->ws);
+    t->ws = nullptr;
+    t->ws_cap = 0;
+    const size_t want_bytes = off + off / 8;
+    TR_CUDA(cudaMalloc(reinterpret_cast<void**>(&t->ws), want_bytes));
+    t->ws_cap = want_bytes;
+  }
   for (auto& c : carve) *c.first = t->ws + c.second;
   t->n_seg = n_seg;
   t->seg_len = seg_len;
   t->seg_stride = stride;
   t->r_pad = r_pad;
   t->debug.clear();
-  tr_drop_graphs(t);
   {
-    // segment metadata of the packed-row layout: a training minibatch has n_seg segments of seg_len rows, so it is staged once
-    std::vector<int32_t> lens(n_seg, seg_len);
-    StagedMeta sm;
-    int rc = stage_meta(m, lens.data(), n_seg, r_pad, t->meta, nullptr, &sm);
-    if (rc != XV_OK) return rc;
-    TR_CUDA(cudaStreamSynchronize(nullptr));
-    if (sm.r_pad != r_pad) return fail(XV_ESTATE, "internal: packed row count mismatch");
-    t->seg_meta = sm.seg;
-    t->blk_info_dev = sm.blk_info_dev;
+    const int64_t blk_info_off = round_up(int64_t(3) * n_seg, 4);
+    t->blk_info_off = int32_t(blk_info_off);
+    t->seg_meta = xvk::SegMeta{t->meta, t->meta + n_seg, t->meta + 2 * n_seg, n_seg};
+    t->blk_info_dev = reinterpret_cast<const int4*>(t->meta + blk_info_off);
   }
   return XV_OK;
 }
@@ -644,6 +650,16 @@ int tr_step_body(xv_trainer* t, const float* feats_dev, const int32_t* labels_de
 
   // ---- metadata + pack --------------------------------------------------------------------------
   {
+    const int32_t n_blk_all = int32_t(r_pad / 32);
+    TR_LAUNCH("train_meta_kernel", trk::train_meta_kernel, dim3((std::max(n_blk_all, n_seg) + 255) / 256), dim3(256), 0, t->meta, n_seg, seg_len,
+              t->seg_stride, n_blk_all, t->blk_info_off);
+    if (training) {
+      // rows past the last segment of the last layer's dz are written by no kernel (pool_relu_bwd works per segment) but read
+      // by the weight / data gradient kernels: exact zeros
+      const int64_t tail0 = int64_t(n_seg) * t->seg_stride;
+      TrFrame& LZ = t->frames[nl - 1];
+      if (r_pad > tail0) TR_CUDA(cudaMemsetAsync(LZ.dz + tail0 * LZ.c_out, 0, size_t(r_pad - tail0) * LZ.c_out * 2, stream));
+    }
     xvk::PackArgs a{};
     a.feats = feats_dev;
     a.r_pad = int32_t(r_pad);
@@ -905,8 +921,16 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
   const void* gkey = grad_dev ? static_cast<const void*>(grad_dev) : static_cast<const void*>(t->grad);
   xv_trainer::StepGraph* found = nullptr;
   for (auto& g : t->graphs)
-    if (g.feats == feats_dev && g.labels == labels_dev && g.grad == gkey && g.loss == loss_acc_dev) found = &g;
+    if (g.feats == feats_dev && g.labels == labels_dev && g.grad == gkey && g.loss == loss_acc_dev && g.n_seg == n_seg && g.seg_len == seg_len)
+      found = &g;
   if (!found) {
+    // egs archives mix minibatch lengths: capturing costs about two steps, so only a geometry that comes back is captured
+    const std::pair<int32_t, int32_t> geo(n_seg, seg_len);
+    if (std::find(t->seen_geometries.begin(), t->seen_geometries.end(), geo) == t->seen_geometries.end()) {
+      if (t->seen_geometries.size() >= 4096) t->seen_geometries.clear();
+      t->seen_geometries.push_back(geo);
+      return tr_step_body(t, feats_dev, labels_dev, n_seg, seg_len, grad_dev, loss_acc_dev, stream, true);
+    }
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamBeginCapture(t->gstream, cudaStreamCaptureModeThreadLocal);
     if (e == cudaSuccess) {
@@ -921,8 +945,8 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
       t->opt_graph = 0;
       return tr_step_body(t, feats_dev, labels_dev, n_seg, seg_len, grad_dev, loss_acc_dev, stream, true);
     }
-    if (t->graphs.size() >= 8) tr_drop_graphs(t);
-    t->graphs.push_back(xv_trainer::StepGraph{feats_dev, labels_dev, gkey, loss_acc_dev, exec, t->last_launches});
+    if (t->graphs.size() >= 64) tr_drop_graphs(t);
+    t->graphs.push_back(xv_trainer::StepGraph{feats_dev, labels_dev, gkey, loss_acc_dev, n_seg, seg_len, exec, t->last_launches});
     found = &t->graphs.back();
   }
   // the caller's stream order is kept: its earlier work -> graph -> its later work

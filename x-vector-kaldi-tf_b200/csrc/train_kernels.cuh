@@ -798,6 +798,28 @@ l2_term_kernel(const float* __restrict__ p, float* __restrict__ g, int64_t n, fl
   if (threadIdx.x == 0) loss_acc[0] += float(0.5 * double(coef) * red[0]);
 }
 
+// Segment metadata of a training minibatch (n_seg segments of seg_len rows, seg_stride packed rows each), written on the
+// device so that nothing is staged from the host when the minibatch geometry changes (the layout stage_meta builds for the
+// extraction path): meta = [row_start(n_seg) | feat_start(n_seg) | len(n_seg) | pad to int4 | blk_info(r_pad/32 x int4)],
+// blk_info = {first feature row, first frame of the block in its segment, segment length, valid rows}.
+__global__ void __launch_bounds__(256)
+train_meta_kernel(int32_t* __restrict__ meta, int32_t n_seg, int32_t seg_len, int32_t seg_stride, int32_t n_blk, int32_t blk_info_off) {
+  cudaTriggerProgrammaticLaunchCompletion();
+  cudaGridDependencySynchronize();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_seg) {
+    meta[i] = i * seg_stride;
+    meta[n_seg + i] = i * seg_len;
+    meta[2 * n_seg + i] = seg_len;
+  }
+  if (i < n_blk) {
+    const int bps = seg_stride / 32, seg = i / bps, t0 = (i % bps) * 32;
+    int4 e = make_int4(0, 0, 0, 0);
+    if (seg < n_seg) e = make_int4(seg * seg_len + t0, t0, seg_len, max(0, min(32, seg_len - t0)));
+    reinterpret_cast<int4*>(meta + blk_info_off)[i] = e;
+  }
+}
+
 // float16 minibatch as stored in the egs archives (examples_io.py:165) -> float32 features, 8 values per thread
 __global__ void __launch_bounds__(256) f16_to_f32_kernel(const __half* __restrict__ src, float* __restrict__ dst, int64_t n) {
   cudaTriggerProgrammaticLaunchCompletion();
