@@ -338,7 +338,10 @@ def run_b200(args):
     n_blk = B * (-(-T // 32))
     # (kernel, bound, algorithmic FLOP or bytes per launch) in launch order
     table = [("pack_im2col_kernel", "hbm", frames * (FEAT_DIM * 4 + k0_pad * 2 + 1))]
-    table += [("tdnn_pair_kernel[L%d]" % i, "tensor", frames * f) for i, f in enumerate(fl)]
+    # layer 0 (K = 128) is bound by its own output stream (K0 = 117 760 FLOP / (92 + 1 024) B = 105 FLOP/B, HBM-bound):
+    # judged against HBM with SURVEY's algorithmic bytes per frame (fp32 features in, fp16 activations out); layers 1.. tensor bound
+    table += [("tdnn_pair_kernel[L0]", "hbm", frames * (FEAT_DIM * 4 + topo["layer_sizes"][0] * 2))]
+    table += [("tdnn_pair_kernel[L%d]" % i, "tensor", frames * f) for i, f in enumerate(fl) if i > 0]
     if topo.get("pooling") == "attention":       # models.py:1037-1051: score GEMM [frames, C] x [C, C], softmax over time, weighted sums
         c_last //= 2
         table += [("tdnn_pair_kernel<3>[attention scores]", "tensor", frames * 2 * c_last * c_last),
