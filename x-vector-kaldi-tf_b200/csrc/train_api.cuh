@@ -714,7 +714,7 @@ int tr_step_body(xv_trainer* t, const float* feats_dev, const int32_t* labels_de
     b.gamma = t->params + L.off_gamma; b.beta = t->params + L.off_beta;
     b.moving_mean = t->moving + L.off_mov; b.moving_var = t->moving + L.off_mov + L.c_out;
     b.mean = L.bn; b.inv = L.bn + L.c_out; b.scale = L.bn + 2 * L.c_out; b.shift = L.bn + 3 * L.c_out;
-    TR_LAUNCH("bn_fwd_finalize_kernel", trk::bn_fwd_finalize_kernel, dim3(L.c_out / 32), dim3(dim3(32, trk::RED_Y)), 0, b);
+    TR_LAUNCH("bn_fwd_finalize_kernel", trk::bn_fwd_finalize_kernel, dim3(L.c_out / trk::RED_X), dim3(trk::RED_X, trk::RED_Y), 0, b);
     if (i < nl - 1) {
       const int64_t n8 = r_pad * L.c_out / 8;
       TR_LAUNCH("bn_apply_kernel", trk::bn_apply_kernel, dim3(unsigned((n8 + 1023) / 1024)), dim3(256), 0, L.r, t->row_valid, b.scale, b.shift, n8, L.c_out / 8, L.y, m->overflow_dev);
@@ -847,7 +847,7 @@ int tr_step_body(xv_trainer* t, const float* feats_dev, const int32_t* labels_de
     a.coefA = t->coefA; a.coefG = t->coefG; a.d_gamma = grad + LL.off_gamma; a.d_beta = grad + LL.off_beta;
     TR_LAUNCH("pool_bwd_coef_kernel", trk::pool_bwd_coef_kernel, dim3((C + 31) / 32), dim3(dim3(32, trk::SEG_Y)), 0, a);
     TR_LAUNCH("pool_relu_bwd_kernel", trk::pool_relu_bwd_kernel, dim3(C / trk::COLS_PER_CTA, n_seg), dim3(256), 0, static_cast<const __half*>(LL.r), C, t->seg_stride, seg_len, static_cast<const float*>(t->coefA), static_cast<const float*>(t->coefG), LL.dz, t->partial1, m->overflow_dev, t->neg_slope);
-    TR_LAUNCH("colsum_finalize_kernel", trk::colsum_finalize_kernel, dim3(C / 32), dim3(32, trk::RED_Y), 0, static_cast<const float*>(t->partial1), n_seg, C, inv_S, grad + LL.off_b);
+    TR_LAUNCH("colsum_finalize_kernel", trk::colsum_finalize_kernel, dim3(C / trk::RED_X), dim3(trk::RED_X, trk::RED_Y), 0, static_cast<const float*>(t->partial1), n_seg, C, inv_S, grad + LL.off_b);
   }
 
   // ---- frame layers backward ---------------------------------------------------------------------------
@@ -861,9 +861,9 @@ int tr_step_body(xv_trainer* t, const float* feats_dev, const int32_t* labels_de
       b.gamma = t->params + L.off_gamma; b.mean = L.bn; b.inv = L.bn + L.c_out;
       b.cA = t->cA; b.cB = t->cB; b.cC = t->cC;
       b.d_gamma = grad + L.off_gamma; b.d_beta = grad + L.off_beta;
-      TR_LAUNCH("bn_bwd_finalize_kernel", trk::bn_bwd_finalize_kernel, dim3(L.c_out / 32), dim3(dim3(32, trk::RED_Y)), 0, b);
+      TR_LAUNCH("bn_bwd_finalize_kernel", trk::bn_bwd_finalize_kernel, dim3(L.c_out / trk::RED_X), dim3(trk::RED_X, trk::RED_Y), 0, b);
       TR_LAUNCH("bn_relu_bwd_kernel", trk::bn_relu_bwd_kernel, dim3(L.c_out / trk::COLS_PER_CTA, n_part), dim3(256), 0, static_cast<const __half*>(L.dy), static_cast<const __half*>(L.r), L.c_out, ROWS_PER_PART, static_cast<const float*>(t->cA), static_cast<const float*>(t->cB), static_cast<const float*>(t->cC), L.dz, t->partial1, m->overflow_dev, t->neg_slope, static_cast<const uint8_t*>(t->row_valid));
-      TR_LAUNCH("colsum_finalize_kernel", trk::colsum_finalize_kernel, dim3(L.c_out / 32), dim3(32, trk::RED_Y), 0, static_cast<const float*>(t->partial1), n_part, L.c_out, inv_S, grad + L.off_b);
+      TR_LAUNCH("colsum_finalize_kernel", trk::colsum_finalize_kernel, dim3(L.c_out / trk::RED_X), dim3(trk::RED_X, trk::RED_Y), 0, static_cast<const float*>(t->partial1), n_part, L.c_out, inv_S, grad + L.off_b);
     }
     const __half* x = (i == 0) ? t->x0 : t->frames[i - 1].y;
     rc = tr_wgrad(t, stream, "wgrad_pair_kernel", L, x, L.dz, grad + L.off_w, inv_S);

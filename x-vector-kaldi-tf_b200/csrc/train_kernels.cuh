@@ -91,12 +91,14 @@ blk_col_sums_kernel(const __half* __restrict__ x, const __half* __restrict__ y, 
   partial[(int64_t(part) * 2 + 1) * C + c0 + t] = b;
 }
 
-// Sum partial[blk][j][c] over blk for 32 channels per CTA (block 32 x RED_Y), fp64, fixed order.
-constexpr int RED_Y = 32;
+// Sum partial[blk][j][c] over blk for RED_X channels per CTA (block RED_X x RED_Y), fp64, fixed order.  Few channels per CTA:
+// the partial rows sit in L2 and the reduction is latency bound, so it wants many CTAs (C / 8 = 64 .. 192) more than wide rows.
+constexpr int RED_X = 8;
+constexpr int RED_Y = 128;
 constexpr int SEG_Y = 8;      // row groups of the segment-level (<= 64 rows) kernels
 template <int NSUM>
 __device__ __forceinline__ void reduce_blocks(const float* __restrict__ partial, int32_t n_blk, int32_t C, int c, double (&out)[NSUM],
-                                              double (*sred)[NSUM][32]) {
+                                              double (*sred)[NSUM][RED_X]) {
   double s[NSUM], u[NSUM];
 #pragma unroll
   for (int j = 0; j < NSUM; ++j) { s[j] = 0.0; u[j] = 0.0; }
@@ -140,8 +142,8 @@ struct BnFwdArgs {
 __global__ void __launch_bounds__(1024) bn_fwd_finalize_kernel(const BnFwdArgs a) {
   cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
   cudaGridDependencySynchronize();
-  __shared__ double sred[RED_Y][2][32];
-  const int c = blockIdx.x * 32 + threadIdx.x;
+  __shared__ double sred[RED_Y][2][RED_X];
+  const int c = blockIdx.x * RED_X + threadIdx.x;
   double s[2];
   reduce_blocks<2>(a.partial, a.n_blk, a.C, c, s, sred);
   if (threadIdx.y != 0) return;
@@ -224,8 +226,8 @@ struct BnBwdArgs {
 __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const BnBwdArgs a) {
   cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
   cudaGridDependencySynchronize();
-  __shared__ double sred[RED_Y][2][32];
-  const int c = blockIdx.x * 32 + threadIdx.x;
+  __shared__ double sred[RED_Y][2][RED_X];
+  const int c = blockIdx.x * RED_X + threadIdx.x;
   double s[2];
   reduce_blocks<2>(a.partial, a.n_blk, a.C, c, s, sred);
   if (threadIdx.y != 0) return;
@@ -305,8 +307,8 @@ __global__ void __launch_bounds__(1024)
 colsum_finalize_kernel(const float* __restrict__ partial1, int32_t n_blk, int32_t C, float scale, float* __restrict__ out) {
   cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
   cudaGridDependencySynchronize();
-  __shared__ double sred[RED_Y][1][32];
-  const int c = blockIdx.x * 32 + threadIdx.x;
+  __shared__ double sred[RED_Y][1][RED_X];
+  const int c = blockIdx.x * RED_X + threadIdx.x;
   double s[1];
   reduce_blocks<1>(partial1, n_blk, C, c, s, sred);
   if (threadIdx.y == 0) out[c] = float(s[0] * double(scale));
