@@ -203,3 +203,16 @@ def test_eval_dnn_cli_rejects_bad_arguments(tmp_path):
     (mdir / "model.meta").write_text("{}")
     with pytest.raises(Exception, match="tar file"):
         eval_dnn.get_args(["--tar-file", str(tmp_path / "valid_egs.1.tar"), "--input-dir", str(mdir), "--log-file", str(tmp_path / "l.log")])
+
+
+@pytest.mark.parametrize("topology", ["ModelWithoutDropoutTdnn", "ModelWithoutDropout", "ModelL2LossWithoutDropoutLRelu"])
+def test_golden_minibatch(topology):
+    """The oracle against its own committed outputs (tests/golden/make_golden_train.py): guards refactorings of the oracle."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden_train
+    got = make_golden_train.compute(topology)
+    with np.load(os.path.join(ROOT, "tests", "golden", "train_golden.npz")) as z:
+        want = {k.split("|", 1)[1]: z[k] for k in z.files if k.startswith(topology + "|")}
+    assert set(got) == set(want)
+    for k in want:
+        np.testing.assert_allclose(got[k], want[k], rtol=1e-9, atol=1e-12, err_msg=k)
