@@ -1,96 +1,103 @@
 #!/bin/bash
-# GPU counterpart of the reference's local/tf/extract_xvectors.sh (same positional arguments, options, stages and output
-# files: xvector.JOB.{ark,scp}, xvector.scp, spk_xvector.{ark,scp}, num_utts.ark).
+# extract_xvectors.sh <nnet-dir> <data-dir> <xvector-dir>
 #
-# What differs from the reference (local/tf/extract_xvectors.sh:63-95): there the data directory is split into --nj pieces
-# and every piece is a separate TensorFlow process.  Here --nj is the number of GPU processes: each job reads its split
-# through the same Kaldi feature pipe (apply-cmvn-sliding | select-voiced-frames) and runs extract_embedding.py from this
-# directory on GPU (job-1) mod --num-gpus; one process keeps a whole GPU busy, so --nj defaults to the number of GPUs.
-# (One multi-GPU process over ONE pipe is the other way to run it: torchrun --nproc-per-node N extract_embedding.py ...)
+# GPU counterpart of the reference's local/tf/extract_xvectors.sh: same positional arguments, same option names where they
+# still mean something, same stages and the same files left behind (xvector.<job>.{ark,scp}, xvector.scp,
+# spk_xvector.{ark,scp}, num_utts.ark, log/extract.<job>.log), so sid-style recipes can call it unchanged.
+#
+# The reference splits the data directory into --nj pieces and starts one TensorFlow process per piece
+# (local/tf/extract_xvectors.sh:63-88).  Here a job is one process of this directory's extract_embedding.py bound to one
+# GPU (job j -> device (j-1) mod num-gpus through XVEC_DEVICE); one process saturates a B200, so --nj defaults to the
+# number of visible GPUs.  Features come through the same Kaldi pipe the reference builds (sliding-window CMN over 300
+# frames, then voiced frames only; local/tf/extract_xvectors.sh:68).
 
-# Begin configuration section.
-num_gpus=$(nvidia-smi -L 2>/dev/null | wc -l)
-[ "${num_gpus}" -ge 1 ] 2>/dev/null || num_gpus=1
-nj=${num_gpus}
-cmd="run.pl"
+set -o pipefail
 
-chunk_size=-1     # The chunk size over which the embedding is extracted.
-                  # If left unspecified, it uses the max_chunk_size in the nnet directory.
-use_gpu=true      # kept for command-line compatibility: there is no CPU path
+# ---- options (Kaldi's parse_options.sh turns --foo-bar X into foo_bar=X) ----
+num_gpus=$(nvidia-smi -L 2>/dev/null | grep -c '^GPU')
+if [ -z "${num_gpus}" ] || [ "${num_gpus}" -lt 1 ]; then num_gpus=1; fi
+nj=                 # jobs; empty = one per GPU
+cmd=run.pl
+chunk_size=-1       # <= 0: take max_chunk_size of the nnet dir
+use_gpu=true        # accepted for compatibility; this build has no CPU path
 stage=0
 
-echo "${0} $@"  # Print the command line for logging
+echo "$0 $*"
 
-here=$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)
+script_dir=$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)
+[ -f path.sh ] && . ./path.sh
+. parse_options.sh || exit 1
 
-if [ -f path.sh ]; then . ./path.sh; fi
-. parse_options.sh || exit 1;
+die() { echo "$0: $*" >&2; exit 1; }
 
-if [ $# != 3 ]; then
-  echo "Usage: ${0} <nnet-dir> <data> <xvector-dir>"
-  echo " e.g.: ${0} exp/xvector_nnet data/train exp/xvectors_train"
-  echo "main options (for others, see top of script file)"
-  echo "  --cmd (utils/run.pl|utils/queue.pl <queue opts>) # how to run jobs."
-  echo "  --num-gpus <n|all visible>                       # GPUs to spread the jobs over"
-  echo "  --nj <n|num-gpus>                                # Number of jobs (one process per job)"
-  echo "  --stage <stage|0>                                # To control partial reruns"
-  echo "  --chunk-size <n|-1>                              # If provided, extracts embeddings with specified"
-  echo "                                                   # chunk size, and averages to produce final embedding"
-  exit 1;
+if [ $# -ne 3 ]; then
+  cat >&2 <<USAGE
+Usage: $0 [options] <nnet-dir> <data> <xvector-dir>
+ e.g.: $0 exp/xvector_nnet data/train exp/xvectors_train
+Options:
+  --cmd (utils/run.pl|utils/queue.pl <queue opts>)   how to run the jobs
+  --num-gpus <n>      GPUs to use (default: all visible)
+  --nj <n>            number of jobs, one process each (default: --num-gpus)
+  --stage <n>         0 extract, 1 merge scp files, 2 speaker means
+  --chunk-size <n>    frames per chunk; chunks of an utterance are averaged (default: max_chunk_size of the nnet dir)
+USAGE
+  exit 1
 fi
 
-srcdir=$1
-data=$2
-dir=$3
+nnet_dir=$1
+data_dir=$2
+out_dir=$3
+[ -n "${nj}" ] || nj=${num_gpus}
 
-for f in ${srcdir}/model_final/model.meta ${srcdir}/min_chunk_size ${srcdir}/max_chunk_size ${data}/feats.scp ${data}/vad.scp ; do
-  [ ! -f ${f} ] && echo "No such file $f" && exit 1;
+for required in "${nnet_dir}/model_final/model.meta" "${nnet_dir}/min_chunk_size" "${nnet_dir}/max_chunk_size" \
+                "${data_dir}/feats.scp" "${data_dir}/vad.scp"; do
+  [ -f "${required}" ] || die "No such file ${required}"
 done
 
-min_chunk_size=`cat ${srcdir}/min_chunk_size 2>/dev/null`
-max_chunk_size=`cat ${srcdir}/max_chunk_size 2>/dev/null`
+min_chunk=$(cat "${nnet_dir}/min_chunk_size")
+max_chunk=$(cat "${nnet_dir}/max_chunk_size")
+[ "${chunk_size}" -gt 0 ] || chunk_size=${max_chunk}
+[ "${chunk_size}" -le "${max_chunk}" ] || die "specified chunk size of ${chunk_size} is larger than the maximum chunk size, ${max_chunk}"
 
-model_dir=${srcdir}/model_final
+mkdir -p "${out_dir}/log"
+utils/split_data.sh --per-utt "${data_dir}" "${nj}" || exit 1
+split_dir=${data_dir}/split${nj}utt
 
-if [ ${chunk_size} -le 0 ]; then
-  chunk_size=${max_chunk_size}
-fi
+# feature pipe of job $1 (what extract_embedding.py opens as its --feature-rspecifier)
+feature_pipe() {
+  local part=${split_dir}/$1
+  echo "apply-cmvn-sliding --norm-vars=false --center=true --cmn-window=300 scp:${part}/feats.scp ark:- |" \
+       "select-voiced-frames ark:- scp,s,cs:${part}/vad.scp ark:- |"
+}
 
-if [ ${max_chunk_size} -lt ${chunk_size} ]; then
-  echo "${0}: specified chunk size of ${chunk_size} is larger than the maximum chunk size, ${max_chunk_size}" && exit 1;
-fi
-
-mkdir -p ${dir}/log
-
-utils/split_data.sh --per-utt ${data} ${nj}
-echo "${0}: extracting xvectors for ${data}"
-sdata=${data}/split${nj}utt/JOB
-
-# Set up the features
-feature_rspecifier="apply-cmvn-sliding --norm-vars=false --center=true --cmn-window=300 scp:${sdata}/feats.scp ark:- | select-voiced-frames ark:- scp,s,cs:${sdata}/vad.scp ark:- |"
-
-if [ ${stage} -le 0 ]; then
-  echo "${0}: extracting xvectors from nnet on ${num_gpus} GPU(s), ${nj} job(s)"
-  for g in $(seq ${nj}); do
-    XVEC_DEVICE=$(( (g - 1) % num_gpus )) ${cmd} "${dir}/log/extract.${g}.log" \
-      python "${here}/extract_embedding.py" \
-        --use-gpu=yes --min-chunk-size=${min_chunk_size} --chunk-size=${chunk_size} \
-        --feature-rspecifier="`echo ${feature_rspecifier} | sed s/JOB/${g}/g`" \
-        --vector-wspecifier="| copy-vector ark:- ark,scp:${dir}/xvector.${g}.ark,${dir}/xvector.${g}.scp" \
-        --model-dir="${model_dir}" || exit 1 &
+if [ "${stage}" -le 0 ]; then
+  echo "$0: extracting xvectors for ${data_dir}: ${nj} job(s) on ${num_gpus} GPU(s)"
+  pids=()
+  for job in $(seq "${nj}"); do
+    XVEC_DEVICE=$(( (job - 1) % num_gpus )) ${cmd} "${out_dir}/log/extract.${job}.log" \
+      python "${script_dir}/extract_embedding.py" --use-gpu=yes \
+        --min-chunk-size="${min_chunk}" --chunk-size="${chunk_size}" \
+        --feature-rspecifier="$(feature_pipe "${job}")" \
+        --vector-wspecifier="| copy-vector ark:- ark,scp:${out_dir}/xvector.${job}.ark,${out_dir}/xvector.${job}.scp" \
+        --model-dir="${nnet_dir}/model_final" &
+    pids+=($!)
   done
-  wait
+  failed=0
+  for pid in "${pids[@]}"; do wait "${pid}" || failed=$((failed + 1)); done
+  [ "${failed}" -eq 0 ] || die "${failed} extraction job(s) failed; see ${out_dir}/log/extract.*.log"
 fi
 
-if [ ${stage} -le 1 ]; then
-  echo "${0}: combining xvectors across jobs"
-  for j in $(seq ${nj}); do cat ${dir}/xvector.${j}.scp; done > ${dir}/xvector.scp || exit 1;
+if [ "${stage}" -le 1 ]; then
+  echo "$0: combining xvectors across jobs"
+  : > "${out_dir}/xvector.scp"
+  for job in $(seq "${nj}"); do
+    cat "${out_dir}/xvector.${job}.scp" >> "${out_dir}/xvector.scp" || exit 1
+  done
 fi
 
-if [ ${stage} -le 2 ]; then
-  # Average the utterance-level xvectors to get speaker-level xvectors.
-  echo "${0}: computing mean of xvectors for each speaker"
-  run.pl ${dir}/log/speaker_mean.log \
-    ivector-mean ark:${data}/spk2utt scp:${dir}/xvector.scp \
-    ark,scp:${dir}/spk_xvector.ark,${dir}/spk_xvector.scp ark,t:${dir}/num_utts.ark || exit 1;
+if [ "${stage}" -le 2 ]; then
+  echo "$0: computing mean of xvectors for each speaker"
+  run.pl "${out_dir}/log/speaker_mean.log" \
+    ivector-mean "ark:${data_dir}/spk2utt" "scp:${out_dir}/xvector.scp" \
+      "ark,scp:${out_dir}/spk_xvector.ark,${out_dir}/spk_xvector.scp" "ark,t:${out_dir}/num_utts.ark" || exit 1
 fi
