@@ -35,6 +35,16 @@ class XvTopology(ctypes.Structure):
                 ("bn_eps", ctypes.c_float), ("var_eps", ctypes.c_float), ("pooling", ctypes.c_int32)]
 
 
+class XvCmvnOpts(ctypes.Structure):
+    """xv_cmvn_opts (include/xvec_frontend.h): the options of Kaldi's apply-cmvn-sliding; defaults are what the
+    reference passes (local/tf/extract_xvectors.sh:68)."""
+    _fields_ = [("cmn_window", ctypes.c_int32), ("min_window", ctypes.c_int32), ("center", ctypes.c_int32),
+                ("normalize_variance", ctypes.c_int32)]
+
+    def __init__(self, cmn_window=300, min_window=100, center=True, normalize_variance=False):
+        super().__init__(int(cmn_window), int(min(min_window, cmn_window)), int(bool(center)), int(bool(normalize_variance)))
+
+
 class XvecError(RuntimeError):
     def __init__(self, code, message):
         super().__init__("xvec_b200 error %d: %s" % (code, message))
@@ -47,6 +57,7 @@ def build_library(verbose=False):
     sources = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
     sources.append(os.path.join(REPO_ROOT, "include", "xvec.h"))
     sources.append(os.path.join(REPO_ROOT, "include", "xvec_train.h"))
+    sources.append(os.path.join(REPO_ROOT, "include", "xvec_frontend.h"))
     if os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in sources):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
@@ -136,6 +147,13 @@ def load_library():
     lib.xv_convert_f16_to_f32.restype = ctypes.c_int
     lib.xv_train_last_kernel_names.argtypes = [P, ctypes.c_char_p, I64]
     lib.xv_train_last_kernel_names.restype = I64
+    # feature front end (include/xvec_frontend.h)
+    lib.xv_frontend_workspace_bytes.argtypes = [P, I64, I32]
+    lib.xv_frontend_workspace_bytes.restype = SZ
+    lib.xv_frontend.argtypes = [P, P, P, P, P, I32, ctypes.POINTER(XvCmvnOpts), P, P, SZ, P]
+    lib.xv_frontend.restype = ctypes.c_int
+    lib.xv_submit_host_raw.argtypes = [P, P, P, P, P, I32, ctypes.POINTER(XvCmvnOpts), P, I32, P, ctypes.POINTER(I32)]
+    lib.xv_submit_host_raw.restype = ctypes.c_int
     _lib = lib
     return lib
 
@@ -147,7 +165,9 @@ EXPORTED_SYMBOLS = ["xv_create", "xv_destroy", "xv_set_param", "xv_workspace_byt
                     "xv_train_create", "xv_train_destroy", "xv_train_size", "xv_train_span", "xv_train_upload",
                     "xv_train_download", "xv_train_set_step", "xv_train_get_step", "xv_train_forward_backward", "xv_train_eval",
                     "xv_train_apply", "xv_train_sync_model", "xv_train_debug_tensor", "xv_train_set_option",
-                    "xv_train_last_launch_count", "xv_train_last_kernel_names", "xv_convert_f16_to_f32"]
+                    "xv_train_last_launch_count", "xv_train_last_kernel_names", "xv_convert_f16_to_f32",
+                    # include/xvec_frontend.h
+                    "xv_frontend_workspace_bytes", "xv_frontend", "xv_submit_host_raw"]
 
 
 def _check(lib, rc):
@@ -284,6 +304,65 @@ class XvecEngine:
 
     def collect(self, ticket):
         _check(self.lib, self.lib.xv_collect(self.handle, int(ticket)))
+
+    # ---- feature front end: apply-cmvn-sliding | select-voiced-frames on the device (include/xvec_frontend.h) ----
+    def frontend(self, feats_dev, vad_dev, utt_lens, out_keep=None, opts=None, out_dev=None, stream=None):
+        """feats_dev: float32 CUDA [sum(utt_lens), feat_dim] raw rows; vad_dev: float32 CUDA [sum(utt_lens)] or None;
+        out_keep: selected rows to write per utterance (int32 host; required with a VAD track).  Enqueues on ``stream``;
+        returns out_dev [sum(out_keep), feat_dim], laid out as the ``feats_dev`` of ``forward``."""
+        import torch
+        lens = np.ascontiguousarray(utt_lens, dtype=np.int32)
+        n_utt, total = int(lens.shape[0]), int(lens.sum())
+        assert feats_dev.is_cuda and feats_dev.dtype == torch.float32 and feats_dev.is_contiguous()
+        assert feats_dev.shape[0] == total and feats_dev.shape[1] == self.feat_dim
+        if vad_dev is not None:
+            assert vad_dev.is_cuda and vad_dev.dtype == torch.float32 and vad_dev.is_contiguous() and vad_dev.numel() == total
+            assert out_keep is not None, "out_keep (voiced rows to write per utterance) is required with a VAD track"
+        keep = lens if out_keep is None else np.ascontiguousarray(out_keep, dtype=np.int32)
+        assert keep.shape == lens.shape
+        dev = feats_dev.device
+        if out_dev is None:
+            out_dev = torch.empty((int(keep.sum()), self.feat_dim), dtype=torch.float32, device=dev)
+        assert out_dev.is_contiguous() and out_dev.shape[0] >= int(keep.sum())
+        opts = XvCmvnOpts() if opts is None else opts
+        need = int(self.lib.xv_frontend_workspace_bytes(self.handle, total, n_utt))
+        if getattr(self, "_fe_ws", None) is None or self._fe_ws.numel() < need:
+            self._fe_ws = torch.empty(int(need * 1.25) + 1024, dtype=torch.uint8, device=dev)
+        s = torch.cuda.current_stream(dev) if stream is None else stream
+        _check(self.lib, self.lib.xv_frontend(self.handle, feats_dev.data_ptr(), None if vad_dev is None else vad_dev.data_ptr(),
+                                              lens.ctypes.data_as(ctypes.c_void_p),
+                                              None if out_keep is None else keep.ctypes.data_as(ctypes.c_void_p), n_utt,
+                                              ctypes.byref(opts), out_dev.data_ptr(), self._fe_ws.data_ptr(),
+                                              self._fe_ws.numel(), s.cuda_stream))
+        return out_dev
+
+    def submit_host_raw(self, feats_host, vad_host, utt_lens, out_keep, seg_lens, emb_host, opts=None):
+        """``submit_host`` with the front end in front: raw rows + VAD track (host, should be pinned) in, embeddings of
+        the ``seg_lens`` segments that tile the selected rows out.  Collect with ``collect(ticket)``."""
+        lens = np.ascontiguousarray(utt_lens, dtype=np.int32)
+        segs = np.ascontiguousarray(seg_lens, dtype=np.int32)
+        total = int(lens.sum())
+
+        def host_ptr(a, rows):
+            if a is None:
+                return None
+            if hasattr(a, "data_ptr"):
+                assert a.is_contiguous() and a.shape[0] == rows
+                return a.data_ptr()
+            assert a.dtype == np.float32 and a.flags.c_contiguous and a.shape[0] == rows
+            return a.ctypes.data
+
+        keep = None if out_keep is None else np.ascontiguousarray(out_keep, dtype=np.int32)
+        opts = XvCmvnOpts() if opts is None else opts
+        eptr = emb_host.data_ptr() if hasattr(emb_host, "data_ptr") else emb_host.ctypes.data
+        ticket = ctypes.c_int32(-1)
+        _check(self.lib, self.lib.xv_submit_host_raw(self.handle, host_ptr(feats_host, total), host_ptr(vad_host, total),
+                                                     lens.ctypes.data_as(ctypes.c_void_p),
+                                                     None if keep is None else keep.ctypes.data_as(ctypes.c_void_p),
+                                                     int(lens.shape[0]), ctypes.byref(opts),
+                                                     segs.ctypes.data_as(ctypes.c_void_p), int(segs.shape[0]), eptr,
+                                                     ctypes.byref(ticket)))
+        return int(ticket.value)
 
     def last_kernel_ms(self):
         """Device duration (ms) of every launch of the last forward (option ``profile`` must be 1);

@@ -111,11 +111,17 @@ struct xv_model {
     float* feats_dev = nullptr; size_t feats_cap = 0;
     float* emb_dev = nullptr; size_t emb_cap = 0;
     void* ws_dev = nullptr; size_t ws_cap = 0;
+    // xv_submit_host_raw (include/xvec_frontend.h): raw rows, VAD track and scratch of the feature front end
+    float* raw_dev = nullptr; size_t raw_cap = 0;
+    float* vad_dev = nullptr; size_t vad_cap = 0;
+    void* fe_ws_dev = nullptr; size_t fe_ws_cap = 0;
     uint32_t* overflow_host = nullptr;   // pinned
     bool busy = false;
   } slots[XV_HOST_SLOTS];
   int slot_next = 0;
   int32_t last_launches = 0;
+  int32_t last_frontend_launches = 0;
+  size_t fe_smem_opted = 0;          // dynamic shared memory cmvn_select_kernel has been opted in for
   // options
   int num_clusters = 74;             // co-resident CTA pairs of tdnn_pair_kernel
   int opt_resident = 0;              // 1: keep a channel tile's weights resident in shared memory when they fit
@@ -306,6 +312,15 @@ int finalize_params(xv_model* m) {
   }
   m->dirty = false;
   return XV_OK;
+}
+
+// The model's sticky device flag: bit 0 = an fp16 store overflowed, bit 1 = the feature front end found fewer voiced rows
+// in an utterance than the caller's out_keep said (frontend.cuh).
+int sticky_flag_error(uint32_t flag) {
+  if (flag & 2u)
+    return fail(XV_EINVAL, "feature front end: an utterance has fewer voiced rows than out_keep says (VAD track and row "
+                           "counts disagree); results are not trustworthy");
+  return fail(XV_EOVERFLOW, "an activation exceeded the fp16 range (|x| > 65504); results are not trustworthy");
 }
 
 int ensure_meta_capacity(xv_model* m, int64_t n_ints) {
@@ -906,6 +921,7 @@ void xv_destroy(xv_model* m) {
   if (m->overflow_host) cudaFreeHost(m->overflow_host);
   for (auto& sl : m->slots) {
     cudaFree(sl.feats_dev); cudaFree(sl.emb_dev); cudaFree(sl.ws_dev);
+    cudaFree(sl.raw_dev); cudaFree(sl.vad_dev); cudaFree(sl.fe_ws_dev);
     if (sl.overflow_host) cudaFreeHost(sl.overflow_host);
     if (sl.stream) cudaStreamDestroy(sl.stream);
   }
@@ -1033,7 +1049,7 @@ int xv_collect(xv_model* m, int32_t ticket) {
   XV_CUDA(cudaStreamSynchronize(sl.stream));
   if (*sl.overflow_host != 0) {
     XV_CUDA(cudaMemsetAsync(m->overflow_dev, 0, 4, sl.stream));
-    return fail(XV_EOVERFLOW, "an activation exceeded the fp16 range (|x| > 65504); results are not trustworthy");
+    return sticky_flag_error(*sl.overflow_host);
   }
   return XV_OK;
 }
@@ -1053,7 +1069,7 @@ int xv_check_overflow(xv_model* m, void* stream) {
   XV_CUDA(cudaStreamSynchronize(s));
   if (*m->overflow_host != 0) {
     XV_CUDA(cudaMemsetAsync(m->overflow_dev, 0, 4, s));
-    return fail(XV_EOVERFLOW, "an activation exceeded the fp16 range (|x| > 65504); results are not trustworthy");
+    return sticky_flag_error(*m->overflow_host);
   }
   return XV_OK;
 }
@@ -1092,3 +1108,6 @@ int xv_set_option(xv_model* m, const char* name, int64_t value) {
 
 // ---- training step (include/xvec_train.h) ----
 #include "train_api.cuh"
+
+// ---- feature front end: sliding-window CMVN + voiced-frame selection (include/xvec_frontend.h) ----
+#include "frontend_api.cuh"

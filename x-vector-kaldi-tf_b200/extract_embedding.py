@@ -52,6 +52,16 @@ _FLAGS = (
     ("--feature-rspecifier", "feature_rspecifier", str, None, True, "Kaldi rspecifier of the feature matrices (file, 'ark:file', or 'command |')."),
     ("--vector-wspecifier", "vector_wspecifier", str, None, True, "Kaldi wspecifier for the x-vectors (file, '| command', 'ark,scp:A,S')."),
     ("--model-dir", "model_dir", str, None, True, "Model directory holding model.meta, model.npz and done."),
+    # ---- additive: the Kaldi pipe of local/tf/extract_xvectors.sh:68 on the device (include/xvec_frontend.h) ----
+    ("--apply-cmvn-sliding", "apply_cmvn_sliding", str, "no", False, "'yes': --feature-rspecifier holds RAW features; sliding-window "
+                                                                    "CMVN runs on the GPU (what apply-cmvn-sliding does in the recipe)."),
+    ("--cmn-window", "cmn_window", int, 300, False, "apply-cmvn-sliding --cmn-window."),
+    ("--norm-vars", "norm_vars", str, "false", False, "apply-cmvn-sliding --norm-vars (true/false)."),
+    ("--center", "center", str, "true", False, "apply-cmvn-sliding --center (true/false)."),
+    ("--min-cmn-window", "min_cmn_window", int, 100, False, "apply-cmvn-sliding --min-cmn-window (only used with --center=false)."),
+    ("--vad-rspecifier", "vad_rspecifier", str, None, False, "Kaldi rspecifier of per-frame VAD decisions (e.g. 'scp:data/vad.scp'); "
+                                                             "given: only voiced frames reach the network (select-voiced-frames), "
+                                                             "selected on the GPU after the CMVN."),
 )
 
 
@@ -59,7 +69,7 @@ def get_args(argv=None):
     parser = argparse.ArgumentParser(description="B200-native x-vector extraction from Kaldi features.",
                                      formatter_class=argparse.ArgumentDefaultsHelpFormatter, conflict_handler="resolve")
     for flag, dest, typ, default, required, text in _FLAGS:
-        extra = dict(choices=["yes", "no"]) if dest == "use_gpu" else {}
+        extra = dict(choices=["yes", "no"]) if dest in ("use_gpu", "apply_cmvn_sliding") else {}
         parser.add_argument(flag, dest=dest, type=typ, default=default, required=required, help=text, **extra)
     return process_args(parser.parse_args(argv))
 
@@ -127,13 +137,60 @@ def eval_dnn(args):
     rank, _ = sharding.dist_info()
     want_gpu = args.use_gpu == "yes"
     extractor = Model()
-    with kaldi_io.open_or_fd(args.feature_rspecifier) as features:
-        if rank != 0:                                   # other ranks compute their share; only rank 0 owns the output
-            extractor.make_embedding(features, None, args.model_dir, args.min_chunk_size, args.chunk_size, want_gpu, logger)
-            return
-        with kaldi_io.open_vector_writer(wspecifier) as vectors:
-            extractor.make_embedding(features, vectors, args.model_dir, args.min_chunk_size, args.chunk_size, want_gpu, logger)
+    frontend = _frontend_arguments(args)
+    with _open_features(args.feature_rspecifier) as features:
+        try:
+            if rank != 0:                               # other ranks compute their share; only rank 0 owns the output
+                extractor.make_embedding(features, None, args.model_dir, args.min_chunk_size, args.chunk_size, want_gpu,
+                                         logger, **frontend)
+                return
+            with kaldi_io.open_vector_writer(wspecifier) as vectors:
+                extractor.make_embedding(features, vectors, args.model_dir, args.min_chunk_size, args.chunk_size, want_gpu,
+                                         logger, **frontend)
+        finally:
+            if frontend.get("vad_table") is not None:
+                frontend["vad_table"].close()
     _publish_outputs(ark, scp)
+
+
+def _kaldi_bool(text):
+    return str(text).strip().lower() in ("true", "yes", "1", "t")
+
+
+def _frontend_arguments(args):
+    """Keyword arguments of make_embedding that put apply-cmvn-sliding / select-voiced-frames on the device."""
+    want_cmvn = getattr(args, "apply_cmvn_sliding", "no") == "yes"
+    vad_rspecifier = getattr(args, "vad_rspecifier", None)
+    if not want_cmvn and not vad_rspecifier:
+        return {}
+    if vad_rspecifier and not want_cmvn:
+        raise Exception("--vad-rspecifier needs --apply-cmvn-sliding=yes: the recipe selects voiced frames AFTER the sliding "
+                        "CMVN (local/tf/extract_xvectors.sh:68), and both run in one pass on the device")
+    from ._native import XvCmvnOpts
+    out = dict(cmvn_opts=XvCmvnOpts(args.cmn_window, args.min_cmn_window, _kaldi_bool(args.center), _kaldi_bool(args.norm_vars)))
+    if vad_rspecifier:
+        out["vad_table"] = kaldi_io.VecTable(vad_rspecifier)
+    return out
+
+
+class _open_features(object):
+    """``scp:`` rspecifiers are walked entry by entry (raw feats.scp, no Kaldi pipe in front); anything else is opened
+    as the archive stream the reference passes to make_embedding (extract_embedding.py:121-125)."""
+
+    def __init__(self, rspecifier):
+        self.rspecifier = rspecifier
+        self.obj = None
+
+    def __enter__(self):
+        if self.rspecifier.startswith("scp") and ":" in self.rspecifier.split()[0] and not self.rspecifier.rstrip().endswith("|"):
+            self.obj = kaldi_io.read_mat_scp_entries(self.rspecifier)
+        else:
+            self.obj = kaldi_io.open_or_fd(self.rspecifier)
+        return self.obj
+
+    def __exit__(self, *exc):
+        self.obj.close()
+        return False
 
 
 def main(argv=None):

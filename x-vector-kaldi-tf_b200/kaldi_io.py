@@ -405,6 +405,113 @@ def read_mat_ark_entries(file_or_fd):
             fd.close()
 
 
+def _entry_at(fd, key):
+    """MatArkEntry for the matrix whose '\0B' flag starts at the current position of ``fd``."""
+    flag = _read_exact(fd, 2).decode()
+    if flag == "\0B":
+        header = _read_exact(fd, 3).decode()
+        if header in ("FM ", "DM "):
+            _, rows, _, cols = struct.unpack("<bibi", _read_exact(fd, 10))
+            return MatArkEntry(key, rows, cols, fd, header[:2])
+        if header.startswith("CM"):
+            m = _read_compressed_mat(fd, header)
+            return MatArkEntry(key, m.shape[0], m.shape[1], fd, "decoded", m)
+        raise UnknownMatrixHeader("The header contained '%s'" % header)
+    assert flag == " ["
+    m = _read_mat_ascii(fd)
+    return MatArkEntry(key, m.shape[0], m.shape[1] if m.ndim == 2 else 0, fd, "decoded", m)
+
+
+class _RxFileCache(object):
+    """Keeps the most recently used ark of an scp open: consecutive scp lines nearly always point into one file."""
+
+    def __init__(self):
+        self.path, self.fd = None, None
+
+    def seek(self, rxfile):
+        rxfile = rxfile.strip()
+        if _OFFSET_RE.search(rxfile) and not rxfile.endswith("|"):
+            path, offset = rxfile.rsplit(":", 1)
+            if path != self.path:
+                self.close()
+                self.path, self.fd = path, open_or_fd(path)
+            self.fd.seek(int(offset))
+            return self.fd
+        self.close()
+        self.path, self.fd = rxfile, open_or_fd(rxfile)
+        return self.fd
+
+    def close(self):
+        if self.fd is not None:
+            self.fd.close()
+        self.path, self.fd = None, None
+
+
+def read_mat_scp_entries(file_or_fd):
+    """read_mat_ark_entries over an scp table (``key rxfilename[:offset]`` lines, reference kaldi_io.py:350-369): what
+    ``scp:data/feats.scp`` means as a feature rspecifier when the feature front end runs on the device."""
+    fd = open_or_fd(file_or_fd)
+    cache = _RxFileCache()
+    try:
+        for line in fd:
+            line = line.decode() if isinstance(line, bytes) else line
+            if not line.strip():
+                continue
+            key, rxfile = line.rstrip("\n").split(" ", 1)
+            entry = _entry_at(cache.seek(rxfile), key)
+            yield entry
+            entry.skip()
+    finally:
+        cache.close()
+        if fd is not file_or_fd:
+            fd.close()
+
+
+class VecTable(object):
+    """Float vectors by key: the ``scp,s,cs:vad.scp`` table select-voiced-frames opens
+    (reference local/tf/extract_xvectors.sh:68).  An scp is loaded as a key -> rxfilename map and read on demand; an
+    ark is walked once, front to back, assuming the caller asks in the archive's order (Kaldi's ``s,cs``)."""
+
+    def __init__(self, rspecifier):
+        self._cache = _RxFileCache()
+        self._table = None
+        self._iter = None
+        self._pending = None
+        spec = _SPECIFIER_RE.search(rspecifier) if isinstance(rspecifier, str) else None
+        if spec is not None and spec.group(0).startswith("scp"):
+            self._table = {}
+            with open_or_fd(rspecifier) as fd:
+                for line in fd:
+                    line = line.decode() if isinstance(line, bytes) else line
+                    if line.strip():
+                        key, rxfile = line.rstrip("\n").split(" ", 1)
+                        self._table[key] = rxfile
+        else:
+            self._iter = read_vec_flt_ark(rspecifier)
+
+    def get(self, key):
+        """The vector stored under ``key`` or None."""
+        if self._table is not None:
+            rxfile = self._table.get(key)
+            return None if rxfile is None else read_vec_flt(self._cache.seek(rxfile))
+        while True:
+            if self._pending is None:
+                self._pending = next(self._iter, None)
+                if self._pending is None:
+                    return None
+            if self._pending[0] == key:
+                vec, self._pending = self._pending[1], None
+                return vec
+            if self._pending[0] > key:               # sorted tables: the key is not there
+                return None
+            self._pending = None
+
+    def close(self):
+        self._cache.close()
+        if self._iter is not None:
+            self._iter.close()
+
+
 def read_mat_scp(file_or_fd):
     """Generator of (key, matrix) following an scp file."""
     fd = open_or_fd(file_or_fd)

@@ -78,13 +78,15 @@ def chunk_plan(num_rows, min_chunk_size, chunk_size):
 
 
 class _Batch(object):
-    __slots__ = ("slot", "n_frames", "seg_lens", "utts")
+    __slots__ = ("slot", "n_frames", "seg_lens", "utts", "raw_lens", "keeps")
 
     def __init__(self, slot):
         self.slot = slot
-        self.n_frames = 0
+        self.n_frames = 0       # rows in the staging buffer (raw rows when the feature front end runs on the device)
         self.seg_lens = []
         self.utts = []          # (global_index, key, first_segment, [lengths])
+        self.raw_lens = []      # device front end only: raw rows / selected rows the network sees, per utterance
+        self.keeps = []
 
 
 # noinspection PyAttributeOutsideInit
@@ -445,8 +447,18 @@ class Model(object):
             self._engine = _create_engine(self.meta, self.params, device)
         return self._engine
 
-    def make_embedding(self, input_stream, output_stream, model_dir, min_chunk_size, chunk_size, use_gpu, logger):
+    def make_embedding(self, input_stream, output_stream, model_dir, min_chunk_size, chunk_size, use_gpu, logger,
+                       vad_table=None, cmvn_opts=None):
+        """The reference's signature (models.py:356) plus two optional arguments that move the Kaldi pipe of
+        local/tf/extract_xvectors.sh:68 onto the device: ``cmvn_opts`` (an ``_native.XvCmvnOpts``: apply-cmvn-sliding)
+        and ``vad_table`` (a ``kaldi_io.VecTable`` of VAD decisions: select-voiced-frames).  With either one,
+        ``input_stream`` carries RAW features and the skip / chunk rules apply to the voiced frames, as they do in the
+        reference where the pipe runs first.  ``input_stream`` may also be an iterator of ``kaldi_io.MatArkEntry``."""
         start_time = time.time()
+        device_frontend = vad_table is not None or cmvn_opts is not None
+        if device_frontend and cmvn_opts is None:
+            from ._native import XvCmvnOpts
+            cmvn_opts = XvCmvnOpts()
         device = set_cuda_visible_devices(use_gpu=use_gpu, logger=logger)
         self.load_model(None, model_dir, logger)
         engine = self._get_engine(device)
@@ -456,7 +468,7 @@ class Model(object):
         rank, world = sharding.dist_info()
 
         # page-locked staging buffers: the reader thread fills one while two batches are in flight on the GPU
-        staging = _Staging(feat_dim, batch_frames)
+        staging = _Staging(feat_dim, batch_frames, with_vad=vad_table is not None)
         counters = dict(total_segments=0, total_segments_len=0, num_fail=0, num_success=0)
         work = queue.Queue(maxsize=_Staging.SLOTS)
         failure = []
@@ -464,7 +476,7 @@ class Model(object):
         def reader():
             try:
                 self._read_batches(input_stream, staging, work, counters, min_chunk_size, chunk_size,
-                                   batch_frames, rank, world, logger)
+                                   batch_frames, rank, world, logger, device_frontend, vad_table)
             except BaseException as e:      # surfaced on the main thread
                 failure.append(e)
             finally:
@@ -483,7 +495,12 @@ class Model(object):
                 feats = staging.view(batch.slot, batch.n_frames)
                 emb_buf = staging.emb_view(batch.slot, len(batch.seg_lens), emb_dim)
                 gpu_waiting = time.time()
-                ticket = engine.submit_host(feats, np.asarray(batch.seg_lens, dtype=np.int32), emb_buf)
+                if device_frontend:
+                    vad = staging.vad_view(batch.slot, batch.n_frames) if vad_table is not None else None
+                    ticket = engine.submit_host_raw(feats, vad, batch.raw_lens, batch.keeps if vad is not None else None,
+                                                    batch.seg_lens, emb_buf, cmvn_opts)
+                else:
+                    ticket = engine.submit_host(feats, np.asarray(batch.seg_lens, dtype=np.int32), emb_buf)
                 total_gpu_waiting += time.time() - gpu_waiting
                 submitted = (ticket, batch, emb_buf)
             if pending is not None:          # batch k-1 finishes while batch k copies in / computes
@@ -525,18 +542,42 @@ class Model(object):
                         ((time.time() - start_time) / 60.0))
 
     def _read_batches(self, input_stream, staging, work, counters, min_chunk_size, chunk_size, batch_frames,
-                      rank, world, logger):
+                      rank, world, logger, device_frontend=False, vad_table=None):
         """Reader thread: parse the ark, apply the reference's skip/chunk rules, copy the rows of
-        this rank's utterances into a pinned buffer and hand full batches to the GPU loop."""
+        this rank's utterances into a pinned buffer and hand full batches to the GPU loop.
+
+        With ``device_frontend`` the stream holds raw features: ``raw_rows`` of them are staged (plus the VAD track),
+        while ``num_rows`` -- what the reference's loop sees after select-voiced-frames -- is the voiced count."""
         keys_in_order = []
         counters["keys_in_order"] = keys_in_order
         batch = None
         ok_index = 0
-        for entry in kaldi_io.read_mat_ark_entries(input_stream):
+        is_stream = isinstance(input_stream, str) or hasattr(input_stream, "read")
+        entries = kaldi_io.read_mat_ark_entries(input_stream) if is_stream else input_stream   # else: MatArkEntry iterator
+        for entry in entries:
             key, num_rows = entry.key, entry.rows
+            raw_rows, vad = entry.rows, None
             if logger is not None:
                 logger.debug("Processing features with key '%s' which have shape '%s'" % (key, str((entry.rows, entry.cols))))
             counters["total_segments"] += 1
+            if vad_table is not None:
+                # select-voiced-frames: no VAD / length mismatch / no voiced frame -> the utterance never reaches the network
+                vad = vad_table.get(key)
+                problem = None
+                if vad is None:
+                    problem = "No VAD decisions for utterance '%s'" % key
+                elif vad.shape[0] != raw_rows:
+                    problem = "Mismatch in number of frames for features and VAD of utterance '%s': %d vs %d" % (
+                        key, raw_rows, vad.shape[0])
+                else:
+                    num_rows = int(np.count_nonzero(vad))
+                    if num_rows == 0 and raw_rows > 0:
+                        problem = "No features were judged as voiced for utterance '%s'" % key
+                if problem is not None:
+                    if logger is not None:
+                        logger.warning(problem)
+                    counters["num_fail"] += 1
+                    continue
             if num_rows == 0:
                 if logger is not None:
                     logger.warning("Zero-length utterance: '%s'" % key)
@@ -560,18 +601,25 @@ class Model(object):
                     continue                                 # another rank's utterance: payload skipped unread
             if entry.cols != staging.feat_dim:
                 raise ValueError("utterance %s has feature dim %d, model expects %d" % (key, entry.cols, staging.feat_dim))
-            if batch is not None and batch.n_frames + num_rows > max(batch_frames, num_rows):
+            if batch is not None and batch.n_frames + raw_rows > max(batch_frames, raw_rows):
                 work.put(batch)
                 batch = None
             if batch is None:
-                batch = _Batch(staging.acquire(max(batch_frames, num_rows)))
+                batch = _Batch(staging.acquire(max(batch_frames, raw_rows)))
             # the payload goes straight from the stream into the page-locked buffer (no intermediate copy); rows of a
             # dropped tail are overwritten by the next utterance
-            entry.read_into(staging.view(batch.slot, batch.n_frames + num_rows)[batch.n_frames:])
+            entry.read_into(staging.view(batch.slot, batch.n_frames + raw_rows)[batch.n_frames:])
             first_seg = len(batch.seg_lens)
             for _, length in plan:
                 batch.seg_lens.append(length)
-            batch.n_frames += used
+            if device_frontend:                              # every raw row stays: the CMVN windows need them
+                if vad is not None:
+                    staging.vad_view(batch.slot, batch.n_frames + raw_rows)[batch.n_frames:] = vad
+                batch.raw_lens.append(raw_rows)
+                batch.keeps.append(used)                     # the front end drops a short tail chunk itself
+                batch.n_frames += raw_rows
+            else:
+                batch.n_frames += used
             batch.utts.append((this_index, key, first_seg, [n for _, n in plan]))
         if batch is not None and batch.utts:
             work.put(batch)
@@ -613,8 +661,10 @@ class _Staging(object):
     between the reader thread and the GPU loop: one being filled, two in flight."""
     SLOTS = 3
 
-    def __init__(self, feat_dim, cap_frames):
+    def __init__(self, feat_dim, cap_frames, with_vad=False):
         self.feat_dim = feat_dim
+        self.with_vad = with_vad
+        self.vads = [None] * self.SLOTS      # [cap] float32 VAD track next to the raw rows (device front end)
         self.free = queue.Queue()
         self.bufs = [None] * self.SLOTS
         self.caps = [0] * self.SLOTS
@@ -640,8 +690,13 @@ class _Staging(object):
         if self.caps[slot] < need_frames:
             cap = max(need_frames, self._cap0)
             self.bufs[slot] = self._alloc(cap, self.feat_dim)
+            if self.with_vad:
+                self.vads[slot] = self._alloc(cap, 1).reshape(-1)
             self.caps[slot] = cap
         return slot
+
+    def vad_view(self, slot, n_frames):
+        return self.vads[slot][:n_frames]
 
     def view(self, slot, n_frames):
         return self.bufs[slot][:n_frames]
