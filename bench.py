@@ -379,6 +379,8 @@ def run_b200(args):
                     peak_sustained=peaks["tflops_sustained"],
                     launches=launches)
 
+    frontend = measure_frontend(args, eng, dev, stream, flush, rank, peaks)
+
     out = dict(metric=METRIC, value=round(value, 1), unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                ms_per_step=round(ms_per_step, 5), higher_is_better=True, scaling="weak", vs_baseline=None,
                dtype="f16", data="synthetic",
@@ -393,7 +395,7 @@ def run_b200(args):
                         d2h_bytes_per_step=B * EMB_DIM * 4 + 4, ms_per_step=round(e2e_total / args.steps, 5),
                         api="xv_submit_host / xv_collect, 2 in flight (pinned host buffers; xv_extract_host is the blocking form)"),
                gpu_launches=int(launches_per_step * args.steps),
-               clocks=clocks, roofline=roofline, ragged=ragged)
+               clocks=clocks, roofline=roofline, ragged=ragged, frontend=frontend)
     if remeasured:
         out["clocks"]["note"] = "first measurement rejected (throttle reason / low clocks); this is the re-measurement"
 
@@ -407,6 +409,79 @@ def run_b200(args):
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(out), flush=True)
+
+
+def measure_frontend(args, eng, dev, stream, flush, rank, peaks):
+    """The Kaldi pipe of local/tf/extract_xvectors.sh:68 on the device (include/xvec_frontend.h): sliding-window CMVN
+    (window 300, centred) + voiced-frame selection over configs[1]'s geometry taken as RAW frames with a synthetic VAD
+    track; kernel time by CUDA events on the launching stream (L2 flushed between iterations), judged against HBM with
+    the algorithmic bytes (raw rows + VAD in, voiced rows out), and the raw host path (xv_submit_host_raw) end to end."""
+    import torch
+    from oracle import kaldi_frontend_oracle as feo
+    from xvector_b200 import _native, synthetic
+    B, T = args.batch, args.frames
+    lens = np.full(B, T, np.int32)
+    raw = synthetic.mfcc_batch(7 + 1000 * rank, lens) + np.float32(-30.0) * (np.arange(FEAT_DIM) == 0).astype(np.float32)
+    rng = np.random.default_rng(7 + rank)
+    tracks = [feo.synthetic_vad(rng, T) for _ in range(B)]
+    for v in tracks:
+        if v.sum() < 25:                      # every utterance passes the extractor's min-chunk-size rule
+            v[:min(T, 100)] = 1.0
+    vad = np.concatenate(tracks)
+    keep = vad.reshape(B, T).astype(bool).sum(axis=1).astype(np.int32)
+    raw_host = torch.from_numpy(raw).pin_memory()
+    vad_host = torch.from_numpy(vad).pin_memory()
+    raw_dev, vad_dev = raw_host.to(dev), vad_host.to(dev)
+    out_dev = torch.empty((int(keep.sum()), FEAT_DIM), dtype=torch.float32, device=dev)
+    opts = _native.XvCmvnOpts()
+    for _ in range(3):
+        eng.frontend(raw_dev, vad_dev, lens, keep, opts, out_dev=out_dev, stream=stream)
+    evs = []
+    n_it = min(args.steps, 50)
+    for _ in range(n_it):
+        flush.zero_()
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_.record(stream); eng.frontend(raw_dev, vad_dev, lens, keep, opts, out_dev=out_dev, stream=stream); e_.record(stream)
+        evs.append((s_, e_))
+    torch.cuda.synchronize(dev)
+    ms = float(np.mean([s_.elapsed_time(e_) for s_, e_ in evs]))
+    alg_bytes = int(B * T * (FEAT_DIM * 4 + 4) + int(keep.sum()) * FEAT_DIM * 4)
+    gbs = alg_bytes / (ms * 1e-3) / 1e9
+    # raw host path: pinned raw rows + VAD in, embeddings out, two submissions in flight
+    emb = [torch.empty((B, EMB_DIM), dtype=torch.float32).pin_memory() for _ in range(2)]
+    def run(n):
+        pending = None
+        for i in range(n):
+            t = eng.submit_host_raw(raw_host, vad_host, lens, keep, keep, emb[i % 2], opts)
+            if pending is not None:
+                eng.collect(pending)
+            pending = t
+        eng.collect(pending)
+    run(3)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    run(n_it)
+    torch.cuda.synchronize(dev)
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / n_it
+    # the oracle (Kaldi's recursion restated in numpy, one core) on a bounded sample, for scale
+    n_cpu = min(B, 32)
+    t0 = time.perf_counter()
+    for i in range(n_cpu):
+        feo.frontend(raw[i * T:(i + 1) * T], vad[i * T:(i + 1) * T])
+    cpu_s = time.perf_counter() - t0
+    return dict(workload="apply-cmvn-sliding(300, centred) | select-voiced-frames on %d x %d RAW frames, %.0f %% voiced"
+                         % (B, T, 100.0 * float(keep.sum()) / (B * T)),
+                kernels="vad_tile_count_kernel + cmvn_select_kernel", ms_per_call=round(ms, 5),
+                raw_frames_per_sec=round(B * T / (ms * 1e-3), 1),
+                roofline=dict(bound="hbm", achieved=round(gbs, 1), peak=peaks["hbm_gbs"], unit="GB/s",
+                              frac=round(gbs / peaks["hbm_gbs"], 4), algorithmic_bytes_per_call=alg_bytes),
+                e2e=dict(api="xv_submit_host_raw / xv_collect, 2 in flight (raw rows + VAD track from pinned host memory, "
+                             "front end + network on the device, embeddings back)",
+                         ms_per_step=round(e2e_ms, 5), raw_frames_per_sec=round(B * T / (e2e_ms * 1e-3), 1),
+                         voiced_frames_per_sec=round(float(keep.sum()) / (e2e_ms * 1e-3), 1),
+                         h2d_bytes_per_step=int(B * T * (FEAT_DIM * 4 + 4) + B * 4 * 3), d2h_bytes_per_step=B * EMB_DIM * 4 + 4),
+                cpu_baseline=dict(value=round(n_cpu * T / cpu_s, 1), unit="raw frames/s", cores=1, kind="port",
+                                  sample="%d utterances of %d frames through oracle/kaldi_frontend_oracle.py" % (n_cpu, T)))
 
 
 def measure_train_step(args, dev, rank, world, peaks, topo):

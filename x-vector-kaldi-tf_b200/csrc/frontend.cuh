@@ -3,14 +3,16 @@
 //   apply-cmvn-sliding --norm-vars=false --center=true --cmn-window=300 | select-voiced-frames
 //                                                                  (reference local/tf/extract_xvectors.sh:68)
 //
-//   vad_tile_count_kernel : voiced rows of every 128-row tile of every utterance.
+//   vad_tile_count_kernel : voiced rows of every 128-row tile of every utterance (launched only when an utterance is
+//                           longer than 4096 frames; shorter ones count the rows in front of a tile in place).
 //   cmvn_select_kernel    : one CTA per tile.  The rows every window of the tile touches (<= 128 + cmn_window of them,
 //                           ONE contiguous span of the caller's matrix) are staged in shared memory with coalesced
-//                           16-byte loads; thread (cepstral bin, run of 16 frames) sums its first window in double and
-//                           then slides it (subtract the row that left, add the row that entered), which is the
-//                           recursion of Kaldi's SlidingWindowCmnInternal restarted every 16 frames; the normalised row
-//                           goes straight to its compacted position  out_row0 + (voiced rows before it)  -- each row is
-//                           23 consecutive floats written by 23 consecutive lanes.
+//                           16-byte loads and summed once per (cepstral bin, 16-row segment) in double; thread (bin,
+//                           run of 16 frames) builds its first window from those partial sums and then slides it
+//                           (subtract the row that left, add the row that entered), which is the recursion of Kaldi's
+//                           SlidingWindowCmnInternal restarted every 16 frames; the normalised row goes straight to its
+//                           compacted position  out_row0 + (voiced rows before it)  -- each row is 23 consecutive
+//                           floats written by 23 consecutive lanes.
 //
 // Algorithmic traffic per raw frame: 4*D (read) + 4 (VAD) + 4*D*voiced_fraction (write) bytes; the window re-reads
 // (x(1 + W/128)) are served by L1/L2.
@@ -22,6 +24,8 @@ namespace xvfe {
 
 constexpr int TILE = 128;        // frames per CTA
 constexpr int RUN = 16;          // consecutive frames per thread
+constexpr int SEG = 16;          // slab rows per partial sum
+constexpr int DIRECT_COUNT_MAX = 4096;      // utterances up to this long: voiced rows in front of a tile counted in place
 constexpr int THREADS = 256;
 constexpr int COUNT_THREADS = 128;
 constexpr uint32_t ERR_VAD_MISMATCH = 2u;   // bit of the model's sticky device flag (bit 0 = fp16 overflow)
@@ -32,6 +36,7 @@ struct UttMeta {
   const int32_t* out_row0;  // [n_utt] first output row
   const int32_t* keep;      // [n_utt] selected rows to write
   const int32_t* tile0;     // [n_utt + 1] first tile of the utterance; tile0[n_utt] = number of tiles
+  const int32_t* tile_utt;  // [n_tiles] utterance of every tile
   int32_t n_utt;
 };
 
@@ -60,38 +65,58 @@ __host__ __device__ __forceinline__ void window_bounds(int t, int T, const CmvnO
   }
 }
 
-// utterance of a tile: last u with tile0[u] <= tile (utterances without rows own no tile and are skipped)
-__device__ __forceinline__ int find_utt(const int32_t* __restrict__ tile0, int n_utt, int tile) {
-  int lo = 0, hi = n_utt;          // invariant: tile0[lo] <= tile < tile0[hi]
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (__ldg(tile0 + mid) <= tile) lo = mid; else hi = mid;
+// The same placement without branches (what the kernel's inner loops use):
+//   centred : ws = clamp(t - W/2, 0, max(T - W, 0)),  we = min(T, ws + W)
+//   trailing: we' = max(t + 1, min_window), ws' = max(t - W, 0); if we' > T the window is shifted left by we' - T
+__device__ __forceinline__ void window_bounds_fast(int t, int T, const CmvnOpts& o, int& ws, int& we) {
+  if (o.center) {
+    ws = max(0, min(t - (o.cmn_window >> 1), T - o.cmn_window));
+    we = min(T, ws + o.cmn_window);
+  } else {
+    const int e = max(t + 1, o.min_window);
+    ws = max(0, max(t - o.cmn_window, 0) - max(e - T, 0));
+    we = min(e, T);
   }
-  return lo;
 }
 
 __global__ void __launch_bounds__(COUNT_THREADS)
 vad_tile_count_kernel(UttMeta um, const float* __restrict__ vad, int32_t* __restrict__ tile_cnt) {
   cudaGridDependencySynchronize();
   const int tile = blockIdx.x;
-  const int u = find_utt(um.tile0, um.n_utt, tile);
+  const int u = __ldg(um.tile_utt + tile);
   const int t = (tile - __ldg(um.tile0 + u)) * TILE + threadIdx.x;
   const bool voiced = t < __ldg(um.len + u) && __ldg(vad + size_t(__ldg(um.in_row0 + u)) + t) != 0.f;
   const int n = __syncthreads_count(voiced);
   if (threadIdx.x == 0) tile_cnt[tile] = n;
 }
 
+// Dynamic shared memory of cmvn_select_kernel: the slab, then (8-byte aligned) the per-16-row partial sums.
+__host__ __device__ inline size_t slab_floats(int cmn_window, int D) { return (size_t(TILE + cmn_window) * D + 4 + 1) & ~size_t(1); }
+__host__ __device__ inline int max_segs(int cmn_window) { return (TILE + cmn_window) / SEG + 2; }
+inline size_t cmvn_smem_bytes(int cmn_window, int D, bool norm_vars) {
+  return slab_floats(cmn_window, D) * sizeof(float) + size_t(max_segs(cmn_window)) * D * sizeof(double) * (norm_vars ? 2 : 1);
+}
+
+// tile_cnt == nullptr: the voiced rows in front of the tile are counted here from the VAD track (the host launches
+// vad_tile_count_kernel only when some utterance is longer than DIRECT_COUNT_MAX frames).
+template <bool NV>                                  // NV: also normalise the variance (sums of squares carried along)
 __global__ void __launch_bounds__(THREADS)
 cmvn_select_kernel(UttMeta um, CmvnOpts opts, int32_t D, const float* __restrict__ feats, const float* __restrict__ vad,
                    const int32_t* __restrict__ tile_cnt, float* __restrict__ out, uint32_t* __restrict__ err_flag) {
   extern __shared__ __align__(16) float slab[];    // [(we_last - ws_first) * D] (+ up to 3 floats of alignment slack)
   __shared__ int32_t s_pos[TILE];                   // output row inside the utterance, or -1 (unvoiced / beyond keep)
+  __shared__ int4 s_row[TILE];                      // per frame of the tile: {window start, window end (slab rows), pos, -}
+  __shared__ double s_scale[TILE];                  // -1 / window frames
   __shared__ int32_t s_warp_cnt[TILE / 32];
   __shared__ int32_t s_before;
+  double* seg_sum = reinterpret_cast<double*>(slab + slab_floats(opts.cmn_window, D));   // [n_segs][D]
+  double* seg_sq = seg_sum + max_segs(opts.cmn_window) * D;                               // [n_segs][D] (variance only)
 
   const int tid = threadIdx.x;
   const int tile = blockIdx.x;
-  const int u = find_utt(um.tile0, um.n_utt, tile);
+  if (tid == 0) s_before = 0;
+  cudaGridDependencySynchronize();
+  const int u = __ldg(um.tile_utt + tile);
   const int tile_first = __ldg(um.tile0 + u);
   const int T = __ldg(um.len + u);
   const int keep = __ldg(um.keep + u);
@@ -100,10 +125,8 @@ cmvn_select_kernel(UttMeta um, CmvnOpts opts, int32_t D, const float* __restrict
   const int t0 = (tile - tile_first) * TILE;
   const int nr = min(TILE, T - t0);
   int ws_first, we_first, ws_last, we_last;
-  window_bounds(t0, T, opts, ws_first, we_first);
-  window_bounds(t0 + nr - 1, T, opts, ws_last, we_last);
-  if (tid == 0) s_before = 0;
-  cudaGridDependencySynchronize();
+  window_bounds_fast(t0, T, opts, ws_first, we_first);
+  window_bounds_fast(t0 + nr - 1, T, opts, ws_last, we_last);
 
   // ---- stage rows [ws_first, we_last) of the utterance: one contiguous span of floats, 16-byte loads in the middle
   const int64_t e_begin = (in_row0 + ws_first) * D, e_end = (in_row0 + we_last) * D;
@@ -122,20 +145,55 @@ cmvn_select_kernel(UttMeta um, CmvnOpts opts, int32_t D, const float* __restrict
     }
   }
 
-  __syncthreads();                                 // s_before is initialised (and the slab is complete)
-
   // ---- where every row of the tile goes: voiced rows before it in the utterance
+  bool voiced = false;
+  int before_part = 0;
   if (tid < TILE) {
-    const bool voiced = tid < nr && (vad == nullptr || __ldg(vad + in_row0 + t0 + tid) != 0.f);
+    voiced = tid < nr && (vad == nullptr || __ldg(vad + in_row0 + t0 + tid) != 0.f);
+  } else if (vad != nullptr) {
+    if (tile_cnt != nullptr) {
+      for (int j = tile_first + (tid - TILE); j < tile; j += THREADS - TILE) before_part += __ldg(tile_cnt + j);
+    } else {
+      const float* v = vad + in_row0;
+      for (int j = tid - TILE; j < t0; j += THREADS - TILE) before_part += __ldg(v + j) != 0.f ? 1 : 0;
+    }
+  }
+  __syncthreads();                                 // s_before is initialised and the slab is complete
+  if (tid < TILE) {
     const unsigned ballot = __ballot_sync(0xffffffffu, voiced);
     if ((tid & 31) == 0) s_warp_cnt[tid >> 5] = __popc(ballot);
     s_pos[tid] = voiced ? __popc(ballot & ((1u << (tid & 31)) - 1u)) : -1;
   } else if (vad != nullptr) {
-    int part = 0;
-    for (int j = tile_first + (tid - TILE); j < tile; j += THREADS - TILE) part += __ldg(tile_cnt + j);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if ((tid & 31) == 0 && part != 0) atomicAdd(&s_before, part);
+    for (int o = 16; o > 0; o >>= 1) before_part += __shfl_xor_sync(0xffffffffu, before_part, o);
+    if ((tid & 31) == 0 && before_part != 0) atomicAdd(&s_before, before_part);
+  }
+
+  // ---- partial sums of every 16 slab rows, per cepstral bin (thread = (bin, 16-row segment))
+  const float* x = slab + shift;                   // x[(t - ws_first) * D + d]
+  const int slab_rows = we_last - ws_first;
+  const int n_segs = (slab_rows + SEG - 1) / SEG;
+  for (int item = tid; item < n_segs * D; item += THREADS) {
+    const int sgm = item / D, d = item - sgm * D;
+    const int cnt = min(slab_rows - sgm * SEG, SEG);
+    const float* p = x + sgm * SEG * D + d;
+    double a0 = 0.0, a1 = 0.0, q0 = 0.0, q1 = 0.0;
+    if (cnt == SEG) {
+#pragma unroll
+      for (int i = 0; i < SEG; i += 2, p += 2 * D) {
+        const double v0 = double(p[0]), v1 = double(p[D]);
+        a0 += v0; a1 += v1;
+        if (NV) { q0 += v0 * v0; q1 += v1 * v1; }
+      }
+    } else {
+      for (int i = 0; i < cnt; ++i, p += D) {
+        const double v0 = double(p[0]);
+        a0 += v0;
+        if (NV) q0 += v0 * v0;
+      }
+    }
+    seg_sum[item] = a0 + a1;                        // seg_sum[sgm * D + d]
+    if (NV) seg_sq[item] = q0 + q1;
   }
   __syncthreads();
   if (tid < TILE) {
@@ -144,6 +202,12 @@ cmvn_select_kernel(UttMeta um, CmvnOpts opts, int32_t D, const float* __restrict
     const int p = s_pos[tid];
     const int pos = p < 0 ? -1 : before + p;
     s_pos[tid] = pos < keep ? pos : -1;
+    if (tid < nr) {                      // the frame's window, once per tile instead of once per cepstral bin
+      int ws, we;
+      window_bounds_fast(t0 + tid, T, opts, ws, we);
+      s_row[tid] = make_int4(ws - ws_first, we - ws_first, pos < keep ? pos : -1, 0);
+      s_scale[tid] = -1.0 / double(we - ws);
+    }
     if (tid == 0 && t0 + nr == T) {      // last tile of the utterance: did it hold as many voiced rows as the caller said?
       int total = before;
       for (int w = 0; w < TILE / 32; ++w) total += s_warp_cnt[w];
@@ -152,61 +216,87 @@ cmvn_select_kernel(UttMeta um, CmvnOpts opts, int32_t D, const float* __restrict
   }
   __syncthreads();
 
-  // ---- sliding sums: thread = (cepstral bin d, run of RUN frames)
-  const float* x = slab + shift;                   // x[(t - ws_first) * D + d]
+  // ---- sliding sums: thread = (cepstral bin d, run of RUN frames).  The first window of a run is put together from
+  // whole-segment partial sums plus the rows at its two ragged ends; after that the recursion of Kaldi's
+  // SlidingWindowCmnInternal (subtract the row that left, add the row that entered).  Sums of floats are exact in
+  // double (until their exponents are > 2^20 apart), so the association order does not show in the result.
   const int n_runs = (nr + RUN - 1) / RUN;
   for (int item = tid; item < n_runs * D; item += THREADS) {
-    const int d = item % D, r0 = (item / D) * RUN;
+    const int run = item / D, d = item - run * D;
+    const int r0 = run * RUN;
     const int r1 = min(nr, r0 + RUN);
-    int ws, we;
-    window_bounds(t0 + r0, T, opts, ws, we);
+    const float* xd = x + d;                                    // column d of the slab
+    int4 row = s_row[r0];                                       // slab rows [row.x, row.y) are frame r0's window
     double sum = 0.0, sumsq = 0.0;
     {
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      const float* p = x + (ws - ws_first) * D + d;
-      int i = ws;
-      for (; i + 4 <= we; i += 4, p += 4 * D) {
-        a0 += double(p[0]); a1 += double(p[D]); a2 += double(p[2 * D]); a3 += double(p[3 * D]);
+      const int a = row.x, b = row.y;
+      const int sa = (a + SEG - 1) / SEG, sb = b / SEG;         // whole segments [sa, sb)
+      int head_end = b, tail_begin = b;
+      if (sa < sb) {
+        head_end = sa * SEG;
+        tail_begin = sb * SEG;
+        double c0 = 0.0, c1 = 0.0;
+        const double* ps = seg_sum + sa * D + d;
+        int k = sa;
+        for (; k + 2 <= sb; k += 2, ps += 2 * D) { c0 += ps[0]; c1 += ps[D]; }
+        if (k < sb) c0 += ps[0];
+        sum = c0 + c1;
+        if (NV) {
+          const double* pq = seg_sq + sa * D + d;
+          for (int k2 = sa; k2 < sb; ++k2, pq += D) sumsq += *pq;
+        }
       }
-      for (; i < we; ++i, p += D) a0 += double(*p);
-      sum = (a0 + a1) + (a2 + a3);
-      if (opts.normalize_variance) {
-        const float* q = x + (ws - ws_first) * D + d;
-        for (int j = ws; j < we; ++j, q += D) sumsq += double(*q) * double(*q);
+      const float* ph = xd + a * D;
+      for (int i = a; i < head_end; ++i, ph += D) {
+        const double v = double(*ph);
+        sum += v;
+        if (NV) sumsq += v * v;
+      }
+      const float* pt = xd + tail_begin * D;
+      for (int i = tail_begin; i < b; ++i, pt += D) {
+        const double v = double(*pt);
+        sum += v;
+        if (NV) sumsq += v * v;
       }
     }
-    for (int r = r0; r < r1; ++r) {
-      const int t = t0 + r;
+    const float* p_lo = xd + row.x * D;                         // row leaving next / row entering next / current row
+    const float* p_hi = xd + row.y * D;
+    const float* p_t = xd + (t0 + r0 - ws_first) * D;
+    float* p_out = out + out_row0 * D + d;
+    for (int r = r0; r < r1; ++r, p_t += D) {
       if (r > r0) {
-        int nws, nwe;
-        window_bounds(t, T, opts, nws, nwe);
-        if (nws > ws) {
-          const double v = double(x[(ws - ws_first) * D + d]);
+        const int4 next = s_row[r];
+        if (next.x > row.x) {
+          const double v = double(*p_lo);
+          p_lo += D;
           sum -= v;
-          if (opts.normalize_variance) sumsq -= v * v;
+          if (NV) sumsq -= v * v;
         }
-        if (nwe > we) {
-          const double v = double(x[(we - ws_first) * D + d]);
+        if (next.y > row.y) {
+          const double v = double(*p_hi);
+          p_hi += D;
           sum += v;
-          if (opts.normalize_variance) sumsq += v * v;
+          if (NV) sumsq += v * v;
         }
-        ws = nws;
-        we = nwe;
+        row = next;
       }
-      const int pos = s_pos[r];
-      if (pos < 0) continue;
-      const int n = we - ws;
-      double y = double(x[(t - ws_first) * D + d]) + (-1.0 / double(n)) * sum;
-      if (opts.normalize_variance) {
+      if (row.z < 0) continue;
+      // Kaldi: output_frame.AddVec(-1.0 / window_frames, cur_sum), i.e. a separately rounded product and sum.  No FMA
+      // here on purpose: x - mean lands EXACTLY on a float rounding midpoint surprisingly often (the window sum of
+      // floats is exact in double), and which way such a tie falls is decided by the last bit of the product.
+      double y = __dadd_rn(double(*p_t), __dmul_rn(s_scale[r], sum));
+      if (NV) {
+        const int n = row.y - row.x;
         if (n == 1) {
           y = 0.0;
         } else {
-          double var = sumsq * (1.0 / double(n)) + (-1.0 / (double(n) * double(n))) * sum * sum;
+          double var = __dadd_rn(__dmul_rn(sumsq, 1.0 / double(n)),
+                                 __dmul_rn(-1.0 / (double(n) * double(n)), __dmul_rn(sum, sum)));
           var = fmax(var, 1.0e-10);
-          y *= 1.0 / sqrt(var);
+          y = __dmul_rn(y, 1.0 / sqrt(var));
         }
       }
-      out[(out_row0 + pos) * D + d] = float(y);
+      p_out[size_t(row.z) * D] = float(y);
     }
   }
 }

@@ -20,7 +20,7 @@ inline FrontendPlan fe_plan(int64_t total_rows, int32_t n_utt) {
   FrontendPlan p;
   p.total_rows = total_rows;
   p.off_meta = 0;
-  p.off_tile_cnt = size_t(round_up((int64_t(5) * n_utt + 1) * 4, 1024));
+  p.off_tile_cnt = size_t(round_up((int64_t(5) * n_utt + 1 + fe_tiles_upper_bound(total_rows, n_utt)) * 4, 1024));
   p.bytes = p.off_tile_cnt + size_t(round_up(fe_tiles_upper_bound(total_rows, n_utt) * 4, 1024));
   return p;
 }
@@ -29,7 +29,7 @@ int fe_check_opts(const xv_model* m, const xv_cmvn_opts* o, size_t* smem_bytes) 
   if (!o) return fail(XV_EINVAL, "null cmvn options");
   if (o->cmn_window < 1) return fail(XV_EINVAL, "cmn_window must be >= 1");
   if (o->min_window < 0 || o->min_window > o->cmn_window) return fail(XV_EINVAL, "min_window must be in [0, cmn_window]");
-  const size_t smem = (size_t(xvfe::TILE + o->cmn_window) * m->topo.feat_dim + 4) * sizeof(float);
+  const size_t smem = xvfe::cmvn_smem_bytes(o->cmn_window, m->topo.feat_dim, o->normalize_variance != 0);
   if (smem > size_t(200) * 1024)
     return fail(XV_EINVAL, "cmn_window * feat_dim too large for one CTA's shared memory (" + std::to_string(smem) + " bytes)");
   *smem_bytes = smem;
@@ -61,16 +61,20 @@ int frontend_impl(xv_model* m, const float* feats_dev, const float* vad_dev, con
     return fail(XV_ENOMEM, "frontend workspace too small: need " + std::to_string(p.bytes) + " bytes, got " + std::to_string(workspace_bytes));
   if (reinterpret_cast<uintptr_t>(workspace_dev) % 16 != 0) return fail(XV_EINVAL, "frontend workspace must be 16-byte aligned");
 
-  // ---- utterance table, built in a pinned staging slot: [in_row0 | len | out_row0 | keep | tile0 (n_utt + 1)] ----
-  rc = ensure_meta_capacity(m, int64_t(5) * n_utt + 1);
+  // ---- utterance table, built in a pinned staging slot: [in_row0 | len | out_row0 | keep | tile0 (n_utt + 1) | tile_utt] ----
+  rc = ensure_meta_capacity(m, int64_t(5) * n_utt + 1 + fe_tiles_upper_bound(total_rows, n_utt));
   if (rc != XV_OK) return rc;
   const int slot = m->meta_next;
   m->meta_next = (m->meta_next + 1) % META_SLOTS;
   XV_CUDA(cudaEventSynchronize(m->meta_event[slot]));
   int32_t* mh = m->meta_host[slot];
   int64_t in_row = 0, out_row = 0, tile = 0;
+  int32_t longest = 0;
+  int32_t* tile_utt = mh + 5 * int64_t(n_utt) + 1;
   for (int i = 0; i < n_utt; ++i) {
     const int32_t len = utt_len_host[i];
+    longest = std::max(longest, len);
+    for (int32_t k = 0; k < (len + xvfe::TILE - 1) / xvfe::TILE; ++k) tile_utt[tile + k] = i;
     const int32_t keep = out_keep_host ? out_keep_host[i] : len;
     mh[i] = int32_t(in_row);
     mh[n_utt + i] = len;
@@ -88,22 +92,26 @@ int frontend_impl(xv_model* m, const float* feats_dev, const float* vad_dev, con
   uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
   int32_t* meta_dev = reinterpret_cast<int32_t*>(ws + p.off_meta);
   int32_t* tile_cnt = reinterpret_cast<int32_t*>(ws + p.off_tile_cnt);
-  XV_CUDA(cudaMemcpyAsync(meta_dev, mh, (size_t(5) * n_utt + 1) * 4, cudaMemcpyHostToDevice, stream));
+  XV_CUDA(cudaMemcpyAsync(meta_dev, mh, (size_t(5) * n_utt + 1 + size_t(tile)) * 4, cudaMemcpyHostToDevice, stream));
   XV_CUDA(cudaEventRecord(m->meta_event[slot], stream));
 
-  xvfe::UttMeta um{meta_dev, meta_dev + n_utt, meta_dev + 2 * n_utt, meta_dev + 3 * n_utt, meta_dev + 4 * n_utt, n_utt};
+  xvfe::UttMeta um{meta_dev, meta_dev + n_utt, meta_dev + 2 * n_utt, meta_dev + 3 * n_utt, meta_dev + 4 * n_utt,
+                   meta_dev + 5 * int64_t(n_utt) + 1, n_utt};
+  const bool count_pass = vad_dev != nullptr && longest > xvfe::DIRECT_COUNT_MAX;
   const xvfe::CmvnOpts o{opts->cmn_window, opts->min_window, opts->center != 0, opts->normalize_variance != 0};
   const bool pdl = m->opt_pdl != 0;
-  if (vad_dev) {
+  if (count_pass) {
     XV_CUDA(launch_k(pdl, xvfe::vad_tile_count_kernel, dim3(unsigned(tile)), dim3(xvfe::COUNT_THREADS), 0, stream, um, vad_dev, tile_cnt));
     ++m->last_frontend_launches;
   }
-  if (smem > size_t(48) * 1024 && smem > m->fe_smem_opted) {
-    XV_CUDA(cudaFuncSetAttribute(xvfe::cmvn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    m->fe_smem_opted = smem;
+  auto kernel = o.normalize_variance ? xvfe::cmvn_select_kernel<true> : xvfe::cmvn_select_kernel<false>;
+  size_t& opted = o.normalize_variance ? m->fe_smem_opted_nv : m->fe_smem_opted;
+  if (smem > size_t(48) * 1024 && smem > opted) {
+    XV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    opted = smem;
   }
-  XV_CUDA(launch_k(pdl, xvfe::cmvn_select_kernel, dim3(unsigned(tile)), dim3(xvfe::THREADS), smem, stream, um, o,
-                   int32_t(m->topo.feat_dim), feats_dev, vad_dev, static_cast<const int32_t*>(tile_cnt), out_dev, m->overflow_dev));
+  XV_CUDA(launch_k(pdl, kernel, dim3(unsigned(tile)), dim3(xvfe::THREADS), smem, stream, um, o, int32_t(m->topo.feat_dim),
+                   feats_dev, vad_dev, static_cast<const int32_t*>(count_pass ? tile_cnt : nullptr), out_dev, m->overflow_dev));
   ++m->last_frontend_launches;
   XV_CUDA(cudaGetLastError());
   return XV_OK;

@@ -121,7 +121,7 @@ struct xv_model {
   int slot_next = 0;
   int32_t last_launches = 0;
   int32_t last_frontend_launches = 0;
-  size_t fe_smem_opted = 0;          // dynamic shared memory cmvn_select_kernel has been opted in for
+  size_t fe_smem_opted = 0, fe_smem_opted_nv = 0;   // dynamic shared memory cmvn_select_kernel<NV> has been opted in for
   // options
   int num_clusters = 74;             // co-resident CTA pairs of tdnn_pair_kernel
   int opt_resident = 0;              // 1: keep a channel tile's weights resident in shared memory when they fit
