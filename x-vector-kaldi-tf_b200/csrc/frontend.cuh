@@ -106,7 +106,7 @@ cmvn_select_kernel(UttMeta um, CmvnOpts opts, int32_t D, const float* __restrict
   extern __shared__ __align__(16) float slab[];    // [(we_last - ws_first) * D] (+ up to 3 floats of alignment slack)
   __shared__ int32_t s_pos[TILE];                   // output row inside the utterance, or -1 (unvoiced / beyond keep)
   __shared__ int4 s_row[TILE];                      // per frame of the tile: {window start, window end (slab rows), pos, -}
-  __shared__ double s_scale[TILE];                  // -1 / window frames
+  __shared__ double s_scale[TILE];                  // -1 / window frames (one double division per frame, not per bin)
   __shared__ int32_t s_warp_cnt[TILE / 32];
   __shared__ int32_t s_before;
   double* seg_sum = reinterpret_cast<double*>(slab + slab_floats(opts.cmn_window, D));   // [n_segs][D]
@@ -262,31 +262,16 @@ cmvn_select_kernel(UttMeta um, CmvnOpts opts, int32_t D, const float* __restrict
     const float* p_lo = xd + row.x * D;                         // row leaving next / row entering next / current row
     const float* p_hi = xd + row.y * D;
     const float* p_t = xd + (t0 + r0 - ws_first) * D;
-    float* p_out = out + out_row0 * D + d;
-    for (int r = r0; r < r1; ++r, p_t += D) {
-      if (r > r0) {
-        const int4 next = s_row[r];
-        if (next.x > row.x) {
-          const double v = double(*p_lo);
-          p_lo += D;
-          sum -= v;
-          if (NV) sumsq -= v * v;
-        }
-        if (next.y > row.y) {
-          const double v = double(*p_hi);
-          p_hi += D;
-          sum += v;
-          if (NV) sumsq += v * v;
-        }
-        row = next;
-      }
-      if (row.z < 0) continue;
-      // Kaldi: output_frame.AddVec(-1.0 / window_frames, cur_sum), i.e. a separately rounded product and sum.  No FMA
-      // here on purpose: x - mean lands EXACTLY on a float rounding midpoint surprisingly often (the window sum of
-      // floats is exact in double), and which way such a tie falls is decided by the last bit of the product.
-      double y = __dadd_rn(double(*p_t), __dmul_rn(s_scale[r], sum));
+    float* p_out = out + out_row0 * D + d;                      // + pos * D: 32-bit offsets inside one utterance
+    const double* p_scale = s_scale + r0;
+    // one frame: normalise and store.  Kaldi: output_frame.AddVec(-1.0 / window_frames, cur_sum), i.e. a separately
+    // rounded product and sum.  No FMA here on purpose: x - mean lands EXACTLY on a float rounding midpoint surprisingly
+    // often (the window sum of floats is exact in double), and which way such a tie falls is decided by the last bit
+    // of the product.
+    auto emit = [&](const int4& rw, const float* pt, double scale) {
+      double y = __dadd_rn(double(*pt), __dmul_rn(scale, sum));
       if (NV) {
-        const int n = row.y - row.x;
+        const int n = rw.y - rw.x;
         if (n == 1) {
           y = 0.0;
         } else {
@@ -296,7 +281,27 @@ cmvn_select_kernel(UttMeta um, CmvnOpts opts, int32_t D, const float* __restrict
           y = __dmul_rn(y, 1.0 / sqrt(var));
         }
       }
-      p_out[size_t(row.z) * D] = float(y);
+      p_out[rw.z * D] = float(y);
+    };
+    if (row.z >= 0) emit(row, p_t, *p_scale);
+    for (int r = r0 + 1; r < r1; ++r) {
+      const int4 next = s_row[r];
+      p_t += D;
+      ++p_scale;
+      if (next.x > row.x) {
+        const double v = double(*p_lo);
+        p_lo += D;
+        sum -= v;
+        if (NV) sumsq -= v * v;
+      }
+      if (next.y > row.y) {
+        const double v = double(*p_hi);
+        p_hi += D;
+        sum += v;
+        if (NV) sumsq += v * v;
+      }
+      row = next;
+      if (row.z >= 0) emit(row, p_t, *p_scale);
     }
   }
 }

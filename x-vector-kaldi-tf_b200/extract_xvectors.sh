@@ -20,6 +20,8 @@ nj=                 # jobs; empty = one per GPU
 cmd=run.pl
 chunk_size=-1       # <= 0: take max_chunk_size of the nnet dir
 use_gpu=true        # accepted for compatibility; this build has no CPU path
+device_frontend=true  # true: sliding CMVN + voiced-frame selection run on the GPU (raw feats.scp + vad.scp go in);
+                      # false: the reference's Kaldi pipe (apply-cmvn-sliding | select-voiced-frames) feeds the job
 stage=0
 
 echo "$0 $*"
@@ -40,6 +42,7 @@ Options:
   --nj <n>            number of jobs, one process each (default: --num-gpus)
   --stage <n>         0 extract, 1 merge scp files, 2 speaker means
   --chunk-size <n>    frames per chunk; chunks of an utterance are averaged (default: max_chunk_size of the nnet dir)
+  --device-frontend (true|false)   CMVN + VAD selection on the GPU instead of the Kaldi pipe (default: true)
 USAGE
   exit 1
 fi
@@ -74,10 +77,16 @@ if [ "${stage}" -le 0 ]; then
   echo "$0: extracting xvectors for ${data_dir}: ${nj} job(s) on ${num_gpus} GPU(s)"
   pids=()
   for job in $(seq "${nj}"); do
+    if [ "${device_frontend}" = true ]; then
+      # same options the pipe passes to apply-cmvn-sliding; select-voiced-frames becomes --vad-rspecifier
+      feature_args=(--feature-rspecifier="scp:${split_dir}/${job}/feats.scp" --apply-cmvn-sliding=yes --cmn-window=300
+                    --norm-vars=false --center=true --vad-rspecifier="scp,s,cs:${split_dir}/${job}/vad.scp")
+    else
+      feature_args=(--feature-rspecifier="$(feature_pipe "${job}")")
+    fi
     XVEC_DEVICE=$(( (job - 1) % num_gpus )) ${cmd} "${out_dir}/log/extract.${job}.log" \
       python "${script_dir}/extract_embedding.py" --use-gpu=yes \
-        --min-chunk-size="${min_chunk}" --chunk-size="${chunk_size}" \
-        --feature-rspecifier="$(feature_pipe "${job}")" \
+        --min-chunk-size="${min_chunk}" --chunk-size="${chunk_size}" "${feature_args[@]}" \
         --vector-wspecifier="| copy-vector ark:- ark,scp:${out_dir}/xvector.${job}.ark,${out_dir}/xvector.${job}.scp" \
         --model-dir="${nnet_dir}/model_final" &
     pids+=($!)
