@@ -166,3 +166,49 @@ def test_cli_with_device_frontend(model_dir, tmp_path):
         extract_embedding.eval_dnn(extract_embedding.get_args(
             ["--model-dir=" + d, "--feature-rspecifier=scp:" + scp, "--vad-rspecifier=scp:" + vscp,
              "--vector-wspecifier=ark,scp:%s,%s" % (str(tmp_path / "o.ark"), str(tmp_path / "o.scp"))]))
+
+
+_WORKER = r"""
+import io, os, sys, logging
+sys.path.insert(0, %(root)r)
+sys.path.insert(0, os.path.join(%(root)r, "tests"))
+import torch.distributed as dist
+from xvector_b200 import models, kaldi_io
+import test_frontend_host as T
+dist.init_process_group(backend="gloo")
+rank = dist.get_rank()
+models._create_engine = lambda meta, params, device: T.OracleFrontendEngine(meta, params)
+os.environ["XVEC_BATCH_FRAMES"] = "500"
+out = io.BytesIO() if rank == 0 else None
+table = kaldi_io.VecTable("scp:" + %(vscp)r)
+models.Model().make_embedding(kaldi_io.read_mat_scp_entries("scp:" + %(scp)r), out, %(model)r, 25, 100, True,
+                              logging.getLogger("w"), vad_table=table)
+if rank == 0:
+    open(%(out)r, "wb").write(out.getvalue())
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_gloo_raw_extraction_is_byte_identical_to_one_rank(model_dir, tmp_path, monkeypatch):
+    """Utterance sharding with the front end on the device: every rank walks the whole feats.scp / vad table (so that the
+    skip rules give all ranks the same numbering), stages only its own utterances, rank 0 gathers and writes."""
+    import subprocess
+    import sys
+    d, _ = model_dir
+    monkeypatch.setenv("XVEC_BATCH_FRAMES", "500")
+    feats, vads = _raw_corpus()
+    feats = dict(sorted(feats.items()))
+    ark, scp, vark, vscp = _write(tmp_path, feats, vads)
+    single = io.BytesIO()
+    models.Model().make_embedding(kaldi_io.read_mat_scp_entries("scp:" + scp), single, d, 25, 100, True, None,
+                                  vad_table=kaldi_io.VecTable("scp:" + vscp))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out_path = str(tmp_path / "two_rank.ark")
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER % dict(root=root, model=d, out=out_path, scp=scp, vscp=vscp))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29741", str(script)],
+                       capture_output=True, text=True, timeout=300, env=dict(os.environ, XVEC_SEED="11"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert len(single.getvalue()) > 4 * 512 * 4 and open(out_path, "rb").read() == single.getvalue()
