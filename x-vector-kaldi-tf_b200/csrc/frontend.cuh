@@ -3,9 +3,10 @@
 //   apply-cmvn-sliding --norm-vars=false --center=true --cmn-window=300 | select-voiced-frames
 //                                                                  (reference local/tf/extract_xvectors.sh:68)
 //
-//   vad_tile_count_kernel : voiced rows of every 128-row tile of every utterance (launched only when an utterance is
+//   vad_tile_count_kernel : voiced rows of every tile of every utterance (launched only when an utterance is
 //                           longer than 4096 frames; shorter ones count the rows in front of a tile in place).
-//   cmvn_select_kernel    : one CTA per tile.  The rows every window of the tile touches (<= 128 + cmn_window of them,
+//   cmvn_select_kernel    : one CTA per tile = a whole utterance of up to 512 frames (longer ones are split evenly).  The
+//                           rows every window of the tile touches (the utterance itself, or <= tile + cmn_window rows:
 //                           ONE contiguous span of the caller's matrix) are staged in shared memory with coalesced
 //                           16-byte loads and summed once per (cepstral bin, 16-row segment) in double; thread (bin,
 //                           run of 16 frames) builds its first window from those partial sums and then slides it
@@ -14,19 +15,20 @@
 //                           compacted position  out_row0 + (voiced rows before it)  -- each row is 23 consecutive
 //                           floats written by 23 consecutive lanes.
 //
-// Algorithmic traffic per raw frame: 4*D (read) + 4 (VAD) + 4*D*voiced_fraction (write) bytes; the window re-reads
-// (x(1 + W/128)) are served by L1/L2.
+// Algorithmic traffic per raw frame: 4*D (read) + 4 (VAD) + 4*D*voiced_fraction (write) bytes; a tile that is a whole
+// utterance reads nothing twice, split utterances re-read <= cmn_window rows per tile from L2.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace xvfe {
 
-constexpr int TILE = 128;        // frames per CTA
-constexpr int RUN = 16;          // consecutive frames per thread
-constexpr int SEG = 16;          // slab rows per partial sum
+constexpr int THREADS = 512;
+constexpr int TILE_MAX = THREADS; // most frames per CTA: utterances up to this long are ONE tile (one thread per frame for the
+                                  // per-frame steps), longer ones are split evenly into tiles of a multiple of 32 frames
+constexpr int RUN = 16;          // consecutive frames per thread (the kernel lengthens runs until one pass covers the tile)
+constexpr int SEG = 16;          // fewest slab rows per partial sum (ditto)
 constexpr int DIRECT_COUNT_MAX = 4096;      // utterances up to this long: voiced rows in front of a tile counted in place
-constexpr int THREADS = 256;
 constexpr int COUNT_THREADS = 128;
 constexpr uint32_t ERR_VAD_MISMATCH = 2u;   // bit of the model's sticky device flag (bit 0 = fp16 overflow)
 
@@ -37,6 +39,7 @@ struct UttMeta {
   const int32_t* keep;      // [n_utt] selected rows to write
   const int32_t* tile0;     // [n_utt + 1] first tile of the utterance; tile0[n_utt] = number of tiles
   const int32_t* tile_utt;  // [n_tiles] utterance of every tile
+  const int32_t* tile_rows; // [n_utt] frames per tile of the utterance
   int32_t n_utt;
 };
 
@@ -84,33 +87,53 @@ vad_tile_count_kernel(UttMeta um, const float* __restrict__ vad, int32_t* __rest
   cudaGridDependencySynchronize();
   const int tile = blockIdx.x;
   const int u = __ldg(um.tile_utt + tile);
-  const int t = (tile - __ldg(um.tile0 + u)) * TILE + threadIdx.x;
-  const bool voiced = t < __ldg(um.len + u) && __ldg(vad + size_t(__ldg(um.in_row0 + u)) + t) != 0.f;
-  const int n = __syncthreads_count(voiced);
-  if (threadIdx.x == 0) tile_cnt[tile] = n;
+  const int rp = __ldg(um.tile_rows + u);
+  const int T = __ldg(um.len + u);
+  const int t0 = (tile - __ldg(um.tile0 + u)) * rp;
+  const int t1 = min(T, t0 + rp);
+  const float* v = vad + size_t(__ldg(um.in_row0 + u));
+  int n = 0;
+  for (int t = t0 + threadIdx.x; t < t1; t += COUNT_THREADS) n += __ldg(v + t) != 0.f ? 1 : 0;
+  __shared__ int s_n;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  if ((threadIdx.x & 31) == 0 && n != 0) atomicAdd(&s_n, n);
+  __syncthreads();
+  if (threadIdx.x == 0) tile_cnt[tile] = s_n;
 }
 
-// Dynamic shared memory of cmvn_select_kernel: the slab, then (8-byte aligned) the per-16-row partial sums.
-__host__ __device__ inline size_t slab_floats(int cmn_window, int D) { return (size_t(TILE + cmn_window) * D + 4 + 1) & ~size_t(1); }
-__host__ __device__ inline int max_segs(int cmn_window) { return (TILE + cmn_window) / SEG + 2; }
-inline size_t cmvn_smem_bytes(int cmn_window, int D, bool norm_vars) {
-  return slab_floats(cmn_window, D) * sizeof(float) + size_t(max_segs(cmn_window)) * D * sizeof(double) * (norm_vars ? 2 : 1);
+// Dynamic shared memory of cmvn_select_kernel, carved in this order (sizes fixed per launch by the host from the longest
+// tile / slab of the batch): slab floats | per-16-row partial sums (doubles; twice with variance) | -1/N per frame
+// (doubles) | per-frame table (int4).
+struct SmemPlan {
+  int32_t slab_rows_cap;   // most slab rows of any tile of the launch
+  int32_t rows_cap;        // most frames of any tile (multiple of 32)
+};
+__host__ __device__ inline size_t slab_floats(int slab_rows_cap, int D) { return (size_t(slab_rows_cap) * D + 4 + 3) & ~size_t(3); }
+__host__ __device__ inline int seg_doubles(int slab_rows_cap, int D) { return ((slab_rows_cap / SEG + 2) * D + 1) & ~1; }   // even: keeps 16-byte alignment behind it
+inline size_t cmvn_smem_bytes(const SmemPlan& sp, int D, bool norm_vars) {
+  return slab_floats(sp.slab_rows_cap, D) * sizeof(float) + size_t(seg_doubles(sp.slab_rows_cap, D)) * sizeof(double) * (norm_vars ? 2 : 1) +
+         size_t(sp.rows_cap) * (sizeof(double) + sizeof(int4));
 }
 
-// tile_cnt == nullptr: the voiced rows in front of the tile are counted here from the VAD track (the host launches
-// vad_tile_count_kernel only when some utterance is longer than DIRECT_COUNT_MAX frames).
+// One CTA per tile; a tile is a whole utterance when it has at most TILE_MAX frames (then the slab IS the utterance and
+// nothing is summed twice), else an even split of it.  tile_cnt == nullptr: the voiced rows in front of the tile are
+// counted here from the VAD track (the host launches vad_tile_count_kernel only when some utterance is longer than
+// DIRECT_COUNT_MAX frames).
 template <bool NV>                                  // NV: also normalise the variance (sums of squares carried along)
 __global__ void __launch_bounds__(THREADS)
-cmvn_select_kernel(UttMeta um, CmvnOpts opts, int32_t D, const float* __restrict__ feats, const float* __restrict__ vad,
-                   const int32_t* __restrict__ tile_cnt, float* __restrict__ out, uint32_t* __restrict__ err_flag) {
+cmvn_select_kernel(UttMeta um, CmvnOpts opts, SmemPlan sp, int32_t D, const float* __restrict__ feats,
+                   const float* __restrict__ vad, const int32_t* __restrict__ tile_cnt, float* __restrict__ out,
+                   uint32_t* __restrict__ err_flag) {
   extern __shared__ __align__(16) float slab[];    // [(we_last - ws_first) * D] (+ up to 3 floats of alignment slack)
-  __shared__ int32_t s_pos[TILE];                   // output row inside the utterance, or -1 (unvoiced / beyond keep)
-  __shared__ int4 s_row[TILE];                      // per frame of the tile: {window start, window end (slab rows), pos, -}
-  __shared__ double s_scale[TILE];                  // -1 / window frames (one double division per frame, not per bin)
-  __shared__ int32_t s_warp_cnt[TILE / 32];
+  __shared__ int32_t s_warp_cnt[THREADS / 32];
   __shared__ int32_t s_before;
-  double* seg_sum = reinterpret_cast<double*>(slab + slab_floats(opts.cmn_window, D));   // [n_segs][D]
-  double* seg_sq = seg_sum + max_segs(opts.cmn_window) * D;                               // [n_segs][D] (variance only)
+  double* seg_sum = reinterpret_cast<double*>(slab + slab_floats(sp.slab_rows_cap, D));   // [n_segs][D]
+  double* seg_sq = seg_sum + (NV ? seg_doubles(sp.slab_rows_cap, D) : 0);                 // [n_segs][D] (variance only)
+  double* s_scale = seg_sq + seg_doubles(sp.slab_rows_cap, D);                            // [rows_cap] -1 / window frames
+  int4* s_row = reinterpret_cast<int4*>(s_scale + sp.rows_cap);   // [rows_cap] {window start, end (slab rows), output row or -1, -}
 
   const int tid = threadIdx.x;
   const int tile = blockIdx.x;
@@ -120,10 +143,11 @@ cmvn_select_kernel(UttMeta um, CmvnOpts opts, int32_t D, const float* __restrict
   const int tile_first = __ldg(um.tile0 + u);
   const int T = __ldg(um.len + u);
   const int keep = __ldg(um.keep + u);
+  const int rp = __ldg(um.tile_rows + u);            // frames per tile of this utterance (multiple of 32, <= THREADS)
   const int64_t in_row0 = __ldg(um.in_row0 + u);
   const int64_t out_row0 = __ldg(um.out_row0 + u);
-  const int t0 = (tile - tile_first) * TILE;
-  const int nr = min(TILE, T - t0);
+  const int t0 = (tile - tile_first) * rp;
+  const int nr = min(rp, T - t0);
   int ws_first, we_first, ws_last, we_last;
   window_bounds_fast(t0, T, opts, ws_first, we_first);
   window_bounds_fast(t0 + nr - 1, T, opts, ws_last, we_last);
@@ -146,62 +170,58 @@ cmvn_select_kernel(UttMeta um, CmvnOpts opts, int32_t D, const float* __restrict
   }
 
   // ---- where every row of the tile goes: voiced rows before it in the utterance
-  bool voiced = false;
+  const bool voiced = tid < nr && (vad == nullptr || __ldg(vad + in_row0 + t0 + tid) != 0.f);
   int before_part = 0;
-  if (tid < TILE) {
-    voiced = tid < nr && (vad == nullptr || __ldg(vad + in_row0 + t0 + tid) != 0.f);
-  } else if (vad != nullptr) {
+  if (vad != nullptr) {
     if (tile_cnt != nullptr) {
-      for (int j = tile_first + (tid - TILE); j < tile; j += THREADS - TILE) before_part += __ldg(tile_cnt + j);
+      for (int j = tile_first + tid; j < tile; j += THREADS) before_part += __ldg(tile_cnt + j);
     } else {
       const float* v = vad + in_row0;
-      for (int j = tid - TILE; j < t0; j += THREADS - TILE) before_part += __ldg(v + j) != 0.f ? 1 : 0;
+      for (int j = tid; j < t0; j += THREADS) before_part += __ldg(v + j) != 0.f ? 1 : 0;
     }
   }
   __syncthreads();                                 // s_before is initialised and the slab is complete
-  if (tid < TILE) {
-    const unsigned ballot = __ballot_sync(0xffffffffu, voiced);
-    if ((tid & 31) == 0) s_warp_cnt[tid >> 5] = __popc(ballot);
-    s_pos[tid] = voiced ? __popc(ballot & ((1u << (tid & 31)) - 1u)) : -1;
-  } else if (vad != nullptr) {
+  const unsigned ballot = __ballot_sync(0xffffffffu, voiced);
+  if ((tid & 31) == 0) s_warp_cnt[tid >> 5] = __popc(ballot);
+  const int rank_in_warp = voiced ? __popc(ballot & ((1u << (tid & 31)) - 1u)) : -1;
+  if (vad != nullptr && t0 > 0) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) before_part += __shfl_xor_sync(0xffffffffu, before_part, o);
     if ((tid & 31) == 0 && before_part != 0) atomicAdd(&s_before, before_part);
   }
 
-  // ---- partial sums of every 16 slab rows, per cepstral bin (thread = (bin, 16-row segment))
+  // ---- partial sums of every `seg` slab rows, per cepstral bin (thread = (bin, segment)).  `seg` (>= SEG) is the
+  // shortest segment for which every (bin, segment) pair gets its own thread: one pass, no straggling second one.
   const float* x = slab + shift;                   // x[(t - ws_first) * D + d]
   const int slab_rows = we_last - ws_first;
-  const int n_segs = (slab_rows + SEG - 1) / SEG;
+  int seg = max(SEG, (slab_rows * D + THREADS - 1) / THREADS);
+  while (((slab_rows + seg - 1) / seg) * D > THREADS && seg < slab_rows) ++seg;
+  const int n_segs = (slab_rows + seg - 1) / seg;
   for (int item = tid; item < n_segs * D; item += THREADS) {
     const int sgm = item / D, d = item - sgm * D;
-    const int cnt = min(slab_rows - sgm * SEG, SEG);
-    const float* p = x + sgm * SEG * D + d;
+    const int cnt = min(slab_rows - sgm * seg, seg);
+    const float* p = x + sgm * seg * D + d;
     double a0 = 0.0, a1 = 0.0, q0 = 0.0, q1 = 0.0;
-    if (cnt == SEG) {
-#pragma unroll
-      for (int i = 0; i < SEG; i += 2, p += 2 * D) {
-        const double v0 = double(p[0]), v1 = double(p[D]);
-        a0 += v0; a1 += v1;
-        if (NV) { q0 += v0 * v0; q1 += v1 * v1; }
-      }
-    } else {
-      for (int i = 0; i < cnt; ++i, p += D) {
-        const double v0 = double(p[0]);
-        a0 += v0;
-        if (NV) q0 += v0 * v0;
-      }
+    int i = 0;
+#pragma unroll 4
+    for (; i + 2 <= cnt; i += 2, p += 2 * D) {
+      const double v0 = double(p[0]), v1 = double(p[D]);
+      a0 += v0; a1 += v1;
+      if (NV) { q0 += v0 * v0; q1 += v1 * v1; }
+    }
+    if (i < cnt) {
+      const double v0 = double(p[0]);
+      a0 += v0;
+      if (NV) q0 += v0 * v0;
     }
     seg_sum[item] = a0 + a1;                        // seg_sum[sgm * D + d]
     if (NV) seg_sq[item] = q0 + q1;
   }
   __syncthreads();
-  if (tid < TILE) {
+  {
     int before = vad != nullptr ? s_before : t0;
     for (int w = 0; w < (tid >> 5); ++w) before += s_warp_cnt[w];
-    const int p = s_pos[tid];
-    const int pos = p < 0 ? -1 : before + p;
-    s_pos[tid] = pos < keep ? pos : -1;
+    const int pos = rank_in_warp < 0 ? -1 : before + rank_in_warp;
     if (tid < nr) {                      // the frame's window, once per tile instead of once per cepstral bin
       int ws, we;
       window_bounds_fast(t0 + tid, T, opts, ws, we);
@@ -210,7 +230,7 @@ cmvn_select_kernel(UttMeta um, CmvnOpts opts, int32_t D, const float* __restrict
     }
     if (tid == 0 && t0 + nr == T) {      // last tile of the utterance: did it hold as many voiced rows as the caller said?
       int total = before;
-      for (int w = 0; w < TILE / 32; ++w) total += s_warp_cnt[w];
+      for (int w = 0; w < THREADS / 32; ++w) total += s_warp_cnt[w];
       if (total < keep) atomicOr(err_flag, ERR_VAD_MISMATCH);
     }
   }
@@ -220,21 +240,23 @@ cmvn_select_kernel(UttMeta um, CmvnOpts opts, int32_t D, const float* __restrict
   // whole-segment partial sums plus the rows at its two ragged ends; after that the recursion of Kaldi's
   // SlidingWindowCmnInternal (subtract the row that left, add the row that entered).  Sums of floats are exact in
   // double (until their exponents are > 2^20 apart), so the association order does not show in the result.
-  const int n_runs = (nr + RUN - 1) / RUN;
+  int run_len = max(RUN / 2, (nr * D + THREADS - 1) / THREADS);   // as above: one (bin, run) pair per thread, one pass
+  while (((nr + run_len - 1) / run_len) * D > THREADS && run_len < nr) ++run_len;
+  const int n_runs = (nr + run_len - 1) / run_len;
   for (int item = tid; item < n_runs * D; item += THREADS) {
     const int run = item / D, d = item - run * D;
-    const int r0 = run * RUN;
-    const int r1 = min(nr, r0 + RUN);
+    const int r0 = run * run_len;
+    const int r1 = min(nr, r0 + run_len);
     const float* xd = x + d;                                    // column d of the slab
     int4 row = s_row[r0];                                       // slab rows [row.x, row.y) are frame r0's window
     double sum = 0.0, sumsq = 0.0;
     {
       const int a = row.x, b = row.y;
-      const int sa = (a + SEG - 1) / SEG, sb = b / SEG;         // whole segments [sa, sb)
+      const int sa = (a + seg - 1) / seg, sb = b / seg;         // whole segments [sa, sb)
       int head_end = b, tail_begin = b;
       if (sa < sb) {
-        head_end = sa * SEG;
-        tail_begin = sb * SEG;
+        head_end = sa * seg;
+        tail_begin = sb * seg;
         double c0 = 0.0, c1 = 0.0;
         const double* ps = seg_sum + sa * D + d;
         int k = sa;

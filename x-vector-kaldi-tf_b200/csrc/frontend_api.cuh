@@ -13,27 +13,31 @@ struct FrontendPlan {
 };
 
 inline int64_t fe_tiles_upper_bound(int64_t total_rows, int32_t n_utt) {
-  return total_rows / xvfe::TILE + n_utt;      // every utterance ends in at most one partial tile
+  return total_rows / xvfe::TILE_MAX + n_utt;  // ceil(len / TILE_MAX) tiles per utterance
 }
 
 inline FrontendPlan fe_plan(int64_t total_rows, int32_t n_utt) {
   FrontendPlan p;
   p.total_rows = total_rows;
   p.off_meta = 0;
-  p.off_tile_cnt = size_t(round_up((int64_t(5) * n_utt + 1 + fe_tiles_upper_bound(total_rows, n_utt)) * 4, 1024));
+  p.off_tile_cnt = size_t(round_up((int64_t(6) * n_utt + 1 + fe_tiles_upper_bound(total_rows, n_utt)) * 4, 1024));
   p.bytes = p.off_tile_cnt + size_t(round_up(fe_tiles_upper_bound(total_rows, n_utt) * 4, 1024));
   return p;
 }
 
-int fe_check_opts(const xv_model* m, const xv_cmvn_opts* o, size_t* smem_bytes) {
+int fe_check_opts(const xv_model* m, const xv_cmvn_opts* o) {
   if (!o) return fail(XV_EINVAL, "null cmvn options");
   if (o->cmn_window < 1) return fail(XV_EINVAL, "cmn_window must be >= 1");
   if (o->min_window < 0 || o->min_window > o->cmn_window) return fail(XV_EINVAL, "min_window must be in [0, cmn_window]");
-  const size_t smem = xvfe::cmvn_smem_bytes(o->cmn_window, m->topo.feat_dim, o->normalize_variance != 0);
-  if (smem > size_t(200) * 1024)
-    return fail(XV_EINVAL, "cmn_window * feat_dim too large for one CTA's shared memory (" + std::to_string(smem) + " bytes)");
-  *smem_bytes = smem;
+  (void)m;
   return XV_OK;
+}
+
+// Frames per tile of an utterance: the whole utterance when it fits one CTA, else an even split; multiple of 32.
+inline int32_t fe_tile_rows(int32_t len) {
+  if (len <= 0) return 32;
+  const int32_t nt = (len + xvfe::TILE_MAX - 1) / xvfe::TILE_MAX;
+  return int32_t(round_up((len + nt - 1) / nt, 32));
 }
 
 int frontend_impl(xv_model* m, const float* feats_dev, const float* vad_dev, const int32_t* utt_len_host,
@@ -42,8 +46,7 @@ int frontend_impl(xv_model* m, const float* feats_dev, const float* vad_dev, con
   if (!m || !feats_dev || !utt_len_host || !out_dev || !workspace_dev) return fail(XV_EINVAL, "null argument");
   if (n_utt <= 0) return fail(XV_EINVAL, "n_utt must be >= 1");
   if (vad_dev && !out_keep_host) return fail(XV_EINVAL, "out_keep_host is required when a VAD track is given");
-  size_t smem = 0;
-  int rc = fe_check_opts(m, opts, &smem);
+  int rc = fe_check_opts(m, opts);
   if (rc != XV_OK) return rc;
   XV_CUDA(cudaSetDevice(m->device));
   int64_t total_rows = 0;
@@ -61,8 +64,9 @@ int frontend_impl(xv_model* m, const float* feats_dev, const float* vad_dev, con
     return fail(XV_ENOMEM, "frontend workspace too small: need " + std::to_string(p.bytes) + " bytes, got " + std::to_string(workspace_bytes));
   if (reinterpret_cast<uintptr_t>(workspace_dev) % 16 != 0) return fail(XV_EINVAL, "frontend workspace must be 16-byte aligned");
 
-  // ---- utterance table, built in a pinned staging slot: [in_row0 | len | out_row0 | keep | tile0 (n_utt + 1) | tile_utt] ----
-  rc = ensure_meta_capacity(m, int64_t(5) * n_utt + 1 + fe_tiles_upper_bound(total_rows, n_utt));
+  // ---- utterance table, built in a pinned staging slot:
+  //      [in_row0 | len | out_row0 | keep | tile0 (n_utt + 1) | tile_rows | tile_utt (n_tiles)] ----
+  rc = ensure_meta_capacity(m, int64_t(6) * n_utt + 1 + fe_tiles_upper_bound(total_rows, n_utt));
   if (rc != XV_OK) return rc;
   const int slot = m->meta_next;
   m->meta_next = (m->meta_next + 1) % META_SLOTS;
@@ -70,20 +74,29 @@ int frontend_impl(xv_model* m, const float* feats_dev, const float* vad_dev, con
   int32_t* mh = m->meta_host[slot];
   int64_t in_row = 0, out_row = 0, tile = 0;
   int32_t longest = 0;
-  int32_t* tile_utt = mh + 5 * int64_t(n_utt) + 1;
+  xvfe::SmemPlan sp{1, 32};
+  int32_t* tile_rows = mh + 5 * int64_t(n_utt) + 1;
+  int32_t* tile_utt = mh + 6 * int64_t(n_utt) + 1;
   for (int i = 0; i < n_utt; ++i) {
     const int32_t len = utt_len_host[i];
-    longest = std::max(longest, len);
-    for (int32_t k = 0; k < (len + xvfe::TILE - 1) / xvfe::TILE; ++k) tile_utt[tile + k] = i;
     const int32_t keep = out_keep_host ? out_keep_host[i] : len;
+    const int32_t rp = fe_tile_rows(len);
+    const int32_t nt = (len + rp - 1) / rp;
+    longest = std::max(longest, len);
+    for (int32_t k = 0; k < nt; ++k) tile_utt[tile + k] = i;
+    if (len > 0) {
+      sp.rows_cap = std::max(sp.rows_cap, rp);
+      sp.slab_rows_cap = std::max(sp.slab_rows_cap, std::min(len, rp + opts->cmn_window));   // every window lies inside the utterance
+    }
     mh[i] = int32_t(in_row);
     mh[n_utt + i] = len;
     mh[2 * n_utt + i] = int32_t(out_row);
     mh[3 * n_utt + i] = keep;
     mh[4 * n_utt + i] = int32_t(tile);
+    tile_rows[i] = rp;
     in_row += len;
     out_row += keep;
-    tile += (len + xvfe::TILE - 1) / xvfe::TILE;
+    tile += nt;
   }
   mh[5 * n_utt] = int32_t(tile);
   if (total_keep_out) *total_keep_out = out_row;
@@ -92,11 +105,14 @@ int frontend_impl(xv_model* m, const float* feats_dev, const float* vad_dev, con
   uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
   int32_t* meta_dev = reinterpret_cast<int32_t*>(ws + p.off_meta);
   int32_t* tile_cnt = reinterpret_cast<int32_t*>(ws + p.off_tile_cnt);
-  XV_CUDA(cudaMemcpyAsync(meta_dev, mh, (size_t(5) * n_utt + 1 + size_t(tile)) * 4, cudaMemcpyHostToDevice, stream));
+  const size_t smem = xvfe::cmvn_smem_bytes(sp, m->topo.feat_dim, opts->normalize_variance != 0);
+  if (smem > size_t(226) * 1024)
+    return fail(XV_EINVAL, "cmn_window * feat_dim too large for one CTA's shared memory (" + std::to_string(smem) + " bytes)");
+  XV_CUDA(cudaMemcpyAsync(meta_dev, mh, (size_t(6) * n_utt + 1 + size_t(tile)) * 4, cudaMemcpyHostToDevice, stream));
   XV_CUDA(cudaEventRecord(m->meta_event[slot], stream));
 
   xvfe::UttMeta um{meta_dev, meta_dev + n_utt, meta_dev + 2 * n_utt, meta_dev + 3 * n_utt, meta_dev + 4 * n_utt,
-                   meta_dev + 5 * int64_t(n_utt) + 1, n_utt};
+                   meta_dev + 6 * int64_t(n_utt) + 1, meta_dev + 5 * int64_t(n_utt) + 1, n_utt};
   const bool count_pass = vad_dev != nullptr && longest > xvfe::DIRECT_COUNT_MAX;
   const xvfe::CmvnOpts o{opts->cmn_window, opts->min_window, opts->center != 0, opts->normalize_variance != 0};
   const bool pdl = m->opt_pdl != 0;
@@ -110,7 +126,7 @@ int frontend_impl(xv_model* m, const float* feats_dev, const float* vad_dev, con
     XV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     opted = smem;
   }
-  XV_CUDA(launch_k(pdl, kernel, dim3(unsigned(tile)), dim3(xvfe::THREADS), smem, stream, um, o, int32_t(m->topo.feat_dim),
+  XV_CUDA(launch_k(pdl, kernel, dim3(unsigned(tile)), dim3(xvfe::THREADS), smem, stream, um, o, sp, int32_t(m->topo.feat_dim),
                    feats_dev, vad_dev, static_cast<const int32_t*>(count_pass ? tile_cnt : nullptr), out_dev, m->overflow_dev));
   ++m->last_frontend_launches;
   XV_CUDA(cudaGetLastError());
