@@ -200,3 +200,46 @@ def test_entry_reader_on_unbuffered_pipe_and_truncation():
     with pytest.raises(kaldi_io.BadInputFormat):
         for e in kaldi_io.read_mat_ark_entries(io.BytesIO(buf.getvalue()[:-10])):
             e.read_into(np.empty((e.rows, e.cols), np.float32))
+
+
+# ---- integer vectors, posteriors, confusion-network times, segments: pinned by fixtures the reference's own readers /
+# writer produced (tests/golden/make_golden_misc.py) ----
+
+def _misc():
+    return np.load(os.path.join(GOLD, "misc_expected.npz"))
+
+
+def test_int_vectors_match_the_reference_bytes_and_values(tmp_path):
+    want = _misc()
+    got = dict(kaldi_io.read_vec_int_ark(os.path.join(GOLD, "vec_int.ark")))
+    assert list(got) == ["utt-a", "utt.b", "spk/utt_c"]
+    for k, v in got.items():
+        assert v.dtype == np.int32 and np.array_equal(v, want["vec_int/" + k])
+    assert [k for k, _ in kaldi_io.read_ali_ark(os.path.join(GOLD, "vec_int.ark"))] == list(got)
+    out = tmp_path / "rewritten.ark"
+    with open(out, "wb") as f:
+        for k, v in got.items():
+            kaldi_io.write_vec_int(f, v, key=k)
+    assert out.read_bytes() == open(os.path.join(GOLD, "vec_int.ark"), "rb").read()     # byte-identical to the reference's writer
+    text = tmp_path / "ali.txt"
+    text.write_bytes(b"u1 4 8 15 16 23 42\nu2  [ 1 2 3 ]\n")
+    parsed = dict(kaldi_io.read_vec_int_ark(str(text)))
+    assert parsed["u1"].tolist() == [4, 8, 15, 16, 23, 42] and parsed["u2"].tolist() == [1, 2, 3]
+
+
+def test_posteriors_and_bin_times_match_the_reference_readers():
+    want = _misc()
+    posts = dict(kaldi_io.read_post_ark(os.path.join(GOLD, "post.ark")))
+    assert list(posts) == ["p1", "p2"] and list(dict(kaldi_io.read_cnet_ark(os.path.join(GOLD, "post.ark")))) == ["p1", "p2"]
+    for k, post in posts.items():
+        assert [len(fr) for fr in post] == want["post/%s/lens" % k].tolist()
+        assert [i for fr in post for i, _ in fr] == want["post/%s/idx" % k].tolist()
+        assert np.array_equal(np.array([v for fr in post for _, v in fr], np.float64), want["post/%s/val" % k])
+    for k, bins in kaldi_io.read_cntime_ark(os.path.join(GOLD, "cntime.ark")):
+        assert np.array_equal(np.array(bins, np.float64), want["cntime/" + k])
+
+
+def test_segments_as_bool_vec_matches_the_reference():
+    got = kaldi_io.read_segments_as_bool_vec(os.path.join(GOLD, "segments.txt"))
+    want = _misc()["segments"]
+    assert got.dtype == bool and np.array_equal(got, want) and got.sum() == 45 + 40 + 17

@@ -166,6 +166,152 @@ def _check_binary_writable(fd):
 
 
 # --------------------------------------------------------------------------------------
+# integer vectors (alignments, utt2int-style tables), posteriors, confusion-network times, segments
+# (reference kaldi_io.py:139-222, :553-700).  None of them is on the extraction or training path; they complete the
+# module's surface for recipes that import it.
+
+_INT_RECORD = np.dtype([("size", "i1"), ("value", "<i4")])                                   # '\4' <int32>
+_POST_RECORD = np.dtype([("size_idx", "i1"), ("idx", "<i4"), ("size_post", "i1"), ("post", "<f4")])
+_TIME_RECORD = np.dtype([("size_beg", "i1"), ("t_beg", "<f4"), ("size_end", "i1"), ("t_end", "<f4")])
+
+
+def _read_sized_int(fd):
+    """One '\4' <int32> token of a Kaldi binary stream."""
+    tag = _read_exact(fd, 1)
+    assert tag == b"\4", "expected a 4-byte integer, size tag was %r" % tag
+    return struct.unpack("<i", _read_exact(fd, 4))[0]
+
+
+def _read_records(fd, count, dtype, size_fields):
+    rec = np.frombuffer(_read_exact(fd, count * dtype.itemsize), dtype=dtype, count=count)
+    for name in size_fields:
+        assert count == 0 or rec[0][name] == 4
+    return rec
+
+
+def read_vec_int(file_or_fd):
+    """One Kaldi integer vector, binary or text (values as int32 / int)."""
+    fd = open_or_fd(file_or_fd)
+    try:
+        flag = _read_exact(fd, 2).decode()
+        if flag == "\0B":
+            n = _read_sized_int(fd)
+            return _read_records(fd, n, _INT_RECORD, ("size",))["value"]
+        tokens = [t for t in (flag + fd.readline().decode()).split() if t not in ("[", "]")]
+        return np.array(tokens, dtype=int)
+    finally:
+        if fd is not file_or_fd:
+            fd.close()
+
+
+def read_vec_int_ark(file_or_fd):
+    """Generator of (key, int vector) over an ark."""
+    fd = open_or_fd(file_or_fd)
+    try:
+        key = read_key(fd)
+        while key:
+            yield key, read_vec_int(fd)
+            key = read_key(fd)
+    finally:
+        if fd is not file_or_fd:
+            fd.close()
+
+
+def read_ali_ark(file_or_fd):
+    """Alignments are integer vectors."""
+    return read_vec_int_ark(file_or_fd)
+
+
+def write_vec_int(file_or_fd, v, key=""):
+    """Append one binary integer vector: [key ' '] '\0B' '\4' <dim> then '\4' <value> per element."""
+    fd = open_or_fd(file_or_fd, mode="wb")
+    _check_binary_writable(fd)
+    try:
+        v = np.asarray(v)
+        body = np.empty(v.shape[0], dtype=_INT_RECORD)
+        body["size"] = 4
+        body["value"] = v
+        head = (key + " ").encode() if key != "" else b""
+        fd.write(head + b"\0B\4" + struct.pack("<i", v.shape[0]) + body.tobytes())
+    finally:
+        if fd is not file_or_fd:
+            fd.close()
+
+
+def read_post(file_or_fd):
+    """One binary Kaldi Posterior (vector<vector<pair<int32, float>>>) as a list, per frame, of (index, value) tuples."""
+    fd = open_or_fd(file_or_fd)
+    try:
+        assert _read_exact(fd, 2) == b"\0B"
+        frames = []
+        for _ in range(_read_sized_int(fd)):
+            rec = _read_records(fd, _read_sized_int(fd), _POST_RECORD, ("size_idx", "size_post"))
+            frames.append(rec[["idx", "post"]].tolist())
+        return frames
+    finally:
+        if fd is not file_or_fd:
+            fd.close()
+
+
+def read_post_ark(file_or_fd):
+    """Generator of (key, posterior) over an ark."""
+    fd = open_or_fd(file_or_fd)
+    try:
+        key = read_key(fd)
+        while key:
+            yield key, read_post(fd)
+            key = read_key(fd)
+    finally:
+        if fd is not file_or_fd:
+            fd.close()
+
+
+def read_cnet_ark(file_or_fd):
+    """Confusion networks are stored as posteriors."""
+    return read_post_ark(file_or_fd)
+
+
+def read_cntime(file_or_fd):
+    """Begin / end times of the bins of one confusion network: list of (t_beg, t_end)."""
+    fd = open_or_fd(file_or_fd)
+    try:
+        assert _read_exact(fd, 2) == b"\0B"
+        rec = _read_records(fd, _read_sized_int(fd), _TIME_RECORD, ("size_beg", "size_end"))
+        return rec[["t_beg", "t_end"]].tolist()
+    finally:
+        if fd is not file_or_fd:
+            fd.close()
+
+
+def read_cntime_ark(file_or_fd):
+    """Generator of (key, bin times) over an ark."""
+    fd = open_or_fd(file_or_fd)
+    try:
+        key = read_key(fd)
+        while key:
+            yield key, read_cntime(fd)
+            key = read_key(fd)
+    finally:
+        if fd is not file_or_fd:
+            fd.close()
+
+
+def read_segments_as_bool_vec(segments_file):
+    """A Kaldi ``segments`` file of ONE recording ('<utt> <rec> <t-beg> <t-end>', seconds) as a per-frame bool vector at
+    100 frames per second: True inside a segment, ending at the last segment's end."""
+    segs = np.loadtxt(segments_file, dtype="object,object,f,f", ndmin=1)
+    assert len(segs) > 0, "empty segmentation"
+    assert len({rec[1] for rec in segs}) == 1, "segments of more than one recording"
+    start = np.rint([100 * rec[2] for rec in segs]).astype(int)
+    end = np.rint([100 * rec[3] for rec in segs]).astype(int)
+    frames = np.zeros(int(end[-1]) if len(end) else 0, dtype=bool)
+    for b, e in zip(start, end):
+        frames[b:e] = True
+    assert frames.sum() == np.sum(end - start)
+    return frames
+
+
+# --------------------------------------------------------------------------------------
 # float vectors
 
 def _read_vec_flt_binary(fd):
