@@ -423,13 +423,12 @@ def measure_frontend(args, eng, dev, stream, flush, rank, peaks):
     track; kernel time by CUDA events on the launching stream (L2 flushed between iterations), judged against HBM with
     the algorithmic bytes (raw rows + VAD in, voiced rows out), and the raw host path (xv_submit_host_raw) end to end."""
     import torch
-    from oracle import kaldi_frontend_oracle as feo
     from xvector_b200 import _native, synthetic
     B, T = args.batch, args.frames
     lens = np.full(B, T, np.int32)
     raw = synthetic.mfcc_batch(7 + 1000 * rank, lens) + np.float32(-30.0) * (np.arange(FEAT_DIM) == 0).astype(np.float32)
     rng = np.random.default_rng(7 + rank)
-    tracks = [feo.synthetic_vad(rng, T) for _ in range(B)]
+    tracks = [synthetic.synthetic_vad(rng, T) for _ in range(B)]
     for v in tracks:
         if v.sum() < 25:                      # every utterance passes the extractor's min-chunk-size rule
             v[:min(T, 100)] = 1.0
@@ -469,12 +468,17 @@ def measure_frontend(args, eng, dev, stream, flush, rank, peaks):
     run(n_it)
     torch.cuda.synchronize(dev)
     e2e_ms = (time.perf_counter() - t0) * 1e3 / n_it
-    # the oracle (Kaldi's recursion restated in numpy, one core) on a bounded sample, for scale
-    n_cpu = min(B, 32)
-    t0 = time.perf_counter()
-    for i in range(n_cpu):
-        feo.frontend(raw[i * T:(i + 1) * T], vad[i * T:(i + 1) * T])
-    cpu_s = time.perf_counter() - t0
+    # cpu_baseline leg (rank 0, N = 1 only): the oracle (Kaldi's recursion restated in numpy, one core) on a bounded sample
+    cpu = None
+    if rank == 0 and int(os.environ.get("WORLD_SIZE", "1")) == 1 and not args.no_cpu_baseline:
+        from oracle import kaldi_frontend_oracle as feo
+        n_cpu = min(B, 32)
+        t0 = time.perf_counter()
+        for i in range(n_cpu):
+            feo.frontend(raw[i * T:(i + 1) * T], vad[i * T:(i + 1) * T])
+        cpu_s = time.perf_counter() - t0
+        cpu = dict(value=round(n_cpu * T / cpu_s, 1), unit="raw frames/s", cores=1, kind="port",
+                   sample="%d utterances of %d frames through oracle/kaldi_frontend_oracle.py" % (n_cpu, T))
     return dict(workload="apply-cmvn-sliding(300, centred) | select-voiced-frames on %d x %d RAW frames, %.0f %% voiced"
                          % (B, T, 100.0 * float(keep.sum()) / (B * T)),
                 kernels="cmvn_select_kernel (one launch; vad_tile_count_kernel in front only for utterances > 4096 frames)", ms_per_call=round(ms, 5),
@@ -486,8 +490,7 @@ def measure_frontend(args, eng, dev, stream, flush, rank, peaks):
                          ms_per_step=round(e2e_ms, 5), raw_frames_per_sec=round(B * T / (e2e_ms * 1e-3), 1),
                          voiced_frames_per_sec=round(float(keep.sum()) / (e2e_ms * 1e-3), 1),
                          h2d_bytes_per_step=int(B * T * (FEAT_DIM * 4 + 4) + B * 4 * 3), d2h_bytes_per_step=B * EMB_DIM * 4 + 4),
-                cpu_baseline=dict(value=round(n_cpu * T / cpu_s, 1), unit="raw frames/s", cores=1, kind="port",
-                                  sample="%d utterances of %d frames through oracle/kaldi_frontend_oracle.py" % (n_cpu, T)))
+                cpu_baseline=cpu)
 
 
 def measure_train_step(args, dev, rank, world, peaks, topo):

@@ -8,17 +8,14 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import kaldi_frontend_oracle as fe          # noqa: E402  (synthetic VAD tracks only)
-from oracle import xvector_oracle as orc                # noqa: E402
 from xvector_b200 import _native, synthetic             # noqa: E402
 
 B, T = 256, 400
-t = orc.TOPOLOGIES["ModelWithoutDropoutTdnn"]
-eng = _native.XvecEngine(t["kernel_sizes"], t["dilations"], t["layer_sizes"], 512, 23, device=0)
+eng = _native.XvecEngine([5, 3, 3, 1, 1], [1, 2, 3, 1, 1], [512, 512, 512, 512, 1536], 512, 23, device=0)
 lens = np.full(B, T, np.int32)
 rng = np.random.default_rng(7)
 raw = torch.from_numpy(synthetic.mfcc_batch(7, lens)).cuda()
-vad_np = np.concatenate([fe.synthetic_vad(rng, T) for _ in range(B)])
+vad_np = np.concatenate([synthetic.synthetic_vad(rng, T) for _ in range(B)])
 vad = torch.from_numpy(vad_np).cuda()
 keep = vad_np.reshape(B, T).astype(bool).sum(axis=1).astype(np.int32)
 out = torch.empty((int(keep.sum()), 23), device="cuda")

@@ -117,3 +117,18 @@ def make_params(kernel_sizes, layer_sizes, embedding_sizes, feat_dim=FEAT_DIM, n
         p["output/w:0"] = rng.uniform(-lim, lim, (prev, num_classes)).astype(np.float32)
         p["output/b:0"] = np.full(num_classes, 0.1, np.float32)
     return p
+
+
+def synthetic_vad(rng, num_frames, voiced_fraction=0.75, mean_run=40):
+    """A 0/1 float32 VAD track of alternating voiced / unvoiced runs (what compute-vad's energy decisions look like):
+    the second input of the feature front end (select-voiced-frames, reference local/tf/extract_xvectors.sh:68)."""
+    out = np.zeros(num_frames, np.float32)
+    t = 0
+    state = rng.random() < voiced_fraction
+    while t < num_frames:
+        mean = mean_run * (voiced_fraction if state else (1.0 - voiced_fraction)) * 2.0
+        run = 1 + int(rng.exponential(max(mean, 1.0)))
+        out[t:t + run] = 1.0 if state else 0.0
+        t += run
+        state = not state
+    return out
