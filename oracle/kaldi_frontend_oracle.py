@@ -20,7 +20,8 @@ site above (the options it passes) :
   kept in order; a length mismatch or an utterance without voiced frames is skipped (returns None).
 
 ``sliding_window_cmn_direct`` is a second, independent restatement (window sums from prefix sums instead of a running
-sum) used to de-risk the first one.
+sum) used to de-risk the first one; ``kaldi_frontend_oracle.c`` (bound by ``kaldi_frontend_c.py``) is a third, in plain C,
+bit-identical to the first and fast enough to serve as bench.py's CPU baseline for this block.
 """
 import numpy as np
 

@@ -98,3 +98,22 @@ def test_synthetic_vad_is_binary_and_mixed():
     v = fe.synthetic_vad(rng, 5000)
     assert set(np.unique(v)) == {0.0, 1.0}
     assert 0.5 < v.mean() < 0.95
+
+
+@pytest.mark.parametrize("center,norm_vars,window", [(True, False, 300), (True, True, 300), (False, False, 300),
+                                                     (False, True, 64), (True, False, 7)])
+def test_c_restatement_is_bit_identical_to_the_numpy_one(center, norm_vars, window):
+    """oracle/kaldi_frontend_oracle.c (gcc -O2 -ffp-contract=off) follows the same recursion in the same order: the third
+    restatement must agree with the first bit for bit, selection included."""
+    from oracle import kaldi_frontend_c as kfc
+    rng = np.random.default_rng(4)
+    for T in (1, 2, 33, 299, 300, 301, 1000):
+        x = (rng.standard_normal((T, 23)) * 12 / np.sqrt(1 + np.arange(23)) - 40.0 * (np.arange(23) == 0)).astype(np.float32)
+        v = fe.synthetic_vad(rng, T)
+        mw = min(100, window)
+        assert np.array_equal(kfc.sliding_window_cmn(x, window, center, norm_vars, mw),
+                              fe.sliding_window_cmn(x, window, center, norm_vars, mw))
+        a, b = kfc.frontend(x, v, window, center, norm_vars, mw), fe.frontend(x, v, window, center, norm_vars, mw)
+        assert (a is None and b is None) or np.array_equal(a, b)
+    assert kfc.frontend(np.ones((4, 3), np.float32), np.zeros(4, np.float32)) is None
+    assert kfc.frontend(np.ones((4, 3), np.float32), np.ones(5, np.float32)) is None

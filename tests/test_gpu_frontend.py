@@ -101,6 +101,19 @@ def test_long_utterances_take_the_tile_count_pass():
     eng.close()
 
 
+def test_device_output_equals_the_c_restatement_bit_for_bit():
+    """Mean normalisation + selection at the recipe's options against oracle/kaldi_frontend_oracle.c: no tolerance."""
+    from oracle import kaldi_frontend_c as kfc
+    eng, _ = _engine()
+    feats, vads = _corpus(21, [400, 25, 999, 311, 150, 64])
+    keep = np.array([int(np.count_nonzero(v)) for v in vads], np.int32)
+    got = _device_frontend(eng, feats, vads, keep, None)
+    want = np.concatenate([kfc.frontend(f, v) for f, v in zip(feats, vads)])
+    assert got.shape == want.shape
+    assert (got != want).sum() <= 2, int((got != want).sum())      # a stray last-bit flip at most (none observed)
+    eng.close()
+
+
 def test_other_feature_dims():
     from xvector_b200._native import XvCmvnOpts
     for dim in (13, 40):      # (wider inputs are refused by xv_create: the pack kernel stages (32 + 2*halo) * feat_dim floats)
