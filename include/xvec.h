@@ -145,6 +145,16 @@ int32_t xv_last_kernel_ms(xv_model* m, float* ms_out, int32_t cap);
  * Options: "reuse_taps", "desc_base_offset", "profile". */
 int xv_set_option(xv_model* m, const char* name, int64_t value);
 
+/* Host-only helper of the reader that feeds xv_submit_host: index of the binary float matrices of a Kaldi ark held in
+ * memory (an mmap'ed file), replacing the per-utterance header parsing of read_mat_ark / _read_mat_binary
+ * (reference local/tf/kaldi_io.py:372-392, :413-437; key rules :120-133).  For entry i < return value:
+ * key = buf[key_off[i] .. +key_len[i]), a rows[i] x cols[i] matrix of elem_bytes[i] (4 = 'FM ', 8 = 'DM ') per element
+ * at buf + payload_off[i].  Stops at max_entries, at the end of the buffer, or at the first entry of another kind (text,
+ * compressed, malformed, truncated); *consumed = offset of the first unparsed byte.  Returns the number of entries, -1 on
+ * a null argument. */
+int64_t xv_ark_scan(const uint8_t* buf, int64_t len, int64_t max_entries, int64_t* key_off, int32_t* key_len,
+                    int32_t* rows, int32_t* cols, int32_t* elem_bytes, int64_t* payload_off, int64_t* consumed);
+
 const char* xv_last_error(void);
 const char* xv_version(void);
 

@@ -252,3 +252,43 @@ def test_product_package_never_imports_the_oracle():
         if name.endswith(".py"):
             src = open(os.path.join(pkg, name)).read()
             assert "oracle" not in src.replace("the oracle", ""), "%s mentions the oracle package" % name
+
+
+def test_native_ark_index_and_parallel_reader_match_the_stream_parser(model_dir, tmp_path, monkeypatch):
+    """An ark in a regular file goes through xv_ark_scan (native header index over the mmap'ed file) and grouped pread
+    jobs on the reader pool; the x-vectors written must be byte-identical to the in-memory stream path, also when the
+    file holds float64, text and zero-row entries (the scanner hands the text entry and what follows to the parser)."""
+    from xvector_b200 import _native
+    d, _ = model_dir
+    monkeypatch.setenv("XVEC_BATCH_FRAMES", "300")
+    monkeypatch.setattr(models._Batch, "GROUP_BYTES", 20000)          # several pool jobs per batch
+    utts = _utts()
+    buf = io.BytesIO()
+    for i, (k, m) in enumerate(utts.items()):
+        if k == "c":                                                  # a text-form matrix in the middle of the file
+            buf.write((k + "  [\n" + "\n".join(" ".join("%.9g" % v for v in row) for row in m) + " ]\n").encode())
+        else:
+            kaldi_io.write_mat(buf, m.astype(np.float64) if k == "b" else m, key=k)
+    data = buf.getvalue()
+    path = tmp_path / "feats.ark"
+    path.write_bytes(data)
+
+    (key_off, key_len, rows, cols, elem, pay), consumed = _native.ark_scan(data)
+    keys = [data[o:o + n].decode() for o, n in zip(key_off.tolist(), key_len.tolist())]
+    assert keys == ["a", "tooshort", "b", "empty"]                    # stops in front of the text entry "c"
+    assert rows.tolist() == [130, 10, 60, 0] and cols.tolist() == [23, 23, 23, 23] and elem.tolist() == [4, 4, 8, 4]
+    assert data[consumed:consumed + 2] == b"c " and np.array_equal(
+        np.frombuffer(data, "<f4", 130 * 23, int(pay[0])).reshape(130, 23), utts["a"])
+
+    want = io.BytesIO()
+    models.Model().make_embedding(io.BytesIO(data), want, d, 25, 100, True, None)
+    for threads in ("4", "1"):
+        monkeypatch.setenv("XVEC_READER_THREADS", threads)
+        got = io.BytesIO()
+        with open(path, "rb") as f:
+            models.Model().make_embedding(f, got, d, 25, 100, True, None)
+        assert got.getvalue() == want.getvalue() and len(got.getvalue()) > 5 * 512 * 4
+    path.write_bytes(data[:len(data) // 3])                           # truncated payload: the parser's error surfaces
+    monkeypatch.setenv("XVEC_READER_THREADS", "4")
+    with open(path, "rb") as f, pytest.raises(Exception):
+        models.Model().make_embedding(f, io.BytesIO(), d, 25, 100, True, None)

@@ -111,6 +111,8 @@ def load_library():
     lib.xv_last_error.restype = ctypes.c_char_p
     lib.xv_version.argtypes = []
     lib.xv_version.restype = ctypes.c_char_p
+    lib.xv_ark_scan.argtypes = [P, I64, I64, P, P, P, P, P, P, ctypes.POINTER(I64)]
+    lib.xv_ark_scan.restype = I64
     # training step (include/xvec_train.h)
     F32, F64 = ctypes.c_float, ctypes.c_double
     lib.xv_train_create.argtypes = [ctypes.POINTER(P), P, I32, I32]
@@ -160,7 +162,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = ["xv_create", "xv_destroy", "xv_set_param", "xv_workspace_bytes", "xv_forward",
                     "xv_forward_layers", "xv_extract_host", "xv_submit_host", "xv_collect", "xv_check_overflow", "xv_last_launch_count",
-                    "xv_last_kernel_ms", "xv_set_option", "xv_last_error", "xv_version",
+                    "xv_last_kernel_ms", "xv_set_option", "xv_last_error", "xv_version", "xv_ark_scan",
                     # include/xvec_train.h
                     "xv_train_create", "xv_train_destroy", "xv_train_size", "xv_train_span", "xv_train_upload",
                     "xv_train_download", "xv_train_set_step", "xv_train_get_step", "xv_train_forward_backward", "xv_train_eval",
@@ -173,6 +175,27 @@ EXPORTED_SYMBOLS = ["xv_create", "xv_destroy", "xv_set_param", "xv_workspace_byt
 def _check(lib, rc):
     if rc != XV_OK:
         raise XvecError(rc, lib.xv_last_error().decode(errors="replace"))
+
+
+def ark_scan(buffer, start=0, max_entries=1 << 20):
+    """Index of the binary float matrices of a Kaldi ark held in ``buffer`` (bytes-like, e.g. an mmap) from byte
+    ``start``: (key_off, key_len, rows, cols, elem_bytes, payload_off) numpy arrays -- offsets relative to the start of
+    ``buffer`` -- and the offset of the first byte that was not parsed.  Host-only (xv_ark_scan); needs no GPU."""
+    lib = load_library()
+    view = np.frombuffer(buffer, dtype=np.uint8)
+    n_max = int(min(max_entries, max(1, (view.shape[0] - start) // 16 + 1)))
+    key_off = np.empty(n_max, np.int64)
+    key_len = np.empty(n_max, np.int32)
+    rows = np.empty(n_max, np.int32)
+    cols = np.empty(n_max, np.int32)
+    elem = np.empty(n_max, np.int32)
+    pay = np.empty(n_max, np.int64)
+    consumed = ctypes.c_int64(0)
+    n = int(lib.xv_ark_scan(view.ctypes.data + start, view.shape[0] - start, n_max, key_off.ctypes.data, key_len.ctypes.data,
+                            rows.ctypes.data, cols.ctypes.data, elem.ctypes.data, pay.ctypes.data, ctypes.byref(consumed)))
+    if n < 0:
+        raise XvecError(XV_EINVAL, "xv_ark_scan: bad argument")
+    return (key_off[:n] + start, key_len[:n], rows[:n], cols[:n], elem[:n], pay[:n] + start), start + int(consumed.value)
 
 
 class XvecEngine:

@@ -1111,3 +1111,6 @@ int xv_set_option(xv_model* m, const char* name, int64_t value) {
 
 // ---- feature front end: sliding-window CMVN + voiced-frame selection (include/xvec_frontend.h) ----
 #include "frontend_api.cuh"
+
+// ---- host-only: ark index for the extractor's reader (xv_ark_scan, include/xvec.h) ----
+#include "ark_scan.cuh"

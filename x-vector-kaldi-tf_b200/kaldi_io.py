@@ -24,7 +24,10 @@ from __future__ import annotations
 
 import gzip
 import io
+import mmap
+import os
 import re
+import stat
 import struct
 import subprocess
 import sys
@@ -472,6 +475,48 @@ def read_mat_ark(file_or_fd):
             fd.close()
 
 
+def _plain_file(fd):
+    """True for a buffered reader over a regular file: payloads can then be fetched with pread, by any thread,
+    without touching the stream's position."""
+    try:
+        return isinstance(fd, io.BufferedReader) and stat.S_ISREG(os.fstat(fd.fileno()).st_mode)
+    except (OSError, ValueError, AttributeError):
+        return False
+
+
+class PayloadGroup(object):
+    """A few megabytes of matrix payloads to fetch with pread in ONE job of the extractor's reader pool (a job per matrix
+    costs more in hand-over than the 50 KB read it does).  Every distinct file is duplicated once, while it is certainly
+    still open, so that the scp reader may move on and close it; ``fetch`` closes the duplicates."""
+    __slots__ = ("items", "nbytes", "_dups")
+
+    def __init__(self):
+        self.items, self.nbytes, self._dups = [], 0, {}
+
+    def add(self, fileobj, offset, dst):
+        key = id(fileobj)
+        if key not in self._dups:
+            self._dups[key] = (fileobj, os.dup(fileobj.fileno()))      # the reference to fileobj keeps id() unique
+        self.items.append((self._dups[key][1], offset, dst))
+        self.nbytes += dst.nbytes
+
+    def fetch(self):
+        """Runs on a pool thread: read system calls release the GIL, so groups are read in parallel."""
+        try:
+            for fd, offset, dst in self.items:
+                view = memoryview(dst).cast("B")
+                got, need = 0, len(view)
+                while got < need:
+                    n = os.preadv(fd, [view[got:]], offset + got)
+                    if n <= 0:
+                        raise BadInputFormat("truncated matrix payload at byte %d" % (offset + got))
+                    got += n
+        finally:
+            for _, fd in self._dups.values():
+                os.close(fd)
+            self._dups = {}
+
+
 class MatArkEntry(object):
     """One entry of ``read_mat_ark_entries``: header known, payload not consumed yet.  Exactly one of
     ``read_into`` / ``read`` / ``skip`` must be called before the generator is advanced."""
@@ -515,9 +560,86 @@ class MatArkEntry(object):
         else:
             dst[...] = self.read()
 
+    def detach_payload(self):
+        """For a binary float32 matrix stored in a regular file: move the stream past the payload WITHOUT reading it and
+        return ``(file object, offset)`` for ``PayloadGroup.add``.  ``None`` when the payload has to come through the
+        stream (pipes, gzip, in-memory streams, other matrix kinds)."""
+        nbytes = self.rows * self.cols * 4
+        if self._kind != "FM" or self._done or nbytes == 0 or not _plain_file(self._fd):
+            return None
+        offset = self._fd.tell()
+        self._fd.seek(nbytes, 1)
+        self._done = True
+        return self._fd, offset
+
     def skip(self):
-        if not self._done:
+        if self._done:
+            return
+        if self._kind in ("FM", "DM") and _plain_file(self._fd):
+            self._done = True
+            self._fd.seek(self.rows * self.cols * (4 if self._kind == "FM" else 8), 1)
+        else:
             self.read()
+
+
+class IndexedMatEntry(object):
+    """Entry of ``read_mat_ark_entries_indexed``: same interface as MatArkEntry, but the header came from a native scan
+    of the mmap'ed file and the payload is fetched with pread (nothing goes through the stream)."""
+    __slots__ = ("key", "rows", "cols", "_fd", "_offset", "_elem")
+
+    def __init__(self, key, rows, cols, fd, offset, elem_bytes):
+        self.key, self.rows, self.cols, self._fd, self._offset, self._elem = key, rows, cols, fd, offset, elem_bytes
+
+    def _pread(self, view):
+        got, need, fileno = 0, len(view), self._fd.fileno()
+        while got < need:
+            n = os.preadv(fileno, [view[got:]], self._offset + got)
+            if n <= 0:
+                raise BadInputFormat("truncated matrix for key %r" % self.key)
+            got += n
+
+    def read(self):
+        out = np.empty((self.rows, self.cols), dtype="<f4" if self._elem == 4 else "<f8")
+        if out.size:
+            self._pread(memoryview(out).cast("B"))
+        return out
+
+    def read_into(self, dst):
+        assert dst.shape == (self.rows, self.cols) and dst.dtype == np.float32 and dst.flags.c_contiguous
+        if self._elem == 4 and dst.size:
+            self._pread(memoryview(dst).cast("B"))
+        else:
+            dst[...] = self.read()
+
+    def detach_payload(self):
+        if self._elem != 4 or self.rows * self.cols == 0:
+            return None
+        return self._fd, self._offset
+
+    def skip(self):
+        pass
+
+
+def read_mat_ark_entries_indexed(fd, scan, chunk_entries=1 << 16):
+    """``read_mat_ark_entries`` for an ark in a regular file (``fd``: buffered reader at an entry boundary): headers are
+    indexed ``chunk_entries`` at a time by ``scan(buffer, start, max_entries)`` (the native xv_ark_scan through
+    _native.ark_scan) over the mmap'ed file instead of being parsed one by one; entries the scanner does not know (text,
+    compressed) and everything after them go through the general parser, which also owns the error messages."""
+    pos = fd.tell()
+    size = os.fstat(fd.fileno()).st_size
+    if size > pos:
+        with mmap.mmap(fd.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+            while True:
+                (key_off, key_len, rows, cols, elem, pay), consumed = scan(mm, pos, chunk_entries)
+                keys = [mm[o:o + n].decode() for o, n in zip(key_off.tolist(), key_len.tolist())]
+                for key, r, c, e, p in zip(keys, rows.tolist(), cols.tolist(), elem.tolist(), pay.tolist()):
+                    yield IndexedMatEntry(key, r, c, fd, p, e)
+                pos = consumed
+                if len(keys) < chunk_entries:
+                    break
+    fd.seek(pos)
+    for entry in read_mat_ark_entries(fd):
+        yield entry
 
 
 def read_mat_ark_entries(file_or_fd):
