@@ -576,11 +576,10 @@ class Model(object):
         while ``num_rows`` -- what the reference's loop sees after select-voiced-frames -- is the voiced count."""
         keys_in_order = []
         counters["keys_in_order"] = keys_in_order
-        batch = None
-        ok_index = 0
         # matrices that sit in regular files (an ark on disk, the arks behind a feats.scp) are fetched by a few threads
-        # with pread straight into the page-locked buffer: one thread's read() tops out near 2 GB/s (the copy out of the
-        # page cache), far below what the GPU consumes.  Pipes and in-memory streams keep the sequential path.
+        # with pread straight into the page-locked buffer, 4 MB per job: one thread's header parsing + read() gives
+        # 45 M frames/s on the B200 box's host, the indexed / pooled path 63 M (profiles/r01_reader_throughput.txt), both
+        # well below what the GPU consumes.  Pipes and in-memory streams keep the sequential path.
         n_readers = int(os.environ.get("XVEC_READER_THREADS", str(min(4, max(1, (os.cpu_count() or 2) // 2)))))
         pool = ThreadPoolExecutor(max_workers=n_readers, thread_name_prefix="xvec-pread") if n_readers > 1 else None
         try:
