@@ -259,6 +259,7 @@ def test_native_ark_index_and_parallel_reader_match_the_stream_parser(model_dir,
     jobs on the reader pool; the x-vectors written must be byte-identical to the in-memory stream path, also when the
     file holds float64, text and zero-row entries (the scanner hands the text entry and what follows to the parser)."""
     from xvector_b200 import _native
+    _native.build_library()                                           # no-op when the in-tree library is up to date
     d, _ = model_dir
     monkeypatch.setenv("XVEC_BATCH_FRAMES", "300")
     monkeypatch.setattr(models._Batch, "GROUP_BYTES", 20000)          # several pool jobs per batch
