@@ -475,13 +475,21 @@ def read_mat_ark(file_or_fd):
             fd.close()
 
 
+_last_plain = (None, False)
+
+
 def _plain_file(fd):
     """True for a buffered reader over a regular file: payloads can then be fetched with pread, by any thread,
-    without touching the stream's position."""
+    without touching the stream's position.  (The last answer is remembered: the reader asks once per matrix.)"""
+    global _last_plain
+    if fd is _last_plain[0]:
+        return _last_plain[1]
     try:
-        return isinstance(fd, io.BufferedReader) and stat.S_ISREG(os.fstat(fd.fileno()).st_mode)
+        plain = isinstance(fd, io.BufferedReader) and stat.S_ISREG(os.fstat(fd.fileno()).st_mode)
     except (OSError, ValueError, AttributeError):
-        return False
+        plain = False
+    _last_plain = (fd, plain)
+    return plain
 
 
 class PayloadGroup(object):
@@ -715,22 +723,82 @@ class _RxFileCache(object):
         self.path, self.fd = None, None
 
 
+class _MappedFiles(object):
+    """The regular files an scp table points into, opened and mmap'ed once each and kept until ``close``: headers are
+    then parsed from memory (no seek / read system calls per entry) and payloads fetched with pread."""
+
+    def __init__(self):
+        self._open = {}
+
+    def get(self, path):
+        """(file object, mmap) or (None, None) when ``path`` is not a plain, non-empty, uncompressed file."""
+        hit = self._open.get(path)
+        if hit is None:
+            hit = (None, None)
+            if not path.endswith(".gz") and os.path.isfile(path):
+                f = open(path, "rb")
+                if _plain_file(f) and os.fstat(f.fileno()).st_size > 0:
+                    hit = (f, mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ))
+                else:
+                    f.close()
+            self._open[path] = hit
+        return hit
+
+    def close(self):
+        for f, mm in self._open.values():
+            if mm is not None:
+                mm.close()
+                f.close()
+        self._open = {}
+
+
+def _split_rxfile(rxfile):
+    """('path', offset) of an scp target of the form ``path:offset``; (None, None) for pipes and offset-less names."""
+    rxfile = rxfile.strip()
+    if rxfile.endswith("|") or not _OFFSET_RE.search(rxfile):
+        return None, None
+    path, offset = rxfile.rsplit(":", 1)
+    return path, int(offset)
+
+
+def _mapped_mat_entry(mm, fileobj, key, offset):
+    """IndexedMatEntry for the binary float matrix whose '\0B' flag is at ``offset`` of the mapped file, or None when
+    something else is stored there (text, compressed: the stream parser takes over)."""
+    hdr = mm[offset:offset + 15]
+    if len(hdr) < 15 or hdr[0:2] != b"\0B" or hdr[2:5] not in (b"FM ", b"DM ") or hdr[5] != 4 or hdr[10] != 4:
+        return None
+    rows, cols = struct.unpack_from("<i", hdr, 6)[0], struct.unpack_from("<i", hdr, 11)[0]
+    elem = 4 if hdr[2:3] == b"F" else 8
+    if rows < 0 or cols < 0 or offset + 15 + rows * cols * elem > len(mm):
+        raise BadInputFormat("truncated matrix for key %r" % key)
+    return IndexedMatEntry(key, rows, cols, fileobj, offset + 15, elem)
+
+
 def read_mat_scp_entries(file_or_fd):
     """read_mat_ark_entries over an scp table (``key rxfilename[:offset]`` lines, reference kaldi_io.py:350-369): what
     ``scp:data/feats.scp`` means as a feature rspecifier when the feature front end runs on the device."""
     fd = open_or_fd(file_or_fd)
     cache = _RxFileCache()
+    files = _MappedFiles()
     try:
         for line in fd:
             line = line.decode() if isinstance(line, bytes) else line
             if not line.strip():
                 continue
             key, rxfile = line.rstrip("\n").split(" ", 1)
-            entry = _entry_at(cache.seek(rxfile), key)
+            path, offset = _split_rxfile(rxfile)
+            entry = None
+            if path is not None:
+                fileobj, mm = files.get(path)
+                if mm is not None:
+                    entry = _mapped_mat_entry(mm, fileobj, key, offset)
+            if entry is None:                            # pipes, gzip, text / compressed matrices
+                entry = _entry_at(cache.seek(rxfile), key)
             yield entry
             entry.skip()
     finally:
         cache.close()
+        files.close()
         if fd is not file_or_fd:
             fd.close()
 
@@ -742,6 +810,7 @@ class VecTable(object):
 
     def __init__(self, rspecifier):
         self._cache = _RxFileCache()
+        self._files = _MappedFiles()
         self._table = None
         self._iter = None
         self._pending = None
@@ -761,7 +830,20 @@ class VecTable(object):
         """The vector stored under ``key`` or None."""
         if self._table is not None:
             rxfile = self._table.get(key)
-            return None if rxfile is None else read_vec_flt(self._cache.seek(rxfile))
+            if rxfile is None:
+                return None
+            path, offset = _split_rxfile(rxfile)
+            if path is not None:
+                _, mm = self._files.get(path)
+                if mm is not None:
+                    hdr = mm[offset:offset + 10]
+                    if len(hdr) == 10 and hdr[0:2] == b"\0B" and hdr[2:5] in (b"FV ", b"DV ") and hdr[5] == 4:
+                        dtype = np.dtype("<f4" if hdr[2:3] == b"F" else "<f8")
+                        dim = struct.unpack_from("<i", hdr, 6)[0]
+                        if dim < 0 or offset + 10 + dim * dtype.itemsize > len(mm):
+                            raise BadInputFormat("truncated vector for key %r" % key)
+                        return np.frombuffer(mm, dtype=dtype, count=dim, offset=offset + 10).copy()
+            return read_vec_flt(self._cache.seek(rxfile))
         while True:
             if self._pending is None:
                 self._pending = next(self._iter, None)
@@ -776,6 +858,7 @@ class VecTable(object):
 
     def close(self):
         self._cache.close()
+        self._files.close()
         if self._iter is not None:
             self._iter.close()
 
