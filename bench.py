@@ -409,6 +409,7 @@ def run_b200(args):
     if not args.no_train and topo.get("act", "relu") == "relu" and topo.get("pooling", "stats") == "stats":
         out["train_step"] = measure_train_step(args, dev, rank, world, peaks, topo)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["reader"] = measure_reader()
         out["cpu_baseline"] = cpu_baseline_subprocess(args)
     if world > 1:
         dist.barrier()
@@ -484,6 +485,68 @@ def measure_frontend(args, eng, dev, stream, flush, rank, peaks):
                          voiced_frames_per_sec=round(float(keep.sum()) / (e2e_ms * 1e-3), 1),
                          h2d_bytes_per_step=int(B * T * (FEAT_DIM * 4 + 4) + B * 4 * 3), d2h_bytes_per_step=B * EMB_DIM * 4 + 4),
                 cpu_baseline=cpu)
+
+
+def measure_reader(n_utts=1500, passes=3):
+    """Host side of the ark -> x-vector product path, alone (no kernel runs): Model._read_batches over a configs[2]-like ark
+    FILE (200-1000 frames per utterance, in the page cache) into the page-locked staging buffers, batches dropped by a null
+    consumer; once with the sequential stream parser (one thread) and once with the native header index (xv_ark_scan) +
+    pooled pread jobs (the default for regular files).  Never fails the bench: errors are reported in the block."""
+    import queue
+    import shutil
+    import tempfile
+    from xvector_b200 import kaldi_io, models, synthetic
+    tmp = tempfile.mkdtemp(prefix="xvec_reader_")
+    saved = os.environ.get("XVEC_READER_THREADS")
+    try:
+        path = os.path.join(tmp, "feats.ark")
+        lens = synthetic.lengths_uniform(3, n_utts)
+        with open(path, "wb") as f:
+            for i, n in enumerate(lens):
+                kaldi_io.write_mat(f, synthetic.mfcc(1000 + i, int(n)), key="utt%07d" % i)
+        out = dict(workload="%d utterances of 200-1000 frames x %d (%.0f MB ark file, page cache) -> staging buffers"
+                            % (n_utts, FEAT_DIM, os.path.getsize(path) / 1e6), unit="frames/s")
+        for label, threads in (("sequential_parser_1_thread", "1"), ("indexed_pooled_pread_default", None)):
+            if threads is None:
+                os.environ.pop("XVEC_READER_THREADS", None)
+            else:
+                os.environ["XVEC_READER_THREADS"] = threads
+            model = models.Model.__new__(models.Model)
+            staging = models._Staging(FEAT_DIM, 400000)
+            work = queue.Queue(maxsize=3)
+            counters = dict(total_segments=0, total_segments_len=0, num_fail=0, num_success=0)
+
+            def consume():
+                while True:
+                    b = work.get()
+                    if b is None:
+                        return
+                    staging.release(b.slot)
+
+            th = threading.Thread(target=consume)
+            th.start()
+            try:
+                with open(path, "rb") as f:                      # warm-up: page cache, staging buffers
+                    model._read_batches(f, staging, work, counters, 25, 10000, 400000, 0, 1, None)
+                counters["total_segments_len"] = 0
+                t0 = time.perf_counter()
+                for _ in range(passes):
+                    with open(path, "rb") as f:
+                        model._read_batches(f, staging, work, counters, 25, 10000, 400000, 0, 1, None)
+                dt = time.perf_counter() - t0
+            finally:
+                work.put(None)
+                th.join()
+            out[label] = round(counters["total_segments_len"] / dt, 1)
+        return out
+    except Exception as err:                                     # noqa: BLE001  (a diagnostic block must not cost the bench line)
+        return dict(error="%s: %s" % (type(err).__name__, err))
+    finally:
+        if saved is None:
+            os.environ.pop("XVEC_READER_THREADS", None)
+        else:
+            os.environ["XVEC_READER_THREADS"] = saved
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 def frontend_cpu_baseline(raw, vad, n_utt, T, seconds=2.0):
