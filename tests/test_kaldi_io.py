@@ -243,3 +243,40 @@ def test_segments_as_bool_vec_matches_the_reference():
     got = kaldi_io.read_segments_as_bool_vec(os.path.join(GOLD, "segments.txt"))
     want = _misc()["segments"]
     assert got.dtype == bool and np.array_equal(got, want) and got.sum() == 45 + 40 + 17
+
+
+def test_native_ark_scan_agrees_with_the_python_parser_on_random_arks():
+    """xv_ark_scan (host-only, loads without a GPU) against read_mat_ark_entries over random archives: same keys, shapes,
+    element sizes and payload bytes; a buffer cut anywhere yields exactly the entries that are whole."""
+    from xvector_b200 import _native
+    rng = np.random.default_rng(12)
+    alphabet = "abcXYZ019._-/"
+    for trial in range(20):
+        buf = io.BytesIO()
+        want = []
+        for i in range(int(rng.integers(1, 12))):
+            key = "".join(rng.choice(list(alphabet), size=int(rng.integers(1, 20))))
+            rows, cols = int(rng.integers(0, 40)), int(rng.integers(1, 30))
+            m = rng.standard_normal((rows, cols)).astype(np.float64 if rng.random() < 0.3 else np.float32)
+            kaldi_io.write_mat(buf, m, key=key)
+            want.append((key, m))
+        data = buf.getvalue()
+        (key_off, key_len, rows, cols, elem, pay), consumed = _native.ark_scan(data)
+        assert consumed == len(data) and len(key_off) == len(want)
+        parsed = [(e.key, e.read()) for e in kaldi_io.read_mat_ark_entries(io.BytesIO(data))]
+        for i, (key, m) in enumerate(want):
+            assert data[key_off[i]:key_off[i] + key_len[i]].decode() == key == parsed[i][0]
+            assert (rows[i], cols[i], elem[i]) == (m.shape[0], m.shape[1], m.dtype.itemsize)
+            got = np.frombuffer(data, m.dtype, m.size, int(pay[i])).reshape(m.shape)
+            assert np.array_equal(got, m) and np.array_equal(parsed[i][1], m)
+        cut = int(rng.integers(0, len(data)))
+        (k2, _, _, _, _, p2), consumed2 = _native.ark_scan(data[:cut])
+        whole = sum(1 for i in range(len(want)) if int(pay[i]) + want[i][1].nbytes <= cut)
+        assert len(k2) == whole and consumed2 <= cut
+        # an offset start: scanning from the second entry
+        if len(want) > 1:
+            start = int(pay[0]) + want[0][1].nbytes
+            (k3, l3, _, _, _, _), c3 = _native.ark_scan(data, start)
+            assert len(k3) == len(want) - 1 and c3 == len(data) and data[k3[0]:k3[0] + l3[0]].decode() == want[1][0]
+    bad = b"bad key! \0BFM \4" + b"\0" * 20                             # a key the reference's regex rejects: scan stops
+    assert len(_native.ark_scan(bad)[0][0]) == 0
