@@ -104,6 +104,26 @@ class ClockSampler(threading.Thread):
     BITS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
             0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
 
+    _nvml = {}      # cuda index -> (pynvml, handle, sm_max) or an error string; filled ONCE per process (nvmlInit and the
+                    # handle lookup serialise across the processes of a node: r1 paid them inside the timed window)
+
+    @classmethod
+    def prepare(cls, cuda_index):
+        if cuda_index in cls._nvml:
+            return
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(cuda_index).uuid)
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(cuda_index)
+            cls._nvml[cuda_index] = (pynvml, h, int(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)))
+        except Exception as e:      # clocks are evidence, not the product: report why they are missing
+            cls._nvml[cuda_index] = repr(e)
+
     def __init__(self, cuda_index, period=0.004):
         super().__init__(daemon=True)
         self.period = period
@@ -111,20 +131,13 @@ class ClockSampler(threading.Thread):
         self.sm_max = None
         self._stop_evt = threading.Event()
         self.ok = False
-        try:
-            import pynvml
-            import torch
-            self.nv = pynvml
-            pynvml.nvmlInit()
-            uuid = str(torch.cuda.get_device_properties(cuda_index).uuid)
-            try:
-                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
-            except Exception:
-                self.h = pynvml.nvmlDeviceGetHandleByIndex(cuda_index)
-            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        self.prepare(cuda_index)
+        st = self._nvml[cuda_index]
+        if isinstance(st, str):
+            self.err = st
+        else:
+            self.nv, self.h, self.sm_max = st
             self.ok = True
-        except Exception as e:      # clocks are evidence, not the product: report why they are missing
-            self.err = repr(e)
 
     def run(self):
         if not self.ok:
@@ -198,6 +211,7 @@ def run_b200(args):
     for kv in args.option:
         eng.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 
+    ClockSampler.prepare(local_rank)               # nvmlInit + handle lookup OUTSIDE every timed window
     B, T = args.batch, args.frames
     lens = np.full(B, T, np.int32)
     frames = int(lens.sum())
@@ -207,10 +221,19 @@ def run_b200(args):
     emb_host = torch.empty((B, EMB_DIM), dtype=torch.float32, pin_memory=True)
     feats_dev = feats_host.to(dev)
     emb_dev = torch.empty((B, EMB_DIM), dtype=torch.float32, device=dev)
-    # N > 1: like make_embedding, every rank keeps its embeddings and ONE gather to rank 0 ends the job
-    # (models.py gathers once per extraction, not per batch); the gather is inside the timed region.
-    emb_all = torch.empty((args.steps, B, EMB_DIM), dtype=torch.float32, device=dev) if world > 1 else None
-    gathered = [torch.empty_like(emb_all) for _ in range(world)] if (world > 1 and rank == 0) else None
+    # N > 1: rank 0 owns the job's result table [N x steps x B, 512] in its HBM, every rank maps it (CUDA IPC) and the
+    # kernel that finishes a batch (utt_average_kernel) stores its rows straight into the table over NVLink: the
+    # "gather to rank 0" is that store, there is no end-of-job collective (r1 had one dist.gather, whose window soaked
+    # up 12 ms of rank skew at N = 8).  A barrier after the last step orders the writers before rank 0's read.
+    peer = None
+    if world > 1:
+        table_rows = world * args.steps * B
+        if rank == 0:
+            peer = _native.PeerTable.create(local_rank, table_rows, EMB_DIM)
+        box = [peer.handle if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        if rank != 0:
+            peer = _native.PeerTable.open(local_rank, table_rows, EMB_DIM, box[0])
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
 
@@ -218,54 +241,59 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
 
+    def out_of(i):
+        """Where step i's x-vectors go: the local buffer (N = 1, warm-up) or this rank's rows of rank 0's table."""
+        if peer is None or i is None:
+            return emb_dev
+        return peer.data_ptr((rank * args.steps + i) * B)
+
     def step_resident(i=None):
-        eng.forward(feats_dev, lens, emb_dev=(emb_dev if (i is None or world == 1) else emb_all[i]), stream=stream)
+        # the product's per-batch call: forward + make_embedding's chunk average (one chunk per utterance here)
+        eng.forward_utts(feats_dev, lens, out_of(i), stream=stream)
 
     feats_host2 = [feats_host, feats_host.clone().pin_memory()]
     emb_host2 = [emb_host, torch.empty_like(emb_host).pin_memory()]
 
-    def finish_e2e(ticket, slot, i):
-        eng.collect(ticket)                                            # embeddings of that step are in emb_host2[slot]
-        if world > 1 and i is not None:
-            emb_all[i].copy_(emb_host2[slot], non_blocking=True)       # staged for the single end-of-job gather
-
     def run_e2e(steps):
-        """K steps through xv_submit_host / xv_collect (pinned host in, pinned host out), two in flight:
+        """K steps through xv_submit_host_utts / xv_collect (pinned host in, pinned host out), two in flight:
         the H2D copy of step i+1 overlaps the kernels of step i.  Returns wall seconds."""
+        timed = steps == args.steps
         t0 = time.perf_counter()
         prev = None
         for i in range(steps):
             slot = i & 1
-            ticket = eng.submit_host(feats_host2[slot], lens, emb_host2[slot])
+            ticket = eng.submit_host_utts(feats_host2[slot], lens, out_host=emb_host2[slot],
+                                          out_dev=(out_of(i) if (timed and peer is not None) else None))
             if prev is not None:
-                finish_e2e(*prev)
-            prev = (ticket, slot, i if steps == args.steps else None)
-        finish_e2e(*prev)
-        if world > 1 and steps == args.steps:
-            dist.gather(emb_all, gathered, dst=0)
+                eng.collect(prev)
+            prev = ticket
+        eng.collect(prev)
+        if world > 1 and timed:
+            dist.barrier()                                             # every rank's rows are in rank 0's table
             if rank == 0:
-                gathered[-1][-1].cpu()                                 # rank 0 reads the job's result
-            torch.cuda.synchronize(dev)
+                peer.read(peer.rows - B, B)                          # rank 0 reads the job's result (last rows: rank N-1's)
         return time.perf_counter() - t0
 
     def timed_resident(steps):
+        sampler = ClockSampler(local_rank)
         barrier(); torch.cuda.synchronize(dev)
-        sampler = ClockSampler(local_rank); sampler.start()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps + 1)]
-        for i, (s, e) in enumerate(evs[:steps]):
+        w0 = time.perf_counter()
+        sampler.start()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for i, (s, e) in enumerate(evs):
             flush.zero_()                                              # evict L2 between steps (untimed)
             s.record(stream)
             step_resident(i)
             e.record(stream)
-        s, e = evs[steps]                                              # the end-of-job gather (N > 1), timed too
-        s.record(stream)
-        if world > 1:
-            dist.gather(emb_all, gathered, dst=0)
-        e.record(stream)
-        torch.cuda.synchronize(dev); barrier()
+        torch.cuda.synchronize(dev)
+        w1 = time.perf_counter()
+        barrier()                                                      # N > 1: all writers done -> the table is complete
+        w2 = time.perf_counter()
         clocks = sampler.finish()
         ms = [s.elapsed_time(e) for s, e in evs]
-        return ms, clocks
+        # own_ms: this rank's wall time for its K steps incl. the untimed L2 flushes; wait_ms: what it then waited for the
+        # slowest rank at the closing barrier (rank skew + barrier latency; there is no data left to move)
+        return ms, clocks, dict(own_ms=(w1 - w0) * 1e3, wait_ms=(w2 - w1) * 1e3)
 
     def timed_e2e(steps):
         barrier(); torch.cuda.synchronize(dev)
@@ -280,21 +308,50 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def all_ranks(x):
+        if world == 1:
+            return [x]
+        t = torch.zeros(world, dtype=torch.float64, device=dev)
+        t[rank] = x
+        dist.all_reduce(t)
+        return [float(v) for v in t.tolist()]
+
     # ---- warm-up, then the timed regions ------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
         step_resident()
-    if world > 1:                                  # warm-up of the collective too (communicator / channel set-up)
-        dist.gather(emb_all, gathered, dst=0)
+    if peer is not None:                          # first touch of the peer mapping
+        step_resident(0)
     torch.cuda.synchronize(dev)
+    barrier()
     eng.check_overflow()
-    ms, clocks = timed_resident(args.steps)
+    ms, clocks, walls = timed_resident(args.steps)
     remeasured = False
     if clocks_rejected(clocks):
         remeasured = True
-        ms, clocks = timed_resident(args.steps)
-    total_ms = max_over_ranks(sum(ms))
+        ms, clocks, walls = timed_resident(args.steps)
+    per_rank_ms = all_ranks(sum(ms))
+    total_ms = max(per_rank_ms)
     ms_per_step = total_ms / args.steps
     value = world * frames / (ms_per_step * 1e-3)
+    multi = None
+    if world > 1:
+        # the job's result as rank 0 sees it: every row of the table written (finite, non-zero), rank 0's own rows
+        # bit-identical to a local run of the same batch
+        ok = None
+        if rank == 0:
+            got = peer.read()
+            step_resident()
+            torch.cuda.synchronize(dev)
+            mine = emb_dev.cpu().numpy()
+            ok = bool(np.isfinite(got).all() and (np.abs(got).max(axis=1) > 0).all()
+                      and all(np.array_equal(got[i * B:(i + 1) * B], mine) for i in range(args.steps)))
+        multi = dict(gather="none: utt_average_kernel stores each batch's rows into rank 0's table over NVLink (CUDA IPC peer "
+                            "mapping); one barrier after the last step",
+                     step_ms_sum_per_rank=[round(v, 4) for v in per_rank_ms],
+                     skew_ms=round(max(per_rank_ms) - min(per_rank_ms), 4),
+                     own_wall_ms_per_rank=[round(v, 3) for v in all_ranks(walls["own_ms"])],
+                     closing_barrier_wait_ms_per_rank=[round(v, 3) for v in all_ranks(walls["wait_ms"])],
+                     table_rows=peer.rows, table_complete_and_rank0_rows_bit_identical=ok)
 
     run_e2e(max(args.warmup, 3))
     e2e_total = max_over_ranks(timed_e2e(args.steps))
@@ -332,7 +389,7 @@ def run_b200(args):
         step_resident()
     for _ in range(min(args.steps, 50)):
         flush.zero_()
-        eng.forward(feats_dev, lens, emb_dev=emb_dev, stream=stream)
+        eng.forward_utts(feats_dev, lens, emb_dev, stream=stream)
         per_launch.append(eng.last_kernel_ms())
     eng.set_option("profile", 0)
     launches_per_step = eng.last_launch_count
@@ -354,11 +411,12 @@ def run_b200(args):
                   ("attn_softmax_kernel", "hbm", frames * (2 * (c_last // 256) + 2) * 4),
                   ("attn_pool_kernel", "hbm", frames * c_last * 2 + n_blk * 2 * c_last * 4)]
     table += [("pool_stats_kernel", "hbm", n_blk * 2 * c_last * 4 + B * 2 * c_last * 6)]
-    if len(kms) == len(table) + 2:      # embed_layer-0 on tensor cores: split-fp16 GEMM (3 products) + K-split reduction
+    if len(kms) == len(table) + 3:      # embed_layer-0 on tensor cores: split-fp16 GEMM (3 products) + K-split reduction
         table += [("tdnn_pair_kernel<2>[embed_layer-0]", "tensor", 2 * B * 2 * c_last * EMB_DIM),
                   ("embed_reduce_kernel", "hbm", B * EMB_DIM * 4 * 2)]
     else:
         table += [("embed_fc_kernel", "hbm", B * 2 * c_last * 4 + 2 * c_last * EMB_DIM * 4 + B * EMB_DIM * 4)]
+    table += [("utt_average_kernel", "hbm", B * EMB_DIM * 4 * 2 + B * 16)]      # make_embedding's chunk average -> result rows
     launches = []
     for (name, bound, work), ms in zip(table, kms):
         d = dict(kernel=name, ms=round(float(ms), 5), bound=bound)
@@ -395,16 +453,25 @@ def run_b200(args):
                                                        "taps %s dil %s" % (topo["kernel_sizes"], topo["dilations"]),
                                                        args.weight_set),
                            frames_per_step_per_gpu=frames, l2="flushed between steps (%d MiB write)" % (L2_FLUSH_BYTES >> 20),
-                           parallelism="utterance sharding x%d, one NCCL gather to rank 0 at the end of the job" % world if world > 1 else "single GPU",
+                           parallelism=("utterance sharding x%d; each batch's x-vectors are stored into rank 0's result table over "
+                                        "NVLink peer memory by the kernel that produces them (no gather collective; NCCL only for "
+                                        "barriers)" % world) if world > 1 else "single GPU",
                            arithmetic="fp16 operands (RN), fp32 accumulate (tcgen05 kind::f16), fp32 epilogue/pooling"),
                e2e=dict(value=round(e2e_value, 1), unit=UNIT, h2d_bytes_per_step=frames * FEAT_DIM * 4 + B * 3 * 4,
                         d2h_bytes_per_step=B * EMB_DIM * 4 + 4, ms_per_step=round(e2e_total / args.steps, 5),
-                        api="xv_submit_host / xv_collect, 2 in flight (pinned host buffers; xv_extract_host is the blocking form)"),
+                        api="xv_submit_host_utts / xv_collect, 2 in flight (pinned host buffers in and out"
+                            + ("; rows also stored to rank 0's table, closing barrier + rank 0's read inside the window)" if world > 1 else ")")),
                gpu_launches=int(launches_per_step * args.steps),
                clocks=clocks, roofline=roofline, ragged=ragged, frontend=frontend)
+    if multi is not None:
+        out["multi_gpu"] = multi
     if remeasured:
         out["clocks"]["note"] = "first measurement rejected (throttle reason / low clocks); this is the re-measurement"
 
+    if peer is not None:
+        torch.cuda.synchronize(dev)
+        barrier()
+        peer.close()
     eng.close()
     if not args.no_train and topo.get("act", "relu") == "relu" and topo.get("pooling", "stats") == "stats":
         out["train_step"] = measure_train_step(args, dev, rank, world, peaks, topo)

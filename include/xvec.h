@@ -31,6 +31,7 @@ extern "C" {
 #endif
 
 #define XV_MAX_FRAME_LAYERS 8
+#define XV_ABI_VERSION 2        /* bumped whenever a struct or a signature below changes */
 
 enum {
   XV_OK = 0,
@@ -125,6 +126,39 @@ int xv_submit_host(xv_model* m, const float* feats_host, const int32_t* seg_len_
                    int32_t n_seg, float* emb_host, int32_t* ticket);
 int xv_collect(xv_model* m, int32_t ticket);
 
+/* Utterance-level form of xv_forward: the chunk loop of make_embedding (models.py:398-421) finished on the device.
+ * Segments [utt_first_seg_host[u], utt_first_seg_host[u+1]) are the chunks of utterance u (utt_first_seg_host: [n_utt+1],
+ * HOST, starts at 0, ends at n_seg; NULL = every segment is its own utterance and n_utt is ignored).  Row
+ * utt_dst_row_host[u] (HOST int64; NULL = u) of out_dev receives
+ *     xvector_avg = sum_c float32(len_c) * xvector_c  (chunk order, float32, separately rounded multiply and add)
+ *                   / float32(sum_c len_c)
+ * i.e. exactly the reference's float32 arithmetic, so the row is bit-identical to that loop run over the same chunk
+ * x-vectors.  out_dev may be PEER device memory (xv_peer_open): in a multi-GPU job every rank stores its utterances
+ * straight into rank 0's result table over NVLink and no gather collective is left (replaces the per-job arks +
+ * `cat xvector.*.scp` merge of local/tf/extract_xvectors.sh:83-95).  Enqueue only. */
+int xv_forward_utts(xv_model* m, const float* feats_dev, const int32_t* seg_len_host, int32_t n_seg,
+                    const int32_t* utt_first_seg_host, const int64_t* utt_dst_row_host, int32_t n_utt, float* out_dev,
+                    void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* xv_submit_host with utterance-level output: rows go to out_dev[utt_dst_row_host[u]] (device or peer memory; may be
+ * NULL) and / or contiguously, in utterance order, to out_host[u] (HOST, should be page-locked; may be NULL).
+ * Collected with xv_collect like any other ticket. */
+int xv_submit_host_utts(xv_model* m, const float* feats_host, const int32_t* seg_len_host, int32_t n_seg,
+                        const int32_t* utt_first_seg_host, const int64_t* utt_dst_row_host, int32_t n_utt, float* out_dev,
+                        float* out_host, int32_t* ticket);
+
+/* Peer memory for the result table of a multi-GPU job on one node (one process per GPU).  The owner (rank 0) allocates
+ * `bytes` of device memory and gets a 64-byte handle (a cudaIpcMemHandle_t) to hand to the other processes by any means
+ * (torch.distributed broadcast, a file); they map it with xv_peer_open and pass the mapped pointer as the out_dev of
+ * xv_forward_utts / xv_submit_host_utts.  A writer's rows are visible to the owner once the writer has synchronised its
+ * stream (xv_collect does) and the two processes have met at a barrier.  xv_peer_read is a blocking device->host copy for
+ * owners that hold no other handle on the memory. */
+int xv_peer_alloc(int device, size_t bytes, void** dev_ptr, uint8_t* handle64);
+int xv_peer_open(int device, const uint8_t* handle64, void** dev_ptr);
+int xv_peer_close(int device, void* dev_ptr);
+int xv_peer_free(int device, void* dev_ptr);
+int xv_peer_read(int device, void* dst_host, const void* src_dev, size_t bytes);
+
 /* Returns XV_OK, or XV_EOVERFLOW if any activation exceeded the fp16 range since the last
  * call (synchronises `stream`; clears the flag). */
 int xv_check_overflow(xv_model* m, void* stream);
@@ -157,6 +191,10 @@ int64_t xv_ark_scan(const uint8_t* buf, int64_t len, int64_t max_entries, int64_
 
 const char* xv_last_error(void);
 const char* xv_version(void);
+/* Guards for bindings written against this header: XV_ABI_VERSION of the built library and
+ * sizeof(xv_topology) as the library sees it -- a binding whose struct is shorter must refuse to call xv_create. */
+int32_t xv_abi_version(void);
+size_t xv_topology_size(void);
 
 #ifdef __cplusplus
 }

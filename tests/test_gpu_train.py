@@ -397,6 +397,7 @@ def test_train_one_iteration_through_the_model_surface(tmp_path):
     models.ModelWithoutDropoutTdnn().train_one_iteration(examples_io.TarFileDataLoader(tar), args2, logger)
     with np.load(os.path.join(args2.output_dir, "model.npz")) as z:
         assert abs(float(z["beta1_power:0"][0]) - 0.9 ** 24) < 1e-6
+        assert z["global_adam_step:0"].dtype == np.int64 and int(z["global_adam_step:0"][0]) == 24
     # the trained model extracts
     emb_model = models.ModelWithoutDropoutTdnn()
     emb_model.load_model(None, args2.output_dir, logger)

@@ -293,3 +293,66 @@ def test_native_ark_index_and_parallel_reader_match_the_stream_parser(model_dir,
     monkeypatch.setenv("XVEC_READER_THREADS", "4")
     with open(path, "rb") as f, pytest.raises(Exception):
         models.Model().make_embedding(f, io.BytesIO(), d, 25, 100, True, None)
+
+
+def test_adam_step_counter_survives_the_float32_underflow_of_beta1_power():
+    # 0.9**t stored as float32 is 0.0 from t ~ 990 on; the counter must come from the explicit entry, else
+    # from beta2_power, and a power that reads 0 is a saturated counter -- never step 0
+    from xvector_b200.models import adam_step_from_checkpoint, ADAM_STEP_KEY
+    f32 = lambda v: np.asarray([v], dtype=np.float32)
+    for t in (0, 1, 12, 985, 1000, 5000, 40000):
+        tf_style = {"beta1_power:0": f32(0.9 ** t), "beta2_power:0": f32(0.999 ** t)}
+        got = adam_step_from_checkpoint(tf_style)
+        assert abs(got - t) <= max(1, t // 2000), (t, got)                  # float32 beta2_power: exact to ~0.05 %
+        assert adam_step_from_checkpoint(dict(tf_style, **{ADAM_STEP_KEY: np.asarray([t], np.int64)})) == t
+    assert adam_step_from_checkpoint({"beta1_power:0": f32(0.0), "beta2_power:0": f32(0.0)}) >= 100000
+    assert adam_step_from_checkpoint({"beta1_power:0": f32(0.0)}) >= 100000
+    assert adam_step_from_checkpoint({}) == 0
+
+
+def test_pooled_reader_never_lets_a_dropped_tail_overwrite_the_next_utterance(tmp_path, monkeypatch):
+    # utterances whose tail chunk is dropped (< min_chunk_size) keep only `used` rows in the staging
+    # buffer and the next utterance starts right behind them; payloads are fetched by concurrent pread jobs, so a job must
+    # fetch the kept rows only.  40 utterances of 1050 rows, chunks of 1000, tail of 50 < 100 dropped, many small jobs.
+    import queue
+    import threading
+    monkeypatch.setenv("XVEC_READER_THREADS", "4")
+    monkeypatch.setattr(models._Batch, "GROUP_BYTES", 64 << 10)
+    n_utt, rows = 40, 1050
+    mats = [synthetic.mfcc(300 + i, rows) + np.float32(i) for i in range(n_utt)]
+    path = str(tmp_path / "feats.ark")
+    with open(path, "wb") as f:
+        for i, m in enumerate(mats):
+            kaldi_io.write_mat(f, m, key="utt%03d" % i)
+    for trial in range(5):
+        model = models.Model.__new__(models.Model)
+        staging = models._Staging(23, 8000)
+        work = queue.Queue(maxsize=3)
+        counters = dict(total_segments=0, total_segments_len=0, num_fail=0, num_success=0)
+        seen = []
+
+        def consume():
+            while True:
+                b = work.get()
+                if b is None:
+                    return
+                view = staging.view(b.slot, b.n_frames).copy()
+                off = 0
+                for idx, key, first, lengths in b.utts:
+                    used = sum(lengths)
+                    seen.append((idx, view[off:off + used]))
+                    off += used
+                staging.release(b.slot)
+
+        th = threading.Thread(target=consume)
+        th.start()
+        try:
+            with open(path, "rb") as f:
+                model._read_batches(f, staging, work, counters, 100, 1000, 8000, 0, 1, None)
+        finally:
+            work.put(None)
+            th.join()
+        assert len(seen) == n_utt
+        for idx, got in seen:
+            assert got.shape == (1000, 23)
+            assert np.array_equal(got, mats[idx][:1000]), "utterance %d corrupted in trial %d" % (idx, trial)

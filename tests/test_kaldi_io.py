@@ -280,3 +280,26 @@ def test_native_ark_scan_agrees_with_the_python_parser_on_random_arks():
             assert len(k3) == len(want) - 1 and c3 == len(data) and data[k3[0]:k3[0] + l3[0]].decode() == want[1][0]
     bad = b"bad key! \0BFM \4" + b"\0" * 20                             # a key the reference's regex rejects: scan stops
     assert len(_native.ark_scan(bad)[0][0]) == 0
+
+
+def test_shell_pipes_are_waited_for_and_a_failing_child_fails_the_caller(tmp_path):
+    # the clean-up thread of popen is non-daemon (reference kaldi_io.py:91-95) and wait_for_children /
+    # ze_utils.wait_for_background_commands re-raise a non-zero exit on the caller's thread
+    from xvector_b200 import ze_utils
+    out = str(tmp_path / "late.ark")
+    fd = kaldi_io.open_or_fd("| (sleep 0.4; cat > %s)" % out, "wb")          # a writer that is slow to flush
+    kaldi_io.write_vec_flt(fd, np.arange(4, dtype=np.float32), key="v")
+    fd.close()
+    ze_utils.wait_for_background_commands()                                   # returns only after the child has exited
+    assert dict(kaldi_io.read_vec_flt_ark(out))["v"].tolist() == [0.0, 1.0, 2.0, 3.0]
+    fd = kaldi_io.open_or_fd("| (cat > /dev/null; exit 3)", "wb")
+    fd.write(b"x")
+    fd.close()
+    with pytest.raises(kaldi_io.SubprocessFailed, match="returned 3"):
+        kaldi_io.wait_for_children()
+    kaldi_io.wait_for_children()                                              # reported once, then forgotten
+    src = str(tmp_path / "in.ark")
+    with open(src, "wb") as f:
+        kaldi_io.write_vec_flt(f, np.ones(3, dtype=np.float32), key="a")
+    assert [k for k, _ in kaldi_io.read_vec_flt_ark("cat %s |" % src)] == ["a"]
+    kaldi_io.wait_for_children()

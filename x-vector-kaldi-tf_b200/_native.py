@@ -20,6 +20,7 @@ CSRC = os.path.join(_HERE, "csrc")
 REPO_ROOT = os.path.dirname(_HERE)
 
 XV_MAX_FRAME_LAYERS = 8
+XV_ABI_VERSION = 2
 XV_OK, XV_EINVAL, XV_ECUDA, XV_ENOMEM, XV_ESTATE, XV_EOVERFLOW = 0, -1, -2, -3, -4, -5
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -99,6 +100,28 @@ def load_library():
     lib.xv_submit_host.restype = ctypes.c_int
     lib.xv_collect.argtypes = [P, I32]
     lib.xv_collect.restype = ctypes.c_int
+    lib.xv_forward_utts.argtypes = [P, P, P, I32, P, P, I32, P, P, SZ, P]
+    lib.xv_forward_utts.restype = ctypes.c_int
+    lib.xv_submit_host_utts.argtypes = [P, P, P, I32, P, P, I32, P, P, ctypes.POINTER(I32)]
+    lib.xv_submit_host_utts.restype = ctypes.c_int
+    lib.xv_peer_alloc.argtypes = [ctypes.c_int, SZ, ctypes.POINTER(P), P]
+    lib.xv_peer_alloc.restype = ctypes.c_int
+    lib.xv_peer_open.argtypes = [ctypes.c_int, P, ctypes.POINTER(P)]
+    lib.xv_peer_open.restype = ctypes.c_int
+    lib.xv_peer_close.argtypes = [ctypes.c_int, P]
+    lib.xv_peer_close.restype = ctypes.c_int
+    lib.xv_peer_free.argtypes = [ctypes.c_int, P]
+    lib.xv_peer_free.restype = ctypes.c_int
+    lib.xv_peer_read.argtypes = [ctypes.c_int, P, P, SZ]
+    lib.xv_peer_read.restype = ctypes.c_int
+    lib.xv_abi_version.argtypes = []
+    lib.xv_abi_version.restype = I32
+    lib.xv_topology_size.argtypes = []
+    lib.xv_topology_size.restype = SZ
+    if lib.xv_abi_version() != XV_ABI_VERSION or lib.xv_topology_size() != ctypes.sizeof(XvTopology):
+        raise XvecError(XV_ESTATE, "%s is ABI version %d with a %d-byte xv_topology; this binding is version %d / %d bytes: "
+                                    "rebuild the library" % (LIB_PATH, lib.xv_abi_version(), lib.xv_topology_size(),
+                                                             XV_ABI_VERSION, ctypes.sizeof(XvTopology)))
     lib.xv_check_overflow.argtypes = [P, P]
     lib.xv_check_overflow.restype = ctypes.c_int
     lib.xv_last_launch_count.argtypes = [P]
@@ -163,6 +186,8 @@ def load_library():
 EXPORTED_SYMBOLS = ["xv_create", "xv_destroy", "xv_set_param", "xv_workspace_bytes", "xv_forward",
                     "xv_forward_layers", "xv_extract_host", "xv_submit_host", "xv_collect", "xv_check_overflow", "xv_last_launch_count",
                     "xv_last_kernel_ms", "xv_set_option", "xv_last_error", "xv_version", "xv_ark_scan",
+                    "xv_forward_utts", "xv_submit_host_utts", "xv_peer_alloc", "xv_peer_open", "xv_peer_close", "xv_peer_free",
+                    "xv_peer_read", "xv_abi_version", "xv_topology_size",
                     # include/xvec_train.h
                     "xv_train_create", "xv_train_destroy", "xv_train_size", "xv_train_span", "xv_train_upload",
                     "xv_train_download", "xv_train_set_step", "xv_train_get_step", "xv_train_forward_backward", "xv_train_eval",
@@ -328,6 +353,57 @@ class XvecEngine:
     def collect(self, ticket):
         _check(self.lib, self.lib.xv_collect(self.handle, int(ticket)))
 
+    # ---- utterance-level output (chunk average on the device; destination rows may be peer memory) ----
+    @staticmethod
+    def _utt_plan(n_seg, utt_first_seg, dst_rows):
+        first = None if utt_first_seg is None else np.ascontiguousarray(utt_first_seg, dtype=np.int32)
+        n_utt = n_seg if first is None else int(first.shape[0]) - 1
+        dst = None if dst_rows is None else np.ascontiguousarray(dst_rows, dtype=np.int64)
+        assert dst is None or dst.shape[0] == n_utt
+        return first, dst, n_utt
+
+    def forward_utts(self, feats_dev, seg_lens, out, utt_first_seg=None, dst_rows=None, stream=None):
+        """``forward`` + the frame-weighted chunk average of make_embedding on the device.  ``out``: a float32 CUDA
+        tensor, a ``PeerTable`` or a raw device address; row ``dst_rows[u]`` (default ``u``) receives utterance ``u``."""
+        import torch
+        lens = np.ascontiguousarray(seg_lens, dtype=np.int32)
+        n_seg, total = int(lens.shape[0]), int(lens.sum())
+        assert feats_dev.is_cuda and feats_dev.dtype == torch.float32 and feats_dev.is_contiguous()
+        assert feats_dev.shape[0] == total and feats_dev.shape[1] == self.feat_dim
+        first, dst, n_utt = self._utt_plan(n_seg, utt_first_seg, dst_rows)
+        ws = self._workspace(self.workspace_bytes(total, n_seg))
+        s = torch.cuda.current_stream(feats_dev.device) if stream is None else stream
+        optr = out if isinstance(out, int) else out.data_ptr()
+        _check(self.lib, self.lib.xv_forward_utts(self.handle, feats_dev.data_ptr(), lens.ctypes.data_as(ctypes.c_void_p), n_seg,
+                                                  None if first is None else first.ctypes.data_as(ctypes.c_void_p),
+                                                  None if dst is None else dst.ctypes.data_as(ctypes.c_void_p), n_utt,
+                                                  optr, ws.data_ptr(), ws.numel(), s.cuda_stream))
+        return n_utt
+
+    def submit_host_utts(self, feats_host, seg_lens, utt_first_seg=None, dst_rows=None, out_dev=None, out_host=None):
+        """``submit_host`` with utterance-level output: averaged rows to ``out_dev[dst_rows[u]]`` (CUDA tensor, PeerTable
+        or raw address; may be peer memory) and / or to the host array ``out_host[u]``."""
+        lens = np.ascontiguousarray(seg_lens, dtype=np.int32)
+        n_seg = int(lens.shape[0])
+        if hasattr(feats_host, "data_ptr"):
+            assert feats_host.is_contiguous() and feats_host.shape[0] == int(lens.sum())
+            fptr = feats_host.data_ptr()
+        else:
+            assert feats_host.dtype == np.float32 and feats_host.flags.c_contiguous and feats_host.shape[0] == int(lens.sum())
+            fptr = feats_host.ctypes.data
+        first, dst, n_utt = self._utt_plan(n_seg, utt_first_seg, dst_rows)
+        optr = None if out_dev is None else (out_dev if isinstance(out_dev, int) else out_dev.data_ptr())
+        hptr = None
+        if out_host is not None:
+            assert out_host.shape[0] >= n_utt
+            hptr = out_host.data_ptr() if hasattr(out_host, "data_ptr") else out_host.ctypes.data
+        ticket = ctypes.c_int32(-1)
+        _check(self.lib, self.lib.xv_submit_host_utts(self.handle, fptr, lens.ctypes.data_as(ctypes.c_void_p), n_seg,
+                                                      None if first is None else first.ctypes.data_as(ctypes.c_void_p),
+                                                      None if dst is None else dst.ctypes.data_as(ctypes.c_void_p), n_utt,
+                                                      optr, hptr, ctypes.byref(ticket)))
+        return int(ticket.value)
+
     # ---- feature front end: apply-cmvn-sliding | select-voiced-frames on the device (include/xvec_frontend.h) ----
     def frontend(self, feats_dev, vad_dev, utt_lens, out_keep=None, opts=None, out_dev=None, stream=None):
         """feats_dev: float32 CUDA [sum(utt_lens), feat_dim] raw rows; vad_dev: float32 CUDA [sum(utt_lens)] or None;
@@ -399,6 +475,54 @@ class XvecEngine:
     @property
     def last_launch_count(self):
         return int(self.lib.xv_last_launch_count(self.handle))
+
+
+class PeerTable:
+    """Rank 0's [rows, cols] float32 result table in device memory, mapped into every rank of a one-node job
+    (xv_peer_alloc / xv_peer_open, include/xvec.h).  The owner creates it with ``PeerTable.create`` and hands ``handle``
+    (64 bytes) to the other processes, which map it with ``PeerTable.open``; every rank then passes the table as the
+    ``out`` of ``forward_utts`` / ``submit_host_utts`` and its rows land on rank 0 over NVLink."""
+
+    def __init__(self, device, rows, cols, ptr, handle, owner):
+        self.device, self.rows, self.cols, self.ptr, self.handle, self.owner = device, int(rows), int(cols), ptr, handle, owner
+        self.lib = load_library()
+
+    @classmethod
+    def create(cls, device, rows, cols):
+        lib = load_library()
+        ptr = ctypes.c_void_p()
+        handle = (ctypes.c_uint8 * 64)()
+        _check(lib, lib.xv_peer_alloc(int(device), max(int(rows) * int(cols) * 4, 4), ctypes.byref(ptr), handle))
+        return cls(device, rows, cols, int(ptr.value), bytes(handle), True)
+
+    @classmethod
+    def open(cls, device, rows, cols, handle):
+        lib = load_library()
+        ptr = ctypes.c_void_p()
+        buf = (ctypes.c_uint8 * 64).from_buffer_copy(handle)
+        _check(lib, lib.xv_peer_open(int(device), buf, ctypes.byref(ptr)))
+        return cls(device, rows, cols, int(ptr.value), bytes(handle), False)
+
+    def data_ptr(self, row=0):
+        return self.ptr + int(row) * self.cols * 4
+
+    def read(self, row0=0, n_rows=None, out=None):
+        """Blocking device -> host copy of rows [row0, row0 + n_rows) (the caller has synchronised with the writers)."""
+        n_rows = self.rows - row0 if n_rows is None else int(n_rows)
+        if out is None:
+            out = np.empty((n_rows, self.cols), dtype=np.float32)
+        if n_rows > 0:
+            _check(self.lib, self.lib.xv_peer_read(self.device, out.ctypes.data_as(ctypes.c_void_p),
+                                                   ctypes.c_void_p(self.data_ptr(row0)), n_rows * self.cols * 4))
+        return out
+
+    def close(self):
+        if self.ptr:
+            if self.owner:
+                self.lib.xv_peer_free(self.device, ctypes.c_void_p(self.ptr))
+            else:
+                self.lib.xv_peer_close(self.device, ctypes.c_void_p(self.ptr))
+            self.ptr = 0
 
 
 TRAIN_PARAMS, TRAIN_ADAM_M, TRAIN_ADAM_V, TRAIN_MOVING, TRAIN_GRAD = 0, 1, 2, 3, 4

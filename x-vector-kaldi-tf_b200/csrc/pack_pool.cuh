@@ -199,6 +199,50 @@ __global__ void __launch_bounds__(64) embed_reduce_kernel(const FcReduceArgs a) 
 }
 
 // ------------------------------------------------------------------------------------------
+// Frame-weighted average of the chunk x-vectors of each utterance (make_embedding, models.py:398-421):
+//   xvector_avg = 0; for each chunk: xvector_avg += offset * xvector; xvector_avg /= tot_weight
+// in the reference's own float32 arithmetic and order (separately rounded multiply / add / divide, no FMA), so the
+// result is bit-identical to that loop evaluated on the same chunk x-vectors.  A row goes to out[dst_row[u]] -- which may
+// be PEER memory (rank 0's result table mapped over NVLink: the "gather" of a multi-GPU job is this store) -- and / or
+// to the contiguous out_local[u] (the copy the host reads).
+struct UttAvgArgs {
+  const float* seg_emb;       // [n_seg, E] embed_layer-0 scores per segment (chunk)
+  const int32_t* first_seg;   // [n_utt + 1] segments [first_seg[u], first_seg[u + 1]) are utterance u's chunks
+  const int32_t* seg_len;     // [n_seg] rows of each segment = the reference's `offset`
+  const int64_t* dst_row;     // [n_utt] destination row in `out` (null: u)
+  float* out;                 // may be null
+  float* out_local;           // [n_utt, E], may be null
+  int32_t n_utt, E;
+};
+
+__global__ void __launch_bounds__(128) utt_average_kernel(const UttAvgArgs a) {
+  cudaTriggerProgrammaticLaunchCompletion();
+  cudaGridDependencySynchronize();
+  const int64_t i4 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;          // one float4 of one utterance
+  const int e4 = a.E / 4;
+  if (i4 >= int64_t(a.n_utt) * e4) return;
+  const int u = int(i4 / e4), o4 = int(i4 % e4);
+  const int s0 = __ldg(a.first_seg + u), s1 = __ldg(a.first_seg + u + 1);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  double tot = 0.0;
+  for (int s = s0; s < s1; ++s) {
+    const int len = __ldg(a.seg_len + s);
+    const float w = float(len);
+    const float4 x = __ldcg(reinterpret_cast<const float4*>(a.seg_emb + int64_t(s) * a.E) + o4);
+    acc.x = __fadd_rn(acc.x, __fmul_rn(w, x.x)); acc.y = __fadd_rn(acc.y, __fmul_rn(w, x.y));
+    acc.z = __fadd_rn(acc.z, __fmul_rn(w, x.z)); acc.w = __fadd_rn(acc.w, __fmul_rn(w, x.w));
+    tot += double(len);
+  }
+  const float wt = float(tot);
+  const float4 r = make_float4(__fdiv_rn(acc.x, wt), __fdiv_rn(acc.y, wt), __fdiv_rn(acc.z, wt), __fdiv_rn(acc.w, wt));
+  if (a.out != nullptr) {
+    const int64_t row = a.dst_row != nullptr ? a.dst_row[u] : int64_t(u);
+    reinterpret_cast<float4*>(a.out + row * a.E)[o4] = r;
+  }
+  if (a.out_local != nullptr) reinterpret_cast<float4*>(a.out_local + int64_t(u) * a.E)[o4] = r;
+}
+
+// ------------------------------------------------------------------------------------------
 // embed_layer-0 (tf.nn.xw_plus_b, models.py:495): emb[n_seg, E] = stats[n_seg, K] @ W0[K, E] + b0,
 // the x-vector.  fp32 SIMT GEMM (the 1e-3 parity budget leaves no room for 16-bit statistics):
 // split over K; the last CTA of a tile adds the K-splits in a fixed order, so every output is

@@ -59,6 +59,8 @@ struct Plan {
   int32_t fc_counters = 0;
   int32_t tc_splits = 1;             // K-splits of the tensor-core embedding GEMM
   size_t off_split = 0;
+  size_t off_seg_emb = 0;            // [n_seg, E] per-segment embeddings when the caller asks for utterance averages
+  size_t off_utt = 0;                // utterance plan: first_seg (n_seg + 1 int32, padded) | dst_row (n_seg int64)
   size_t off_score = 0, off_attn = 0;
   size_t off_meta = 0, off_counters = 0, off_valid = 0, off_blk_valid = 0, off_x0 = 0, off_ha = 0, off_hb = 0,
          off_hlast = 0, off_pool_partial = 0, off_stats = 0, off_partial = 0, bytes = 0;
@@ -104,6 +106,11 @@ struct xv_model {
   cudaEvent_t meta_event[META_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
   int64_t meta_cap = 0;
   int meta_next = 0;
+  // same ring for the utterance plan of xv_forward_utts (first_seg | dst_row)
+  int32_t* utt_host[META_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t utt_event[META_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+  int64_t utt_cap = 0;
+  int utt_next = 0;
   // xv_extract_host / xv_submit_host state: two independent submission slots (own stream and device
   // buffers) so that the host->device copy of one batch overlaps the kernels of the previous one
   struct HostSlot {
@@ -181,6 +188,8 @@ Plan make_plan(const xv_model* m, int64_t total_frames, int32_t n_seg) {
   p.off_split = take(size_t(round_up(n_seg, tdnn2::CTA_ROWS)) * 3 * K * 2);   // rows padded to the TMA box (never read back)
   p.off_partial = take(std::max(size_t(p.fc_splits) * n_seg, size_t(p.tc_splits) * std::min<int64_t>(n_seg, FC_GROUP)) *
                        m->topo.emb_dim * 4);
+  p.off_seg_emb = take(size_t(n_seg) * m->topo.emb_dim * 4);
+  p.off_utt = take(size_t(round_up(n_seg + 1, 2)) * 4 + size_t(n_seg) * 8);
   p.bytes = off;
   return p;
 }
@@ -337,6 +346,20 @@ int ensure_meta_capacity(xv_model* m, int64_t n_ints) {
   return XV_OK;
 }
 
+int ensure_utt_capacity(xv_model* m, int64_t n_ints) {
+  if (n_ints <= m->utt_cap) return XV_OK;
+  const int64_t cap = std::max<int64_t>(n_ints * 2, 4096);
+  for (int s = 0; s < META_SLOTS; ++s) {
+    if (m->utt_event[s]) XV_CUDA(cudaEventSynchronize(m->utt_event[s]));
+    if (m->utt_host[s]) XV_CUDA(cudaFreeHost(m->utt_host[s]));
+    m->utt_host[s] = nullptr;
+    XV_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&m->utt_host[s]), size_t(cap) * 4, cudaHostAllocDefault));
+    if (!m->utt_event[s]) XV_CUDA(cudaEventCreateWithFlags(&m->utt_event[s], cudaEventDisableTiming));
+  }
+  m->utt_cap = cap;
+  return XV_OK;
+}
+
 // Profiling (opt_profile): an event pair around every launch, on the launching stream.
 int prof_mark(xv_model* m, cudaStream_t stream) {
   if (!m->opt_profile) return XV_OK;
@@ -420,11 +443,35 @@ int stage_meta(xv_model* m, const int32_t* seg_len_host, int32_t n_seg, int64_t 
   return XV_OK;
 }
 
+// Utterance-level output of a forward (xv_forward_utts): the frame-weighted chunk average of make_embedding
+// (models.py:398-421), written to scattered rows of `out_dev` (possibly peer memory) and / or contiguously to `out_local_dev`.
+struct UttOut {
+  const int32_t* first_seg_host = nullptr;   // [n_utt + 1], null: every segment is its own utterance
+  const int64_t* dst_row_host = nullptr;     // [n_utt], null: row u
+  int32_t n_utt = 0;
+  float* out_dev = nullptr;
+  float* out_local_dev = nullptr;
+};
+
 int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_host, int32_t n_seg, float* emb_dev,
                  void* workspace_dev, size_t workspace_bytes, cudaStream_t stream, float* const* layer_out_dev,
-                 float* stats_out_dev) {
-  if (!m || !feats_dev || !seg_len_host || !emb_dev || !workspace_dev) return fail(XV_EINVAL, "null argument");
+                 float* stats_out_dev, const UttOut* utt = nullptr) {
+  if (!m || !feats_dev || !seg_len_host || (!emb_dev && !utt) || !workspace_dev) return fail(XV_EINVAL, "null argument");
   if (n_seg <= 0) return fail(XV_EINVAL, "n_seg must be >= 1");
+  if (utt) {
+    if (!utt->out_dev && !utt->out_local_dev) return fail(XV_EINVAL, "utterance output: no destination");
+    const int32_t nu = utt->first_seg_host ? utt->n_utt : n_seg;
+    if (nu <= 0 || nu > n_seg) return fail(XV_EINVAL, "n_utt must be in [1, n_seg]");
+    if (utt->first_seg_host) {
+      if (utt->first_seg_host[0] != 0 || utt->first_seg_host[nu] != n_seg)
+        return fail(XV_EINVAL, "utt_first_seg must start at 0 and end at n_seg");
+      for (int u = 0; u < nu; ++u)
+        if (utt->first_seg_host[u + 1] <= utt->first_seg_host[u]) return fail(XV_EINVAL, "utt_first_seg must be strictly increasing");
+    }
+    if (utt->dst_row_host)
+      for (int u = 0; u < nu; ++u)
+        if (utt->dst_row_host[u] < 0) return fail(XV_EINVAL, "negative destination row");
+  }
   XV_CUDA(cudaSetDevice(m->device));
   int rc = finalize_params(m);
   if (rc != XV_OK) return rc;
@@ -447,6 +494,29 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
   if (rc != XV_OK) return rc;
   const int64_t r_pad = sm.r_pad;                                   // <= p.r_pad (the plan's upper bound)
   const xvk::SegMeta seg = sm.seg;
+  if (utt && !emb_dev) emb_dev = reinterpret_cast<float*>(ws + p.off_seg_emb);
+  const int32_t* utt_first_dev = nullptr;
+  const int64_t* utt_dst_dev = nullptr;
+  const int32_t n_utt = utt ? (utt->first_seg_host ? utt->n_utt : n_seg) : 0;
+  if (utt) {
+    // the utterance plan rides in its own pinned slot (same ring discipline as the segment metadata)
+    const int64_t first_ints = round_up(int64_t(n_seg) + 1, 2);
+    rc = ensure_utt_capacity(m, first_ints + 2 * int64_t(n_seg));
+    if (rc != XV_OK) return rc;
+    const int slot = m->utt_next;
+    m->utt_next = (m->utt_next + 1) % META_SLOTS;
+    XV_CUDA(cudaEventSynchronize(m->utt_event[slot]));
+    int32_t* uh = m->utt_host[slot];
+    if (utt->first_seg_host) std::memcpy(uh, utt->first_seg_host, size_t(n_utt + 1) * 4);
+    else for (int i = 0; i <= n_seg; ++i) uh[i] = i;
+    int64_t* dh = reinterpret_cast<int64_t*>(uh + first_ints);
+    if (utt->dst_row_host) std::memcpy(dh, utt->dst_row_host, size_t(n_utt) * 8);
+    uint8_t* ud = ws + p.off_utt;
+    XV_CUDA(cudaMemcpyAsync(ud, uh, size_t(first_ints) * 4 + (utt->dst_row_host ? size_t(n_utt) * 8 : 0), cudaMemcpyHostToDevice, stream));
+    XV_CUDA(cudaEventRecord(m->utt_event[slot], stream));
+    utt_first_dev = reinterpret_cast<const int32_t*>(ud);
+    if (utt->dst_row_host) utt_dst_dev = reinterpret_cast<const int64_t*>(ud + size_t(first_ints) * 4);
+  }
   const int4* blk_info_dev = sm.blk_info_dev;
 
   uint8_t* row_valid = ws + p.off_valid;
@@ -772,6 +842,23 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       ++launches;
     }
   }
+  if (utt) {
+    xvk::UttAvgArgs a{};
+    a.seg_emb = emb_dev;
+    a.first_seg = utt_first_dev;
+    a.seg_len = seg.len;
+    a.dst_row = utt_dst_dev;
+    a.out = utt->out_dev;
+    a.out_local = utt->out_local_dev;
+    a.n_utt = n_utt;
+    a.E = m->topo.emb_dim;
+    const int64_t n4 = int64_t(n_utt) * a.E / 4;
+    XV_PROF();
+    XV_CUDA(launch_k(pdl, xvk::utt_average_kernel, dim3(unsigned((n4 + 127) / 128)), dim3(128), 0, stream, a));
+    XV_PROF();
+    XV_CUDA(cudaGetLastError());
+    ++launches;
+  }
   m->last_launches = launches;
 #undef XV_PROF
   return XV_OK;
@@ -782,7 +869,9 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
 extern "C" {
 
 const char* xv_last_error(void) { return g_err.c_str(); }
-const char* xv_version(void) { return "xvec_b200 0.1 (sm_100a; tcgen05 + TMA)"; }
+const char* xv_version(void) { return "xvec_b200 0.2 (sm_100a; tcgen05 + TMA)"; }
+int32_t xv_abi_version(void) { return XV_ABI_VERSION; }
+size_t xv_topology_size(void) { return sizeof(xv_topology); }
 
 int xv_create(xv_model** out, int device, const xv_topology* topo) {
   if (!out || !topo) return fail(XV_EINVAL, "null argument");
@@ -914,6 +1003,8 @@ void xv_destroy(xv_model* m) {
   for (int s = 0; s < META_SLOTS; ++s) {
     if (m->meta_host[s]) cudaFreeHost(m->meta_host[s]);
     if (m->meta_event[s]) cudaEventDestroy(m->meta_event[s]);
+    if (m->utt_host[s]) cudaFreeHost(m->utt_host[s]);
+    if (m->utt_event[s]) cudaEventDestroy(m->utt_event[s]);
   }
   for (cudaEvent_t e : m->prof_events) cudaEventDestroy(e);
   cudaFree(m->overflow_dev);
@@ -1000,9 +1091,11 @@ int xv_forward_layers(xv_model* m, const float* feats_dev, const int32_t* seg_le
                       static_cast<cudaStream_t>(stream), layer_out_dev, stats_out_dev);
 }
 
-int xv_submit_host(xv_model* m, const float* feats_host, const int32_t* seg_len_host, int32_t n_seg, float* emb_host,
-                   int32_t* ticket) {
-  if (!m || !feats_host || !seg_len_host || !emb_host || !ticket) return fail(XV_EINVAL, "null argument");
+namespace {
+// Common body of xv_submit_host / xv_submit_host_utts.
+int submit_impl(xv_model* m, const float* feats_host, const int32_t* seg_len_host, int32_t n_seg, float* emb_host,
+                const UttOut* utt_in, float* utt_host_out, int32_t* ticket) {
+  if (!m || !feats_host || !seg_len_host || !ticket) return fail(XV_EINVAL, "null argument");
   if (n_seg <= 0) return fail(XV_EINVAL, "n_seg must be >= 1");
   XV_CUDA(cudaSetDevice(m->device));
   int64_t total = 0;
@@ -1030,13 +1123,106 @@ int xv_submit_host(xv_model* m, const float* feats_host, const int32_t* seg_len_
   XV_CUDA(grow(reinterpret_cast<void**>(&sl.emb_dev), &sl.emb_cap, emb_bytes));
   XV_CUDA(grow(&sl.ws_dev, &sl.ws_cap, ws_bytes));
   XV_CUDA(cudaMemcpyAsync(sl.feats_dev, feats_host, feat_bytes, cudaMemcpyHostToDevice, sl.stream));
-  int rc = forward_impl(m, sl.feats_dev, seg_len_host, n_seg, sl.emb_dev, sl.ws_dev, sl.ws_cap, sl.stream, nullptr, nullptr);
-  if (rc != XV_OK) return rc;
-  XV_CUDA(cudaMemcpyAsync(emb_host, sl.emb_dev, emb_bytes, cudaMemcpyDeviceToHost, sl.stream));
+  int rc;
+  if (utt_in) {
+    UttOut u = *utt_in;
+    const int32_t n_utt = u.first_seg_host ? u.n_utt : n_seg;
+    u.out_local_dev = utt_host_out ? sl.emb_dev : nullptr;       // the slot's buffer holds the rows the host reads
+    rc = forward_impl(m, sl.feats_dev, seg_len_host, n_seg, nullptr, sl.ws_dev, sl.ws_cap, sl.stream, nullptr, nullptr, &u);
+    if (rc != XV_OK) return rc;
+    if (utt_host_out)
+      XV_CUDA(cudaMemcpyAsync(utt_host_out, sl.emb_dev, size_t(n_utt) * m->topo.emb_dim * 4, cudaMemcpyDeviceToHost, sl.stream));
+  } else {
+    rc = forward_impl(m, sl.feats_dev, seg_len_host, n_seg, sl.emb_dev, sl.ws_dev, sl.ws_cap, sl.stream, nullptr, nullptr);
+    if (rc != XV_OK) return rc;
+    XV_CUDA(cudaMemcpyAsync(emb_host, sl.emb_dev, emb_bytes, cudaMemcpyDeviceToHost, sl.stream));
+  }
   XV_CUDA(cudaMemcpyAsync(sl.overflow_host, m->overflow_dev, 4, cudaMemcpyDeviceToHost, sl.stream));
   sl.busy = true;
   m->slot_next = (si + 1) % XV_HOST_SLOTS;
   *ticket = si;
+  return XV_OK;
+}
+}  // namespace
+
+int xv_submit_host(xv_model* m, const float* feats_host, const int32_t* seg_len_host, int32_t n_seg, float* emb_host,
+                   int32_t* ticket) {
+  if (!emb_host) return fail(XV_EINVAL, "null argument");
+  return submit_impl(m, feats_host, seg_len_host, n_seg, emb_host, nullptr, nullptr, ticket);
+}
+
+int xv_forward_utts(xv_model* m, const float* feats_dev, const int32_t* seg_len_host, int32_t n_seg,
+                    const int32_t* utt_first_seg_host, const int64_t* utt_dst_row_host, int32_t n_utt, float* out_dev,
+                    void* workspace_dev, size_t workspace_bytes, void* stream) {
+  if (!out_dev) return fail(XV_EINVAL, "null argument");
+  UttOut u;
+  u.first_seg_host = utt_first_seg_host;
+  u.dst_row_host = utt_dst_row_host;
+  u.n_utt = n_utt;
+  u.out_dev = out_dev;
+  return forward_impl(m, feats_dev, seg_len_host, n_seg, nullptr, workspace_dev, workspace_bytes,
+                      static_cast<cudaStream_t>(stream), nullptr, nullptr, &u);
+}
+
+int xv_submit_host_utts(xv_model* m, const float* feats_host, const int32_t* seg_len_host, int32_t n_seg,
+                        const int32_t* utt_first_seg_host, const int64_t* utt_dst_row_host, int32_t n_utt, float* out_dev,
+                        float* out_host, int32_t* ticket) {
+  if (!out_dev && !out_host) return fail(XV_EINVAL, "xv_submit_host_utts: no destination (out_dev and out_host are both null)");
+  UttOut u;
+  u.first_seg_host = utt_first_seg_host;
+  u.dst_row_host = utt_dst_row_host;
+  u.n_utt = n_utt;
+  u.out_dev = out_dev;
+  return submit_impl(m, feats_host, seg_len_host, n_seg, nullptr, &u, out_host, ticket);
+}
+
+// ---- peer memory (one node, one process per GPU): rank 0's result table mapped into every rank ----
+int xv_peer_alloc(int device, size_t bytes, void** dev_ptr, uint8_t* handle64) {
+  if (!dev_ptr || !handle64 || bytes == 0) return fail(XV_EINVAL, "bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  XV_CUDA(cudaSetDevice(device));
+  void* p = nullptr;
+  XV_CUDA(cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return fail(XV_ECUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+  }
+  std::memcpy(handle64, &h, 64);
+  *dev_ptr = p;
+  return XV_OK;
+}
+
+int xv_peer_open(int device, const uint8_t* handle64, void** dev_ptr) {
+  if (!dev_ptr || !handle64) return fail(XV_EINVAL, "bad argument");
+  XV_CUDA(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  XV_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *dev_ptr = p;
+  return XV_OK;
+}
+
+int xv_peer_close(int device, void* dev_ptr) {
+  if (!dev_ptr) return XV_OK;
+  XV_CUDA(cudaSetDevice(device));
+  XV_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+  return XV_OK;
+}
+
+int xv_peer_free(int device, void* dev_ptr) {
+  if (!dev_ptr) return XV_OK;
+  XV_CUDA(cudaSetDevice(device));
+  XV_CUDA(cudaFree(dev_ptr));
+  return XV_OK;
+}
+
+int xv_peer_read(int device, void* dst_host, const void* src_dev, size_t bytes) {
+  if (!dst_host || !src_dev) return fail(XV_EINVAL, "null argument");
+  XV_CUDA(cudaSetDevice(device));
+  XV_CUDA(cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost));
   return XV_OK;
 }
 

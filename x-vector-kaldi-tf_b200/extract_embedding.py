@@ -150,6 +150,9 @@ def eval_dnn(args):
         finally:
             if frontend.get("vad_table") is not None:
                 frontend["vad_table"].close()
+    # both streams are closed: a `| copy-vector ark:- ark,scp:A.tmp.ark,S.tmp.scp` writer (or the feature pipe) must have
+    # exited -- successfully -- before its files are renamed; a non-zero exit fails the job here
+    kaldi_io.wait_for_children()
     _publish_outputs(ark, scp)
 
 

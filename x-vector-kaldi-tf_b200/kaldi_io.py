@@ -67,11 +67,18 @@ class SubprocessFailed(Exception):
 # --------------------------------------------------------------------------------------
 # opening streams
 
+_children = []                 # one record per shell pipe opened by popen: {"cmd", "proc", "thread", "ret"}
+_children_lock = threading.Lock()
+
+
 def popen(cmd, mode="rb"):
     """Run ``cmd`` through the shell and return the pipe end matching ``mode``.
 
-    A watcher thread raises SubprocessFailed when the child exits non-zero (reference
-    kaldi_io.py:84-117).
+    As in the reference (kaldi_io.py:84-117) a NON-daemon clean-up thread waits for the child and raises SubprocessFailed
+    when it exits non-zero, so the interpreter does not end while e.g. ``| copy-vector ark:- ark,scp:...`` is still
+    flushing.  An exception in a thread cannot fail the job, so the exit status is also recorded and
+    ``wait_for_children`` (called by ze_utils.wait_for_background_commands and before extract_embedding.py publishes its
+    outputs) re-raises it on the caller's thread.
     """
     if not isinstance(cmd, str):
         raise TypeError("invalid cmd type (%s, expected string)" % type(cmd))
@@ -81,15 +88,39 @@ def popen(cmd, mode="rb"):
     proc = subprocess.Popen(cmd, shell=True,
                             stdout=subprocess.PIPE if reading else None,
                             stdin=None if reading else subprocess.PIPE)
+    rec = dict(cmd=cmd, proc=proc, ret=None, thread=None)
 
     def watch():
-        ret = proc.wait()
-        if ret > 0:
-            raise SubprocessFailed("cmd %s returned %d !" % (cmd, ret))
+        rec["ret"] = proc.wait()
+        if rec["ret"] > 0:
+            raise SubprocessFailed("cmd %s returned %d !" % (cmd, rec["ret"]))
 
-    threading.Thread(target=watch, daemon=True).start()
+    rec["thread"] = threading.Thread(target=watch, name="kaldi_io-popen-cleanup")
+    rec["thread"].start()
+    with _children_lock:
+        _children.append(rec)
     pipe = proc.stdout if reading else proc.stdin
     return pipe if mode.endswith("b") else io.TextIOWrapper(pipe)
+
+
+def wait_for_children(timeout=None):
+    """Wait for every child started by ``popen`` to exit (their pipes must have been closed / drained by now) and raise
+    SubprocessFailed for the first one that returned non-zero.  Children still running after ``timeout`` seconds (None =
+    wait for ever, as the reference's thread join does) are left alone and stay registered."""
+    with _children_lock:
+        pending = list(_children)
+    failed = None
+    for rec in pending:
+        rec["thread"].join(timeout)
+        if rec["thread"].is_alive():
+            continue
+        with _children_lock:
+            if rec in _children:
+                _children.remove(rec)
+        if rec["ret"] is not None and rec["ret"] > 0 and failed is None:      # > 0 as the reference: a SIGPIPE'd reader is fine
+            failed = rec
+    if failed is not None:
+        raise SubprocessFailed("cmd %s returned %d !" % (failed["cmd"], failed["ret"]))
 
 
 def open_or_fd(file, mode="rb"):

@@ -36,6 +36,10 @@ from .ze_utils import set_cuda_visible_devices
 VAR2STD_EPSILON = 0.00001       # reference models.py:16
 BN_EPSILON = 1e-3               # reference tf_block.py:9
 META_FORMAT = "xvec-b200-v1"
+# checkpoint entries that are optimizer state, not network variables: Adam slots and beta powers under TF's names, plus the
+# explicit step counter (TF's float32 beta1_power underflows to 0 after ~990 steps, so it cannot carry the counter)
+ADAM_STEP_KEY = "global_adam_step:0"
+OPTIMIZER_STATE_SUFFIXES = ("/Adam:0", "/Adam_1:0", "_power:0", "_step:0")
 
 
 class _Session(object):
@@ -54,7 +58,7 @@ def _create_engine(meta, params, device):
                      bn_eps=BN_EPSILON, var_eps=VAR2STD_EPSILON, activation=meta.get("activation", "relu"),
                      pooling=meta.get("pooling", "stats"))
     # optimizer state saved by train_one_iteration ("<var>/Adam:0", "<var>/Adam_1:0", "beta*_power:0") is not a network variable
-    eng.set_params({k: v for k, v in params.items() if not k.endswith(("/Adam:0", "/Adam_1:0", "_power:0"))})
+    eng.set_params({k: v for k, v in params.items() if not k.endswith(OPTIMIZER_STATE_SUFFIXES)})
     return eng
 
 
@@ -78,6 +82,25 @@ def chunk_plan(num_rows, min_chunk_size, chunk_size):
             continue
         plan.append((chunk_idx * this_chunk_size, offset))
     return plan
+
+
+def adam_step_from_checkpoint(params):
+    """Adam's step counter t of a checkpoint.  Ours carry it explicitly (``global_adam_step:0``, int64).  A checkpoint
+    that only has TensorFlow's ``beta1_power`` / ``beta2_power`` (b^t, float32) gives t back from beta2_power -- 0.999^t is
+    a normal float32 up to t ~ 87 000, while 0.9^t underflows to 0 near t = 990 and loses digits long before; a power
+    that reads 0 is a SATURATED counter, never step 0 (restarting the bias correction while keeping the m / v slots
+    would run every following update at a fraction of the intended learning rate)."""
+    if ADAM_STEP_KEY in params:
+        return int(np.asarray(params[ADAM_STEP_KEY]).reshape(-1)[0])
+    b2p = float(np.asarray(params["beta2_power:0"]).reshape(-1)[0]) if "beta2_power:0" in params else None
+    b1p = float(np.asarray(params["beta1_power:0"]).reshape(-1)[0]) if "beta1_power:0" in params else None
+    if b2p is not None and 0.0 < b2p < 1.0:
+        return int(round(np.log(b2p) / np.log(0.999)))
+    if b1p is not None and 0.0 < b1p < 1.0:
+        return int(round(np.log(b1p) / np.log(0.9)))
+    if (b2p is not None and b2p <= 0.0) or (b1p is not None and b1p <= 0.0):
+        return 1 << 20                      # both powers underflowed: bias correction is 1 to float precision from here on
+    return 0
 
 
 class _Batch(object):
@@ -169,7 +192,8 @@ class Model(object):
         with open(save_path + ".meta", "wt") as fid:
             json.dump(sess.meta, fid, indent=1, sort_keys=True)
         with open(save_path + ".npz", "wb") as fid:
-            np.savez(fid, **{k: np.asarray(v, dtype=np.float32) for k, v in sess.params.items()})
+            np.savez(fid, **{k: (np.asarray(v, dtype=np.int64) if k.endswith("_step:0") else np.asarray(v, dtype=np.float32))
+                             for k, v in sess.params.items()})
         with open(os.path.join(output_dir, "done"), "wt") as fid:
             fid.write("done")
         if logger is not None:
@@ -252,7 +276,7 @@ class Model(object):
         tr = XvecTrainer(eng, self.num_classes, self.embedding_sizes[1])
         if self.l2_beta:
             tr.set_option("l2_beta", self.l2_beta)
-        state = {k: v for k, v in self.params.items() if not k.endswith(self.ADAM_SLOTS) and not k.endswith("_power:0")}
+        state = {k: v for k, v in self.params.items() if not k.endswith(OPTIMIZER_STATE_SUFFIXES)}
         tr.set_params(state)
         for name in state:
             base = name[:-2]
@@ -260,9 +284,7 @@ class Model(object):
                 if base + suffix in self.params:
                     _, off, cnt = tr.span(name)
                     tr.upload(which, self.params[base + suffix], off)
-        if "beta1_power:0" in self.params:          # TF keeps b1^t; recover Adam's step counter t
-            b1p = float(np.asarray(self.params["beta1_power:0"]).reshape(-1)[0])
-            tr.step = int(round(np.log(b1p) / np.log(0.9))) if 0.0 < b1p < 1.0 else 0
+        tr.step = adam_step_from_checkpoint(self.params)
         return eng, tr
 
     def _download_state(self, tr):
@@ -270,7 +292,7 @@ class Model(object):
         from ._native import TRAIN_ADAM_M, TRAIN_ADAM_V
         out = {}
         for name, arr in self.params.items():
-            if name.endswith(self.ADAM_SLOTS) or name.endswith("_power:0"):
+            if name.endswith(OPTIMIZER_STATE_SUFFIXES):
                 continue
             which, off, cnt = tr.span(name)
             shape = np.asarray(arr).shape
@@ -280,6 +302,7 @@ class Model(object):
                 out[name[:-2] + self.ADAM_SLOTS[1]] = tr.download(TRAIN_ADAM_V, off, cnt).reshape(shape)
         out["beta1_power:0"] = np.asarray([0.9 ** tr.step], dtype=np.float32)
         out["beta2_power:0"] = np.asarray([0.999 ** tr.step], dtype=np.float32)
+        out[ADAM_STEP_KEY] = np.asarray([tr.step], dtype=np.int64)
         return out
 
     def _run_minibatches(self, data_loader, tr, eng, logger, training, learning_rate=0.0, print_interval=10, data_parallel=True):
@@ -601,11 +624,13 @@ class Model(object):
             entries = kaldi_io.read_mat_ark_entries_indexed(input_stream, ark_scan)
         else:
             entries = kaldi_io.read_mat_ark_entries(input_stream)
+        debug_lines = logger is not None and logger.isEnabledFor(10)      # logging.DEBUG
         for entry in entries:
             key, num_rows = entry.key, entry.rows
             raw_rows, vad = entry.rows, None
             if logger is not None:
-                logger.debug("Processing features with key '%s' which have shape '%s'" % (key, str((entry.rows, entry.cols))))
+                if debug_lines:
+                    logger.debug("Processing features with key '%s' which have shape '%s'" % (key, str((entry.rows, entry.cols))))
             counters["total_segments"] += 1
             if vad_table is not None:
                 # select-voiced-frames: no VAD / length mismatch / no voiced frame -> the utterance never reaches the network
@@ -654,14 +679,17 @@ class Model(object):
                 batch = None
             if batch is None:
                 batch = _Batch(staging.acquire(max(batch_frames, raw_rows)))
-            # the payload goes straight from the stream into the page-locked buffer (no intermediate copy); rows of a
-            # dropped tail are overwritten by the next utterance
+            # the payload goes straight from the stream into the page-locked buffer (no intermediate copy)
             dst = staging.view(batch.slot, batch.n_frames + raw_rows)[batch.n_frames:]
             span = entry.detach_payload() if pool is not None else None
             if span is not None:
-                batch.fetch_later(pool, span[0], span[1], dst)
+                # pooled pread jobs run concurrently and in any order: every job must own its destination rows.  Without
+                # the device front end only the `used` rows are kept (a tail shorter than min_chunk_size is dropped,
+                # models.py:404-405) and the next utterance starts right behind them, so only those rows are fetched -- a
+                # full-payload read would land on the neighbour's head after the neighbour's own read
+                batch.fetch_later(pool, span[0], span[1], dst if device_frontend else dst[:used])
             else:
-                entry.read_into(dst)
+                entry.read_into(dst)      # sequential stream: the dropped tail is overwritten by the next utterance's read
             first_seg = len(batch.seg_lens)
             for _, length in plan:
                 batch.seg_lens.append(length)

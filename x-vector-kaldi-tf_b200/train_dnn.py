@@ -122,9 +122,12 @@ def get_successful_models(objectives, difference_threshold=1.0):
     return [accepted, max_index + 1]
 
 
+COUNTER_SUFFIXES = ("_power:0", "_step:0")      # Adam's step counters: taken from the first job, never averaged
+
+
 def average_model_dirs(job_dirs, out_dir):
     """Element-wise mean of every array of the jobs' ``model.npz`` (what nnet3-average does for the reference's intended
-    flow, ze_utils.py:176-183); Adam's step counters (beta*_power) are taken from the first job."""
+    flow, ze_utils.py:176-183); Adam's step counters (beta*_power, global_adam_step) are taken from the first job."""
     acc, meta = None, None
     for d in job_dirs:
         with np.load(os.path.join(d, "model.npz")) as z:
@@ -134,14 +137,15 @@ def average_model_dirs(job_dirs, out_dir):
             meta = open(os.path.join(d, "model.meta"), "rt").read()
         else:
             for k in acc:
-                if not k.endswith("_power:0"):
+                if not k.endswith(COUNTER_SUFFIXES):
                     acc[k] += cur[k]
     n = float(len(job_dirs))
     os.makedirs(out_dir, exist_ok=True)
     with open(os.path.join(out_dir, "model.meta"), "wt") as fid:
         fid.write(meta)
     with open(os.path.join(out_dir, "model.npz"), "wb") as fid:
-        np.savez(fid, **{k: (v if k.endswith("_power:0") else v / n).astype(np.float32) for k, v in acc.items()})
+        np.savez(fid, **{k: (np.rint(v).astype(np.int64) if k.endswith("_step:0") else
+                             (v if k.endswith(COUNTER_SUFFIXES) else v / n).astype(np.float32)) for k, v in acc.items()})
     with open(os.path.join(out_dir, "done"), "wt") as fid:
         fid.write("done")
 

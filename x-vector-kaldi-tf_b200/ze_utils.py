@@ -6,8 +6,9 @@
     ``LOCAL_RANK`` (torchrun) / ``XVEC_DEVICE`` and ``use_gpu=False`` only logs a note.
   * ``is_correct_model_dir`` (ze_utils.py:561-567) -- unchanged contract: non-empty
     ``model.meta`` and ``done``.
-  * ``wait_for_background_commands`` (called by extract_embedding.py:157) -- no background
-    commands exist on this path; kept as a no-op so the CLI reads like the reference's.
+  * ``wait_for_background_commands`` (reference ze_utils.py:240-247, called by extract_embedding.py:157) -- joins the
+    clean-up threads of the shell pipes kaldi_io.popen started and, unlike the reference, fails the caller when a child
+    exited non-zero (an exception inside a thread cannot).
 """
 from __future__ import annotations
 
@@ -25,8 +26,9 @@ def pick_device():
 
 def set_cuda_visible_devices(use_gpu=True, logger=None):
     if not use_gpu and logger is not None:
-        logger.info("--use-gpu=no was requested, but this build has no CPU path: "
-                    "running the sm_100a kernels on CUDA device %d." % pick_device())
+        # the reference's own wrapper passes --use-gpu=no (extract_xvectors.sh:72-79): a drop-in run changes device here
+        logger.warning("--use-gpu=no was requested, but this build has no CPU path: "
+                       "running the sm_100a kernels on CUDA device %d." % pick_device())
     elif logger is not None:
         logger.info("Using CUDA device %d" % pick_device())
     return pick_device()
@@ -40,4 +42,5 @@ def is_correct_model_dir(model_dir):
 
 
 def wait_for_background_commands():
-    return None
+    from . import kaldi_io
+    kaldi_io.wait_for_children()
