@@ -647,7 +647,7 @@ def measure_train_step(args, dev, rank, world, peaks, topo):
     feats_host.numpy()[:] = synthetic.mfcc(5 + 1000 * rank, B * T)                      # configs[4]: seed 5
     lab_host = torch.from_numpy(np.random.default_rng(5 + rank).integers(0, NC, B).astype(np.int32)).pin_memory()
     feats, lab = feats_host.to(dev), lab_host.to(dev)
-    grad = torch.zeros(tr.n_params, dtype=torch.float32, device=dev) if world > 1 else None
+    grad = torch.zeros(tr.n_grad, dtype=torch.float32, device=dev) if world > 1 else None
     la_host = torch.zeros(2, dtype=torch.float32, pin_memory=True)
 
     def step(e2e):

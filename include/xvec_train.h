@@ -35,6 +35,7 @@ extern "C" {
 typedef struct xv_trainer xv_trainer;
 
 enum { XV_TRAIN_PARAMS = 0, XV_TRAIN_ADAM_M = 1, XV_TRAIN_ADAM_V = 2, XV_TRAIN_MOVING = 3, XV_TRAIN_GRAD = 4 };
+#define XV_TRAIN_GRAD_TAIL 4     /* floats behind the gradient: [0] = the step's gradient-overflow flag (see xv_train_apply) */
 
 /* Replaces Model.build_model's graph construction for training (models.py:441-534): the frame-level topology is
  * the xv_model's; emb1_dim = embedding_sizes[1] (512), num_classes = width of "output/w".  The xv_model supplies
@@ -59,7 +60,7 @@ int64_t xv_train_get_step(const xv_trainer* t);
 /* Forward + backward of one minibatch (the loss/accuracy/gradient half of models.py:263).
  *   feats_dev   [n_seg * seg_len, feat_dim] fp32 on the device (input_x, every segment seg_len rows)
  *   labels_dev  [n_seg] int32 class ids on the device (the argmax of input_y's one-hot rows, models.py:164-169)
- *   grad_dev    [xv_train_size(PARAMS)] fp32 out, or NULL to use the trainer's own buffer (XV_TRAIN_GRAD)
+ *   grad_dev    [xv_train_size(XV_TRAIN_GRAD)] fp32 out (gradient + XV_TRAIN_GRAD_TAIL floats), or NULL to use the trainer's own buffer (XV_TRAIN_GRAD)
  *   loss_acc_dev [2] fp32 out: mean cross-entropy, accuracy
  * Also applies the moving-statistics update of every BatchNorm (tf_block.py:20-21).  Enqueue only. */
 int xv_train_forward_backward(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, int32_t n_seg,
@@ -70,9 +71,17 @@ int xv_train_eval(xv_trainer* t, const float* feats_dev, const int32_t* labels_d
                   float* loss_acc_dev, void* stream);
 /* Adam update (the optimizer half of models.py:263) with gradient grad_dev * grad_scale (NULL = own buffer;
  * grad_scale = 1/world_size after a sum all-reduce), then refreshes the fp16 operand copies.  Enqueue only.
- * If a loss-scaled fp16 gradient overflowed since the last xv_check_overflow(model), the update is skipped on the device
- * (variables and slots untouched); the caller sees XV_EOVERFLOW from xv_check_overflow and lowers "loss_scale". */
+ * grad_dev holds xv_train_size(XV_TRAIN_GRAD) = n_params + XV_TRAIN_GRAD_TAIL floats: behind the gradient rides the
+ * step's gradient-overflow flag (0 / 1, written by xv_train_forward_backward), so that a data-parallel caller's sum
+ * all-reduce of the WHOLE buffer combines it over the ranks.  If the combined flag is non-zero -- a loss-scaled fp16
+ * gradient left the fp16 range on any rank -- the update is skipped on the device on every rank alike (variables and slots
+ * untouched) and counted; the caller reads the count with xv_train_skipped_updates and lowers "loss_scale".  Overflow of
+ * a forward ACTIVATION is a different condition (no loss scale can help): it is the xv_model's flag, reported by
+ * xv_check_overflow. */
 int xv_train_apply(xv_trainer* t, const float* grad_dev, float learning_rate, float grad_scale, void* stream);
+/* Updates skipped so far because of gradient overflow.  blocking = 0: never waits -- returns the newest value whose
+ * read-back has landed and starts another read-back on `stream` (call once per step); blocking = 1: synchronises. */
+int64_t xv_train_skipped_updates(xv_trainer* t, void* stream, int32_t blocking);
 
 /* Copies the current variables and moving statistics into the xv_model, so that xv_forward / xv_extract_host
  * evaluate the trained network: what Model.save_model + load_model do between train and extract. */

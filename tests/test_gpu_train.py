@@ -445,20 +445,48 @@ def test_overflowing_gradients_skip_the_update_and_a_lower_loss_scale_recovers()
     p = Problem("ModelWithoutDropoutTdnn", "B", 8, 64, 50)
     try:
         before = p.tr.download(p.native.TRAIN_PARAMS)
+        assert p.tr.n_grad == p.tr.n_params + 4 and p.tr.skipped_updates(blocking=True) == 0
         p.tr.set_option("loss_scale", 2.0 ** 40)                 # absurd: every frame-level gradient overflows fp16
         p.tr.forward_backward(p.feats, p.lab, p.B, p.T)
         p.tr.apply(1e-3)
         torch.cuda.synchronize()
-        with pytest.raises(p.native.XvecError) as ei:
-            p.eng.check_overflow()
-        assert ei.value.code == p.native.XV_EOVERFLOW
+        assert p.tr.skipped_updates(blocking=True) == 1          # counted on the device by adam_kernel
+        assert p.tr.download(p.native.TRAIN_GRAD)[p.tr.n_params] == 1.0      # the flag rides behind the gradient
+        p.eng.check_overflow()                                   # no ACTIVATION overflowed: the model's own flag stays clear
         assert np.array_equal(p.tr.download(p.native.TRAIN_PARAMS), before)       # adam_kernel left everything alone
         assert not p.tr.download(p.native.TRAIN_ADAM_M).any()
-        p.tr.set_option("loss_scale", 0)                         # automatic again; the flag was cleared by check_overflow
+        p.tr.set_option("loss_scale", 0)                         # automatic again; the step flag is reset by every step
         la = p.step()
         p.tr.apply(1e-3)
         torch.cuda.synchronize()
+        assert p.tr.skipped_updates(blocking=True) == 1 and p.tr.download(p.native.TRAIN_GRAD)[p.tr.n_params] == 0.0
         assert np.isfinite(la).all() and not np.array_equal(p.tr.download(p.native.TRAIN_PARAMS), before)
+    finally:
+        p.close()
+
+
+def test_another_ranks_overflow_flag_in_the_reduced_gradient_skips_the_update_here_too():
+    # data parallel: only the gradient is all-reduced, so the overflow flag travels INSIDE it (grad[n_params]);
+    # a replica whose own step was clean must skip as well when the summed flag is non-zero -- emulated here by handing
+    # xv_train_apply a reduced buffer whose tail another rank has raised
+    p = Problem("ModelWithoutDropoutTdnn", "B", 8, 64, 50)
+    try:
+        before = p.tr.download(p.native.TRAIN_PARAMS)
+        grad = torch.zeros(p.tr.n_grad, dtype=torch.float32, device="cuda")
+        p.tr.forward_backward(p.feats, p.lab, p.B, p.T, grad_dev=grad)
+        torch.cuda.synchronize()
+        assert float(grad[p.tr.n_params]) == 0.0 and bool(torch.isfinite(grad).all())
+        reduced = grad.clone()
+        reduced[p.tr.n_params] += 1.0                            # what the sum all-reduce leaves when one other rank overflowed
+        p.tr.apply(1e-3, grad_dev=reduced, grad_scale=0.5)
+        torch.cuda.synchronize()
+        assert np.array_equal(p.tr.download(p.native.TRAIN_PARAMS), before) and p.tr.skipped_updates(blocking=True) == 1
+        p.tr.apply(1e-3, grad_dev=grad, grad_scale=1.0)          # the clean buffer updates
+        torch.cuda.synchronize()
+        assert not np.array_equal(p.tr.download(p.native.TRAIN_PARAMS), before) and p.tr.skipped_updates(blocking=True) == 1
+        # polling form never blocks and catches up
+        p.tr.skipped_updates(); torch.cuda.synchronize()
+        assert p.tr.skipped_updates() == 1
     finally:
         p.close()
 

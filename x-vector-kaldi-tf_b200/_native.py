@@ -160,6 +160,8 @@ def load_library():
     lib.xv_train_eval.restype = ctypes.c_int
     lib.xv_train_apply.argtypes = [P, P, F32, F32, P]
     lib.xv_train_apply.restype = ctypes.c_int
+    lib.xv_train_skipped_updates.argtypes = [P, P, I32]
+    lib.xv_train_skipped_updates.restype = I64
     lib.xv_train_sync_model.argtypes = [P]
     lib.xv_train_sync_model.restype = ctypes.c_int
     lib.xv_train_debug_tensor.argtypes = [P, ctypes.c_char_p, P, I64]
@@ -191,7 +193,7 @@ EXPORTED_SYMBOLS = ["xv_create", "xv_destroy", "xv_set_param", "xv_workspace_byt
                     # include/xvec_train.h
                     "xv_train_create", "xv_train_destroy", "xv_train_size", "xv_train_span", "xv_train_upload",
                     "xv_train_download", "xv_train_set_step", "xv_train_get_step", "xv_train_forward_backward", "xv_train_eval",
-                    "xv_train_apply", "xv_train_sync_model", "xv_train_debug_tensor", "xv_train_set_option",
+                    "xv_train_apply", "xv_train_skipped_updates", "xv_train_sync_model", "xv_train_debug_tensor", "xv_train_set_option",
                     "xv_train_last_launch_count", "xv_train_last_kernel_names", "xv_convert_f16_to_f32",
                     # include/xvec_frontend.h
                     "xv_frontend_workspace_bytes", "xv_frontend", "xv_submit_host_raw"]
@@ -539,6 +541,7 @@ class XvecTrainer:
         self.handle = ctypes.c_void_p()
         _check(self.lib, self.lib.xv_train_create(ctypes.byref(self.handle), engine.handle, int(num_classes), int(emb1_dim)))
         self.n_params = int(self.lib.xv_train_size(self.handle, TRAIN_PARAMS))
+        self.n_grad = int(self.lib.xv_train_size(self.handle, TRAIN_GRAD))     # gradient + the combined-overflow-flag tail
         self.n_moving = int(self.lib.xv_train_size(self.handle, TRAIN_MOVING))
         self._loss_acc = None
         self._geom = None
@@ -628,6 +631,15 @@ class XvecTrainer:
         s = torch.cuda.current_stream(self.engine.device) if stream is None else stream
         gptr = None if grad_dev is None else grad_dev.data_ptr()
         _check(self.lib, self.lib.xv_train_apply(self.handle, gptr, float(learning_rate), float(grad_scale), s.cuda_stream))
+
+    def skipped_updates(self, stream=None, blocking=False):
+        """Updates skipped so far because a loss-scaled fp16 gradient overflowed on any rank (never waits unless blocking)."""
+        import torch
+        s = torch.cuda.current_stream(self.engine.device) if stream is None else stream
+        n = int(self.lib.xv_train_skipped_updates(self.handle, s.cuda_stream, 1 if blocking else 0))
+        if n < 0:
+            _check(self.lib, n)
+        return n
 
     def convert_f16(self, src_dev, dst_dev, n, stream=None):
         """float16 CUDA tensor -> float32 CUDA tensor (first n values), on ``stream``."""

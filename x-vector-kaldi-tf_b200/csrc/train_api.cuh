@@ -104,6 +104,14 @@ struct xv_trainer {
   std::map<std::string, TrDebug> debug;
   int32_t last_launches = 0;
   std::vector<std::string> prof_names;
+  // gradient-overflow bookkeeping (separate from the xv_model's forward-activation flag): gflag[0] = a loss-scaled fp16
+  // gradient of THIS step left the fp16 range (zeroed at the start of every step, published as grad[n_params] so that a
+  // data-parallel all-reduce combines it over the ranks), gflag[1] = updates skipped so far (adam_kernel)
+  uint32_t* gflag = nullptr;
+  uint32_t* gflag_host = nullptr;    // pinned copy of gflag[1] for xv_train_skipped_updates
+  cudaEvent_t gflag_event = nullptr;
+  bool gflag_pending = false;
+  uint32_t gflag_seen = 0;
 };
 
 namespace {
@@ -270,7 +278,7 @@ int tr_ensure_workspace(xv_trainer* t, int32_t n_seg, int32_t seg_len) {
 // One frame-level contraction through tdnn_pair_kernel<0, 2, LEAKY> (store mode): out = act(in (*) w + bias)*scale + shift
 int tr_pair_layer(xv_trainer* t, cudaStream_t stream, const char* name, const __half* in, int c_in_gemm, __half* out, int c_out,
                   const __half* w, int k_total, int gemm_taps, int dilation, const float* bias, const float* scale,
-                  const float* shift, const float* alpha, float* col_partial = nullptr) {
+                  const float* shift, const float* alpha, float* col_partial = nullptr, uint32_t* overflow_flag = nullptr) {
   xv_model* m = t->m;
   const int64_t r_pad = t->r_pad;
   const int halo = (gemm_taps - 1) / 2 * dilation;
@@ -297,7 +305,7 @@ int tr_pair_layer(xv_trainer* t, cudaStream_t stream, const char* name, const __
   a.row_valid = t->row_valid;
   a.blk_valid = t->blk_valid;
   a.partial = col_partial;           // STATS instantiation: per 32-row block column sums of the stored output
-  a.overflow_flag = m->overflow_dev;
+  a.overflow_flag = overflow_flag ? overflow_flag : m->overflow_dev;
   a.mode = 0;
   const int64_t cap = tdnn2::RING_BYTES;
   const int64_t act_atom = reuse ? tdnn2::ACT_ATOM_BYTES : tdnn2::ACT_BOX_ROWS_PLAIN * 128;
@@ -513,7 +521,11 @@ int xv_train_create(xv_trainer** out, xv_model* model, int32_t num_classes, int3
   alloc0(&t->params, t->n_params);
   alloc0(&t->adam_m, t->n_params);
   alloc0(&t->adam_v, t->n_params);
-  alloc0(&t->grad, t->n_params);
+  alloc0(&t->grad, t->n_params + XV_TRAIN_GRAD_TAIL);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&t->gflag), 16);
+  if (e == cudaSuccess) e = cudaMemset(t->gflag, 0, 16);
+  if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&t->gflag_host), 4, cudaHostAllocDefault);
+  if (e == cudaSuccess) { *t->gflag_host = 0; e = cudaEventCreateWithFlags(&t->gflag_event, cudaEventDisableTiming); }
   alloc0(&t->moving, t->n_moving);
   alloc0(&t->zeros, c_max);
   alloc0(&t->ones, c_max);
@@ -560,13 +572,17 @@ void xv_train_destroy(xv_trainer* t) {
   for (auto& L : t->frames) { cudaFree(L.wf); cudaFree(L.wd); cudaFree(L.bn); }
   for (auto& S : t->seg) cudaFree(S.bn);
   cudaFree(t->params); cudaFree(t->adam_m); cudaFree(t->adam_v); cudaFree(t->grad); cudaFree(t->moving);
+  cudaFree(t->gflag);
+  if (t->gflag_host) cudaFreeHost(t->gflag_host);
+  if (t->gflag_event) cudaEventDestroy(t->gflag_event);
   cudaFree(t->ones); cudaFree(t->zeros); cudaFree(t->ws); cudaFree(t->slope_dev);
   delete t;
 }
 
 int64_t xv_train_size(const xv_trainer* t, int32_t which) {
   if (!t) return 0;
-  return which == XV_TRAIN_MOVING ? t->n_moving : (which >= XV_TRAIN_PARAMS && which <= XV_TRAIN_GRAD ? t->n_params : 0);
+  if (which == XV_TRAIN_GRAD) return t->n_params + XV_TRAIN_GRAD_TAIL;   // + the combined overflow flag behind the gradient
+  return which == XV_TRAIN_MOVING ? t->n_moving : (which >= XV_TRAIN_PARAMS && which < XV_TRAIN_GRAD ? t->n_params : 0);
 }
 
 int xv_train_span(const xv_trainer* t, const char* tf_var_name, int32_t* which, int64_t* offset, int64_t* count) {
@@ -659,6 +675,7 @@ int tr_step_body(xv_trainer* t, const float* feats_dev, const int32_t* labels_de
       const int64_t tail0 = int64_t(n_seg) * t->seg_stride;
       TrFrame& LZ = t->frames[nl - 1];
       if (r_pad > tail0) TR_CUDA(cudaMemsetAsync(LZ.dz + tail0 * LZ.c_out, 0, size_t(r_pad - tail0) * LZ.c_out * 2, stream));
+      TR_CUDA(cudaMemsetAsync(t->gflag, 0, 4, stream));          // this step's gradient-overflow flag
     }
     xvk::PackArgs a{};
     a.feats = feats_dev;
@@ -846,7 +863,7 @@ int tr_step_body(xv_trainer* t, const float* feats_dev, const int32_t* labels_de
     a.gamma = t->params + LL.off_gamma; a.mean = LL.bn; a.inv = LL.bn + C; a.scale = LL.bn + 2 * C;
     a.coefA = t->coefA; a.coefG = t->coefG; a.d_gamma = grad + LL.off_gamma; a.d_beta = grad + LL.off_beta;
     TR_LAUNCH("pool_bwd_coef_kernel", trk::pool_bwd_coef_kernel, dim3((C + 31) / 32), dim3(dim3(32, trk::SEG_Y)), 0, a);
-    TR_LAUNCH("pool_relu_bwd_kernel", trk::pool_relu_bwd_kernel, dim3(C / trk::COLS_PER_CTA, n_seg), dim3(256), 0, static_cast<const __half*>(LL.r), C, t->seg_stride, seg_len, static_cast<const float*>(t->coefA), static_cast<const float*>(t->coefG), LL.dz, t->partial1, m->overflow_dev, t->neg_slope);
+    TR_LAUNCH("pool_relu_bwd_kernel", trk::pool_relu_bwd_kernel, dim3(C / trk::COLS_PER_CTA, n_seg), dim3(256), 0, static_cast<const __half*>(LL.r), C, t->seg_stride, seg_len, static_cast<const float*>(t->coefA), static_cast<const float*>(t->coefG), LL.dz, t->partial1, t->gflag, t->neg_slope);
     TR_LAUNCH("colsum_finalize_kernel", trk::colsum_finalize_kernel, dim3(C / trk::RED_X), dim3(trk::RED_X, trk::RED_Y), 0, static_cast<const float*>(t->partial1), n_seg, C, inv_S, grad + LL.off_b);
   }
 
@@ -862,7 +879,7 @@ int tr_step_body(xv_trainer* t, const float* feats_dev, const int32_t* labels_de
       b.cA = t->cA; b.cB = t->cB; b.cC = t->cC;
       b.d_gamma = grad + L.off_gamma; b.d_beta = grad + L.off_beta;
       TR_LAUNCH("bn_bwd_finalize_kernel", trk::bn_bwd_finalize_kernel, dim3(L.c_out / trk::RED_X), dim3(trk::RED_X, trk::RED_Y), 0, b);
-      TR_LAUNCH("bn_relu_bwd_kernel", trk::bn_relu_bwd_kernel, dim3(L.c_out / trk::COLS_PER_CTA, n_part), dim3(256), 0, static_cast<const __half*>(L.dy), static_cast<const __half*>(L.r), L.c_out, ROWS_PER_PART, static_cast<const float*>(t->cA), static_cast<const float*>(t->cB), static_cast<const float*>(t->cC), L.dz, t->partial1, m->overflow_dev, t->neg_slope, static_cast<const uint8_t*>(t->row_valid));
+      TR_LAUNCH("bn_relu_bwd_kernel", trk::bn_relu_bwd_kernel, dim3(L.c_out / trk::COLS_PER_CTA, n_part), dim3(256), 0, static_cast<const __half*>(L.dy), static_cast<const __half*>(L.r), L.c_out, ROWS_PER_PART, static_cast<const float*>(t->cA), static_cast<const float*>(t->cB), static_cast<const float*>(t->cC), L.dz, t->partial1, t->gflag, t->neg_slope, static_cast<const uint8_t*>(t->row_valid));
       TR_LAUNCH("colsum_finalize_kernel", trk::colsum_finalize_kernel, dim3(L.c_out / trk::RED_X), dim3(trk::RED_X, trk::RED_Y), 0, static_cast<const float*>(t->partial1), n_part, L.c_out, inv_S, grad + L.off_b);
     }
     const __half* x = (i == 0) ? t->x0 : t->frames[i - 1].y;
@@ -871,10 +888,12 @@ int tr_step_body(xv_trainer* t, const float* feats_dev, const int32_t* labels_de
     if (i > 0) {
       TrFrame& P = t->frames[i - 1];
       rc = tr_pair_layer(t, stream, "tdnn_pair_kernel[dgrad]", L.dz, L.c_out, P.dy, L.c_in, L.wd, L.taps * L.c_out, L.taps, L.dil,
-                         t->zeros, t->ones, t->zeros, t->ones);
+                         t->zeros, t->ones, t->zeros, t->ones, nullptr, t->gflag);
       if (rc != XV_OK) return rc;
     }
   }
+  // the step's gradient-overflow flag rides behind the gradient (grad[n_params]): summed with it by the all-reduce
+  TR_LAUNCH("grad_flag_kernel", trk::grad_flag_kernel, dim3(1), dim3(32), 0, static_cast<const uint32_t*>(t->gflag), grad + t->n_params);
 
   // parity hooks
   t->debug.clear();
@@ -981,8 +1000,33 @@ int xv_train_apply(xv_trainer* t, const float* grad_dev, float learning_rate, fl
   const double b1t = std::pow(double(ADAM_B1), double(t->step)), b2t = std::pow(double(ADAM_B2), double(t->step));
   const float lr_t = float(double(learning_rate) * std::sqrt(1.0 - b2t) / (1.0 - b1t));
   TR_LAUNCH("adam_kernel", trk::adam_kernel, dim3(unsigned((t->n_params + 255) / 256)), dim3(256), 0, t->params, g, t->adam_m, t->adam_v, t->n_params, lr_t, ADAM_B1, ADAM_B2, ADAM_EPS, grad_scale,
-            static_cast<const uint32_t*>(t->m->overflow_dev));
+            g + t->n_params, t->gflag + 1);
   return tr_repack(t, stream);
+}
+
+int64_t xv_train_skipped_updates(xv_trainer* t, void* stream_, int32_t blocking) {
+  if (!t) return fail(XV_EINVAL, "null argument");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  XV_CUDA(cudaSetDevice(t->m->device));
+  if (blocking) {
+    XV_CUDA(cudaMemcpyAsync(t->gflag_host, t->gflag + 1, 4, cudaMemcpyDeviceToHost, stream));
+    XV_CUDA(cudaStreamSynchronize(stream));
+    t->gflag_pending = false;
+    t->gflag_seen = *t->gflag_host;
+    return int64_t(t->gflag_seen);
+  }
+  // non-blocking poll: harvest the previous read-back if it has landed, then start the next one
+  if (t->gflag_pending) {
+    cudaError_t q = cudaEventQuery(t->gflag_event);
+    if (q == cudaErrorNotReady) return int64_t(t->gflag_seen);
+    XV_CUDA(q);
+    t->gflag_seen = *t->gflag_host;
+    t->gflag_pending = false;
+  }
+  XV_CUDA(cudaMemcpyAsync(t->gflag_host, t->gflag + 1, 4, cudaMemcpyDeviceToHost, stream));
+  XV_CUDA(cudaEventRecord(t->gflag_event, stream));
+  t->gflag_pending = true;
+  return int64_t(t->gflag_seen);
 }
 
 int xv_train_sync_model(xv_trainer* t) {

@@ -727,16 +727,29 @@ __global__ void __launch_bounds__(256) colsum_rows_kernel(const float* __restric
   out[n] = s;
 }
 
+// grad[n_params .. +4) = this step's gradient-overflow flag as a float (0 / 1): the tail the all-reduce carries
+__global__ void grad_flag_kernel(const uint32_t* __restrict__ flag, float* __restrict__ tail) {
+  cudaTriggerProgrammaticLaunchCompletion();
+  cudaGridDependencySynchronize();
+  if (threadIdx.x < 4) tail[threadIdx.x] = (threadIdx.x == 0 && *flag != 0u) ? 1.f : 0.f;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // tf.train.AdamOptimizer._apply_dense: m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr_t * m / (sqrt(v) + eps)
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
-            float lr_t, float b1, float b2, float eps, float grad_scale, const uint32_t* __restrict__ skip_flag) {
+            float lr_t, float b1, float b2, float eps, float grad_scale, const float* __restrict__ combined_flag,
+            uint32_t* __restrict__ skipped) {
   cudaTriggerProgrammaticLaunchCompletion();   // PDL: dependents may be scheduled; they wait in cudaGridDependencySynchronize()
   cudaGridDependencySynchronize();
-  // a loss-scaled fp16 gradient overflowed somewhere in this step (the flag xv_check_overflow reports): the gradient is not
-  // trustworthy, leave variables and slots alone (what a dynamic loss scaler does) -- the caller lowers the loss scale
-  if (skip_flag != nullptr && *skip_flag != 0u) return;
+  // a loss-scaled fp16 gradient overflowed somewhere in this step -- on ANY rank: the flag rides behind the gradient
+  // (grad[n_params], written by grad_flag_kernel) and is summed by the same all-reduce, so every replica takes the same
+  // decision.  The gradient is not trustworthy: leave variables and slots alone (what a dynamic loss scaler does) and
+  // count the skip -- the caller lowers the loss scale.  (NaN != 0 is true: a poisoned flag skips as well.)
+  if (*combined_flag != 0.f) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(skipped, 1u);
+    return;
+  }
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float gi = g[i] * grad_scale;

@@ -324,7 +324,7 @@ class Model(object):
                 raise ValueError("data-parallel training needs the same number of minibatches on every rank: this rank has %d, "
                                  "the ranks hold between %d and %d" % (minibatch_count, int(lo[0]), -int(lo[1])))
         results = torch.zeros((max(minibatch_count, 1), 2), dtype=torch.float32, device=dev)
-        grad = torch.zeros(tr.n_params, dtype=torch.float32, device=dev) if (training and world > 1) else None
+        grad = torch.zeros(tr.n_grad, dtype=torch.float32, device=dev) if (training and world > 1) else None
         slots = [dict(feats=None, labels=None, ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
         start_minibatch = 1
         total_segments, minibatch_segments, total_segments_len = 0, 0, 0
@@ -365,6 +365,43 @@ class Model(object):
             sl["is_half"] = half
             return sl, x.shape
 
+        skip_state = dict(seen=tr.skipped_updates(compute, blocking=True) if training else 0, lowered=0)
+        n_seg_last = [0, 0]
+
+        def lower_loss_scale(skipped, n_seg, seg_len, at_minibatch):
+            nonlocal loss_scale
+            if skipped <= skip_state["seen"]:
+                return
+            new = skipped - skip_state["seen"]
+            skip_state["seen"] = skipped
+            skip_state["lowered"] += 1
+            if skip_state["lowered"] > 8:
+                raise RuntimeError("gradients keep leaving the fp16 range after %d reductions of the loss scale (now %g): "
+                                   "giving up at minibatch %d" % (skip_state["lowered"] - 1, loss_scale, at_minibatch))
+            loss_scale = (loss_scale or float(2 ** int(np.ceil(np.log2(8.0 * n_seg * seg_len))))) / 16.0
+            tr.set_option("loss_scale", loss_scale)
+            logger.warning("fp16 overflow in the gradients around minibatch %d: %d update(s) skipped on every rank; loss scale "
+                           "lowered to %g" % (at_minibatch, new, loss_scale))
+
+        def check_forward_overflow(at_minibatch):
+            """An ACTIVATION beyond the fp16 range (the xv_model's flag) is not curable by the loss scale: fail, on every
+            rank together (the flag is combined first, or the healthy ranks would hang in the next all-reduce)."""
+            err = None
+            try:
+                eng.check_overflow(compute)
+            except Exception as e:                                       # noqa: BLE001
+                err = e
+            bad = 1 if err is not None else 0
+            if world > 1:
+                import torch.distributed as dist
+                flag = torch.tensor([bad], dtype=torch.int32, device=dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+                bad = int(flag.item())
+            if err is not None:
+                raise err
+            if bad:
+                raise RuntimeError("another rank reported an activation overflow before minibatch %d" % at_minibatch)
+
         for minibatch_idx in range(minibatch_count):
             try:
                 disk_waiting = time.time()
@@ -382,6 +419,7 @@ class Model(object):
             gpu_waiting = time.time()
             sl, shape = stage(minibatch_idx, batch_data, labels)
             n_seg, seg_len = int(shape[0]), int(shape[1])
+            n_seg_last[0], n_seg_last[1] = n_seg, seg_len
             with torch.cuda.stream(compute):
                 compute.wait_event(sl["ready"])
                 if sl["is_half"]:
@@ -401,19 +439,15 @@ class Model(object):
             window.append(minibatch_idx)
             total_gpu_waiting += time.time() - gpu_waiting
             end_minibatch = minibatch_idx + 1
+            if training:
+                # gradient overflow: the skip itself is decided on the device from the flag the all-reduce combined over the
+                # ranks (every replica skips alike); here the count of skipped updates is polled WITHOUT waiting, every
+                # step, so the loss scale drops a step or two after the first overflow instead of at the next log line
+                lower_loss_scale(tr.skipped_updates(compute), n_seg, seg_len, end_minibatch)
             if training and end_minibatch % print_interval == 0:
                 compute.synchronize()
-                try:
-                    eng.check_overflow(compute)
-                except Exception as e:                                   # noqa: BLE001
-                    if getattr(e, "code", None) != -5:                   # XV_EOVERFLOW
-                        raise
-                    # a loss-scaled fp16 gradient left the fp16 range: the optimizer skipped every update since (adam_kernel
-                    # tests the same flag); lower the loss scale and go on, as a dynamic loss scaler does
-                    loss_scale = (loss_scale or float(2 ** int(np.ceil(np.log2(8.0 * n_seg * seg_len))))) / 16.0
-                    tr.set_option("loss_scale", loss_scale)
-                    logger.warning("fp16 overflow in the gradients of minibatches %d-%d: their updates were skipped; loss scale "
-                                   "lowered to %g" % (start_minibatch, end_minibatch, loss_scale))
+                lower_loss_scale(tr.skipped_updates(compute, blocking=True), n_seg, seg_len, end_minibatch)
+                check_forward_overflow(end_minibatch)
                 res = results[window].cpu().numpy().astype(np.float64)
                 cnt = end_minibatch - start_minibatch + 1
                 minibatch_loss, minibatch_accuracy = res[:, 0].sum(), res[:, 1].sum()
@@ -430,7 +464,10 @@ class Model(object):
                 total_gpu_waiting = 0.0
                 total_disk_waiting = 0.0
         compute.synchronize()
-        eng.check_overflow(compute)
+        if training:
+            # the trailing (partial) window is handled like any other: skipped updates are logged, the iteration is kept
+            lower_loss_scale(tr.skipped_updates(compute, blocking=True), max(n_seg_last[0], 1), max(n_seg_last[1], 1), minibatch_count)
+        check_forward_overflow(minibatch_count)
         res = results[done].cpu().numpy().astype(np.float64) if done else np.zeros((0, 2))
         return dict(minibatch_count=minibatch_count, total_segments=total_segments, total_segments_len=total_segments_len,
                     total_loss=float(res[:, 0].sum()), total_accuracy=float(res[:, 1].sum()), losses=res[:, 0],
