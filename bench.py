@@ -473,6 +473,8 @@ def run_b200(args):
         barrier()
         peer.close()
     eng.close()
+    if not args.no_product:
+        out["product"] = measure_product(args, dev, rank, world, params, topo)
     if not args.no_train and topo.get("act", "relu") == "relu" and topo.get("pooling", "stats") == "stats":
         out["train_step"] = measure_train_step(args, dev, rank, world, peaks, topo)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -552,6 +554,142 @@ def measure_frontend(args, eng, dev, stream, flush, rank, peaks):
                          voiced_frames_per_sec=round(float(keep.sum()) / (e2e_ms * 1e-3), 1),
                          h2d_bytes_per_step=int(B * T * (FEAT_DIM * 4 + 4) + B * 4 * 3), d2h_bytes_per_step=B * EMB_DIM * 4 + 4),
                 cpu_baseline=cpu)
+
+
+def _scratch_dir():
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    import tempfile
+    return tempfile.mkdtemp(prefix="xvec_product_", dir=base)
+
+
+def write_model_dir(path, topology, params, num_classes=0):
+    """A model directory Model.load_model reads (model.meta + model.npz + done) holding the bench's synthetic weights."""
+    from xvector_b200 import models
+    topo = TOPOLOGIES[topology]
+    meta = dict(pooling=topo.get("pooling", "stats"), format=models.META_FORMAT, model_class=topology, num_classes=int(num_classes),
+                input_feature_dim=FEAT_DIM, kernel_sizes=list(topo["kernel_sizes"]), dilation_rates=list(topo["dilations"]),
+                layer_sizes=list(topo["layer_sizes"]), embedding_sizes=list(topo["embedding_sizes"]), activation=topo.get("act", "relu"))
+    models.Model.save_model(models._Session(params, meta), path, None)
+
+
+def measure_product(args, dev, rank, world, params, topo):
+    """BASELINE configs[2] (N = 1) / configs[3] scaled to 12 500 utterances per GPU (N > 1) through the PRODUCT entry point:
+    Model.make_embedding from a feature ark FILE (200-1000 frames per utterance, seed 3) to an x-vector ark + scp written by
+    rank 0 -- wall clock around the call on every rank, barrier on both sides, max over ranks.  Inside the window: header
+    index of the rank's byte stripe, the stripe-boundary exchange, pread into page-locked batches, H2D, the network, the
+    chunk average, the stores into rank 0's table (N > 1), the closing barrier, rank 0's read of the table, formatting
+    and writing the output files.  Outside: writing the synthetic input (page cache), loading the model on the first call."""
+    import shutil
+    import torch
+    import torch.distributed as dist
+    from xvector_b200 import kaldi_io, models, synthetic
+    out = dict()
+    tmp = None
+    try:
+        n_per_rank = 10000 if world == 1 else 12500
+        box = [None]
+        if rank == 0:
+            tmp = _scratch_dir()
+            box[0] = tmp
+        if world > 1:
+            dist.broadcast_object_list(box, src=0)
+        tmp = box[0]
+        # every rank writes its share of the input (the same 1250-utterance block of synthetic MFCC under fresh keys: content
+        # does not matter to throughput, and 100 k utterances need not be generated), rank 0 concatenates
+        lens = synthetic.lengths_uniform(3, 1250 if world > 1 else n_per_rank)
+        feats = synthetic.mfcc_batch(3, lens)
+        offs = np.concatenate([[0], np.cumsum(lens)])
+        part = os.path.join(tmp, "part.%d" % rank)
+        with open(part, "wb") as f:
+            for i in range(n_per_rank):
+                j = i % len(lens)
+                kaldi_io.write_mat(f, feats[offs[j]:offs[j + 1]], key="utt%07d" % (rank * n_per_rank + i))
+        n_frames_rank = int(lens.sum()) * (n_per_rank // len(lens)) + int(lens[:n_per_rank % len(lens)].sum())
+        path = os.path.join(tmp, "feats.ark")
+        if world > 1:
+            dist.barrier()
+        if rank == 0:
+            with open(path, "wb") as dst:
+                for r in range(world):
+                    with open(os.path.join(tmp, "part.%d" % r), "rb") as src:
+                        shutil.copyfileobj(src, dst, 64 << 20)
+                    os.unlink(os.path.join(tmp, "part.%d" % r))
+            write_model_dir(os.path.join(tmp, "model"), args.topology, params)
+        if world > 1:
+            dist.barrier()
+        total_frames = n_frames_rank * world
+        model = getattr(models, args.topology)()
+        runs = []
+        for it in range(3):
+            ark, scp = os.path.join(tmp, "xvector.%d.ark" % it), os.path.join(tmp, "xvector.%d.scp" % it)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            if rank == 0:
+                with kaldi_io.open_vector_writer("ark,scp:%s,%s" % (ark, scp)) as w:
+                    model.make_embedding(path, w, os.path.join(tmp, "model"), 25, 10000, True, None)
+            else:
+                model.make_embedding(path, None, os.path.join(tmp, "model"), 25, 10000, True, None)
+            torch.cuda.synchronize(dev)
+            if world > 1:
+                dist.barrier()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            runs.append(dt)
+        check = None
+        if rank == 0:
+            # the job's output: every key once and in order, the scp points at the same vectors, sampled rows bit-identical
+            # to the device path run directly on those utterances
+            ark = os.path.join(tmp, "xvector.2.ark")
+            n_out, last, ok_order = 0, None, True
+            sample = {}
+            want_idx = {0, 1, n_per_rank * world - 1, (n_per_rank * world) // 2}
+            for i, (k, v) in enumerate(kaldi_io.read_vec_flt_ark(ark)):
+                ok_order = ok_order and k == "utt%07d" % i
+                if i in want_idx:
+                    sample[i] = v
+                n_out += 1
+            eng = model._engine
+            same = True
+            for i, v in sample.items():
+                j = (i % n_per_rank) % len(lens)
+                x = torch.from_numpy(feats[offs[j]:offs[j + 1]]).to(dev)
+                o = torch.empty((1, EMB_DIM), dtype=torch.float32, device=dev)
+                eng.forward_utts(x, np.array([lens[j]], np.int32), o)
+                torch.cuda.synchronize(dev)
+                same = same and np.array_equal(o.cpu().numpy()[0], v)
+            first = open(os.path.join(tmp, "xvector.2.scp")).readline().split()
+            check = dict(utterances_written=n_out, keys_in_input_order=bool(ok_order), scp_first_line=first[0] if first else None,
+                         sampled_rows_bit_identical_to_direct_forward=bool(same), output_bytes=os.path.getsize(ark))
+        warm = min(runs[1:])
+        out = dict(workload=("configs[2]: %d utterances of 200-1000 frames (%.1f M frames, %.0f MB feature ark file in the page "
+                             "cache) -> x-vector ark + scp, Model.make_embedding" if world == 1 else
+                             "configs[3] scaled: %d utterances of 200-1000 frames (%.1f M frames, %.0f MB feature ark file in the "
+                             "page cache), byte-striped over the ranks -> ONE x-vector ark + scp written by rank 0, "
+                             "Model.make_embedding under torchrun") % (n_per_rank * world, total_frames / 1e6,
+                                                                         total_frames * 92 / 1e6),
+                   unit=UNIT, value=round(total_frames / warm, 1), seconds=round(warm, 4),
+                   first_call=dict(seconds=round(runs[0], 4), value=round(total_frames / runs[0], 1),
+                                   note="includes Model.load_model, weight upload and the first allocation of page-locked "
+                                        "batch buffers / device workspaces"),
+                   all_runs_s=[round(r, 4) for r in runs], reader_threads=os.environ.get("XVEC_READER_THREADS", "default"),
+                   check=check)
+    except Exception as err:                                     # noqa: BLE001  (a diagnostic block must not cost the bench line)
+        import traceback
+        out = dict(error="%s: %s" % (type(err).__name__, err), trace=traceback.format_exc()[-1500:])
+    finally:
+        if world > 1:
+            try:
+                dist.barrier()
+            except Exception:                                    # noqa: BLE001
+                pass
+        if rank == 0 and tmp is not None:
+            shutil.rmtree(tmp, ignore_errors=True)
+    return out
 
 
 def measure_reader(n_utts=1500, passes=3):
@@ -843,6 +981,7 @@ def main():
     ap.add_argument("--option", action="append", default=[], help="xv_set_option name=value (diagnostics)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the configs[4] training-step block")
+    ap.add_argument("--no-product", action="store_true", help="skip the ark -> ark product-path block (configs[2] / [3])")
     ap.add_argument("--step-seconds", type=float, default=1.5, help="reference arm: CPU seconds per step (calibrated)")
     args = ap.parse_args()
     if args.impl == "reference":

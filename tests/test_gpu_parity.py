@@ -333,6 +333,42 @@ def test_config3_ragged_ark_through_make_embedding(tmp_path):
     assert m["max_rel"] <= TOL and m["l2_rel"] <= TOL, m
 
 
+def test_native_ark_file_job_is_byte_identical_to_the_stream_path(tmp_path, monkeypatch):
+    # the same archive once as an in-memory stream (general path: Python parser, host-side chunk average) and once as a
+    # regular file (native job path: striped reader, chunk average on the device, native formatter) -- with chunking, a
+    # dropped tail, skipped utterances and several batches; the outputs must agree to the byte
+    from xvector_b200 import kaldi_io
+    from xvector_b200.models import Model, ModelWithoutDropoutTdnn
+    monkeypatch.setenv("XVEC_SEED", "13")
+    monkeypatch.setenv("XVEC_BATCH_FRAMES", "20000")
+    model_dir = str(tmp_path / "model_0")
+    ModelWithoutDropoutTdnn().build_model(10, 23, model_dir, None)
+    lens = np.concatenate([synthetic.lengths_uniform(5, 300, 20, 900), [0, 10, 1310, 2999, 300, 325]]).astype(np.int64)
+    feats = synthetic.mfcc_batch(5, lens)
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    buf = io.BytesIO()
+    for i in range(len(lens)):
+        kaldi_io.write_mat(buf, feats[offs[i]:offs[i + 1]], key="spk%03d-utt%05d" % (i % 7, i))
+    data = buf.getvalue()
+    path = tmp_path / "feats.ark"
+    path.write_bytes(data)
+    model = Model()
+    want = io.BytesIO()
+    model.make_embedding(io.BytesIO(data), want, model_dir, 25, 300, True, None)
+    got = io.BytesIO()
+    with open(path, "rb") as f:
+        model.make_embedding(f, got, model_dir, 25, 300, True, None)
+    assert len(want.getvalue()) > 0 and got.getvalue() == want.getvalue()
+    a, s_ = str(tmp_path / "x.ark"), str(tmp_path / "x.scp")
+    with kaldi_io.open_vector_writer("ark,scp:%s,%s" % (a, s_)) as w:
+        model.make_embedding(str(path), w, model_dir, 25, 300, True, None)
+    assert open(a, "rb").read() == want.getvalue()
+    by_scp = list(kaldi_io.read_vec_flt_scp(s_))
+    by_ark = list(kaldi_io.read_vec_flt_ark(a))
+    assert len(by_scp) == len(by_ark) == int(((lens >= 25)).sum())
+    assert all(k1 == k2 and np.array_equal(v1, v2) for (k1, v1), (k2, v2) in zip(by_scp, by_ark))
+
+
 def test_extreme_batch_shapes():
     # edge cases of the packed-row layout and of the embedding GEMM's row tiling:
     # one minimal segment; thousands of short segments (n_seg >> 256: several GEMM row tiles, fewer K-splits);

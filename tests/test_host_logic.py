@@ -28,6 +28,7 @@ class OracleEngine(object):
         self.in_flight = {}
         self.next_ticket = 0
         self.calls = 0
+        self.utts_calls = 0
 
     def _run(self, feats, lens, out):
         topo = dict(kernel_sizes=self.meta["kernel_sizes"], dilations=self.meta["dilation_rates"],
@@ -46,9 +47,23 @@ class OracleEngine(object):
         self.in_flight[t] = (np.array(feats, copy=True), np.array(lens), emb)
         return t
 
+    def submit_host_utts(self, feats, lens, utt_first_seg=None, dst_rows=None, out_dev=None, out_host=None):
+        assert out_dev is None and dst_rows is None, "the stand-in has no peer memory"
+        self.utts_calls += 1
+        seg = np.empty((len(lens), 512), np.float32)
+        t = self.submit_host(feats, lens, seg)
+        first = np.arange(len(lens) + 1) if utt_first_seg is None else np.array(utt_first_seg)
+        self.in_flight[t] = self.in_flight[t] + (first, out_host)
+        return t
+
     def collect(self, ticket):
-        feats, lens, emb = self.in_flight.pop(ticket)
+        item = self.in_flight.pop(ticket)
+        feats, lens, emb = item[:3]
         self._run(feats, lens, emb)
+        if len(item) == 5:          # utterance-level: the reference's float32 chunk average (models.py:398-421)
+            first, out_host = item[3], item[4]
+            utts = [(u, None, int(first[u]), [int(n) for n in lens[first[u]:first[u + 1]]]) for u in range(len(first) - 1)]
+            out_host[...] = models._average_chunks(emb, utts)
 
     def extract_host(self, feats, lens, emb=None):
         emb = np.empty((len(lens), 512), np.float32) if emb is None else emb

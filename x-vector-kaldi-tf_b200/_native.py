@@ -46,6 +46,30 @@ class XvCmvnOpts(ctypes.Structure):
         super().__init__(int(cmn_window), int(min(min_window, cmn_window)), int(bool(center)), int(bool(normalize_variance)))
 
 
+class XvArkReaderOpts(ctypes.Structure):
+    """xv_ark_reader_opts (include/xvec_job.h)."""
+    _fields_ = [("feat_dim", ctypes.c_int32), ("min_chunk_size", ctypes.c_int32), ("chunk_size", ctypes.c_int32),
+                ("n_threads", ctypes.c_int32), ("n_slots", ctypes.c_int32), ("pinned", ctypes.c_int32),
+                ("batch_frames", ctypes.c_int64), ("byte_begin", ctypes.c_int64), ("byte_end", ctypes.c_int64),
+                ("begin_is_boundary", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class XvArkIndexInfo(ctypes.Structure):
+    """xv_ark_index_info (include/xvec_job.h)."""
+    _fields_ = [(n, ctypes.c_int64) for n in ("n_entries", "n_ok", "n_fail", "n_segments", "rows_used", "n_batches",
+                                              "first_marker_off", "next_marker_off", "next_key_off", "stopped_at", "key_bytes")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class XvArkBatch(ctypes.Structure):
+    """xv_ark_batch (include/xvec_job.h)."""
+    _fields_ = [("slot", ctypes.c_int32), ("n_seg", ctypes.c_int32), ("n_utt", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("n_rows", ctypes.c_int64), ("feats", ctypes.c_void_p), ("seg_len", ctypes.c_void_p),
+                ("utt_first_seg", ctypes.c_void_p), ("utt_dst_row", ctypes.c_void_p), ("first_ok_index", ctypes.c_int64)]
+
+
 class XvecError(RuntimeError):
     def __init__(self, code, message):
         super().__init__("xvec_b200 error %d: %s" % (code, message))
@@ -59,6 +83,7 @@ def build_library(verbose=False):
     sources.append(os.path.join(REPO_ROOT, "include", "xvec.h"))
     sources.append(os.path.join(REPO_ROOT, "include", "xvec_train.h"))
     sources.append(os.path.join(REPO_ROOT, "include", "xvec_frontend.h"))
+    sources.append(os.path.join(REPO_ROOT, "include", "xvec_job.h"))
     if os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in sources):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
@@ -136,6 +161,31 @@ def load_library():
     lib.xv_version.restype = ctypes.c_char_p
     lib.xv_ark_scan.argtypes = [P, I64, I64, P, P, P, P, P, P, ctypes.POINTER(I64)]
     lib.xv_ark_scan.restype = I64
+    # extraction job: striped ark reader + vector-ark formatter (include/xvec_job.h)
+    lib.xv_ark_reader_open.argtypes = [ctypes.POINTER(P), ctypes.c_char_p, ctypes.POINTER(XvArkReaderOpts)]
+    lib.xv_ark_reader_open.restype = ctypes.c_int
+    lib.xv_ark_reader_index.argtypes = [P, ctypes.POINTER(XvArkIndexInfo)]
+    lib.xv_ark_reader_index.restype = ctypes.c_int
+    lib.xv_ark_reader_set_first.argtypes = [P, I64, I64, ctypes.POINTER(XvArkIndexInfo)]
+    lib.xv_ark_reader_set_first.restype = ctypes.c_int
+    lib.xv_ark_reader_keys.argtypes = [P, P, I64, P]
+    lib.xv_ark_reader_keys.restype = ctypes.c_int
+    lib.xv_ark_reader_failures.argtypes = [P, P, P, P, I64, P]
+    lib.xv_ark_reader_failures.restype = ctypes.c_int
+    lib.xv_ark_reader_start.argtypes = [P, I64]
+    lib.xv_ark_reader_start.restype = ctypes.c_int
+    lib.xv_ark_reader_next.argtypes = [P, ctypes.POINTER(XvArkBatch)]
+    lib.xv_ark_reader_next.restype = ctypes.c_int
+    lib.xv_ark_reader_release.argtypes = [P, I32]
+    lib.xv_ark_reader_release.restype = ctypes.c_int
+    lib.xv_ark_reader_close.argtypes = [P]
+    lib.xv_ark_reader_close.restype = None
+    lib.xv_vec_ark_bytes.argtypes = [P, I64, I32]
+    lib.xv_vec_ark_bytes.restype = I64
+    lib.xv_vec_ark_format.argtypes = [P, P, I64, P, I32, P, I64, P, I32]
+    lib.xv_vec_ark_format.restype = I64
+    lib.xv_scp_format.argtypes = [P, P, I64, ctypes.c_char_p, I64, P, P, I64]
+    lib.xv_scp_format.restype = I64
     # training step (include/xvec_train.h)
     F32, F64 = ctypes.c_float, ctypes.c_double
     lib.xv_train_create.argtypes = [ctypes.POINTER(P), P, I32, I32]
@@ -190,6 +240,10 @@ EXPORTED_SYMBOLS = ["xv_create", "xv_destroy", "xv_set_param", "xv_workspace_byt
                     "xv_last_kernel_ms", "xv_set_option", "xv_last_error", "xv_version", "xv_ark_scan",
                     "xv_forward_utts", "xv_submit_host_utts", "xv_peer_alloc", "xv_peer_open", "xv_peer_close", "xv_peer_free",
                     "xv_peer_read", "xv_abi_version", "xv_topology_size",
+                    # include/xvec_job.h
+                    "xv_ark_reader_open", "xv_ark_reader_index", "xv_ark_reader_set_first", "xv_ark_reader_keys",
+                    "xv_ark_reader_failures", "xv_ark_reader_start", "xv_ark_reader_next", "xv_ark_reader_release",
+                    "xv_ark_reader_close", "xv_vec_ark_bytes", "xv_vec_ark_format", "xv_scp_format",
                     # include/xvec_train.h
                     "xv_train_create", "xv_train_destroy", "xv_train_size", "xv_train_span", "xv_train_upload",
                     "xv_train_download", "xv_train_set_step", "xv_train_get_step", "xv_train_forward_backward", "xv_train_eval",
@@ -223,6 +277,133 @@ def ark_scan(buffer, start=0, max_entries=1 << 20):
     if n < 0:
         raise XvecError(XV_EINVAL, "xv_ark_scan: bad argument")
     return (key_off[:n] + start, key_len[:n], rows[:n], cols[:n], elem[:n], pay[:n] + start), start + int(consumed.value)
+
+
+class ArkBatch(object):
+    """One batch of an ArkReader: numpy views over the reader's own memory, valid until ``release``."""
+    __slots__ = ("slot", "n_seg", "n_utt", "n_rows", "feats", "seg_len", "utt_first_seg", "utt_dst_row", "first_ok_index")
+
+
+def _view(ptr, ctype, n, dtype):
+    if n == 0:
+        return np.empty(0, dtype)
+    return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctype)), shape=(n,))
+
+
+class ArkReader(object):
+    """xv_ark_reader (include/xvec_job.h): the host side of an extraction job over a feature ark in a regular file --
+    header index of one byte stripe, make_embedding's skip / chunk rules, batches filled by a pread pool.  Needs no GPU
+    with ``pinned=False``."""
+
+    def __init__(self, path, feat_dim, min_chunk_size, chunk_size, batch_frames, byte_begin=0, byte_end=-1,
+                 begin_is_boundary=True, n_threads=4, n_slots=3, pinned=True):
+        self.lib = load_library()
+        opts = XvArkReaderOpts(int(feat_dim), int(min_chunk_size), int(chunk_size), int(n_threads), int(n_slots),
+                               1 if pinned else 0, int(batch_frames), int(byte_begin), int(byte_end),
+                               1 if begin_is_boundary else 0, 0)
+        self.feat_dim = int(feat_dim)
+        self.handle = ctypes.c_void_p()
+        _check(self.lib, self.lib.xv_ark_reader_open(ctypes.byref(self.handle), os.fsencode(path), ctypes.byref(opts)))
+        self.info = None
+
+    def index(self):
+        info = XvArkIndexInfo()
+        _check(self.lib, self.lib.xv_ark_reader_index(self.handle, ctypes.byref(info)))
+        self.info = info.as_dict()
+        return self.info
+
+    def set_first(self, marker_off, key_off):
+        info = XvArkIndexInfo()
+        _check(self.lib, self.lib.xv_ark_reader_set_first(self.handle, int(marker_off), int(key_off), ctypes.byref(info)))
+        self.info = info.as_dict()
+        return self.info
+
+    def keys(self):
+        """(blob, key_off): keys of the ok utterances, in order, as one bytes-like blob + int64 offsets [n_ok + 1]."""
+        n = self.info["n_ok"]
+        blob = np.empty(max(self.info["key_bytes"], 1), np.uint8)
+        off = np.empty(n + 1, np.int64)
+        _check(self.lib, self.lib.xv_ark_reader_keys(self.handle, blob.ctypes.data, self.info["key_bytes"], off.ctypes.data))
+        return blob[:self.info["key_bytes"]], off
+
+    def failures(self):
+        """[(key, reason, rows)] of the skipped utterances, in order (reason: XV_UTT_ZERO_LENGTH = 1, XV_UTT_TOO_SHORT = 2)."""
+        n = self.info["n_fail"]
+        if n == 0:
+            return []
+        reason, rows, off = np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n + 1, np.int64)
+        blob = np.empty(n * 4097, np.uint8)
+        _check(self.lib, self.lib.xv_ark_reader_failures(self.handle, reason.ctypes.data, rows.ctypes.data, blob.ctypes.data,
+                                                         blob.shape[0], off.ctypes.data))
+        raw = blob.tobytes()
+        return [(raw[off[i]:off[i + 1]].decode(), int(reason[i]), int(rows[i])) for i in range(n)]
+
+    def start(self, dst_row_base=0):
+        _check(self.lib, self.lib.xv_ark_reader_start(self.handle, int(dst_row_base)))
+
+    def next(self):
+        """The next batch (blocks until its payloads are in memory), or None after the last one."""
+        b = XvArkBatch()
+        _check(self.lib, self.lib.xv_ark_reader_next(self.handle, ctypes.byref(b)))
+        if b.n_utt == 0:
+            return None
+        out = ArkBatch()
+        out.slot, out.n_seg, out.n_utt, out.n_rows, out.first_ok_index = b.slot, b.n_seg, b.n_utt, int(b.n_rows), int(b.first_ok_index)
+        out.feats = _view(b.feats, ctypes.c_float, out.n_rows * self.feat_dim, np.float32).reshape(out.n_rows, self.feat_dim)
+        out.seg_len = _view(b.seg_len, ctypes.c_int32, b.n_seg, np.int32)
+        out.utt_first_seg = _view(b.utt_first_seg, ctypes.c_int32, b.n_utt + 1, np.int32)
+        out.utt_dst_row = _view(b.utt_dst_row, ctypes.c_int64, b.n_utt, np.int64)
+        return out
+
+    def release(self, slot):
+        _check(self.lib, self.lib.xv_ark_reader_release(self.handle, int(slot)))
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self.lib.xv_ark_reader_close(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def vec_ark_format(key_blob, key_off, vecs, with_markers=False, n_threads=4):
+    """The bytes write_vec_flt (reference kaldi_io.py:309-343) emits for the float32 rows of ``vecs``, keyed by
+    ``key_blob[key_off[i]:key_off[i+1]]`` -- one uint8 array -- and, with ``with_markers``, each entry's marker offset."""
+    lib = load_library()
+    vecs = np.ascontiguousarray(vecs, dtype=np.float32)
+    key_off = np.ascontiguousarray(key_off, dtype=np.int64)
+    key_blob = np.ascontiguousarray(key_blob, dtype=np.uint8)
+    n, dim = int(vecs.shape[0]), int(vecs.shape[1])
+    assert key_off.shape[0] == n + 1
+    total = int(lib.xv_vec_ark_bytes(key_off.ctypes.data, n, dim))
+    out = np.empty(max(total, 1), np.uint8)
+    markers = np.empty(max(n, 1), np.int64) if with_markers else None
+    # key_off may be a window of a larger table: the formatter indexes the blob with the absolute offsets
+    got = int(lib.xv_vec_ark_format(key_blob.ctypes.data, key_off.ctypes.data, n, vecs.ctypes.data, dim, out.ctypes.data, total,
+                                    None if markers is None else markers.ctypes.data, int(n_threads)))
+    if got < 0:
+        _check(lib, got)
+    return (out[:total], markers[:n]) if with_markers else out[:total]
+
+
+def scp_format(key_blob, key_off, ark_name, base, markers):
+    """The scp lines beside such an ark: ``key ark_name:offset`` (offset = base + marker)."""
+    lib = load_library()
+    key_off = np.ascontiguousarray(key_off, dtype=np.int64)
+    key_blob = np.ascontiguousarray(key_blob, dtype=np.uint8)
+    markers = np.ascontiguousarray(markers, dtype=np.int64)
+    n = int(markers.shape[0])
+    name = os.fsencode(ark_name)
+    cap = int(key_off[n] - key_off[0]) + n * (len(name) + 24) + 1
+    out = np.empty(cap, np.uint8)
+    got = int(lib.xv_scp_format(key_blob.ctypes.data, key_off.ctypes.data, n, name, int(base), markers.ctypes.data, out.ctypes.data, cap))
+    if got < 0:
+        _check(lib, got)
+    return out[:got]
 
 
 class XvecEngine:

@@ -1,0 +1,589 @@
+// ark_job.cuh -- host side of an ark -> x-vector-ark extraction job (include/xvec_job.h): striped header index,
+// make_embedding's skip / chunk rules, a pread pool that fills page-locked batches, and the vector-ark / scp formatters.
+// Host-only; included at the end of xvec_api.cu (shares fail() / XV_CUDA and xv_ark_scan).
+#pragma once
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+
+#include "../../include/xvec_job.h"
+
+namespace arkjob {
+
+struct Entry {
+  int64_t key_off;
+  int64_t payload_off;
+  int32_t key_len;
+  int32_t rows;
+  int32_t elem;      // 4 = float32, 8 = float64
+  int32_t used;      // rows kept (chunks are contiguous from row 0; only a tail shorter than min_chunk_size is dropped)
+  int32_t n_chunks;  // 0: skipped
+  int32_t reason;    // XV_UTT_*
+};
+
+struct Batch {
+  int64_t u0, u1;        // ok-utterance range
+  int64_t seg0;          // first segment (global over the stripe)
+  int64_t first0;        // offset of this batch's utt_first_seg run in first_seg_all (n_utt + 1 entries)
+  int64_t n_rows;
+  int32_t n_seg;
+  int32_t n_tasks;
+};
+
+struct Task { int32_t batch; int64_t u0, u1; };
+
+constexpr int64_t TASK_BYTES = 2 << 20;       // payload bytes one worker fetches per claim
+constexpr int VALIDATE_ENTRIES = 4;           // headers that must chain behind a resynchronisation candidate
+
+}  // namespace arkjob
+
+struct xv_ark_reader {
+  xv_ark_reader_opts o{};
+  int fd = -1;
+  int64_t file_size = 0;
+  const uint8_t* map = nullptr;
+  std::vector<arkjob::Entry> entries;          // every matrix of the stripe, in file order
+  std::vector<int64_t> ok;                     // entry index of the i-th ok utterance
+  std::vector<int64_t> row_in_batch;           // [n_ok] first row of the utterance inside its batch buffer
+  std::vector<int32_t> seg_len_all;            // [n_segments]
+  std::vector<int32_t> first_seg_all;          // batch-relative utt_first_seg runs, (n_utt + 1) per batch
+  std::vector<int64_t> dst_row_all;            // [n_ok]
+  std::vector<arkjob::Batch> batches;
+  std::vector<arkjob::Task> tasks;
+  xv_ark_index_info info{};
+  int64_t scan_from = 0;                       // where the stripe's scan starts (a boundary or a candidate's key)
+  bool first_is_candidate = false;             // entries[0] came from a resynchronisation (its key start is provisional)
+  // ring
+  std::vector<float*> slot_buf;
+  std::vector<size_t> slot_bytes;
+  int64_t slot_rows = 0;
+  std::vector<std::thread> workers;
+  std::mutex mu;
+  std::condition_variable cv_work, cv_ready;
+  size_t next_task = 0;
+  std::vector<int32_t> batch_done;             // tasks finished per batch
+  int64_t released = 0;                        // batches handed back by the consumer (in order)
+  int64_t next_batch = 0;                      // next batch the consumer gets
+  bool stop = false, started = false;
+  std::string error;
+};
+
+namespace arkjob {
+
+// Page-locked batch buffers are expensive to create (cudaHostAlloc pins every page: ~10 ms per 40 MB) and a process that
+// runs several jobs needs the same sizes again: closed readers park their buffers here (at most POOL_CAP_BYTES).
+struct PinnedPool {
+  std::mutex mu;
+  std::vector<std::pair<float*, size_t>> free_list;
+  size_t bytes = 0;
+  static constexpr size_t POOL_CAP_BYTES = size_t(1) << 30;
+  float* take(size_t need) {
+    std::lock_guard<std::mutex> lk(mu);
+    int best = -1;
+    for (int i = 0; i < int(free_list.size()); ++i)
+      if (free_list[i].second >= need && (best < 0 || free_list[i].second < free_list[best].second)) best = i;
+    if (best < 0 || free_list[best].second > 2 * need + (size_t(1) << 20)) return nullptr;
+    float* p = free_list[best].first;
+    bytes -= free_list[best].second;
+    free_list.erase(free_list.begin() + best);
+    return p;
+  }
+  bool give(float* p, size_t n) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (bytes + n > POOL_CAP_BYTES) return false;
+    free_list.emplace_back(p, n);
+    bytes += n;
+    return true;
+  }
+};
+inline PinnedPool& pinned_pool() { static PinnedPool pool; return pool; }
+
+inline bool key_char(uint8_t c) { return ark_key_char(c); }
+
+// A "\0B[FD]M \4 rows \4 cols" header at h whose matrix has the expected width and fits in the file.
+bool plausible_header(const xv_ark_reader* r, int64_t h, int64_t* payload_end) {
+  const uint8_t* b = r->map;
+  if (h < 2 || h + 15 > r->file_size) return false;
+  if (b[h] != 0 || b[h + 1] != 'B' || (b[h + 2] != 'F' && b[h + 2] != 'D') || b[h + 3] != 'M' || b[h + 4] != ' ' ||
+      b[h + 5] != 4 || b[h + 10] != 4 || b[h - 1] != ' ' || !key_char(b[h - 2]))
+    return false;
+  int32_t rows, cols;
+  memcpy(&rows, b + h + 6, 4);
+  memcpy(&cols, b + h + 11, 4);
+  if (rows < 0 || cols != r->o.feat_dim) return false;
+  const int64_t end = h + 15 + int64_t(rows) * cols * (b[h + 2] == 'F' ? 4 : 8);
+  if (end > r->file_size) return false;
+  *payload_end = end;
+  return true;
+}
+
+// First marker offset >= from whose header is plausible AND behind which VALIDATE_ENTRIES further entries (or the end of
+// the file) parse in a chain.  -1: none.
+int64_t resync(const xv_ark_reader* r, int64_t from) {
+  const uint8_t* b = r->map;
+  int64_t pos = std::max<int64_t>(from, 2);
+  while (pos + 15 <= r->file_size) {
+    const void* z = memchr(b + pos, 0, size_t(r->file_size - pos));
+    if (!z) return -1;
+    const int64_t h = static_cast<const uint8_t*>(z) - b;
+    int64_t end = 0;
+    if (plausible_header(r, h, &end)) {
+      int64_t ko[VALIDATE_ENTRIES], po[VALIDATE_ENTRIES], consumed = 0;
+      int32_t kl[VALIDATE_ENTRIES], rw[VALIDATE_ENTRIES], cl[VALIDATE_ENTRIES], eb[VALIDATE_ENTRIES];
+      const int64_t n = xv_ark_scan(b + end, r->file_size - end, VALIDATE_ENTRIES, ko, kl, rw, cl, eb, po, &consumed);
+      bool ok = n == VALIDATE_ENTRIES || (n >= 0 && end + consumed == r->file_size);
+      for (int64_t i = 0; i < n && ok; ++i) ok = cl[i] == r->o.feat_dim;
+      if (ok) return h;
+    }
+    pos = h + 1;
+  }
+  return -1;
+}
+
+// make_embedding's rules for one utterance (models.py:377-409).
+void plan_entry(const xv_ark_reader_opts& o, Entry* e) {
+  const int64_t rows = e->rows;
+  e->used = 0; e->n_chunks = 0; e->reason = XV_UTT_OK;
+  if (rows == 0) { e->reason = XV_UTT_ZERO_LENGTH; return; }
+  if (rows < o.min_chunk_size) { e->reason = XV_UTT_TOO_SHORT; return; }
+  if (o.chunk_size == -1 || rows <= o.chunk_size) { e->used = int32_t(rows); e->n_chunks = 1; return; }
+  const int64_t cs = o.chunk_size;
+  const int64_t n = (rows + cs - 1) / cs;
+  const int64_t tail = rows - (n - 1) * cs;
+  if (tail < o.min_chunk_size) { e->n_chunks = int32_t(n - 1); e->used = int32_t((n - 1) * cs); }
+  else { e->n_chunks = int32_t(n); e->used = int32_t(rows); }
+}
+
+int build_plan(xv_ark_reader* r) {
+  const xv_ark_reader_opts& o = r->o;
+  r->ok.clear(); r->row_in_batch.clear(); r->seg_len_all.clear(); r->first_seg_all.clear(); r->batches.clear(); r->tasks.clear();
+  xv_ark_index_info& inf = r->info;
+  inf.n_entries = int64_t(r->entries.size());
+  inf.n_ok = inf.n_fail = inf.n_segments = inf.rows_used = inf.key_bytes = 0;
+  Batch cur{};
+  bool open = false;
+  auto close_batch = [&]() {
+    if (!open) return;
+    cur.u1 = int64_t(r->ok.size());
+    r->first_seg_all.push_back(cur.n_seg);
+    // tasks: runs of utterances of about TASK_BYTES
+    int64_t bytes = 0, t0 = cur.u0;
+    cur.n_tasks = 0;
+    for (int64_t u = cur.u0; u < cur.u1; ++u) {
+      bytes += int64_t(r->entries[r->ok[u]].used) * o.feat_dim * 4;
+      if (bytes >= TASK_BYTES || u + 1 == cur.u1) {
+        r->tasks.push_back(Task{int32_t(r->batches.size()), t0, u + 1});
+        ++cur.n_tasks;
+        t0 = u + 1;
+        bytes = 0;
+      }
+    }
+    r->batches.push_back(cur);
+    open = false;
+  };
+  for (size_t i = 0; i < r->entries.size(); ++i) {
+    Entry& e = r->entries[i];
+    plan_entry(o, &e);
+    if (e.n_chunks == 0) { ++inf.n_fail; continue; }
+    if (open && cur.n_rows + e.used > std::max<int64_t>(o.batch_frames, e.used)) close_batch();
+    if (!open) {
+      cur = Batch{};
+      cur.u0 = int64_t(r->ok.size());
+      cur.seg0 = int64_t(r->seg_len_all.size());
+      cur.first0 = int64_t(r->first_seg_all.size());
+      open = true;
+    }
+    r->row_in_batch.push_back(cur.n_rows);
+    r->first_seg_all.push_back(cur.n_seg);
+    const int64_t cs = o.chunk_size;
+    for (int32_t c = 0; c < e.n_chunks; ++c) {
+      const int32_t len = e.n_chunks == 1 && (cs == -1 || e.rows <= cs) ? e.used : int32_t(std::min<int64_t>(cs, e.rows - int64_t(c) * cs));
+      r->seg_len_all.push_back(len);
+    }
+    cur.n_seg += e.n_chunks;
+    cur.n_rows += e.used;
+    r->ok.push_back(int64_t(i));
+    ++inf.n_ok;
+    inf.n_segments += e.n_chunks;
+    inf.rows_used += e.used;
+    inf.key_bytes += e.key_len;
+  }
+  close_batch();
+  inf.n_batches = int64_t(r->batches.size());
+  inf.first_marker_off = r->entries.empty() ? -1 : r->entries[0].payload_off - 15;
+  return XV_OK;
+}
+
+// Scan [from, ...) as a chain of entries, keeping those whose marker lies below byte_end.
+int scan_stripe(xv_ark_reader* r, int64_t from, bool first_is_candidate) {
+  const xv_ark_reader_opts& o = r->o;
+  const int64_t end_limit = o.byte_end < 0 ? r->file_size : std::min<int64_t>(o.byte_end, r->file_size);
+  r->entries.clear();
+  r->scan_from = from;
+  r->first_is_candidate = first_is_candidate;
+  xv_ark_index_info& inf = r->info;
+  inf = xv_ark_index_info{};
+  inf.stopped_at = -1;
+  inf.next_marker_off = inf.next_key_off = r->file_size;
+  constexpr int64_t CHUNK = 8192;
+  std::vector<int64_t> ko(CHUNK), po(CHUNK);
+  std::vector<int32_t> kl(CHUNK), rw(CHUNK), cl(CHUNK), eb(CHUNK);
+  int64_t pos = from;
+  bool done = false;
+  while (!done && pos < r->file_size) {
+    int64_t consumed = 0;
+    const int64_t n = xv_ark_scan(r->map + pos, r->file_size - pos, CHUNK, ko.data(), kl.data(), rw.data(), cl.data(), eb.data(),
+                                  po.data(), &consumed);
+    if (n < 0) return fail(XV_EINVAL, "xv_ark_scan failed");
+    for (int64_t i = 0; i < n; ++i) {
+      const int64_t marker = pos + po[i] - 15;
+      if (marker >= end_limit) {
+        inf.next_marker_off = marker;
+        inf.next_key_off = pos + ko[i];
+        done = true;
+        break;
+      }
+      if (cl[i] != o.feat_dim && rw[i] > 0)
+        return fail(XV_EINVAL, "utterance " + std::string(reinterpret_cast<const char*>(r->map + pos + ko[i]), size_t(kl[i])) +
+                                   " has feature dim " + std::to_string(cl[i]) + ", model expects " + std::to_string(o.feat_dim));
+      Entry e{};
+      e.key_off = pos + ko[i]; e.key_len = kl[i]; e.rows = rw[i]; e.elem = eb[i]; e.payload_off = pos + po[i];
+      r->entries.push_back(e);
+    }
+    if (done) break;
+    if (n < CHUNK) {
+      if (pos + consumed < r->file_size) {
+        // trailing white space is tolerated (a text-mode tail); anything else is an entry this scanner does not know
+        int64_t q = pos + consumed;
+        while (q < r->file_size && ark_space(r->map[q])) ++q;
+        if (q < r->file_size) inf.stopped_at = pos + consumed;
+      }
+      break;
+    }
+    pos += consumed;
+  }
+  return build_plan(r);
+}
+
+void worker_main(xv_ark_reader* r) {
+  std::vector<double> tmp;
+  for (;;) {
+    Task t;
+    {
+      std::unique_lock<std::mutex> lk(r->mu);
+      for (;;) {
+        if (r->stop || !r->error.empty()) return;
+        if (r->next_task < r->tasks.size() && r->tasks[r->next_task].batch < r->released + int64_t(r->slot_buf.size())) break;
+        if (r->next_task >= r->tasks.size()) return;
+        r->cv_work.wait(lk);
+      }
+      t = r->tasks[r->next_task++];
+    }
+    const Batch& b = r->batches[t.batch];
+    float* base = r->slot_buf[t.batch % r->slot_buf.size()];
+    std::string err;
+    for (int64_t u = t.u0; u < t.u1 && err.empty(); ++u) {
+      const Entry& e = r->entries[r->ok[u]];
+      float* dst = base + r->row_in_batch[u] * r->o.feat_dim;
+      const int64_t n_val = int64_t(e.used) * r->o.feat_dim;
+      uint8_t* p;
+      int64_t need;
+      if (e.elem == 4) { p = reinterpret_cast<uint8_t*>(dst); need = n_val * 4; }
+      else { tmp.resize(size_t(n_val)); p = reinterpret_cast<uint8_t*>(tmp.data()); need = n_val * 8; }
+      int64_t got = 0;
+      while (got < need) {
+        const ssize_t k = pread(r->fd, p + got, size_t(need - got), off_t(e.payload_off + got));
+        if (k <= 0) { err = "truncated matrix payload at byte " + std::to_string(e.payload_off + got); break; }
+        got += k;
+      }
+      if (e.elem == 8 && err.empty())
+        for (int64_t i = 0; i < n_val; ++i) dst[i] = float(tmp[size_t(i)]);
+    }
+    (void)b;
+    {
+      std::lock_guard<std::mutex> lk(r->mu);
+      if (!err.empty() && r->error.empty()) r->error = err;
+      if (++r->batch_done[t.batch] == r->batches[t.batch].n_tasks || !r->error.empty()) r->cv_ready.notify_all();
+      if (!r->error.empty()) r->cv_work.notify_all();
+    }
+  }
+}
+
+void stop_workers(xv_ark_reader* r) {
+  {
+    std::lock_guard<std::mutex> lk(r->mu);
+    r->stop = true;
+  }
+  r->cv_work.notify_all();
+  r->cv_ready.notify_all();
+  for (auto& w : r->workers) if (w.joinable()) w.join();
+  r->workers.clear();
+}
+
+}  // namespace arkjob
+
+extern "C" {
+
+int xv_ark_reader_open(xv_ark_reader** out, const char* path, const xv_ark_reader_opts* opts) {
+  if (!out || !path || !opts) return fail(XV_EINVAL, "null argument");
+  *out = nullptr;
+  if (opts->feat_dim <= 0 || opts->n_threads < 1 || opts->n_slots < 2 || opts->batch_frames < 1 || opts->byte_begin < 0 ||
+      opts->min_chunk_size < 0 || (opts->chunk_size < 1 && opts->chunk_size != -1))
+    return fail(XV_EINVAL, "xv_ark_reader_open: bad options");
+  if (opts->chunk_size != -1 && opts->chunk_size < opts->min_chunk_size)
+    return fail(XV_EINVAL, "chunk_size is smaller than min_chunk_size: no chunk would ever be evaluated");
+  const int fd = open(path, O_RDONLY | O_CLOEXEC);
+  if (fd < 0) return fail(XV_EINVAL, std::string("cannot open ") + path + ": " + strerror(errno));
+  struct stat st;
+  if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) {
+    close(fd);
+    return fail(XV_EINVAL, std::string(path) + " is not a regular file");
+  }
+  xv_ark_reader* r = new xv_ark_reader();
+  r->o = *opts;
+  r->fd = fd;
+  r->file_size = int64_t(st.st_size);
+  if (r->file_size > 0) {
+    void* m = mmap(nullptr, size_t(r->file_size), PROT_READ, MAP_SHARED, fd, 0);
+    if (m == MAP_FAILED) {
+      close(fd);
+      delete r;
+      return fail(XV_ENOMEM, std::string("mmap of ") + path + " failed: " + strerror(errno));
+    }
+    r->map = static_cast<const uint8_t*>(m);
+  }
+  *out = r;
+  return XV_OK;
+}
+
+int xv_ark_reader_index(xv_ark_reader* r, xv_ark_index_info* info) {
+  if (!r || !info) return fail(XV_EINVAL, "null argument");
+  if (r->started) return fail(XV_ESTATE, "the reader has been started");
+  int64_t from = std::min(r->o.byte_begin, r->file_size);
+  bool candidate = false;
+  if (!r->o.begin_is_boundary && from > 0) {
+    const int64_t h = arkjob::resync(r, from);
+    if (h < 0) from = r->file_size;
+    else {
+      // provisional key start: the longest run of key characters in front of the separating space (the previous payload's
+      // last bytes may look like key characters too; xv_ark_reader_set_first fixes it)
+      int64_t k = h - 1;
+      while (k > 0 && arkjob::key_char(r->map[k - 1]) && h - k < 4096) --k;
+      from = k;
+      candidate = true;
+    }
+  }
+  int rc = arkjob::scan_stripe(r, from, candidate);
+  if (rc != XV_OK) return rc;
+  *info = r->info;
+  return XV_OK;
+}
+
+int xv_ark_reader_set_first(xv_ark_reader* r, int64_t marker_off, int64_t key_off, xv_ark_index_info* info) {
+  if (!r || !info) return fail(XV_EINVAL, "null argument");
+  if (r->started) return fail(XV_ESTATE, "the reader has been started");
+  const int64_t end_limit = r->o.byte_end < 0 ? r->file_size : std::min<int64_t>(r->o.byte_end, r->file_size);
+  if (marker_off < 0 || key_off < 0 || key_off > marker_off) return fail(XV_EINVAL, "bad boundary");
+  if (marker_off >= end_limit) {
+    // the previous stripe's chain runs past this stripe: it is empty, and hands the same boundary on
+    r->entries.clear();
+    r->first_is_candidate = false;
+    int rc = arkjob::build_plan(r);
+    if (rc != XV_OK) return rc;
+    r->info.stopped_at = -1;
+    r->info.next_marker_off = marker_off;
+    r->info.next_key_off = key_off;
+  } else if (!r->entries.empty() && r->entries[0].payload_off - 15 == marker_off) {
+    // the candidate was right: fix where its key starts
+    arkjob::Entry& e = r->entries[0];
+    e.key_len = int32_t(marker_off - 1 - key_off);
+    e.key_off = key_off;
+    r->first_is_candidate = false;
+    int rc = arkjob::build_plan(r);
+    if (rc != XV_OK) return rc;
+  } else {
+    int rc = arkjob::scan_stripe(r, key_off, false);       // re-index from the true boundary
+    if (rc != XV_OK) return rc;
+  }
+  *info = r->info;
+  return XV_OK;
+}
+
+int xv_ark_reader_keys(const xv_ark_reader* r, char* blob, int64_t blob_cap, int64_t* key_off) {
+  if (!r || !key_off || (!blob && blob_cap > 0)) return fail(XV_EINVAL, "null argument");
+  if (blob_cap < r->info.key_bytes) return fail(XV_ENOMEM, "key buffer too small");
+  int64_t pos = 0;
+  for (size_t i = 0; i < r->ok.size(); ++i) {
+    const arkjob::Entry& e = r->entries[r->ok[i]];
+    key_off[i] = pos;
+    memcpy(blob + pos, r->map + e.key_off, size_t(e.key_len));
+    pos += e.key_len;
+  }
+  key_off[r->ok.size()] = pos;
+  return XV_OK;
+}
+
+int xv_ark_reader_failures(const xv_ark_reader* r, int32_t* reason, int32_t* rows, char* blob, int64_t blob_cap, int64_t* key_off) {
+  if (!r || !reason || !rows || !key_off) return fail(XV_EINVAL, "null argument");
+  int64_t pos = 0, n = 0;
+  for (const arkjob::Entry& e : r->entries) {
+    if (e.n_chunks != 0) continue;
+    if (pos + e.key_len > blob_cap) return fail(XV_ENOMEM, "key buffer too small");
+    reason[n] = e.reason; rows[n] = e.rows; key_off[n] = pos;
+    memcpy(blob + pos, r->map + e.key_off, size_t(e.key_len));
+    pos += e.key_len;
+    ++n;
+  }
+  key_off[n] = pos;
+  return XV_OK;
+}
+
+int xv_ark_reader_start(xv_ark_reader* r, int64_t dst_row_base) {
+  if (!r) return fail(XV_EINVAL, "null argument");
+  if (r->started) return fail(XV_ESTATE, "the reader has been started");
+  if (r->first_is_candidate) return fail(XV_ESTATE, "the stripe's first entry is unconfirmed: call xv_ark_reader_set_first");
+  r->dst_row_all.resize(r->ok.size());
+  for (size_t i = 0; i < r->ok.size(); ++i) r->dst_row_all[i] = dst_row_base + int64_t(i);
+  int64_t rows = 1;
+  for (const auto& b : r->batches) rows = std::max(rows, b.n_rows);
+  r->slot_rows = rows;
+  const int n_slots = int(std::min<int64_t>(r->o.n_slots, std::max<int64_t>(int64_t(r->batches.size()), 1)));
+  r->slot_buf.assign(size_t(n_slots), nullptr);
+  r->slot_bytes.assign(size_t(n_slots), 0);
+  for (int s = 0; s < n_slots; ++s) {
+    const size_t bytes = size_t(rows) * r->o.feat_dim * 4;
+    r->slot_bytes[s] = bytes;
+    if (r->o.pinned) {
+      r->slot_buf[s] = arkjob::pinned_pool().take(bytes);
+      if (r->slot_buf[s]) continue;
+      cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&r->slot_buf[s]), bytes, cudaHostAllocDefault);
+      if (e != cudaSuccess) return fail(XV_ECUDA, std::string("cudaHostAlloc of a batch buffer: ") + cudaGetErrorString(e));
+    } else {
+      r->slot_buf[s] = static_cast<float*>(malloc(bytes));
+      if (!r->slot_buf[s]) return fail(XV_ENOMEM, "out of memory for a batch buffer");
+    }
+  }
+  r->batch_done.assign(r->batches.size(), 0);
+  r->started = true;
+  const int n_threads = int(std::min<size_t>(size_t(r->o.n_threads), std::max<size_t>(r->tasks.size(), 1)));
+  for (int i = 0; i < n_threads; ++i) r->workers.emplace_back(arkjob::worker_main, r);
+  return XV_OK;
+}
+
+int xv_ark_reader_next(xv_ark_reader* r, xv_ark_batch* batch) {
+  if (!r || !batch) return fail(XV_EINVAL, "null argument");
+  if (!r->started) return fail(XV_ESTATE, "the reader has not been started");
+  *batch = xv_ark_batch{};
+  if (r->next_batch >= int64_t(r->batches.size())) return XV_OK;      // n_utt == 0: end of the stripe
+  const int64_t bi = r->next_batch;
+  {
+    std::unique_lock<std::mutex> lk(r->mu);
+    r->cv_ready.wait(lk, [&] { return !r->error.empty() || r->batch_done[bi] == r->batches[bi].n_tasks; });
+    if (!r->error.empty()) return fail(XV_EINVAL, r->error);
+  }
+  const arkjob::Batch& b = r->batches[bi];
+  batch->slot = int32_t(bi % int64_t(r->slot_buf.size()));
+  batch->n_seg = b.n_seg;
+  batch->n_utt = int32_t(b.u1 - b.u0);
+  batch->n_rows = b.n_rows;
+  batch->feats = r->slot_buf[batch->slot];
+  batch->seg_len = r->seg_len_all.data() + b.seg0;
+  batch->utt_first_seg = r->first_seg_all.data() + b.first0;
+  batch->utt_dst_row = r->dst_row_all.data() + b.u0;
+  batch->first_ok_index = b.u0;
+  ++r->next_batch;
+  return XV_OK;
+}
+
+int xv_ark_reader_release(xv_ark_reader* r, int32_t slot) {
+  if (!r) return fail(XV_EINVAL, "null argument");
+  {
+    std::lock_guard<std::mutex> lk(r->mu);
+    if (r->released >= r->next_batch) return fail(XV_ESTATE, "no batch is out");
+    if (slot != int32_t(r->released % int64_t(r->slot_buf.size()))) return fail(XV_ESTATE, "batches must be released in order");
+    ++r->released;
+  }
+  r->cv_work.notify_all();
+  return XV_OK;
+}
+
+void xv_ark_reader_close(xv_ark_reader* r) {
+  if (!r) return;
+  arkjob::stop_workers(r);
+  for (size_t s = 0; s < r->slot_buf.size(); ++s) {
+    float* p = r->slot_buf[s];
+    if (!p) continue;
+    if (!r->o.pinned) free(p);
+    else if (!arkjob::pinned_pool().give(p, r->slot_bytes[s])) cudaFreeHost(p);
+  }
+  if (r->map) munmap(const_cast<uint8_t*>(r->map), size_t(r->file_size));
+  if (r->fd >= 0) close(r->fd);
+  delete r;
+}
+
+int64_t xv_vec_ark_bytes(const int64_t* key_off, int64_t n, int32_t dim) {
+  if (!key_off || n < 0 || dim < 0) return -1;
+  return (key_off[n] - key_off[0]) + n * (11 + int64_t(dim) * 4);
+}
+
+int64_t xv_vec_ark_format(const char* key_blob, const int64_t* key_off, int64_t n, const float* vecs, int32_t dim, uint8_t* out,
+                          int64_t out_cap, int64_t* marker_off, int32_t n_threads) {
+  if (!key_off || n < 0 || dim < 0 || (n > 0 && (!key_blob || !vecs || !out))) return fail(XV_EINVAL, "bad argument");
+  const int64_t total = xv_vec_ark_bytes(key_off, n, dim);
+  if (total > out_cap) return fail(XV_ENOMEM, "output buffer too small");
+  const int64_t per = 11 + int64_t(dim) * 4;
+  auto run = [&](int64_t i0, int64_t i1) {
+    for (int64_t i = i0; i < i1; ++i) {
+      const int64_t klen = key_off[i + 1] - key_off[i];
+      uint8_t* p = out + (key_off[i] - key_off[0]) + i * per;
+      memcpy(p, key_blob + key_off[i], size_t(klen));
+      p += klen;
+      if (marker_off) marker_off[i] = (p + 1) - out;
+      const uint8_t head[7] = {' ', 0, 'B', 'F', 'V', ' ', 4};
+      memcpy(p, head, 7);
+      const uint32_t d = uint32_t(dim);
+      memcpy(p + 7, &d, 4);
+      memcpy(p + 11, vecs + i * int64_t(dim), size_t(dim) * 4);
+    }
+  };
+  const int nt = int(std::max<int64_t>(1, std::min<int64_t>(n_threads, n / 4096)));
+  if (nt <= 1) run(0, n);
+  else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) th.emplace_back(run, n * t / nt, n * (t + 1) / nt);
+    for (auto& x : th) x.join();
+  }
+  return total;
+}
+
+int64_t xv_scp_format(const char* key_blob, const int64_t* key_off, int64_t n, const char* ark_name, int64_t base,
+                      const int64_t* marker_off, char* out, int64_t out_cap) {
+  if (!key_off || !ark_name || !marker_off || n < 0 || (n > 0 && (!key_blob || !out))) return fail(XV_EINVAL, "bad argument");
+  const size_t name_len = strlen(ark_name);
+  int64_t pos = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t klen = key_off[i + 1] - key_off[i];
+    if (pos + klen + int64_t(name_len) + 24 > out_cap) return fail(XV_ENOMEM, "output buffer too small");
+    memcpy(out + pos, key_blob + key_off[i], size_t(klen));
+    pos += klen;
+    out[pos++] = ' ';
+    memcpy(out + pos, ark_name, name_len);
+    pos += int64_t(name_len);
+    out[pos++] = ':';
+    char digits[24];
+    int nd = 0;
+    uint64_t v = uint64_t(base + marker_off[i]);
+    do { digits[nd++] = char('0' + v % 10); v /= 10; } while (v);
+    while (nd) out[pos++] = digits[--nd];
+    out[pos++] = '\n';
+  }
+  return pos;
+}
+
+}  // extern "C"

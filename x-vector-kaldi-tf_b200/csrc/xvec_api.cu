@@ -1300,3 +1300,6 @@ int xv_set_option(xv_model* m, const char* name, int64_t value) {
 
 // ---- host-only: ark index for the extractor's reader (xv_ark_scan, include/xvec.h) ----
 #include "ark_scan.cuh"
+
+// ---- host-only: striped ark reader + vector-ark formatter of an extraction job (include/xvec_job.h) ----
+#include "ark_job.cuh"

@@ -951,6 +951,16 @@ class ArkScpWriter(object):
         self.ark.write(b"".join(blobs))
         self.scp.write("".join(lines))
 
+    def write_vec_block(self, key_blob, key_off, vectors):
+        """``write_vec_entries`` for a block whose keys come as one uint8 blob + int64 offsets [n + 1]: ark bytes and scp
+        lines are formatted natively (xv_vec_ark_format / xv_scp_format, include/xvec_job.h), same bytes."""
+        from ._native import scp_format, vec_ark_format
+        blob, markers = vec_ark_format(key_blob, key_off, vectors, with_markers=True)
+        lines = scp_format(key_blob, key_off, self.name, self.pos, markers)
+        self.pos += int(blob.shape[0])
+        self.ark.write(memoryview(blob))
+        self.scp.write(lines.tobytes().decode())
+
     def close(self):
         self.ark.close()
         self.scp.close()

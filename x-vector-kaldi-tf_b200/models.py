@@ -156,6 +156,7 @@ class Model(object):
         self.params = None
         self.meta = None
         self._engine = None
+        self._loaded_stamp = None
 
     # ------------------------------------------------------------------ build / save / load
     def build_model(self, num_classes, input_feature_dim, output_dir, logger=None):
@@ -546,12 +547,31 @@ class Model(object):
             from ._native import XvCmvnOpts
             cmvn_opts = XvCmvnOpts()
         device = set_cuda_visible_devices(use_gpu=use_gpu, logger=logger)
-        self.load_model(None, model_dir, logger)
+        # a Model that extracts repeatedly from the same, unchanged model directory keeps its variables and its device
+        # engine (the reference pays a full graph restore per call, models.py:365-366)
+        stamp = _model_dir_stamp(model_dir)
+        if self._engine is None or self._loaded_stamp != stamp:
+            self.load_model(None, model_dir, logger)
+            if self._engine is not None:
+                getattr(self._engine, "close", lambda: None)()
+                self._engine = None
+            self._loaded_stamp = stamp
         engine = self._get_engine(device)
         feat_dim = self.meta["input_feature_dim"]
         emb_dim = self.embedding_sizes[0]
         batch_frames = int(os.environ.get("XVEC_BATCH_FRAMES", "400000"))
         rank, world = sharding.dist_info()
+
+        # A feature ark in a regular file takes the native job path: no per-utterance Python at all (headers indexed and
+        # batches filled by libxvec_b200.so's reader, chunk averages finished on the device, vector ark formatted natively).
+        # Pipes (the recipe's Kaldi feature pipe), in-memory streams, scp tables, text / compressed matrices, the device
+        # front end and DEBUG logging (one line per utterance) keep the general path below.
+        if not device_frontend and os.environ.get("XVEC_NATIVE_READER", "1") != "0" and \
+                not (logger is not None and logger.isEnabledFor(10)):
+            source = _regular_ark_file(input_stream)
+            if source is not None and self._make_embedding_from_ark_file(source, output_stream, engine, device, min_chunk_size,
+                                                                         chunk_size, batch_frames, logger, start_time):
+                return
 
         # page-locked staging buffers: the reader thread fills one while two batches are in flight on the GPU
         staging = _Staging(feat_dim, batch_frames, with_vad=vad_table is not None)
@@ -626,6 +646,118 @@ class Model(object):
             logger.info("Total time for neural network computations is %.2f minutes." % (total_gpu_waiting / 60.0))
             logger.info("Elapsed time for extracting whole embeddings is %.2f minutes." %
                         ((time.time() - start_time) / 60.0))
+
+    def _make_embedding_from_ark_file(self, source, output_stream, engine, device, min_chunk_size, chunk_size, batch_frames,
+                                      logger, start_time):
+        """make_embedding over an ark in a regular file (reference models.py:373-432, same skip rules, chunk plan, average,
+        output bytes and log lines).  Returns False -- having touched nothing -- when the archive holds entries the native
+        scanner does not parse, so that the caller can take the general path."""
+        from . import ark_job
+        path, start = source
+        rank, world = sharding.dist_info()
+        feat_dim, emb_dim = self.meta["input_feature_dim"], self.embedding_sizes[0]
+        on_gpu = getattr(engine, "handle", None) is not None       # a device engine (stand-ins of the host-logic tests have none)
+        dev_name = "cuda:%d" % device if on_gpu else "cpu"
+        reader, counts = ark_job.open_striped_reader(path, start, feat_dim, min_chunk_size, chunk_size, batch_frames,
+                                                     device=dev_name, pinned=on_gpu)
+        if reader is None:
+            return False
+        peer = None
+        try:
+            info = reader.info
+            if logger is not None:
+                for key, reason, rows in reader.failures():
+                    if reason == 1:
+                        logger.warning("Zero-length utterance: '%s'" % key)
+                    else:
+                        logger.warning("Minimum chunk size of %d is greater than the number of rows in utterance: %s" %
+                                       (min_chunk_size, key))
+            n_ok_total = int(counts[:, 1].sum())
+            base = int(counts[:rank, 1].sum())
+            key_blob, key_off = reader.keys()
+            sink = ark_job.VectorSink(output_stream) if rank == 0 else None
+            use_peer = world > 1 and on_gpu
+            if use_peer:
+                # rank 0 owns the job's result table; every rank's utt_average_kernel stores its rows there over NVLink
+                import torch.distributed as dist
+                from ._native import PeerTable
+                if rank == 0:
+                    peer = PeerTable.create(device, max(n_ok_total, 1), emb_dim)
+                box = [peer.handle if rank == 0 else None]
+                dist.broadcast_object_list(box, src=0)
+                if rank != 0:
+                    peer = PeerTable.open(device, max(n_ok_total, 1), emb_dim, box[0])
+            reader.start(base if use_peer else 0)
+            host_rows = [None, None]                     # page-locked [n_utt, emb_dim] per submission slot (not needed with a peer table)
+            local = [] if (world > 1 and not use_peer) else None
+            total_gpu_waiting = 0.0
+            pending = None
+            k = 0
+            while True:
+                b = reader.next()
+                submitted = None
+                if b is not None:
+                    out_host = None
+                    if not use_peer:
+                        if host_rows[k & 1] is None or host_rows[k & 1].shape[0] < b.n_utt:
+                            host_rows[k & 1] = _pinned_rows(max(2 * b.n_utt, 1024), emb_dim, on_gpu)
+                        out_host = host_rows[k & 1][:b.n_utt]
+                    t0 = time.time()
+                    ticket = engine.submit_host_utts(b.feats, b.seg_len, utt_first_seg=b.utt_first_seg,
+                                                     dst_rows=b.utt_dst_row if use_peer else None,
+                                                     out_dev=peer if use_peer else None, out_host=out_host)
+                    total_gpu_waiting += time.time() - t0
+                    submitted = (ticket, b, out_host)
+                    k += 1
+                if pending is not None:
+                    ticket, done, rows = pending
+                    t0 = time.time()
+                    engine.collect(ticket)
+                    total_gpu_waiting += time.time() - t0
+                    if world == 1:
+                        sink.write(key_blob, key_off[done.first_ok_index:done.first_ok_index + done.n_utt + 1], rows)
+                    elif not use_peer:
+                        local.append(rows.copy())
+                    reader.release(done.slot)
+                pending = submitted
+                if b is None:
+                    break
+            if world > 1:
+                import torch.distributed as dist
+                blobs = ark_job.gather_bytes_to_rank0(key_blob, dev_name)
+                lens = ark_job.gather_bytes_to_rank0(np.diff(key_off).astype(np.int32).view(np.uint8), dev_name)
+                full = None
+                if use_peer:
+                    import torch
+                    torch.cuda.synchronize(device)
+                    dist.barrier()                       # every rank's rows are in rank 0's table
+                else:                                    # no peer memory (gloo): one gather of the host rows
+                    emb = np.concatenate(local, axis=0) if local else np.zeros((0, emb_dim), np.float32)
+                    full = sharding.gather_to_rank0(np.arange(base, base + emb.shape[0], dtype=np.int64), emb, n_ok_total,
+                                                    emb_dim, device=dev_name)
+                if rank == 0:
+                    all_blob = np.concatenate(blobs) if blobs else np.zeros(0, np.uint8)
+                    all_len = np.concatenate([l.view(np.int32) for l in lens]) if lens else np.zeros(0, np.int32)
+                    all_off = np.concatenate([[0], np.cumsum(all_len, dtype=np.int64)])
+                    block = 1 << 16
+                    for r0 in range(0, n_ok_total, block):
+                        n = min(block, n_ok_total - r0)
+                        rows = peer.read(r0, n) if use_peer else full[r0:r0 + n]
+                        sink.write(all_blob, all_off[r0:r0 + n + 1], rows)
+                if use_peer:
+                    dist.barrier()                       # rank 0 has read the table: the mappings may go
+            if logger is not None:
+                n_entries, n_ok, n_fail, rows_used = (int(counts[:, i].sum()) for i in range(4))
+                logger.info("Processed %d features of average size %d frames. Done %d and failed %d" %
+                            (n_entries, rows_used / max(n_entries, 1), n_ok, n_fail))
+                logger.info("Total time for neural network computations is %.2f minutes." % (total_gpu_waiting / 60.0))
+                logger.info("Elapsed time for extracting whole embeddings is %.2f minutes." %
+                            ((time.time() - start_time) / 60.0))
+            return True
+        finally:
+            reader.close()
+            if peer is not None:
+                peer.close()
 
     def _read_batches(self, input_stream, staging, work, counters, min_chunk_size, chunk_size, batch_frames,
                       rank, world, logger, device_frontend=False, vad_table=None):
@@ -742,6 +874,48 @@ class Model(object):
         if batch is not None and batch.utts:
             batch.wait_for_payloads(pool)
             work.put(batch)
+
+
+def _model_dir_stamp(model_dir):
+    """Identity of a model directory's contents: path + size / mtime of the files load_model reads."""
+    out = [os.path.realpath(model_dir)]
+    for name in ("model.meta", "model.npz", "model.index", "done"):
+        try:
+            st = os.stat(os.path.join(model_dir, name))
+            out.append((name, st.st_size, st.st_mtime_ns))
+        except OSError:
+            out.append((name, None))
+    return tuple(out)
+
+
+def _regular_ark_file(input_stream):
+    """(path, start offset) when ``input_stream`` is a binary archive in a regular file the native reader can open: a
+    buffered reader (its position is the start) or a plain / ``ark:``-prefixed file name; None otherwise."""
+    import io
+    import stat
+    if isinstance(input_stream, io.BufferedReader):
+        try:
+            if stat.S_ISREG(os.fstat(input_stream.fileno()).st_mode):
+                return "/proc/self/fd/%d" % input_stream.fileno(), input_stream.tell()
+        except (OSError, ValueError):
+            return None
+        return None
+    if isinstance(input_stream, str):
+        name = input_stream.strip()
+        if name.startswith("ark:"):
+            name = name[4:]
+        if "|" in name or name.endswith(".gz") or ":" in name or not os.path.isfile(name):
+            return None
+        return name, 0
+    return None
+
+
+def _pinned_rows(rows, cols, pinned):
+    try:
+        import torch
+        return torch.empty((rows, cols), dtype=torch.float32, pin_memory=bool(pinned and torch.cuda.is_available())).numpy()
+    except ImportError:
+        return np.empty((rows, cols), dtype=np.float32)
 
 
 def _write_vectors(output_stream, keys, vectors):
