@@ -676,7 +676,9 @@ def measure_product(args, dev, rank, world, params, topo):
                    first_call=dict(seconds=round(runs[0], 4), value=round(total_frames / runs[0], 1),
                                    note="includes Model.load_model, weight upload and the first allocation of page-locked "
                                         "batch buffers / device workspaces"),
-                   all_runs_s=[round(r, 4) for r in runs], reader_threads=os.environ.get("XVEC_READER_THREADS", "default"),
+                   all_runs_s=[round(r, 4) for r in runs],
+                   rank0_breakdown_s={k: (round(v, 4) if isinstance(v, float) else v) for k, v in getattr(model, "last_job_stats", {}).items()},
+                   batch_frames=int(os.environ.get("XVEC_BATCH_FRAMES", "0")) or "default", reader_threads=os.environ.get("XVEC_READER_THREADS", "default"),
                    check=check)
     except Exception as err:                                     # noqa: BLE001  (a diagnostic block must not cost the bench line)
         import traceback

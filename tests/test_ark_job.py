@@ -329,3 +329,33 @@ def test_three_rank_gloo_job_over_a_striped_file_is_byte_identical(T_model_dir, 
                        capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stderr[-3000:]
     assert open(out_path, "rb").read() == single.getvalue()          # same keys, same order, same bytes
+
+
+@pytest.mark.parametrize("poison", [False, True])
+def test_parallel_index_of_a_large_stripe_equals_the_sequential_chain(tmp_path, poison):
+    # stripes of more than a few MB are indexed by several threads from resynchronised sub-range starts and stitched
+    path = str(tmp_path / "big.ark")
+    utts = _random_ark(path, 21, 700, lo=100, hi=900, double_every=13, poison=poison)
+    assert os.path.getsize(path) > 24 << 20
+    ok, fail = _expected(utts, 25, 400)
+    seq = _native.ArkReader(path, 23, 25, 400, 60000, n_threads=1, pinned=False)
+    par = _native.ArkReader(path, 23, 25, 400, 60000, n_threads=6, pinned=False)
+    a, b = seq.index(), par.index()
+    assert a == b and a["n_ok"] == len(ok) and a["n_fail"] == len(fail)
+    ka, kb = seq.keys(), par.keys()
+    assert np.array_equal(ka[0], kb[0]) and np.array_equal(ka[1], kb[1])
+    got, sizes = _drain(par)
+    assert all(np.array_equal(rows, m[:sum(segs)]) and segs == want for (rows, segs, _), (_, m, want) in zip(got, ok))
+    assert sizes[0] <= 60000                                   # (ramp-up only applies to batch_frames >= 131072)
+    seq.close(); par.close()
+    # two ranks, each with a parallel index of its stripe
+    readers, infos, _ = _striped(path, 2, chunk=400, batch_frames=200000)
+    assert sum(i["n_ok"] for i in infos) == len(ok)
+    keys = []
+    for rd, info in zip(readers, infos):
+        blob, off = rd.keys()
+        keys += [blob.tobytes()[off[i]:off[i + 1]].decode() for i in range(info["n_ok"])]
+        got, sizes = _drain(rd)
+        assert sizes[0] <= 200000 // 8 + 900 and sizes[1] <= 200000 // 4 + 900       # ramp-up: 1/8, 1/4, 1/2, full
+        rd.close()
+    assert keys == [k for k, _, _ in ok]

@@ -191,7 +191,11 @@ int build_plan(xv_ark_reader* r) {
     Entry& e = r->entries[i];
     plan_entry(o, &e);
     if (e.n_chunks == 0) { ++inf.n_fail; continue; }
-    if (open && cur.n_rows + e.used > std::max<int64_t>(o.batch_frames, e.used)) close_batch();
+    // the first batches are small, so that the device starts after a fraction of a millisecond of reading: 1/8, 1/4, 1/2
+    // of batch_frames, then full batches (a batch of 50 000 frames already runs the kernels at full efficiency)
+    const int64_t nb = int64_t(r->batches.size());
+    const int64_t target = (o.batch_frames >= 131072 && nb < 3) ? (o.batch_frames >> (3 - nb)) : o.batch_frames;
+    if (open && cur.n_rows + e.used > std::max<int64_t>(target, e.used)) close_batch();
     if (!open) {
       cur = Batch{};
       cur.u0 = int64_t(r->ok.size());
@@ -220,7 +224,69 @@ int build_plan(xv_ark_reader* r) {
   return XV_OK;
 }
 
-// Scan [from, ...) as a chain of entries, keeping those whose marker lies below byte_end.
+// Chain scan of [from, ...): the entries whose marker lies below end_limit, and what follows them.  Thread-safe (no fail()).
+struct RangeScan {
+  std::vector<Entry> entries;
+  int64_t next_marker = 0, next_key = 0, stopped_at = -1;
+  std::string err;
+};
+
+void scan_range(const xv_ark_reader* r, int64_t from, int64_t end_limit, RangeScan* out) {
+  const xv_ark_reader_opts& o = r->o;
+  out->entries.clear();
+  out->stopped_at = -1;
+  out->next_marker = out->next_key = r->file_size;
+  out->err.clear();
+  constexpr int64_t CHUNK = 4096;
+  std::vector<int64_t> ko(CHUNK), po(CHUNK);
+  std::vector<int32_t> kl(CHUNK), rw(CHUNK), cl(CHUNK), eb(CHUNK);
+  int64_t pos = from;
+  while (pos < r->file_size) {
+    int64_t consumed = 0;
+    const int64_t n = xv_ark_scan(r->map + pos, r->file_size - pos, CHUNK, ko.data(), kl.data(), rw.data(), cl.data(), eb.data(),
+                                  po.data(), &consumed);
+    if (n < 0) { out->err = "xv_ark_scan failed"; return; }
+    for (int64_t i = 0; i < n; ++i) {
+      const int64_t marker = pos + po[i] - 15;
+      if (marker >= end_limit) {
+        out->next_marker = marker;
+        out->next_key = pos + ko[i];
+        return;
+      }
+      if (cl[i] != o.feat_dim && rw[i] > 0) {
+        out->err = "utterance " + std::string(reinterpret_cast<const char*>(r->map + pos + ko[i]), size_t(kl[i])) +
+                   " has feature dim " + std::to_string(cl[i]) + ", model expects " + std::to_string(o.feat_dim);
+        return;
+      }
+      Entry e{};
+      e.key_off = pos + ko[i]; e.key_len = kl[i]; e.rows = rw[i]; e.elem = eb[i]; e.payload_off = pos + po[i];
+      out->entries.push_back(e);
+    }
+    if (n < CHUNK) {
+      if (pos + consumed < r->file_size) {
+        // trailing white space is tolerated (a text-mode tail); anything else is an entry this scanner does not know
+        int64_t q = pos + consumed;
+        while (q < r->file_size && ark_space(r->map[q])) ++q;
+        if (q < r->file_size) out->stopped_at = pos + consumed;
+      }
+      return;
+    }
+    pos += consumed;
+  }
+}
+
+// Provisional start of the key in front of the marker at h: the longest run of key characters before the separating space
+// (the previous payload's last bytes may look like key characters too; the chain of the range in front knows the truth).
+int64_t provisional_key(const xv_ark_reader* r, int64_t h) {
+  int64_t k = h - 1;
+  while (k > 0 && key_char(r->map[k - 1]) && h - k < 4096) --k;
+  return k;
+}
+
+// Index of the stripe [from, end_limit).  The chain is sequential by nature (a header tells where the next one is) and
+// every header costs a page fault of the mapping (~1 us: 10 ms per 10 000 utterances), so the stripe is cut into
+// sub-ranges that are scanned in parallel from resynchronised candidates and then stitched: a sub-range whose first
+// marker is not the one its predecessor's chain arrives at is scanned again from the true boundary.
 int scan_stripe(xv_ark_reader* r, int64_t from, bool first_is_candidate) {
   const xv_ark_reader_opts& o = r->o;
   const int64_t end_limit = o.byte_end < 0 ? r->file_size : std::min<int64_t>(o.byte_end, r->file_size);
@@ -230,44 +296,49 @@ int scan_stripe(xv_ark_reader* r, int64_t from, bool first_is_candidate) {
   xv_ark_index_info& inf = r->info;
   inf = xv_ark_index_info{};
   inf.stopped_at = -1;
-  inf.next_marker_off = inf.next_key_off = r->file_size;
-  constexpr int64_t CHUNK = 8192;
-  std::vector<int64_t> ko(CHUNK), po(CHUNK);
-  std::vector<int32_t> kl(CHUNK), rw(CHUNK), cl(CHUNK), eb(CHUNK);
-  int64_t pos = from;
-  bool done = false;
-  while (!done && pos < r->file_size) {
-    int64_t consumed = 0;
-    const int64_t n = xv_ark_scan(r->map + pos, r->file_size - pos, CHUNK, ko.data(), kl.data(), rw.data(), cl.data(), eb.data(),
-                                  po.data(), &consumed);
-    if (n < 0) return fail(XV_EINVAL, "xv_ark_scan failed");
-    for (int64_t i = 0; i < n; ++i) {
-      const int64_t marker = pos + po[i] - 15;
-      if (marker >= end_limit) {
-        inf.next_marker_off = marker;
-        inf.next_key_off = pos + ko[i];
-        done = true;
-        break;
-      }
-      if (cl[i] != o.feat_dim && rw[i] > 0)
-        return fail(XV_EINVAL, "utterance " + std::string(reinterpret_cast<const char*>(r->map + pos + ko[i]), size_t(kl[i])) +
-                                   " has feature dim " + std::to_string(cl[i]) + ", model expects " + std::to_string(o.feat_dim));
-      Entry e{};
-      e.key_off = pos + ko[i]; e.key_len = kl[i]; e.rows = rw[i]; e.elem = eb[i]; e.payload_off = pos + po[i];
-      r->entries.push_back(e);
+  constexpr int64_t MIN_PART = int64_t(4) << 20;
+  const int parts = int(std::max<int64_t>(1, std::min<int64_t>(std::min(o.n_threads, 16), (end_limit - from) / MIN_PART)));
+  std::vector<RangeScan> scans(size_t(parts), RangeScan{});
+  std::vector<int64_t> part_end(size_t(parts), end_limit), first_marker(size_t(parts), -1);
+  for (int i = 0; i + 1 < parts; ++i) part_end[i] = from + (end_limit - from) * (i + 1) / parts;
+  auto run_part = [&](int i) {
+    int64_t start = from;
+    if (i > 0) {
+      const int64_t h = resync(r, part_end[i - 1]);
+      if (h < 0 || h >= part_end[i]) { scans[i].next_marker = scans[i].next_key = -1; return; }   // nothing found in the sub-range
+      first_marker[i] = h;
+      start = provisional_key(r, h);
     }
-    if (done) break;
-    if (n < CHUNK) {
-      if (pos + consumed < r->file_size) {
-        // trailing white space is tolerated (a text-mode tail); anything else is an entry this scanner does not know
-        int64_t q = pos + consumed;
-        while (q < r->file_size && ark_space(r->map[q])) ++q;
-        if (q < r->file_size) inf.stopped_at = pos + consumed;
-      }
-      break;
-    }
-    pos += consumed;
+    scan_range(r, start, part_end[i], &scans[i]);
+  };
+  if (parts == 1) run_part(0);
+  else {
+    std::vector<std::thread> th;
+    for (int i = 1; i < parts; ++i) th.emplace_back(run_part, i);
+    run_part(0);
+    for (auto& t : th) t.join();
   }
+  // stitch
+  RangeScan& head = scans[0];
+  if (!head.err.empty()) return fail(XV_EINVAL, head.err);
+  r->entries.swap(head.entries);
+  int64_t next_marker = head.next_marker, next_key = head.next_key, stopped = head.stopped_at;
+  for (int i = 1; i < parts && stopped < 0; ++i) {
+    if (next_marker >= part_end[i]) continue;                  // the chain in front runs past this whole sub-range
+    RangeScan& s = scans[i];
+    if (first_marker[i] != next_marker || s.entries.empty()) {
+      scan_range(r, next_key, part_end[i], &s);                // the candidate was wrong (or missing): true boundary
+    } else {
+      s.entries[0].key_len = int32_t(next_marker - 1 - next_key);
+      s.entries[0].key_off = next_key;
+    }
+    if (!s.err.empty()) return fail(XV_EINVAL, s.err);
+    r->entries.insert(r->entries.end(), s.entries.begin(), s.entries.end());
+    next_marker = s.next_marker; next_key = s.next_key; stopped = s.stopped_at;
+  }
+  inf.next_marker_off = next_marker;
+  inf.next_key_off = next_key;
+  inf.stopped_at = stopped;
   return build_plan(r);
 }
 
@@ -373,9 +444,7 @@ int xv_ark_reader_index(xv_ark_reader* r, xv_ark_index_info* info) {
     else {
       // provisional key start: the longest run of key characters in front of the separating space (the previous payload's
       // last bytes may look like key characters too; xv_ark_reader_set_first fixes it)
-      int64_t k = h - 1;
-      while (k > 0 && arkjob::key_char(r->map[k - 1]) && h - k < 4096) --k;
-      from = k;
+      from = arkjob::provisional_key(r, h);
       candidate = true;
     }
   }
@@ -522,8 +591,20 @@ void xv_ark_reader_close(xv_ark_reader* r) {
     if (!r->o.pinned) free(p);
     else if (!arkjob::pinned_pool().give(p, r->slot_bytes[s])) cudaFreeHost(p);
   }
-  if (r->map) munmap(const_cast<uint8_t*>(r->map), size_t(r->file_size));
-  if (r->fd >= 0) close(r->fd);
+  // tearing down the mapping of a large archive costs milliseconds (page tables, TLB shootdowns): not on the caller's clock
+  if (r->map) {
+    uint8_t* map = const_cast<uint8_t*>(r->map);
+    const size_t size = size_t(r->file_size);
+    const int fd = r->fd;
+    try {
+      std::thread([map, size, fd] { munmap(map, size); if (fd >= 0) close(fd); }).detach();
+    } catch (...) {
+      munmap(map, size);
+      if (fd >= 0) close(fd);
+    }
+  } else if (r->fd >= 0) {
+    close(r->fd);
+  }
   delete r;
 }
 

@@ -658,10 +658,15 @@ class Model(object):
         feat_dim, emb_dim = self.meta["input_feature_dim"], self.embedding_sizes[0]
         on_gpu = getattr(engine, "handle", None) is not None       # a device engine (stand-ins of the host-logic tests have none)
         dev_name = "cuda:%d" % device if on_gpu else "cpu"
+        stats = dict(pre_s=time.time() - start_time, index_s=0.0, reader_wait_s=0.0, submit_s=0.0, collect_s=0.0, write_s=0.0,
+                     tail_s=0.0, batches=0)
+        t_job = time.time()
         reader, counts = ark_job.open_striped_reader(path, start, feat_dim, min_chunk_size, chunk_size, batch_frames,
                                                      device=dev_name, pinned=on_gpu)
         if reader is None:
             return False
+        stats["index_s"] = time.time() - t_job
+        self.last_job_stats = stats                  # where the wall time of the last native job went (bench / diagnostics)
         peer = None
         try:
             info = reader.info
@@ -694,9 +699,12 @@ class Model(object):
             pending = None
             k = 0
             while True:
+                t0 = time.time()
                 b = reader.next()
+                stats["reader_wait_s"] += time.time() - t0
                 submitted = None
                 if b is not None:
+                    stats["batches"] += 1
                     out_host = None
                     if not use_peer:
                         if host_rows[k & 1] is None or host_rows[k & 1].shape[0] < b.n_utt:
@@ -707,6 +715,7 @@ class Model(object):
                                                      dst_rows=b.utt_dst_row if use_peer else None,
                                                      out_dev=peer if use_peer else None, out_host=out_host)
                     total_gpu_waiting += time.time() - t0
+                    stats["submit_s"] += time.time() - t0
                     submitted = (ticket, b, out_host)
                     k += 1
                 if pending is not None:
@@ -714,14 +723,18 @@ class Model(object):
                     t0 = time.time()
                     engine.collect(ticket)
                     total_gpu_waiting += time.time() - t0
+                    stats["collect_s"] += time.time() - t0
+                    t0 = time.time()
                     if world == 1:
                         sink.write(key_blob, key_off[done.first_ok_index:done.first_ok_index + done.n_utt + 1], rows)
                     elif not use_peer:
                         local.append(rows.copy())
                     reader.release(done.slot)
+                    stats["write_s"] += time.time() - t0
                 pending = submitted
                 if b is None:
                     break
+            t_tail = time.time()
             if world > 1:
                 import torch.distributed as dist
                 blobs = ark_job.gather_bytes_to_rank0(key_blob, dev_name)
@@ -746,6 +759,8 @@ class Model(object):
                         sink.write(all_blob, all_off[r0:r0 + n + 1], rows)
                 if use_peer:
                     dist.barrier()                       # rank 0 has read the table: the mappings may go
+            stats["tail_s"] = time.time() - t_tail
+            stats["total_s"] = time.time() - t_job
             if logger is not None:
                 n_entries, n_ok, n_fail, rows_used = (int(counts[:, i].sum()) for i in range(4))
                 logger.info("Processed %d features of average size %d frames. Done %d and failed %d" %
@@ -755,9 +770,11 @@ class Model(object):
                             ((time.time() - start_time) / 60.0))
             return True
         finally:
+            t0 = time.time()
             reader.close()
             if peer is not None:
                 peer.close()
+            stats["close_s"] = time.time() - t0
 
     def _read_batches(self, input_stream, staging, work, counters, min_chunk_size, chunk_size, batch_frames,
                       rank, world, logger, device_frontend=False, vad_table=None):
