@@ -640,6 +640,30 @@ def measure_product(args, dev, rank, world, params, topo):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 dt = float(t.item())
             runs.append(dt)
+        file_stats = dict(getattr(model, "last_job_stats", {}))
+        peer_variant = None
+        if world > 1:
+            # the same job with rank 0's output a STREAM (what a `| copy-vector ...` wspecifier is): rows go to rank 0's
+            # peer-memory table over NVLink and rank 0 writes them all
+            import io
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            buf = io.BytesIO() if rank == 0 else None
+            model.make_embedding(path, buf, os.path.join(tmp, "model"), 25, 10000, True, None)
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            dt = time.perf_counter() - t0
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            same = None
+            if rank == 0:
+                with open(os.path.join(tmp, "xvector.2.ark"), "rb") as f:
+                    same = f.read() == buf.getvalue()
+            peer_variant = dict(output="in-memory stream on rank 0 (peer-memory result table)", seconds=round(float(t.item()), 4),
+                                value=round(total_frames / float(t.item()), 1), bytes_identical_to_the_file_output=same,
+                                rank0_breakdown_s={k: (round(v, 4) if isinstance(v, float) else v)
+                                                   for k, v in getattr(model, "last_job_stats", {}).items()})
         check = None
         if rank == 0:
             # the job's output: every key once and in order, the scp points at the same vectors, sampled rows bit-identical
@@ -677,9 +701,11 @@ def measure_product(args, dev, rank, world, params, topo):
                                    note="includes Model.load_model, weight upload and the first allocation of page-locked "
                                         "batch buffers / device workspaces"),
                    all_runs_s=[round(r, 4) for r in runs],
-                   rank0_breakdown_s={k: (round(v, 4) if isinstance(v, float) else v) for k, v in getattr(model, "last_job_stats", {}).items()},
+                   rank0_breakdown_s={k: (round(v, 4) if isinstance(v, float) else v) for k, v in file_stats.items()},
                    batch_frames=int(os.environ.get("XVEC_BATCH_FRAMES", "0")) or "default", reader_threads=os.environ.get("XVEC_READER_THREADS", "default"),
                    check=check)
+        if peer_variant is not None:
+            out["stream_output_variant"] = peer_variant
     except Exception as err:                                     # noqa: BLE001  (a diagnostic block must not cost the bench line)
         import traceback
         out = dict(error="%s: %s" % (type(err).__name__, err), trace=traceback.format_exc()[-1500:])

@@ -359,3 +359,59 @@ def test_parallel_index_of_a_large_stripe_equals_the_sequential_chain(tmp_path, 
         assert sizes[0] <= 200000 // 8 + 900 and sizes[1] <= 200000 // 4 + 900       # ramp-up: 1/8, 1/4, 1/2, full
         rd.close()
     assert keys == [k for k, _, _ in ok]
+
+
+_WORKER_FILES = r"""
+import io, os, sys, logging
+import numpy as np
+sys.path.insert(0, %(root)r)
+sys.path.insert(0, os.path.join(%(root)r, "tests"))
+import torch.distributed as dist
+from xvector_b200 import models, kaldi_io
+import test_host_logic as T
+dist.init_process_group(backend="gloo")
+rank = dist.get_rank()
+models._create_engine = lambda meta, params, device: T.OracleEngine(meta, params)
+os.environ["XVEC_BATCH_FRAMES"] = "300"
+m = models.Model()
+if rank == 0:
+    with kaldi_io.open_vector_writer("ark,scp:%(ark)s,%(scp)s") as w:
+        w.write_vec_entries(["preamble"], [np.arange(512, dtype=np.float32)])      # the job starts behind earlier entries
+        m.make_embedding(%(feats)r, w, %(model)r, 25, 100, True, logging.getLogger("w"))
+        w.write_vec_entries(["postscript"], [np.ones(512, dtype=np.float32)])      # ... and the writer goes on behind it
+    with open(%(plain)r, "wb") as f:
+        m.make_embedding(%(feats)r, f, %(model)r, 25, 100, True, None)
+else:
+    m.make_embedding(%(feats)r, None, %(model)r, 25, 100, True, None)
+    m.make_embedding(%(feats)r, None, %(model)r, 25, 100, True, None)
+assert m.last_job_stats["output"] == "shared_file", m.last_job_stats
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def test_every_rank_writes_its_byte_range_of_the_one_output_file(T_model_dir, tmp_path, monkeypatch):
+    d, _ = T_model_dir
+    monkeypatch.setenv("XVEC_BATCH_FRAMES", "300")
+    feats = str(tmp_path / "feats.ark")
+    _random_ark(feats, 10, 50, lo=20, hi=260)
+    names = dict(ark=str(tmp_path / "x.ark"), scp=str(tmp_path / "x.scp"), plain=str(tmp_path / "plain.ark"))
+    ref_ark, ref_scp = str(tmp_path / "ref.ark"), str(tmp_path / "ref.scp")
+    with kaldi_io.ArkScpWriter(ref_ark, ref_scp, scp_ark_name=names["ark"]) as w:
+        w.write_vec_entries(["preamble"], [np.arange(512, dtype=np.float32)])
+        models.Model().make_embedding(io.BytesIO(open(feats, "rb").read()), w, d, 25, 100, True, None)   # one process, general path
+        w.write_vec_entries(["postscript"], [np.ones(512, dtype=np.float32)])
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER_FILES % dict(root=ROOT, model=d, feats=feats, **names))
+    env = dict(os.environ, XVEC_SEED="11")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=3",
+                        "--master-addr", "127.0.0.1", "--master-port", "29743", str(script)],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert open(names["ark"], "rb").read() == open(ref_ark, "rb").read()
+    assert open(names["scp"], "rb").read() == open(ref_scp, "rb").read()
+    body = open(ref_ark, "rb").read()
+    pre = len("preamble") + 11 + 2048
+    assert open(names["plain"], "rb").read() == body[pre:len(body) - (len("postscript") + 11 + 2048)]
+    got = dict(kaldi_io.read_vec_flt_scp(names["scp"]))
+    assert len(got) > 10 and np.array_equal(got["postscript"], np.ones(512, np.float32))

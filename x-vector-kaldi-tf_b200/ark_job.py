@@ -43,8 +43,8 @@ def stripe_bounds(start, size, rank, world):
 def open_striped_reader(path, start, feat_dim, min_chunk_size, chunk_size, batch_frames, device="cpu", pinned=True,
                         n_threads=None, n_slots=3, rank=None, world=None):
     """Index this rank's stripe of ``path`` (entries from byte ``start`` on) and agree the stripe boundaries with the
-    other ranks.  Returns ``(reader, counts)`` with ``counts`` = [world, 5] int64 rows
-    (n_entries, n_ok, n_fail, rows_used, stopped_at) of every rank -- or ``(None, counts)`` when some stripe holds an entry
+    other ranks.  Returns ``(reader, counts)`` with ``counts`` = [world, 6] int64 rows
+    (n_entries, n_ok, n_fail, rows_used, stopped_at, key_bytes) of every rank -- or ``(None, counts)`` when some stripe holds an entry
     the native scanner cannot parse (text / compressed matrices): the caller then takes its general path."""
     from ._native import ArkReader
     if rank is None:
@@ -77,7 +77,8 @@ def open_striped_reader(path, start, feat_dim, min_chunk_size, chunk_size, batch
                     break
             else:
                 raise RuntimeError("the stripes of %s did not settle on common boundaries" % path)
-        counts = _all_gather_i64([info["n_entries"], info["n_ok"], info["n_fail"], info["rows_used"], info["stopped_at"]], device)
+        counts = _all_gather_i64([info["n_entries"], info["n_ok"], info["n_fail"], info["rows_used"], info["stopped_at"],
+                                  info["key_bytes"]], device)
         if (counts[:, 4] >= 0).any():
             reader.close()
             return None, counts
@@ -125,3 +126,38 @@ def gather_bytes_to_rank0(data, device):
     if rank != 0:
         return None
     return [bufs[r][:int(sizes[r])].cpu().numpy() for r in range(world)]
+
+
+def shared_output_spec(output_stream):
+    """Rank 0: if the job's output lies in regular files that every rank of the node can open -- a
+    ``kaldi_io.ArkScpWriter`` or a buffered writer over a named regular file -- the description the other ranks need to
+    write their byte ranges themselves: ``dict(ark=path, base=offset where this job's first entry goes, scp_name=name the
+    scp lines use for the ark or None)``.  None for pipes, in-memory streams, gzip, anything else."""
+    import io
+    import stat
+    try:
+        if hasattr(output_stream, "write_vec_block") and hasattr(output_stream, "ark"):        # ArkScpWriter
+            output_stream.ark.flush()
+            output_stream.scp.flush()
+            return dict(ark=os.path.abspath(output_stream.ark.name), base=int(output_stream.pos), scp_name=output_stream.name)
+        if isinstance(output_stream, io.BufferedWriter) and isinstance(output_stream.name, str) and \
+                stat.S_ISREG(os.fstat(output_stream.fileno()).st_mode):
+            output_stream.flush()
+            return dict(ark=os.path.abspath(output_stream.name), base=int(output_stream.tell()), scp_name=None)
+    except (OSError, ValueError, AttributeError):
+        return None
+    return None
+
+
+def finish_shared_output(output_stream, spec, total_bytes, scp_parts):
+    """Rank 0, after every rank has written its byte range: move the writer behind the job's entries and append the scp
+    lines the ranks produced (in rank order)."""
+    end = spec["base"] + total_bytes
+    if spec["scp_name"] is not None:
+        output_stream.ark.seek(end)
+        output_stream.pos = end
+        for part in scp_parts:
+            if len(part):
+                output_stream.scp.write(part.tobytes().decode())
+    else:
+        output_stream.seek(end)

@@ -204,6 +204,7 @@ int xv_submit_host_raw(xv_model* m, const float* feats_host, const float* vad_ho
   m->last_launches += fe_launches;
   XV_CUDA(cudaMemcpyAsync(emb_host, sl.emb_dev, emb_bytes, cudaMemcpyDeviceToHost, sl.stream));
   XV_CUDA(cudaMemcpyAsync(sl.overflow_host, m->overflow_dev, 4, cudaMemcpyDeviceToHost, sl.stream));
+  XV_CUDA(cudaEventRecord(sl.done, sl.stream));
   sl.busy = true;
   m->slot_next = (si + 1) % XV_HOST_SLOTS;
   *ticket = si;

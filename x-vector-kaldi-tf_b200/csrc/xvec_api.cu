@@ -123,6 +123,8 @@ struct xv_model {
     float* vad_dev = nullptr; size_t vad_cap = 0;
     void* fe_ws_dev = nullptr; size_t fe_ws_cap = 0;
     uint32_t* overflow_host = nullptr;   // pinned
+    cudaEvent_t done = nullptr;          // recorded behind the submission's last copy; created with cudaEventBlockingSync so that
+                                         // xv_collect SLEEPS instead of spinning (a multi-GPU job runs reader threads on those cores)
     bool busy = false;
   } slots[XV_HOST_SLOTS];
   int slot_next = 0;
@@ -985,6 +987,7 @@ int xv_create(xv_model** out, int device, const xv_topology* topo) {
   for (int i = 0; i < XV_HOST_SLOTS && e == cudaSuccess; ++i) {
     e = cudaStreamCreateWithFlags(&m->slots[i].stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&m->slots[i].overflow_host), 4, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->slots[i].done, cudaEventBlockingSync | cudaEventDisableTiming);
   }
   if (e != cudaSuccess) {
     std::string msg = std::string("xv_create: ") + cudaGetErrorName(e) + ": " + cudaGetErrorString(e);
@@ -1014,6 +1017,7 @@ void xv_destroy(xv_model* m) {
     cudaFree(sl.feats_dev); cudaFree(sl.emb_dev); cudaFree(sl.ws_dev);
     cudaFree(sl.raw_dev); cudaFree(sl.vad_dev); cudaFree(sl.fe_ws_dev);
     if (sl.overflow_host) cudaFreeHost(sl.overflow_host);
+    if (sl.done) cudaEventDestroy(sl.done);
     if (sl.stream) cudaStreamDestroy(sl.stream);
   }
   delete m;
@@ -1138,6 +1142,7 @@ int submit_impl(xv_model* m, const float* feats_host, const int32_t* seg_len_hos
     XV_CUDA(cudaMemcpyAsync(emb_host, sl.emb_dev, emb_bytes, cudaMemcpyDeviceToHost, sl.stream));
   }
   XV_CUDA(cudaMemcpyAsync(sl.overflow_host, m->overflow_dev, 4, cudaMemcpyDeviceToHost, sl.stream));
+  XV_CUDA(cudaEventRecord(sl.done, sl.stream));
   sl.busy = true;
   m->slot_next = (si + 1) % XV_HOST_SLOTS;
   *ticket = si;
@@ -1232,7 +1237,7 @@ int xv_collect(xv_model* m, int32_t ticket) {
   if (!sl.busy) return fail(XV_ESTATE, "ticket is not in flight");
   XV_CUDA(cudaSetDevice(m->device));
   sl.busy = false;
-  XV_CUDA(cudaStreamSynchronize(sl.stream));
+  XV_CUDA(cudaEventSynchronize(sl.done));
   if (*sl.overflow_host != 0) {
     XV_CUDA(cudaMemsetAsync(m->overflow_dev, 0, 4, sl.stream));
     return sticky_flag_error(*sl.overflow_host);

@@ -651,7 +651,16 @@ class Model(object):
                                       logger, start_time):
         """make_embedding over an ark in a regular file (reference models.py:373-432, same skip rules, chunk plan, average,
         output bytes and log lines).  Returns False -- having touched nothing -- when the archive holds entries the native
-        scanner does not parse, so that the caller can take the general path."""
+        scanner does not parse, so that the caller can take the general path.
+
+        How the x-vectors of a multi-GPU job reach the ONE output (the reference has ``nj`` jobs write ``nj`` arks and
+        concatenates their scp files, extract_xvectors.sh:83-95):
+          * output in regular files (``ark:file``, ``ark,scp:A,S``): entry sizes are known once the keys are, so every rank
+            formats its own rows and ``pwrite``s them into ITS byte range of the one ark while it computes; rank 0 only
+            appends the scp lines the ranks hand it.  No x-vector crosses to rank 0 at all.
+          * output is a stream on rank 0 (pipe, in-memory): every rank's utt_average_kernel stores its rows into rank 0's
+            result table over NVLink peer memory, rank 0 reads the table after one barrier and writes the stream.
+          * no peer memory (CPU process groups of the host-logic tests): one gather of the host rows."""
         from . import ark_job
         path, start = source
         rank, world = sharding.dist_info()
@@ -667,9 +676,8 @@ class Model(object):
             return False
         stats["index_s"] = time.time() - t_job
         self.last_job_stats = stats                  # where the wall time of the last native job went (bench / diagnostics)
-        peer = None
+        peer, shared_fd = None, None
         try:
-            info = reader.info
             if logger is not None:
                 for key, reason, rows in reader.failures():
                     if reason == 1:
@@ -680,11 +688,18 @@ class Model(object):
             n_ok_total = int(counts[:, 1].sum())
             base = int(counts[:rank, 1].sum())
             key_blob, key_off = reader.keys()
-            sink = ark_job.VectorSink(output_stream) if rank == 0 else None
-            use_peer = world > 1 and on_gpu
-            if use_peer:
-                # rank 0 owns the job's result table; every rank's utt_average_kernel stores its rows there over NVLink
+            entry_bytes = 11 + 4 * emb_dim               # an entry is its key + this (kaldi_io.write_vec_flt)
+            mode = "local"
+            shared = None
+            if world > 1:
                 import torch.distributed as dist
+                box = [ark_job.shared_output_spec(output_stream) if rank == 0 else None]
+                dist.broadcast_object_list(box, src=0)
+                shared = box[0]
+                mode = "shared_file" if shared is not None else ("peer" if on_gpu else "host_gather")
+            stats["output"] = mode
+            sink = ark_job.VectorSink(output_stream) if rank == 0 else None
+            if mode == "peer":
                 from ._native import PeerTable
                 if rank == 0:
                     peer = PeerTable.create(device, max(n_ok_total, 1), emb_dim)
@@ -692,9 +707,14 @@ class Model(object):
                 dist.broadcast_object_list(box, src=0)
                 if rank != 0:
                     peer = PeerTable.open(device, max(n_ok_total, 1), emb_dim, box[0])
-            reader.start(base if use_peer else 0)
-            host_rows = [None, None]                     # page-locked [n_utt, emb_dim] per submission slot (not needed with a peer table)
-            local = [] if (world > 1 and not use_peer) else None
+            ark_base = 0
+            scp_parts = []
+            if mode == "shared_file":
+                ark_base = shared["base"] + int((counts[:rank, 5] + counts[:rank, 1] * entry_bytes).sum())
+                shared_fd = os.open(shared["ark"], os.O_WRONLY)
+            reader.start(base if mode == "peer" else 0)
+            host_rows = [None, None]                     # page-locked [n_utt, emb_dim] per submission slot
+            local = [] if mode == "host_gather" else None
             total_gpu_waiting = 0.0
             pending = None
             k = 0
@@ -706,14 +726,14 @@ class Model(object):
                 if b is not None:
                     stats["batches"] += 1
                     out_host = None
-                    if not use_peer:
+                    if mode != "peer":
                         if host_rows[k & 1] is None or host_rows[k & 1].shape[0] < b.n_utt:
                             host_rows[k & 1] = _pinned_rows(max(2 * b.n_utt, 1024), emb_dim, on_gpu)
                         out_host = host_rows[k & 1][:b.n_utt]
                     t0 = time.time()
                     ticket = engine.submit_host_utts(b.feats, b.seg_len, utt_first_seg=b.utt_first_seg,
-                                                     dst_rows=b.utt_dst_row if use_peer else None,
-                                                     out_dev=peer if use_peer else None, out_host=out_host)
+                                                     dst_rows=b.utt_dst_row if mode == "peer" else None,
+                                                     out_dev=peer if mode == "peer" else None, out_host=out_host)
                     total_gpu_waiting += time.time() - t0
                     stats["submit_s"] += time.time() - t0
                     submitted = (ticket, b, out_host)
@@ -725,9 +745,17 @@ class Model(object):
                     total_gpu_waiting += time.time() - t0
                     stats["collect_s"] += time.time() - t0
                     t0 = time.time()
-                    if world == 1:
-                        sink.write(key_blob, key_off[done.first_ok_index:done.first_ok_index + done.n_utt + 1], rows)
-                    elif not use_peer:
+                    window = key_off[done.first_ok_index:done.first_ok_index + done.n_utt + 1]
+                    if mode == "local":
+                        sink.write(key_blob, window, rows)
+                    elif mode == "shared_file":
+                        from ._native import scp_format, vec_ark_format
+                        blob, markers = vec_ark_format(key_blob, window, rows, with_markers=True)
+                        at = ark_base + int(window[0]) + done.first_ok_index * entry_bytes
+                        _pwrite_all(shared_fd, blob, at)
+                        if shared["scp_name"] is not None:
+                            scp_parts.append(scp_format(key_blob, window, shared["scp_name"], at, markers))
+                    elif mode == "host_gather":
                         local.append(rows.copy())
                     reader.release(done.slot)
                     stats["write_s"] += time.time() - t0
@@ -735,16 +763,21 @@ class Model(object):
                 if b is None:
                     break
             t_tail = time.time()
-            if world > 1:
-                import torch.distributed as dist
+            if mode == "shared_file":
+                lines = ark_job.gather_bytes_to_rank0(np.concatenate(scp_parts) if scp_parts else np.zeros(0, np.uint8), dev_name)
+                dist.barrier()                           # every rank's byte range of the ark is written
+                if rank == 0:
+                    total = int((counts[:, 5] + counts[:, 1] * entry_bytes).sum())
+                    ark_job.finish_shared_output(output_stream, shared, total, lines)
+            elif world > 1:
                 blobs = ark_job.gather_bytes_to_rank0(key_blob, dev_name)
                 lens = ark_job.gather_bytes_to_rank0(np.diff(key_off).astype(np.int32).view(np.uint8), dev_name)
                 full = None
-                if use_peer:
+                if mode == "peer":
                     import torch
                     torch.cuda.synchronize(device)
                     dist.barrier()                       # every rank's rows are in rank 0's table
-                else:                                    # no peer memory (gloo): one gather of the host rows
+                else:
                     emb = np.concatenate(local, axis=0) if local else np.zeros((0, emb_dim), np.float32)
                     full = sharding.gather_to_rank0(np.arange(base, base + emb.shape[0], dtype=np.int64), emb, n_ok_total,
                                                     emb_dim, device=dev_name)
@@ -755,9 +788,9 @@ class Model(object):
                     block = 1 << 16
                     for r0 in range(0, n_ok_total, block):
                         n = min(block, n_ok_total - r0)
-                        rows = peer.read(r0, n) if use_peer else full[r0:r0 + n]
+                        rows = peer.read(r0, n) if mode == "peer" else full[r0:r0 + n]
                         sink.write(all_blob, all_off[r0:r0 + n + 1], rows)
-                if use_peer:
+                if mode == "peer":
                     dist.barrier()                       # rank 0 has read the table: the mappings may go
             stats["tail_s"] = time.time() - t_tail
             stats["total_s"] = time.time() - t_job
@@ -774,6 +807,8 @@ class Model(object):
             reader.close()
             if peer is not None:
                 peer.close()
+            if shared_fd is not None:
+                os.close(shared_fd)
             stats["close_s"] = time.time() - t0
 
     def _read_batches(self, input_stream, staging, work, counters, min_chunk_size, chunk_size, batch_frames,
@@ -925,6 +960,13 @@ def _regular_ark_file(input_stream):
             return None
         return name, 0
     return None
+
+
+def _pwrite_all(fd, data, offset):
+    view = memoryview(data).cast("B")
+    done = 0
+    while done < len(view):
+        done += os.pwrite(fd, view[done:], offset + done)
 
 
 def _pinned_rows(rows, cols, pinned):
