@@ -370,9 +370,10 @@ class ArkReader(object):
             pass
 
 
-def vec_ark_format(key_blob, key_off, vecs, with_markers=False, n_threads=4):
+def vec_ark_format(key_blob, key_off, vecs, with_markers=False, n_threads=4, out=None):
     """The bytes write_vec_flt (reference kaldi_io.py:309-343) emits for the float32 rows of ``vecs``, keyed by
-    ``key_blob[key_off[i]:key_off[i+1]]`` -- one uint8 array -- and, with ``with_markers``, each entry's marker offset."""
+    ``key_blob[key_off[i]:key_off[i+1]]`` -- one uint8 array -- and, with ``with_markers``, each entry's marker offset.
+    ``out``: a writable uint8 array to format into (e.g. a window of the mmap'ed output file) instead of a fresh one."""
     lib = load_library()
     vecs = np.ascontiguousarray(vecs, dtype=np.float32)
     key_off = np.ascontiguousarray(key_off, dtype=np.int64)
@@ -380,7 +381,9 @@ def vec_ark_format(key_blob, key_off, vecs, with_markers=False, n_threads=4):
     n, dim = int(vecs.shape[0]), int(vecs.shape[1])
     assert key_off.shape[0] == n + 1
     total = int(lib.xv_vec_ark_bytes(key_off.ctypes.data, n, dim))
-    out = np.empty(max(total, 1), np.uint8)
+    if out is None:
+        out = np.empty(max(total, 1), np.uint8)
+    assert out.dtype == np.uint8 and out.flags.c_contiguous and out.shape[0] >= total
     markers = np.empty(max(n, 1), np.int64) if with_markers else None
     # key_off may be a window of a larger table: the formatter indexes the blob with the absolute offsets
     got = int(lib.xv_vec_ark_format(key_blob.ctypes.data, key_off.ctypes.data, n, vecs.ctypes.data, dim, out.ctypes.data, total,

@@ -128,21 +128,24 @@ def gather_bytes_to_rank0(data, device):
     return [bufs[r][:int(sizes[r])].cpu().numpy() for r in range(world)]
 
 
-def shared_output_spec(output_stream):
+def shared_output_spec(output_stream, total_bytes):
     """Rank 0: if the job's output lies in regular files that every rank of the node can open -- a
     ``kaldi_io.ArkScpWriter`` or a buffered writer over a named regular file -- the description the other ranks need to
     write their byte ranges themselves: ``dict(ark=path, base=offset where this job's first entry goes, scp_name=name the
-    scp lines use for the ark or None)``.  None for pipes, in-memory streams, gzip, anything else."""
+    scp lines use for the ark or None)``.  The file is extended by ``total_bytes`` (the size of the job's entries) so that the
+    ranks can map their ranges.  None for pipes, in-memory streams, gzip, anything else."""
     import io
     import stat
     try:
         if hasattr(output_stream, "write_vec_block") and hasattr(output_stream, "ark"):        # ArkScpWriter
             output_stream.ark.flush()
             output_stream.scp.flush()
+            os.ftruncate(output_stream.ark.fileno(), int(output_stream.pos) + int(total_bytes))
             return dict(ark=os.path.abspath(output_stream.ark.name), base=int(output_stream.pos), scp_name=output_stream.name)
         if isinstance(output_stream, io.BufferedWriter) and isinstance(output_stream.name, str) and \
                 stat.S_ISREG(os.fstat(output_stream.fileno()).st_mode):
             output_stream.flush()
+            os.ftruncate(output_stream.fileno(), int(output_stream.tell()) + int(total_bytes))
             return dict(ark=os.path.abspath(output_stream.name), base=int(output_stream.tell()), scp_name=None)
     except (OSError, ValueError, AttributeError):
         return None

@@ -91,6 +91,7 @@ struct xv_model {
                                      // counters cost ~40 us; kept as an option and as a cross-check
   int opt_pdl = 1;                   // programmatic dependent launch between the kernels of a forward
   int opt_fc = 1;                    // 1: embed_layer-0 on tensor cores (split fp16), 0: fp32 SIMT GEMM
+  int opt_blocking_collect = 0;      // 1: xv_collect sleeps on a blocking-sync event instead of spinning
   int c_pool = 0;                    // channels that are pooled: width of the last frame layer (attention pooling: half of it)
   __half* att_w_dev = nullptr;       // attention pooling: [C, C] fp16 K-major (out channel major) copy of "attention/w:0"
   float* att_b_dev = nullptr;        // [C]
@@ -1237,7 +1238,10 @@ int xv_collect(xv_model* m, int32_t ticket) {
   if (!sl.busy) return fail(XV_ESTATE, "ticket is not in flight");
   XV_CUDA(cudaSetDevice(m->device));
   sl.busy = false;
-  XV_CUDA(cudaEventSynchronize(sl.done));
+  // option "blocking_collect": sleep on the slot's blocking-sync event instead of spinning in the driver (frees a core per
+  // process at the price of a wake-up latency per collect; measured slower for 0.5 ms steps, so off by default)
+  if (m->opt_blocking_collect) XV_CUDA(cudaEventSynchronize(sl.done));
+  else XV_CUDA(cudaStreamSynchronize(sl.stream));
   if (*sl.overflow_host != 0) {
     XV_CUDA(cudaMemsetAsync(m->overflow_dev, 0, 4, sl.stream));
     return sticky_flag_error(*sl.overflow_host);
@@ -1286,6 +1290,7 @@ int xv_set_option(xv_model* m, const char* name, int64_t value) {
   else if (n == "prefetch") m->opt_prefetch = value != 0;
   else if (n == "fc") m->opt_fc = int(value);
   else if (n == "pdl") m->opt_pdl = value != 0;
+  else if (n == "blocking_collect") m->opt_blocking_collect = value != 0;
   else if (n == "stack") m->opt_stack = value != 0;
   else if (n == "stack_debug") m->opt_stack_debug = int(value);
   else if (n == "fc_max_splits") m->opt_fc_max_splits = std::max(1, int(value));
