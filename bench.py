@@ -82,17 +82,22 @@ def load_peaks():
     return dict(hbm_gbs=6650.0, tflops=1590.0, tflops_sustained=1400.0, source="fallback")
 
 
-def ncu_traffic_bytes():
-    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the fused TDNN layer kernel, averaged
-    over its captured launches, from the committed `ncu --set full` summary under profiles/ (None if absent)."""
-    import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_summary.json")))
-    if not files:
+NCU_TRAFFIC_FILE = "r02_ncu_full_summary.json"      # ncu --set full of the SHIPPED extraction kernels at configs[1], both topologies
+
+
+def ncu_traffic_bytes(topology):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the fused TDNN layer kernel, averaged over the
+    frame-layer launches of ONE captured extraction step of `topology` at configs[1], from the committed summary
+    profiles/r02_ncu_full_summary.json (written by tools/ncu_summary.py from the capture of tools/profile_step.py).
+    (None, None) if that file or that topology's capture is absent -- never another workload's numbers."""
+    path = os.path.join(ROOT, "profiles", NCU_TRAFFIC_FILE)
+    if not os.path.exists(path):
         return None, None
-    with open(files[-1]) as f:
-        rows = [r for r in json.load(f) if "tdnn_pair_kernel<0" in r.get("kernel", "") or "tdnn_pair_kernel<1" in r.get("kernel", "")]
+    with open(path) as f:
+        rows = [r for r in json.load(f) if topology in r.get("report", "") and
+                ("tdnn_pair_kernel<0" in r.get("kernel", "") or "tdnn_pair_kernel<1" in r.get("kernel", ""))]
     vals = [(r["dram_read_MB"] + r["dram_write_MB"]) * 1e6 for r in rows if r.get("dram_read_MB") is not None]
-    return (round(sum(vals) / len(vals)) if vals else None), os.path.basename(files[-1])
+    return (round(sum(vals) / len(vals)) if vals else None), NCU_TRAFFIC_FILE
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -429,12 +434,12 @@ def run_b200(args):
         launches.append(d)
     tdnn_ms = float(kms[1:1 + len(fl)].sum())
     tdnn_tf = frames * sum(fl) / (tdnn_ms * 1e-3) / 1e12
-    traffic, traffic_src = ncu_traffic_bytes()
+    traffic, traffic_src = ncu_traffic_bytes(args.topology)
     roofline = dict(kernel="tdnn_pair_kernel (%d launches/step, figures are per-step sums / averages)" % len(fl),
                     bound="tensor", achieved=round(tdnn_tf, 1), peak=peaks["tflops"], unit="TFLOP/s",
                     frac=round(tdnn_tf / peaks["tflops"], 4), traffic=traffic,
-                    traffic_source="profiles/%s: mean DRAM bytes per launch over the captured frame-layer launches (tdnn splice, config 2)"
-                                   % traffic_src if traffic_src else None,
+                    traffic_source=("profiles/%s: mean DRAM bytes per launch over the %d frame-layer launches of one captured step of %s "
+                                    "at configs[1]" % (traffic_src, len(fl), args.topology)) if traffic is not None else None,
                     flop_per_launch_avg=round(frames * sum(fl) / len(fl)),
                     peak_source="%s bf16/fp16 burst (MEASURED_PEAKS.json)" % peaks["source"],
                     share_of_step=round(tdnn_ms / float(kms.sum()), 4),
@@ -442,6 +447,66 @@ def run_b200(args):
                     step_frac_of_sustained_peak=round(value / world * sum(fl) / 1e12 / peaks["tflops_sustained"], 4),
                     peak_sustained=peaks["tflops_sustained"],
                     launches=launches)
+
+    # ---- sustained regime: >= 2 s of back-to-back steps (what a 1 M-utterance job lives in: the power cap settles) --------
+    def timed_run(engine, seconds):
+        engine.forward_utts(feats_dev, lens, emb_dev, stream=stream)
+        torch.cuda.synchronize(dev)
+        n = max(200, int(seconds / (ms_per_step * 1e-3)))
+        sampler = ClockSampler(local_rank, period=0.02)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.start()
+        e0.record(stream)
+        for _ in range(n):
+            engine.forward_utts(feats_dev, lens, emb_dev, stream=stream)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n, n, sampler.finish()
+
+    sus_ms, sus_n, sus_clocks = timed_run(eng, 2.0)
+    sustained = dict(note="back-to-back steps, no L2 flush between them (the layer activations, 100+ MB each, exceed L2 anyway)",
+                     steps=sus_n, seconds=round(sus_ms * sus_n * 1e-3, 3), ms_per_step=round(sus_ms, 5),
+                     value_per_gpu=round(frames / (sus_ms * 1e-3), 1), unit=UNIT,
+                     frac_of_sustained_tensor_peak=round(frames * sum(fl) / (sus_ms * 1e-3) / 1e12 / peaks["tflops_sustained"], 4),
+                     frac_of_burst_tensor_peak=round(frames * sum(fl) / (sus_ms * 1e-3) / 1e12 / peaks["tflops"], 4),
+                     peak_sustained=peaks["tflops_sustained"], clocks=sus_clocks)
+
+    # ---- the recipe's default topology (run_xvector.sh:90 ModelWithoutDropout: dense kernels 5,5,7,1,1) -----------------
+    dense = None
+    if args.topology != "ModelWithoutDropout":
+        dtopo = TOPOLOGIES["ModelWithoutDropout"]
+        deng = _native.XvecEngine(dtopo["kernel_sizes"], dtopo["dilations"], dtopo["layer_sizes"], EMB_DIM, FEAT_DIM, device=local_rank)
+        deng.set_params(synthetic.make_params(dtopo["kernel_sizes"], dtopo["layer_sizes"], dtopo["embedding_sizes"],
+                                              weight_set=args.weight_set))
+        for _ in range(3):
+            deng.forward_utts(feats_dev, lens, emb_dev, stream=stream)
+        devs = []
+        for _ in range(min(args.steps, 50)):
+            flush.zero_()
+            s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_.record(stream); deng.forward_utts(feats_dev, lens, emb_dev, stream=stream); e_.record(stream)
+            devs.append((s_, e_))
+        torch.cuda.synchronize(dev)
+        d_ms = float(np.mean([s_.elapsed_time(e_) for s_, e_ in devs]))
+        dfl = flop_per_frame(dtopo)
+        deng.set_option("profile", 1)
+        dk = []
+        for _ in range(10):
+            flush.zero_()
+            deng.forward_utts(feats_dev, lens, emb_dev, stream=stream)
+            dk.append(deng.last_kernel_ms())
+        deng.set_option("profile", 0)
+        dk = np.asarray(dk, dtype=np.float64).mean(axis=0)
+        d_layers = float(dk[1:1 + len(dfl)].sum())
+        d_tf = frames * sum(dfl) / (d_layers * 1e-3) / 1e12
+        dense = dict(workload="configs[1] with ModelWithoutDropout (taps %s)" % dtopo["kernel_sizes"], ms_per_step=round(d_ms, 5),
+                     value_per_gpu=round(frames / (d_ms * 1e-3), 1), unit=UNIT,
+                     roofline=dict(bound="tensor", achieved=round(d_tf, 1), peak=peaks["tflops"], unit="TFLOP/s",
+                                   frac=round(d_tf / peaks["tflops"], 4), share_of_step=round(d_layers / float(dk.sum()), 4),
+                                   traffic=ncu_traffic_bytes("ModelWithoutDropout")[0],
+                                   layer_ms=[round(float(v), 5) for v in dk[1:1 + len(dfl)]]),
+                     step_frac_of_tensor_peak=round(frames * sum(dfl) / (d_ms * 1e-3) / 1e12 / peaks["tflops"], 4))
+        deng.close()
 
     frontend = measure_frontend(args, eng, dev, stream, flush, rank, peaks)
 
@@ -462,7 +527,7 @@ def run_b200(args):
                         api="xv_submit_host_utts / xv_collect, 2 in flight (pinned host buffers in and out"
                             + ("; rows also stored to rank 0's table, closing barrier + rank 0's read inside the window)" if world > 1 else ")")),
                gpu_launches=int(launches_per_step * args.steps),
-               clocks=clocks, roofline=roofline, ragged=ragged, frontend=frontend)
+               clocks=clocks, roofline=roofline, sustained=sustained, dense_topology=dense, ragged=ragged, frontend=frontend)
     if multi is not None:
         out["multi_gpu"] = multi
     if remeasured:

@@ -793,10 +793,11 @@ class Model(object):
                     all_blob = np.concatenate(blobs) if blobs else np.zeros(0, np.uint8)
                     all_len = np.concatenate([l.view(np.int32) for l in lens]) if lens else np.zeros(0, np.int32)
                     all_off = np.concatenate([[0], np.cumsum(all_len, dtype=np.int64)])
-                    block = 1 << 16
+                    block = 1 << 14
+                    stage = _pinned_rows(block, emb_dim, True) if mode == "peer" else None     # page-locked: D2H at full PCIe rate
                     for r0 in range(0, n_ok_total, block):
                         n = min(block, n_ok_total - r0)
-                        rows = peer.read(r0, n) if mode == "peer" else full[r0:r0 + n]
+                        rows = peer.read(r0, n, out=stage[:n]) if mode == "peer" else full[r0:r0 + n]
                         sink.write(all_blob, all_off[r0:r0 + n + 1], rows)
                 if mode == "peer":
                     dist.barrier()                       # rank 0 has read the table: the mappings may go
