@@ -39,7 +39,7 @@ enum {
   XV_ECUDA = -2,       /* CUDA runtime or driver error (message has the CUDA error string) */
   XV_ENOMEM = -3,      /* workspace too small / allocation failed                          */
   XV_ESTATE = -4,      /* parameters missing at forward time                               */
-  XV_EOVERFLOW = -5    /* an activation left the fp16 range (reported by xv_check_overflow)*/
+  XV_EOVERFLOW = -5    /* an activation left the fp16 range and was not rescued (see xv_check_overflow) */
 };
 
 /* Frame-layer nonlinearity (between bias_add and BatchNorm):
@@ -159,9 +159,20 @@ int xv_peer_close(int device, void* dev_ptr);
 int xv_peer_free(int device, void* dev_ptr);
 int xv_peer_read(int device, void* dst_host, const void* src_dev, size_t bytes);
 
-/* Returns XV_OK, or XV_EOVERFLOW if any activation exceeded the fp16 range since the last
- * call (synchronises `stream`; clears the flag). */
+/* fp16 range.  Activations travel between the frame layers as fp16 (|x| <= 65 504); the reference computes in fp32 and
+ * loads any trained model (models.py:476-480).  Every store tracks its largest magnitude, and a model whose activations
+ * pass the range is RESCUED rather than refused: layer i's rows are then stored divided by 2^e_i (folded into its
+ * BatchNorm scale / shift, undone by the consumer's fp32 accumulator -- exact operations), likewise the pooled
+ * statistics on their way into the embedding GEMM.
+ *   - xv_collect / xv_extract_host do this by themselves: exponents are raised for what overflowed and the submission is
+ *     run again from its device copy of the features; the exponents stay with the model (option "rescue" = 0 turns this
+ *     off: XV_EOVERFLOW is returned instead, as in ABI version 1).
+ *   - xv_forward / xv_forward_utts only enqueue, so their caller checks: xv_check_overflow returns XV_OK, or
+ *     XV_EOVERFLOW if any store overflowed since the last call (synchronises `stream`; clears the flag);
+ *     xv_rescue_overflow does the same check and, on overflow, raises the exponents and returns how many it raised
+ *     (> 0: enqueue the forward again; 0: nothing overflowed; < 0: XV_E*, e.g. beyond the largest rescue scale 2^96). */
 int xv_check_overflow(xv_model* m, void* stream);
+int xv_rescue_overflow(xv_model* m, void* stream);
 
 /* Number of kernels the last xv_forward / xv_extract_host / xv_submit_host launched (for bench.py's
  * "gpu_launches" claim). */
@@ -176,7 +187,7 @@ int32_t xv_last_kernel_ms(xv_model* m, float* ms_out, int32_t cap);
 
 /* Tuning knob for experiments: 0 = one TMA box per (tap, channel chunk); 1 = load each
  * activation slab once and address every tap inside it (default chosen by the library).
- * Options: "reuse_taps", "desc_base_offset", "profile". */
+ * Options: "profile", "pdl", "fc", "fc_max_splits", "resident", "prefetch", "rescue", "blocking_collect", "trace_*". */
 int xv_set_option(xv_model* m, const char* name, int64_t value);
 
 /* Host-only helper of the reader that feeds xv_submit_host: index of the binary float matrices of a Kaldi ark held in

@@ -149,6 +149,8 @@ def load_library():
                                                              XV_ABI_VERSION, ctypes.sizeof(XvTopology)))
     lib.xv_check_overflow.argtypes = [P, P]
     lib.xv_check_overflow.restype = ctypes.c_int
+    lib.xv_rescue_overflow.argtypes = [P, P]
+    lib.xv_rescue_overflow.restype = ctypes.c_int
     lib.xv_last_launch_count.argtypes = [P]
     lib.xv_last_launch_count.restype = I32
     lib.xv_last_kernel_ms.argtypes = [P, ctypes.POINTER(ctypes.c_float), I32]
@@ -236,7 +238,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = ["xv_create", "xv_destroy", "xv_set_param", "xv_workspace_bytes", "xv_forward",
-                    "xv_forward_layers", "xv_extract_host", "xv_submit_host", "xv_collect", "xv_check_overflow", "xv_last_launch_count",
+                    "xv_forward_layers", "xv_extract_host", "xv_submit_host", "xv_collect", "xv_check_overflow", "xv_rescue_overflow", "xv_last_launch_count",
                     "xv_last_kernel_ms", "xv_set_option", "xv_last_error", "xv_version", "xv_ark_scan",
                     "xv_forward_utts", "xv_submit_host_utts", "xv_peer_alloc", "xv_peer_open", "xv_peer_close", "xv_peer_free",
                     "xv_peer_read", "xv_abi_version", "xv_topology_size",
@@ -500,6 +502,16 @@ class XvecEngine:
         import torch
         s = torch.cuda.current_stream(self.device) if stream is None else stream
         _check(self.lib, self.lib.xv_check_overflow(self.handle, s.cuda_stream))
+
+    def rescue_overflow(self, stream=None):
+        """For the enqueue-only calls (``forward`` / ``forward_utts``): 0 if nothing overflowed the fp16 range since the
+        last check, else the number of per-layer scales that were raised -- run the forward again."""
+        import torch
+        s = torch.cuda.current_stream(self.device) if stream is None else stream
+        rc = int(self.lib.xv_rescue_overflow(self.handle, s.cuda_stream))
+        if rc < 0:
+            _check(self.lib, rc)
+        return rc
 
     def extract_host(self, feats_host, seg_lens, emb_host=None):
         """Host in / host out (the reference's sess.run boundary).  feats_host: float32

@@ -127,7 +127,7 @@ int frontend_impl(xv_model* m, const float* feats_dev, const float* vad_dev, con
     opted = smem;
   }
   XV_CUDA(launch_k(pdl, kernel, dim3(unsigned(tile)), dim3(xvfe::THREADS), smem, stream, um, o, sp, int32_t(m->topo.feat_dim),
-                   feats_dev, vad_dev, static_cast<const int32_t*>(count_pass ? tile_cnt : nullptr), out_dev, m->overflow_dev));
+                   feats_dev, vad_dev, static_cast<const int32_t*>(count_pass ? tile_cnt : nullptr), out_dev, m->cur_flag));
   ++m->last_frontend_launches;
   XV_CUDA(cudaGetLastError());
   return XV_OK;
@@ -195,16 +195,20 @@ int xv_submit_host_raw(xv_model* m, const float* feats_host, const float* vad_ho
   XV_CUDA(grow(&sl.ws_dev, &sl.ws_cap, ws_bytes));
   XV_CUDA(cudaMemcpyAsync(sl.raw_dev, feats_host, raw_bytes, cudaMemcpyHostToDevice, sl.stream));
   if (vad_host) XV_CUDA(cudaMemcpyAsync(sl.vad_dev, vad_host, vad_bytes, cudaMemcpyHostToDevice, sl.stream));
+  m->cur_flag = m->overflow_dev + 1 + si;          // this submission's flag word (front-end mismatch bit, fp16 store overflow bits)
   int rc = frontend_impl(m, sl.raw_dev, vad_host ? sl.vad_dev : nullptr, utt_len_host, out_keep_host, n_utt, opts, sl.feats_dev,
                          sl.fe_ws_dev, sl.fe_ws_cap, sl.stream, nullptr);
+  m->cur_flag = m->overflow_dev;
   if (rc != XV_OK) return rc;
   const int fe_launches = m->last_frontend_launches;
-  rc = forward_impl(m, sl.feats_dev, seg_len_host, n_seg, sl.emb_dev, sl.ws_dev, sl.ws_cap, sl.stream, nullptr, nullptr);
+  // the network part is remembered like any other submission: an fp16 range rescue re-runs it from sl.feats_dev
+  xv_model::HostSlot::Redo& rd = sl.redo;
+  rd.seg_len.assign(seg_len_host, seg_len_host + n_seg);
+  rd.utt = false; rd.has_first = rd.has_dst = false; rd.n_utt = 0; rd.out_dev = nullptr;
+  rd.host_out = emb_host;
+  rc = enqueue_slot(m, si);
   if (rc != XV_OK) return rc;
   m->last_launches += fe_launches;
-  XV_CUDA(cudaMemcpyAsync(emb_host, sl.emb_dev, emb_bytes, cudaMemcpyDeviceToHost, sl.stream));
-  XV_CUDA(cudaMemcpyAsync(sl.overflow_host, m->overflow_dev, 4, cudaMemcpyDeviceToHost, sl.stream));
-  XV_CUDA(cudaEventRecord(sl.done, sl.stream));
   sl.busy = true;
   m->slot_next = (si + 1) % XV_HOST_SLOTS;
   *ticket = si;

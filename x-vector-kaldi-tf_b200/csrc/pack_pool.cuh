@@ -115,6 +115,9 @@ struct StatsArgs {
                               // of the split-precision embedding GEMM, x = hi + lo to ~2^-22
   float var_eps;
   int32_t weighted;           // 1: the partial sums are already weighted by attention weights that sum to 1 (n := 1)
+  float sum_scale;            // the partial sums are of y / sum_scale (the last layer's rescue exponent; 0 = 1)
+  float split_scale;          // the split copy holds statistic * split_scale (2^-e: the fp16 range rescue; 0 = 1)
+  uint32_t* overflow_flag;    // bit 16 is set when a scaled statistic still leaves the fp16 range (may be null)
 };
 
 __device__ __forceinline__ void store_split(__half* row, int K, int k, float x) {
@@ -151,8 +154,9 @@ __global__ void __launch_bounds__(STATS_THREADS) pool_stats_kernel(const StatsAr
     s2 += double(__ldg(p + int64_t(b) * 2 * C + C));
   }
   const double inv_n = a.weighted ? 1.0 : 1.0 / double(len);
-  const double mean = s1 * inv_n;
-  const double var = fmax(s2 * inv_n - mean * mean, 0.0);
+  const double up = a.sum_scale != 0.f ? double(a.sum_scale) : 1.0;
+  const double mean = s1 * inv_n * up;
+  const double var = fmax(s2 * inv_n * up * up - mean * mean, 0.0);
   const float fm = float(mean), fs = float(sqrt(var + double(a.var_eps)));
   if (a.stats != nullptr) {
     a.stats[int64_t(seg) * 2 * C + c] = fm;
@@ -160,8 +164,11 @@ __global__ void __launch_bounds__(STATS_THREADS) pool_stats_kernel(const StatsAr
   }
   if (a.split != nullptr) {
     __half* row = a.split + int64_t(seg) * 6 * C;
-    store_split(row, 2 * C, c, fm);
-    store_split(row, 2 * C, C + c, fs);
+    const float k = a.split_scale != 0.f ? a.split_scale : 1.f;
+    const float sm = fm * k, ss = fs * k;
+    if (!(fabsf(sm) <= 65504.f && ss <= 65504.f) && a.overflow_flag != nullptr) atomicOr(a.overflow_flag, 1u << 16);
+    store_split(row, 2 * C, c, sm);
+    store_split(row, 2 * C, C + c, ss);
   }
 }
 
@@ -172,6 +179,7 @@ struct FcReduceArgs {
   const float* b0;            // [E]
   float* emb;                 // [n_seg, E]
   int32_t n_seg, E, splits;
+  float out_scale;            // the K-split sum is multiplied by this before the bias (2^e of the statistics' rescue; 0 = 1)
 };
 
 __global__ void __launch_bounds__(64) embed_reduce_kernel(const FcReduceArgs a) {
@@ -181,7 +189,9 @@ __global__ void __launch_bounds__(64) embed_reduce_kernel(const FcReduceArgs a) 
   const int64_t n4 = int64_t(a.n_seg) * a.E / 4;
   if (i4 >= n4) return;
   const int o4 = int(i4 % (a.E / 4));
-  float4 sum = __ldg(reinterpret_cast<const float4*>(a.b0) + o4);
+  const float4 bias = __ldg(reinterpret_cast<const float4*>(a.b0) + o4);
+  const bool scaled = a.out_scale != 0.f && a.out_scale != 1.f;
+  float4 sum = scaled ? make_float4(0.f, 0.f, 0.f, 0.f) : bias;       // unscaled: bias first, as before (same bits)
   const float4* p = reinterpret_cast<const float4*>(a.partial) + i4;
   int s = 0;
   for (; s + 12 <= a.splits; s += 12) {                                        // 12 loads in flight, fixed order
@@ -194,6 +204,10 @@ __global__ void __launch_bounds__(64) embed_reduce_kernel(const FcReduceArgs a) 
   for (; s < a.splits; ++s) {
     const float4 v = __ldcg(p + int64_t(s) * n4);
     sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+  }
+  if (scaled) {
+    sum.x = fmaf(sum.x, a.out_scale, bias.x); sum.y = fmaf(sum.y, a.out_scale, bias.y);
+    sum.z = fmaf(sum.z, a.out_scale, bias.z); sum.w = fmaf(sum.w, a.out_scale, bias.w);
   }
   reinterpret_cast<float4*>(a.emb)[i4] = sum;
 }
@@ -349,14 +363,14 @@ __global__ void __launch_bounds__(FC_THREADS) embed_fc_kernel(const FcArgs a) {
 
 // ------------------------------------------------------------------------------------------
 __global__ void unpack_rows_kernel(const __half* __restrict__ h, SegMeta seg, int32_t channels,
-                                   float* __restrict__ out) {
+                                   float* __restrict__ out, float scale) {
   cudaTriggerProgrammaticLaunchCompletion();
   cudaGridDependencySynchronize();
   const int s = blockIdx.x;
   const int len = seg.len[s];
   const int64_t src0 = int64_t(seg.row_start[s]) * channels, dst0 = int64_t(seg.feat_start[s]) * channels;
   const int64_t n = int64_t(len) * channels;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) out[dst0 + i] = __half2float(h[src0 + i]);
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) out[dst0 + i] = __half2float(h[src0 + i]) * scale;
 }
 
 
@@ -404,7 +418,7 @@ attn_softmax_kernel(const float* __restrict__ score_partial, int32_t n_part, Seg
 // (the layout pool_stats_kernel combines; h2 = columns [col0, col0 + C) of the last layer's stored activation).
 __global__ void __launch_bounds__(256)
 attn_pool_kernel(const __half* __restrict__ h, int32_t row_stride, int32_t col0, int32_t C, const float* __restrict__ attn,
-                 const uint8_t* __restrict__ blk_valid, float* __restrict__ partial) {
+                 const uint8_t* __restrict__ blk_valid, float* __restrict__ partial, float in_scale) {
   __shared__ float red[8][2][256];
   cudaTriggerProgrammaticLaunchCompletion();
   cudaGridDependencySynchronize();
@@ -430,7 +444,8 @@ attn_pool_kernel(const __half* __restrict__ h, int32_t row_stride, int32_t col0,
     const __half2* hp = reinterpret_cast<const __half2*>(&u[rr]);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float2 f = __half22float2(hp[i]);
+      float2 f = __half22float2(hp[i]);
+      f.x *= in_scale; f.y *= in_scale;                 // rows are stored / 2^e (fp16 range rescue); exact
       s1[2 * i] = fmaf(a[rr], f.x, s1[2 * i]);         s2[2 * i] = fmaf(a[rr] * f.x, f.x, s2[2 * i]);
       s1[2 * i + 1] = fmaf(a[rr], f.y, s1[2 * i + 1]); s2[2 * i + 1] = fmaf(a[rr] * f.y, f.y, s2[2 * i + 1]);
     }

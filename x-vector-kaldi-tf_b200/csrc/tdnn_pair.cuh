@@ -102,7 +102,10 @@ struct PairArgs {
   const uint8_t* blk_valid; // [R_pad/32]  mode 1: valid rows in the block (they are its first rows)
   float* partial;           // [R_pad/32][2][C_out]  mode 1;  [R_pad][2 * n_ch_tiles]  mode 3 (score partials)
   float* out_f32;           // [k_splits][n_rows][C_out]  mode 2: raw accumulators
-  uint32_t* overflow_flag;  // set to 1 if an fp16 output overflowed to inf
+  uint32_t* overflow_flag;  // overflow_bit is OR-ed in if an fp16 output overflowed to inf
+  uint32_t overflow_bit;    // 0 = 1u
+  float acc_scale;          // 0 = 1: the pre-activation is acc * acc_scale + bias (acc_scale = 2^e when the INPUT rows are stored
+                            // divided by 2^e: the fp16 range rescue of xvec_api.cu; exact, powers of two)
   long long* trace;         // diagnostics (tools/trace_tiles.py): [cluster][rank][TRACE_TILES][8] SM clock stamps, or null
 };
 constexpr int TRACE_TILES = 16;
@@ -116,8 +119,8 @@ __device__ __forceinline__ void trace_stamp(const PairArgs& a, int cluster, uint
 // One tcgen05.ld chunk of the store epilogue: 32 channels of one row -> 16 packed half2.
 // act(a): relu (models.py:479), or with LEAKY max(0,a) + alpha*min(0,a) (tf_block.py:47 / tf.nn.leaky_relu)
 template <bool LEAKY>
-__device__ __forceinline__ float act_bn(float acc, float b, float sc, float sh, float al) {
-  const float a = acc + b;
+__device__ __forceinline__ float act_bn(float acc, float b, float sc, float sh, float al, float as) {
+  const float a = fmaf(acc, as, b);                 // as = 1: acc + b, bit for bit
   const float r = LEAKY ? fmaf(al, fminf(a, 0.f), fmaxf(a, 0.f)) : fmaxf(a, 0.f);
   return fmaf(r, sc, sh);                           // BatchNorm eval branch folded: r * inv + shift (tf_block.py:26)
 }
@@ -125,7 +128,7 @@ __device__ __forceinline__ float act_bn(float acc, float b, float sc, float sh, 
 // s_par: shared-memory address of this tile's [bias(256) | scale(256) | shift(256) | alpha(256)] floats.
 template <bool LEAKY>
 __device__ __forceinline__ void epi_store_math(const uint32_t (&v)[32], uint32_t s_par, int c, bool valid,
-                                               uint32_t (&p)[16], uint32_t& hmax) {
+                                               uint32_t (&p)[16], uint32_t& hmax, float as) {
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
     const float4 b4 = ptx::lds_f4(s_par + uint32_t(c + g * 4) * 4u);
@@ -133,10 +136,10 @@ __device__ __forceinline__ void epi_store_math(const uint32_t (&v)[32], uint32_t
     const float4 h4 = ptx::lds_f4(s_par + uint32_t(2 * TILE_CH + c + g * 4) * 4u);
     float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (LEAKY) a4 = ptx::lds_f4(s_par + uint32_t(3 * TILE_CH + c + g * 4) * 4u);
-    const float y0 = act_bn<LEAKY>(__uint_as_float(v[g * 4 + 0]), b4.x, s4.x, h4.x, a4.x);
-    const float y1 = act_bn<LEAKY>(__uint_as_float(v[g * 4 + 1]), b4.y, s4.y, h4.y, a4.y);
-    const float y2 = act_bn<LEAKY>(__uint_as_float(v[g * 4 + 2]), b4.z, s4.z, h4.z, a4.z);
-    const float y3 = act_bn<LEAKY>(__uint_as_float(v[g * 4 + 3]), b4.w, s4.w, h4.w, a4.w);
+    const float y0 = act_bn<LEAKY>(__uint_as_float(v[g * 4 + 0]), b4.x, s4.x, h4.x, a4.x, as);
+    const float y1 = act_bn<LEAKY>(__uint_as_float(v[g * 4 + 1]), b4.y, s4.y, h4.y, a4.y, as);
+    const float y2 = act_bn<LEAKY>(__uint_as_float(v[g * 4 + 2]), b4.z, s4.z, h4.z, a4.z, as);
+    const float y3 = act_bn<LEAKY>(__uint_as_float(v[g * 4 + 3]), b4.w, s4.w, h4.w, a4.w, as);
     const uint32_t p0 = ptx::pack_half2(y0, y1), p1 = ptx::pack_half2(y2, y3);
     hmax = ptx::habs2_max(ptx::habs2_max(hmax, p0), p1);
     p[g * 2 + 0] = valid ? p0 : 0u;                  // gap rows stay exact zeros
@@ -398,6 +401,7 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
     const int colh = e >> 2;                         // which 128-column half of the accumulator
     const int te = threadIdx.x - 64;                 // 0..255
     const uint32_t t_empty_leader = ptx::mapa_cluster(t_empty(0), 0);   // + 8 * acc
+    const float acc_scale = args.acc_scale != 0.f ? args.acc_scale : 1.f;
     uint32_t it = 0;
     if (MODE == 2) {
       for (TileCursor tc = cur0; tc.item < n_items; tc.next(), ++it) {
@@ -465,7 +469,7 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
             const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const float x = __uint_as_float(v[chunk & 1][g * 4 + k]) + bb[k];
+              const float x = fmaf(__uint_as_float(v[chunk & 1][g * 4 + k]), acc_scale, bb[k]);
               const float th = 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f);      // tanh(x); saturates cleanly at +-1
               sum[k] = fmaf(vv[k], th, sum[k]);
             }
@@ -528,7 +532,7 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
             if (lane == 0) ptx::mbar_arrive_cluster(t_empty_leader + 8u * acc);
           }
           uint32_t p[16];
-          epi_store_math<LEAKY>(v[chunk & 1], s_par, colh * 128 + chunk * C_CHUNK, valid, p, hmax);
+          epi_store_math<LEAKY>(v[chunk & 1], s_par, colh * 128 + chunk * C_CHUNK, valid, p, hmax, acc_scale);
           const uint32_t buf = sC;                        // one box per warp: the previous chunk's store has had the
           if (lane == 0) ptx::tma_store_wait_read<0>();   // whole tcgen05.ld + math of this chunk to read it
           __syncwarp();
@@ -569,7 +573,8 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
                     static_cast<unsigned long long>(clock64()));
       }
       if (lane == 0) ptx::tma_store_wait_all<0>();
-      if ((hmax & 0x7fffu) >= 0x7c00u || ((hmax >> 16) & 0x7fffu) >= 0x7c00u) atomicOr(args.overflow_flag, 1u);
+      if ((hmax & 0x7fffu) >= 0x7c00u || ((hmax >> 16) & 0x7fffu) >= 0x7c00u)
+        atomicOr(args.overflow_flag, args.overflow_bit ? args.overflow_bit : 1u);
     } else {
       for (TileCursor tc = cur0; tc.item < n_items; tc.next(), ++it) {
         const uint32_t acc = it & 1u;
@@ -602,14 +607,14 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
             if (nv >= POOL_BLOCK) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
-                const float y = act_bn<LEAKY>(__uint_as_float(v[chunk & 1][i]), b, sc, sh, al);
+                const float y = act_bn<LEAKY>(__uint_as_float(v[chunk & 1][i]), b, sc, sh, al, acc_scale);
                 s1[i & 3] += y;
                 s2[i & 3] = fmaf(y, y, s2[i & 3]);
               }
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
-                float y = act_bn<LEAKY>(__uint_as_float(v[chunk & 1][i]), b, sc, sh, al);
+                float y = act_bn<LEAKY>(__uint_as_float(v[chunk & 1][i]), b, sc, sh, al, acc_scale);
                 y = (i < nv) ? y : 0.f;                              // rows past the segment end do not count
                 s1[i & 3] += y;
                 s2[i & 3] = fmaf(y, y, s2[i & 3]);

@@ -1079,7 +1079,7 @@ int64_t xv_train_debug_tensor(xv_trainer* t, const char* name, float* host_out, 
   if (capacity < n) return fail(XV_ENOMEM, "host buffer too small");
   float* tmp = nullptr;
   XV_CUDA(cudaMalloc(reinterpret_cast<void**>(&tmp), size_t(n) * 4));
-  xvk::unpack_rows_kernel<<<t->n_seg, 256>>>(static_cast<const __half*>(d.ptr), t->seg_meta, d.cols, tmp);
+  xvk::unpack_rows_kernel<<<t->n_seg, 256>>>(static_cast<const __half*>(d.ptr), t->seg_meta, d.cols, tmp, 1.0f);
   cudaError_t e = cudaDeviceSynchronize();
   if (e == cudaSuccess) e = cudaMemcpy(host_out, tmp, size_t(n) * 4, cudaMemcpyDeviceToHost);
   cudaFree(tmp);

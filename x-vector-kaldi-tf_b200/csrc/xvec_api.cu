@@ -17,7 +17,6 @@
 
 #include "pack_pool.cuh"
 #include "tdnn_pair.cuh"
-#include "tdnn_stack.cuh"
 
 namespace {
 
@@ -49,6 +48,10 @@ struct FrameLayer {
   float* scale_dev = nullptr;  // [c_out]
   float* shift_dev = nullptr;  // [c_out]
   float* alpha_dev = nullptr;  // [c_out] negative slope (leaky / PReLU topologies), else null
+  // fp16 range rescue: this layer's output rows are stored divided by 2^exp_out (scale_dev / shift_dev hold the folded
+  // BatchNorm times 2^-exp_out; the next layer's epilogue multiplies its accumulator by 2^exp_out).  Powers of two: exact.
+  int exp_out = 0;
+  std::vector<float> scale_host, shift_host;     // the unscaled folded BatchNorm
 };
 
 struct Plan {
@@ -84,11 +87,6 @@ struct xv_model {
   std::vector<FrameLayer> layers;
   __half* w0_split_dev = nullptr;    // [E, 3 * 2C] fp16 K-major [hi | lo | hi]: B operand of the split-precision GEMM
   int opt_fc_max_splits = 36;        // cap on the K-splits of the tensor-core embedding GEMM
-  int opt_stack_debug = 0;
-  int opt_stack = 0;                 // 1: all frame layers in ONE persistent launch (tdnn_stack_kernel).  Bit-identical
-                                     // to one launch per layer but measured 10-18 % SLOWER on B200: the step is bound by
-                                     // the 1 kW power cap, so removing idle gaps buys nothing and the dependency
-                                     // counters cost ~40 us; kept as an option and as a cross-check
   int opt_pdl = 1;                   // programmatic dependent launch between the kernels of a forward
   int opt_fc = 1;                    // 1: embed_layer-0 on tensor cores (split fp16), 0: fp32 SIMT GEMM
   int opt_blocking_collect = 0;      // 1: xv_collect sleeps on a blocking-sync event instead of spinning
@@ -99,8 +97,12 @@ struct xv_model {
   float* w0_dev = nullptr;           // [2C, E]
   float* b0_dev = nullptr;           // [E]
   int32_t* pack_lut_dev = nullptr;   // [k0_pad] spliced column -> staged feature offset (pack kernel)
-  uint32_t* overflow_dev = nullptr;
+  uint32_t* overflow_dev = nullptr;  // [1 + XV_HOST_SLOTS] flag words: [0] xv_forward / training, [1 + s] submission slot s
+  uint32_t* cur_flag = nullptr;      // the word the kernels of the enqueue in progress report to
   uint32_t* overflow_host = nullptr; // pinned
+  int exp_stats = 0;                 // fp16 range rescue of the pooled statistics (see apply_exponents)
+  int opt_rescue = 1;                // 1: xv_collect raises exponents and re-runs a batch whose fp16 stores overflowed
+  int rescues = 0;                   // batches re-run so far
   EncodeTiledFn encode = nullptr;
   // pinned staging ring for segment metadata
   int32_t* meta_host[META_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
@@ -124,6 +126,15 @@ struct xv_model {
     float* vad_dev = nullptr; size_t vad_cap = 0;
     void* fe_ws_dev = nullptr; size_t fe_ws_cap = 0;
     uint32_t* overflow_host = nullptr;   // pinned
+    // what a re-run after an fp16 range rescue needs (the caller's arrays may be gone by xv_collect)
+    struct Redo {
+      std::vector<int32_t> seg_len, first_seg;
+      std::vector<int64_t> dst_row;
+      bool utt = false, has_first = false, has_dst = false;
+      int32_t n_utt = 0;
+      float* out_dev = nullptr;
+      float* host_out = nullptr;         // emb_host / out_host of the submission (may be null)
+    } redo;
     cudaEvent_t done = nullptr;          // recorded behind the submission's last copy; created with cudaEventBlockingSync so that
                                          // xv_collect SLEEPS instead of spinning (a multi-GPU job runs reader threads on those cores)
     bool busy = false;
@@ -160,8 +171,7 @@ Plan make_plan(const xv_model* m, int64_t total_frames, int32_t n_seg) {
   p.fc_splits = K / 256;                                       // C_last is a multiple of 128
   p.fc_k_per_split = K / p.fc_splits;
   p.fc_counters = p.fc_m_tiles * p.fc_n_tiles;
-  // + per-layer row-tile completion counters of the whole-stack kernel (zeroed by the pack kernel with the rest)
-  p.n_counters = p.fc_counters + m->topo.n_frame_layers * int32_t(p.r_pad / tdnn2::TILE_ROWS);
+  p.n_counters = p.fc_counters;
   {
     // tensor-core embedding GEMM: K' = 3K in 128-wide chunks, always cut into the same number of K-splits (the
     // largest divisor of the chunk count that leaves >= 2 chunks per split) whatever the batch: the summation order
@@ -230,6 +240,47 @@ const std::vector<float>* find_param(const xv_model* m, const std::string& name,
   return &it->second;
 }
 
+// fp16 range rescue.  Every stored activation tensor is fp16; a trained model whose activations pass 65 504 (the reference
+// computes in fp32 and loads any model, models.py:476-480) is handled by storing layer i's rows divided by 2^exp_out[i]:
+// y' = (act(a) * scale + shift) * 2^-e is folded into scale / shift, the consumer multiplies its fp32 accumulator by 2^e
+// before the bias -- exact operations, so results equal the unscaled arithmetic wherever that one does not overflow
+// (only fp16 subnormals, |y| < 6e-5 * 2^e, round differently).  The pooled statistics get the same treatment on their
+// way into the split-fp16 embedding GEMM (exp_stats).  Exponents start at 0 and are raised when a store overflows
+// (xv_rescue_overflow; xv_collect does it by itself and re-runs the batch).
+int apply_exponents(xv_model* m, cudaStream_t stream_or_null) {
+  for (auto& L : m->layers) {
+    std::vector<float> sc(L.scale_host), sh(L.shift_host);
+    const float f = std::ldexp(1.0f, -L.exp_out);
+    for (auto& v : sc) v *= f;
+    for (auto& v : sh) v *= f;
+    if (stream_or_null) XV_CUDA(cudaStreamSynchronize(stream_or_null));
+    XV_CUDA(cudaMemcpy(L.scale_dev, sc.data(), sc.size() * 4, cudaMemcpyHostToDevice));
+    XV_CUDA(cudaMemcpy(L.shift_dev, sh.data(), sh.size() * 4, cudaMemcpyHostToDevice));
+  }
+  return XV_OK;
+}
+
+// Overflow flag word: bit 0 = an fp16 store of the training path overflowed, bit 1 = front-end row-count mismatch,
+// bit 8 + i = a store of frame layer i overflowed, bit 16 = a pooled statistic left the fp16 range on its way into the
+// embedding GEMM.  Raises the exponents of what overflowed; returns how many were raised.
+constexpr int RESCUE_STEP = 6;        // x 1/64 per attempt
+constexpr int RESCUE_MAX_EXP = 96;    // fp32 accumulators hold up to 3e38
+int raise_exponents(xv_model* m, uint32_t flag) {
+  int raised = 0;
+  for (int i = 0; i < int(m->layers.size()); ++i)
+    if ((flag >> (8 + i)) & 1u) {
+      if (m->layers[i].exp_out + RESCUE_STEP > RESCUE_MAX_EXP) return -1;
+      m->layers[i].exp_out += RESCUE_STEP;
+      ++raised;
+    }
+  if ((flag >> 16) & 1u) {
+    if (m->exp_stats + RESCUE_STEP > RESCUE_MAX_EXP) return -1;
+    m->exp_stats += RESCUE_STEP;
+    ++raised;
+  }
+  return raised;
+}
+
 // Pack host parameters into device layouts.  BatchNorm (evaluation branch, tf_block.py:25-26)
 // is folded to scale = gamma * rsqrt(var + eps), shift = beta - mean * scale, in fp32.
 int finalize_params(xv_model* m) {
@@ -269,8 +320,9 @@ int finalize_params(xv_model* m) {
     XV_CUDA(cudaMalloc(&L.shift_dev, L.c_out * 4));
     XV_CUDA(cudaMemcpy(L.w_dev, wt.data(), wt.size() * sizeof(__half), cudaMemcpyHostToDevice));
     XV_CUDA(cudaMemcpy(L.bias_dev, b->data(), L.c_out * 4, cudaMemcpyHostToDevice));
-    XV_CUDA(cudaMemcpy(L.scale_dev, scale.data(), L.c_out * 4, cudaMemcpyHostToDevice));
-    XV_CUDA(cudaMemcpy(L.shift_dev, shift.data(), L.c_out * 4, cudaMemcpyHostToDevice));
+    L.scale_host = scale;
+    L.shift_host = shift;
+    L.exp_out = 0;
     if (t.act != XV_ACT_RELU) {
       std::vector<float> alpha(L.c_out, 0.2f);                       // tf.nn.leaky_relu(h, alpha=0.2)  (models.py:912)
       if (t.act == XV_ACT_PRELU) {                                   // prelu(h, shared=False)  (tf_block.py:38-47)
@@ -322,8 +374,9 @@ int finalize_params(xv_model* m) {
     XV_CUDA(cudaMalloc(&m->w0_split_dev, ws.size() * sizeof(__half)));
     XV_CUDA(cudaMemcpy(m->w0_split_dev, ws.data(), ws.size() * sizeof(__half), cudaMemcpyHostToDevice));
   }
+  m->exp_stats = 0;
   m->dirty = false;
-  return XV_OK;
+  return apply_exponents(m, nullptr);
 }
 
 // The model's sticky device flag: bit 0 = an fp16 store overflowed, bit 1 = the feature front end found fewer voiced rows
@@ -564,67 +617,7 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
   const bool attention = m->topo.pooling == XV_POOL_ATTENTION;
   const bool want_last = attention || (layer_out_dev && layer_out_dev[nl - 1]);   // attention pooling reads the stored activation
   const __half* in = x0;
-  const bool use_stack = m->opt_stack && !attention && !layer_out_dev && !m->opt_profile && !m->opt_resident && nl <= tdnn2::MAX_STACK_LAYERS;
-  if (use_stack) {
-    // ---- all frame layers in one persistent launch; layers are chained by per-row-tile completion counters ----
-    tdnn2::StackArgs sa{};
-    sa.n_layers = nl;
-    sa.n_row_tiles = int32_t(r_pad / tdnn2::TILE_ROWS);
-    sa.row_valid = row_valid;
-    sa.blk_valid = blk_valid;
-    sa.partial = pool_partial;
-    sa.overflow_flag = m->overflow_dev;
-    sa.done = counters + p.fc_counters;
-    sa.debug = m->opt_stack_debug;
-    const __half* lin = x0;
-    for (int i = 0; i < nl; ++i) {
-      const FrameLayer& L = m->layers[i];
-      const bool last = i == nl - 1;
-      __half* out = last ? hlast : ((i & 1) ? hb : ha);
-      const int halo = (L.gemm_taps - 1) / 2 * L.dilation;
-      const int c_in_gemm = (i == 0) ? L.k_total : L.c_in_pad;
-      const bool reuse = L.gemm_taps > 1 && halo <= tdnn2::MAX_REUSE_HALO;
-      if (halo > tdnn2::TILE_ROWS) return fail(XV_EINVAL, "temporal context wider than one row tile");
-      tdnn2::StackLayer& S = sa.layer[i];
-      rc = encode_2d(m, &S.tmap_act, const_cast<__half*>(lin), uint64_t(c_in_gemm), uint64_t(r_pad), tdnn2::BLOCK_K,
-                     reuse ? tdnn2::ACT_BOX_ROWS_REUSE : tdnn2::ACT_BOX_ROWS_PLAIN, CU_TENSOR_MAP_SWIZZLE_128B);
-      if (rc != XV_OK) return rc;
-      rc = encode_2d(m, &S.tmap_wgt, L.w_dev, uint64_t(L.k_total), uint64_t(L.c_out), tdnn2::BLOCK_K, tdnn2::CTA_CH,
-                     CU_TENSOR_MAP_SWIZZLE_128B);
-      if (rc != XV_OK) return rc;
-      rc = encode_2d(m, &S.tmap_out, out, uint64_t(L.c_out), uint64_t(r_pad), tdnn2::C_CHUNK, 32, CU_TENSOR_MAP_SWIZZLE_64B);
-      if (rc != XV_OK) return rc;
-      S.n_ch_tiles = L.c_out / tdnn2::TILE_CH;
-      S.c_chunks = c_in_gemm / (2 * tdnn2::BLOCK_K);
-      S.taps = L.gemm_taps;
-      S.dilation = L.dilation;
-      S.c_in_pad = c_in_gemm;
-      S.reuse = reuse ? 1 : 0;
-      const int64_t act_atom = reuse ? tdnn2::ACT_ATOM_BYTES : tdnn2::ACT_BOX_ROWS_PLAIN * 128;
-      if (reuse) {
-        S.n_act_stages = 2;
-        S.n_wgt_stages = int(std::min<int64_t>(tdnn2::MAX_STAGES, (tdnn2::RING_BYTES - 2 * 2 * act_atom) / (2 * tdnn2::WGT_ATOM_BYTES)));
-      } else {
-        S.n_act_stages = S.n_wgt_stages =
-            int(std::min<int64_t>(tdnn2::MAX_STAGES, tdnn2::RING_BYTES / (2 * (act_atom + tdnn2::WGT_ATOM_BYTES))));
-      }
-      S.mode = last ? 1 : 0;
-      S.c_out = L.c_out;
-      S.bias = L.bias_dev;
-      S.scale = L.scale_dev;
-      S.shift = L.shift_dev;
-      S.alpha = L.alpha_dev;
-      lin = out;
-    }
-    const int grid = 2 * int(std::min<int64_t>(int64_t(sa.n_row_tiles) * sa.layer[0].n_ch_tiles, m->num_clusters));
-    if (m->layers[0].alpha_dev != nullptr)
-      XV_CUDA(launch_k(pdl, tdnn2::tdnn_stack_kernel<true>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, sa));
-    else
-      XV_CUDA(launch_k(pdl, tdnn2::tdnn_stack_kernel<false>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, sa));
-    XV_CUDA(cudaGetLastError());
-    ++launches;
-  }
-  for (int i = 0; i < nl && !use_stack; ++i) {
+  for (int i = 0; i < nl; ++i) {
     const FrameLayer& L = m->layers[i];
     const bool last = i == nl - 1;
     __half* out = last ? hlast : ((i & 1) ? hb : ha);
@@ -664,7 +657,9 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       a.row_valid = row_valid;
       a.blk_valid = blk_valid;
       a.partial = pool_partial;
-      a.overflow_flag = m->overflow_dev;
+      a.overflow_flag = m->cur_flag;
+      a.overflow_bit = 1u << (8 + i);
+      a.acc_scale = i > 0 ? std::ldexp(1.0f, m->layers[i - 1].exp_out) : 1.0f;      // the input rows are stored / 2^exp
       a.trace = (i == m->opt_trace_layer) ? m->opt_trace : nullptr;
       a.wgt_resident = resident ? 1 : 0;
       a.prefetch = m->opt_prefetch;
@@ -706,7 +701,8 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       }
     }
     if (layer_out_dev && layer_out_dev[i]) {
-      XV_CUDA(launch_k(pdl, xvk::unpack_rows_kernel, dim3(n_seg), dim3(256), 0, stream, static_cast<const __half*>(out), seg, int32_t(L.c_out), layer_out_dev[i]));
+      XV_CUDA(launch_k(pdl, xvk::unpack_rows_kernel, dim3(n_seg), dim3(256), 0, stream, static_cast<const __half*>(out), seg, int32_t(L.c_out), layer_out_dev[i],
+                       std::ldexp(1.0f, L.exp_out)));
       XV_CUDA(cudaGetLastError());
       ++launches;
     }
@@ -732,7 +728,8 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       a.c_out = C;
       a.bias = m->att_b_dev; a.scale = m->att_v_dev;
       a.partial = score;
-      a.overflow_flag = m->overflow_dev;
+      a.overflow_flag = m->cur_flag;
+      a.acc_scale = std::ldexp(1.0f, m->layers[nl - 1].exp_out);
       a.mode = 3;
       a.n_act_stages = a.n_wgt_stages = int(std::min<int64_t>(tdnn2::MAX_STAGES, tdnn2::RING_BYTES / (2 * (tdnn2::ACT_BOX_ROWS_PLAIN * 128 + tdnn2::WGT_ATOM_BYTES))));
       a.c_chunks = C / (2 * tdnn2::BLOCK_K);
@@ -751,7 +748,8 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       ++launches;
       XV_PROF();
       XV_CUDA(launch_k(pdl, xvk::attn_pool_kernel, dim3(unsigned(r_pad / 32) * (C / 256)), dim3(256), 0, stream, static_cast<const __half*>(hlast),
-                       int32_t(W), int32_t(C), int32_t(C), static_cast<const float*>(attn), static_cast<const uint8_t*>(blk_valid), pool_partial));
+                       int32_t(W), int32_t(C), int32_t(C), static_cast<const float*>(attn), static_cast<const uint8_t*>(blk_valid), pool_partial,
+                       std::ldexp(1.0f, m->layers[nl - 1].exp_out)));
       XV_PROF();
       XV_CUDA(cudaGetLastError());
       ++launches;
@@ -770,6 +768,9 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       a.stats = stats;
       a.split = split;
       a.var_eps = m->topo.var_eps;
+      a.sum_scale = attention ? 1.0f : std::ldexp(1.0f, m->layers[nl - 1].exp_out);   // (attn_pool_kernel already rescaled its rows)
+      a.split_scale = std::ldexp(1.0f, -m->exp_stats);
+      a.overflow_flag = m->cur_flag;
       dim3 grid((a.channels + xvk::STATS_THREADS - 1) / xvk::STATS_THREADS, n_seg);
       XV_PROF();
       XV_CUDA(launch_k(pdl, xvk::pool_stats_kernel, grid, dim3(xvk::STATS_THREADS), 0, stream, a));
@@ -803,7 +804,7 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
         a.c_out = E;
         a.n_rows = gn;
         a.out_f32 = fc_partial;
-        a.overflow_flag = m->overflow_dev;
+        a.overflow_flag = m->cur_flag;
         const int64_t tiles = int64_t(a.n_row_tiles) * a.n_ch_tiles * a.k_splits;
         const int grid = 2 * int(std::min<int64_t>(tiles, m->num_clusters));
         XV_PROF();
@@ -818,6 +819,7 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
         r.n_seg = gn;
         r.E = E;
         r.splits = p.tc_splits;
+        r.out_scale = std::ldexp(1.0f, m->exp_stats);
         const int64_t n4 = int64_t(gn) * E / 4;
         XV_PROF();
         XV_CUDA(launch_k(pdl, xvk::embed_reduce_kernel, dim3(unsigned((n4 + 63) / 64)), dim3(64), 0, stream, r));
@@ -954,10 +956,6 @@ int xv_create(xv_model** out, int device, const xv_topology* topo) {
         tdnn2::tdnn_pair_kernel<3, 2, false>};
     for (auto k : kernels)
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(tdnn2::tdnn_stack_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(tdnn2::tdnn_stack_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
   }
   if (e == cudaSuccess) {
     cudaLaunchConfig_t cfg{};
@@ -982,8 +980,9 @@ int xv_create(xv_model** out, int device, const xv_topology* topo) {
     e = cudaMalloc(&m->pack_lut_dev, lut.size() * 4);
     if (e == cudaSuccess) e = cudaMemcpy(m->pack_lut_dev, lut.data(), lut.size() * 4, cudaMemcpyHostToDevice);
   }
-  if (e == cudaSuccess) e = cudaMalloc(&m->overflow_dev, 4);
-  if (e == cudaSuccess) e = cudaMemset(m->overflow_dev, 0, 4);
+  if (e == cudaSuccess) e = cudaMalloc(&m->overflow_dev, 4 * (1 + XV_HOST_SLOTS));
+  if (e == cudaSuccess) e = cudaMemset(m->overflow_dev, 0, 4 * (1 + XV_HOST_SLOTS));
+  m->cur_flag = m->overflow_dev;
   if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&m->overflow_host), 4, cudaHostAllocDefault);
   for (int i = 0; i < XV_HOST_SLOTS && e == cudaSuccess; ++i) {
     e = cudaStreamCreateWithFlags(&m->slots[i].stream, cudaStreamNonBlocking);
@@ -1097,6 +1096,36 @@ int xv_forward_layers(xv_model* m, const float* feats_dev, const int32_t* seg_le
 }
 
 namespace {
+// Forward of the submission remembered in slot `si` (features already in the slot's device buffer) + the copies back.
+int enqueue_slot(xv_model* m, int si) {
+  xv_model::HostSlot& sl = m->slots[si];
+  const xv_model::HostSlot::Redo& rd = sl.redo;
+  const int32_t n_seg = int32_t(rd.seg_len.size());
+  m->cur_flag = m->overflow_dev + 1 + si;
+  int rc;
+  if (rd.utt) {
+    UttOut u;
+    u.first_seg_host = rd.has_first ? rd.first_seg.data() : nullptr;
+    u.dst_row_host = rd.has_dst ? rd.dst_row.data() : nullptr;
+    u.n_utt = rd.n_utt;
+    u.out_dev = rd.out_dev;
+    u.out_local_dev = rd.host_out ? sl.emb_dev : nullptr;        // the slot's buffer holds the rows the host reads
+    rc = forward_impl(m, sl.feats_dev, rd.seg_len.data(), n_seg, nullptr, sl.ws_dev, sl.ws_cap, sl.stream, nullptr, nullptr, &u);
+    m->cur_flag = m->overflow_dev;
+    if (rc != XV_OK) return rc;
+    if (rd.host_out)
+      XV_CUDA(cudaMemcpyAsync(rd.host_out, sl.emb_dev, size_t(rd.n_utt) * m->topo.emb_dim * 4, cudaMemcpyDeviceToHost, sl.stream));
+  } else {
+    rc = forward_impl(m, sl.feats_dev, rd.seg_len.data(), n_seg, sl.emb_dev, sl.ws_dev, sl.ws_cap, sl.stream, nullptr, nullptr);
+    m->cur_flag = m->overflow_dev;
+    if (rc != XV_OK) return rc;
+    XV_CUDA(cudaMemcpyAsync(rd.host_out, sl.emb_dev, size_t(n_seg) * m->topo.emb_dim * 4, cudaMemcpyDeviceToHost, sl.stream));
+  }
+  XV_CUDA(cudaMemcpyAsync(sl.overflow_host, m->overflow_dev + 1 + si, 4, cudaMemcpyDeviceToHost, sl.stream));
+  XV_CUDA(cudaEventRecord(sl.done, sl.stream));
+  return XV_OK;
+}
+
 // Common body of xv_submit_host / xv_submit_host_utts.
 int submit_impl(xv_model* m, const float* feats_host, const int32_t* seg_len_host, int32_t n_seg, float* emb_host,
                 const UttOut* utt_in, float* utt_host_out, int32_t* ticket) {
@@ -1128,22 +1157,22 @@ int submit_impl(xv_model* m, const float* feats_host, const int32_t* seg_len_hos
   XV_CUDA(grow(reinterpret_cast<void**>(&sl.emb_dev), &sl.emb_cap, emb_bytes));
   XV_CUDA(grow(&sl.ws_dev, &sl.ws_cap, ws_bytes));
   XV_CUDA(cudaMemcpyAsync(sl.feats_dev, feats_host, feat_bytes, cudaMemcpyHostToDevice, sl.stream));
-  int rc;
+  // remember the submission: an fp16 range rescue in xv_collect re-runs it from the slot's device copy of the features
+  xv_model::HostSlot::Redo& rd = sl.redo;
+  rd.seg_len.assign(seg_len_host, seg_len_host + n_seg);
+  rd.utt = utt_in != nullptr;
+  rd.has_first = rd.has_dst = false;
+  rd.n_utt = 0;
+  rd.out_dev = nullptr;
+  rd.host_out = utt_in ? utt_host_out : emb_host;
   if (utt_in) {
-    UttOut u = *utt_in;
-    const int32_t n_utt = u.first_seg_host ? u.n_utt : n_seg;
-    u.out_local_dev = utt_host_out ? sl.emb_dev : nullptr;       // the slot's buffer holds the rows the host reads
-    rc = forward_impl(m, sl.feats_dev, seg_len_host, n_seg, nullptr, sl.ws_dev, sl.ws_cap, sl.stream, nullptr, nullptr, &u);
-    if (rc != XV_OK) return rc;
-    if (utt_host_out)
-      XV_CUDA(cudaMemcpyAsync(utt_host_out, sl.emb_dev, size_t(n_utt) * m->topo.emb_dim * 4, cudaMemcpyDeviceToHost, sl.stream));
-  } else {
-    rc = forward_impl(m, sl.feats_dev, seg_len_host, n_seg, sl.emb_dev, sl.ws_dev, sl.ws_cap, sl.stream, nullptr, nullptr);
-    if (rc != XV_OK) return rc;
-    XV_CUDA(cudaMemcpyAsync(emb_host, sl.emb_dev, emb_bytes, cudaMemcpyDeviceToHost, sl.stream));
+    rd.n_utt = utt_in->first_seg_host ? utt_in->n_utt : n_seg;
+    rd.out_dev = utt_in->out_dev;
+    if (utt_in->first_seg_host) { rd.has_first = true; rd.first_seg.assign(utt_in->first_seg_host, utt_in->first_seg_host + rd.n_utt + 1); }
+    if (utt_in->dst_row_host) { rd.has_dst = true; rd.dst_row.assign(utt_in->dst_row_host, utt_in->dst_row_host + rd.n_utt); }
   }
-  XV_CUDA(cudaMemcpyAsync(sl.overflow_host, m->overflow_dev, 4, cudaMemcpyDeviceToHost, sl.stream));
-  XV_CUDA(cudaEventRecord(sl.done, sl.stream));
+  int rc = enqueue_slot(m, si);
+  if (rc != XV_OK) return rc;
   sl.busy = true;
   m->slot_next = (si + 1) % XV_HOST_SLOTS;
   *ticket = si;
@@ -1242,11 +1271,45 @@ int xv_collect(xv_model* m, int32_t ticket) {
   // process at the price of a wake-up latency per collect; measured slower for 0.5 ms steps, so off by default)
   if (m->opt_blocking_collect) XV_CUDA(cudaEventSynchronize(sl.done));
   else XV_CUDA(cudaStreamSynchronize(sl.stream));
-  if (*sl.overflow_host != 0) {
-    XV_CUDA(cudaMemsetAsync(m->overflow_dev, 0, 4, sl.stream));
-    return sticky_flag_error(*sl.overflow_host);
+  uint32_t flag = *sl.overflow_host;
+  // fp16 range rescue: a store of a frame layer (bits 8..) or a pooled statistic (bit 16) overflowed.  Raise the exponents
+  // of what overflowed and run the submission again from the slot's device copy of its features, until it fits.
+  for (int attempt = 0; flag != 0 && (flag & 3u) == 0 && m->opt_rescue && attempt < 20; ++attempt) {
+    if (raise_exponents(m, flag) <= 0) break;
+    for (auto& other : m->slots) XV_CUDA(cudaStreamSynchronize(other.stream));   // nobody reads the old scale / shift any more
+    int rc = apply_exponents(m, nullptr);
+    if (rc != XV_OK) return rc;
+    XV_CUDA(cudaMemsetAsync(m->overflow_dev + 1 + ticket, 0, 4, sl.stream));
+    rc = enqueue_slot(m, ticket);
+    if (rc != XV_OK) return rc;
+    XV_CUDA(cudaStreamSynchronize(sl.stream));
+    flag = *sl.overflow_host;
+    ++m->rescues;
+  }
+  if (flag != 0) {
+    XV_CUDA(cudaMemsetAsync(m->overflow_dev + 1 + ticket, 0, 4, sl.stream));
+    return sticky_flag_error(flag);
   }
   return XV_OK;
+}
+
+int xv_rescue_overflow(xv_model* m, void* stream) {
+  if (!m) return fail(XV_EINVAL, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  XV_CUDA(cudaSetDevice(m->device));
+  XV_CUDA(cudaMemcpyAsync(m->overflow_host, m->overflow_dev, 4, cudaMemcpyDeviceToHost, s));
+  XV_CUDA(cudaStreamSynchronize(s));
+  const uint32_t flag = *m->overflow_host;
+  if (flag == 0) return 0;
+  XV_CUDA(cudaMemsetAsync(m->overflow_dev, 0, 4, s));
+  if (flag & 3u) return sticky_flag_error(flag);
+  const int raised = raise_exponents(m, flag);
+  if (raised <= 0) return fail(XV_EOVERFLOW, "activations exceed the fp16 range even after the largest rescue scale");
+  for (auto& sl : m->slots) XV_CUDA(cudaStreamSynchronize(sl.stream));
+  int rc = apply_exponents(m, s);
+  if (rc != XV_OK) return rc;
+  ++m->rescues;
+  return raised;
 }
 
 int xv_extract_host(xv_model* m, const float* feats_host, const int32_t* seg_len_host, int32_t n_seg, float* emb_host) {
@@ -1291,8 +1354,7 @@ int xv_set_option(xv_model* m, const char* name, int64_t value) {
   else if (n == "fc") m->opt_fc = int(value);
   else if (n == "pdl") m->opt_pdl = value != 0;
   else if (n == "blocking_collect") m->opt_blocking_collect = value != 0;
-  else if (n == "stack") m->opt_stack = value != 0;
-  else if (n == "stack_debug") m->opt_stack_debug = int(value);
+  else if (n == "rescue") m->opt_rescue = value != 0;
   else if (n == "fc_max_splits") m->opt_fc_max_splits = std::max(1, int(value));
   else if (n == "trace_ptr") m->opt_trace = reinterpret_cast<long long*>(static_cast<intptr_t>(value));   // device buffer
   else if (n == "trace_layer") m->opt_trace_layer = int(value);
