@@ -41,6 +41,7 @@ struct PackArgs {
   const int4* blk_info;      // [r_pad / 32] host-built: {first feature row, first frame in segment, segment length, valid rows}
   uint32_t* counters;        // [n_counters] zeroed here for embed_fc_kernel
   int32_t n_counters;
+  int32_t split;             // 1: rows are [hi (k0_pad) | lo (k0_pad)], x = hi + lo (split-precision model)
 };
 
 // One CTA per aligned 32-row block.  The block's feature rows (plus the first layer's context) are
@@ -62,10 +63,11 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_im2col_kernel(const PackArg
   const int t0 = bi.y, len = bi.z, nv = bi.w;
   if (threadIdx.x == 0) a.blk_valid[blockIdx.x] = uint8_t(nv);
   if (threadIdx.x < PACK_ROWS_PER_BLOCK) a.row_valid[r0 + threadIdx.x] = threadIdx.x < nv ? 1 : 0;
-  const int pieces = a.k0_pad >> 3;                                   // 16-byte pieces per row
+  const int pieces = a.k0_pad >> 3;                                   // 16-byte pieces per row (of one term)
+  const int row_w = a.split ? 2 * a.k0_pad : a.k0_pad;                // halfs per stored row
   if (nv == 0) {                                                      // gap / tail block: zero rows
-    for (int idx = threadIdx.x; idx < PACK_ROWS_PER_BLOCK * pieces; idx += PACK_THREADS)
-      reinterpret_cast<uint4*>(a.x0 + int64_t(r0) * a.k0_pad)[idx] = make_uint4(0u, 0u, 0u, 0u);
+    for (int idx = threadIdx.x; idx < PACK_ROWS_PER_BLOCK * (row_w >> 3); idx += PACK_THREADS)
+      reinterpret_cast<uint4*>(a.x0 + int64_t(r0) * row_w)[idx] = make_uint4(0u, 0u, 0u, 0u);
     return;
   }
   // stage frames t0-halo .. t0+31+halo: staged float i is feats[(fs + t0 - halo) * D + i] when its frame exists
@@ -83,16 +85,21 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_im2col_kernel(const PackArg
   __syncthreads();
   if (lr0 < rows_per_pass) {
     for (int lr = lr0; lr < PACK_ROWS_PER_BLOCK; lr += rows_per_pass) {
-      uint32_t w[4] = {0u, 0u, 0u, 0u};
+      uint32_t w[4] = {0u, 0u, 0u, 0u}, wl[4] = {0u, 0u, 0u, 0u};
       if (lr < nv) {
         const float* src = s_feat + lr * D;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const __half2 h = __floats2half2_rn(lut[2 * e] >= 0 ? src[lut[2 * e]] : 0.f, lut[2 * e + 1] >= 0 ? src[lut[2 * e + 1]] : 0.f);
+          const float x0 = lut[2 * e] >= 0 ? src[lut[2 * e]] : 0.f, x1 = lut[2 * e + 1] >= 0 ? src[lut[2 * e + 1]] : 0.f;
+          const __half2 h = __floats2half2_rn(x0, x1);
           w[e] = *reinterpret_cast<const uint32_t*>(&h);
+          const float2 hf = __half22float2(h);
+          const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+          wl[e] = *reinterpret_cast<const uint32_t*>(&l);
         }
       }
-      reinterpret_cast<uint4*>(a.x0 + int64_t(r0 + lr) * a.k0_pad)[pc] = make_uint4(w[0], w[1], w[2], w[3]);
+      reinterpret_cast<uint4*>(a.x0 + int64_t(r0 + lr) * row_w)[pc] = make_uint4(w[0], w[1], w[2], w[3]);
+      if (a.split) reinterpret_cast<uint4*>(a.x0 + int64_t(r0 + lr) * row_w + a.k0_pad)[pc] = make_uint4(wl[0], wl[1], wl[2], wl[3]);
     }
   }
 }
@@ -363,13 +370,22 @@ __global__ void __launch_bounds__(FC_THREADS) embed_fc_kernel(const FcArgs a) {
 
 // ------------------------------------------------------------------------------------------
 __global__ void unpack_rows_kernel(const __half* __restrict__ h, SegMeta seg, int32_t channels,
-                                   float* __restrict__ out, float scale) {
+                                   float* __restrict__ out, float scale, int32_t split = 0) {
   cudaTriggerProgrammaticLaunchCompletion();
   cudaGridDependencySynchronize();
   const int s = blockIdx.x;
   const int len = seg.len[s];
-  const int64_t src0 = int64_t(seg.row_start[s]) * channels, dst0 = int64_t(seg.feat_start[s]) * channels;
+  const int64_t dst0 = int64_t(seg.feat_start[s]) * channels;
   const int64_t n = int64_t(len) * channels;
+  if (split) {                                       // rows are [hi (channels) | lo (channels)]
+    const __half* base = h + int64_t(seg.row_start[s]) * 2 * channels;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+      const int64_t r = i / channels, c = i % channels;
+      out[dst0 + i] = (__half2float(base[r * 2 * channels + c]) + __half2float(base[r * 2 * channels + channels + c])) * scale;
+    }
+    return;
+  }
+  const int64_t src0 = int64_t(seg.row_start[s]) * channels;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) out[dst0 + i] = __half2float(h[src0 + i]) * scale;
 }
 
@@ -418,7 +434,7 @@ attn_softmax_kernel(const float* __restrict__ score_partial, int32_t n_part, Seg
 // (the layout pool_stats_kernel combines; h2 = columns [col0, col0 + C) of the last layer's stored activation).
 __global__ void __launch_bounds__(256)
 attn_pool_kernel(const __half* __restrict__ h, int32_t row_stride, int32_t col0, int32_t C, const float* __restrict__ attn,
-                 const uint8_t* __restrict__ blk_valid, float* __restrict__ partial, float in_scale) {
+                 const uint8_t* __restrict__ blk_valid, float* __restrict__ partial, float in_scale, int32_t lo_off) {
   __shared__ float red[8][2][256];
   cudaTriggerProgrammaticLaunchCompletion();
   cudaGridDependencySynchronize();
@@ -430,21 +446,26 @@ attn_pool_kernel(const __half* __restrict__ h, int32_t row_stride, int32_t col0,
   float s1[8], s2[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
-  uint4 u[4];
+  uint4 u[4], ul[4];
   float a[4];
 #pragma unroll
   for (int rr = 0; rr < 4; ++rr) {                    // all loads first (rows past nv are gap rows: zeros, weight 0)
     const int r = w * 4 + rr;
     const int64_t row = int64_t(blk) * 32 + r;
     u[rr] = __ldg(reinterpret_cast<const uint4*>(h + row * row_stride + col0 + c0 + lane * 8));
+    ul[rr] = lo_off > 0 ? __ldg(reinterpret_cast<const uint4*>(h + row * row_stride + lo_off + col0 + c0 + lane * 8))
+                        : make_uint4(0u, 0u, 0u, 0u);  // split-precision rows: the lo terms
     a[rr] = r < nv ? __ldg(attn + row) : 0.f;
   }
 #pragma unroll
   for (int rr = 0; rr < 4; ++rr) {
     const __half2* hp = reinterpret_cast<const __half2*>(&u[rr]);
+    const __half2* lp = reinterpret_cast<const __half2*>(&ul[rr]);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float2 f = __half22float2(hp[i]);
+      const float2 fl = __half22float2(lp[i]);
+      f.x += fl.x; f.y += fl.y;
       f.x *= in_scale; f.y *= in_scale;                 // rows are stored / 2^e (fp16 range rescue); exact
       s1[2 * i] = fmaf(a[rr], f.x, s1[2 * i]);         s2[2 * i] = fmaf(a[rr] * f.x, f.x, s2[2 * i]);
       s1[2 * i + 1] = fmaf(a[rr], f.y, s1[2 * i + 1]); s2[2 * i + 1] = fmaf(a[rr] * f.y, f.y, s2[2 * i + 1]);

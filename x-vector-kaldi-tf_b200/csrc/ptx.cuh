@@ -197,6 +197,9 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ float2 unpack_half2(uint32_t packed) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&packed));
+}
 
 
 

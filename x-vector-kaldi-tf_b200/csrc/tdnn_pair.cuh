@@ -104,6 +104,9 @@ struct PairArgs {
   float* out_f32;           // [k_splits][n_rows][C_out]  mode 2: raw accumulators
   uint32_t* overflow_flag;  // overflow_bit is OR-ed in if an fp16 output overflowed to inf
   uint32_t overflow_bit;    // 0 = 1u
+  int32_t split_c;          // > 0: split-precision operands.  The input rows hold [hi (split_c) | ... | lo at split_lo_off]: two fp16
+  int32_t split_lo_off;     //   terms per value (x = hi + lo to ~2^-22), the weights [w_hi | w_lo | w_hi] per tap, and the K loop walks
+                            //   the VIRTUAL columns [hi | hi | lo] (3 * split_c) = hi*w_hi + hi*w_lo + lo*w_hi in one accumulator
   float acc_scale;          // 0 = 1: the pre-activation is acc * acc_scale + bias (acc_scale = 2^e when the INPUT rows are stored
                             // divided by 2^e: the fp16 range rescue of xvec_api.cu; exact, powers of two)
   long long* trace;         // diagnostics (tools/trace_tiles.py): [cluster][rank][TRACE_TILES][8] SM clock stamps, or null
@@ -126,9 +129,9 @@ __device__ __forceinline__ float act_bn(float acc, float b, float sc, float sh, 
 }
 
 // s_par: shared-memory address of this tile's [bias(256) | scale(256) | shift(256) | alpha(256)] floats.
-template <bool LEAKY>
+template <bool LEAKY, bool SPLIT = false>
 __device__ __forceinline__ void epi_store_math(const uint32_t (&v)[32], uint32_t s_par, int c, bool valid,
-                                               uint32_t (&p)[16], uint32_t& hmax, float as) {
+                                               uint32_t (&p)[16], uint32_t& hmax, float as, uint32_t* plo = nullptr) {
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
     const float4 b4 = ptx::lds_f4(s_par + uint32_t(c + g * 4) * 4u);
@@ -144,6 +147,12 @@ __device__ __forceinline__ void epi_store_math(const uint32_t (&v)[32], uint32_t
     hmax = ptx::habs2_max(ptx::habs2_max(hmax, p0), p1);
     p[g * 2 + 0] = valid ? p0 : 0u;                  // gap rows stay exact zeros
     p[g * 2 + 1] = valid ? p1 : 0u;
+    if (SPLIT) {                                     // second term: what the fp16 rounding of y dropped
+      const float2 h0 = ptx::unpack_half2(p0), h1 = ptx::unpack_half2(p1);
+      const uint32_t l0 = ptx::pack_half2(y0 - h0.x, y1 - h0.y), l1 = ptx::pack_half2(y2 - h1.x, y3 - h1.y);
+      plo[g * 2 + 0] = valid ? l0 : 0u;
+      plo[g * 2 + 1] = valid ? l1 : 0u;
+    }
   }
 }
 
@@ -171,7 +180,9 @@ struct TileCursor {
 // STATS (mode 0 only, training): the epilogue also leaves the column sums of every [32 rows x 32 channels] box it stores --
 // of the fp16 values as stored -- in partial[row_block][{sum, sum of squares}][channel]: the batch-norm moments of the training
 // branch (tf_block.py:19) and the pooling sums of the last layer come out of the layer kernel instead of a second pass over HBM.
-template <int MODE, int ATOMS, bool LEAKY, bool STATS = false>
+// SPLIT (mode 0 only): the output is stored as two fp16 terms, hi = rn(y) at column c and lo = rn(y - hi) at column C_out + c
+// (the next layer's split-precision input); the caller's tmap_out then spans 2 * C_out columns.
+template <int MODE, int ATOMS, bool LEAKY, bool STATS = false, bool SPLIT = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations in  [R_pad, C_in_pad] fp16
                  const __grid_constant__ CUtensorMap tmap_wgt,   // weights [C_out, taps*C_in_pad] fp16 (K-major)
@@ -266,9 +277,12 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
               if (leader) ptx::mbar_arrive_expect_tx(act_full(sa), 2u * ATOMS * act_box_bytes);   // both CTAs' boxes
               const int row = reuse ? (r0 - halo) : (r0 + (j - half_ctx) * args.dilation);
 #pragma unroll
-              for (int h = 0; h < ATOMS; ++h)
-                ptx::tma_load_2d_2sm(sAct + sa * ACT_STAGE_BYTES + h * ACT_ATOM_STRIDE, &tmap_act, act_full_leader + 8u * sa,
-                                     (k_base + cc) * STAGE_K + h * BLOCK_K, row);
+              for (int h = 0; h < ATOMS; ++h) {
+                int col = (k_base + cc) * STAGE_K + h * BLOCK_K;
+                if (args.split_c > 0)                  // virtual [hi | hi | lo] -> stored [hi | .. | lo]
+                  col = col < args.split_c ? col : (col < 2 * args.split_c ? col - args.split_c : col - 2 * args.split_c + args.split_lo_off);
+                ptx::tma_load_2d_2sm(sAct + sa * ACT_STAGE_BYTES + h * ACT_ATOM_STRIDE, &tmap_act, act_full_leader + 8u * sa, col, row);
+              }
               // the same boxes of this cluster's NEXT item -> L2 now: with resident weights the ring holds too few
               // bytes to cover an HBM round trip (~2000 cycles), an L2 hit (~700) it does cover
               if (args.prefetch && tc.item + tc.step < n_items) {
@@ -531,8 +545,8 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(t_empty_leader + 8u * acc);
           }
-          uint32_t p[16];
-          epi_store_math<LEAKY>(v[chunk & 1], s_par, colh * 128 + chunk * C_CHUNK, valid, p, hmax, acc_scale);
+          uint32_t p[16], plo[SPLIT ? 16 : 1];
+          epi_store_math<LEAKY, SPLIT>(v[chunk & 1], s_par, colh * 128 + chunk * C_CHUNK, valid, p, hmax, acc_scale, plo);
           const uint32_t buf = sC;                        // one box per warp: the previous chunk's store has had the
           if (lane == 0) ptx::tma_store_wait_read<0>();   // whole tcgen05.ld + math of this chunk to read it
           __syncwarp();
@@ -548,6 +562,22 @@ tdnn_pair_kernel(const __grid_constant__ CUtensorMap tmap_act,   // activations 
           if (lane == 0) {
             ptx::tma_store_2d(&tmap_out, buf, ch0 + colh * 128 + chunk * C_CHUNK, r_cta + q * 32);
             ptx::tma_store_commit();
+          }
+          if (SPLIT) {                                    // the lo terms: same box, once the hi store has read it
+            if (lane == 0) ptx::tma_store_wait_read<0>();
+            __syncwarp();
+#pragma unroll
+            for (uint32_t c16 = 0; c16 < 4; ++c16) {
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((c16 ^ swz) << 4)),
+                           "r"(plo[c16 * 4 + 0]), "r"(plo[c16 * 4 + 1]), "r"(plo[c16 * 4 + 2]), "r"(plo[c16 * 4 + 3])
+                           : "memory");
+            }
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              ptx::tma_store_2d(&tmap_out, buf, args.c_out + ch0 + colh * 128 + chunk * C_CHUNK, r_cta + q * 32);
+              ptx::tma_store_commit();
+            }
           }
           if (STATS) {
             // lane = channel: read the staged box column-wise (row r is one 64-byte line whose 16-byte pieces are XOR-swizzled

@@ -90,6 +90,10 @@ struct xv_model {
   int opt_pdl = 1;                   // programmatic dependent launch between the kernels of a forward
   int opt_fc = 1;                    // 1: embed_layer-0 on tensor cores (split fp16), 0: fp32 SIMT GEMM
   int opt_blocking_collect = 0;      // 1: xv_collect sleeps on a blocking-sync event instead of spinning
+  int opt_split = 0;                 // option "precision" = 1: split-precision operands (two fp16 terms per activation and per
+                                     // weight, three products per contraction: ~2^-22 relative instead of 2^-11; 3x the MMA work).
+                                     // Default for attention pooling, whose softmax over time turns absolute score errors into
+                                     // relative weight errors: plain fp16 misses the 1e-3 gate there (tests/test_precision_model.py)
   int c_pool = 0;                    // channels that are pooled: width of the last frame layer (attention pooling: half of it)
   __half* att_w_dev = nullptr;       // attention pooling: [C, C] fp16 K-major (out channel major) copy of "attention/w:0"
   float* att_b_dev = nullptr;        // [C]
@@ -188,10 +192,11 @@ Plan make_plan(const xv_model* m, int64_t total_frames, int32_t n_seg) {
   p.off_counters = take(size_t(p.n_counters) * 4);
   p.off_valid = take(size_t(p.r_pad));
   p.off_blk_valid = take(size_t(p.r_pad / tdnn2::POOL_BLOCK));
-  p.off_x0 = take(size_t(p.r_pad) * m->k0_pad * 2);
-  p.off_ha = take(size_t(p.r_pad) * m->w_mid * 2);
-  p.off_hb = take(size_t(p.r_pad) * m->w_mid * 2);
-  p.off_hlast = take(size_t(p.r_pad) * c_last * 2);          // only written when a caller asks for the last layer's activations
+  const size_t terms = m->opt_split ? 2 : 1;                 // split precision: every stored row is [hi | lo]
+  p.off_x0 = take(size_t(p.r_pad) * m->k0_pad * 2 * terms);
+  p.off_ha = take(size_t(p.r_pad) * m->w_mid * 2 * terms);
+  p.off_hb = take(size_t(p.r_pad) * m->w_mid * 2 * terms);
+  p.off_hlast = take(size_t(p.r_pad) * c_last * 2 * terms);  // only written when a caller asks for the last layer's activations
   p.off_pool_partial = take(size_t(p.r_pad / tdnn2::POOL_BLOCK) * 2 * c_last * 4);
   p.off_stats = take(size_t(n_seg) * K * 4);
   if (m->topo.pooling == XV_POOL_ATTENTION) {
@@ -301,12 +306,24 @@ int finalize_params(xv_model* m) {
       return fail(XV_ESTATE, "missing or mis-shaped parameter(s) under scope '" + s + "' (need w,b,gamma,beta,mean,variance)");
     // weights: TF [k, Cin, Cout] -> [Cout, K] fp16 (round to nearest), K index = tap * c_in_pad + c
     // (first layer: c_in_pad == c_in, i.e. densely spliced, zero padded up to k_total)
-    std::vector<__half> wt(size_t(L.c_out) * L.k_total, __float2half_rn(0.f));
+    // split precision: per tap (first layer: per spliced row) the K run is [w_hi | w_lo | w_hi], against the activations'
+    // virtual [x_hi | x_hi | x_lo]
+    const int split = m->opt_split ? 1 : 0;
+    const int run = (i == 0) ? L.k_total : L.c_in_pad;             // K columns of one tap's run (one term)
+    const int kw = (split ? 3 : 1) * L.k_total;                    // packed row length
+    std::vector<__half> wt(size_t(L.c_out) * kw, __float2half_rn(0.f));
     for (int j = 0; j < L.taps; ++j)
       for (int c = 0; c < L.c_in; ++c) {
         const float* src = w->data() + (size_t(j) * L.c_in + c) * L.c_out;
-        const size_t kidx = size_t(j) * L.c_in_pad + c;
-        for (int o = 0; o < L.c_out; ++o) wt[size_t(o) * L.k_total + kidx] = __float2half_rn(src[o]);
+        const size_t kidx = size_t(j) * L.c_in_pad + c;            // index within the unsplit layout
+        const size_t tap = kidx / run, within = kidx % run;
+        for (int o = 0; o < L.c_out; ++o) {
+          const __half hi = __float2half_rn(src[o]);
+          if (!split) { wt[size_t(o) * kw + kidx] = hi; continue; }
+          const __half lo = __float2half_rn(src[o] - __half2float(hi));
+          __half* row = wt.data() + size_t(o) * kw + tap * 3 * run;
+          row[within] = hi; row[run + within] = lo; row[2 * run + within] = hi;
+        }
       }
     std::vector<float> scale(L.c_out), shift(L.c_out);
     for (int o = 0; o < L.c_out; ++o) {
@@ -341,9 +358,16 @@ int finalize_params(xv_model* m) {
     const auto* ab = find_param(m, "attention/b:0", {C});
     const auto* av = find_param(m, "attention/v:0", {C});
     if (!aw || !ab || !av) return fail(XV_ESTATE, "missing or mis-shaped attention/w:0, attention/b:0 or attention/v:0");
-    std::vector<__half> wt(size_t(C) * C);                       // einsum('ijk,kl->ijl'): [k, l] -> [l][k], K-major
+    const int kw = m->opt_split ? 3 * C : C;
+    std::vector<__half> wt(size_t(C) * kw);                      // einsum('ijk,kl->ijl'): [k, l] -> [l][k], K-major
     for (int k = 0; k < C; ++k)
-      for (int l = 0; l < C; ++l) wt[size_t(l) * C + k] = __float2half_rn((*aw)[size_t(k) * C + l]);
+      for (int l = 0; l < C; ++l) {
+        const float x = (*aw)[size_t(k) * C + l];
+        const __half hi = __float2half_rn(x);
+        __half* row = wt.data() + size_t(l) * kw;
+        row[k] = hi;
+        if (m->opt_split) { row[C + k] = __float2half_rn(x - __half2float(hi)); row[2 * C + k] = hi; }
+      }
     XV_CUDA(cudaMalloc(&m->att_w_dev, wt.size() * sizeof(__half)));
     XV_CUDA(cudaMalloc(&m->att_b_dev, C * 4));
     XV_CUDA(cudaMalloc(&m->att_v_dev, C * 4));
@@ -604,6 +628,7 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
     a.lut = m->pack_lut_dev;
     a.counters = counters;
     a.n_counters = p.n_counters;
+    a.split = m->opt_split ? 1 : 0;
     const int blocks = int(r_pad / xvk::PACK_ROWS_PER_BLOCK);      // >= n_seg: covers n_counters with 256 threads each
     XV_PROF();
     XV_CUDA(launch_k(pdl, xvk::pack_im2col_kernel, dim3(blocks), dim3(xvk::PACK_THREADS), 0, stream, a));
@@ -622,17 +647,20 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
     const bool last = i == nl - 1;
     __half* out = last ? hlast : ((i & 1) ? hb : ha);
     const int halo = (L.gemm_taps - 1) / 2 * L.dilation;
-    const int c_in_gemm = (i == 0) ? L.k_total : L.c_in_pad;       // row width of the input matrix
+    const int c_in_real = (i == 0) ? L.k_total : L.c_in_pad;       // values per input row
+    const int split = m->opt_split ? 1 : 0;
+    // split precision: rows hold [hi | lo] (2 x c_in_real halfs), the K loop walks the virtual [hi | hi | lo]
+    const int c_in_gemm = split ? 3 * c_in_real : c_in_real;
     {
       const bool reuse = L.gemm_taps > 1 && halo <= tdnn2::MAX_REUSE_HALO;
       CUtensorMap ta, tw, tc;
-      rc = encode_2d(m, &ta, const_cast<__half*>(in), uint64_t(c_in_gemm), uint64_t(r_pad), tdnn2::BLOCK_K,
+      rc = encode_2d(m, &ta, const_cast<__half*>(in), uint64_t((split ? 2 : 1) * c_in_real), uint64_t(r_pad), tdnn2::BLOCK_K,
                      reuse ? tdnn2::ACT_BOX_ROWS_REUSE : tdnn2::ACT_BOX_ROWS_PLAIN, CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc != XV_OK) return rc;
-      rc = encode_2d(m, &tw, L.w_dev, uint64_t(L.k_total), uint64_t(L.c_out), tdnn2::BLOCK_K, tdnn2::CTA_CH,
+      rc = encode_2d(m, &tw, L.w_dev, uint64_t((split ? 3 : 1) * L.k_total), uint64_t(L.c_out), tdnn2::BLOCK_K, tdnn2::CTA_CH,
                      CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc != XV_OK) return rc;
-      rc = encode_2d(m, &tc, out, uint64_t(L.c_out), uint64_t(r_pad), tdnn2::C_CHUNK, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+      rc = encode_2d(m, &tc, out, uint64_t((split ? 2 : 1) * L.c_out), uint64_t(r_pad), tdnn2::C_CHUNK, 32, CU_TENSOR_MAP_SWIZZLE_64B);
       if (rc != XV_OK) return rc;
       // Weights of one channel tile fit in shared memory next to an activation ring when K_total <= 512
       // (every k=1 layer and the spliced first layer): keep them resident, stream activations in 64-wide
@@ -640,7 +668,7 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       const int64_t ring_cap = tdnn2::RING_BYTES;
       const int n_ch_tiles = L.c_out / tdnn2::TILE_CH;
       const int k_atoms = L.gemm_taps * (c_in_gemm / tdnn2::BLOCK_K);
-      bool resident = m->opt_resident && L.gemm_taps == 1 && k_atoms % 2 == 0 && k_atoms <= tdnn2::MAX_STAGES &&
+      bool resident = m->opt_resident && !split && L.gemm_taps == 1 && k_atoms % 2 == 0 && k_atoms <= tdnn2::MAX_STAGES &&
                       m->num_clusters >= n_ch_tiles;
       tdnn2::PairArgs a{};
       a.n_row_tiles = int32_t(r_pad / tdnn2::TILE_ROWS);
@@ -660,6 +688,8 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       a.overflow_flag = m->cur_flag;
       a.overflow_bit = 1u << (8 + i);
       a.acc_scale = i > 0 ? std::ldexp(1.0f, m->layers[i - 1].exp_out) : 1.0f;      // the input rows are stored / 2^exp
+      a.split_c = split ? c_in_real : 0;
+      a.split_lo_off = c_in_real;
       a.trace = (i == m->opt_trace_layer) ? m->opt_trace : nullptr;
       a.wgt_resident = resident ? 1 : 0;
       a.prefetch = m->opt_prefetch;
@@ -691,6 +721,7 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
           const bool leaky = L.alpha_dev != nullptr;
 #define XV_PICK(MO, AT) (leaky ? tdnn2::tdnn_pair_kernel<MO, AT, true> : tdnn2::tdnn_pair_kernel<MO, AT, false>)
           if (mode == 1) kern = atoms == 1 ? XV_PICK(1, 1) : XV_PICK(1, 2);
+          else if (split) kern = leaky ? tdnn2::tdnn_pair_kernel<0, 2, true, false, true> : tdnn2::tdnn_pair_kernel<0, 2, false, false, true>;
           else kern = atoms == 1 ? XV_PICK(0, 1) : XV_PICK(0, 2);
 #undef XV_PICK
           XV_CUDA(launch_k(pdl, kern, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
@@ -702,7 +733,7 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
     }
     if (layer_out_dev && layer_out_dev[i]) {
       XV_CUDA(launch_k(pdl, xvk::unpack_rows_kernel, dim3(n_seg), dim3(256), 0, stream, static_cast<const __half*>(out), seg, int32_t(L.c_out), layer_out_dev[i],
-                       std::ldexp(1.0f, L.exp_out)));
+                       std::ldexp(1.0f, L.exp_out), int32_t(split)));
       XV_CUDA(cudaGetLastError());
       ++launches;
     }
@@ -717,14 +748,19 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       float* score = reinterpret_cast<float*>(ws + p.off_score);
       float* attn = reinterpret_cast<float*>(ws + p.off_attn);
       CUtensorMap ta, tw;
-      rc = encode_2d(m, &ta, hlast, uint64_t(C), uint64_t(r_pad), tdnn2::BLOCK_K, tdnn2::ACT_BOX_ROWS_PLAIN, CU_TENSOR_MAP_SWIZZLE_128B, uint64_t(W));
+      const int split = m->opt_split ? 1 : 0;
+      // h1 = the first C channels of the stored last layer; split precision: their lo terms sit W columns further on
+      rc = encode_2d(m, &ta, hlast, uint64_t(split ? W + C : C), uint64_t(r_pad), tdnn2::BLOCK_K, tdnn2::ACT_BOX_ROWS_PLAIN,
+                     CU_TENSOR_MAP_SWIZZLE_128B, uint64_t((split ? 2 : 1) * W));
       if (rc != XV_OK) return rc;
-      rc = encode_2d(m, &tw, m->att_w_dev, uint64_t(C), uint64_t(C), tdnn2::BLOCK_K, tdnn2::CTA_CH, CU_TENSOR_MAP_SWIZZLE_128B);
+      rc = encode_2d(m, &tw, m->att_w_dev, uint64_t((split ? 3 : 1) * C), uint64_t(C), tdnn2::BLOCK_K, tdnn2::CTA_CH, CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc != XV_OK) return rc;
       tdnn2::PairArgs a{};
       a.n_row_tiles = int32_t(r_pad / tdnn2::TILE_ROWS);
       a.n_ch_tiles = C / tdnn2::TILE_CH;
-      a.taps = 1; a.dilation = 1; a.c_in_pad = C; a.reuse = 0;
+      a.taps = 1; a.dilation = 1; a.c_in_pad = (split ? 3 : 1) * C; a.reuse = 0;
+      a.split_c = split ? C : 0;
+      a.split_lo_off = W;
       a.c_out = C;
       a.bias = m->att_b_dev; a.scale = m->att_v_dev;
       a.partial = score;
@@ -732,7 +768,7 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       a.acc_scale = std::ldexp(1.0f, m->layers[nl - 1].exp_out);
       a.mode = 3;
       a.n_act_stages = a.n_wgt_stages = int(std::min<int64_t>(tdnn2::MAX_STAGES, tdnn2::RING_BYTES / (2 * (tdnn2::ACT_BOX_ROWS_PLAIN * 128 + tdnn2::WGT_ATOM_BYTES))));
-      a.c_chunks = C / (2 * tdnn2::BLOCK_K);
+      a.c_chunks = (split ? 3 : 1) * C / (2 * tdnn2::BLOCK_K);
       const int64_t tiles = int64_t(a.n_row_tiles) * a.n_ch_tiles;
       const int grid = 2 * int(std::min<int64_t>(tiles, m->num_clusters));
       XV_PROF();
@@ -748,8 +784,8 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       ++launches;
       XV_PROF();
       XV_CUDA(launch_k(pdl, xvk::attn_pool_kernel, dim3(unsigned(r_pad / 32) * (C / 256)), dim3(256), 0, stream, static_cast<const __half*>(hlast),
-                       int32_t(W), int32_t(C), int32_t(C), static_cast<const float*>(attn), static_cast<const uint8_t*>(blk_valid), pool_partial,
-                       std::ldexp(1.0f, m->layers[nl - 1].exp_out)));
+                       int32_t((split ? 2 : 1) * W), int32_t(C), int32_t(C), static_cast<const float*>(attn), static_cast<const uint8_t*>(blk_valid), pool_partial,
+                       std::ldexp(1.0f, m->layers[nl - 1].exp_out), int32_t(split ? W : 0)));
       XV_PROF();
       XV_CUDA(cudaGetLastError());
       ++launches;
@@ -939,6 +975,7 @@ int xv_create(xv_model** out, int device, const xv_topology* topo) {
   }
   m->gap = std::max(m->gap, 1);
   m->c_pool = t.pooling == XV_POOL_ATTENTION ? prev / 2 : prev;
+  m->opt_split = t.pooling == XV_POOL_ATTENTION ? 1 : 0;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -953,7 +990,8 @@ int xv_create(xv_model** out, int device, const xv_topology* topo) {
         tdnn2::tdnn_pair_kernel<0, 1, false>, tdnn2::tdnn_pair_kernel<0, 2, false>, tdnn2::tdnn_pair_kernel<1, 1, false>,
         tdnn2::tdnn_pair_kernel<1, 2, false>, tdnn2::tdnn_pair_kernel<0, 1, true>,  tdnn2::tdnn_pair_kernel<0, 2, true>,
         tdnn2::tdnn_pair_kernel<1, 1, true>,  tdnn2::tdnn_pair_kernel<1, 2, true>,  tdnn2::tdnn_pair_kernel<2, 2, false>,
-        tdnn2::tdnn_pair_kernel<3, 2, false>};
+        tdnn2::tdnn_pair_kernel<3, 2, false>, tdnn2::tdnn_pair_kernel<0, 2, false, false, true>,
+        tdnn2::tdnn_pair_kernel<0, 2, true, false, true>};
     for (auto k : kernels)
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
   }
@@ -1355,6 +1393,7 @@ int xv_set_option(xv_model* m, const char* name, int64_t value) {
   else if (n == "pdl") m->opt_pdl = value != 0;
   else if (n == "blocking_collect") m->opt_blocking_collect = value != 0;
   else if (n == "rescue") m->opt_rescue = value != 0;
+  else if (n == "precision") { m->opt_split = value != 0; m->dirty = true; }
   else if (n == "fc_max_splits") m->opt_fc_max_splits = std::max(1, int(value));
   else if (n == "trace_ptr") m->opt_trace = reinterpret_cast<long long*>(static_cast<intptr_t>(value));   // device buffer
   else if (n == "trace_layer") m->opt_trace_layer = int(value);
