@@ -416,12 +416,9 @@ def run_b200(args):
                   ("attn_softmax_kernel", "hbm", frames * (2 * (c_last // 256) + 2) * 4),
                   ("attn_pool_kernel", "hbm", frames * c_last * 2 + n_blk * 2 * c_last * 4)]
     table += [("pool_stats_kernel", "hbm", n_blk * 2 * c_last * 4 + B * 2 * c_last * 6)]
-    if len(kms) == len(table) + 3:      # embed_layer-0 on tensor cores: split-fp16 GEMM (3 products) + K-split reduction
-        table += [("tdnn_pair_kernel<2>[embed_layer-0]", "tensor", 2 * B * 2 * c_last * EMB_DIM),
-                  ("embed_reduce_kernel", "hbm", B * EMB_DIM * 4 * 2)]
-    else:
-        table += [("embed_fc_kernel", "hbm", B * 2 * c_last * 4 + 2 * c_last * EMB_DIM * 4 + B * EMB_DIM * 4)]
-    table += [("utt_average_kernel", "hbm", B * EMB_DIM * 4 * 2 + B * 16)]      # make_embedding's chunk average -> result rows
+    # embed_layer-0 on tensor cores: split-fp16 GEMM (3 products), then K-split reduction + make_embedding's chunk average
+    table += [("tdnn_pair_kernel<2>[embed_layer-0]", "tensor", 2 * B * 2 * c_last * EMB_DIM),
+              ("embed_reduce_utt_kernel", "hbm", B * EMB_DIM * 4 * 2 + B * 16)]
     launches = []
     for (name, bound, work), ms in zip(table, kms):
         d = dict(kernel=name, ms=round(float(ms), 5), bound=bound)

@@ -263,6 +263,61 @@ __global__ void __launch_bounds__(128) utt_average_kernel(const UttAvgArgs a) {
   if (a.out_local != nullptr) reinterpret_cast<float4*>(a.out_local + int64_t(u) * a.E)[o4] = r;
 }
 
+// embed_reduce_kernel + utt_average_kernel in one launch (the usual case: all segments of the call in one GEMM group):
+// thread = one float4 of one UTTERANCE; per chunk the K-split sum in embed_reduce_kernel's order, then the reference's
+// float32 chunk average.  Bit-identical to the two kernels run one after the other.
+struct FcReduceUttArgs {
+  FcReduceArgs r;             // r.emb is not used
+  UttAvgArgs u;               // u.seg_emb is not used
+};
+
+__global__ void __launch_bounds__(128) embed_reduce_utt_kernel(const FcReduceUttArgs a) {
+  cudaTriggerProgrammaticLaunchCompletion();
+  cudaGridDependencySynchronize();
+  const int64_t i4 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int e4 = a.r.E / 4;
+  if (i4 >= int64_t(a.u.n_utt) * e4) return;
+  const int u = int(i4 / e4), o4 = int(i4 % e4);
+  const int s0 = __ldg(a.u.first_seg + u), s1 = __ldg(a.u.first_seg + u + 1);
+  const int64_t n4 = int64_t(a.r.n_seg) * e4;
+  const float4 bias = __ldg(reinterpret_cast<const float4*>(a.r.b0) + o4);
+  const bool scaled = a.r.out_scale != 0.f && a.r.out_scale != 1.f;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  double tot = 0.0;
+  for (int sg = s0; sg < s1; ++sg) {
+    float4 sum = scaled ? make_float4(0.f, 0.f, 0.f, 0.f) : bias;
+    const float4* p = reinterpret_cast<const float4*>(a.r.partial) + int64_t(sg) * e4 + o4;
+    int s = 0;
+    for (; s + 12 <= a.r.splits; s += 12) {
+      float4 v[12];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) v[k] = __ldcg(p + int64_t(s + k) * n4);
+#pragma unroll
+      for (int k = 0; k < 12; ++k) { sum.x += v[k].x; sum.y += v[k].y; sum.z += v[k].z; sum.w += v[k].w; }
+    }
+    for (; s < a.r.splits; ++s) {
+      const float4 v = __ldcg(p + int64_t(s) * n4);
+      sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+    }
+    if (scaled) {
+      sum.x = fmaf(sum.x, a.r.out_scale, bias.x); sum.y = fmaf(sum.y, a.r.out_scale, bias.y);
+      sum.z = fmaf(sum.z, a.r.out_scale, bias.z); sum.w = fmaf(sum.w, a.r.out_scale, bias.w);
+    }
+    const int len = __ldg(a.u.seg_len + sg);
+    const float w = float(len);
+    acc.x = __fadd_rn(acc.x, __fmul_rn(w, sum.x)); acc.y = __fadd_rn(acc.y, __fmul_rn(w, sum.y));
+    acc.z = __fadd_rn(acc.z, __fmul_rn(w, sum.z)); acc.w = __fadd_rn(acc.w, __fmul_rn(w, sum.w));
+    tot += double(len);
+  }
+  const float wt = float(tot);
+  const float4 res = make_float4(__fdiv_rn(acc.x, wt), __fdiv_rn(acc.y, wt), __fdiv_rn(acc.z, wt), __fdiv_rn(acc.w, wt));
+  if (a.u.out != nullptr) {
+    const int64_t row = a.u.dst_row != nullptr ? a.u.dst_row[u] : int64_t(u);
+    reinterpret_cast<float4*>(a.u.out + row * a.r.E)[o4] = res;
+  }
+  if (a.u.out_local != nullptr) reinterpret_cast<float4*>(a.u.out_local + int64_t(u) * a.r.E)[o4] = res;
+}
+
 // ------------------------------------------------------------------------------------------
 // embed_layer-0 (tf.nn.xw_plus_b, models.py:495): emb[n_seg, E] = stats[n_seg, K] @ W0[K, E] + b0,
 // the x-vector.  fp32 SIMT GEMM (the 1e-3 parity budget leaves no room for 16-bit statistics):

@@ -741,6 +741,7 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
   }
 
   // ---- statistics pooling + embed_layer-0 -----------------------------------------------
+  bool utt_done = false;
   {
     if (attention) {
       // ---- self-attention pooling (models.py:1037-1051): score GEMM on the tensor cores, softmax over time, weighted sums
@@ -856,6 +857,26 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
         r.E = E;
         r.splits = p.tc_splits;
         r.out_scale = std::ldexp(1.0f, m->exp_stats);
+        if (utt && n_seg <= FC_GROUP) {
+          // one group holds every segment: K-split reduction and make_embedding's chunk average in ONE launch
+          xvk::FcReduceUttArgs ru{};
+          ru.r = r;
+          ru.u.first_seg = utt_first_dev;
+          ru.u.seg_len = seg.len;
+          ru.u.dst_row = utt_dst_dev;
+          ru.u.out = utt->out_dev;
+          ru.u.out_local = utt->out_local_dev;
+          ru.u.n_utt = n_utt;
+          ru.u.E = E;
+          const int64_t u4 = int64_t(n_utt) * E / 4;
+          XV_PROF();
+          XV_CUDA(launch_k(pdl, xvk::embed_reduce_utt_kernel, dim3(unsigned((u4 + 127) / 128)), dim3(128), 0, stream, ru));
+          XV_PROF();
+          XV_CUDA(cudaGetLastError());
+          ++launches;
+          utt_done = true;
+          break;
+        }
         const int64_t n4 = int64_t(gn) * E / 4;
         XV_PROF();
         XV_CUDA(launch_k(pdl, xvk::embed_reduce_kernel, dim3(unsigned((n4 + 63) / 64)), dim3(64), 0, stream, r));
@@ -883,7 +904,7 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       ++launches;
     }
   }
-  if (utt) {
+  if (utt && !utt_done) {
     xvk::UttAvgArgs a{};
     a.seg_emb = emb_dev;
     a.first_seg = utt_first_dev;
