@@ -224,7 +224,7 @@ def test_extract_host_equals_device_forward():
     dev = _run(eng, feats, lens)
     host = eng.extract_host(feats, lens)
     assert np.array_equal(dev, host)
-    assert eng.last_launch_count == 9          # pack + 5 layers + pool stats + embed GEMM + K-split reduction
+    assert eng.last_launch_count == 8          # pack + 3 layers + fused last two layers + pool stats + embed GEMM + K-split reduction
     eng.close()
 
 
@@ -364,6 +364,28 @@ def test_native_ark_file_job_is_byte_identical_to_the_stream_path(tmp_path, monk
     by_ark = list(kaldi_io.read_vec_flt_ark(a))
     assert len(by_scp) == len(by_ark) == int(((lens >= 25)).sum())
     assert all(k1 == k2 and np.array_equal(v1, v2) for (k1, v1), (k2, v2) in zip(by_scp, by_ark))
+
+
+@pytest.mark.parametrize("topology,weight_set", [("ModelWithoutDropoutTdnn", "B"), ("ModelWithoutDropout", "A"),
+                                                 ("ModelL2LossWithoutDropoutLRelu", "B"), ("ModelWithoutDropoutPRelu", "B")])
+def test_fused_tail_is_bit_identical_to_one_launch_per_layer(topology, weight_set):
+    # tdnn_tail.cuh keeps the 512-wide output of the fourth layer in shared memory as the fifth layer's operand; same
+    # arithmetic in the same order as the two tdnn_pair_kernel launches, so not one bit may differ
+    eng, params = _engine(topology, weight_set)
+    lens = np.concatenate([synthetic.lengths_uniform(91, 60, 25, 700), [25, 1, 10000 - 7]]).astype(np.int32)
+    feats = synthetic.mfcc_batch(91, lens)
+    fused = _run(eng, feats, lens)
+    n_fused = eng.last_launch_count
+    eng.set_option("fuse_tail", 0)
+    plain = _run(eng, feats, lens)
+    assert eng.last_launch_count == n_fused + 1
+    assert np.array_equal(fused, plain)
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    pick = [0, 7, 59, 60, 62]
+    want = np.stack([orc.forward(feats[offs[i]:offs[i + 1]], params, topology) for i in pick])
+    m = orc.parity_metrics(fused[pick], want)
+    assert m["max_rel"] <= TOL and m["l2_rel"] <= TOL, m
+    eng.close()
 
 
 @pytest.mark.parametrize("topology", ["ModelWithoutDropoutTdnn", "ModelWithoutDropout"])

@@ -17,6 +17,7 @@
 
 #include "pack_pool.cuh"
 #include "tdnn_pair.cuh"
+#include "tdnn_tail.cuh"
 
 namespace {
 
@@ -90,6 +91,8 @@ struct xv_model {
   int opt_pdl = 1;                   // programmatic dependent launch between the kernels of a forward
   int opt_fc = 1;                    // 1: embed_layer-0 on tensor cores (split fp16), 0: fp32 SIMT GEMM
   int opt_blocking_collect = 0;      // 1: xv_collect sleeps on a blocking-sync event instead of spinning
+  int opt_fuse_tail = 1;             // 1: the last two (context-free) frame layers of a statistics-pooling model run as ONE kernel
+                                     // that keeps the 512-wide intermediate in shared memory (tdnn_tail.cuh); 0: one launch per layer
   int opt_split = 0;                 // option "precision" = 1: split-precision operands (two fp16 terms per activation and per
                                      // weight, three products per contraction: ~2^-22 relative instead of 2^-11; 3x the MMA work).
                                      // Default for attention pooling, whose softmax over time turns absolute score errors into
@@ -642,7 +645,49 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
   const bool attention = m->topo.pooling == XV_POOL_ATTENTION;
   const bool want_last = attention || (layer_out_dev && layer_out_dev[nl - 1]);   // attention pooling reads the stored activation
   const __half* in = x0;
+  // the last two frame layers as one kernel when both are context-free, the intermediate is 512 wide and nobody asks for
+  // their stored activations (statistics pooling, plain fp16 operands)
+  const bool fuse_tail = m->opt_fuse_tail && !attention && !m->opt_split && !layer_out_dev && nl >= 3 && !m->opt_resident &&
+                         m->layers[nl - 2].gemm_taps == 1 && m->layers[nl - 1].gemm_taps == 1 &&
+                         m->layers[nl - 2].c_out == tdnn2::FT_MID_CH && m->layers[nl - 2].c_in_pad % tdnn2::BLOCK_K == 0 &&
+                         m->opt_trace_layer < 0;
   for (int i = 0; i < nl; ++i) {
+    if (fuse_tail && i == nl - 2) {
+      const FrameLayer& L3 = m->layers[nl - 2];
+      const FrameLayer& L4 = m->layers[nl - 1];
+      CUtensorMap tx, tw3, tw4;
+      rc = encode_2d(m, &tx, const_cast<__half*>(in), uint64_t(L3.c_in_pad), uint64_t(r_pad), tdnn2::BLOCK_K, tdnn2::ACT_BOX_ROWS_PLAIN,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc != XV_OK) return rc;
+      rc = encode_2d(m, &tw3, L3.w_dev, uint64_t(L3.k_total), uint64_t(L3.c_out), tdnn2::BLOCK_K, tdnn2::CTA_CH, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc != XV_OK) return rc;
+      rc = encode_2d(m, &tw4, L4.w_dev, uint64_t(L4.k_total), uint64_t(L4.c_out), tdnn2::BLOCK_K, tdnn2::CTA_CH, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc != XV_OK) return rc;
+      tdnn2::FusedTailArgs a{};
+      a.n_row_tiles = int32_t(r_pad / tdnn2::TILE_ROWS);
+      a.k_atoms_in = L3.c_in_pad / tdnn2::BLOCK_K;
+      a.n_ch_tiles = L4.c_out / tdnn2::TILE_CH;
+      a.c_out = L4.c_out;
+      a.bias3 = L3.bias_dev; a.scale3 = L3.scale_dev; a.shift3 = L3.shift_dev; a.alpha3 = L3.alpha_dev;
+      a.acc_scale3 = std::ldexp(1.0f, m->layers[nl - 3].exp_out);
+      a.bias4 = L4.bias_dev; a.scale4 = L4.scale_dev; a.shift4 = L4.shift_dev; a.alpha4 = L4.alpha_dev;
+      a.acc_scale4 = std::ldexp(1.0f, L3.exp_out);
+      a.row_valid = row_valid;
+      a.blk_valid = blk_valid;
+      a.partial = pool_partial;
+      a.overflow_flag = m->cur_flag;
+      a.overflow_bit3 = 1u << (8 + nl - 2);
+      const int grid = 2 * int(std::min<int64_t>(a.n_row_tiles, m->num_clusters));
+      XV_PROF();
+      if (L3.alpha_dev != nullptr)
+        XV_CUDA(launch_k(pdl, tdnn2::tdnn_tail_fused_kernel<true>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::FT_SMEM_BYTES, stream, tx, tw3, tw4, a));
+      else
+        XV_CUDA(launch_k(pdl, tdnn2::tdnn_tail_fused_kernel<false>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::FT_SMEM_BYTES, stream, tx, tw3, tw4, a));
+      XV_PROF();
+      XV_CUDA(cudaGetLastError());
+      ++launches;
+      break;
+    }
     const FrameLayer& L = m->layers[i];
     const bool last = i == nl - 1;
     __half* out = last ? hlast : ((i & 1) ? hb : ha);
@@ -1015,6 +1060,8 @@ int xv_create(xv_model** out, int device, const xv_topology* topo) {
         tdnn2::tdnn_pair_kernel<0, 2, true, false, true>};
     for (auto k : kernels)
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tdnn2::tdnn_tail_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::FT_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tdnn2::tdnn_tail_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::FT_SMEM_BYTES);
   }
   if (e == cudaSuccess) {
     cudaLaunchConfig_t cfg{};
@@ -1414,6 +1461,7 @@ int xv_set_option(xv_model* m, const char* name, int64_t value) {
   else if (n == "pdl") m->opt_pdl = value != 0;
   else if (n == "blocking_collect") m->opt_blocking_collect = value != 0;
   else if (n == "rescue") m->opt_rescue = value != 0;
+  else if (n == "fuse_tail") m->opt_fuse_tail = value != 0;
   else if (n == "precision") { m->opt_split = value != 0; m->dirty = true; }
   else if (n == "fc_max_splits") m->opt_fc_max_splits = std::max(1, int(value));
   else if (n == "trace_ptr") m->opt_trace = reinterpret_cast<long long*>(static_cast<intptr_t>(value));   // device buffer
