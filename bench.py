@@ -95,7 +95,8 @@ def ncu_traffic_bytes(topology):
         return None, None
     with open(path) as f:
         rows = [r for r in json.load(f) if r.get("report", "").endswith("prof_%s.ncu-rep" % topology) and
-                ("tdnn_pair_kernel<0" in r.get("kernel", "") or "tdnn_pair_kernel<1" in r.get("kernel", ""))]
+                ("tdnn_pair_kernel<0" in r.get("kernel", "") or "tdnn_pair_kernel<1" in r.get("kernel", "") or
+                 "tdnn_tail_fused_kernel" in r.get("kernel", ""))]
     vals = [(r["dram_read_MB"] + r["dram_write_MB"]) * 1e6 for r in rows if r.get("dram_read_MB") is not None]
     return (round(sum(vals) / len(vals)) if vals else None), NCU_TRAFFIC_FILE
 
@@ -409,7 +410,13 @@ def run_b200(args):
     # layer 0 (K = 128) is bound by its own output stream (K0 = 117 760 FLOP / (92 + 1 024) B = 105 FLOP/B, HBM-bound):
     # judged against HBM with SURVEY's algorithmic bytes per frame (fp32 features in, fp16 activations out); layers 1.. tensor bound
     table += [("tdnn_pair_kernel[L0]", "hbm", frames * (FEAT_DIM * 4 + topo["layer_sizes"][0] * 2))]
-    table += [("tdnn_pair_kernel[L%d]" % i, "tensor", frames * f) for i, f in enumerate(fl) if i > 0]
+    n_tail = 2 + (3 if topo.get("pooling") == "attention" else 0)       # launches behind the frame layers (+ attention's three)
+    fused_tail = len(kms) == 1 + (len(fl) - 1) + 1 + n_tail               # pack, layers 0..n-3, fused last two, pool_stats, embed, reduce
+    if fused_tail:
+        table += [("tdnn_pair_kernel[L%d]" % i, "tensor", frames * f) for i, f in enumerate(fl) if 0 < i < len(fl) - 2]
+        table += [("tdnn_tail_fused_kernel[L%d+L%d]" % (len(fl) - 2, len(fl) - 1), "tensor", frames * (fl[-2] + fl[-1]))]
+    else:
+        table += [("tdnn_pair_kernel[L%d]" % i, "tensor", frames * f) for i, f in enumerate(fl) if i > 0]
     if topo.get("pooling") == "attention":       # models.py:1037-1051: score GEMM [frames, C] x [C, C], softmax over time, weighted sums
         c_last //= 2
         table += [("tdnn_pair_kernel<3>[attention scores]", "tensor", frames * 2 * c_last * c_last),
@@ -429,15 +436,17 @@ def run_b200(args):
             gbs = work / (ms * 1e-3) / 1e9
             d.update(achieved=round(gbs, 1), unit="GB/s", frac=round(gbs / peaks["hbm_gbs"], 4))
         launches.append(d)
-    tdnn_ms = float(kms[1:1 + len(fl)].sum())
+    n_layer_launches = len(fl) - 1 if fused_tail else len(fl)
+    tdnn_ms = float(kms[1:1 + n_layer_launches].sum())
     tdnn_tf = frames * sum(fl) / (tdnn_ms * 1e-3) / 1e12
     traffic, traffic_src = ncu_traffic_bytes(args.topology)
-    roofline = dict(kernel="tdnn_pair_kernel (%d launches/step, figures are per-step sums / averages)" % len(fl),
+    roofline = dict(kernel="tdnn_pair_kernel x%d%s (%d launches/step, figures are per-step sums / averages)"
+                           % (n_layer_launches - (1 if fused_tail else 0), " + tdnn_tail_fused_kernel" if fused_tail else "", n_layer_launches),
                     bound="tensor", achieved=round(tdnn_tf, 1), peak=peaks["tflops"], unit="TFLOP/s",
                     frac=round(tdnn_tf / peaks["tflops"], 4), traffic=traffic,
                     traffic_source=("profiles/%s: mean DRAM bytes per launch over the %d frame-layer launches of one captured step of %s "
                                     "at configs[1]" % (traffic_src, len(fl), args.topology)) if traffic is not None else None,
-                    flop_per_launch_avg=round(frames * sum(fl) / len(fl)),
+                    flop_per_launch_avg=round(frames * sum(fl) / n_layer_launches),
                     peak_source="%s bf16/fp16 burst (MEASURED_PEAKS.json)" % peaks["source"],
                     share_of_step=round(tdnn_ms / float(kms.sum()), 4),
                     step_frac_of_tensor_peak=round(value / world * sum(fl) / 1e12 / peaks["tflops"], 4),
@@ -494,14 +503,15 @@ def run_b200(args):
             dk.append(deng.last_kernel_ms())
         deng.set_option("profile", 0)
         dk = np.asarray(dk, dtype=np.float64).mean(axis=0)
-        d_layers = float(dk[1:1 + len(dfl)].sum())
+        d_n = len(dfl) - 1 if len(dk) == len(dfl) + 3 else len(dfl)      # last two layers fused: one launch fewer
+        d_layers = float(dk[1:1 + d_n].sum())
         d_tf = frames * sum(dfl) / (d_layers * 1e-3) / 1e12
         dense = dict(workload="configs[1] with ModelWithoutDropout (taps %s)" % dtopo["kernel_sizes"], ms_per_step=round(d_ms, 5),
                      value_per_gpu=round(frames / (d_ms * 1e-3), 1), unit=UNIT,
                      roofline=dict(bound="tensor", achieved=round(d_tf, 1), peak=peaks["tflops"], unit="TFLOP/s",
                                    frac=round(d_tf / peaks["tflops"], 4), share_of_step=round(d_layers / float(dk.sum()), 4),
                                    traffic=ncu_traffic_bytes("ModelWithoutDropout")[0],
-                                   layer_ms=[round(float(v), 5) for v in dk[1:1 + len(dfl)]]),
+                                   layer_ms=[round(float(v), 5) for v in dk[1:1 + d_n]]),
                      step_frac_of_tensor_peak=round(frames * sum(dfl) / (d_ms * 1e-3) / 1e12 / peaks["tflops"], 4))
         deng.close()
 

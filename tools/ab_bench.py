@@ -33,7 +33,7 @@ feats = torch.from_numpy(synthetic.mfcc_batch(2, lens)).cuda()
 emb = torch.empty((args.batch, 512), dtype=torch.float32, device="cuda")
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 stream = torch.cuda.current_stream()
-DEFAULTS = dict(resident=0, prefetch=0, fc=1, fc_max_splits=36, pdl=1)
+DEFAULTS = dict(resident=0, prefetch=0, fc=1, fc_max_splits=36, pdl=1, fuse_tail=1)
 
 
 def apply(cfg):

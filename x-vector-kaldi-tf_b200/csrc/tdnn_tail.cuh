@@ -30,12 +30,13 @@
 namespace tdnn2 {
 
 constexpr int FT_SLOT_BYTES = 16384;
-constexpr int FT_SLOTS = 6;
+constexpr int FT_SLOTS = 5;
 constexpr int FT_MID_CH = 512;                                  // width of the intermediate (two 256-column accumulators)
 constexpr int FT_MID_ATOMS = FT_MID_CH / BLOCK_K;               // 8
 constexpr int FT_OFF_MID = 0;
 constexpr int FT_OFF_RING = FT_MID_ATOMS * FT_SLOT_BYTES;       // 131072
-constexpr int FT_OFF_BARS = FT_OFF_RING + FT_SLOTS * FT_SLOT_BYTES;   // 229376
+constexpr int FT_OFF_PAR = FT_OFF_RING + FT_SLOTS * FT_SLOT_BYTES;    // 212992: bias | scale | shift | slope of the 512 intermediate channels
+constexpr int FT_OFF_BARS = FT_OFF_PAR + 4 * FT_MID_CH * 4;           // 221184
 constexpr int FT_NUM_BARS = 2 * FT_SLOTS + 6;                   // full, empty | t_full[2], t_empty[2], mid_ready[2]
 constexpr int FT_OFF_TMEM_PTR = FT_OFF_BARS + (FT_NUM_BARS + 2) * 8;
 constexpr int FT_SMEM_BYTES = FT_OFF_TMEM_PTR + 16 + 1024;      // + slack for 1024-byte alignment
@@ -46,7 +47,9 @@ struct FusedTailArgs {
   int32_t k_atoms_in;       // C_in / 64 of layer n-2
   int32_t n_ch_tiles;       // C_out / 256 of layer n-1
   int32_t c_out;
-  // layer n-2 (512 channels): conv bias, folded BatchNorm, negative slope; acc_scale as in PairArgs
+  // layer n-2 (512 channels): conv bias, folded BatchNorm, negative slope (staged in shared memory once per CTA: the
+  // store-orientation epilogue needs all of a chunk's 32 channels in every thread; global or constant-bank reads made
+  // that epilogue 2-4x slower); acc_scale as in PairArgs
   const float* bias3; const float* scale3; const float* shift3; const float* alpha3;
   float acc_scale3;
   // layer n-1
@@ -57,7 +60,12 @@ struct FusedTailArgs {
   float* partial;           // [R_pad / 32][2][C_out]
   uint32_t* overflow_flag;
   uint32_t overflow_bit3;   // OR-ed in when a stored value of the intermediate overflowed fp16
+  long long* trace;         // diagnostics: [cluster][rank][TRACE_TILES jobs][8] SM clock stamps (slots as in tdnn_pair.cuh), or null
 };
+__device__ __forceinline__ void ft_stamp(const FusedTailArgs& a, int cluster, uint32_t rank, uint32_t job, int slot) {
+  if (a.trace != nullptr && job < TRACE_TILES)
+    a.trace[((size_t(cluster) * 2 + rank) * TRACE_TILES + job) * 8 + slot] = clock64();
+}
 
 __device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
@@ -118,7 +126,7 @@ tdnn_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap_x,    // [R_pad,
 
   if (warp == 0) {
     // ============================ TMA producer ============================
-    uint32_t s = 0, ph = 0;
+    uint32_t s = 0, ph = 0, pg = 0;
     const uint32_t full_leader = ptx::mapa_cluster(full(0), 0);
     auto load = [&](const CUtensorMap* map, int col, int row) {
       ptx::mbar_wait(empty(s), ph ^ 1u);
@@ -131,13 +139,27 @@ tdnn_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap_x,    // [R_pad,
     };
     for (int tile = cluster_id; tile < args.n_row_tiles; tile += n_clusters) {
       const int r0 = tile * TILE_ROWS + int(rank) * CTA_ROWS;
-      for (int nt = 0; nt < 2; ++nt)
+      for (int nt = 0; nt < 2; ++nt, ++pg) {
         for (int ka = 0; ka < KA; ++ka) {
           load(&tmap_x, ka * BLOCK_K, r0);
+          if (ka == 0 && lane == 0) ft_stamp(args, cluster_id, rank, pg, 0);
           load(&tmap_w3, ka * BLOCK_K, nt * TILE_CH + int(rank) * CTA_CH);
         }
-      for (int ct = 0; ct < NCT; ++ct)
-        for (int ka = 0; ka < FT_MID_ATOMS; ++ka) load(&tmap_w4, ka * BLOCK_K, ct * TILE_CH + int(rank) * CTA_CH);
+        if (lane == 0) ft_stamp(args, cluster_id, rank, pg, 1);
+      }
+      for (int ct = 0; ct < NCT; ++ct, ++pg) {
+        if (ct == 1 && tile + n_clusters < args.n_row_tiles && ptx::elect_one()) {
+          // the next row tile's input rows -> L2 now, so that the short ring of the layer n-2 phase (3 K steps in flight)
+          // only has to cover an L2 hit
+          for (int ka = 0; ka < KA; ++ka) ptx::tma_prefetch_l2_2d(&tmap_x, ka * BLOCK_K, r0 + n_clusters * TILE_ROWS);
+        }
+        __syncwarp();
+        for (int ka = 0; ka < FT_MID_ATOMS; ++ka) {
+          load(&tmap_w4, ka * BLOCK_K, ct * TILE_CH + int(rank) * CTA_CH);
+          if (ka == 0 && lane == 0) ft_stamp(args, cluster_id, rank, pg, 0);
+        }
+        if (lane == 0) ft_stamp(args, cluster_id, rank, pg, 1);
+      }
     }
   } else if (warp == 1) {
     // ============================ MMA issuer (leader) ============================
@@ -153,6 +175,7 @@ tdnn_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap_x,    // [R_pad,
           ptx::mbar_wait_cluster(t_empty(acc), ((g >> 1) & 1u) ^ 1u);
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * TILE_CH;
+          if (lane == 0) ft_stamp(args, cluster_id, rank, g, 2);
           for (int ka = 0; ka < KA; ++ka) {
             const uint32_t sx = s, phx = ph;
             if (++s == FT_SLOTS) { s = 0; ph ^= 1u; }
@@ -173,6 +196,7 @@ tdnn_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap_x,    // [R_pad,
           }
           if (ptx::elect_one()) ptx::umma_commit_2sm(t_full(acc));
           __syncwarp();
+          if (lane == 0) ft_stamp(args, cluster_id, rank, g, 3);
         }
         // ---- layer n-1: pooled orientation, B = the resident intermediate ----
         for (int ct = 0; ct < NCT; ++ct, ++g) {
@@ -180,6 +204,7 @@ tdnn_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap_x,    // [R_pad,
           ptx::mbar_wait_cluster(t_empty(acc), ((g >> 1) & 1u) ^ 1u);
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * TILE_CH;
+          if (lane == 0) ft_stamp(args, cluster_id, rank, g, 2);
           for (int ka = 0; ka < FT_MID_ATOMS; ++ka) {
             if (ct == 0 && (ka == 0 || ka == FT_MID_ATOMS / 2)) {     // the half of the intermediate this atom lies in is written
               ptx::mbar_wait_cluster(mid_ready(ka == 0 ? 0u : 1u), ti & 1u);
@@ -199,6 +224,7 @@ tdnn_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap_x,    // [R_pad,
           }
           if (ptx::elect_one()) ptx::umma_commit_2sm(t_full(acc));
           __syncwarp();
+          if (lane == 0) ft_stamp(args, cluster_id, rank, g, 3);
         }
       }
     }
@@ -209,6 +235,14 @@ tdnn_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap_x,    // [R_pad,
     const int colh = e >> 2;                         // which 128-column half of the accumulator
     const uint32_t t_empty_leader = ptx::mapa_cluster(t_empty(0), 0);
     const uint32_t mid_ready_leader = ptx::mapa_cluster(mid_ready(0), 0);
+    const uint32_t sPar = smem_base + FT_OFF_PAR;
+    for (int c = threadIdx.x - 64; c < FT_MID_CH; c += NUM_EPI_THREADS) {          // once: the parameters do not change with the tile
+      ptx::sts_f(sPar + uint32_t(c) * 4u, __ldg(args.bias3 + c));
+      ptx::sts_f(sPar + uint32_t(FT_MID_CH + c) * 4u, __ldg(args.scale3 + c));
+      ptx::sts_f(sPar + uint32_t(2 * FT_MID_CH + c) * 4u, __ldg(args.shift3 + c));
+      ptx::sts_f(sPar + uint32_t(3 * FT_MID_CH + c) * 4u, LEAKY ? __ldg(args.alpha3 + c) : 0.f);
+    }
+    ptx::named_bar_sync(1, NUM_EPI_THREADS);
     const float as3 = args.acc_scale3 != 0.f ? args.acc_scale3 : 1.f;
     const float as4 = args.acc_scale4 != 0.f ? args.acc_scale4 : 1.f;
     uint32_t hmax = 0, g = 0;
@@ -221,6 +255,7 @@ tdnn_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap_x,    // [R_pad,
         const uint32_t acc = g & 1u;
         ptx::mbar_wait(t_full(acc), (g >> 1) & 1u);
         ptx::tc_fence_after();
+        if (e == 0 && lane == 0) ft_stamp(args, cluster_id, rank, g, 4);
         const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * TILE_CH + uint32_t(colh) * 128u;
         uint32_t v[2][32];
         ptx::tmem_ld_32x32(t_row, v[0]);
@@ -233,16 +268,18 @@ tdnn_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap_x,    // [R_pad,
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(t_empty_leader + 8u * acc);
+            if (e == 0 && lane == 0) ft_stamp(args, cluster_id, rank, g, 5);
           }
           const int ch = nt * TILE_CH + colh * 128 + chunk * C_CHUNK;   // first of this chunk's 32 intermediate channels
           uint32_t p[16];
 #pragma unroll
           for (int gq = 0; gq < 8; ++gq) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.bias3 + ch) + gq);
-            const float4 s4 = __ldg(reinterpret_cast<const float4*>(args.scale3 + ch) + gq);
-            const float4 h4 = __ldg(reinterpret_cast<const float4*>(args.shift3 + ch) + gq);
+            const uint32_t c4 = uint32_t(ch + gq * 4) * 4u;
+            const float4 b4 = ptx::lds_f4(sPar + c4);
+            const float4 s4 = ptx::lds_f4(sPar + FT_MID_CH * 4u + c4);
+            const float4 h4 = ptx::lds_f4(sPar + 2u * FT_MID_CH * 4u + c4);
             float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (LEAKY) a4 = __ldg(reinterpret_cast<const float4*>(args.alpha3 + ch) + gq);
+            if (LEAKY) a4 = ptx::lds_f4(sPar + 3u * FT_MID_CH * 4u + c4);
             const float y0 = act_bn<LEAKY>(__uint_as_float(v[chunk & 1][gq * 4 + 0]), b4.x, s4.x, h4.x, a4.x, as3);
             const float y1 = act_bn<LEAKY>(__uint_as_float(v[chunk & 1][gq * 4 + 1]), b4.y, s4.y, h4.y, a4.y, as3);
             const float y2 = act_bn<LEAKY>(__uint_as_float(v[chunk & 1][gq * 4 + 2]), b4.z, s4.z, h4.z, a4.z, as3);
@@ -266,6 +303,7 @@ tdnn_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap_x,    // [R_pad,
         ptx::fence_proxy_async_smem();               // the tensor core reads these rows through the async proxy
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster_release(mid_ready_leader + 8u * uint32_t(nt));
+        if (e == 0 && lane == 0) ft_stamp(args, cluster_id, rank, g, 6);
       }
       // ---- layer n-1: pooled partial sums (lane = channel, registers = 32 consecutive frames) ----
       for (int ct = 0; ct < NCT; ++ct, ++g) {
@@ -278,6 +316,7 @@ tdnn_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap_x,    // [R_pad,
         const uint32_t nv4 = *reinterpret_cast<const uint32_t*>(args.blk_valid + blk0);   // 4 blocks, 1 byte each
         ptx::mbar_wait(t_full(acc), (g >> 1) & 1u);
         ptx::tc_fence_after();
+        if (e == 0 && lane == 0) ft_stamp(args, cluster_id, rank, g, 4);
         const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * TILE_CH + uint32_t(colh) * 128u;
         uint32_t v[2][32];
         ptx::tmem_ld_32x32(t_row, v[0]);
@@ -315,6 +354,7 @@ tdnn_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap_x,    // [R_pad,
             dst[args.c_out] = (s2[0] + s2[1]) + (s2[2] + s2[3]);
           }
         }
+        if (e == 0 && lane == 0) ft_stamp(args, cluster_id, rank, g, 6);
       }
     }
     if ((hmax & 0x7fffu) >= 0x7c00u || ((hmax >> 16) & 0x7fffu) >= 0x7c00u)

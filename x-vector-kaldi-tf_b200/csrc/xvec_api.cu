@@ -53,6 +53,7 @@ struct FrameLayer {
   // BatchNorm times 2^-exp_out; the next layer's epilogue multiplies its accumulator by 2^exp_out).  Powers of two: exact.
   int exp_out = 0;
   std::vector<float> scale_host, shift_host;     // the unscaled folded BatchNorm
+  std::vector<float> bias_host, alpha_host;      // host copies for kernels that take them by value (tdnn_tail.cuh)
 };
 
 struct Plan {
@@ -342,6 +343,8 @@ int finalize_params(xv_model* m) {
     XV_CUDA(cudaMemcpy(L.bias_dev, b->data(), L.c_out * 4, cudaMemcpyHostToDevice));
     L.scale_host = scale;
     L.shift_host = shift;
+    L.bias_host = *b;
+    L.alpha_host.clear();
     L.exp_out = 0;
     if (t.act != XV_ACT_RELU) {
       std::vector<float> alpha(L.c_out, 0.2f);                       // tf.nn.leaky_relu(h, alpha=0.2)  (models.py:912)
@@ -352,6 +355,7 @@ int finalize_params(xv_model* m) {
       }
       XV_CUDA(cudaMalloc(&L.alpha_dev, L.c_out * 4));
       XV_CUDA(cudaMemcpy(L.alpha_dev, alpha.data(), L.c_out * 4, cudaMemcpyHostToDevice));
+      L.alpha_host = alpha;
     }
   }
   const int c_last = m->c_pool;
@@ -650,7 +654,7 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
   const bool fuse_tail = m->opt_fuse_tail && !attention && !m->opt_split && !layer_out_dev && nl >= 3 && !m->opt_resident &&
                          m->layers[nl - 2].gemm_taps == 1 && m->layers[nl - 1].gemm_taps == 1 &&
                          m->layers[nl - 2].c_out == tdnn2::FT_MID_CH && m->layers[nl - 2].c_in_pad % tdnn2::BLOCK_K == 0 &&
-                         m->opt_trace_layer < 0;
+                         (m->opt_trace_layer < 0 || m->opt_trace_layer == nl - 2);
   for (int i = 0; i < nl; ++i) {
     if (fuse_tail && i == nl - 2) {
       const FrameLayer& L3 = m->layers[nl - 2];
@@ -677,6 +681,7 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
       a.partial = pool_partial;
       a.overflow_flag = m->cur_flag;
       a.overflow_bit3 = 1u << (8 + nl - 2);
+      a.trace = (m->opt_trace_layer == nl - 2) ? m->opt_trace : nullptr;
       const int grid = 2 * int(std::min<int64_t>(a.n_row_tiles, m->num_clusters));
       XV_PROF();
       if (L3.alpha_dev != nullptr)
