@@ -111,6 +111,19 @@ int64_t xv_vec_ark_format(const char* key_blob, const int64_t* key_off, int64_t 
 int64_t xv_scp_format(const char* key_blob, const int64_t* key_off, int64_t n, const char* ark_name, int64_t base,
                       const int64_t* marker_off, char* out, int64_t out_cap);
 
+/* Synthetic workload (bench / scale tests only; SURVEY 8d, BASELINE configs[3]): the MFCC rows of n_utt utterances generated
+ * on the device from (seed, utterance id, frame, coefficient) -- out_dev [sum(len), feat_dim] fp32, utterances concatenated
+ * in order.  utt_id_host / len_host are HOST arrays; the same integer recipe in numpy (synthetic.counter_mfcc) reproduces any
+ * utterance bit for bit.  Enqueue only (two small host->device copies ride on `stream`). */
+int xv_synth_mfcc(int device, float* out_dev, const int64_t* utt_id_host, const int32_t* len_host, int32_t n_utt, int32_t feat_dim,
+                  uint64_t seed, void* stream);
+
+/* xv_submit_host_utts (include/xvec.h) for features that are ALREADY on the device (they must stay untouched until the
+ * ticket is collected: an fp16 range rescue re-runs the submission from them). */
+int xv_submit_dev_utts(xv_model* m, const float* feats_dev, const int32_t* seg_len_host, int32_t n_seg,
+                       const int32_t* utt_first_seg_host, const int64_t* utt_dst_row_host, int32_t n_utt, float* out_dev,
+                       float* out_host, int32_t* ticket);
+
 #ifdef __cplusplus
 }
 #endif

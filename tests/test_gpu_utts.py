@@ -118,3 +118,42 @@ def test_peer_table_round_trip_in_one_process():
     assert np.array_equal(got, local.cpu().numpy())
     table.close()
     eng.close()
+
+
+def test_device_generated_utterances_equal_the_numpy_restatement_and_run_through_the_job_loop(tmp_path):
+    # xv_synth_mfcc (the workload generator of BASELINE configs[3]) against synthetic.counter_mfcc, bit for bit; then a small
+    # SyntheticSource job through Model._run_extraction_job: keys in order, rows equal to a direct forward of the regenerated rows
+    import io
+    import time
+    import torch
+    from xvector_b200 import _native, ark_job, kaldi_io, models
+    ids = np.array([0, 7, 123456, 999999], np.int64)
+    lens = np.array([200, 333, 25, 1000], np.int32)
+    out = torch.empty((int(lens.sum()), 23), dtype=torch.float32, device="cuda")
+    _native.synth_mfcc(0, out, ids, lens, seed=4)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    want = np.concatenate([synthetic.counter_mfcc(4, int(i), int(n)) for i, n in zip(ids, lens)])
+    assert np.array_equal(got, want)
+    assert abs(float(got[:, 0].std()) - 12.0) < 0.8 and abs(float(got.mean())) < 0.3
+
+    import os
+    os.environ["XVEC_SEED"] = "5"
+    model_dir = str(tmp_path / "model_0")
+    models.ModelWithoutDropoutTdnn().build_model(10, 23, model_dir, None)
+    model = models.Model()
+    model.load_model(None, model_dir, None)
+    engine = model._get_engine(0)
+    src = ark_job.SyntheticSource(0, 300, 4, 40000, rank=0, world=1)
+    buf = io.BytesIO()
+    t0 = time.time()
+    model._run_extraction_job(src, src.counts("cuda:0"), buf, engine, 0, 25, None, t0, t0)
+    rows = list(kaldi_io.read_vec_flt_ark(io.BytesIO(buf.getvalue())))
+    assert [k for k, _ in rows] == ["utt%07d" % i for i in range(300)]
+    all_lens = synthetic.lengths_uniform(4, 300)
+    for i in (0, 151, 299):
+        x = torch.from_numpy(synthetic.counter_mfcc(4, i, int(all_lens[i]))).cuda()
+        o = torch.empty((1, 512), dtype=torch.float32, device="cuda")
+        engine.forward_utts(x, np.array([all_lens[i]], np.int32), o)
+        torch.cuda.synchronize()
+        assert np.array_equal(o.cpu().numpy()[0], rows[i][1])

@@ -188,6 +188,10 @@ def load_library():
     lib.xv_vec_ark_format.restype = I64
     lib.xv_scp_format.argtypes = [P, P, I64, ctypes.c_char_p, I64, P, P, I64]
     lib.xv_scp_format.restype = I64
+    lib.xv_synth_mfcc.argtypes = [ctypes.c_int, P, P, P, I32, I32, ctypes.c_uint64, P]
+    lib.xv_synth_mfcc.restype = ctypes.c_int
+    lib.xv_submit_dev_utts.argtypes = [P, P, P, I32, P, P, I32, P, P, ctypes.POINTER(I32)]
+    lib.xv_submit_dev_utts.restype = ctypes.c_int
     # training step (include/xvec_train.h)
     F32, F64 = ctypes.c_float, ctypes.c_double
     lib.xv_train_create.argtypes = [ctypes.POINTER(P), P, I32, I32]
@@ -245,7 +249,8 @@ EXPORTED_SYMBOLS = ["xv_create", "xv_destroy", "xv_set_param", "xv_workspace_byt
                     # include/xvec_job.h
                     "xv_ark_reader_open", "xv_ark_reader_index", "xv_ark_reader_set_first", "xv_ark_reader_keys",
                     "xv_ark_reader_failures", "xv_ark_reader_start", "xv_ark_reader_next", "xv_ark_reader_release",
-                    "xv_ark_reader_close", "xv_vec_ark_bytes", "xv_vec_ark_format", "xv_scp_format",
+                    "xv_ark_reader_close", "xv_vec_ark_bytes", "xv_vec_ark_format", "xv_scp_format", "xv_synth_mfcc",
+                    "xv_submit_dev_utts",
                     # include/xvec_train.h
                     "xv_train_create", "xv_train_destroy", "xv_train_size", "xv_train_span", "xv_train_upload",
                     "xv_train_download", "xv_train_set_step", "xv_train_get_step", "xv_train_forward_backward", "xv_train_eval",
@@ -370,6 +375,19 @@ class ArkReader(object):
             self.close()
         except Exception:
             pass
+
+
+def synth_mfcc(device, out_dev, utt_ids, lens, seed, stream=None):
+    """Rows of the synthetic utterances ``utt_ids`` (lengths ``lens``) generated on the device into ``out_dev`` (float32 CUDA
+    [>= sum(lens), feat_dim]); ``synthetic.counter_mfcc`` is the same recipe in numpy."""
+    import torch
+    lib = load_library()
+    ids = np.ascontiguousarray(utt_ids, dtype=np.int64)
+    ln = np.ascontiguousarray(lens, dtype=np.int32)
+    assert out_dev.is_cuda and out_dev.dtype == torch.float32 and out_dev.is_contiguous() and out_dev.shape[0] >= int(ln.sum())
+    s = torch.cuda.current_stream(device) if stream is None else stream
+    _check(lib, lib.xv_synth_mfcc(int(device), out_dev.data_ptr(), ids.ctypes.data, ln.ctypes.data, int(ids.shape[0]),
+                                  int(out_dev.shape[1]), int(seed) & (2 ** 64 - 1), s.cuda_stream))
 
 
 def vec_ark_format(key_blob, key_off, vecs, with_markers=False, n_threads=4, out=None):
@@ -577,6 +595,24 @@ class XvecEngine:
                                                   None if dst is None else dst.ctypes.data_as(ctypes.c_void_p), n_utt,
                                                   optr, ws.data_ptr(), ws.numel(), s.cuda_stream))
         return n_utt
+
+    def submit_dev_utts(self, feats_dev, seg_lens, utt_first_seg=None, dst_rows=None, out_dev=None, out_host=None):
+        """``submit_host_utts`` for features already on the device (a float32 CUDA tensor that stays untouched until collected)."""
+        lens = np.ascontiguousarray(seg_lens, dtype=np.int32)
+        n_seg = int(lens.shape[0])
+        assert feats_dev.is_cuda and feats_dev.is_contiguous() and feats_dev.shape[0] >= int(lens.sum())
+        first, dst, n_utt = self._utt_plan(n_seg, utt_first_seg, dst_rows)
+        optr = None if out_dev is None else (out_dev if isinstance(out_dev, int) else out_dev.data_ptr())
+        hptr = None
+        if out_host is not None:
+            assert out_host.shape[0] >= n_utt
+            hptr = out_host.data_ptr() if hasattr(out_host, "data_ptr") else out_host.ctypes.data
+        ticket = ctypes.c_int32(-1)
+        _check(self.lib, self.lib.xv_submit_dev_utts(self.handle, feats_dev.data_ptr(), lens.ctypes.data_as(ctypes.c_void_p), n_seg,
+                                                     None if first is None else first.ctypes.data_as(ctypes.c_void_p),
+                                                     None if dst is None else dst.ctypes.data_as(ctypes.c_void_p), n_utt,
+                                                     optr, hptr, ctypes.byref(ticket)))
+        return int(ticket.value)
 
     def submit_host_utts(self, feats_host, seg_lens, utt_first_seg=None, dst_rows=None, out_dev=None, out_host=None):
         """``submit_host`` with utterance-level output: averaged rows to ``out_dev[dst_rows[u]]`` (CUDA tensor, PeerTable

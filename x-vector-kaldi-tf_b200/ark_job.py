@@ -164,3 +164,86 @@ def finish_shared_output(output_stream, spec, total_bytes, scp_parts):
                 output_stream.scp.write(part.tobytes().decode())
     else:
         output_stream.seek(end)
+
+
+class _SynthBatch(object):
+    __slots__ = ("slot", "n_seg", "n_utt", "n_rows", "feats", "seg_len", "utt_first_seg", "utt_dst_row", "first_ok_index")
+
+
+class SyntheticSource(object):
+    """A batch source with ``_native.ArkReader``'s interface whose utterances are GENERATED on the device
+    (xv_synth_mfcc: counter-based, reproducible on the host with ``synthetic.counter_mfcc``): the workload of
+    BASELINE configs[3] -- 1 M utterances of 200-1000 frames, 55 GB of features, more than a host can hold or feed
+    (SURVEY 7, hard part 7).  Rank r owns the contiguous block of utterance ids [n * r / world, n * (r + 1) / world);
+    keys are ``utt%07d``.  Lengths: ``synthetic.lengths_uniform(seed, n)``."""
+    feats_on_device = True
+
+    def __init__(self, device, n_utts, seed, batch_frames, feat_dim=23, rank=None, world=None, slots=3):
+        import torch
+        from . import synthetic
+        if rank is None:
+            rank, world = sharding.dist_info()
+        self.device, self.seed, self.feat_dim = int(device), int(seed), int(feat_dim)
+        lo, hi = n_utts * rank // world, n_utts * (rank + 1) // world
+        self.ids = np.arange(lo, hi, dtype=np.int64)
+        self.lens = synthetic.lengths_uniform(seed, n_utts)[lo:hi].astype(np.int32)
+        n = len(self.ids)
+        # batches: greedy runs of utterances of at most batch_frames rows
+        ends = np.cumsum(self.lens, dtype=np.int64)
+        self.bounds = [0]
+        while self.bounds[-1] < n:
+            start_rows = ends[self.bounds[-1] - 1] if self.bounds[-1] else 0
+            nxt = int(np.searchsorted(ends, start_rows + batch_frames, side="right"))
+            self.bounds.append(max(nxt, self.bounds[-1] + 1))
+        self.bounds[-1] = n
+        cap = max(int(batch_frames), int(self.lens.max()) if n else 1)
+        self.bufs = [torch.empty((cap, feat_dim), dtype=torch.float32, device="cuda:%d" % device) for _ in range(min(slots, max(len(self.bounds) - 1, 1)))]
+        self.stream = torch.cuda.Stream(device)
+        self.next_batch, self.released, self.base = 0, 0, 0
+        self.info = dict(n_entries=n, n_ok=n, n_fail=0, rows_used=int(self.lens.sum()), stopped_at=-1, key_bytes=10 * n)
+
+    def counts(self, device_name):
+        i = self.info
+        return _all_gather_i64([i["n_entries"], i["n_ok"], i["n_fail"], i["rows_used"], i["stopped_at"], i["key_bytes"]], device_name)
+
+    def failures(self):
+        return []
+
+    def keys(self):
+        n = len(self.ids)
+        blob = np.empty((n, 10), np.uint8)
+        blob[:, :3] = np.frombuffer(b"utt", np.uint8)
+        v = self.ids.copy()
+        for k in range(7):
+            blob[:, 9 - k] = 48 + (v % 10)
+            v //= 10
+        return blob.reshape(-1), np.arange(n + 1, dtype=np.int64) * 10
+
+    def start(self, dst_row_base=0):
+        self.base = int(dst_row_base)
+
+    def next(self):
+        from ._native import synth_mfcc
+        if self.next_batch >= len(self.bounds) - 1:
+            return None
+        assert self.next_batch - self.released < len(self.bufs), "release a batch first"
+        u0, u1 = self.bounds[self.next_batch], self.bounds[self.next_batch + 1]
+        b = _SynthBatch()
+        b.slot = self.next_batch % len(self.bufs)
+        b.n_utt = b.n_seg = u1 - u0
+        b.seg_len = self.lens[u0:u1]
+        b.n_rows = int(b.seg_len.sum())
+        b.utt_first_seg = np.arange(b.n_utt + 1, dtype=np.int32)
+        b.utt_dst_row = self.base + np.arange(u0, u1, dtype=np.int64)
+        b.first_ok_index = u0
+        b.feats = self.bufs[b.slot][:b.n_rows]
+        synth_mfcc(self.device, self.bufs[b.slot], self.ids[u0:u1], b.seg_len, self.seed, stream=self.stream)
+        self.stream.synchronize()                     # the submission runs on the engine's own stream
+        self.next_batch += 1
+        return b
+
+    def release(self, slot):
+        self.released += 1
+
+    def close(self):
+        self.bufs = []

@@ -13,6 +13,7 @@
 #include <thread>
 
 #include "../../include/xvec_job.h"
+#include "synth.cuh"
 
 namespace arkjob {
 
@@ -606,6 +607,43 @@ void xv_ark_reader_close(xv_ark_reader* r) {
     close(r->fd);
   }
   delete r;
+}
+
+int xv_synth_mfcc(int device, float* out_dev, const int64_t* utt_id_host, const int32_t* len_host, int32_t n_utt, int32_t feat_dim,
+                  uint64_t seed, void* stream_) {
+  if (!out_dev || !utt_id_host || !len_host || n_utt < 1 || feat_dim < 1 || feat_dim > synth::MAX_DIM) return fail(XV_EINVAL, "bad argument");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  XV_CUDA(cudaSetDevice(device));
+  // per-call scratch for the two small tables (freed stream-ordered)
+  std::vector<int32_t> start(size_t(n_utt) + 1, 0);
+  for (int i = 0; i < n_utt; ++i) {
+    if (len_host[i] < 0) return fail(XV_EINVAL, "negative length");
+    start[i + 1] = start[i] + len_host[i];
+  }
+  void* scratch = nullptr;
+  const size_t id_bytes = size_t(n_utt) * 8, st_bytes = (size_t(n_utt) + 1) * 4;
+  XV_CUDA(cudaMallocAsync(&scratch, id_bytes + st_bytes, stream));
+  XV_CUDA(cudaMemcpyAsync(scratch, utt_id_host, id_bytes, cudaMemcpyHostToDevice, stream));
+  XV_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(scratch) + id_bytes, start.data(), st_bytes, cudaMemcpyHostToDevice, stream));
+  XV_CUDA(cudaStreamSynchronize(stream));            // `start` is a local: the copy must have left it
+  synth::Args a{};
+  a.out = out_dev;
+  a.utt_id = static_cast<const int64_t*>(scratch);
+  a.row_start = reinterpret_cast<const int32_t*>(static_cast<uint8_t*>(scratch) + id_bytes);
+  a.n_utt = n_utt;
+  a.feat_dim = feat_dim;
+  a.total_rows = start[n_utt];
+  a.seed = seed;
+  // x has unit variance before the per-coefficient scale 12 / sqrt(1 + d) (synthetic.mfcc's law): Irwin-Hall(4) of 32-bit
+  // uniforms has variance 2^64 / 3
+  for (int d = 0; d < feat_dim; ++d)
+    a.k[d] = float(std::sqrt(3.0) / 4294967296.0 * 12.0 / std::sqrt(1.0 + double(d)));
+  if (a.total_rows > 0) {
+    synth::synth_mfcc_kernel<<<unsigned((a.total_rows + 255) / 256), 256, 0, stream>>>(a);
+    XV_CUDA(cudaGetLastError());
+  }
+  XV_CUDA(cudaFreeAsync(scratch, stream));
+  return XV_OK;
 }
 
 int64_t xv_vec_ark_bytes(const int64_t* key_off, int64_t n, int32_t dim) {

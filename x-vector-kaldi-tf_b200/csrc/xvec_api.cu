@@ -142,6 +142,7 @@ struct xv_model {
       int32_t n_utt = 0;
       float* out_dev = nullptr;
       float* host_out = nullptr;         // emb_host / out_host of the submission (may be null)
+      const float* feats_ext = nullptr;  // features the caller keeps on the device (xv_submit_dev_utts), else the slot's copy
     } redo;
     cudaEvent_t done = nullptr;          // recorded behind the submission's last copy; created with cudaEventBlockingSync so that
                                          // xv_collect SLEEPS instead of spinning (a multi-GPU job runs reader threads on those cores)
@@ -1221,13 +1222,15 @@ int enqueue_slot(xv_model* m, int si) {
     u.n_utt = rd.n_utt;
     u.out_dev = rd.out_dev;
     u.out_local_dev = rd.host_out ? sl.emb_dev : nullptr;        // the slot's buffer holds the rows the host reads
-    rc = forward_impl(m, sl.feats_dev, rd.seg_len.data(), n_seg, nullptr, sl.ws_dev, sl.ws_cap, sl.stream, nullptr, nullptr, &u);
+    rc = forward_impl(m, rd.feats_ext ? rd.feats_ext : sl.feats_dev, rd.seg_len.data(), n_seg, nullptr, sl.ws_dev, sl.ws_cap, sl.stream,
+                      nullptr, nullptr, &u);
     m->cur_flag = m->overflow_dev;
     if (rc != XV_OK) return rc;
     if (rd.host_out)
       XV_CUDA(cudaMemcpyAsync(rd.host_out, sl.emb_dev, size_t(rd.n_utt) * m->topo.emb_dim * 4, cudaMemcpyDeviceToHost, sl.stream));
   } else {
-    rc = forward_impl(m, sl.feats_dev, rd.seg_len.data(), n_seg, sl.emb_dev, sl.ws_dev, sl.ws_cap, sl.stream, nullptr, nullptr);
+    rc = forward_impl(m, rd.feats_ext ? rd.feats_ext : sl.feats_dev, rd.seg_len.data(), n_seg, sl.emb_dev, sl.ws_dev, sl.ws_cap, sl.stream,
+                      nullptr, nullptr);
     m->cur_flag = m->overflow_dev;
     if (rc != XV_OK) return rc;
     XV_CUDA(cudaMemcpyAsync(rd.host_out, sl.emb_dev, size_t(n_seg) * m->topo.emb_dim * 4, cudaMemcpyDeviceToHost, sl.stream));
@@ -1239,8 +1242,8 @@ int enqueue_slot(xv_model* m, int si) {
 
 // Common body of xv_submit_host / xv_submit_host_utts.
 int submit_impl(xv_model* m, const float* feats_host, const int32_t* seg_len_host, int32_t n_seg, float* emb_host,
-                const UttOut* utt_in, float* utt_host_out, int32_t* ticket) {
-  if (!m || !feats_host || !seg_len_host || !ticket) return fail(XV_EINVAL, "null argument");
+                const UttOut* utt_in, float* utt_host_out, int32_t* ticket, const float* feats_dev_ext = nullptr) {
+  if (!m || (!feats_host && !feats_dev_ext) || !seg_len_host || !ticket) return fail(XV_EINVAL, "null argument");
   if (n_seg <= 0) return fail(XV_EINVAL, "n_seg must be >= 1");
   XV_CUDA(cudaSetDevice(m->device));
   int64_t total = 0;
@@ -1264,10 +1267,11 @@ int submit_impl(xv_model* m, const float* feats_host, const int32_t* seg_len_hos
     if (e == cudaSuccess) *cap = want;
     return e;
   };
-  XV_CUDA(grow(reinterpret_cast<void**>(&sl.feats_dev), &sl.feats_cap, feat_bytes));
+  if (!feats_dev_ext) XV_CUDA(grow(reinterpret_cast<void**>(&sl.feats_dev), &sl.feats_cap, feat_bytes));
   XV_CUDA(grow(reinterpret_cast<void**>(&sl.emb_dev), &sl.emb_cap, emb_bytes));
   XV_CUDA(grow(&sl.ws_dev, &sl.ws_cap, ws_bytes));
-  XV_CUDA(cudaMemcpyAsync(sl.feats_dev, feats_host, feat_bytes, cudaMemcpyHostToDevice, sl.stream));
+  if (!feats_dev_ext) XV_CUDA(cudaMemcpyAsync(sl.feats_dev, feats_host, feat_bytes, cudaMemcpyHostToDevice, sl.stream));
+  sl.redo.feats_ext = feats_dev_ext;
   // remember the submission: an fp16 range rescue in xv_collect re-runs it from the slot's device copy of the features
   xv_model::HostSlot::Redo& rd = sl.redo;
   rd.seg_len.assign(seg_len_host, seg_len_host + n_seg);
@@ -1320,6 +1324,19 @@ int xv_submit_host_utts(xv_model* m, const float* feats_host, const int32_t* seg
   u.n_utt = n_utt;
   u.out_dev = out_dev;
   return submit_impl(m, feats_host, seg_len_host, n_seg, nullptr, &u, out_host, ticket);
+}
+
+int xv_submit_dev_utts(xv_model* m, const float* feats_dev, const int32_t* seg_len_host, int32_t n_seg,
+                       const int32_t* utt_first_seg_host, const int64_t* utt_dst_row_host, int32_t n_utt, float* out_dev,
+                       float* out_host, int32_t* ticket) {
+  if (!feats_dev) return fail(XV_EINVAL, "null argument");
+  if (!out_dev && !out_host) return fail(XV_EINVAL, "xv_submit_dev_utts: no destination (out_dev and out_host are both null)");
+  UttOut u;
+  u.first_seg_host = utt_first_seg_host;
+  u.dst_row_host = utt_dst_row_host;
+  u.n_utt = n_utt;
+  u.out_dev = out_dev;
+  return submit_impl(m, nullptr, seg_len_host, n_seg, nullptr, &u, out_host, ticket, feats_dev);
 }
 
 // ---- peer memory (one node, one process per GPU): rank 0's result table mapped into every rank ----

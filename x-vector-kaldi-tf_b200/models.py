@@ -663,18 +663,28 @@ class Model(object):
           * no peer memory (CPU process groups of the host-logic tests): one gather of the host rows."""
         from . import ark_job
         path, start = source
-        rank, world = sharding.dist_info()
-        feat_dim, emb_dim = self.meta["input_feature_dim"], self.embedding_sizes[0]
+        feat_dim = self.meta["input_feature_dim"]
         on_gpu = getattr(engine, "handle", None) is not None       # a device engine (stand-ins of the host-logic tests have none)
         dev_name = "cuda:%d" % device if on_gpu else "cpu"
-        stats = dict(pre_s=time.time() - start_time, index_s=0.0, reader_wait_s=0.0, submit_s=0.0, collect_s=0.0, write_s=0.0,
-                     tail_s=0.0, batches=0)
         t_job = time.time()
         reader, counts = ark_job.open_striped_reader(path, start, feat_dim, min_chunk_size, chunk_size, batch_frames,
                                                      device=dev_name, pinned=on_gpu)
         if reader is None:
             return False
-        stats["index_s"] = time.time() - t_job
+        self._run_extraction_job(reader, counts, output_stream, engine, device, min_chunk_size, logger, start_time, t_job)
+        return True
+
+    def _run_extraction_job(self, reader, counts, output_stream, engine, device, min_chunk_size, logger, start_time, t_job):
+        """The batch loop of an extraction job over a batch source (``_native.ArkReader``, or ``ark_job.SyntheticSource``
+        whose features are generated on the device): submissions two deep, outputs as described above."""
+        from . import ark_job
+        rank, world = sharding.dist_info()
+        emb_dim = self.embedding_sizes[0]
+        on_gpu = getattr(engine, "handle", None) is not None
+        dev_name = "cuda:%d" % device if on_gpu else "cpu"
+        feats_on_device = bool(getattr(reader, "feats_on_device", False))
+        stats = dict(pre_s=t_job - start_time, index_s=time.time() - t_job, reader_wait_s=0.0, submit_s=0.0, collect_s=0.0, write_s=0.0,
+                     tail_s=0.0, batches=0)
         self.last_job_stats = stats                  # where the wall time of the last native job went (bench / diagnostics)
         peer, shared_fd, shared_map, shared_view = None, None, None, None
         try:
@@ -740,9 +750,10 @@ class Model(object):
                             host_rows[k & 1] = _pinned_rows(max(2 * b.n_utt, 1024), emb_dim, on_gpu)
                         out_host = host_rows[k & 1][:b.n_utt]
                     t0 = time.time()
-                    ticket = engine.submit_host_utts(b.feats, b.seg_len, utt_first_seg=b.utt_first_seg,
-                                                     dst_rows=b.utt_dst_row if mode == "peer" else None,
-                                                     out_dev=peer if mode == "peer" else None, out_host=out_host)
+                    submit = engine.submit_dev_utts if feats_on_device else engine.submit_host_utts
+                    ticket = submit(b.feats, b.seg_len, utt_first_seg=b.utt_first_seg,
+                                    dst_rows=b.utt_dst_row if mode == "peer" else None,
+                                    out_dev=peer if mode == "peer" else None, out_host=out_host)
                     total_gpu_waiting += time.time() - t0
                     stats["submit_s"] += time.time() - t0
                     submitted = (ticket, b, out_host)
@@ -810,7 +821,6 @@ class Model(object):
                 logger.info("Total time for neural network computations is %.2f minutes." % (total_gpu_waiting / 60.0))
                 logger.info("Elapsed time for extracting whole embeddings is %.2f minutes." %
                             ((time.time() - start_time) / 60.0))
-            return True
         finally:
             t0 = time.time()
             reader.close()

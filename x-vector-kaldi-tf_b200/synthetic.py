@@ -35,6 +35,28 @@ def lengths_uniform(seed, n, lo=200, hi=1000):
     return rng.integers(lo, hi + 1, size=n).astype(np.int32)
 
 
+def _splitmix64(z):
+    z = (z + np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
+    z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)).astype(np.uint64)
+    z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)).astype(np.uint64)
+    return z ^ (z >> np.uint64(31))
+
+
+def counter_mfcc(seed, utt_id, num_frames, feat_dim=FEAT_DIM):
+    """The utterance the DEVICE generator (xv_synth_mfcc, csrc/synth.cuh) produces for (seed, utt_id): same integer recipe,
+    bit for bit -- Irwin-Hall(4) of the 32-bit halves of two splitmix64 words per value, scaled like ``mfcc``."""
+    with np.errstate(over="ignore"):
+        frame = np.arange(num_frames, dtype=np.uint64)[:, None]
+        d = np.arange(feat_dim, dtype=np.uint64)[None, :]
+        base = np.uint64(int(seed) & (2 ** 64 - 1)) ^ (((np.uint64(utt_id) << np.uint64(20)) | frame) * np.uint64(0x9E3779B97F4A7C15))
+        h1 = _splitmix64(base + d)
+        h2 = _splitmix64(h1)
+        m32 = np.uint64(0xFFFFFFFF)
+        s = ((h1 & m32) + (h1 >> np.uint64(32)) + (h2 & m32) + (h2 >> np.uint64(32))).astype(np.int64) - (np.int64(1) << np.int64(33))
+    k = (np.sqrt(3.0) / 4294967296.0 * 12.0 / np.sqrt(1.0 + np.arange(feat_dim, dtype=np.float64))).astype(np.float32)
+    return s.astype(np.float32) * k[None, :]
+
+
 def _trunc_normal(rng, shape, sigma):
     x = rng.standard_normal(shape)
     bad = np.abs(x) > 2.0
