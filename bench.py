@@ -830,7 +830,7 @@ def measure_config4(args, dev, rank, world, params, topo):
             counts = src.counts("cuda:%d" % dev.index)
             writer = kaldi_io.open_vector_writer("ark,scp:%s,%s" % (ark, scp)) if rank == 0 else None
             try:
-                model._run_extraction_job(src, counts, writer, engine, dev.index, 25, None, t0, t0)
+                model._run_extraction_job(src, counts, writer, engine, dev.index, 25, None, time.time(), time.time())
             finally:
                 if writer is not None:
                     writer.close()

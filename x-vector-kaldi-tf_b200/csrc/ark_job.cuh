@@ -639,7 +639,7 @@ int xv_synth_mfcc(int device, float* out_dev, const int64_t* utt_id_host, const 
   for (int d = 0; d < feat_dim; ++d)
     a.k[d] = float(std::sqrt(3.0) / 4294967296.0 * 12.0 / std::sqrt(1.0 + double(d)));
   if (a.total_rows > 0) {
-    synth::synth_mfcc_kernel<<<unsigned((a.total_rows + 255) / 256), 256, 0, stream>>>(a);
+    synth::synth_mfcc_kernel<<<unsigned((a.total_rows * feat_dim + 255) / 256), 256, 0, stream>>>(a);
     XV_CUDA(cudaGetLastError());
   }
   XV_CUDA(cudaFreeAsync(scratch, stream));

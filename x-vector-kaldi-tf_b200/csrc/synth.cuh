@@ -30,8 +30,10 @@ struct Args {
 };
 
 __global__ void __launch_bounds__(256) synth_mfcc_kernel(const Args a) {
-  const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (row >= a.total_rows) return;
+  const int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;      // one value per thread: coalesced stores
+  if (e >= a.total_rows * a.feat_dim) return;
+  const int64_t row = e / a.feat_dim;
+  const int d = int(e - row * a.feat_dim);
   int lo = 0, hi = a.n_utt;                    // the utterance holding this row: last u with row_start[u] <= row
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
@@ -39,12 +41,9 @@ __global__ void __launch_bounds__(256) synth_mfcc_kernel(const Args a) {
   }
   const uint64_t frame = uint64_t(row - __ldg(a.row_start + lo));
   const uint64_t base = a.seed ^ (((uint64_t(__ldg(a.utt_id + lo)) << 20) | frame) * 0x9E3779B97F4A7C15ull);
-  float* dst = a.out + row * a.feat_dim;
-  for (int d = 0; d < a.feat_dim; ++d) {
-    const uint64_t h1 = splitmix64(base + uint64_t(d)), h2 = splitmix64(h1);
-    const int64_t s = int64_t((h1 & 0xffffffffull) + (h1 >> 32) + (h2 & 0xffffffffull) + (h2 >> 32)) - (int64_t(1) << 33);
-    dst[d] = __fmul_rn(__ll2float_rn(s), a.k[d]);
-  }
+  const uint64_t h1 = splitmix64(base + uint64_t(d)), h2 = splitmix64(h1);
+  const int64_t s = int64_t((h1 & 0xffffffffull) + (h1 >> 32) + (h2 & 0xffffffffull) + (h2 >> 32)) - (int64_t(1) << 33);
+  a.out[e] = __fmul_rn(__ll2float_rn(s), a.k[d]);
 }
 
 }  // namespace synth
