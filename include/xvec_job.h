@@ -119,10 +119,11 @@ int xv_synth_mfcc(int device, float* out_dev, const int64_t* utt_id_host, const 
                   uint64_t seed, void* stream);
 
 /* xv_submit_host_utts (include/xvec.h) for features that are ALREADY on the device (they must stay untouched until the
- * ticket is collected: an fp16 range rescue re-runs the submission from them). */
+ * ticket is collected: an fp16 range rescue re-runs the submission from them).  ready_event: a cudaEvent_t recorded behind
+ * the work that produces the features on another stream (the submission waits for it on the device), or NULL. */
 int xv_submit_dev_utts(xv_model* m, const float* feats_dev, const int32_t* seg_len_host, int32_t n_seg,
                        const int32_t* utt_first_seg_host, const int64_t* utt_dst_row_host, int32_t n_utt, float* out_dev,
-                       float* out_host, int32_t* ticket);
+                       float* out_host, void* ready_event, int32_t* ticket);
 
 #ifdef __cplusplus
 }

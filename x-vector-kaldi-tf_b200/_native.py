@@ -190,7 +190,7 @@ def load_library():
     lib.xv_scp_format.restype = I64
     lib.xv_synth_mfcc.argtypes = [ctypes.c_int, P, P, P, I32, I32, ctypes.c_uint64, P]
     lib.xv_synth_mfcc.restype = ctypes.c_int
-    lib.xv_submit_dev_utts.argtypes = [P, P, P, I32, P, P, I32, P, P, ctypes.POINTER(I32)]
+    lib.xv_submit_dev_utts.argtypes = [P, P, P, I32, P, P, I32, P, P, P, ctypes.POINTER(I32)]
     lib.xv_submit_dev_utts.restype = ctypes.c_int
     # training step (include/xvec_train.h)
     F32, F64 = ctypes.c_float, ctypes.c_double
@@ -596,8 +596,9 @@ class XvecEngine:
                                                   optr, ws.data_ptr(), ws.numel(), s.cuda_stream))
         return n_utt
 
-    def submit_dev_utts(self, feats_dev, seg_lens, utt_first_seg=None, dst_rows=None, out_dev=None, out_host=None):
-        """``submit_host_utts`` for features already on the device (a float32 CUDA tensor that stays untouched until collected)."""
+    def submit_dev_utts(self, feats_dev, seg_lens, utt_first_seg=None, dst_rows=None, out_dev=None, out_host=None, ready_event=None):
+        """``submit_host_utts`` for features already on the device (a float32 CUDA tensor that stays untouched until collected).
+        ``ready_event``: a ``torch.cuda.Event`` recorded behind the work that produces them on another stream."""
         lens = np.ascontiguousarray(seg_lens, dtype=np.int32)
         n_seg = int(lens.shape[0])
         assert feats_dev.is_cuda and feats_dev.is_contiguous() and feats_dev.shape[0] >= int(lens.sum())
@@ -611,7 +612,8 @@ class XvecEngine:
         _check(self.lib, self.lib.xv_submit_dev_utts(self.handle, feats_dev.data_ptr(), lens.ctypes.data_as(ctypes.c_void_p), n_seg,
                                                      None if first is None else first.ctypes.data_as(ctypes.c_void_p),
                                                      None if dst is None else dst.ctypes.data_as(ctypes.c_void_p), n_utt,
-                                                     optr, hptr, ctypes.byref(ticket)))
+                                                     optr, hptr, None if ready_event is None else ctypes.c_void_p(ready_event.cuda_event),
+                                                     ctypes.byref(ticket)))
         return int(ticket.value)
 
     def submit_host_utts(self, feats_host, seg_lens, utt_first_seg=None, dst_rows=None, out_dev=None, out_host=None):

@@ -152,6 +152,35 @@ def shared_output_spec(output_stream, total_bytes):
     return None
 
 
+def populate_pages(mapped, offset, length):
+    """Fault in the pages of ``mapped[offset : offset + length]`` (a writable mmap of the output file) from a background
+    thread, so that the formatter's first touch of a page is not a page fault on the job's critical path
+    (MADV_POPULATE_WRITE, Linux >= 5.14; silently nothing where it is not supported)."""
+    import ctypes
+    import mmap
+    import threading
+    if length <= 0:
+        return None
+    try:
+        libc = ctypes.CDLL(None, use_errno=True)
+        base = ctypes.addressof(ctypes.c_char.from_buffer(mapped))
+    except (OSError, TypeError, ValueError):
+        return None
+    page = mmap.PAGESIZE
+    lo = (base + offset) // page * page
+    hi = base + offset + length
+
+    def run():
+        step = 8 << 20
+        for a in range(lo, hi, step):
+            if libc.madvise(ctypes.c_void_p(a), ctypes.c_size_t(min(step, hi - a)), 23) != 0:      # MADV_POPULATE_WRITE
+                return
+
+    t = threading.Thread(target=run, name="xvec-populate", daemon=True)
+    t.start()
+    return t
+
+
 def finish_shared_output(output_stream, spec, total_bytes, scp_parts):
     """Rank 0, after every rank has written its byte range: move the writer behind the job's entries and append the scp
     lines the ranks produced (in rank order)."""
@@ -167,7 +196,7 @@ def finish_shared_output(output_stream, spec, total_bytes, scp_parts):
 
 
 class _SynthBatch(object):
-    __slots__ = ("slot", "n_seg", "n_utt", "n_rows", "feats", "seg_len", "utt_first_seg", "utt_dst_row", "first_ok_index")
+    __slots__ = ("slot", "n_seg", "n_utt", "n_rows", "feats", "seg_len", "utt_first_seg", "utt_dst_row", "first_ok_index", "ready_event")
 
 
 class SyntheticSource(object):
@@ -237,8 +266,10 @@ class SyntheticSource(object):
         b.utt_dst_row = self.base + np.arange(u0, u1, dtype=np.int64)
         b.first_ok_index = u0
         b.feats = self.bufs[b.slot][:b.n_rows]
+        import torch
         synth_mfcc(self.device, self.bufs[b.slot], self.ids[u0:u1], b.seg_len, self.seed, stream=self.stream)
-        self.stream.synchronize()                     # the submission runs on the engine's own stream
+        b.ready_event = torch.cuda.Event()            # the submission runs on the engine's own stream: it waits for this on the device
+        b.ready_event.record(self.stream)
         self.next_batch += 1
         return b
 

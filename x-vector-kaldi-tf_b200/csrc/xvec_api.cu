@@ -1328,8 +1328,12 @@ int xv_submit_host_utts(xv_model* m, const float* feats_host, const int32_t* seg
 
 int xv_submit_dev_utts(xv_model* m, const float* feats_dev, const int32_t* seg_len_host, int32_t n_seg,
                        const int32_t* utt_first_seg_host, const int64_t* utt_dst_row_host, int32_t n_utt, float* out_dev,
-                       float* out_host, int32_t* ticket) {
-  if (!feats_dev) return fail(XV_EINVAL, "null argument");
+                       float* out_host, void* ready_event, int32_t* ticket) {
+  if (!m || !feats_dev) return fail(XV_EINVAL, "null argument");
+  if (ready_event) {                        // the producer of the features runs on another stream: order this slot's stream behind it
+    XV_CUDA(cudaSetDevice(m->device));
+    XV_CUDA(cudaStreamWaitEvent(m->slots[m->slot_next].stream, static_cast<cudaEvent_t>(ready_event), 0));
+  }
   if (!out_dev && !out_host) return fail(XV_EINVAL, "xv_submit_dev_utts: no destination (out_dev and out_host are both null)");
   UttOut u;
   u.first_seg_host = utt_first_seg_host;

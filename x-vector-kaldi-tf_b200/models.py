@@ -686,7 +686,7 @@ class Model(object):
         stats = dict(pre_s=t_job - start_time, index_s=time.time() - t_job, reader_wait_s=0.0, submit_s=0.0, collect_s=0.0, write_s=0.0,
                      tail_s=0.0, batches=0)
         self.last_job_stats = stats                  # where the wall time of the last native job went (bench / diagnostics)
-        peer, shared_fd, shared_map, shared_view = None, None, None, None
+        peer, shared_fd, shared_map, shared_view, populate = None, None, None, None, None
         try:
             if logger is not None:
                 for key, reason, rows in reader.failures():
@@ -731,6 +731,7 @@ class Model(object):
                     map_from = ark_base // mmap.ALLOCATIONGRANULARITY * mmap.ALLOCATIONGRANULARITY
                     shared_map = mmap.mmap(shared_fd, ark_base - map_from + my_bytes, offset=map_from)
                     shared_view = np.frombuffer(shared_map, dtype=np.uint8)[ark_base - map_from:]
+                    populate = ark_job.populate_pages(shared_map, ark_base - map_from, my_bytes)      # page faults off the critical path
             reader.start(base if mode == "peer" else 0)
             host_rows = [None, None]                     # page-locked [n_utt, emb_dim] per submission slot
             local = [] if mode == "host_gather" else None
@@ -750,10 +751,12 @@ class Model(object):
                             host_rows[k & 1] = _pinned_rows(max(2 * b.n_utt, 1024), emb_dim, on_gpu)
                         out_host = host_rows[k & 1][:b.n_utt]
                     t0 = time.time()
-                    submit = engine.submit_dev_utts if feats_on_device else engine.submit_host_utts
-                    ticket = submit(b.feats, b.seg_len, utt_first_seg=b.utt_first_seg,
-                                    dst_rows=b.utt_dst_row if mode == "peer" else None,
-                                    out_dev=peer if mode == "peer" else None, out_host=out_host)
+                    kw = dict(utt_first_seg=b.utt_first_seg, dst_rows=b.utt_dst_row if mode == "peer" else None,
+                              out_dev=peer if mode == "peer" else None, out_host=out_host)
+                    if feats_on_device:
+                        ticket = engine.submit_dev_utts(b.feats, b.seg_len, ready_event=getattr(b, "ready_event", None), **kw)
+                    else:
+                        ticket = engine.submit_host_utts(b.feats, b.seg_len, **kw)
                     total_gpu_waiting += time.time() - t0
                     stats["submit_s"] += time.time() - t0
                     submitted = (ticket, b, out_host)
@@ -827,6 +830,8 @@ class Model(object):
             if peer is not None:
                 peer.close()
             shared_view = None
+            if populate is not None:
+                populate.join()
             if shared_map is not None:
                 try:
                     shared_map.close()
