@@ -629,9 +629,17 @@ def measure_frontend(args, eng, dev, stream, flush, rank, peaks):
                 cpu_baseline=cpu)
 
 
-def _scratch_dir():
-    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+def _scratch_dir(need_bytes=16 << 30):
+    """Scratch for the product-path blocks: /dev/shm when it has room (the input is meant to sit in the page cache), else the
+    default temporary directory."""
+    import shutil
     import tempfile
+    base = None
+    try:
+        if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) and shutil.disk_usage("/dev/shm").free > need_bytes:
+            base = "/dev/shm"
+    except OSError:
+        base = None
     return tempfile.mkdtemp(prefix="xvec_product_", dir=base)
 
 
