@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Product-path check on N GPUs of one box: extract_embedding.py (ark in, ark,scp out) single-process vs
-`torchrun --nproc-per-node N` must give byte-identical arks (utterance sharding + one NCCL gather to rank 0).
+"""Product-path check on N GPUs of one box: extract_embedding.py (ark file in) single-process vs `torchrun --nproc-per-node N` must
+give byte-identical outputs -- with `ark,scp:` files (every rank writes its byte range of the one ark, rank 0 the scp) and with a
+pipe wspecifier (rows to rank 0's peer-memory table over NVLink, rank 0 writes the stream).
 usage: python tools/multi_gpu_extract_check.py [N] [n_utts]"""
 import os
 import subprocess
@@ -48,4 +49,16 @@ for tag, launcher in (("1gpu", [sys.executable]),
     print("%s: %d vectors, %d frames, wall %.2f s (incl. process start)" % (tag, n_out, int(lens.sum()), dt), flush=True)
 a, b = outs["1gpu"], outs["%dgpu" % n_gpus]
 assert a == b, "arks differ between 1 and %d GPUs" % n_gpus
-print("byte-identical ark from 1 and %d GPUs (%d bytes)" % (n_gpus, len(a)))
+assert open(os.path.join(tmp, "1gpu.scp")).read().replace("1gpu.ark", "X") == \
+    open(os.path.join(tmp, "%dgpu.scp" % n_gpus)).read().replace("%dgpu.ark" % n_gpus, "X"), "scp files differ"
+print("byte-identical ark + scp from 1 and %d GPUs (%d bytes)" % (n_gpus, len(a)))
+# pipe output: the stream is written by rank 0 from its peer-memory result table
+piped = os.path.join(tmp, "piped.ark")
+r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n_gpus), "--master-addr",
+                    "127.0.0.1", "--master-port", "29612", cli] + common + ["--vector-wspecifier=| cat > %s" % piped],
+                   capture_output=True, text=True)
+if r.returncode != 0:
+    print(r.stderr[-3000:])
+    raise SystemExit("pipe-output run failed")
+assert open(piped, "rb").read() == a, "pipe output differs"
+print("byte-identical ark through a pipe wspecifier on %d GPUs (peer-memory table)" % n_gpus)
