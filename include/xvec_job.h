@@ -47,7 +47,9 @@ typedef struct xv_ark_reader_opts {
   int64_t byte_begin;       /* stripe [byte_begin, byte_end) of the file; byte_end < 0 = end of file               */
   int64_t byte_end;
   int32_t begin_is_boundary;/* 1: byte_begin is the first byte of an entry (start of the stream); 0: resynchronise  */
-  int32_t reserved;
+  int32_t feats_f16;        /* 1: batches hold the rows rounded to float16 (IEEE RN-even, what the device's pack kernel does
+                               to a feature first anyway: bit-identical x-vectors, half the pinned-buffer / PCIe bytes);
+                               consume them with xv_submit_host_utts_f16                                              */
 } xv_ark_reader_opts;
 
 /* Why an utterance produced no x-vector (the reference's warnings, models.py:378-387). */
@@ -70,9 +72,10 @@ typedef struct xv_ark_index_info {
 typedef struct xv_ark_batch {
   int32_t slot;                     /* to hand back with xv_ark_reader_release                                       */
   int32_t n_seg, n_utt;             /* n_utt == 0: end of the stripe                                                 */
-  int32_t reserved;
+  int32_t feats_f16;                /* 1: feats points at float16 values (xv_ark_reader_opts.feats_f16)              */
   int64_t n_rows;
-  const float* feats;               /* [n_rows, feat_dim] page-locked: the feats_host of xv_submit_host_utts         */
+  const float* feats;               /* [n_rows, feat_dim] page-locked: the feats_host of xv_submit_host_utts (float32, or
+                                       float16 bit patterns for xv_submit_host_utts_f16)                             */
   const int32_t* seg_len;           /* [n_seg]                                                                       */
   const int32_t* utt_first_seg;     /* [n_utt + 1]                                                                   */
   const int64_t* utt_dst_row;       /* [n_utt] = dst_row_base + index of the utterance among the stripe's ok ones     */
@@ -110,6 +113,18 @@ int64_t xv_vec_ark_format(const char* key_blob, const int64_t* key_off, int64_t 
  * Returns the bytes written (out_cap >= sum(key_len) + n * (strlen(ark_name) + 24) is always enough) or < 0. */
 int64_t xv_scp_format(const char* key_blob, const int64_t* key_off, int64_t n, const char* ark_name, int64_t base,
                       const int64_t* marker_off, char* out, int64_t out_cap);
+
+/* xv_submit_host_utts (include/xvec.h) for feature rows that are ALREADY rounded to float16 on the host (a reader opened with
+ * feats_f16, or xv_convert_f32_to_f16_host): feats_host_f16 holds [total_frames, feat_dim] float16 bit patterns.  Results are
+ * bit-identical to the float32 call -- the device rounds features to fp16 before anything else -- except with the
+ * split-precision option, which needs the float32 values (XV_EINVAL). */
+int xv_submit_host_utts_f16(xv_model* m, const uint16_t* feats_host_f16, const int32_t* seg_len_host, int32_t n_seg,
+                            const int32_t* utt_first_seg_host, const int64_t* utt_dst_row_host, int32_t n_utt, float* out_dev,
+                            float* out_host, int32_t* ticket);
+/* float32 -> float16, IEEE round-to-nearest-even, on the host (F16C + AVX2 with non-temporal stores when the CPU has them;
+ * the _scalar form is the portable routine both are tested against). */
+void xv_convert_f32_to_f16_host(const float* src, uint16_t* dst, size_t n);
+void xv_convert_f32_to_f16_host_scalar(const float* src, uint16_t* dst, size_t n);
 
 /* Synthetic workload (bench / scale tests only; SURVEY 8d, BASELINE configs[3]): the MFCC rows of n_utt utterances generated
  * on the device from (seed, utterance id, frame, coefficient) -- out_dev [sum(len), feat_dim] fp32, utterances concatenated

@@ -415,3 +415,32 @@ def test_every_rank_writes_its_byte_range_of_the_one_output_file(T_model_dir, tm
     assert open(names["plain"], "rb").read() == body[pre:len(body) - (len("postscript") + 11 + 2048)]
     got = dict(kaldi_io.read_vec_flt_scp(names["scp"]))
     assert len(got) > 10 and np.array_equal(got["postscript"], np.ones(512, np.float32))
+
+
+def test_reader_can_round_rows_to_float16_on_the_way_into_the_batches(tmp_path):
+    # feats_f16: IEEE round-to-nearest-even, the bits numpy's float16 cast gives -- for float32 and float64 payloads, any
+    # alignment of the destination rows, vector and scalar converter alike
+    path = str(tmp_path / "feats.ark")
+    utts = _random_ark(path, 31, 200, lo=0, hi=700, double_every=5)
+    ok, _ = _expected(utts, 25, 300)
+    r = _native.ArkReader(path, 23, 25, 300, 9000, n_threads=3, pinned=False, feats_f16=True)
+    r.index()
+    got, _ = _drain(r)
+    assert len(got) == len(ok) and got[0][0].dtype == np.float16
+    for (rows, segs, _), (key, m, want_segs) in zip(got, ok):
+        assert segs == want_segs
+        assert np.array_equal(rows.view(np.uint16), m[:sum(segs)].astype(np.float16).view(np.uint16)), key
+    r.close()
+    lib = _native.load_library()
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.standard_normal(40001).astype(np.float32) * 60,
+                        np.array([0, -0.0, 65504, 65519.9, 65520, 1e9, -1e9, np.inf, 6.1e-5, 6e-8, 2.9802322e-8, 3e-8, 1e-10], np.float32),
+                        rng.integers(0, 2 ** 32, 100000, dtype=np.uint64).astype(np.uint32).view(np.float32)])
+    x = x[~np.isnan(x)]
+    with np.errstate(over="ignore"):
+        want = x.astype(np.float16).view(np.uint16)
+    for fn in (lib.xv_convert_f32_to_f16_host, lib.xv_convert_f32_to_f16_host_scalar):
+        for off in (0, 1, 5):
+            out = np.zeros(len(x) + 16, np.uint16)
+            fn(x.ctypes.data, out.ctypes.data + 2 * off, len(x))
+            assert np.array_equal(out[off:off + len(x)], want)

@@ -356,6 +356,13 @@ def test_native_ark_file_job_is_byte_identical_to_the_stream_path(tmp_path, monk
     with open(path, "rb") as f:
         model.make_embedding(f, got, model_dir, 25, 300, True, None)
     assert len(want.getvalue()) > 0 and got.getvalue() == want.getvalue()
+    assert model.last_job_stats["output"] == "local"
+    monkeypatch.setenv("XVEC_FEED_F16", "0")                     # float32 rows through the page-locked batches: the same bytes
+    got32 = io.BytesIO()
+    with open(path, "rb") as f:
+        model.make_embedding(f, got32, model_dir, 25, 300, True, None)
+    assert got32.getvalue() == want.getvalue()
+    monkeypatch.delenv("XVEC_FEED_F16")
     a, s_ = str(tmp_path / "x.ark"), str(tmp_path / "x.scp")
     with kaldi_io.open_vector_writer("ark,scp:%s,%s" % (a, s_)) as w:
         model.make_embedding(str(path), w, model_dir, 25, 300, True, None)

@@ -51,7 +51,7 @@ class XvArkReaderOpts(ctypes.Structure):
     _fields_ = [("feat_dim", ctypes.c_int32), ("min_chunk_size", ctypes.c_int32), ("chunk_size", ctypes.c_int32),
                 ("n_threads", ctypes.c_int32), ("n_slots", ctypes.c_int32), ("pinned", ctypes.c_int32),
                 ("batch_frames", ctypes.c_int64), ("byte_begin", ctypes.c_int64), ("byte_end", ctypes.c_int64),
-                ("begin_is_boundary", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("begin_is_boundary", ctypes.c_int32), ("feats_f16", ctypes.c_int32)]
 
 
 class XvArkIndexInfo(ctypes.Structure):
@@ -65,7 +65,7 @@ class XvArkIndexInfo(ctypes.Structure):
 
 class XvArkBatch(ctypes.Structure):
     """xv_ark_batch (include/xvec_job.h)."""
-    _fields_ = [("slot", ctypes.c_int32), ("n_seg", ctypes.c_int32), ("n_utt", ctypes.c_int32), ("reserved", ctypes.c_int32),
+    _fields_ = [("slot", ctypes.c_int32), ("n_seg", ctypes.c_int32), ("n_utt", ctypes.c_int32), ("feats_f16", ctypes.c_int32),
                 ("n_rows", ctypes.c_int64), ("feats", ctypes.c_void_p), ("seg_len", ctypes.c_void_p),
                 ("utt_first_seg", ctypes.c_void_p), ("utt_dst_row", ctypes.c_void_p), ("first_ok_index", ctypes.c_int64)]
 
@@ -79,7 +79,7 @@ class XvecError(RuntimeError):
 def build_library(verbose=False):
     """Compile csrc/xvec_api.cu for sm_100a into the in-tree shared library (nvcc cross-compiles
     without a GPU).  Skips the compile when the library is newer than every source."""
-    sources = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    sources = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".cpp"))]
     sources.append(os.path.join(REPO_ROOT, "include", "xvec.h"))
     sources.append(os.path.join(REPO_ROOT, "include", "xvec_train.h"))
     sources.append(os.path.join(REPO_ROOT, "include", "xvec_frontend.h"))
@@ -87,7 +87,8 @@ def build_library(verbose=False):
     if os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in sources):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH, os.path.join(CSRC, "xvec_api.cu")]
+    # f16_convert.cpp is plain C++ (AVX2 / F16C intrinsics behind a runtime check): nvcc hands it to the host compiler as it is
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH, os.path.join(CSRC, "xvec_api.cu"), os.path.join(CSRC, "f16_convert.cpp")]
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     subprocess.run(cmd, check=True)
@@ -129,6 +130,12 @@ def load_library():
     lib.xv_forward_utts.restype = ctypes.c_int
     lib.xv_submit_host_utts.argtypes = [P, P, P, I32, P, P, I32, P, P, ctypes.POINTER(I32)]
     lib.xv_submit_host_utts.restype = ctypes.c_int
+    lib.xv_submit_host_utts_f16.argtypes = [P, P, P, I32, P, P, I32, P, P, ctypes.POINTER(I32)]
+    lib.xv_submit_host_utts_f16.restype = ctypes.c_int
+    lib.xv_convert_f32_to_f16_host.argtypes = [P, P, SZ]
+    lib.xv_convert_f32_to_f16_host.restype = None
+    lib.xv_convert_f32_to_f16_host_scalar.argtypes = [P, P, SZ]
+    lib.xv_convert_f32_to_f16_host_scalar.restype = None
     lib.xv_peer_alloc.argtypes = [ctypes.c_int, SZ, ctypes.POINTER(P), P]
     lib.xv_peer_alloc.restype = ctypes.c_int
     lib.xv_peer_open.argtypes = [ctypes.c_int, P, ctypes.POINTER(P)]
@@ -244,13 +251,13 @@ def load_library():
 EXPORTED_SYMBOLS = ["xv_create", "xv_destroy", "xv_set_param", "xv_workspace_bytes", "xv_forward",
                     "xv_forward_layers", "xv_extract_host", "xv_submit_host", "xv_collect", "xv_check_overflow", "xv_rescue_overflow", "xv_last_launch_count",
                     "xv_last_kernel_ms", "xv_set_option", "xv_last_error", "xv_version", "xv_ark_scan",
-                    "xv_forward_utts", "xv_submit_host_utts", "xv_peer_alloc", "xv_peer_open", "xv_peer_close", "xv_peer_free",
+                    "xv_forward_utts", "xv_submit_host_utts", "xv_submit_host_utts_f16", "xv_peer_alloc", "xv_peer_open", "xv_peer_close", "xv_peer_free",
                     "xv_peer_read", "xv_abi_version", "xv_topology_size",
                     # include/xvec_job.h
                     "xv_ark_reader_open", "xv_ark_reader_index", "xv_ark_reader_set_first", "xv_ark_reader_keys",
                     "xv_ark_reader_failures", "xv_ark_reader_start", "xv_ark_reader_next", "xv_ark_reader_release",
                     "xv_ark_reader_close", "xv_vec_ark_bytes", "xv_vec_ark_format", "xv_scp_format", "xv_synth_mfcc",
-                    "xv_submit_dev_utts",
+                    "xv_submit_dev_utts", "xv_convert_f32_to_f16_host", "xv_convert_f32_to_f16_host_scalar",
                     # include/xvec_train.h
                     "xv_train_create", "xv_train_destroy", "xv_train_size", "xv_train_span", "xv_train_upload",
                     "xv_train_download", "xv_train_set_step", "xv_train_get_step", "xv_train_forward_backward", "xv_train_eval",
@@ -303,11 +310,11 @@ class ArkReader(object):
     with ``pinned=False``."""
 
     def __init__(self, path, feat_dim, min_chunk_size, chunk_size, batch_frames, byte_begin=0, byte_end=-1,
-                 begin_is_boundary=True, n_threads=4, n_slots=3, pinned=True):
+                 begin_is_boundary=True, n_threads=4, n_slots=3, pinned=True, feats_f16=False):
         self.lib = load_library()
         opts = XvArkReaderOpts(int(feat_dim), int(min_chunk_size), int(chunk_size), int(n_threads), int(n_slots),
                                1 if pinned else 0, int(batch_frames), int(byte_begin), int(byte_end),
-                               1 if begin_is_boundary else 0, 0)
+                               1 if begin_is_boundary else 0, 1 if feats_f16 else 0)
         self.feat_dim = int(feat_dim)
         self.handle = ctypes.c_void_p()
         _check(self.lib, self.lib.xv_ark_reader_open(ctypes.byref(self.handle), os.fsencode(path), ctypes.byref(opts)))
@@ -356,7 +363,10 @@ class ArkReader(object):
             return None
         out = ArkBatch()
         out.slot, out.n_seg, out.n_utt, out.n_rows, out.first_ok_index = b.slot, b.n_seg, b.n_utt, int(b.n_rows), int(b.first_ok_index)
-        out.feats = _view(b.feats, ctypes.c_float, out.n_rows * self.feat_dim, np.float32).reshape(out.n_rows, self.feat_dim)
+        if b.feats_f16:                                # rows already rounded to float16 by the reader (feats_f16)
+            out.feats = _view(b.feats, ctypes.c_uint16, out.n_rows * self.feat_dim, np.uint16).view(np.float16).reshape(out.n_rows, self.feat_dim)
+        else:
+            out.feats = _view(b.feats, ctypes.c_float, out.n_rows * self.feat_dim, np.float32).reshape(out.n_rows, self.feat_dim)
         out.seg_len = _view(b.seg_len, ctypes.c_int32, b.n_seg, np.int32)
         out.utt_first_seg = _view(b.utt_first_seg, ctypes.c_int32, b.n_utt + 1, np.int32)
         out.utt_dst_row = _view(b.utt_dst_row, ctypes.c_int64, b.n_utt, np.int64)
@@ -621,11 +631,13 @@ class XvecEngine:
         or raw address; may be peer memory) and / or to the host array ``out_host[u]``."""
         lens = np.ascontiguousarray(seg_lens, dtype=np.int32)
         n_seg = int(lens.shape[0])
+        half = False
         if hasattr(feats_host, "data_ptr"):
             assert feats_host.is_contiguous() and feats_host.shape[0] == int(lens.sum())
             fptr = feats_host.data_ptr()
         else:
-            assert feats_host.dtype == np.float32 and feats_host.flags.c_contiguous and feats_host.shape[0] == int(lens.sum())
+            half = feats_host.dtype == np.float16      # rows the reader already rounded to float16 (what the device does first anyway)
+            assert (half or feats_host.dtype == np.float32) and feats_host.flags.c_contiguous and feats_host.shape[0] == int(lens.sum())
             fptr = feats_host.ctypes.data
         first, dst, n_utt = self._utt_plan(n_seg, utt_first_seg, dst_rows)
         optr = None if out_dev is None else (out_dev if isinstance(out_dev, int) else out_dev.data_ptr())
@@ -634,7 +646,8 @@ class XvecEngine:
             assert out_host.shape[0] >= n_utt
             hptr = out_host.data_ptr() if hasattr(out_host, "data_ptr") else out_host.ctypes.data
         ticket = ctypes.c_int32(-1)
-        _check(self.lib, self.lib.xv_submit_host_utts(self.handle, fptr, lens.ctypes.data_as(ctypes.c_void_p), n_seg,
+        fn = self.lib.xv_submit_host_utts_f16 if half else self.lib.xv_submit_host_utts
+        _check(self.lib, fn(self.handle, fptr, lens.ctypes.data_as(ctypes.c_void_p), n_seg,
                                                       None if first is None else first.ctypes.data_as(ctypes.c_void_p),
                                                       None if dst is None else dst.ctypes.data_as(ctypes.c_void_p), n_utt,
                                                       optr, hptr, ctypes.byref(ticket)))

@@ -41,7 +41,7 @@ def stripe_bounds(start, size, rank, world):
 
 
 def open_striped_reader(path, start, feat_dim, min_chunk_size, chunk_size, batch_frames, device="cpu", pinned=True,
-                        n_threads=None, n_slots=3, rank=None, world=None):
+                        n_threads=None, n_slots=3, rank=None, world=None, feats_f16=False):
     """Index this rank's stripe of ``path`` (entries from byte ``start`` on) and agree the stripe boundaries with the
     other ranks.  Returns ``(reader, counts)`` with ``counts`` = [world, 6] int64 rows
     (n_entries, n_ok, n_fail, rows_used, stopped_at, key_bytes) of every rank -- or ``(None, counts)`` when some stripe holds an entry
@@ -55,7 +55,7 @@ def open_striped_reader(path, start, feat_dim, min_chunk_size, chunk_size, batch
         n_threads = int(os.environ.get("XVEC_READER_THREADS", str(max(2, min(4, (os.cpu_count() or 4) // max(world, 1))))))
     reader = ArkReader(path, feat_dim, min_chunk_size, chunk_size, batch_frames, byte_begin=begin,
                        byte_end=(-1 if rank == world - 1 else end), begin_is_boundary=(rank == 0), n_threads=n_threads,
-                       n_slots=n_slots, pinned=pinned)
+                       n_slots=n_slots, pinned=pinned, feats_f16=feats_f16)
     try:
         info = reader.index()
         if world > 1:

@@ -15,6 +15,8 @@
 #include "../../include/xvec_job.h"
 #include "synth.cuh"
 
+extern "C" void xv_convert_f32_to_f16_host(const float* src, uint16_t* dst, size_t n);     // f16_convert.cpp
+
 namespace arkjob {
 
 struct Entry {
@@ -345,6 +347,7 @@ int scan_stripe(xv_ark_reader* r, int64_t from, bool first_is_candidate) {
 
 void worker_main(xv_ark_reader* r) {
   std::vector<double> tmp;
+  std::vector<float> ftmp;
   for (;;) {
     Task t;
     {
@@ -359,23 +362,43 @@ void worker_main(xv_ark_reader* r) {
     }
     const Batch& b = r->batches[t.batch];
     float* base = r->slot_buf[t.batch % r->slot_buf.size()];
+    const bool f16 = r->o.feats_f16 != 0;
     std::string err;
     for (int64_t u = t.u0; u < t.u1 && err.empty(); ++u) {
       const Entry& e = r->entries[r->ok[u]];
-      float* dst = base + r->row_in_batch[u] * r->o.feat_dim;
       const int64_t n_val = int64_t(e.used) * r->o.feat_dim;
-      uint8_t* p;
-      int64_t need;
-      if (e.elem == 4) { p = reinterpret_cast<uint8_t*>(dst); need = n_val * 4; }
-      else { tmp.resize(size_t(n_val)); p = reinterpret_cast<uint8_t*>(tmp.data()); need = n_val * 8; }
-      int64_t got = 0;
-      while (got < need) {
-        const ssize_t k = pread(r->fd, p + got, size_t(need - got), off_t(e.payload_off + got));
-        if (k <= 0) { err = "truncated matrix payload at byte " + std::to_string(e.payload_off + got); break; }
-        got += k;
+      const int64_t first = r->row_in_batch[u] * r->o.feat_dim;
+      auto read_all = [&](uint8_t* p, int64_t need, int64_t file_off) {
+        int64_t got = 0;
+        while (got < need) {
+          const ssize_t k = pread(r->fd, p + got, size_t(need - got), off_t(file_off + got));
+          if (k <= 0) { err = "truncated matrix payload at byte " + std::to_string(file_off + got); return false; }
+          got += k;
+        }
+        return true;
+      };
+      if (e.elem == 4 && !f16) {                       // float32 payload -> float32 batch: straight into the page-locked buffer
+        read_all(reinterpret_cast<uint8_t*>(base + first), n_val * 4, e.payload_off);
+      } else {
+        // through a cache-resident bounce buffer: narrow float64 payloads and / or round to float16 on the way
+        constexpr int64_t CHUNK = 16384;               // values per step (64 / 128 KB of payload)
+        if (int64_t(tmp.size()) < CHUNK) { tmp.resize(size_t(CHUNK)); ftmp.resize(size_t(CHUNK)); }
+        uint16_t* hbase = reinterpret_cast<uint16_t*>(base);
+        for (int64_t v0 = 0; v0 < n_val && err.empty(); v0 += CHUNK) {
+          const int64_t n = std::min(CHUNK, n_val - v0);
+          const float* src;
+          if (e.elem == 8) {
+            if (!read_all(reinterpret_cast<uint8_t*>(tmp.data()), n * 8, e.payload_off + v0 * 8)) break;
+            for (int64_t i = 0; i < n; ++i) ftmp[size_t(i)] = float(tmp[size_t(i)]);
+            src = ftmp.data();
+          } else {
+            if (!read_all(reinterpret_cast<uint8_t*>(ftmp.data()), n * 4, e.payload_off + v0 * 4)) break;
+            src = ftmp.data();
+          }
+          if (f16) xv_convert_f32_to_f16_host(src, hbase + first + v0, size_t(n));
+          else memcpy(base + first + v0, src, size_t(n) * 4);
+        }
       }
-      if (e.elem == 8 && err.empty())
-        for (int64_t i = 0; i < n_val; ++i) dst[i] = float(tmp[size_t(i)]);
     }
     (void)b;
     {
@@ -527,7 +550,7 @@ int xv_ark_reader_start(xv_ark_reader* r, int64_t dst_row_base) {
   r->slot_buf.assign(size_t(n_slots), nullptr);
   r->slot_bytes.assign(size_t(n_slots), 0);
   for (int s = 0; s < n_slots; ++s) {
-    const size_t bytes = size_t(rows) * r->o.feat_dim * 4;
+    const size_t bytes = size_t(rows) * r->o.feat_dim * (r->o.feats_f16 ? 2 : 4);
     r->slot_bytes[s] = bytes;
     if (r->o.pinned) {
       r->slot_buf[s] = arkjob::pinned_pool().take(bytes);
@@ -561,6 +584,7 @@ int xv_ark_reader_next(xv_ark_reader* r, xv_ark_batch* batch) {
   batch->slot = int32_t(bi % int64_t(r->slot_buf.size()));
   batch->n_seg = b.n_seg;
   batch->n_utt = int32_t(b.u1 - b.u0);
+  batch->feats_f16 = r->o.feats_f16 ? 1 : 0;
   batch->n_rows = b.n_rows;
   batch->feats = r->slot_buf[batch->slot];
   batch->seg_len = r->seg_len_all.data() + b.seg0;

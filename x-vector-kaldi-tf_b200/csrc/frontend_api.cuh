@@ -207,6 +207,7 @@ int xv_submit_host_raw(xv_model* m, const float* feats_host, const float* vad_ho
   rd.utt = false; rd.has_first = rd.has_dst = false; rd.n_utt = 0; rd.out_dev = nullptr;
   rd.host_out = emb_host;
   rd.feats_ext = nullptr;
+  rd.feats_f16 = false;
   rc = enqueue_slot(m, si);
   if (rc != XV_OK) return rc;
   m->last_launches += fe_launches;

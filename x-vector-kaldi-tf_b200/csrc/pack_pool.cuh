@@ -42,6 +42,8 @@ struct PackArgs {
   uint32_t* counters;        // [n_counters] zeroed here for embed_fc_kernel
   int32_t n_counters;
   int32_t split;             // 1: rows are [hi (k0_pad) | lo (k0_pad)], x = hi + lo (split-precision model)
+  int32_t feats_f16;         // 1: `feats` points at float16 values (rounded on the host, xv_submit_host_utts_f16): widening them
+                             //    and rounding again below gives back the same bits
 };
 
 // One CTA per aligned 32-row block.  The block's feature rows (plus the first layer's context) are
@@ -73,8 +75,13 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_im2col_kernel(const PackArg
   // stage frames t0-halo .. t0+31+halo: staged float i is feats[(fs + t0 - halo) * D + i] when its frame exists
   const int n_stage = (PACK_ROWS_PER_BLOCK + 2 * halo) * D;
   const int lo = max(0, halo - t0) * D, hi = min(PACK_ROWS_PER_BLOCK + 2 * halo, len - t0 + halo) * D;
-  const float* src0 = a.feats + (int64_t(bi.x) - halo) * D;
-  for (int i = threadIdx.x; i < n_stage; i += PACK_THREADS) s_feat[i] = (i >= lo && i < hi) ? __ldg(src0 + i) : 0.f;
+  if (a.feats_f16) {
+    const __half* src0 = reinterpret_cast<const __half*>(a.feats) + (int64_t(bi.x) - halo) * D;
+    for (int i = threadIdx.x; i < n_stage; i += PACK_THREADS) s_feat[i] = (i >= lo && i < hi) ? __half2float(__ldg(src0 + i)) : 0.f;
+  } else {
+    const float* src0 = a.feats + (int64_t(bi.x) - halo) * D;
+    for (int i = threadIdx.x; i < n_stage; i += PACK_THREADS) s_feat[i] = (i >= lo && i < hi) ? __ldg(src0 + i) : 0.f;
+  }
   const int rows_per_pass = PACK_THREADS / pieces;                    // k0_pad <= 512 -> pieces <= 64
   const int pc = threadIdx.x % pieces, lr0 = threadIdx.x / pieces;
   int lut[8];

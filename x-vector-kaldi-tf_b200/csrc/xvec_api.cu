@@ -107,6 +107,7 @@ struct xv_model {
   int32_t* pack_lut_dev = nullptr;   // [k0_pad] spliced column -> staged feature offset (pack kernel)
   uint32_t* overflow_dev = nullptr;  // [1 + XV_HOST_SLOTS] flag words: [0] xv_forward / training, [1 + s] submission slot s
   uint32_t* cur_flag = nullptr;      // the word the kernels of the enqueue in progress report to
+  int cur_feats_f16 = 0;             // 1 while an enqueue's features are float16 values (xv_submit_host_utts_f16)
   uint32_t* overflow_host = nullptr; // pinned
   int exp_stats = 0;                 // fp16 range rescue of the pooled statistics (see apply_exponents)
   int opt_rescue = 1;                // 1: xv_collect raises exponents and re-runs a batch whose fp16 stores overflowed
@@ -143,6 +144,7 @@ struct xv_model {
       float* out_dev = nullptr;
       float* host_out = nullptr;         // emb_host / out_host of the submission (may be null)
       const float* feats_ext = nullptr;  // features the caller keeps on the device (xv_submit_dev_utts), else the slot's copy
+      bool feats_f16 = false;            // the slot's copy holds float16 values
     } redo;
     cudaEvent_t done = nullptr;          // recorded behind the submission's last copy; created with cudaEventBlockingSync so that
                                          // xv_collect SLEEPS instead of spinning (a multi-GPU job runs reader threads on those cores)
@@ -637,6 +639,7 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
     a.counters = counters;
     a.n_counters = p.n_counters;
     a.split = m->opt_split ? 1 : 0;
+    a.feats_f16 = m->cur_feats_f16;
     const int blocks = int(r_pad / xvk::PACK_ROWS_PER_BLOCK);      // >= n_seg: covers n_counters with 256 threads each
     XV_PROF();
     XV_CUDA(launch_k(pdl, xvk::pack_im2col_kernel, dim3(blocks), dim3(xvk::PACK_THREADS), 0, stream, a));
@@ -1214,6 +1217,8 @@ int enqueue_slot(xv_model* m, int si) {
   const xv_model::HostSlot::Redo& rd = sl.redo;
   const int32_t n_seg = int32_t(rd.seg_len.size());
   m->cur_flag = m->overflow_dev + 1 + si;
+  m->cur_feats_f16 = rd.feats_f16 ? 1 : 0;
+  struct Restore { xv_model* m; ~Restore() { m->cur_feats_f16 = 0; } } restore{m};
   int rc;
   if (rd.utt) {
     UttOut u;
@@ -1242,7 +1247,8 @@ int enqueue_slot(xv_model* m, int si) {
 
 // Common body of xv_submit_host / xv_submit_host_utts.
 int submit_impl(xv_model* m, const float* feats_host, const int32_t* seg_len_host, int32_t n_seg, float* emb_host,
-                const UttOut* utt_in, float* utt_host_out, int32_t* ticket, const float* feats_dev_ext = nullptr) {
+                const UttOut* utt_in, float* utt_host_out, int32_t* ticket, const float* feats_dev_ext = nullptr,
+                bool feats_f16 = false) {
   if (!m || (!feats_host && !feats_dev_ext) || !seg_len_host || !ticket) return fail(XV_EINVAL, "null argument");
   if (n_seg <= 0) return fail(XV_EINVAL, "n_seg must be >= 1");
   XV_CUDA(cudaSetDevice(m->device));
@@ -1254,7 +1260,9 @@ int submit_impl(xv_model* m, const float* feats_host, const int32_t* seg_len_hos
   const int si = m->slot_next;
   xv_model::HostSlot& sl = m->slots[si];
   if (sl.busy) return fail(XV_ESTATE, "all submission slots are in flight: xv_collect the oldest ticket first");
-  const size_t feat_bytes = size_t(total) * m->topo.feat_dim * 4;
+  if (feats_f16 && m->opt_split)
+    return fail(XV_EINVAL, "float16 features cannot feed the split-precision model: it needs the float32 values (hi + lo terms)");
+  const size_t feat_bytes = size_t(total) * m->topo.feat_dim * (feats_f16 ? 2 : 4);
   const size_t emb_bytes = size_t(n_seg) * m->topo.emb_dim * 4;
   const size_t ws_bytes = xv_workspace_bytes(m, total, n_seg);
   auto grow = [&](void** p, size_t* cap, size_t need) -> cudaError_t {
@@ -1267,6 +1275,7 @@ int submit_impl(xv_model* m, const float* feats_host, const int32_t* seg_len_hos
     if (e == cudaSuccess) *cap = want;
     return e;
   };
+  sl.redo.feats_f16 = feats_f16;
   if (!feats_dev_ext) XV_CUDA(grow(reinterpret_cast<void**>(&sl.feats_dev), &sl.feats_cap, feat_bytes));
   XV_CUDA(grow(reinterpret_cast<void**>(&sl.emb_dev), &sl.emb_cap, emb_bytes));
   XV_CUDA(grow(&sl.ws_dev, &sl.ws_cap, ws_bytes));
@@ -1324,6 +1333,18 @@ int xv_submit_host_utts(xv_model* m, const float* feats_host, const int32_t* seg
   u.n_utt = n_utt;
   u.out_dev = out_dev;
   return submit_impl(m, feats_host, seg_len_host, n_seg, nullptr, &u, out_host, ticket);
+}
+
+int xv_submit_host_utts_f16(xv_model* m, const uint16_t* feats_host_f16, const int32_t* seg_len_host, int32_t n_seg,
+                            const int32_t* utt_first_seg_host, const int64_t* utt_dst_row_host, int32_t n_utt, float* out_dev,
+                            float* out_host, int32_t* ticket) {
+  if (!out_dev && !out_host) return fail(XV_EINVAL, "xv_submit_host_utts_f16: no destination (out_dev and out_host are both null)");
+  UttOut u;
+  u.first_seg_host = utt_first_seg_host;
+  u.dst_row_host = utt_dst_row_host;
+  u.n_utt = n_utt;
+  u.out_dev = out_dev;
+  return submit_impl(m, reinterpret_cast<const float*>(feats_host_f16), seg_len_host, n_seg, nullptr, &u, out_host, ticket, nullptr, true);
 }
 
 int xv_submit_dev_utts(xv_model* m, const float* feats_dev, const int32_t* seg_len_host, int32_t n_seg,

@@ -557,6 +557,8 @@ class Model(object):
                 self._engine = None
             self._loaded_stamp = stamp
         engine = self._get_engine(device)
+        if os.environ.get("XVEC_BLOCKING_COLLECT") is not None and hasattr(engine, "set_option"):
+            engine.set_option("blocking_collect", int(os.environ["XVEC_BLOCKING_COLLECT"]))
         feat_dim = self.meta["input_feature_dim"]
         emb_dim = self.embedding_sizes[0]
         batch_frames = int(os.environ.get("XVEC_BATCH_FRAMES", "400000"))
@@ -667,8 +669,12 @@ class Model(object):
         on_gpu = getattr(engine, "handle", None) is not None       # a device engine (stand-ins of the host-logic tests have none)
         dev_name = "cuda:%d" % device if on_gpu else "cpu"
         t_job = time.time()
+        # the reader rounds the rows to float16 while it copies them into the page-locked batches (the device's pack kernel
+        # does that to a feature first anyway: same bits out, half the bytes through the host's memory and over PCIe);
+        # not for the split-precision models, which need the float32 values
+        feats_f16 = on_gpu and self.pooling != "attention" and os.environ.get("XVEC_FEED_F16", "1") != "0"
         reader, counts = ark_job.open_striped_reader(path, start, feat_dim, min_chunk_size, chunk_size, batch_frames,
-                                                     device=dev_name, pinned=on_gpu)
+                                                     device=dev_name, pinned=on_gpu, feats_f16=feats_f16)
         if reader is None:
             return False
         self._run_extraction_job(reader, counts, output_stream, engine, device, min_chunk_size, logger, start_time, t_job)
