@@ -20,7 +20,8 @@ extern "C" void xv_convert_f32_to_f16_host(const float* src, uint16_t* dst, size
 namespace arkjob {
 
 struct Entry {
-  int64_t key_off;
+  int64_t key_off;     // in the file
+  int64_t key_pos;     // in the reader's key blob (the scan keeps the key bytes it has read anyway)
   int64_t payload_off;
   int32_t key_len;
   int32_t rows;
@@ -52,6 +53,7 @@ struct xv_ark_reader {
   int64_t file_size = 0;
   const uint8_t* map = nullptr;
   std::vector<arkjob::Entry> entries;          // every matrix of the stripe, in file order
+  std::string key_blob;                        // their keys (Entry.key_pos, key_len)
   std::vector<int64_t> ok;                     // entry index of the i-th ok utterance
   std::vector<int64_t> row_in_batch;           // [n_ok] first row of the utterance inside its batch buffer
   std::vector<int32_t> seg_len_all;            // [n_segments]
@@ -230,52 +232,80 @@ int build_plan(xv_ark_reader* r) {
 // Chain scan of [from, ...): the entries whose marker lies below end_limit, and what follows them.  Thread-safe (no fail()).
 struct RangeScan {
   std::vector<Entry> entries;
+  std::string keys;
   int64_t next_marker = 0, next_key = 0, stopped_at = -1;
   std::string err;
 };
 
+// The chain is walked with one small pread per header (a few hundred bytes: key + 15 header bytes) rather than through the
+// mapping: a page fault per header (~1 us, more on some hosts: 8-10 ms per 10 000 utterances were measured) costs more than
+// the system call.
 void scan_range(const xv_ark_reader* r, int64_t from, int64_t end_limit, RangeScan* out) {
   const xv_ark_reader_opts& o = r->o;
   out->entries.clear();
+  out->keys.clear();
   out->stopped_at = -1;
   out->next_marker = out->next_key = r->file_size;
   out->err.clear();
-  constexpr int64_t CHUNK = 4096;
-  std::vector<int64_t> ko(CHUNK), po(CHUNK);
-  std::vector<int32_t> kl(CHUNK), rw(CHUNK), cl(CHUNK), eb(CHUNK);
+  uint8_t small[320];
+  std::vector<uint8_t> big;
   int64_t pos = from;
   while (pos < r->file_size) {
-    int64_t consumed = 0;
-    const int64_t n = xv_ark_scan(r->map + pos, r->file_size - pos, CHUNK, ko.data(), kl.data(), rw.data(), cl.data(), eb.data(),
-                                  po.data(), &consumed);
-    if (n < 0) { out->err = "xv_ark_scan failed"; return; }
-    for (int64_t i = 0; i < n; ++i) {
-      const int64_t marker = pos + po[i] - 15;
-      if (marker >= end_limit) {
-        out->next_marker = marker;
-        out->next_key = pos + ko[i];
-        return;
+    const uint8_t* buf = small;
+    int64_t want = std::min<int64_t>(int64_t(sizeof(small)), r->file_size - pos), avail = 0;
+    int64_t ko = 0, po = 0;
+    int32_t kl = 0, rw = 0, cl = 0, eb = 0;
+    int st;
+    for (;;) {
+      uint8_t* dst = buf == small ? small : big.data();
+      while (avail < want) {
+        const ssize_t k = pread(r->fd, dst + avail, size_t(want - avail), off_t(pos + avail));
+        if (k <= 0) break;
+        avail += k;
       }
-      if (cl[i] != o.feat_dim && rw[i] > 0) {
-        out->err = "utterance " + std::string(reinterpret_cast<const char*>(r->map + pos + ko[i]), size_t(kl[i])) +
-                   " has feature dim " + std::to_string(cl[i]) + ", model expects " + std::to_string(o.feat_dim);
-        return;
-      }
-      Entry e{};
-      e.key_off = pos + ko[i]; e.key_len = kl[i]; e.rows = rw[i]; e.elem = eb[i]; e.payload_off = pos + po[i];
-      out->entries.push_back(e);
+      st = ark_parse_header(dst, avail, r->file_size - pos, &ko, &kl, &rw, &cl, &eb, &po);
+      if (st != -1 || avail < want || buf != small) break;
+      big.resize(4300);                                  // a very long key: one more, larger read
+      memcpy(big.data(), small, size_t(avail));
+      buf = big.data();
+      want = std::min<int64_t>(4300, r->file_size - pos);
     }
-    if (n < CHUNK) {
-      if (pos + consumed < r->file_size) {
-        // trailing white space is tolerated (a text-mode tail); anything else is an entry this scanner does not know
-        int64_t q = pos + consumed;
-        while (q < r->file_size && ark_space(r->map[q])) ++q;
-        if (q < r->file_size) out->stopped_at = pos + consumed;
-      }
+    if (st != 1) {
+      // trailing white space is tolerated (a text-mode tail); anything else is an entry this scanner does not know
+      const uint8_t* p = buf == small ? small : big.data();
+      int64_t q = 0;
+      while (q < avail && ark_space(p[q])) ++q;
+      if (!(q == avail && pos + avail == r->file_size)) out->stopped_at = pos;
       return;
     }
-    pos += consumed;
+    const int64_t marker = pos + po - 15;
+    if (marker >= end_limit) {
+      out->next_marker = marker;
+      out->next_key = pos + ko;
+      return;
+    }
+    if (cl != o.feat_dim && rw > 0) {
+      const uint8_t* p = buf == small ? small : big.data();
+      out->err = "utterance " + std::string(reinterpret_cast<const char*>(p + ko), size_t(kl)) + " has feature dim " +
+                 std::to_string(cl) + ", model expects " + std::to_string(o.feat_dim);
+      return;
+    }
+    Entry e{};
+    e.key_off = pos + ko; e.key_len = kl; e.rows = rw; e.elem = eb; e.payload_off = pos + po;
+    e.key_pos = int64_t(out->keys.size());
+    out->keys.append(reinterpret_cast<const char*>((buf == small ? small : big.data()) + ko), size_t(kl));
+    out->entries.push_back(e);
+    pos = e.payload_off + int64_t(rw) * cl * eb;
   }
+}
+
+// The first entry of a resynchronised range was parsed from a provisional key start; the chain in front knows the true one.
+void fix_first_key(const xv_ark_reader* r, Entry* e, std::string* keys, int64_t marker, int64_t key_off) {
+  const int64_t len = marker - 1 - key_off;
+  e->key_off = key_off;
+  e->key_len = int32_t(len);
+  e->key_pos = int64_t(keys->size());
+  keys->append(reinterpret_cast<const char*>(r->map + key_off), size_t(len));
 }
 
 // Provisional start of the key in front of the marker at h: the longest run of key characters before the separating space
@@ -325,6 +355,7 @@ int scan_stripe(xv_ark_reader* r, int64_t from, bool first_is_candidate) {
   RangeScan& head = scans[0];
   if (!head.err.empty()) return fail(XV_EINVAL, head.err);
   r->entries.swap(head.entries);
+  r->key_blob.swap(head.keys);
   int64_t next_marker = head.next_marker, next_key = head.next_key, stopped = head.stopped_at;
   for (int i = 1; i < parts && stopped < 0; ++i) {
     if (next_marker >= part_end[i]) continue;                  // the chain in front runs past this whole sub-range
@@ -332,10 +363,12 @@ int scan_stripe(xv_ark_reader* r, int64_t from, bool first_is_candidate) {
     if (first_marker[i] != next_marker || s.entries.empty()) {
       scan_range(r, next_key, part_end[i], &s);                // the candidate was wrong (or missing): true boundary
     } else {
-      s.entries[0].key_len = int32_t(next_marker - 1 - next_key);
-      s.entries[0].key_off = next_key;
+      fix_first_key(r, &s.entries[0], &s.keys, next_marker, next_key);
     }
     if (!s.err.empty()) return fail(XV_EINVAL, s.err);
+    const int64_t shift = int64_t(r->key_blob.size());
+    r->key_blob += s.keys;
+    for (auto& e : s.entries) e.key_pos += shift;
     r->entries.insert(r->entries.end(), s.entries.begin(), s.entries.end());
     next_marker = s.next_marker; next_key = s.next_key; stopped = s.stopped_at;
   }
@@ -486,6 +519,7 @@ int xv_ark_reader_set_first(xv_ark_reader* r, int64_t marker_off, int64_t key_of
   if (marker_off >= end_limit) {
     // the previous stripe's chain runs past this stripe: it is empty, and hands the same boundary on
     r->entries.clear();
+    r->key_blob.clear();
     r->first_is_candidate = false;
     int rc = arkjob::build_plan(r);
     if (rc != XV_OK) return rc;
@@ -494,9 +528,7 @@ int xv_ark_reader_set_first(xv_ark_reader* r, int64_t marker_off, int64_t key_of
     r->info.next_key_off = key_off;
   } else if (!r->entries.empty() && r->entries[0].payload_off - 15 == marker_off) {
     // the candidate was right: fix where its key starts
-    arkjob::Entry& e = r->entries[0];
-    e.key_len = int32_t(marker_off - 1 - key_off);
-    e.key_off = key_off;
+    arkjob::fix_first_key(r, &r->entries[0], &r->key_blob, marker_off, key_off);
     r->first_is_candidate = false;
     int rc = arkjob::build_plan(r);
     if (rc != XV_OK) return rc;
@@ -515,7 +547,7 @@ int xv_ark_reader_keys(const xv_ark_reader* r, char* blob, int64_t blob_cap, int
   for (size_t i = 0; i < r->ok.size(); ++i) {
     const arkjob::Entry& e = r->entries[r->ok[i]];
     key_off[i] = pos;
-    memcpy(blob + pos, r->map + e.key_off, size_t(e.key_len));
+    memcpy(blob + pos, r->key_blob.data() + e.key_pos, size_t(e.key_len));
     pos += e.key_len;
   }
   key_off[r->ok.size()] = pos;
@@ -529,7 +561,7 @@ int xv_ark_reader_failures(const xv_ark_reader* r, int32_t* reason, int32_t* row
     if (e.n_chunks != 0) continue;
     if (pos + e.key_len > blob_cap) return fail(XV_ENOMEM, "key buffer too small");
     reason[n] = e.reason; rows[n] = e.rows; key_off[n] = pos;
-    memcpy(blob + pos, r->map + e.key_off, size_t(e.key_len));
+    memcpy(blob + pos, r->key_blob.data() + e.key_pos, size_t(e.key_len));
     pos += e.key_len;
     ++n;
   }
