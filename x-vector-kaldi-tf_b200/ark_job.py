@@ -52,7 +52,7 @@ def open_striped_reader(path, start, feat_dim, min_chunk_size, chunk_size, batch
     size = os.path.getsize(path)
     begin, end = stripe_bounds(start, size, rank, world)
     if n_threads is None:
-        n_threads = int(os.environ.get("XVEC_READER_THREADS", str(max(2, min(4, (os.cpu_count() or 4) // max(world, 1))))))
+        n_threads = int(os.environ.get("XVEC_READER_THREADS", str(max(2, min(8, (os.cpu_count() or 4) // max(world, 1))))))
     reader = ArkReader(path, feat_dim, min_chunk_size, chunk_size, batch_frames, byte_begin=begin,
                        byte_end=(-1 if rank == world - 1 else end), begin_is_boundary=(rank == 0), n_threads=n_threads,
                        n_slots=n_slots, pinned=pinned, feats_f16=feats_f16)
