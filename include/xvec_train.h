@@ -97,8 +97,7 @@ int64_t xv_train_debug_tensor(xv_trainer* t, const char* name, float* host_out, 
 int xv_convert_f16_to_f32(const void* src_dev, float* dst_dev, int64_t n, void* stream);
 /* Options: "graph" (1: a step's kernels are captured once per (geometry, buffers) into a CUDA graph and replayed),
  * "loss_scale" (0 = automatic: 8 * frames rounded to a power of two), "l2_beta" (0; 0.0002 for ModelL2Loss*),
- * "wgrad_lbo", "wgrad_sbo" (diagnostics), "seg_fused" (1: the segment level of a step as one cooperative kernel instead of
- * chained launches; relu only), "seg_ctas", "wgrad_reuse", "fused_stats" (alternative schedules). */
+ * "wgrad_lbo", "wgrad_sbo" (diagnostics), "wgrad_reuse", "fused_stats" (alternative schedules). */
 int xv_train_set_option(xv_trainer* t, const char* name, double value);
 int32_t xv_train_last_launch_count(const xv_trainer* t);
 /* With the xv_model option "profile" on, every launch of a step is bracketed by CUDA events: read the times with

@@ -13,7 +13,6 @@
 #include "../../include/xvec_train.h"
 #include "train_kernels.cuh"
 #include "wgrad_pair.cuh"
-#include "seg_level.cuh"
 
 namespace {
 
@@ -71,11 +70,6 @@ struct xv_trainer {
                                      // columns) whose A-operand reads per FLOP double -- measured 83 vs 75 us (tdnn), 142 vs 129 us
                                      // (dense) for the two layers it applies to: not faster, kept as a tested option
   int opt_fused_stats = 1;           // 1: BatchNorm / pooling column sums come out of the layer kernel's epilogue (STATS instantiation)
-  int opt_seg_ctas = 0, seg_ctas_per_sm = 0;
-  int opt_seg_fused = 0;             // 1: the whole segment level of a training step in ONE cooperative kernel (seg_level.cuh).
-                                     // Same results to fp32 rounding, but measured no faster on B200 (0.226 ms vs ~0.2 ms for the
-                                     // 22 chained launches under PDL: its K loops are bound by L2 latency, one tile in flight per
-                                     // CTA, and more co-resident CTAs only make the 11 grid barriers dearer) -> kept as an option
   float last_loss_scale = 0.f;
   // geometry-dependent workspace
   int32_t n_seg = 0, seg_len = 0, seg_stride = 0;
@@ -240,13 +234,6 @@ int tr_ensure_workspace(xv_trainer* t, int32_t n_seg, int32_t seg_len) {
       const SgemmPlan sp = sgemm_plan(d[0], d[1], d[2], m->num_sms);
       if (sp.splits > 1) sg = std::max(sg, size_t(sp.splits) * d[0] * d[1]);
     }
-  }
-  {
-    // the fused segment-level kernel (seg_level.cuh): up to num_sms / (N/64) K-splits of a [B, N] product, or the logits
-    const size_t B = size_t(n_seg);
-    for (int N : {t->seg[0].out, t->seg[1].out, t->seg[1].in})
-      sg = std::max(sg, size_t(std::max(1, 4 * m->num_sms / ((N + 63) / 64))) * B * N);
-    sg = std::max(sg, B * size_t(t->num_classes));
   }
   t->sg_partial_floats = sg;
   want(reinterpret_cast<void**>(&t->sg_partial), std::max<size_t>(sg, 1) * 4);
@@ -630,11 +617,9 @@ int xv_train_set_option(xv_trainer* t, const char* name, double value) {
   else if (n == "loss_scale") t->opt_loss_scale = value;
   else if (n == "wgrad_lbo") t->opt_wgrad_lbo = int(value);
   else if (n == "wgrad_sbo") t->opt_wgrad_sbo = int(value);
-  else if (n == "seg_fused") t->opt_seg_fused = value != 0.0;
   else if (n == "fused_stats") t->opt_fused_stats = value != 0.0;
   else if (n == "l2_beta") t->opt_l2_beta = value;
   else if (n == "wgrad_reuse") { t->opt_wgrad_reuse = value != 0.0; t->n_seg = 0; }     // the partial buffer is re-planned
-  else if (n == "seg_ctas") { t->opt_seg_ctas = int(value); t->seg_ctas_per_sm = 0; }
   else return fail(XV_EINVAL, "unknown option: " + n);
   return XV_OK;
 }
@@ -751,51 +736,7 @@ int tr_step_body(xv_trainer* t, const float* feats_dev, const int32_t* labels_de
   }
 
   const int NC = t->num_classes, E1 = t->seg[1].out;
-  const bool seg_fused = training && t->opt_seg_fused && t->neg_slope == 0.f;     // the cooperative kernel is relu only
-  if (seg_fused) {
-    // ---- the whole segment level (forward, loss, backward) in one persistent cooperative kernel -----------------------
-    segk::Args a{};
-    a.B = n_seg; a.NC = NC; a.eps = m->topo.bn_eps; a.decay = BN_DECAY;
-    a.h0 = t->h0; a.dh0 = t->dh0;
-    for (int i = 0; i < 2; ++i) {
-      TrSeg& Sg = t->seg[i];
-      segk::Layer& L = a.L[i];
-      L.W = t->params + Sg.off_w; L.b = t->params + Sg.off_b; L.gamma = t->params + Sg.off_gamma; L.beta = t->params + Sg.off_beta;
-      L.moving_mean = t->moving + Sg.off_mov; L.moving_var = t->moving + Sg.off_mov + Sg.out;
-      L.z = Sg.z; L.r = Sg.r; L.y = Sg.y; L.dy = Sg.dy; L.dz = Sg.dz;
-      L.mean = Sg.bn; L.inv = Sg.bn + Sg.out;
-      L.gW = grad + Sg.off_w; L.gb = grad + Sg.off_b; L.ggamma = grad + Sg.off_gamma; L.gbeta = grad + Sg.off_beta;
-      L.in = Sg.in; L.out = Sg.out;
-    }
-    a.Wo = t->params + t->off_wo; a.bo = t->params + t->off_bo; a.gWo = grad + t->off_wo; a.gbo = grad + t->off_bo;
-    a.logits = t->logits; a.dlogits = t->dlogits; a.labels = labels_dev;
-    a.loss_row = t->loss_row; a.correct = t->correct; a.loss_acc = loss_acc_dev;
-    a.partial = t->sg_partial;
-    if (t->seg_ctas_per_sm == 0) {            // co-resident CTAs per SM of the cooperative kernel (latency hiding: take up to 3)
-      int occ = 0;
-      TR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, segk::seg_level_train_kernel, 256, 0));
-      if (occ < 1) return fail(XV_ECUDA, "seg_level_train_kernel cannot be made resident");
-      t->seg_ctas_per_sm = std::min(occ, t->opt_seg_ctas > 0 ? t->opt_seg_ctas : 3);
-    }
-    const int grid = m->num_sms * t->seg_ctas_per_sm;
-    auto pick = [&](int N, int K) { return std::max(1, std::min(grid / ((N + 63) / 64), std::max(1, K / 64))); };
-    a.splits_f1 = pick(a.L[0].out, a.L[0].in);
-    a.splits_f3 = pick(a.L[1].out, a.L[1].in);
-    a.splits_f5 = 1;
-    a.splits_dy6 = pick(a.L[1].out, NC);
-    a.splits_dy5 = pick(a.L[1].in, a.L[1].out);
-    size_t need = size_t(n_seg) * NC;
-    need = std::max(need, size_t(a.splits_f1) * n_seg * a.L[0].out);
-    need = std::max(need, size_t(a.splits_f3) * n_seg * a.L[1].out);
-    need = std::max(need, size_t(a.splits_dy6) * n_seg * a.L[1].out);
-    need = std::max(need, size_t(a.splits_dy5) * n_seg * a.L[1].in);
-    if (need > t->sg_partial_floats) return fail(XV_ESTATE, "segment-level partial buffer too small");
-    void* kargs[] = {&a};
-    TR_BEGIN("seg_level_train_kernel");
-    TR_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(segk::seg_level_train_kernel), dim3(grid), dim3(256), kargs, 0, stream));
-    TR_END();
-  }
-  if (!seg_fused) {
+  {
   // ---- segment level forward (fp32) ---------------------------------------------------------------
   const float* hin = t->h0;
   for (int i = 0; i < 2; ++i) {

@@ -3,8 +3,11 @@
 The reference scales extraction by running ``nj`` unrelated OS processes over a pre-split
 data directory and concatenating their outputs (local/tf/extract_xvectors.sh:63-65,83-95);
 there is no exchange step inside the forward pass.  Here: one process per GPU
-(``torch.distributed``), utterances dealt to ranks with no data-path collective, and ONE
-gather of ``[n_r, emb_dim]`` fp32 + int64 indices to rank 0, which writes the ark.
+(``torch.distributed``) and no data-path collective.  An archive in a regular file is cut into byte stripes (``ark_job.py``:
+every rank reads 1/N of it, and either writes its own byte range of the one output ark or stores its rows into rank 0's
+peer-memory table); what is left here serves streams, whose length is unknown ahead of time: utterances dealt block-cyclically
+and -- for process groups without peer memory (gloo in the CPU tests) -- ONE gather of ``[n_r, emb_dim]`` fp32 + int64 indices
+to rank 0, which writes the ark.
 """
 from __future__ import annotations
 
@@ -20,19 +23,6 @@ def dist_info():
     except ImportError:
         pass
     return 0, 1
-
-
-def serpentine_assignment(lengths, world_size):
-    """Rank of each item when all lengths are known up front: sort by length (stable), deal
-    0..W-1, W-1..0, ...  Frame counts per rank differ by at most ~one utterance per sweep."""
-    lengths = np.asarray(lengths)
-    order = np.argsort(-lengths, kind="stable")
-    pos = np.arange(len(order))
-    sweep, col = pos // world_size, pos % world_size
-    rank_sorted = np.where(sweep % 2 == 0, col, world_size - 1 - col)
-    ranks = np.empty(len(order), dtype=np.int64)
-    ranks[order] = rank_sorted
-    return ranks
 
 
 def block_cyclic_rank(index, world_size, block=16):
