@@ -595,6 +595,32 @@ def measure_frontend(args, eng, dev, stream, flush, rank, peaks):
     ms = float(np.mean([s_.elapsed_time(e_) for s_, e_ in evs]))
     alg_bytes = int(B * T * (FEAT_DIM * 4 + 4) + int(keep.sum()) * FEAT_DIM * 4)
     gbs = alg_bytes / (ms * 1e-3) / 1e9
+    # the same kernel on a problem large enough for an HBM fraction to mean something: 10 240 utterances x 400 raw frames
+    # (4.1 M raw frames, 0.38 GB in) -- the batch above tiled 40 times
+    large = None
+    try:
+        rep = 40
+        lens_l, keep_l = np.tile(lens, rep), np.tile(keep, rep)
+        raw_l, vad_l = raw_dev.repeat(rep, 1), vad_dev.repeat(rep)
+        out_l = torch.empty((int(keep_l.sum()), FEAT_DIM), dtype=torch.float32, device=dev)
+        for _ in range(2):
+            eng.frontend(raw_l, vad_l, lens_l, keep_l, opts, out_dev=out_l, stream=stream)
+        evl = []
+        for _ in range(10):
+            flush.zero_()
+            s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_.record(stream); eng.frontend(raw_l, vad_l, lens_l, keep_l, opts, out_dev=out_l, stream=stream); e_.record(stream)
+            evl.append((s_, e_))
+        torch.cuda.synchronize(dev)
+        ms_l = float(np.mean([s_.elapsed_time(e_) for s_, e_ in evl]))
+        gbs_l = alg_bytes * rep / (ms_l * 1e-3) / 1e9
+        large = dict(workload="%d x %d RAW frames (%.1f M)" % (B * rep, T, B * rep * T / 1e6), ms_per_call=round(ms_l, 5),
+                     raw_frames_per_sec=round(B * rep * T / (ms_l * 1e-3), 1),
+                     roofline=dict(bound="hbm", achieved=round(gbs_l, 1), peak=peaks["hbm_gbs"], unit="GB/s",
+                                   frac=round(gbs_l / peaks["hbm_gbs"], 4), algorithmic_bytes_per_call=alg_bytes * rep))
+        del raw_l, vad_l, out_l
+    except Exception as err:                                     # noqa: BLE001
+        large = dict(error="%s: %s" % (type(err).__name__, err))
     # raw host path: pinned raw rows + VAD in, embeddings out, two submissions in flight
     emb = [torch.empty((B, EMB_DIM), dtype=torch.float32).pin_memory() for _ in range(2)]
     def run(n):
@@ -626,7 +652,7 @@ def measure_frontend(args, eng, dev, stream, flush, rank, peaks):
                          ms_per_step=round(e2e_ms, 5), raw_frames_per_sec=round(B * T / (e2e_ms * 1e-3), 1),
                          voiced_frames_per_sec=round(float(keep.sum()) / (e2e_ms * 1e-3), 1),
                          h2d_bytes_per_step=int(B * T * (FEAT_DIM * 4 + 4) + B * 4 * 3), d2h_bytes_per_step=B * EMB_DIM * 4 + 4),
-                cpu_baseline=cpu)
+                large_problem=large, cpu_baseline=cpu)
 
 
 def _scratch_dir(need_bytes=16 << 30):

@@ -717,13 +717,35 @@ class Model(object):
             stats["output"] = mode
             sink = ark_job.VectorSink(output_stream) if rank == 0 else None
             if mode == "peer":
+                # rank 0's result table mapped into every rank (CUDA IPC).  Where the mapping cannot be made (processes in
+                # different IPC namespaces, a driver without peer access between the devices) every rank learns it here and
+                # the job gathers the host rows instead -- slower at the end, same bytes out.
                 from ._native import PeerTable
-                if rank == 0:
-                    peer = PeerTable.create(device, max(n_ok_total, 1), emb_dim)
-                box = [peer.handle if rank == 0 else None]
+                ok = 1
+                try:
+                    if rank == 0:
+                        peer = PeerTable.create(device, max(n_ok_total, 1), emb_dim)
+                except Exception as err:                                 # noqa: BLE001
+                    ok, peer = 0, None
+                    if logger is not None:
+                        logger.warning("no peer-memory result table (%s): gathering host rows instead" % err)
+                box = [peer.handle if (rank == 0 and peer is not None) else None]
                 dist.broadcast_object_list(box, src=0)
-                if rank != 0:
-                    peer = PeerTable.open(device, max(n_ok_total, 1), emb_dim, box[0])
+                if rank != 0 and box[0] is not None:
+                    try:
+                        peer = PeerTable.open(device, max(n_ok_total, 1), emb_dim, box[0])
+                    except Exception as err:                             # noqa: BLE001
+                        ok, peer = 0, None
+                        if logger is not None:
+                            logger.warning("cannot map rank 0's result table (%s): gathering host rows instead" % err)
+                elif rank != 0:
+                    ok = 0
+                if int(ark_job._all_gather_i64([ok], dev_name).min()) == 0:
+                    if peer is not None:
+                        peer.close()
+                        peer = None
+                    mode = "host_gather"
+                    stats["output"] = mode
             ark_base = 0
             scp_parts = []
             if mode == "shared_file":
