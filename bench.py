@@ -1016,14 +1016,16 @@ def measure_train_step(args, dev, rank, world, peaks, topo):
     feats, lab = feats_host.to(dev), lab_host.to(dev)
     grad = torch.zeros(tr.n_grad, dtype=torch.float32, device=dev) if world > 1 else None
     la_host = torch.zeros(2, dtype=torch.float32, pin_memory=True)
+    comm = torch.cuda.Stream(dev) if world > 1 else None
 
     def step(e2e):
         if e2e:
             feats.copy_(feats_host, non_blocking=True)
             lab.copy_(lab_host, non_blocking=True)
-        la = tr.forward_backward(feats, lab, B, T, grad_dev=grad)
-        if world > 1:
-            dist.all_reduce(grad)
+        if world > 1:        # the segment-level gradients are all-reduced on `comm` under the frame-level backward
+            la = tr.forward_backward_allreduce(feats, lab, B, T, grad, torch.cuda.current_stream(dev), comm)
+        else:
+            la = tr.forward_backward(feats, lab, B, T, grad_dev=grad)
         tr.apply(1e-4, grad_dev=grad, grad_scale=1.0 / world)
         if e2e:
             la_host.copy_(la, non_blocking=True)
@@ -1071,7 +1073,8 @@ def measure_train_step(args, dev, rank, world, peaks, topo):
                ms_per_step=round(ms_res, 4), value=round(world * B * T / (ms_res * 1e-3), 1), unit="frames/s",
                e2e=dict(ms_per_step=round(ms_e2e, 4), value=round(world * B * T / (ms_e2e * 1e-3), 1), unit="frames/s",
                         h2d_bytes_per_step=B * T * FEAT_DIM * 4 + B * 4, d2h_bytes_per_step=8),
-               parallelism="data parallel x%d: NCCL all-reduce of the flat fp32 gradient (%.1f MB) per step" % (world, tr.n_params * 4 / 1e6)
+               parallelism="data parallel x%d: NCCL all-reduce of the flat fp32 gradient (%.1f MB) per step, the segment-level %.1f MB under the frame-level backward"
+                           % (world, tr.n_params * 4 / 1e6, (tr.n_params - tr.seg_grad_offset) * 4 / 1e6)
                if world > 1 else "single GPU",
                gpu_launches_per_step=launches, loss_after=round(loss, 4),
                frame_level_flop_per_step=flop_step,

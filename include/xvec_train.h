@@ -65,6 +65,14 @@ int64_t xv_train_get_step(const xv_trainer* t);
  * Also applies the moving-statistics update of every BatchNorm (tf_block.py:20-21).  Enqueue only. */
 int xv_train_forward_backward(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, int32_t n_seg,
                               int32_t seg_len, float* grad_dev, float* loss_acc_dev, void* stream);
+/* The same step in two halves, so that a data-parallel caller can hide most of its gradient all-reduce (the reference has no
+ * such seam: one sess.run per minibatch).  part 1: forward, loss and the SEGMENT-level backward -- when it ends (in stream order)
+ * the gradients [xv_train_segment_grad_offset(t), n_params) of embed_layer-*, output/* (60 % of the bytes) are final and their
+ * all-reduce can start on another stream; part 2: pooling and frame-level backward, which fills [0, offset) and the overflow
+ * flag behind the gradient; part 0 = both (xv_train_forward_backward).  Same arithmetic, bit for bit. */
+int xv_train_forward_backward_part(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, int32_t n_seg,
+                                   int32_t seg_len, float* grad_dev, float* loss_acc_dev, void* stream, int32_t part);
+int64_t xv_train_segment_grad_offset(const xv_trainer* t);
 /* Loss and accuracy of one minibatch with phase = False (moving statistics, nothing is updated): the
  * sess.run([self.loss, self.accuracy]) of Model.eval (models.py:338-339). */
 int xv_train_eval(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, int32_t n_seg, int32_t seg_len,

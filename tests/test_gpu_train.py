@@ -254,6 +254,35 @@ def test_tap_reuse_weight_gradient_kernel_agrees():
             p.close()
 
 
+def test_the_step_in_two_halves_equals_the_whole_step_bit_for_bit():
+    # xv_train_forward_backward_part: part 1 (forward, loss, segment-level backward) + part 2 (pooling / frame-level backward)
+    # enqueue exactly the launches of the whole step, in the same order; the segment-level gradients are final after part 1
+    whole, split = Problem("ModelWithoutDropoutTdnn", "B", 8, 96, 50), Problem("ModelWithoutDropoutTdnn", "B", 8, 96, 50)
+    try:
+        for _ in range(3):                                   # the third round runs from captured graphs
+            la0 = whole.tr.forward_backward(whole.feats, whole.lab, whole.B, whole.T)
+            torch.cuda.synchronize()
+            g0 = whole.tr.download(whole.native.TRAIN_GRAD)
+            split.tr.download(split.native.TRAIN_GRAD)
+            la1 = split.tr.forward_backward(split.feats, split.lab, split.B, split.T, part=1)
+            torch.cuda.synchronize()
+            off, n = split.tr.seg_grad_offset, split.tr.n_params
+            g_half = split.tr.download(split.native.TRAIN_GRAD)
+            assert 0 < off < n and np.array_equal(g_half[off:n], g0[off:n])          # segment-level gradients: final already
+            split.tr.forward_backward(split.feats, split.lab, split.B, split.T, part=2)
+            torch.cuda.synchronize()
+            assert np.array_equal(split.tr.download(split.native.TRAIN_GRAD), g0)
+            assert np.array_equal(la0.cpu().numpy(), la1.cpu().numpy())
+            assert np.array_equal(split.tr.download(split.native.TRAIN_MOVING), whole.tr.download(whole.native.TRAIN_MOVING))
+            whole.tr.apply(1e-3)
+            split.tr.apply(1e-3)
+            torch.cuda.synchronize()
+            assert np.array_equal(split.tr.download(split.native.TRAIN_PARAMS), whole.tr.download(whole.native.TRAIN_PARAMS))
+    finally:
+        whole.close()
+        split.close()
+
+
 def test_adam_matches_tf_formula_exactly():
     p = Problem("ModelWithoutDropoutTdnn", "B", 4, 40, 50)
     try:

@@ -219,6 +219,10 @@ def load_library():
     lib.xv_train_get_step.restype = I64
     lib.xv_train_forward_backward.argtypes = [P, P, P, I32, I32, P, P, P]
     lib.xv_train_forward_backward.restype = ctypes.c_int
+    lib.xv_train_forward_backward_part.argtypes = [P, P, P, I32, I32, P, P, P, I32]
+    lib.xv_train_forward_backward_part.restype = ctypes.c_int
+    lib.xv_train_segment_grad_offset.argtypes = [P]
+    lib.xv_train_segment_grad_offset.restype = I64
     lib.xv_train_eval.argtypes = [P, P, P, I32, I32, P, P]
     lib.xv_train_eval.restype = ctypes.c_int
     lib.xv_train_apply.argtypes = [P, P, F32, F32, P]
@@ -260,7 +264,8 @@ EXPORTED_SYMBOLS = ["xv_create", "xv_destroy", "xv_set_param", "xv_workspace_byt
                     "xv_submit_dev_utts", "xv_convert_f32_to_f16_host", "xv_convert_f32_to_f16_host_scalar",
                     # include/xvec_train.h
                     "xv_train_create", "xv_train_destroy", "xv_train_size", "xv_train_span", "xv_train_upload",
-                    "xv_train_download", "xv_train_set_step", "xv_train_get_step", "xv_train_forward_backward", "xv_train_eval",
+                    "xv_train_download", "xv_train_set_step", "xv_train_get_step", "xv_train_forward_backward", "xv_train_forward_backward_part",
+                    "xv_train_segment_grad_offset", "xv_train_eval",
                     "xv_train_apply", "xv_train_skipped_updates", "xv_train_sync_model", "xv_train_debug_tensor", "xv_train_set_option",
                     "xv_train_last_launch_count", "xv_train_last_kernel_names", "xv_convert_f16_to_f32",
                     # include/xvec_frontend.h
@@ -789,6 +794,7 @@ class XvecTrainer:
         _check(self.lib, self.lib.xv_train_create(ctypes.byref(self.handle), engine.handle, int(num_classes), int(emb1_dim)))
         self.n_params = int(self.lib.xv_train_size(self.handle, TRAIN_PARAMS))
         self.n_grad = int(self.lib.xv_train_size(self.handle, TRAIN_GRAD))     # gradient + the combined-overflow-flag tail
+        self.seg_grad_offset = int(self.lib.xv_train_segment_grad_offset(self.handle))   # [this, n_params): segment-level gradients
         self.n_moving = int(self.lib.xv_train_size(self.handle, TRAIN_MOVING))
         self._loss_acc = None
         self._geom = None
@@ -845,9 +851,10 @@ class XvecTrainer:
     def step(self, value):
         _check(self.lib, self.lib.xv_train_set_step(self.handle, int(value)))
 
-    def forward_backward(self, feats_dev, labels_dev, n_seg, seg_len, grad_dev=None, stream=None):
+    def forward_backward(self, feats_dev, labels_dev, n_seg, seg_len, grad_dev=None, stream=None, part=0):
         """feats_dev: torch float32 CUDA [n_seg*seg_len, feat_dim]; labels_dev: torch int32 CUDA [n_seg].
-        Enqueues on ``stream``; returns the device tensor [loss, accuracy] (read it after a synchronize)."""
+        Enqueues on ``stream``; returns the device tensor [loss, accuracy] (read it after a synchronize).
+        ``part``: 0 the whole step; 1 / 2 its halves (see ``allreduce_overlapped``)."""
         import torch
         assert feats_dev.is_cuda and feats_dev.dtype == torch.float32 and feats_dev.is_contiguous()
         assert feats_dev.numel() == n_seg * seg_len * self.engine.feat_dim
@@ -856,10 +863,28 @@ class XvecTrainer:
             self._loss_acc = torch.zeros(2, dtype=torch.float32, device=feats_dev.device)
         s = torch.cuda.current_stream(feats_dev.device) if stream is None else stream
         gptr = None if grad_dev is None else grad_dev.data_ptr()
-        _check(self.lib, self.lib.xv_train_forward_backward(self.handle, feats_dev.data_ptr(), labels_dev.data_ptr(), int(n_seg),
-                                                            int(seg_len), gptr, self._loss_acc.data_ptr(), s.cuda_stream))
+        _check(self.lib, self.lib.xv_train_forward_backward_part(self.handle, feats_dev.data_ptr(), labels_dev.data_ptr(), int(n_seg),
+                                                                 int(seg_len), gptr, self._loss_acc.data_ptr(), s.cuda_stream, int(part)))
         self._geom = (int(n_seg), int(seg_len))
         return self._loss_acc
+
+    def forward_backward_allreduce(self, feats_dev, labels_dev, n_seg, seg_len, grad_dev, stream, comm_stream):
+        """Data-parallel step: the all-reduce of the segment-level gradients (60 % of the bytes; final after the first half of
+        the step) runs on ``comm_stream`` UNDER the frame-level backward; the frame-level gradients and the overflow flag
+        follow when the step ends.  On return ``stream`` waits for both: ``apply`` may be enqueued."""
+        import torch
+        import torch.distributed as dist
+        la = self.forward_backward(feats_dev, labels_dev, n_seg, seg_len, grad_dev=grad_dev, stream=stream, part=1)
+        comm_stream.wait_stream(stream)
+        with torch.cuda.stream(comm_stream):
+            dist.all_reduce(grad_dev[self.seg_grad_offset:self.n_params])
+        self.forward_backward(feats_dev, labels_dev, n_seg, seg_len, grad_dev=grad_dev, stream=stream, part=2)
+        comm_stream.wait_stream(stream)
+        with torch.cuda.stream(comm_stream):
+            dist.all_reduce(grad_dev[:self.seg_grad_offset])
+            dist.all_reduce(grad_dev[self.n_params:])
+        stream.wait_stream(comm_stream)
+        return la
 
     def evaluate(self, feats_dev, labels_dev, n_seg, seg_len, stream=None):
         """Loss / accuracy with phase=False (moving statistics); nothing is updated."""

@@ -90,7 +90,7 @@ struct xv_trainer {
   std::vector<std::pair<int32_t, int32_t>> seen_geometries;   // a step is captured into a graph the second time its geometry shows up
   // CUDA graph of one forward_backward (74 launches): captured once per (geometry, buffer pointers), replayed afterwards
   struct StepGraph { const void* feats; const void* labels; const void* grad; const void* loss; int32_t n_seg, seg_len;
-                     cudaGraphExec_t exec; int32_t launches; };
+                     cudaGraphExec_t exec; int32_t launches; int32_t part; };
   std::vector<StepGraph> graphs;
   cudaStream_t gstream = nullptr;
   cudaEvent_t g_in = nullptr, g_out = nullptr;
@@ -101,6 +101,7 @@ struct xv_trainer {
   // gradient-overflow bookkeeping (separate from the xv_model's forward-activation flag): gflag[0] = a loss-scaled fp16
   // gradient of THIS step left the fp16 range (zeroed at the start of every step, published as grad[n_params] so that a
   // data-parallel all-reduce combines it over the ranks), gflag[1] = updates skipped so far (adam_kernel)
+  bool emit = true;                  // false while tr_step_body walks the half of a step that a split call does NOT enqueue
   uint32_t* gflag = nullptr;
   uint32_t* gflag_host = nullptr;    // pinned copy of gflag[1] for xv_train_skipped_updates
   cudaEvent_t gflag_event = nullptr;
@@ -121,19 +122,26 @@ int tr_launch_check(xv_trainer* t) {
 // bracket a launch with profiling events (option "profile" of the xv_model) and count it
 #define TR_BEGIN(name)                                                     \
   do {                                                                     \
+    if (!t->emit) break;                                                   \
     if (t->m->opt_profile) t->prof_names.push_back(name);                  \
     int prc_ = prof_mark(t->m, stream);                                    \
     if (prc_ != XV_OK) return prc_;                                        \
+  } while (0)
+// a stream operation of a training step: skipped while the step's other half is being walked (xv_train_forward_backward_part)
+#define TR_EMIT(expr)                                                      \
+  do {                                                                     \
+    if (t->emit) TR_CUDA(expr);                                            \
   } while (0)
 // launch + count; programmatic dependent launch (every kernel starts with cudaGridDependencySynchronize()) unless profiling
 #define TR_LAUNCH(name, kernel, grid, block, smem, ...)                                                            \
   do {                                                                                                             \
     TR_BEGIN(name);                                                                                                \
-    TR_CUDA(launch_k(t->m->opt_pdl != 0 && !t->m->opt_profile, kernel, grid, block, smem, stream, __VA_ARGS__));   \
+    TR_EMIT(launch_k(t->m->opt_pdl != 0 && !t->m->opt_profile, kernel, grid, block, smem, stream, __VA_ARGS__));   \
     TR_END();                                                                                                      \
   } while (0)
 #define TR_END()                                                           \
   do {                                                                     \
+    if (!t->emit) break;                                                   \
     int prc_ = prof_mark(t->m, stream);                                    \
     if (prc_ != XV_OK) return prc_;                                        \
     prc_ = tr_launch_check(t);                                             \
@@ -307,10 +315,10 @@ int tr_pair_layer(xv_trainer* t, cudaStream_t stream, const char* name, const __
   const int grid = 2 * int(std::min<int64_t>(tiles, m->num_clusters));
   const bool pdl = m->opt_pdl != 0 && !m->opt_profile;
   TR_BEGIN(name);
-  if (col_partial && alpha) TR_CUDA(launch_k(pdl, tdnn2::tdnn_pair_kernel<0, 2, true, true>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
-  else if (col_partial) TR_CUDA(launch_k(pdl, tdnn2::tdnn_pair_kernel<0, 2, false, true>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
-  else if (alpha) TR_CUDA(launch_k(pdl, tdnn2::tdnn_pair_kernel<0, 2, true>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
-  else TR_CUDA(launch_k(pdl, tdnn2::tdnn_pair_kernel<0, 2, false>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
+  if (col_partial && alpha) TR_EMIT(launch_k(pdl, tdnn2::tdnn_pair_kernel<0, 2, true, true>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
+  else if (col_partial) TR_EMIT(launch_k(pdl, tdnn2::tdnn_pair_kernel<0, 2, false, true>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
+  else if (alpha) TR_EMIT(launch_k(pdl, tdnn2::tdnn_pair_kernel<0, 2, true>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
+  else TR_EMIT(launch_k(pdl, tdnn2::tdnn_pair_kernel<0, 2, false>, dim3(grid), dim3(tdnn2::NUM_THREADS), tdnn2::SMEM_BYTES, stream, ta, tw, tc, a));
   TR_END();
   return XV_OK;
 }
@@ -347,7 +355,7 @@ int tr_wgrad(xv_trainer* t, cudaStream_t stream, const char* name, const TrFrame
     const int items = r.k_splits * r.n_groups * r.n_mt * r.n_nt;
     const int grid = 2 * std::min(items, m->num_clusters);
     TR_BEGIN("wgrad_reuse_kernel");
-    TR_CUDA(launch_k(pdl, wgrad::wgrad_reuse_kernel, dim3(grid), dim3(wgrad::NUM_THREADS), wgrad::reuse::SMEM_BYTES, stream, tx, tz, r));
+    TR_EMIT(launch_k(pdl, wgrad::wgrad_reuse_kernel, dim3(grid), dim3(wgrad::NUM_THREADS), wgrad::reuse::SMEM_BYTES, stream, tx, tz, r));
     TR_END();
   } else {
     wgrad::WgradArgs w{};
@@ -366,7 +374,7 @@ int tr_wgrad(xv_trainer* t, cudaStream_t stream, const char* name, const TrFrame
     const int items = w.k_splits * w.taps * w.n_mt * w.n_nt;
     const int grid = 2 * std::min(items, m->num_clusters);
     TR_BEGIN(name);
-    TR_CUDA(launch_k(pdl, wgrad::wgrad_pair_kernel, dim3(grid), dim3(wgrad::NUM_THREADS), wgrad::SMEM_BYTES, stream, tx, tz, w));
+    TR_EMIT(launch_k(pdl, wgrad::wgrad_pair_kernel, dim3(grid), dim3(wgrad::NUM_THREADS), wgrad::SMEM_BYTES, stream, tx, tz, w));
     TR_END();
   }
   const int64_t n4 = int64_t(a.taps) * a.c_in * a.c_out / 4;
@@ -389,9 +397,9 @@ int tr_sgemm(xv_trainer* t, cudaStream_t stream, const char* name, const float* 
   const bool ak = sak == 1, bn = sbn == 1;
   const bool pdl = t->m->opt_pdl != 0 && !t->m->opt_profile;
   TR_BEGIN(name);
-  if (ak && bn) TR_CUDA(launch_k(pdl, trk::sgemm64_kernel<true, true>, grid, dim3(256), 0, stream, a));
-  else if (!ak && bn) TR_CUDA(launch_k(pdl, trk::sgemm64_kernel<false, true>, grid, dim3(256), 0, stream, a));
-  else if (ak && !bn) TR_CUDA(launch_k(pdl, trk::sgemm64_kernel<true, false>, grid, dim3(256), 0, stream, a));
+  if (ak && bn) TR_EMIT(launch_k(pdl, trk::sgemm64_kernel<true, true>, grid, dim3(256), 0, stream, a));
+  else if (!ak && bn) TR_EMIT(launch_k(pdl, trk::sgemm64_kernel<false, true>, grid, dim3(256), 0, stream, a));
+  else if (ak && !bn) TR_EMIT(launch_k(pdl, trk::sgemm64_kernel<true, false>, grid, dim3(256), 0, stream, a));
   else return fail(XV_EINVAL, "sgemm: unsupported operand strides");
   TR_END();
   if (sp.splits > 1) {
@@ -630,8 +638,11 @@ namespace {
 
 // training = true: forward (batch statistics, moving-statistics update) + backward.
 // training = false: forward only with the moving statistics (phase: False), loss and accuracy (Model.eval, models.py:307-354).
+// part: 0 = the whole step; 1 = forward, loss and the segment-level backward (the gradients of embed_layer-*, output/* are final
+// when it ends); 2 = pooling and frame-level backward (+ the overflow flag behind the gradient).  A data-parallel caller runs
+// 1, starts the all-reduce of the segment-level gradients on another stream, runs 2 under it (xv_train_forward_backward_part).
 int tr_step_body(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, int32_t n_seg, int32_t seg_len,
-                 float* grad_dev, float* loss_acc_dev, cudaStream_t stream, bool training) {
+                 float* grad_dev, float* loss_acc_dev, cudaStream_t stream, bool training, int part = 0) {
   xv_model* m = t->m;
   int rc = XV_OK;
   t->last_launches = 0;
@@ -639,6 +650,8 @@ int tr_step_body(xv_trainer* t, const float* feats_dev, const int32_t* labels_de
   t->prof_names.clear();
   float* grad = grad_dev ? grad_dev : t->grad;
   if (t->operands_dirty) { rc = tr_repack(t, stream); if (rc != XV_OK) return rc; }
+  struct EmitGuard { xv_trainer* t; ~EmitGuard() { t->emit = true; } } emit_guard{t};
+  t->emit = part != 2;
   const int nl = int(t->frames.size());
   const int64_t r_pad = t->r_pad;
   constexpr int32_t ROWS_PER_PART = 128;                              // frame layers: rows per partial-sum CTA
@@ -659,8 +672,8 @@ int tr_step_body(xv_trainer* t, const float* feats_dev, const int32_t* labels_de
       // by the weight / data gradient kernels: exact zeros
       const int64_t tail0 = int64_t(n_seg) * t->seg_stride;
       TrFrame& LZ = t->frames[nl - 1];
-      if (r_pad > tail0) TR_CUDA(cudaMemsetAsync(LZ.dz + tail0 * LZ.c_out, 0, size_t(r_pad - tail0) * LZ.c_out * 2, stream));
-      TR_CUDA(cudaMemsetAsync(t->gflag, 0, 4, stream));          // this step's gradient-overflow flag
+      if (r_pad > tail0) TR_EMIT(cudaMemsetAsync(LZ.dz + tail0 * LZ.c_out, 0, size_t(r_pad - tail0) * LZ.c_out * 2, stream));
+      TR_EMIT(cudaMemsetAsync(t->gflag, 0, 4, stream));          // this step's gradient-overflow flag
     }
     xvk::PackArgs a{};
     a.feats = feats_dev;
@@ -796,6 +809,9 @@ int tr_step_body(xv_trainer* t, const float* feats_dev, const int32_t* labels_de
       TR_LAUNCH("l2_term_kernel", trk::l2_term_kernel, dim3(1), dim3(1024), 0, static_cast<const float*>(t->params + tm.off), grad + tm.off, tm.n, tm.coef, loss_acc_dev);
   }
 
+  if (part == 1) return XV_OK;
+  t->emit = true;
+
   // ---- pooling + last layer's BatchNorm + ReLU backward ---------------------------------------------------
   {
     trk::PoolBwdArgs a{};
@@ -862,7 +878,7 @@ int tr_step_body(xv_trainer* t, const float* feats_dev, const int32_t* labels_de
 // this (geometry, buffers) and replayed afterwards -- the host then enqueues one graph instead of 74 kernels (0.87 ms of host
 // time per step otherwise, about what the GPU needs for the step itself).
 int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, int32_t n_seg, int32_t seg_len,
-            float* grad_dev, float* loss_acc_dev, void* stream_, bool training) {
+            float* grad_dev, float* loss_acc_dev, void* stream_, bool training, int part = 0) {
   if (!t || !feats_dev || !labels_dev || !loss_acc_dev) return fail(XV_EINVAL, "null argument");
   if (n_seg < 1 || seg_len < 1) return fail(XV_EINVAL, "need n_seg >= 1 and seg_len >= 1");
   xv_model* m = t->m;
@@ -871,7 +887,7 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
   int rc = tr_ensure_workspace(t, n_seg, seg_len);
   if (rc != XV_OK) return rc;
   if (!training || !t->opt_graph || m->opt_profile)
-    return tr_step_body(t, feats_dev, labels_dev, n_seg, seg_len, grad_dev, loss_acc_dev, stream, training);
+    return tr_step_body(t, feats_dev, labels_dev, n_seg, seg_len, grad_dev, loss_acc_dev, stream, training, part);
   if (t->operands_dirty) { rc = tr_repack(t, stream); if (rc != XV_OK) return rc; }        // never part of the graph
   if (!t->gstream) {
     XV_CUDA(cudaStreamCreateWithFlags(&t->gstream, cudaStreamNonBlocking));
@@ -881,20 +897,21 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
   const void* gkey = grad_dev ? static_cast<const void*>(grad_dev) : static_cast<const void*>(t->grad);
   xv_trainer::StepGraph* found = nullptr;
   for (auto& g : t->graphs)
-    if (g.feats == feats_dev && g.labels == labels_dev && g.grad == gkey && g.loss == loss_acc_dev && g.n_seg == n_seg && g.seg_len == seg_len)
+    if (g.feats == feats_dev && g.labels == labels_dev && g.grad == gkey && g.loss == loss_acc_dev && g.n_seg == n_seg && g.seg_len == seg_len &&
+        g.part == part)
       found = &g;
   if (!found) {
     // egs archives mix minibatch lengths: capturing costs about two steps, so only a geometry that comes back is captured
-    const std::pair<int32_t, int32_t> geo(n_seg, seg_len);
+    const std::pair<int32_t, int32_t> geo(n_seg, seg_len * 4 + part);
     if (std::find(t->seen_geometries.begin(), t->seen_geometries.end(), geo) == t->seen_geometries.end()) {
       if (t->seen_geometries.size() >= 4096) t->seen_geometries.clear();
       t->seen_geometries.push_back(geo);
-      return tr_step_body(t, feats_dev, labels_dev, n_seg, seg_len, grad_dev, loss_acc_dev, stream, true);
+      return tr_step_body(t, feats_dev, labels_dev, n_seg, seg_len, grad_dev, loss_acc_dev, stream, true, part);
     }
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamBeginCapture(t->gstream, cudaStreamCaptureModeThreadLocal);
     if (e == cudaSuccess) {
-      rc = tr_step_body(t, feats_dev, labels_dev, n_seg, seg_len, grad_dev, loss_acc_dev, t->gstream, true);
+      rc = tr_step_body(t, feats_dev, labels_dev, n_seg, seg_len, grad_dev, loss_acc_dev, t->gstream, true, part);
       e = cudaStreamEndCapture(t->gstream, &graph);
     }
     cudaGraphExec_t exec = nullptr;
@@ -903,10 +920,10 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
     if (e != cudaSuccess || rc != XV_OK || !exec) {
       (void)cudaGetLastError();                  // capture not possible here: fall back to plain launches for good
       t->opt_graph = 0;
-      return tr_step_body(t, feats_dev, labels_dev, n_seg, seg_len, grad_dev, loss_acc_dev, stream, true);
+      return tr_step_body(t, feats_dev, labels_dev, n_seg, seg_len, grad_dev, loss_acc_dev, stream, true, part);
     }
     if (t->graphs.size() >= 64) tr_drop_graphs(t);
-    t->graphs.push_back(xv_trainer::StepGraph{feats_dev, labels_dev, gkey, loss_acc_dev, n_seg, seg_len, exec, t->last_launches});
+    t->graphs.push_back(xv_trainer::StepGraph{feats_dev, labels_dev, gkey, loss_acc_dev, n_seg, seg_len, exec, t->last_launches, part});
     found = &t->graphs.back();
   }
   // the caller's stream order is kept: its earlier work -> graph -> its later work
@@ -926,6 +943,14 @@ int xv_train_forward_backward(xv_trainer* t, const float* feats_dev, const int32
                               float* grad_dev, float* loss_acc_dev, void* stream) {
   return tr_step(t, feats_dev, labels_dev, n_seg, seg_len, grad_dev, loss_acc_dev, stream, true);
 }
+
+int xv_train_forward_backward_part(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, int32_t n_seg, int32_t seg_len,
+                                   float* grad_dev, float* loss_acc_dev, void* stream, int32_t part) {
+  if (part < 0 || part > 2) return fail(XV_EINVAL, "part must be 0, 1 or 2");
+  return tr_step(t, feats_dev, labels_dev, n_seg, seg_len, grad_dev, loss_acc_dev, stream, true, part);
+}
+
+int64_t xv_train_segment_grad_offset(const xv_trainer* t) { return t ? t->seg[0].off_w : 0; }
 
 int xv_train_eval(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, int32_t n_seg, int32_t seg_len,
                   float* loss_acc_dev, void* stream) {

@@ -314,7 +314,7 @@ class Model(object):
         dev = torch.device("cuda:%d" % eng.device)
         # data parallel (gradient all-reduce) unless the caller runs independent jobs per rank (train_dnn.py: args.data_parallel=False)
         world = sharding.dist_info()[1] if data_parallel else 1
-        compute, copy = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        compute, copy, comm = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         minibatch_count = data_loader.count
         if training and world > 1:
             # every rank must step the same number of times (one gradient all-reduce per minibatch): check before the loop
@@ -427,10 +427,12 @@ class Model(object):
                     tr.convert_f16(sl["half_dev"], sl["feats_dev"], n_seg * seg_len * shape[2], stream=compute)
                 feats_dev = sl["feats_dev"][:n_seg * seg_len * shape[2]].view(n_seg * seg_len, shape[2])
                 if training:
-                    la = tr.forward_backward(feats_dev, sl["labels_dev"][:n_seg], n_seg, seg_len, grad_dev=grad, stream=compute)
-                    if grad is not None:            # data parallel: sum the flat gradient over the ranks (NCCL)
-                        import torch.distributed as dist
-                        dist.all_reduce(grad)
+                    if grad is not None:
+                        # data parallel: sum the flat gradient (+ the overflow flag behind it) over the ranks (NCCL); the
+                        # segment-level 60 % of it is reduced on `comm` under the frame-level backward
+                        la = tr.forward_backward_allreduce(feats_dev, sl["labels_dev"][:n_seg], n_seg, seg_len, grad, compute, comm)
+                    else:
+                        la = tr.forward_backward(feats_dev, sl["labels_dev"][:n_seg], n_seg, seg_len, grad_dev=grad, stream=compute)
                     tr.apply(learning_rate, grad_dev=grad, grad_scale=1.0 / world, stream=compute)
                 else:
                     la = tr.evaluate(feats_dev, sl["labels_dev"][:n_seg], n_seg, seg_len, stream=compute)
