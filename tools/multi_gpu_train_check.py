@@ -77,7 +77,7 @@ for i in range(MB):
     torch.cuda.synchronize()
 worst = 0.0
 for name, arr in dp.items():
-    if name.endswith(("/Adam:0", "/Adam_1:0", "_power:0")) or name.endswith(("mean:0", "variance:0")):
+    if name.endswith(("/Adam:0", "/Adam_1:0", "_power:0", "_step:0")) or name.endswith(("mean:0", "variance:0")):
         continue
     ref = trs[0].get_param(name).reshape(arr.shape)
     d = float(np.abs(ref - arr).max() / max(np.abs(arr).max(), 1e-30))
