@@ -406,12 +406,20 @@ def run_b200(args):
     k0_pad = -(-topo["kernel_sizes"][0] * FEAT_DIM // 128) * 128
     n_blk = B * (-(-T // 32))
     # (kernel, bound, algorithmic FLOP or bytes per launch) in launch order
-    table = [("pack_im2col_kernel", "hbm", frames * (FEAT_DIM * 4 + k0_pad * 2 + 1))]
+    n_tail = 2 + (3 if topo.get("pooling") == "attention" else 0)       # launches behind the frame layers (+ attention's three)
+    # launches in front of pool_stats: [pack +] layer 0 (+ splice), layers 1..n-3, then the last two layers as one or two launches
+    n_front = len(kms) - 1 - n_tail
+    # len(fl) - 1: splice inside layer 0's kernel AND the last two layers as one launch (the default topologies);
+    # len(fl) + 1: neither (attention pooling / split precision); len(fl): read as "pack launch + fused last two layers"
+    fused_first = n_front == len(fl) - 1
+    fused_tail = n_front <= len(fl)
     # layer 0 (K = 128) is bound by its own output stream (K0 = 117 760 FLOP / (92 + 1 024) B = 105 FLOP/B, HBM-bound):
     # judged against HBM with SURVEY's algorithmic bytes per frame (fp32 features in, fp16 activations out); layers 1.. tensor bound
-    table += [("tdnn_pair_kernel[L0]", "hbm", frames * (FEAT_DIM * 4 + topo["layer_sizes"][0] * 2))]
-    n_tail = 2 + (3 if topo.get("pooling") == "attention" else 0)       # launches behind the frame layers (+ attention's three)
-    fused_tail = len(kms) == 1 + (len(fl) - 1) + 1 + n_tail               # pack, layers 0..n-3, fused last two, pool_stats, embed, reduce
+    if fused_first:
+        table = [("tdnn_first_kernel[splice+L0]", "hbm", frames * (FEAT_DIM * 4 + topo["layer_sizes"][0] * 2))]
+    else:
+        table = [("pack_im2col_kernel", "hbm", frames * (FEAT_DIM * 4 + k0_pad * 2 + 1)),
+                 ("tdnn_pair_kernel[L0]", "hbm", frames * (FEAT_DIM * 4 + topo["layer_sizes"][0] * 2))]
     if fused_tail:
         table += [("tdnn_pair_kernel[L%d]" % i, "tensor", frames * f) for i, f in enumerate(fl) if 0 < i < len(fl) - 2]
         table += [("tdnn_tail_fused_kernel[L%d+L%d]" % (len(fl) - 2, len(fl) - 1), "tensor", frames * (fl[-2] + fl[-1]))]
@@ -437,11 +445,14 @@ def run_b200(args):
             d.update(achieved=round(gbs, 1), unit="GB/s", frac=round(gbs / peaks["hbm_gbs"], 4))
         launches.append(d)
     n_layer_launches = len(fl) - 1 if fused_tail else len(fl)
-    tdnn_ms = float(kms[1:1 + n_layer_launches].sum())
+    first_layer = 0 if fused_first else 1                               # index of layer 0's launch
+    tdnn_ms = float(kms[first_layer:first_layer + n_layer_launches].sum())
     tdnn_tf = frames * sum(fl) / (tdnn_ms * 1e-3) / 1e12
     traffic, traffic_src = ncu_traffic_bytes(args.topology)
-    roofline = dict(kernel="tdnn_pair_kernel x%d%s (%d launches/step, figures are per-step sums / averages)"
-                           % (n_layer_launches - (1 if fused_tail else 0), " + tdnn_tail_fused_kernel" if fused_tail else "", n_layer_launches),
+    roofline = dict(kernel="%stdnn_pair_kernel x%d%s (%d launches/step, figures are per-step sums / averages)"
+                           % ("tdnn_first_kernel + " if fused_first else "",
+                              n_layer_launches - (1 if fused_tail else 0) - (1 if fused_first else 0),
+                              " + tdnn_tail_fused_kernel" if fused_tail else "", n_layer_launches),
                     bound="tensor", achieved=round(tdnn_tf, 1), peak=peaks["tflops"], unit="TFLOP/s",
                     frac=round(tdnn_tf / peaks["tflops"], 4), traffic=traffic,
                     traffic_source=("profiles/%s: mean DRAM bytes per launch over the %d frame-layer launches of one captured step of %s "
@@ -503,15 +514,16 @@ def run_b200(args):
             dk.append(deng.last_kernel_ms())
         deng.set_option("profile", 0)
         dk = np.asarray(dk, dtype=np.float64).mean(axis=0)
-        d_n = len(dfl) - 1 if len(dk) == len(dfl) + 3 else len(dfl)      # last two layers fused: one launch fewer
-        d_layers = float(dk[1:1 + d_n].sum())
+        d_n = len(dfl) - 1                                                 # last two layers fused: one launch fewer
+        d_first = len(dk) - 3 - d_n                                        # 1 with a separate pack launch, 0 with the splice in layer 0's kernel
+        d_layers = float(dk[d_first:d_first + d_n].sum())
         d_tf = frames * sum(dfl) / (d_layers * 1e-3) / 1e12
         dense = dict(workload="configs[1] with ModelWithoutDropout (taps %s)" % dtopo["kernel_sizes"], ms_per_step=round(d_ms, 5),
                      value_per_gpu=round(frames / (d_ms * 1e-3), 1), unit=UNIT,
                      roofline=dict(bound="tensor", achieved=round(d_tf, 1), peak=peaks["tflops"], unit="TFLOP/s",
                                    frac=round(d_tf / peaks["tflops"], 4), share_of_step=round(d_layers / float(dk.sum()), 4),
                                    traffic=ncu_traffic_bytes("ModelWithoutDropout")[0],
-                                   layer_ms=[round(float(v), 5) for v in dk[1:1 + d_n]]),
+                                   layer_ms=[round(float(v), 5) for v in dk[d_first:d_first + d_n]]),
                      step_frac_of_tensor_peak=round(frames * sum(dfl) / (d_ms * 1e-3) / 1e12 / peaks["tflops"], 4))
         deng.close()
 

@@ -224,7 +224,7 @@ def test_extract_host_equals_device_forward():
     dev = _run(eng, feats, lens)
     host = eng.extract_host(feats, lens)
     assert np.array_equal(dev, host)
-    assert eng.last_launch_count == 8          # pack + 3 layers + fused last two layers + pool stats + embed GEMM + K-split reduction
+    assert eng.last_launch_count == 7          # spliced first layer + 2 layers + fused last two layers + pool stats + embed GEMM + K-split reduction
     eng.close()
 
 
@@ -389,6 +389,47 @@ def test_fused_tail_is_bit_identical_to_one_launch_per_layer(topology, weight_se
     assert np.array_equal(fused, plain)
     offs = np.concatenate([[0], np.cumsum(lens)])
     pick = [0, 7, 59, 60, 62]
+    want = np.stack([orc.forward(feats[offs[i]:offs[i + 1]], params, topology) for i in pick])
+    m = orc.parity_metrics(fused[pick], want)
+    assert m["max_rel"] <= TOL and m["l2_rel"] <= TOL, m
+    eng.close()
+
+
+@pytest.mark.parametrize("topology,weight_set", [("ModelWithoutDropoutTdnn", "B"), ("ModelWithoutDropout", "A"),
+                                                 ("ModelL2LossWithoutDropoutLRelu", "B"), ("ModelWithoutDropoutPRelu", "B")])
+def test_fused_first_layer_is_bit_identical_to_pack_plus_layer_launch(topology, weight_set):
+    # tdnn_first.cuh splices the 5 taps of the 23 cepstra inside the first layer's kernel (A operand written straight into
+    # shared memory) instead of pack_im2col_kernel + tdnn_pair_kernel: same values, same K order, same epilogue -- not one
+    # bit of the stored rows, of any later layer or of the x-vectors may differ
+    import torch
+    eng, params = _engine(topology, weight_set)
+    lens = np.concatenate([synthetic.lengths_uniform(92, 60, 25, 700), [25, 1, 2, 31, 32, 33, 10000 - 7]]).astype(np.int32)
+    feats = synthetic.mfcc_batch(92, lens)
+    fused = _run(eng, feats, lens)
+    n_fused = eng.last_launch_count
+    emb_f, layers_f, stats_f = eng.forward(torch.from_numpy(feats).cuda(), lens, return_layers=True)
+    torch.cuda.synchronize()
+    layers_f = [l.cpu().numpy() for l in layers_f]
+    stats_f = stats_f.cpu().numpy()
+    # the float16 feed of the product path (rows rounded on the host; the device's first step is the same rounding)
+    out16, out32 = torch.empty((len(lens), 512)).pin_memory(), torch.empty((len(lens), 512)).pin_memory()
+    eng.collect(eng.submit_host_utts(feats.astype(np.float16), lens, out_host=out16))
+    eng.collect(eng.submit_host_utts(feats, lens, out_host=out32))
+    assert np.array_equal(out16.numpy(), out32.numpy())
+    feed16 = out16.numpy().copy()
+    eng.set_option("fuse_first", 0)
+    plain = _run(eng, feats, lens)
+    assert eng.last_launch_count == n_fused + 1
+    assert np.array_equal(fused, plain)
+    eng.collect(eng.submit_host_utts(feats.astype(np.float16), lens, out_host=out16))
+    assert np.array_equal(out16.numpy(), feed16)
+    emb_p, layers_p, stats_p = eng.forward(torch.from_numpy(feats).cuda(), lens, return_layers=True)
+    torch.cuda.synchronize()
+    for lf, lp in zip(layers_f, layers_p):
+        assert np.array_equal(lf, lp.cpu().numpy())
+    assert np.array_equal(stats_f, stats_p.cpu().numpy())
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    pick = [0, 7, 59, 60, 61, 62, 66]
     want = np.stack([orc.forward(feats[offs[i]:offs[i + 1]], params, topology) for i in pick])
     m = orc.parity_metrics(fused[pick], want)
     assert m["max_rel"] <= TOL and m["l2_rel"] <= TOL, m

@@ -33,7 +33,7 @@ feats = torch.from_numpy(synthetic.mfcc_batch(2, lens)).cuda()
 emb = torch.empty((args.batch, 512), dtype=torch.float32, device="cuda")
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 stream = torch.cuda.current_stream()
-DEFAULTS = dict(resident=0, prefetch=0, fc=1, fc_max_splits=36, pdl=1, fuse_tail=1)
+DEFAULTS = dict(resident=0, prefetch=0, fc=1, fc_max_splits=36, pdl=1, fuse_tail=1, fuse_first=1)
 
 
 def apply(cfg):
@@ -68,13 +68,37 @@ def measure(steps):
     return step, np.median(np.asarray(ks), axis=0)
 
 
+feats_host = [torch.from_numpy(synthetic.mfcc_batch(2, lens)).pin_memory(), torch.from_numpy(synthetic.mfcc_batch(3, lens)).pin_memory()]
+emb_host = [torch.empty((args.batch, 512)).pin_memory(), torch.empty((args.batch, 512)).pin_memory()]
+
+
+def measure_e2e(steps):
+    """ms/step through xv_submit_host_utts / xv_collect with pinned host buffers, two in flight (bench.py's e2e)."""
+    import time
+    def run(n):
+        prev = None
+        t0 = time.perf_counter()
+        for i in range(n):
+            t = eng.submit_host_utts(feats_host[i & 1], lens, out_host=emb_host[i & 1])
+            if prev is not None:
+                eng.collect(prev)
+            prev = t
+        eng.collect(prev)
+        return (time.perf_counter() - t0) * 1e3 / n
+    run(5)
+    return run(steps)
+
+
 res = {c: [] for c in args.configs}
+e2e = {c: [] for c in args.configs}
 for r in range(args.rounds):
     for c in args.configs:
         apply(c)
         res[c].append(measure(args.steps))
+        e2e[c].append(measure_e2e(max(args.steps, 40)))
 for c in args.configs:
     steps = np.array([x[0] for x in res[c]])
     ks = np.median(np.stack([x[1] for x in res[c]]), axis=0)
     print("%-40s step ms median %.4f (min %.4f max %.4f) | kernels us: %s" %
           (c, np.median(steps), steps.min(), steps.max(), " ".join("%.1f" % (k * 1e3) for k in ks)), flush=True)
+    print("%-40s e2e ms/step median %.4f (min %.4f max %.4f)" % ("", np.median(e2e[c]), min(e2e[c]), max(e2e[c])), flush=True)

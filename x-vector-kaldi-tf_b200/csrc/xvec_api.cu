@@ -18,6 +18,7 @@
 #include "pack_pool.cuh"
 #include "tdnn_pair.cuh"
 #include "tdnn_tail.cuh"
+#include "tdnn_first.cuh"
 
 namespace {
 
@@ -105,6 +106,8 @@ struct xv_model {
   float* w0_dev = nullptr;           // [2C, E]
   float* b0_dev = nullptr;           // [E]
   int32_t* pack_lut_dev = nullptr;   // [k0_pad] spliced column -> staged feature offset (pack kernel)
+  bool first_fusable = false;        // the topology fits tdnn_first_kernel (tdnn_first.cuh)
+  int opt_fuse_first = 1;            // 1: the input splice and the first frame layer run as ONE kernel; 0: pack_im2col + tdnn_pair
   uint32_t* overflow_dev = nullptr;  // [1 + XV_HOST_SLOTS] flag words: [0] xv_forward / training, [1 + s] submission slot s
   uint32_t* cur_flag = nullptr;      // the word the kernels of the enqueue in progress report to
   int cur_feats_f16 = 0;             // 1 while an enqueue's features are float16 values (xv_submit_host_utts_f16)
@@ -622,8 +625,11 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
   m->prof_used = 0;
 #define XV_PROF() do { int prc_ = prof_mark(m, stream); if (prc_ != XV_OK) return prc_; } while (0)
 
+  // the input splice inside the first layer's kernel (tdnn_first.cuh) unless the topology or an option asks for the two launches
+  const bool fuse_first = m->opt_fuse_first && m->first_fusable && !m->opt_split && !m->opt_resident &&
+                          reinterpret_cast<uintptr_t>(feats_dev) % 16 == 0;
   // ---- pack: fp32 features -> spliced fp16 packed rows + row / block maps --------------------
-  {
+  if (!fuse_first) {
     xvk::PackArgs a{};
     a.feats = feats_dev;
     a.r_pad = int32_t(r_pad);
@@ -700,6 +706,49 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
     const FrameLayer& L = m->layers[i];
     const bool last = i == nl - 1;
     __half* out = last ? hlast : ((i & 1) ? hb : ha);
+    if (fuse_first && i == 0) {
+      CUtensorMap tw, tc;
+      rc = encode_2d(m, &tw, L.w_dev, uint64_t(L.k_total), uint64_t(L.c_out), tdnn2::BLOCK_K, tdnn2::CTA_CH, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc != XV_OK) return rc;
+      rc = encode_2d(m, &tc, out, uint64_t(L.c_out), uint64_t(r_pad), tdnn2::C_CHUNK, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc != XV_OK) return rc;
+      tdnn2::FirstArgs a{};
+      a.n_row_tiles = int32_t(r_pad / tdnn2::TILE_ROWS);
+      a.n_ch_tiles = L.c_out / tdnn2::TILE_CH;
+      a.c_out = L.c_out;
+      a.feat_dim = m->topo.feat_dim;
+      a.halo = (L.taps - 1) / 2 * L.dilation;
+      a.feats = feats_dev;
+      a.feats_f16 = m->cur_feats_f16;
+      a.n_feat_bytes = total * m->topo.feat_dim * (m->cur_feats_f16 ? 2 : 4);
+      a.taps = L.taps;
+      a.blk_info = blk_info_dev;
+      a.bias = L.bias_dev; a.scale = L.scale_dev; a.shift = L.shift_dev; a.alpha = L.alpha_dev;
+      a.row_valid = row_valid;
+      a.blk_valid = blk_valid;
+      a.counters = counters;
+      a.n_counters = p.n_counters;
+      a.overflow_flag = m->cur_flag;
+      a.overflow_bit = 1u << 8;
+      a.trace = (m->opt_trace_layer == 0) ? m->opt_trace : nullptr;
+      const int grid = 2 * int(std::min<int64_t>(a.n_row_tiles, m->num_clusters));
+      XV_PROF();
+      if (L.alpha_dev != nullptr)
+        XV_CUDA(launch_k(pdl, tdnn2::tdnn_first_kernel<true>, dim3(grid), dim3(tdnn2::F1_THREADS), tdnn2::F1_SMEM_BYTES, stream, tw, tc, a));
+      else
+        XV_CUDA(launch_k(pdl, tdnn2::tdnn_first_kernel<false>, dim3(grid), dim3(tdnn2::F1_THREADS), tdnn2::F1_SMEM_BYTES, stream, tw, tc, a));
+      XV_PROF();
+      XV_CUDA(cudaGetLastError());
+      ++launches;
+      if (layer_out_dev && layer_out_dev[i]) {
+        XV_CUDA(launch_k(pdl, xvk::unpack_rows_kernel, dim3(n_seg), dim3(256), 0, stream, static_cast<const __half*>(out), seg, int32_t(L.c_out), layer_out_dev[i],
+                         std::ldexp(1.0f, L.exp_out), int32_t(0)));
+        XV_CUDA(cudaGetLastError());
+        ++launches;
+      }
+      in = out;
+      continue;
+    }
     const int halo = (L.gemm_taps - 1) / 2 * L.dilation;
     const int c_in_real = (i == 0) ? L.k_total : L.c_in_pad;       // values per input row
     const int split = m->opt_split ? 1 : 0;
@@ -1071,6 +1120,8 @@ int xv_create(xv_model** out, int device, const xv_topology* topo) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tdnn2::tdnn_tail_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::FT_SMEM_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tdnn2::tdnn_tail_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::FT_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tdnn2::tdnn_first_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::F1_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tdnn2::tdnn_first_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tdnn2::F1_SMEM_BYTES);
   }
   if (e == cudaSuccess) {
     cudaLaunchConfig_t cfg{};
@@ -1092,6 +1143,9 @@ int xv_create(xv_model** out, int device, const xv_topology* topo) {
     std::vector<int32_t> lut(m->k0_pad, -1);
     const FrameLayer& L0 = m->layers[0];
     for (int ch = 0; ch < L0.taps * t.feat_dim; ++ch) lut[ch] = (ch / t.feat_dim) * L0.dilation * t.feat_dim + ch % t.feat_dim;
+    const int halo0 = (L0.taps - 1) / 2 * L0.dilation;
+    m->first_fusable = m->k0_pad == tdnn2::F1_K && L0.dilation == 1 && L0.c_out <= tdnn2::F1_MAX_CT * tdnn2::TILE_CH &&
+                       (32 + 2 * halo0) * t.feat_dim * 4 + 30 <= tdnn2::F1_STAGE_BYTES;
     e = cudaMalloc(&m->pack_lut_dev, lut.size() * 4);
     if (e == cudaSuccess) e = cudaMemcpy(m->pack_lut_dev, lut.data(), lut.size() * 4, cudaMemcpyHostToDevice);
   }
@@ -1509,6 +1563,7 @@ int xv_set_option(xv_model* m, const char* name, int64_t value) {
   else if (n == "blocking_collect") m->opt_blocking_collect = value != 0;
   else if (n == "rescue") m->opt_rescue = value != 0;
   else if (n == "fuse_tail") m->opt_fuse_tail = value != 0;
+  else if (n == "fuse_first") m->opt_fuse_first = value != 0;
   else if (n == "precision") { m->opt_split = value != 0; m->dirty = true; }
   else if (n == "fc_max_splits") m->opt_fc_max_splits = std::max(1, int(value));
   else if (n == "trace_ptr") m->opt_trace = reinterpret_cast<long long*>(static_cast<intptr_t>(value));   // device buffer
