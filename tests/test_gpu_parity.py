@@ -436,6 +436,31 @@ def test_fused_first_layer_is_bit_identical_to_pack_plus_layer_launch(topology, 
     eng.close()
 
 
+@pytest.mark.parametrize("feat_dim,kernel_sizes,dilations,layer_sizes,launches", [
+    (24, [5, 3, 3, 1, 1], [1, 2, 3, 1, 1], [512, 512, 512, 512, 1536], 7),    # 120 -> 128 spliced columns: in-kernel splice
+    (20, [3, 3, 3, 1, 1], [1, 2, 3, 1, 1], [256, 512, 512, 512, 1536], 7),    # half context 1, ONE channel tile in the first layer
+    (30, [5, 3, 3, 1, 1], [1, 2, 3, 1, 1], [512, 512, 512, 512, 1536], 8),    # 150 -> 256 columns: pack_im2col + layer launch
+    (23, [5, 3, 3, 1, 1], [2, 2, 3, 1, 1], [512, 512, 512, 512, 1536], 8),    # dilated first layer: pack_im2col + layer launch
+])
+def test_first_layer_geometries_in_kernel_splice_or_two_launches(feat_dim, kernel_sizes, dilations, layer_sizes, launches):
+    # tdnn_first.cuh takes the first layer when its spliced input is 128 wide with dilation 1; every other geometry keeps the
+    # pack kernel.  Both against the oracle, on a ragged batch with 1-frame and block-boundary segments.
+    from xvector_b200 import _native
+    topo = dict(kernel_sizes=kernel_sizes, dilations=dilations, layer_sizes=layer_sizes, embedding_sizes=[512, 512])
+    params = synthetic.make_params(kernel_sizes, layer_sizes, [512, 512], feat_dim=feat_dim, weight_set="B")
+    eng = _native.XvecEngine(kernel_sizes, dilations, layer_sizes, 512, feat_dim, device=0)
+    eng.set_params(params)
+    lens = np.array([200, 57, 1, 32, 33, 31, 64, 333, 25], np.int32)
+    feats = synthetic.mfcc_batch(93, lens, feat_dim)
+    got = _run(eng, feats, lens)
+    assert eng.last_launch_count == launches
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    want = np.stack([orc.forward(feats[offs[i]:offs[i + 1]], params, topo) for i in range(len(lens))])
+    m = orc.parity_metrics(got, want)
+    assert m["max_rel"] <= TOL and m["l2_rel"] <= TOL, m
+    eng.close()
+
+
 @pytest.mark.parametrize("topology", ["ModelWithoutDropoutTdnn", "ModelWithoutDropout"])
 def test_split_precision_option_gives_fp32_grade_x_vectors(topology):
     # option "precision" = 1 on the statistics-pooling topologies: every contraction as hi*hi + hi*lo + lo*hi of two-term fp16

@@ -52,3 +52,8 @@ if n > 3:
     print("epilogue busy (epi_done - epi_sees):", (x[1:n, 6] - x[1:n, 4]).tolist())
     print("mma issue span (mma_issued - mma_start):", (x[1:n, 3] - x[1:n, 2]).tolist())
     print("accumulator ready after last MMA issued (epi_sees - mma_issued):", (x[1:n, 4] - x[1:n, 3]).tolist())
+
+# SM clock during the kernel: slot 7 of the fused tail kernel holds %globaltimer (ns) taken together with slot 2 (mma_start)
+if (x[:n, 7] > 10**15).all() and n > 8:
+    dc = float(x[n - 1, 2] - x[1, 2]); dt = float(x[n - 1, 7] - x[1, 7])
+    print("SM clock over jobs 1..%d: %.0f MHz (%d cycles in %.1f us)" % (n - 1, dc / dt * 1e3, dc, dt / 1e3))

@@ -63,8 +63,12 @@ struct FusedTailArgs {
   long long* trace;         // diagnostics: [cluster][rank][TRACE_TILES jobs][8] SM clock stamps (slots as in tdnn_pair.cuh), or null
 };
 __device__ __forceinline__ void ft_stamp(const FusedTailArgs& a, int cluster, uint32_t rank, uint32_t job, int slot) {
-  if (a.trace != nullptr && job < TRACE_TILES)
+  if (a.trace != nullptr && job < TRACE_TILES) {
     a.trace[((size_t(cluster) * 2 + rank) * TRACE_TILES + job) * 8 + slot] = clock64();
+    // slot 7 <- %globaltimer (ns) next to the "MMA start" stamp: calibrates the SM clock DURING the kernel (measured: 1 557 MHz
+    // while nvidia-smi reports 1 965 -- the tensor kernels of a step run clocked down)
+    if (slot == 2) a.trace[((size_t(cluster) * 2 + rank) * TRACE_TILES + job) * 8 + 7] = (long long)ptx::globaltimer_ns();
+  }
 }
 
 __device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
