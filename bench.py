@@ -96,7 +96,7 @@ def ncu_traffic_bytes(topology):
     with open(path) as f:
         rows = [r for r in json.load(f) if r.get("report", "").endswith("prof_%s.ncu-rep" % topology) and
                 ("tdnn_pair_kernel<0" in r.get("kernel", "") or "tdnn_pair_kernel<1" in r.get("kernel", "") or
-                 "tdnn_tail_fused_kernel" in r.get("kernel", ""))]
+                 "tdnn_tail_fused_kernel" in r.get("kernel", "") or "tdnn_first_kernel" in r.get("kernel", ""))]
     vals = [(r["dram_read_MB"] + r["dram_write_MB"]) * 1e6 for r in rows if r.get("dram_read_MB") is not None]
     return (round(sum(vals) / len(vals)) if vals else None), NCU_TRAFFIC_FILE
 
