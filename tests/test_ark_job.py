@@ -444,3 +444,24 @@ def test_reader_can_round_rows_to_float16_on_the_way_into_the_batches(tmp_path):
             out = np.zeros(len(x) + 16, np.uint16)
             fn(x.ctypes.data, out.ctypes.data + 2 * off, len(x))
             assert np.array_equal(out[off:off + len(x)], want)
+
+
+def test_scp_line_offsets_are_known_before_a_line_is_formatted():
+    # what lets every rank write its own byte range of the one scp: line lengths from key lengths and the decimal digits
+    # of the marker offsets alone -- checked against the formatter across every power of ten an offset can cross
+    from xvector_b200 import ark_job
+    rng = np.random.default_rng(5)
+    entry = 11 + 4 * 512
+    for base in (0, 1, 7, 93, 998, 9_990, 99_000, 999_999, 9_999_000, 99_990_000, 10 ** 10 - 5000, 10 ** 12 + 3):
+        n = 37
+        klens = rng.integers(1, 30, n)
+        keys = ["".join(chr(97 + int(c)) for c in rng.integers(0, 26, k)) for k in klens]
+        blob = np.frombuffer("".join(keys).encode(), np.uint8)
+        off = np.concatenate([[0], np.cumsum(klens)]).astype(np.int64)
+        markers = off[:-1] + np.arange(n) * entry + klens + 1
+        lines = _native.scp_format(blob, off, "/some/where/x.ark", base, markers)
+        cum = ark_job.scp_line_offsets(off, "/some/where/x.ark", base, entry)
+        assert int(cum[-1]) == lines.shape[0]
+        text = lines.tobytes().decode().splitlines(keepends=True)
+        assert [len(t) for t in text] == np.diff(cum).tolist()
+        assert text[3] == "%s /some/where/x.ark:%d\n" % (keys[3], base + markers[3])

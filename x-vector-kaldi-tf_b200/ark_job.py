@@ -141,7 +141,8 @@ def shared_output_spec(output_stream, total_bytes):
             output_stream.ark.flush()
             output_stream.scp.flush()
             os.ftruncate(output_stream.ark.fileno(), int(output_stream.pos) + int(total_bytes))
-            return dict(ark=os.path.abspath(output_stream.ark.name), base=int(output_stream.pos), scp_name=output_stream.name)
+            return dict(ark=os.path.abspath(output_stream.ark.name), base=int(output_stream.pos), scp_name=output_stream.name,
+                        scp=os.path.abspath(output_stream.scp.name), scp_base=int(os.fstat(output_stream.scp.fileno()).st_size))
         if isinstance(output_stream, io.BufferedWriter) and isinstance(output_stream.name, str) and \
                 stat.S_ISREG(os.fstat(output_stream.fileno()).st_mode):
             output_stream.flush()
@@ -181,16 +182,37 @@ def populate_pages(mapped, offset, length):
     return t
 
 
-def finish_shared_output(output_stream, spec, total_bytes, scp_parts):
-    """Rank 0, after every rank has written its byte range: move the writer behind the job's entries and append the scp
-    lines the ranks produced (in rank order)."""
+_POW10 = np.array([10 ** k for k in range(1, 19)], dtype=np.int64)
+
+
+def scp_line_offsets(key_off, ark_name, first_marker_base, entry_bytes):
+    """Byte offset of every scp line ``key ark_name:offset\n`` of a run of entries (int64 [n + 1], starting at 0), computed
+    WITHOUT formatting them: entry i starts ``key_off[i] + i * entry_bytes`` bytes behind ``first_marker_base`` and its
+    offset is that of its binary marker, ``len(key) + 1`` further on.  This is what lets every rank of a job write its own
+    byte range of the ONE scp (sizes are exchanged before a single line exists)."""
+    key_off = np.asarray(key_off, dtype=np.int64)
+    klen = np.diff(key_off)
+    n = int(klen.shape[0])
+    marker = first_marker_base + (key_off[:-1] - key_off[0]) + np.arange(n, dtype=np.int64) * entry_bytes + klen + 1
+    digits = 1 + np.searchsorted(_POW10, marker, side="right")
+    out = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(klen + len(os.fsencode(ark_name)) + 3 + digits, out=out[1:])
+    return out
+
+
+def extend_shared_scp(output_stream, spec, total_scp_bytes):
+    """Rank 0: make room for the job's scp lines behind what the writer already holds (the ranks map their ranges of it)."""
+    output_stream.scp.flush()
+    os.ftruncate(output_stream.scp.fileno(), int(spec["scp_base"]) + int(total_scp_bytes))
+
+
+def finish_shared_output(output_stream, spec, total_bytes):
+    """Rank 0, after every rank has written its byte ranges (ark and scp): move the writer behind the job's entries."""
     end = spec["base"] + total_bytes
     if spec["scp_name"] is not None:
         output_stream.ark.seek(end)
         output_stream.pos = end
-        for part in scp_parts:
-            if len(part):
-                output_stream.scp.write(part.tobytes().decode())
+        output_stream.scp.seek(0, os.SEEK_END)
     else:
         output_stream.seek(end)
 

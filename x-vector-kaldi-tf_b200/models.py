@@ -695,6 +695,7 @@ class Model(object):
                      tail_s=0.0, batches=0)
         self.last_job_stats = stats                  # where the wall time of the last native job went (bench / diagnostics)
         peer, shared_fd, shared_map, shared_view, populate = None, None, None, None, None
+        scp_fd, scp_map, scp_view, scp_cum = None, None, None, None
         try:
             if logger is not None:
                 for key, reason, rows in reader.failures():
@@ -749,7 +750,6 @@ class Model(object):
                     mode = "host_gather"
                     stats["output"] = mode
             ark_base = 0
-            scp_parts = []
             if mode == "shared_file":
                 # this rank's byte range of the one ark, mapped: entries are formatted straight into the file's pages.
                 # (write / pwrite would serialise the ranks on the file's inode lock: measured 98 ms for 26 MB per rank)
@@ -762,6 +762,21 @@ class Model(object):
                     shared_map = mmap.mmap(shared_fd, ark_base - map_from + my_bytes, offset=map_from)
                     shared_view = np.frombuffer(shared_map, dtype=np.uint8)[ark_base - map_from:]
                     populate = ark_job.populate_pages(shared_map, ark_base - map_from, my_bytes)      # page faults off the critical path
+                if shared["scp_name"] is not None:
+                    # ... and of the one scp: a line's length follows from its key and the decimal digits of its offset, so the
+                    # ranks exchange their scp sizes before a line exists and each writes its own range (rank 0 gathering and
+                    # writing a million lines was the tail of the job: 57 of 443 ms at 8 GPUs)
+                    scp_cum = ark_job.scp_line_offsets(key_off, shared["scp_name"], ark_base, entry_bytes)
+                    scp_sizes = ark_job._all_gather_i64([int(scp_cum[-1])], dev_name)[:, 0]
+                    if rank == 0:
+                        ark_job.extend_shared_scp(output_stream, shared, int(scp_sizes.sum()))
+                    dist.barrier()                       # the scp has its final size
+                    my_scp, scp_base = int(scp_sizes[rank]), int(shared["scp_base"]) + int(scp_sizes[:rank].sum())
+                    if my_scp > 0:
+                        scp_fd = os.open(shared["scp"], os.O_RDWR)
+                        map_from = scp_base // mmap.ALLOCATIONGRANULARITY * mmap.ALLOCATIONGRANULARITY
+                        scp_map = mmap.mmap(scp_fd, scp_base - map_from + my_scp, offset=map_from)
+                        scp_view = np.frombuffer(scp_map, dtype=np.uint8)[scp_base - map_from:]
             reader.start(base if mode == "peer" else 0)
             host_rows = [None, None]                     # page-locked [n_utt, emb_dim] per submission slot
             local = [] if mode == "host_gather" else None
@@ -806,7 +821,11 @@ class Model(object):
                         rel = int(window[0]) + done.first_ok_index * entry_bytes      # offset inside this rank's range
                         _, markers = vec_ark_format(key_blob, window, rows, with_markers=True, out=shared_view[rel:])
                         if shared["scp_name"] is not None:
-                            scp_parts.append(scp_format(key_blob, window, shared["scp_name"], ark_base + rel, markers))
+                            lines = scp_format(key_blob, window, shared["scp_name"], ark_base + rel, markers)
+                            lo = int(scp_cum[done.first_ok_index])
+                            if lo + lines.shape[0] != int(scp_cum[done.first_ok_index + done.n_utt]):
+                                raise RuntimeError("scp lines of a batch do not fill their planned byte range")
+                            scp_view[lo:lo + lines.shape[0]] = lines
                     elif mode == "host_gather":
                         local.append(rows.copy())
                     reader.release(done.slot)
@@ -816,11 +835,10 @@ class Model(object):
                     break
             t_tail = time.time()
             if mode == "shared_file":
-                lines = ark_job.gather_bytes_to_rank0(np.concatenate(scp_parts) if scp_parts else np.zeros(0, np.uint8), dev_name)
-                dist.barrier()                           # every rank's byte range of the ark is written
+                dist.barrier()                           # every rank's byte ranges of the ark and of the scp are written
                 if rank == 0:
                     total = int((counts[:, 5] + counts[:, 1] * entry_bytes).sum())
-                    ark_job.finish_shared_output(output_stream, shared, total, lines)
+                    ark_job.finish_shared_output(output_stream, shared, total)
             elif world > 1:
                 blobs = ark_job.gather_bytes_to_rank0(key_blob, dev_name)
                 lens = ark_job.gather_bytes_to_rank0(np.diff(key_off).astype(np.int32).view(np.uint8), dev_name)
@@ -859,7 +877,14 @@ class Model(object):
             reader.close()
             if peer is not None:
                 peer.close()
-            shared_view = None
+            shared_view = scp_view = None
+            if scp_map is not None:
+                try:
+                    scp_map.close()
+                except BufferError:
+                    pass
+            if scp_fd is not None:
+                os.close(scp_fd)
             if populate is not None:
                 populate.join()
             if shared_map is not None:
