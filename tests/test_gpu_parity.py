@@ -461,6 +461,26 @@ def test_first_layer_geometries_in_kernel_splice_or_two_launches(feat_dim, kerne
     eng.close()
 
 
+def test_misaligned_feature_pointer_takes_the_two_launch_first_layer():
+    # tdnn_first_kernel copies the feature rows with 16-byte cp.async pieces: a caller's matrix that does not start on a
+    # 16-byte boundary (a row slice of a larger tensor: rows are 92 bytes) goes through pack_im2col_kernel instead, same bits
+    import torch
+    eng, _ = _engine("ModelWithoutDropoutTdnn", "B")
+    lens = np.array([200, 57, 333], np.int32)
+    feats = synthetic.mfcc_batch(94, lens)
+    want = _run(eng, feats, lens)
+    assert eng.last_launch_count == 7
+    big = torch.empty((feats.shape[0] + 1, 23), dtype=torch.float32, device="cuda")
+    big[1:] = torch.from_numpy(feats).cuda()
+    view = big[1:]
+    assert view.data_ptr() % 16 != 0 and view.is_contiguous()
+    got = eng.forward(view, lens)
+    torch.cuda.synchronize()
+    assert eng.last_launch_count == 8
+    assert np.array_equal(got.cpu().numpy(), want)
+    eng.close()
+
+
 @pytest.mark.parametrize("topology", ["ModelWithoutDropoutTdnn", "ModelWithoutDropout"])
 def test_split_precision_option_gives_fp32_grade_x_vectors(topology):
     # option "precision" = 1 on the statistics-pooling topologies: every contraction as hi*hi + hi*lo + lo*hi of two-term fp16

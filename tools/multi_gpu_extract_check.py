@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Product-path check on N GPUs of one box: extract_embedding.py (ark file in) single-process vs `torchrun --nproc-per-node N` must
-give byte-identical outputs -- with `ark,scp:` files (every rank writes its byte range of the one ark, rank 0 the scp) and with a
+give byte-identical outputs -- with `ark,scp:` files (every rank writes its byte ranges of the one ark and the one scp) and with a
 pipe wspecifier (rows to rank 0's peer-memory table over NVLink, rank 0 writes the stream).
 usage: python tools/multi_gpu_extract_check.py [N] [n_utts]"""
 import os
