@@ -15,8 +15,9 @@
 //     jobs 2..7  D[256 ch, rows] = W4[ct] . MID^T                  (A = W4 streamed, B = MID resident: pooled orientation)
 //                epilogue: as tdnn_pair_kernel mode 1 (lane = channel, the 32 registers of a tcgen05.ld are 32 frames):
 //                partial[block][{sum, sumsq}][channel]
-//   operand bytes per SM per row tile: 2 x 128 KB (X, once per half of layer n-2) + 256 KB (W3) + 768 KB (W4) = 1.25 MB for
-//   32 768 tensor cycles = 39 B/clk/SM -- under the L2 cap -- instead of 2 MB; nothing is written but the pooled partials.
+//   operand bytes per SM per row tile: 192 KB (X: once into the intermediate's dead buffer for the first half of layer n-2 and
+//   atoms 4..7 of the second, atoms 0..3 once more through the ring) + 256 KB (W3) + 768 KB (W4) = 1.19 MB for 32 768 tensor
+//   cycles = 37 B/clk/SM -- under the L2 cap -- instead of 2 MB; nothing is written but the pooled partials.
 //
 // The arithmetic is that of the two separate launches, in the same order (K ascending in 64-wide atoms, same epilogue
 // expressions), so results are BIT-IDENTICAL to them (tests/test_gpu_parity.py::test_fused_tail_is_bit_identical).
@@ -37,7 +38,7 @@ constexpr int FT_OFF_MID = 0;
 constexpr int FT_OFF_RING = FT_MID_ATOMS * FT_SLOT_BYTES;       // 131072
 constexpr int FT_OFF_PAR = FT_OFF_RING + FT_SLOTS * FT_SLOT_BYTES;    // 212992: bias | scale | shift | slope of the 512 intermediate channels
 constexpr int FT_OFF_BARS = FT_OFF_PAR + 4 * FT_MID_CH * 4;           // 221184
-constexpr int FT_NUM_BARS = 2 * FT_SLOTS + 6;                   // full, empty | t_full[2], t_empty[2], mid_ready[2]
+constexpr int FT_NUM_BARS = 2 * FT_SLOTS + 6 + 2 * FT_MID_ATOMS; // full, empty | t_full[2], t_empty[2], mid_ready[2] | x_full[8], mid_free[8]
 constexpr int FT_OFF_TMEM_PTR = FT_OFF_BARS + (FT_NUM_BARS + 2) * 8;
 constexpr int FT_SMEM_BYTES = FT_OFF_TMEM_PTR + 16 + 1024;      // + slack for 1024-byte alignment
 static_assert(FT_SMEM_BYTES <= 232448, "exceeds 227 KB of dynamic shared memory");
@@ -92,6 +93,14 @@ tdnn_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap_x,    // [R_pad,
   auto t_full = [&](uint32_t s) { return bar0 + 8u * (2 * FT_SLOTS + s); };
   auto t_empty = [&](uint32_t s) { return bar0 + 8u * (2 * FT_SLOTS + 2 + s); };
   auto mid_ready = [&](uint32_t s) { return bar0 + 8u * (2 * FT_SLOTS + 4 + s); };
+  // The INPUT rows of the next row tile wait in the intermediate's buffer while it is dead: atom a of it is free once the last
+  // layer n-1 job of a tile has multiplied it (mid_free[a]) and holds input atom a from then (x_full[a]) until the epilogue of
+  // the layer n-2 half that owns it writes the intermediate there.  The first half of layer n-2 then streams only W3 through
+  // the ring (one slot per K step, like layer n-1) and the second half re-reads only input atoms 0..3: 448 KB instead of 512 KB
+  // per SM and row tile in the phase that is bound by the 40 B/clk an SM ingests, and the input is requested ~2 500 cycles
+  // before the phase starts instead of as ring slots free up.
+  auto x_full = [&](uint32_t a) { return bar0 + 8u * (2 * FT_SLOTS + 6 + a); };
+  auto mid_free = [&](uint32_t a) { return bar0 + 8u * (2 * FT_SLOTS + 6 + FT_MID_ATOMS + a); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + FT_OFF_TMEM_PTR);
 
   const int warp = threadIdx.x >> 5;
@@ -111,6 +120,7 @@ tdnn_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap_x,    // [R_pad,
       ptx::mbar_init(t_empty(s), 2 * NUM_EPI_WARPS);
       ptx::mbar_init(mid_ready(s), 2 * NUM_EPI_WARPS);
     }
+    for (uint32_t a = 0; a < FT_MID_ATOMS; ++a) { ptx::mbar_init(x_full(a), 1); ptx::mbar_init(mid_free(a), 1); }
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -141,20 +151,37 @@ tdnn_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap_x,    // [R_pad,
       __syncwarp();
       if (++s == FT_SLOTS) { s = 0; ph ^= 1u; }
     };
+    const uint32_t x_full_leader = ptx::mapa_cluster(x_full(0), 0);
+    uint32_t n_res = 0;                                          // row tiles whose input went into the intermediate's buffer so far
+    // Everything the FIRST half of layer n-2 needs for one row tile: input atom a into the intermediate's atom a as soon as the
+    // previous tile's last layer n-1 job has multiplied it, W3 atom a into the ring slot that job's W4 atom a just left -- both
+    // are requested while that job still runs, in the order it frees them.
+    auto first_half = [&](int row) {
+      for (int a = 0; a < KA; ++a) {                              // (host: KA <= FT_MID_ATOMS)
+        ptx::mbar_wait(mid_free(uint32_t(a)), (n_res & 1u) ^ 1u);
+        if (ptx::elect_one()) {
+          if (leader) ptx::mbar_arrive_expect_tx(x_full(uint32_t(a)), 2u * FT_SLOT_BYTES);
+          ptx::tma_load_2d_2sm(sMid + uint32_t(a) * FT_SLOT_BYTES, &tmap_x, x_full_leader + 8u * uint32_t(a), a * BLOCK_K, row);
+        }
+        __syncwarp();
+        load(&tmap_w3, a * BLOCK_K, int(rank) * CTA_CH);
+      }
+      ++n_res;
+    };
+    if (cluster_id < args.n_row_tiles) first_half(cluster_id * TILE_ROWS + int(rank) * CTA_ROWS);
     for (int tile = cluster_id; tile < args.n_row_tiles; tile += n_clusters) {
       const int r0 = tile * TILE_ROWS + int(rank) * CTA_ROWS;
-      for (int nt = 0; nt < 2; ++nt, ++pg) {
-        for (int ka = 0; ka < KA; ++ka) {
-          load(&tmap_x, ka * BLOCK_K, r0);
-          if (ka == 0 && lane == 0) ft_stamp(args, cluster_id, rank, pg, 0);
-          load(&tmap_w3, ka * BLOCK_K, nt * TILE_CH + int(rank) * CTA_CH);
-        }
-        if (lane == 0) ft_stamp(args, cluster_id, rank, pg, 1);
+      ++pg;                                                       // (the first half's loads were issued with the previous tile)
+      for (int ka = 0; ka < KA; ++ka) {                           // second half: input atoms 0..3 once more (their place holds the
+        if (ka < FT_MID_ATOMS / 2) load(&tmap_x, ka * BLOCK_K, r0);   // intermediate by now), W3
+        if (ka == 0 && lane == 0) ft_stamp(args, cluster_id, rank, pg, 0);
+        load(&tmap_w3, ka * BLOCK_K, TILE_CH + int(rank) * CTA_CH);
       }
+      if (lane == 0) ft_stamp(args, cluster_id, rank, pg, 1);
+      ++pg;
       for (int ct = 0; ct < NCT; ++ct, ++pg) {
         if (ct == 1 && tile + n_clusters < args.n_row_tiles && ptx::elect_one()) {
-          // the next row tile's input rows -> L2 now, so that the short ring of the layer n-2 phase (3 K steps in flight)
-          // only has to cover an L2 hit
+          // the next row tile's input rows -> L2 now
           for (int ka = 0; ka < KA; ++ka) ptx::tma_prefetch_l2_2d(&tmap_x, ka * BLOCK_K, r0 + n_clusters * TILE_ROWS);
         }
         __syncwarp();
@@ -163,6 +190,7 @@ tdnn_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap_x,    // [R_pad,
           if (ka == 0 && lane == 0) ft_stamp(args, cluster_id, rank, pg, 0);
         }
         if (lane == 0) ft_stamp(args, cluster_id, rank, pg, 1);
+        if (ct == NCT - 1 && tile + n_clusters < args.n_row_tiles) first_half(r0 + n_clusters * TILE_ROWS);
       }
     }
   } else if (warp == 1) {
@@ -181,19 +209,29 @@ tdnn_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap_x,    // [R_pad,
           const uint32_t d_tmem = tmem_base + acc * TILE_CH;
           if (lane == 0) ft_stamp(args, cluster_id, rank, g, 2);
           for (int ka = 0; ka < KA; ++ka) {
-            const uint32_t sx = s, phx = ph;
+            // A operand: the resident input atom (first half: all of them, loaded once per row tile; second half: atoms 4..7,
+            // which the first half's epilogue does not touch), else an input atom streamed through the ring
+            const bool ring_x = nt == 1 && ka < FT_MID_ATOMS / 2;
+            uint32_t a_addr = sMid + uint32_t(ka) * FT_SLOT_BYTES;
+            uint32_t sx = 0;
+            if (ring_x) {
+              sx = s;
+              ptx::mbar_wait(full(s), ph);
+              a_addr = sRing + s * FT_SLOT_BYTES;
+              if (++s == FT_SLOTS) { s = 0; ph ^= 1u; }
+            } else if (nt == 0) {
+              ptx::mbar_wait(x_full(uint32_t(ka)), ti & 1u);
+            }
+            const uint32_t sw = s;
+            ptx::mbar_wait(full(s), ph);
             if (++s == FT_SLOTS) { s = 0; ph ^= 1u; }
-            const uint32_t sw = s, phw = ph;
-            if (++s == FT_SLOTS) { s = 0; ph ^= 1u; }
-            ptx::mbar_wait(full(sx), phx);
-            ptx::mbar_wait(full(sw), phw);
             ptx::tc_fence_after();
-            const uint64_t da = desc(sRing + sx * FT_SLOT_BYTES), dw = desc(sRing + sw * FT_SLOT_BYTES);
+            const uint64_t da = desc(a_addr), dw = desc(sRing + sw * FT_SLOT_BYTES);
             if (ptx::elect_one()) {
 #pragma unroll
               for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
                 ptx::umma_f16_2sm(d_tmem, da + uint64_t(2 * k), dw + uint64_t(2 * k), idesc, uint32_t(ka | k));
-              ptx::umma_commit_2sm(empty(sx));
+              if (ring_x) ptx::umma_commit_2sm(empty(sx));
               ptx::umma_commit_2sm(empty(sw));
             }
             __syncwarp();
@@ -222,6 +260,7 @@ tdnn_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap_x,    // [R_pad,
               for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
                 ptx::umma_f16_2sm(d_tmem, dw + uint64_t(2 * k), dm + uint64_t(2 * k), idesc, uint32_t(ka | k));
               ptx::umma_commit_2sm(empty(s));
+              if (ct == NCT - 1) ptx::umma_commit_2sm(mid_free(uint32_t(ka)));   // this atom of the intermediate has had its last reader
             }
             __syncwarp();
             if (++s == FT_SLOTS) { s = 0; ph ^= 1u; }
