@@ -72,6 +72,15 @@ __device__ __forceinline__ void ft_stamp(const FusedTailArgs& a, int cluster, ui
   }
 }
 
+// Order of the layer n-1 half-jobs (channel tile, K half) of a row tile: tiles 0 and 1 interleaved by halves -- (0, lo) (1, lo)
+// (0, hi) (1, hi) -- then (2, lo) (2, hi) (3, lo) ...  Each accumulator still sums atoms 0..7 in order (same bits); but the
+// second tile can start on atoms 0..3 of the intermediate while the epilogue of the second layer n-2 half is still writing
+// atoms 4..7, instead of the first tile waiting for them alone.  (Host: at least two channel tiles.)
+__device__ __forceinline__ void ft_half_job(int hj, int& ct, int& half) {
+  if (hj < 4) { ct = hj & 1; half = hj >> 1; }
+  else { ct = hj >> 1; half = hj & 1; }
+}
+
 __device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
@@ -179,19 +188,22 @@ tdnn_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap_x,    // [R_pad,
       }
       if (lane == 0) ft_stamp(args, cluster_id, rank, pg, 1);
       ++pg;
-      for (int ct = 0; ct < NCT; ++ct, ++pg) {
-        if (ct == 1 && tile + n_clusters < args.n_row_tiles && ptx::elect_one()) {
+      for (int hj = 0; hj < 2 * NCT; ++hj) {                      // W4 atoms in the order the issuer multiplies them (ft_half_job)
+        int ct, half;
+        ft_half_job(hj, ct, half);
+        if (hj == 4 && tile + n_clusters < args.n_row_tiles && ptx::elect_one()) {
           // the next row tile's input rows -> L2 now
           for (int ka = 0; ka < KA; ++ka) ptx::tma_prefetch_l2_2d(&tmap_x, ka * BLOCK_K, r0 + n_clusters * TILE_ROWS);
         }
         __syncwarp();
-        for (int ka = 0; ka < FT_MID_ATOMS; ++ka) {
+        for (int ka = half * (FT_MID_ATOMS / 2); ka < (half + 1) * (FT_MID_ATOMS / 2); ++ka) {
           load(&tmap_w4, ka * BLOCK_K, ct * TILE_CH + int(rank) * CTA_CH);
-          if (ka == 0 && lane == 0) ft_stamp(args, cluster_id, rank, pg, 0);
+          if (ka == 0 && lane == 0) ft_stamp(args, cluster_id, rank, pg + uint32_t(ct), 0);
         }
-        if (lane == 0) ft_stamp(args, cluster_id, rank, pg, 1);
-        if (ct == NCT - 1 && tile + n_clusters < args.n_row_tiles) first_half(r0 + n_clusters * TILE_ROWS);
+        if (half == 1 && lane == 0) ft_stamp(args, cluster_id, rank, pg + uint32_t(ct), 1);
       }
+      pg += uint32_t(NCT);
+      if (tile + n_clusters < args.n_row_tiles) first_half(r0 + n_clusters * TILE_ROWS);
     }
   } else if (warp == 1) {
     // ============================ MMA issuer (leader) ============================
@@ -240,18 +252,25 @@ tdnn_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap_x,    // [R_pad,
           __syncwarp();
           if (lane == 0) ft_stamp(args, cluster_id, rank, g, 3);
         }
-        // ---- layer n-1: pooled orientation, B = the resident intermediate ----
-        for (int ct = 0; ct < NCT; ++ct, ++g) {
-          const uint32_t acc = g & 1u;
-          ptx::mbar_wait_cluster(t_empty(acc), ((g >> 1) & 1u) ^ 1u);
-          ptx::tc_fence_after();
+        // ---- layer n-1: pooled orientation, B = the resident intermediate.  Half-jobs (channel tile, K half) in ft_half_job's
+        //      order: the first two channel tiles start on atoms 0..3 while the second layer n-2 epilogue still writes 4..7.
+        const uint32_t g0 = g;
+        for (int hj = 0; hj < 2 * NCT; ++hj) {
+          int ct, half;
+          ft_half_job(hj, ct, half);
+          const uint32_t gj = g0 + uint32_t(ct);
+          const uint32_t acc = gj & 1u;
+          if (half == 0) {
+            ptx::mbar_wait_cluster(t_empty(acc), ((gj >> 1) & 1u) ^ 1u);
+            ptx::tc_fence_after();
+            if (lane == 0) ft_stamp(args, cluster_id, rank, gj, 2);
+          }
+          if (hj == 0 || hj == 2) {                                   // the half of the intermediate read from here on is written
+            ptx::mbar_wait_cluster(mid_ready(hj == 0 ? 0u : 1u), ti & 1u);
+            ptx::tc_fence_after();
+          }
           const uint32_t d_tmem = tmem_base + acc * TILE_CH;
-          if (lane == 0) ft_stamp(args, cluster_id, rank, g, 2);
-          for (int ka = 0; ka < FT_MID_ATOMS; ++ka) {
-            if (ct == 0 && (ka == 0 || ka == FT_MID_ATOMS / 2)) {     // the half of the intermediate this atom lies in is written
-              ptx::mbar_wait_cluster(mid_ready(ka == 0 ? 0u : 1u), ti & 1u);
-              ptx::tc_fence_after();
-            }
+          for (int ka = half * (FT_MID_ATOMS / 2); ka < (half + 1) * (FT_MID_ATOMS / 2); ++ka) {
             ptx::mbar_wait(full(s), ph);
             ptx::tc_fence_after();
             const uint64_t dw = desc(sRing + s * FT_SLOT_BYTES), dm = desc(sMid + uint32_t(ka) * FT_SLOT_BYTES);
@@ -265,10 +284,13 @@ tdnn_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap_x,    // [R_pad,
             __syncwarp();
             if (++s == FT_SLOTS) { s = 0; ph ^= 1u; }
           }
-          if (ptx::elect_one()) ptx::umma_commit_2sm(t_full(acc));
-          __syncwarp();
-          if (lane == 0) ft_stamp(args, cluster_id, rank, g, 3);
+          if (half == 1) {
+            if (ptx::elect_one()) ptx::umma_commit_2sm(t_full(acc));
+            __syncwarp();
+            if (lane == 0) ft_stamp(args, cluster_id, rank, gj, 3);
+          }
         }
+        g += uint32_t(NCT);
       }
     }
   } else {

@@ -664,7 +664,7 @@ int forward_impl(xv_model* m, const float* feats_dev, const int32_t* seg_len_hos
   const bool fuse_tail = m->opt_fuse_tail && !attention && !m->opt_split && !layer_out_dev && nl >= 3 && !m->opt_resident &&
                          m->layers[nl - 2].gemm_taps == 1 && m->layers[nl - 1].gemm_taps == 1 &&
                          m->layers[nl - 2].c_out == tdnn2::FT_MID_CH && m->layers[nl - 2].c_in_pad % tdnn2::BLOCK_K == 0 &&
-                         m->layers[nl - 2].c_in_pad <= tdnn2::FT_MID_CH &&
+                         m->layers[nl - 2].c_in_pad <= tdnn2::FT_MID_CH && m->layers[nl - 1].c_out >= 2 * tdnn2::TILE_CH &&
                          (m->opt_trace_layer < 0 || m->opt_trace_layer == nl - 2);
   for (int i = 0; i < nl; ++i) {
     if (fuse_tail && i == nl - 2) {
