@@ -765,21 +765,26 @@ def measure_product(args, dev, rank, world, params, topo):
             # the same job with rank 0's output a STREAM (what a `| copy-vector ...` wspecifier is): rows go to rank 0's
             # peer-memory table over NVLink and rank 0 writes them all
             import io
-            dist.barrier()
-            torch.cuda.synchronize(dev)
-            t0 = time.perf_counter()
-            buf = io.BytesIO() if rank == 0 else None
-            model.make_embedding(path, buf, os.path.join(tmp, "model"), 25, 10000, True, None)
-            torch.cuda.synchronize(dev)
-            dist.barrier()
-            dt = time.perf_counter() - t0
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            peer_runs = []
+            for _ in range(2):           # the first run also pays NCCL's connection set-up for the key gather (a pattern no earlier
+                dist.barrier()           # block of this process used); the second is the job itself
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                buf = io.BytesIO() if rank == 0 else None
+                model.make_embedding(path, buf, os.path.join(tmp, "model"), 25, 10000, True, None)
+                torch.cuda.synchronize(dev)
+                dist.barrier()
+                dt = time.perf_counter() - t0
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                peer_runs.append(float(t.item()))
+            t = torch.tensor([min(peer_runs)], dtype=torch.float64)
             same = None
             if rank == 0:
                 with open(os.path.join(tmp, "xvector.2.ark"), "rb") as f:
                     same = f.read() == buf.getvalue()
             peer_variant = dict(output="in-memory stream on rank 0 (peer-memory result table)", seconds=round(float(t.item()), 4),
+                                all_runs_s=[round(r, 4) for r in peer_runs],
                                 value=round(total_frames / float(t.item()), 1), bytes_identical_to_the_file_output=same,
                                 rank0_breakdown_s={k: (round(v, 4) if isinstance(v, float) else v)
                                                    for k, v in getattr(model, "last_job_stats", {}).items()})
@@ -1034,7 +1039,7 @@ def measure_train_step(args, dev, rank, world, peaks, topo):
         if e2e:
             feats.copy_(feats_host, non_blocking=True)
             lab.copy_(lab_host, non_blocking=True)
-        if world > 1:        # the segment-level gradients are all-reduced on `comm` under the frame-level backward
+        if world > 1:        # gradient buckets are all-reduced on `comm` as they become final, under the rest of the backward
             la = tr.forward_backward_allreduce(feats, lab, B, T, grad, torch.cuda.current_stream(dev), comm)
         else:
             la = tr.forward_backward(feats, lab, B, T, grad_dev=grad)
@@ -1085,7 +1090,7 @@ def measure_train_step(args, dev, rank, world, peaks, topo):
                ms_per_step=round(ms_res, 4), value=round(world * B * T / (ms_res * 1e-3), 1), unit="frames/s",
                e2e=dict(ms_per_step=round(ms_e2e, 4), value=round(world * B * T / (ms_e2e * 1e-3), 1), unit="frames/s",
                         h2d_bytes_per_step=B * T * FEAT_DIM * 4 + B * 4, d2h_bytes_per_step=8),
-               parallelism="data parallel x%d: NCCL all-reduce of the flat fp32 gradient (%.1f MB) per step, the segment-level %.1f MB under the frame-level backward"
+               parallelism="data parallel x%d: NCCL all-reduce of the flat fp32 gradient (%.1f MB) per step in buckets as they become final: the segment-level %.1f MB under the frame-level backward, then every frame layer under the backward of the layers below it"
                            % (world, tr.n_params * 4 / 1e6, (tr.n_params - tr.seg_grad_offset) * 4 / 1e6)
                if world > 1 else "single GPU",
                gpu_launches_per_step=launches, loss_after=round(loss, 4),

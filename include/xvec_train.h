@@ -73,6 +73,12 @@ int xv_train_forward_backward(xv_trainer* t, const float* feats_dev, const int32
 int xv_train_forward_backward_part(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, int32_t n_seg,
                                    int32_t seg_len, float* grad_dev, float* loss_acc_dev, void* stream, int32_t part);
 int64_t xv_train_segment_grad_offset(const xv_trainer* t);
+/* part = XV_TRAIN_PART_FRAME + i: the slice of part 2 that ends with the gradients of frame layer i final -- for the top layer
+ * it starts with the pooling backward, for layer 0 it ends with the overflow flag behind the gradient.  Run from the top layer
+ * down after part 1 they are part 2, bit for bit; a data-parallel caller all-reduces [offset, offset + count) of
+ * xv_train_frame_grad_span(t, i) after slice i, under the backward of the layers below. */
+#define XV_TRAIN_PART_FRAME 16
+int xv_train_frame_grad_span(const xv_trainer* t, int32_t layer, int64_t* offset, int64_t* count);
 /* Loss and accuracy of one minibatch with phase = False (moving statistics, nothing is updated): the
  * sess.run([self.loss, self.accuracy]) of Model.eval (models.py:338-339). */
 int xv_train_eval(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, int32_t n_seg, int32_t seg_len,

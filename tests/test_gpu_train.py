@@ -283,6 +283,38 @@ def test_the_step_in_two_halves_equals_the_whole_step_bit_for_bit():
         split.close()
 
 
+def test_the_frame_level_backward_in_layer_slices_equals_the_whole_step_bit_for_bit():
+    # XV_TRAIN_PART_FRAME + i: part 2 cut where frame layer i's gradients are final, so that a data-parallel caller can start
+    # that layer's all-reduce under the backward of the layers below.  The spans tile the frame-level gradients exactly.
+    whole, split = Problem("ModelWithoutDropoutTdnn", "B", 8, 96, 50), Problem("ModelWithoutDropoutTdnn", "B", 8, 96, 50)
+    try:
+        spans = split.tr.frame_grad_spans
+        assert spans[0][0] == 0 and all(spans[i][0] + spans[i][1] == spans[i + 1][0] for i in range(len(spans) - 1))
+        assert spans[-1][0] + spans[-1][1] == split.tr.seg_grad_offset
+        for _ in range(3):                                   # the third round runs from captured graphs
+            la0 = whole.tr.forward_backward(whole.feats, whole.lab, whole.B, whole.T)
+            torch.cuda.synchronize()
+            g0 = whole.tr.download(whole.native.TRAIN_GRAD)
+            la1 = split.tr.forward_backward(split.feats, split.lab, split.B, split.T, part=1)
+            for i in reversed(range(len(spans))):
+                split.tr.forward_backward(split.feats, split.lab, split.B, split.T, part=split.tr.PART_FRAME + i)
+                torch.cuda.synchronize()
+                g = split.tr.download(split.native.TRAIN_GRAD)
+                off, cnt = spans[i]
+                assert np.array_equal(g[off:off + cnt], g0[off:off + cnt])             # layer i's gradients: final already
+            assert np.array_equal(split.tr.download(split.native.TRAIN_GRAD), g0)      # incl. the overflow flag behind them
+            assert np.array_equal(la0.cpu().numpy(), la1.cpu().numpy())
+            whole.tr.apply(1e-3)
+            split.tr.apply(1e-3)
+            torch.cuda.synchronize()
+            assert np.array_equal(split.tr.download(split.native.TRAIN_PARAMS), whole.tr.download(whole.native.TRAIN_PARAMS))
+        with pytest.raises(Exception):
+            split.tr.forward_backward(split.feats, split.lab, split.B, split.T, part=split.tr.PART_FRAME + len(spans))
+    finally:
+        whole.close()
+        split.close()
+
+
 def test_adam_matches_tf_formula_exactly():
     p = Problem("ModelWithoutDropoutTdnn", "B", 4, 40, 50)
     try:

@@ -223,6 +223,8 @@ def load_library():
     lib.xv_train_forward_backward_part.restype = ctypes.c_int
     lib.xv_train_segment_grad_offset.argtypes = [P]
     lib.xv_train_segment_grad_offset.restype = I64
+    lib.xv_train_frame_grad_span.argtypes = [P, I32, ctypes.POINTER(I64), ctypes.POINTER(I64)]
+    lib.xv_train_frame_grad_span.restype = ctypes.c_int
     lib.xv_train_eval.argtypes = [P, P, P, I32, I32, P, P]
     lib.xv_train_eval.restype = ctypes.c_int
     lib.xv_train_apply.argtypes = [P, P, F32, F32, P]
@@ -265,7 +267,7 @@ EXPORTED_SYMBOLS = ["xv_create", "xv_destroy", "xv_set_param", "xv_workspace_byt
                     # include/xvec_train.h
                     "xv_train_create", "xv_train_destroy", "xv_train_size", "xv_train_span", "xv_train_upload",
                     "xv_train_download", "xv_train_set_step", "xv_train_get_step", "xv_train_forward_backward", "xv_train_forward_backward_part",
-                    "xv_train_segment_grad_offset", "xv_train_eval",
+                    "xv_train_segment_grad_offset", "xv_train_frame_grad_span", "xv_train_eval",
                     "xv_train_apply", "xv_train_skipped_updates", "xv_train_sync_model", "xv_train_debug_tensor", "xv_train_set_option",
                     "xv_train_last_launch_count", "xv_train_last_kernel_names", "xv_convert_f16_to_f32",
                     # include/xvec_frontend.h
@@ -795,6 +797,11 @@ class XvecTrainer:
         self.n_params = int(self.lib.xv_train_size(self.handle, TRAIN_PARAMS))
         self.n_grad = int(self.lib.xv_train_size(self.handle, TRAIN_GRAD))     # gradient + the combined-overflow-flag tail
         self.seg_grad_offset = int(self.lib.xv_train_segment_grad_offset(self.handle))   # [this, n_params): segment-level gradients
+        self.frame_grad_spans = []                       # (offset, count) of every frame layer's gradients (w | b | gamma | beta)
+        for i in range(len(engine.layer_sizes)):
+            off, cnt = ctypes.c_int64(0), ctypes.c_int64(0)
+            _check(self.lib, self.lib.xv_train_frame_grad_span(self.handle, i, ctypes.byref(off), ctypes.byref(cnt)))
+            self.frame_grad_spans.append((int(off.value), int(cnt.value)))
         self.n_moving = int(self.lib.xv_train_size(self.handle, TRAIN_MOVING))
         self._loss_acc = None
         self._geom = None
@@ -854,7 +861,8 @@ class XvecTrainer:
     def forward_backward(self, feats_dev, labels_dev, n_seg, seg_len, grad_dev=None, stream=None, part=0):
         """feats_dev: torch float32 CUDA [n_seg*seg_len, feat_dim]; labels_dev: torch int32 CUDA [n_seg].
         Enqueues on ``stream``; returns the device tensor [loss, accuracy] (read it after a synchronize).
-        ``part``: 0 the whole step; 1 / 2 its halves (see ``allreduce_overlapped``)."""
+        ``part``: 0 the whole step; 1 / 2 its halves; ``PART_FRAME + i`` the slice of 2 that ends with frame layer i's
+        gradients final (see ``forward_backward_allreduce``)."""
         import torch
         assert feats_dev.is_cuda and feats_dev.dtype == torch.float32 and feats_dev.is_contiguous()
         assert feats_dev.numel() == n_seg * seg_len * self.engine.feat_dim
@@ -868,20 +876,26 @@ class XvecTrainer:
         self._geom = (int(n_seg), int(seg_len))
         return self._loss_acc
 
+    PART_FRAME = 16                                      # XV_TRAIN_PART_FRAME (include/xvec_train.h)
+
     def forward_backward_allreduce(self, feats_dev, labels_dev, n_seg, seg_len, grad_dev, stream, comm_stream):
-        """Data-parallel step: the all-reduce of the segment-level gradients (60 % of the bytes; final after the first half of
-        the step) runs on ``comm_stream`` UNDER the frame-level backward; the frame-level gradients and the overflow flag
-        follow when the step ends.  On return ``stream`` waits for both: ``apply`` may be enqueued."""
+        """Data-parallel step: every gradient bucket is all-reduced on ``comm_stream`` as soon as it is final -- the
+        segment-level gradients (60 % of the bytes) after the first half of the step, then frame layer by frame layer from the
+        top down, each UNDER the backward of the layers below it; only layer 0's small bucket and the overflow flag follow the
+        step.  On return ``stream`` waits for all of them: ``apply`` may be enqueued."""
         import torch
         import torch.distributed as dist
         la = self.forward_backward(feats_dev, labels_dev, n_seg, seg_len, grad_dev=grad_dev, stream=stream, part=1)
         comm_stream.wait_stream(stream)
         with torch.cuda.stream(comm_stream):
             dist.all_reduce(grad_dev[self.seg_grad_offset:self.n_params])
-        self.forward_backward(feats_dev, labels_dev, n_seg, seg_len, grad_dev=grad_dev, stream=stream, part=2)
-        comm_stream.wait_stream(stream)
+        for i in reversed(range(len(self.frame_grad_spans))):
+            self.forward_backward(feats_dev, labels_dev, n_seg, seg_len, grad_dev=grad_dev, stream=stream, part=self.PART_FRAME + i)
+            off, cnt = self.frame_grad_spans[i]
+            comm_stream.wait_stream(stream)
+            with torch.cuda.stream(comm_stream):
+                dist.all_reduce(grad_dev[off:off + cnt])
         with torch.cuda.stream(comm_stream):
-            dist.all_reduce(grad_dev[:self.seg_grad_offset])
             dist.all_reduce(grad_dev[self.n_params:])
         stream.wait_stream(comm_stream)
         return la

@@ -639,8 +639,11 @@ namespace {
 // training = true: forward (batch statistics, moving-statistics update) + backward.
 // training = false: forward only with the moving statistics (phase: False), loss and accuracy (Model.eval, models.py:307-354).
 // part: 0 = the whole step; 1 = forward, loss and the segment-level backward (the gradients of embed_layer-*, output/* are final
-// when it ends); 2 = pooling and frame-level backward (+ the overflow flag behind the gradient).  A data-parallel caller runs
-// 1, starts the all-reduce of the segment-level gradients on another stream, runs 2 under it (xv_train_forward_backward_part).
+// when it ends); 2 = pooling and frame-level backward (+ the overflow flag behind the gradient); XV_TRAIN_PART_FRAME + i = the
+// slice of 2 that ends with frame layer i's gradients final (the top layer's slice starts with the pooling backward, layer 0's
+// ends with the overflow flag).  A data-parallel caller runs 1, starts the all-reduce of the segment-level gradients on another
+// stream, then the frame slices from the top layer down, each layer's all-reduce under the backward of the layers below it
+// (xv_train_forward_backward_part).
 int tr_step_body(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, int32_t n_seg, int32_t seg_len,
                  float* grad_dev, float* loss_acc_dev, cudaStream_t stream, bool training, int part = 0) {
   xv_model* m = t->m;
@@ -651,8 +654,10 @@ int tr_step_body(xv_trainer* t, const float* feats_dev, const int32_t* labels_de
   float* grad = grad_dev ? grad_dev : t->grad;
   if (t->operands_dirty) { rc = tr_repack(t, stream); if (rc != XV_OK) return rc; }
   struct EmitGuard { xv_trainer* t; ~EmitGuard() { t->emit = true; } } emit_guard{t};
-  t->emit = part != 2;
   const int nl = int(t->frames.size());
+  const bool frame_slice = part >= XV_TRAIN_PART_FRAME;
+  auto emits = [&](int layer) { return part == 0 || part == 2 || part == XV_TRAIN_PART_FRAME + layer; };   // second half, by frame layer
+  t->emit = part != 2 && !frame_slice;
   const int64_t r_pad = t->r_pad;
   constexpr int32_t ROWS_PER_PART = 128;                              // frame layers: rows per partial-sum CTA
   const int32_t n_part = int32_t(r_pad / ROWS_PER_PART);
@@ -810,7 +815,7 @@ int tr_step_body(xv_trainer* t, const float* feats_dev, const int32_t* labels_de
   }
 
   if (part == 1) return XV_OK;
-  t->emit = true;
+  t->emit = emits(nl - 1);
 
   // ---- pooling + last layer's BatchNorm + ReLU backward ---------------------------------------------------
   {
@@ -827,6 +832,7 @@ int tr_step_body(xv_trainer* t, const float* feats_dev, const int32_t* labels_de
   // ---- frame layers backward ---------------------------------------------------------------------------
   for (int i = nl - 1; i >= 0; --i) {
     TrFrame& L = t->frames[i];
+    t->emit = emits(i);
     if (i < nl - 1) {
       // dy_i (written by the data gradient of layer i+1) -> BatchNorm + ReLU backward -> dz_i
       TR_LAUNCH("blk_col_sums_kernel<1>", trk::blk_col_sums_kernel<1>, dim3(L.c_out / trk::COLS_PER_CTA, n_part), dim3(256), 0, static_cast<const __half*>(L.dy), static_cast<const __half*>(L.r), L.c_out, ROWS_PER_PART, t->partial);
@@ -850,6 +856,7 @@ int tr_step_body(xv_trainer* t, const float* feats_dev, const int32_t* labels_de
     }
   }
   // the step's gradient-overflow flag rides behind the gradient (grad[n_params]): summed with it by the all-reduce
+  t->emit = emits(0);
   TR_LAUNCH("grad_flag_kernel", trk::grad_flag_kernel, dim3(1), dim3(32), 0, static_cast<const uint32_t*>(t->gflag), grad + t->n_params);
 
   // parity hooks
@@ -902,7 +909,7 @@ int tr_step(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, in
       found = &g;
   if (!found) {
     // egs archives mix minibatch lengths: capturing costs about two steps, so only a geometry that comes back is captured
-    const std::pair<int32_t, int32_t> geo(n_seg, seg_len * 4 + part);
+    const std::pair<int32_t, int32_t> geo(n_seg, seg_len * 64 + part);
     if (std::find(t->seen_geometries.begin(), t->seen_geometries.end(), geo) == t->seen_geometries.end()) {
       if (t->seen_geometries.size() >= 4096) t->seen_geometries.clear();
       t->seen_geometries.push_back(geo);
@@ -946,11 +953,22 @@ int xv_train_forward_backward(xv_trainer* t, const float* feats_dev, const int32
 
 int xv_train_forward_backward_part(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, int32_t n_seg, int32_t seg_len,
                                    float* grad_dev, float* loss_acc_dev, void* stream, int32_t part) {
-  if (part < 0 || part > 2) return fail(XV_EINVAL, "part must be 0, 1 or 2");
+  if (!t) return fail(XV_EINVAL, "null argument");
+  if (!(part >= 0 && part <= 2) && !(part >= XV_TRAIN_PART_FRAME && part < XV_TRAIN_PART_FRAME + int32_t(t->frames.size())))
+    return fail(XV_EINVAL, "part must be 0, 1, 2 or XV_TRAIN_PART_FRAME + frame layer");
   return tr_step(t, feats_dev, labels_dev, n_seg, seg_len, grad_dev, loss_acc_dev, stream, true, part);
 }
 
 int64_t xv_train_segment_grad_offset(const xv_trainer* t) { return t ? t->seg[0].off_w : 0; }
+
+int xv_train_frame_grad_span(const xv_trainer* t, int32_t layer, int64_t* offset, int64_t* count) {
+  if (!t || !offset || !count) return fail(XV_EINVAL, "null argument");
+  if (layer < 0 || layer >= int32_t(t->frames.size())) return fail(XV_EINVAL, "no such frame layer");
+  const TrFrame& L = t->frames[layer];
+  *offset = L.off_w;                                    // w | b | gamma | beta of a layer lie behind one another
+  *count = L.off_beta + L.c_out - L.off_w;
+  return XV_OK;
+}
 
 int xv_train_eval(xv_trainer* t, const float* feats_dev, const int32_t* labels_dev, int32_t n_seg, int32_t seg_len,
                   float* loss_acc_dev, void* stream) {

@@ -429,7 +429,8 @@ class Model(object):
                 if training:
                     if grad is not None:
                         # data parallel: sum the flat gradient (+ the overflow flag behind it) over the ranks (NCCL); the
-                        # segment-level 60 % of it is reduced on `comm` under the frame-level backward
+                        # buckets are reduced on `comm` as they become final (segment level, then frame layer by frame layer), under the
+                        # rest of the backward
                         la = tr.forward_backward_allreduce(feats_dev, sl["labels_dev"][:n_seg], n_seg, seg_len, grad, compute, comm)
                     else:
                         la = tr.forward_backward(feats_dev, sl["labels_dev"][:n_seg], n_seg, seg_len, grad_dev=grad, stream=compute)
