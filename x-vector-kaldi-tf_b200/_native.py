@@ -878,7 +878,7 @@ class XvecTrainer:
 
     PART_FRAME = 16                                      # XV_TRAIN_PART_FRAME (include/xvec_train.h)
 
-    def forward_backward_allreduce(self, feats_dev, labels_dev, n_seg, seg_len, grad_dev, stream, comm_stream):
+    def forward_backward_allreduce(self, feats_dev, labels_dev, n_seg, seg_len, grad_dev, stream, comm_stream, fine=True):
         """Data-parallel step: every gradient bucket is all-reduced on ``comm_stream`` as soon as it is final -- the
         segment-level gradients (60 % of the bytes) after the first half of the step, then frame layer by frame layer from the
         top down, each UNDER the backward of the layers below it; only layer 0's small bucket and the overflow flag follow the
@@ -889,12 +889,18 @@ class XvecTrainer:
         comm_stream.wait_stream(stream)
         with torch.cuda.stream(comm_stream):
             dist.all_reduce(grad_dev[self.seg_grad_offset:self.n_params])
-        for i in reversed(range(len(self.frame_grad_spans))):
-            self.forward_backward(feats_dev, labels_dev, n_seg, seg_len, grad_dev=grad_dev, stream=stream, part=self.PART_FRAME + i)
-            off, cnt = self.frame_grad_spans[i]
+        if fine:
+            for i in reversed(range(len(self.frame_grad_spans))):
+                self.forward_backward(feats_dev, labels_dev, n_seg, seg_len, grad_dev=grad_dev, stream=stream, part=self.PART_FRAME + i)
+                off, cnt = self.frame_grad_spans[i]
+                comm_stream.wait_stream(stream)
+                with torch.cuda.stream(comm_stream):
+                    dist.all_reduce(grad_dev[off:off + cnt])
+        else:                                            # the frame level as ONE bucket behind the step (diagnostics)
+            self.forward_backward(feats_dev, labels_dev, n_seg, seg_len, grad_dev=grad_dev, stream=stream, part=2)
             comm_stream.wait_stream(stream)
             with torch.cuda.stream(comm_stream):
-                dist.all_reduce(grad_dev[off:off + cnt])
+                dist.all_reduce(grad_dev[:self.seg_grad_offset])
         with torch.cuda.stream(comm_stream):
             dist.all_reduce(grad_dev[self.n_params:])
         stream.wait_stream(comm_stream)

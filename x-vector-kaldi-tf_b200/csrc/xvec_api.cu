@@ -1559,6 +1559,12 @@ int xv_set_option(xv_model* m, const char* name, int64_t value) {
   if (n == "profile") m->opt_profile = value != 0;
   else if (n == "resident") m->opt_resident = int(value);
   else if (n == "prefetch") m->opt_prefetch = value != 0;
+  else if (n == "clusters") {
+    // CTA pairs per persistent grid (default: all that are co-resident, one per pair of SMs).  A data-parallel trainer lowers
+    // it to leave SMs to NCCL's kernels: a collective that has to wait for an SM of a persistent grid holds its late CTAs back
+    if (value < 1 || value > m->num_sms / 2) return fail(XV_EINVAL, "clusters out of range");
+    m->num_clusters = int(value);
+  }
   else if (n == "fc") m->opt_fc = int(value);
   else if (n == "pdl") m->opt_pdl = value != 0;
   else if (n == "blocking_collect") m->opt_blocking_collect = value != 0;
