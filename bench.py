@@ -1090,7 +1090,7 @@ def measure_train_step(args, dev, rank, world, peaks, topo):
                ms_per_step=round(ms_res, 4), value=round(world * B * T / (ms_res * 1e-3), 1), unit="frames/s",
                e2e=dict(ms_per_step=round(ms_e2e, 4), value=round(world * B * T / (ms_e2e * 1e-3), 1), unit="frames/s",
                         h2d_bytes_per_step=B * T * FEAT_DIM * 4 + B * 4, d2h_bytes_per_step=8),
-               parallelism="data parallel x%d: NCCL all-reduce of the flat fp32 gradient (%.1f MB) per step in buckets as they become final: the segment-level %.1f MB under the frame-level backward, then every frame layer under the backward of the layers below it"
+               parallelism="data parallel x%d: NCCL all-reduce of the flat fp32 gradient (%.1f MB) per step in two buckets: the segment-level %.1f MB under the frame-level backward, the frame-level rest behind the step"
                            % (world, tr.n_params * 4 / 1e6, (tr.n_params - tr.seg_grad_offset) * 4 / 1e6)
                if world > 1 else "single GPU",
                gpu_launches_per_step=launches, loss_after=round(loss, 4),

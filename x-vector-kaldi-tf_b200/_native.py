@@ -878,11 +878,13 @@ class XvecTrainer:
 
     PART_FRAME = 16                                      # XV_TRAIN_PART_FRAME (include/xvec_train.h)
 
-    def forward_backward_allreduce(self, feats_dev, labels_dev, n_seg, seg_len, grad_dev, stream, comm_stream, fine=True):
-        """Data-parallel step: every gradient bucket is all-reduced on ``comm_stream`` as soon as it is final -- the
-        segment-level gradients (60 % of the bytes) after the first half of the step, then frame layer by frame layer from the
-        top down, each UNDER the backward of the layers below it; only layer 0's small bucket and the overflow flag follow the
-        step.  On return ``stream`` waits for all of them: ``apply`` may be enqueued."""
+    def forward_backward_allreduce(self, feats_dev, labels_dev, n_seg, seg_len, grad_dev, stream, comm_stream, fine=False):
+        """Data-parallel step: gradient buckets are all-reduced on ``comm_stream`` as soon as they are final -- the
+        segment-level gradients (60 % of the bytes) after the first half of the step; the frame-level ones behind the step, or
+        with ``fine`` frame layer by frame layer from the top down, each under the backward of the layers below it.  (Measured
+        on 8 B200: 1.094 ms/step with two buckets, 1.111 with the fine ones, 0.915 without any all-reduce: a collective's CTAs
+        and the persistent all-SM grids of the backward do not share the SMs well whatever the bucketing)
+        On return ``stream`` waits for all of them: ``apply`` may be enqueued."""
         import torch
         import torch.distributed as dist
         la = self.forward_backward(feats_dev, labels_dev, n_seg, seg_len, grad_dev=grad_dev, stream=stream, part=1)

@@ -429,8 +429,7 @@ class Model(object):
                 if training:
                     if grad is not None:
                         # data parallel: sum the flat gradient (+ the overflow flag behind it) over the ranks (NCCL); the
-                        # buckets are reduced on `comm` as they become final (segment level, then frame layer by frame layer), under the
-                        # rest of the backward
+                        # segment-level 60 % of it is reduced on `comm` under the frame-level backward
                         la = tr.forward_backward_allreduce(feats_dev, sl["labels_dev"][:n_seg], n_seg, seg_len, grad, compute, comm)
                     else:
                         la = tr.forward_backward(feats_dev, sl["labels_dev"][:n_seg], n_seg, seg_len, grad_dev=grad, stream=compute)
