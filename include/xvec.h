@@ -185,9 +185,19 @@ int32_t xv_last_launch_count(const xv_model* m);
  * only wall-clock deltas around sess.run, models.py:413-417.) */
 int32_t xv_last_kernel_ms(xv_model* m, float* ms_out, int32_t cap);
 
-/* Tuning knob for experiments: 0 = one TMA box per (tap, channel chunk); 1 = load each
- * activation slab once and address every tap inside it (default chosen by the library).
- * Options: "profile", "pdl", "fc", "fc_max_splits", "resident", "prefetch", "rescue", "blocking_collect", "trace_*". */
+/* Options of a model (integers; unknown names are refused with XV_EINVAL):
+ *   "precision"        1 = split-precision operands (two fp16 terms per activation and weight; default for attention pooling)
+ *   "fuse_first"       1 (default) = the input splice and the first frame layer as ONE kernel (tdnn_first.cuh) when the
+ *                      topology allows it; 0 = pack_im2col_kernel + the layer kernel.  Same bits either way.
+ *   "fuse_tail"        1 (default) = the last two context-free frame layers as ONE kernel (tdnn_tail.cuh); 0 = one launch each
+ *   "fc"               1 (default) = embed_layer-0 on the tensor cores (split fp16), 0 = fp32 SIMT GEMM; "fc_max_splits"
+ *   "pdl"              programmatic dependent launch between the kernels of a forward (default 1)
+ *   "rescue"           1 (default) = xv_collect raises the fp16 range exponents and re-runs a batch that overflowed
+ *   "blocking_collect" 1 = xv_collect sleeps on a blocking-sync event instead of spinning
+ *   "clusters"         CTA pairs per persistent grid (default: one per pair of SMs); a data-parallel trainer may lower it
+ *   "resident", "prefetch"   measured-not-faster schedules of the layer kernel, kept for experiments
+ *   "profile"          1 = CUDA events around every launch (xv_last_kernel_ms); "trace_ptr" / "trace_layer": per-tile clock
+ *                      stamps of one layer (tools/trace_tiles.py) */
 int xv_set_option(xv_model* m, const char* name, int64_t value);
 
 /* Host-only helper of the reader that feeds xv_submit_host: index of the binary float matrices of a Kaldi ark held in
