@@ -21,8 +21,9 @@
 // 1 KB per row it must write).  Arithmetic: the values, the K order and the epilogue expressions are those of the two
 // launches it replaces, so the stored rows are BIT-IDENTICAL (tests/test_gpu_parity.py::test_fused_first_layer_*).
 //
-// Used when the spliced width is 128 (5 x 23 -> 115 -> 128), the layer is 256 or 512 wide, plain fp16 operands and the
-// staged span of a block fits (else: the two launches).  Option "fuse_first" = 0 gives the two launches.
+// Used when the spliced width is 128 (5 x 23 -> 115 -> 128) with dilation 1, the layer is 256 or 512 wide, plain fp16 operands,
+// the caller's feature matrix starts on a 16-byte boundary and the staged span of a block fits 4 KB (else: the two launches).
+// Option "fuse_first" = 0 gives the two launches.
 #pragma once
 #include <type_traits>
 
